@@ -1,0 +1,145 @@
+"""Generate the golden vectors that pin ``oracle/mmlrec_oracle.py`` to the reference.
+
+Runs ONLY in the build container (needs ``/root/reference``, which is imported read-only and
+never copied).  For each case it builds the reference model class from a synthetic config of the
+BASELINE shape (widths shrunk so fixtures stay small), then executes the reference's own step
+body -- ``model/basemodel.py:262-313``: ``model(x, None).squeeze()`` -> ``optim.zero_grad()`` ->
+sum of ``F.binary_cross_entropy(.., reduction='sum')`` -> ``+ reg + aux + zeros`` -> ``backward``
+-> ``optim.step()`` -- for a few steps on seeded inputs and stores inputs, initial parameters,
+per-step predictions / losses, first-step gradients and the final parameters/buffers.
+
+    python tests/golden/make_golden.py            # rewrites tests/golden/*.npz
+"""
+import io
+import contextlib
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, "/root/reference")
+sys.dont_write_bytecode = True
+
+from mmlrec_b200 import synthetic  # noqa: E402
+
+STEPS = 3
+BATCH = 48
+
+# case -> (workload name, workload kwargs, model_config overrides, optim overrides)
+SMALL = dict(expert_dnn_hidden_units=[16, 8], gate_dnn_hidden_units=[8], tower_dnn_hidden_units=[8],
+             bottom_dnn_hidden_units=[16, 8], dnn_hidden_units=[16, 8])
+CASES = {
+    "mmoe_census_bn_adam": ("census_mmoe", {}, dict(expert_dnn_hidden_units=[16], gate_dnn_hidden_units=[16],
+                                                    tower_dnn_hidden_units=[16]), {}),
+    "mmoe_census_bn_adagrad": ("census_mmoe", {}, dict(expert_dnn_hidden_units=[16], gate_dnn_hidden_units=[16],
+                                                       tower_dnn_hidden_units=[16]), dict(optimizer="adagrad", lr=1e-2)),
+    "ple_ae_t4_adam": ("ae_ple_t4", dict(max_vocab=300), SMALL, {}),
+    "ple_ae_t2_adam": ("ae_ple_t2", dict(max_vocab=300), SMALL, {}),
+    "sharedbottom_kuairec_adam": ("kuairec_sharedbottom", dict(max_vocab=200), SMALL, {}),
+    "esmm_kuairec_adam": ("kuairec_esmm", dict(max_vocab=200), SMALL, {}),
+    "star_movielens_adam": ("movielens_star", dict(vocab_scale=0.02), dict(dnn_hidden_units=[16, 16]), {}),
+    "pepnet_movielens_adam": ("movielens_pepnet", dict(vocab_scale=0.02), dict(dnn_hidden_units=[16, 16]), {}),
+    "mmoe_synth26_adagrad": ("synth26_mmoe", dict(vocab=97), SMALL, {}),
+    "mmoe_nogate_notower_adam": ("movielens_star", dict(vocab_scale=0.02),
+                                 dict(model_name="mmoe", expert_dnn_hidden_units=[16, 16]), {}),
+}
+
+
+def build_reference(cfg, fields):
+    from model.utils import SparseFeat, DenseFeat
+    from model.mmoe import MMOE
+    from model.ple import PLE
+    from model.sharedbottom import SharedBottom
+    from model.esmm import ESMM
+    from model.star import STAR
+    from model.pepnet import PepNet
+    emb = cfg["model_config"]["emb"]
+    cols = [SparseFeat(n, vocabulary_size=v, embedding_dim=emb) if k == "sparse" else DenseFeat(n, 1)
+            for n, k, v in fields]
+    cls = {"mmoe": MMOE, "ple": PLE, "sharedbottom": SharedBottom, "esmm": ESMM, "star": STAR,
+           "pepnet": PepNet}[cfg["model_config"]["model_name"].lower()]
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = cls(cols, device="cpu", config=cfg)
+        model.compile(optimizer=cfg["optim_config"]["optimizer"], loss=cfg["optim_config"]["loss"],
+                      metrics=cfg["optim_config"]["metrics"])
+    return model
+
+
+def unregistered_star_tensors(model):
+    """SharedSpecificLinear keeps all but the last per-domain weight outside ``named_parameters``
+    (model/utils.py:181-191); export them so the oracle can treat them as constants."""
+    extra = {}
+    if type(model).__name__ != "STAR":
+        return extra
+    for prefix, mods in (("linears", model.linears), ("final_layers", model.final_layers)):
+        for j, lin in enumerate(mods):
+            n = len(lin.specific_weights)
+            for i in range(n - 1):
+                extra[f"{prefix}.{j}.specific_weights.{i}"] = lin.specific_weights[i].detach().clone()
+                extra[f"{prefix}.{j}.specific_biases.{i}"] = lin.specific_biases[i].detach().clone()
+    return extra
+
+
+def reference_step(model, X, y):
+    """model/basemodel.py:262-313 verbatim in effect (domain_mask is always None, :265-266)."""
+    x = X.float()
+    y = y.float()
+    y_pred = model(x, None).squeeze()
+    model.optim.zero_grad()
+    loss = sum(F.binary_cross_entropy(y_pred[:, i], y[:, i], reduction="sum") for i in range(model.num_tasks))
+    total = loss + model.get_regularization_loss() + model.aux_loss + torch.zeros((1,))
+    total.backward()
+    grads = {n: (None if p.grad is None else p.grad.detach().clone()) for n, p in model.named_parameters()}
+    model.optim.step()
+    return y_pred.detach(), loss.detach(), grads
+
+
+def main():
+    for case, (wl, kw, mc_over, oc_over) in CASES.items():
+        cfg, fields = synthetic.workload(wl, **kw)
+        cfg["model_config"].update(mc_over)
+        cfg["optim_config"].update(oc_over)
+        torch.manual_seed(1234)
+        np.random.seed(1234)
+        model = build_reference(cfg, fields)
+        model.train()
+        blob = {}
+        for k, v in model.state_dict().items():
+            blob["init/" + k] = v.detach().numpy().copy()
+        for k, v in unregistered_star_tensors(model).items():
+            blob["init/" + k] = v.numpy().copy()
+        blob["meta/trainable"] = np.array([n for n, _ in model.named_parameters()])
+        blob["meta/buffers"] = np.array([n for n, _ in model.named_buffers()])
+        for s in range(STEPS):
+            X, y = synthetic.make_batch(cfg, fields, BATCH, seed=100 + s)
+            blob[f"step{s}/X"], blob[f"step{s}/y"] = X, y
+            pred, loss, grads = reference_step(model, torch.from_numpy(X), torch.from_numpy(y))
+            blob[f"step{s}/pred"] = pred.numpy()
+            blob[f"step{s}/loss"] = loss.numpy()
+            if s == 0:
+                for n, g in grads.items():
+                    if g is not None:
+                        blob["grad0/" + n] = g.numpy()
+                blob["meta/gradless"] = np.array([n for n, g in grads.items() if g is None])
+        model.eval()
+        with torch.no_grad():
+            Xe, _ = synthetic.make_batch(cfg, fields, BATCH, seed=999)
+            blob["eval/X"] = Xe
+            blob["eval/pred"] = model(torch.from_numpy(Xe).float(), None).numpy()
+        for k, v in model.state_dict().items():
+            blob["final/" + k] = v.detach().numpy().copy()
+        import json
+        blob["meta/config"] = np.array(json.dumps(cfg))
+        blob["meta/fields"] = np.array(json.dumps(fields))
+        path = os.path.join(HERE, case + ".npz")
+        np.savez_compressed(path, **blob)
+        print(f"{case:32s} {os.path.getsize(path) / 1024:8.1f} KiB  loss0={float(blob['step0/loss']):.6f}")
+
+
+if __name__ == "__main__":
+    main()
