@@ -1,0 +1,268 @@
+/*
+ * mmlrec_b200.h -- C ABI of the B200-native MMLRec training hot path (libmmlrec_b200.so).
+ *
+ * The reference (/root/reference) is pure Python: it has no FFI of its own.  Each entry point
+ * below replaces the ATen call sequence behind one reference function; the citation names the
+ * reference lines it stands in for.  All pointers are DEVICE pointers unless the name ends in
+ * _host; `stream` is a cudaStream_t passed as void*; every call is stream-ordered, asynchronous
+ * and performs no allocation and no host synchronisation (so a whole step can be captured in a
+ * CUDA graph).  Return value: 0 on success, otherwise a cudaError_t (>0) or -1 for a rejected
+ * argument; mmlrec_last_error() describes the most recent failure of the calling thread.
+ *
+ * Matrices are row-major.  "ld" is the row stride in ELEMENTS.  fp32 everywhere except where a
+ * parameter is spelled bf16 (raw uint16_t bit patterns).
+ */
+#ifndef MMLREC_B200_H_
+#define MMLREC_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMLREC_ABI_VERSION 1
+#define MMLREC_MAX_GATE_EXPERTS 32
+#define MMLREC_MAX_TASKS 16
+
+/* activation codes (model/utils.py:10-37 activation_layer; pepnet.py:31-32 GateNN's 2*sigmoid) */
+enum { MMLREC_ACT_NONE = 0, MMLREC_ACT_RELU = 1, MMLREC_ACT_SIGMOID = 2, MMLREC_ACT_SIGMOID2 = 3 };
+/* optimizer codes (model/basemodel.py:569-584 _get_optim) */
+enum { MMLREC_OPT_SGD = 0, MMLREC_OPT_ADAGRAD = 1, MMLREC_OPT_ADAM = 2, MMLREC_OPT_RMSPROP = 3 };
+/* head kinds (model/utils.py:242-248 PredictionLayer + basemodel.py:595-604 loss) */
+enum { MMLREC_HEAD_SIGMOID_BCE = 0, MMLREC_HEAD_IDENTITY_MSE = 1 };
+
+int         mmlrec_abi_version(void);
+const char* mmlrec_last_error(void);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+int64_t     mmlrec_launch_count(void);
+/* sizeof of ABI struct `which` (0 Hyper, 1 GemmF32, 2 GemmTcDesc, 3 Gate, 4 ExpertGrad, 5 Head) */
+int64_t     mmlrec_struct_size(int32_t which);
+
+/* ---------------------------------------------------------------------------------------------
+ * Optimizer clock.  torch.optim keeps `step` per parameter and derives Adam's bias corrections
+ * from it on the host (torch/optim/adam.py _single_tensor_adam).  To keep the step graph-
+ * capturable the clock lives on the device: one MmlrecHyper per optimizer, advanced by a kernel.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct MmlrecHyper {
+  int32_t step;        /* number of optimizer steps taken (t) */
+  int32_t optimizer;   /* MMLREC_OPT_* */
+  float   lr, beta1, beta2, eps;     /* eps: 1e-8 Adam, 1e-10 Adagrad, 1e-8 RMSprop */
+  float   step_size;   /* Adam: lr / (1 - beta1^t) */
+  float   bc2_sqrt;    /* Adam: sqrt(1 - beta2^t) */
+  float   alpha;       /* RMSprop smoothing (0.99) */
+  float   one_minus_beta1, one_minus_beta2, one_minus_alpha;  /* rounded from double, like torch's python scalars */
+  double  lr_d, beta1_d, beta2_d;    /* the python-float hyper-parameters; bias corrections are formed in double */
+} MmlrecHyper;
+/* step += 1 and refresh step_size / bc2_sqrt (double precision pow, like the host code it replaces) */
+int mmlrec_hyper_advance(MmlrecHyper* hyper, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1: multi-field gather + concat.
+ * Replaces BaseModel.input_from_feature_columns (model/basemodel.py:461-487: per field
+ * X[:, j:j+1].long() -> nn.Embedding) followed by combined_dnn_input (model/utils.py:434-446).
+ *   X            [B, ldx] fp32; sparse ids are carried as fp32 and truncated toward zero.
+ *   emb          flat storage holding every table; field f's table starts at element
+ *                field_meta[f*4+0] and has field_meta[f*4+1] rows of D floats.
+ *   field_meta   int64 [F_s,4] = {table_offset, vocabulary, x_column, out_column}
+ *   dense_xcol   int32 [F_d]: X column of each dense feature; written to out columns
+ *                dense_out_col .. dense_out_col+F_d-1.
+ *   out_f32      [B, ld_f32] (nullable); out_bf16 [B, ld_bf16] (nullable; columns >= in_dim up to
+ *                ld_bf16 are written as zero so the buffer can feed a K-padded tensor-core GEMM).
+ *   oob_flag     nullable int32: set to 1 if any id fell outside [0, vocabulary) (the id is
+ *                clamped; the reference would raise IndexError).
+ * ------------------------------------------------------------------------------------------- */
+int mmlrec_gather_concat(const float* X, int64_t ldx, int32_t B,
+                         const float* emb, const int64_t* field_meta, int32_t F_s, int32_t D,
+                         const int32_t* dense_xcol, int32_t F_d, int32_t dense_out_col,
+                         float* out_f32, int64_t ld_f32,
+                         uint16_t* out_bf16, int64_t ld_bf16,
+                         int32_t* oob_flag, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2: embedding backward as sort + segmented warp-shuffle reduce with the optimizer's row
+ * update fused in.  Replaces F_s x embedding_dense_backward (autograd of basemodel.py:475-477,
+ * which materialises a dense [V,D] gradient per table) plus the torch.optim update of every
+ * table (basemodel.py:313).
+ *
+ * mmlrec_sort_field_ids: per field, stable sort of the batch's ids.
+ *   sorted_ids/sorted_pos int32 [F_s, B]; keys_ws: uint64 workspace of F_s * n_pad elements,
+ *   n_pad = B rounded up to a power of two (>= 32).
+ * mmlrec_emb_backward_update: for every run of equal ids, sum the gradient slices
+ *   d_input[pos, out_column : out_column+D] in ascending pos order (deterministic, no atomics)
+ *   and apply the optimizer to that row.  state1: Adagrad sum / Adam exp_avg / RMSprop
+ *   square_avg; state2: Adam exp_avg_sq.  row_touch (nullable, int32 per table row over the whole
+ *   flat storage, i.e. index = element_offset / D) is stamped with hyper->step for Adam's
+ *   dense sweep.
+ * mmlrec_emb_adam_dense_sweep: torch's Adam is dense (nn.Embedding(sparse=False)): rows with
+ *   zero gradient still move by their momentum.  This applies that zero-gradient update to every
+ *   row NOT stamped in this step (exact dense-Adam semantics).
+ * ------------------------------------------------------------------------------------------- */
+int mmlrec_sort_field_ids(const float* X, int64_t ldx, int32_t B, const int64_t* field_meta, int32_t F_s,
+                          int32_t* sorted_ids, int32_t* sorted_pos, uint64_t* keys_ws, void* stream);
+int mmlrec_emb_backward_update(const float* d_input, int64_t ld, int32_t B,
+                               const int32_t* sorted_ids, const int32_t* sorted_pos,
+                               const int64_t* field_meta, int32_t F_s, int32_t D,
+                               float* emb, float* state1, float* state2, int32_t* row_touch,
+                               const MmlrecHyper* hyper, float* grad_rows_out, void* stream);
+int mmlrec_emb_adam_dense_sweep(float* emb, float* exp_avg, float* exp_avg_sq, const int32_t* row_touch,
+                                int64_t total_rows, int32_t D, const MmlrecHyper* hyper, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3 (fp32 parity mode): grouped GEMM on the CUDA cores.  One launch runs a list of independent
+ * problems C = act(A * B^T + bias) with arbitrary element strides, which covers forward
+ * (A = activations [M,K], B = nn.Linear weight [N,K]; model/utils.py:146-161 DNN.forward),
+ * dgrad (A = dZ [M,N], B = W^T via strides) and wgrad (A = dZ^T, B = X^T via strides).
+ *   mask/ldmask: out = mask(m,n) > 0 ? out : 0  -- the ReLU backward of the layer that produced
+ *                this GEMM's input (fused threshold_backward).
+ *   rowsum_a:    nullable [M]: sum over k of A(m,k); in a wgrad problem A = dZ^T so this is the
+ *                bias gradient.
+ *   accumulate:  C += result.
+ * The problem table lives in device memory; tile_prefix (int32 [n_problems+1], device) is the
+ * exclusive prefix of 64x64 tile counts.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct MmlrecGemmF32 {
+  const float* A; const float* B; float* C;
+  int64_t a_rs, a_cs;    /* A(m,k) = A[m*a_rs + k*a_cs] */
+  int64_t b_rs, b_cs;    /* B(n,k) = B[n*b_rs + k*b_cs] */
+  int64_t ldc;
+  const float* bias;     /* [N] or NULL */
+  const float* mask; int64_t ldmask;
+  float* rowsum_a;       /* [M] or NULL */
+  int32_t M, N, K;
+  int32_t act;           /* MMLREC_ACT_* */
+  int32_t accumulate;
+  int32_t reserved;
+} MmlrecGemmF32;
+int mmlrec_gemm_grouped_f32(const MmlrecGemmF32* problems, const int32_t* tile_prefix,
+                            int32_t n_problems, int32_t total_tiles, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K3 (bf16 mode): grouped GEMM on the tcgen05 tensor cores, TMA-fed, fp32 accumulation in TMEM.
+ * D[M,N] = epilogue(A * B^T): A and B are bf16, each either K-major (row-major [rows,K]) or
+ * MN-major ([K,rows], i.e. the transpose of a row-major activation -- what wgrad needs), so no
+ * transposed copies are ever materialised.  Tensor maps are encoded on the host at plan time
+ * (mmlrec_tc_encode_problem) into an array of device-resident problem records.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct MmlrecGemmTcDesc {           /* host-side description of one problem */
+  const uint16_t* A; const uint16_t* B;     /* bf16 */
+  int64_t lda, ldb;                         /* row stride (elements) of the row-major arrays */
+  int32_t a_mn_major, b_mn_major;           /* 0: array is [rows,K]; 1: array is [K,rows] */
+  int32_t M, N, K;
+  float* C_f32; int64_t ldc_f32;            /* nullable outputs, any combination */
+  uint16_t* C_bf16; int64_t ldc_bf16;
+  const float* bias;                        /* [N] fp32 or NULL */
+  const uint16_t* mask; int64_t ldmask;     /* bf16 [M,N]: keep where mask > 0 */
+  float* colsum;                            /* nullable [N]: column sums of the fp32 result, atomically accumulated */
+  int32_t act, accumulate;                  /* accumulate applies to C_f32 only */
+} MmlrecGemmTcDesc;
+/* size in bytes of one device problem record; the table is `n * mmlrec_tc_record_bytes()` */
+int64_t mmlrec_tc_record_bytes(void);
+/* encode problem `desc_host` into `record_host` (host staging memory, record_bytes long) */
+int mmlrec_tc_encode_problem(const MmlrecGemmTcDesc* desc_host, void* record_host);
+int mmlrec_gemm_grouped_tc(const void* records, const int32_t* tile_prefix, int32_t n_problems,
+                           int32_t total_tiles, void* stream);
+/* tiles a problem occupies (BLOCK_M=128 x BLOCK_N=128) */
+int32_t mmlrec_tc_num_tiles(int32_t M, int32_t N);
+
+/* ---------------------------------------------------------------------------------------------
+ * BatchNorm1d in training mode + activation (model/utils.py:132-134, :153-154; momentum 0.1,
+ * eps 1e-5, unbiased running variance).  Z is the Linear output [M, ldz]; columns [0,N).
+ * Forward writes Y = act(bn(Z)) and saves mean / invstd for backward.  Backward takes dY (already
+ * masked by the activation derivative) and returns dZ plus dgamma / dbeta.
+ * ------------------------------------------------------------------------------------------- */
+int mmlrec_bn_forward(const float* Z, int64_t ldz, int32_t M, int32_t N,
+                      const float* gamma, const float* beta, float* running_mean, float* running_var,
+                      int64_t* num_batches_tracked, int32_t n_tracked,
+                      float* save_mean, float* save_invstd,
+                      float* Y, int64_t ldy, uint16_t* Y_bf16, int64_t ldy_bf16,
+                      int32_t act, int32_t training, void* stream);
+int mmlrec_bn_backward(const float* dY, int64_t lddy, const float* Z, int64_t ldz, int32_t M, int32_t N,
+                       const float* gamma, const float* save_mean, const float* save_invstd,
+                       float* dZ, int64_t lddz, uint16_t* dZ_bf16, int64_t lddz_bf16,
+                       float* dgamma, float* dbeta, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Gate head + softmax + expert mixture (model/mmoe.py:80-88, model/ple.py:127-152):
+ *   logits = gate_in * Wg^T (bias-free), p = softmax(logits), mix = sum_e p_e * expert_e.
+ * One launch serves every gate of a level; records live in device memory.
+ * Backward kernel A (per gate): dlogits, d(gate_in) (optionally ReLU-masked by gate_in > 0,
+ * optionally accumulated), dWg.  Backward kernel B (per expert): d(expert_e) = sum over the gates
+ * that use it of p * d(mix), optionally ReLU-masked by expert_e > 0.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct MmlrecGate {
+  const float* gate_in; int64_t ld_gate_in; int32_t Hg; int32_t n_e;
+  const float* Wg; int64_t ld_Wg;                    /* [n_e, Hg], row stride ld_Wg (dWg uses the same stride) */
+  const float* expert[MMLREC_MAX_GATE_EXPERTS]; int64_t ld_expert; int32_t H; int32_t pad0;
+  float* probs;                                      /* [B, n_e] saved for backward */
+  float* mix; int64_t ld_mix;                        /* [B, H] */
+  uint16_t* mix_bf16; int64_t ld_mix_bf16;           /* nullable bf16 copy (feeds tensor-core GEMMs) */
+  /* backward */
+  const float* d_mix; int64_t ld_d_mix;              /* NULL: this gate receives no gradient */
+  float* d_gate_in; int64_t ld_d_gate_in; int32_t relu_mask_gate_in; int32_t accumulate_d_gate_in;
+  uint16_t* d_gate_in_bf16; int64_t ld_d_gate_in_bf16; /* nullable bf16 copy */
+  float* dWg;                                        /* [n_e, Hg] */
+} MmlrecGate;
+typedef struct MmlrecExpertGrad {
+  const float* expert; int64_t ld_expert;            /* forward output (for the ReLU mask) */
+  float* d_expert; int64_t ld_d_expert; int32_t H; int32_t n_users;
+  const float* user_probs[MMLREC_MAX_TASKS + 1]; int32_t user_prob_ld[MMLREC_MAX_TASKS + 1];
+  int32_t user_prob_col[MMLREC_MAX_TASKS + 1];
+  const float* user_d_mix[MMLREC_MAX_TASKS + 1]; int64_t user_d_mix_ld[MMLREC_MAX_TASKS + 1];
+  int32_t relu_mask; int32_t pad0;
+  uint16_t* d_expert_bf16; int64_t ld_d_expert_bf16; /* nullable bf16 copy */
+} MmlrecExpertGrad;
+int mmlrec_gate_mix_forward(const MmlrecGate* gates, int32_t n_gates, int32_t B, void* stream);
+int mmlrec_gate_mix_backward(const MmlrecGate* gates, int32_t n_gates,
+                             const MmlrecExpertGrad* experts, int32_t n_experts, int32_t B,
+                             int32_t max_ne, int32_t max_hg,
+                             int32_t serialize_gates /* !=0 when two gates share a gate_in: each CTA then walks the
+                                                        gates in order so d(gate_in) accumulates without a race */,
+                             float* scratch, int32_t* counters /* int32 [n_gates], zero-initialised once */,
+                             void* stream);
+/* scratch floats needed by mmlrec_gate_mix_backward (max_ne / max_hg: maxima over the gate table) */
+int64_t mmlrec_gate_mix_backward_scratch(int32_t n_gates, int32_t max_ne, int32_t max_hg, int32_t B);
+
+/* ---------------------------------------------------------------------------------------------
+ * Heads + loss, forward and backward in one pass (training) or forward only (predict).
+ * Replaces tower_dnn_final_layer (Linear(H,1,bias=False), mmoe.py:52-55), PredictionLayer
+ * (utils.py:242-248), F.binary_cross_entropy(.., reduction='sum') summed over tasks
+ * (basemodel.py:294-296; log terms clamped at -100) and their autograd.
+ *   esmm != 0: two heads share ONE bias and pred = [p0, p0*p1] (esmm.py:57-62).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct MmlrecHead {
+  const float* h; int64_t ld_h; int32_t H; int32_t kind;     /* tower output [B,H]; MMLREC_HEAD_* */
+  const float* w; const float* bias;                          /* [H], [1] */
+  float* d_h; int64_t ld_d_h; int32_t relu_mask; int32_t pad0; /* d(tower output), nullable */
+  float* dw; float* dbias;                                    /* [H], [1] */
+  uint16_t* d_h_bf16; int64_t ld_d_h_bf16;                    /* nullable bf16 copy of d_h */
+} MmlrecHead;
+int mmlrec_heads_forward_backward(const MmlrecHead* heads, int32_t T, int32_t B,
+                                  const float* y, int64_t ldy,
+                                  float* pred, int64_t ld_pred, float* loss /*[T+1]: per task, total*/,
+                                  int32_t esmm, int32_t training,
+                                  float* scratch, int64_t scratch_floats, int32_t* counters, void* stream);
+int64_t mmlrec_heads_scratch(int32_t T, int32_t max_h, int32_t B);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense optimizer over the flat parameter store (torch.optim.{Adam,Adagrad,SGD,RMSprop} with
+ * the reference's defaults, basemodel.py:569-584 / :313), one launch for all dense parameters.
+ * Optionally refreshes the bf16 shadow copy the tensor-core GEMMs read.
+ * ------------------------------------------------------------------------------------------- */
+int mmlrec_dense_optimizer_step(float* param, const float* grad, float* state1, float* state2, int64_t n,
+                                const MmlrecHyper* hyper, uint16_t* bf16_shadow, void* stream);
+
+/* small utilities */
+int mmlrec_fill_f32(float* p, int64_t n, float v, void* stream);
+int mmlrec_cast_f32_to_bf16(const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst,
+                            int32_t rows, int32_t cols, int32_t cols_pad, void* stream);
+int mmlrec_cast_bf16_to_f32(const uint16_t* src, int64_t ld_src, float* dst, int64_t ld_dst,
+                            int32_t rows, int32_t cols, void* stream);
+/* out(m,n) = a(m,n) * b(m,n) (* c) ; used by STAR weight build and PEPNet gating */
+int mmlrec_mul_f32(const float* a, int64_t lda, const float* b, int64_t ldb, float* out, int64_t ldo,
+                   int32_t rows, int32_t cols, int32_t accumulate, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMLREC_B200_H_ */

@@ -1,0 +1,58 @@
+"""Build libmmlrec_b200.so in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+    python -m mmlrec_b200.csrc.build        # or: python <this file>
+"""
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SOURCES = ["capi.cu", "gather.cu", "emb_update.cu", "gemm_simt.cu", "gemm_tc.cu", "fused_ops.cu"]
+LIB = os.path.join(HERE, "libmmlrec_b200.so")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "--use_fast_math=false"]
+
+
+def nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), "/usr/local/cuda/bin/nvcc", "nvcc"):
+        if cand and (os.path.isabs(cand) and os.path.exists(cand) or not os.path.isabs(cand)):
+            return cand
+    raise RuntimeError("nvcc not found")
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = SOURCES + ["common.cuh", os.path.join("..", "..", "include", "mmlrec_b200.h")]
+    return any(os.path.getmtime(os.path.join(HERE, d)) > t for d in deps)
+
+
+def build(force: bool = False, verbose: bool = True) -> str:
+    if not force and not needs_build():
+        return LIB
+    objs = []
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
+    procs = []
+    for src in SOURCES:
+        obj = os.path.join(HERE, src.replace(".cu", ".o"))
+        cmd = [nvcc(), *flags, "-c", os.path.join(HERE, src), "-o", obj]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
+        objs.append(obj)
+    for src, p in procs:
+        out, _ = p.communicate()
+        if p.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {src}:\n{out}")
+        if verbose and out.strip():
+            print(out)
+    cmd = [nvcc(), "-shared", "-o", LIB, *objs, "-gencode", "arch=compute_100a,code=sm_100a"]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.run(cmd, check=True)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv))

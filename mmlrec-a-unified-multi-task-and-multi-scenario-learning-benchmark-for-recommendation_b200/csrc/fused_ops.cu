@@ -1,0 +1,564 @@
+// Fused non-GEMM stages of the step: BatchNorm(+activation), gate softmax + expert mixture,
+// prediction heads + BCE (forward and backward in one pass), the flat dense optimizer and a few
+// element-wise utilities.  All of these are HBM/L2-bound streaming kernels; cross-CTA reductions
+// use per-CTA partials + a "last CTA reduces in fixed order" epilogue (deterministic, no float
+// atomics).
+#include "common.cuh"
+
+namespace mmlrec {
+
+// last-CTA-done ticket: returns true in exactly one CTA (the last to arrive), after which all
+// other CTAs' global writes are visible to it.  The counter is reset for the next launch.
+__device__ __forceinline__ bool last_block_ticket(int32_t* counter, int n_blocks) {
+  __shared__ int s_last;
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int t = atomicAdd(counter, 1);
+    s_last = (t == n_blocks - 1) ? 1 : 0;
+    if (s_last) *counter = 0;
+  }
+  __syncthreads();
+  if (s_last) __threadfence();
+  return s_last != 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// BatchNorm1d (training: batch statistics, two-pass variance; eval: running statistics)
+// grid = ceil(N/32); block = 256 = 8 row-groups x 32 columns
+// ------------------------------------------------------------------------------------------------
+constexpr int kBnThreads = 256;
+
+__device__ __forceinline__ float bn_block_colsum(float v, float (*red)[33]) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  red[w][lane] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += red[i][lane];
+  return s;
+}
+
+__global__ void __launch_bounds__(kBnThreads)
+bn_forward_kernel(const float* Z, int64_t ldz, int M, int N, const float* gamma, const float* beta,
+                  float* running_mean, float* running_var, int64_t* nbt, int n_tracked,
+                  float* save_mean, float* save_invstd, float* Y, int64_t ldy, uint16_t* Yb, int64_t ldyb,
+                  int act, int training) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  const bool cv = col < N;
+  const float momentum = 0.1f, eps = 1e-5f;
+  float mean, invstd;
+  if (training) {
+    float s = 0.f;
+    if (cv) for (int r = w; r < M; r += 8) s += Z[r * ldz + col];
+    s = bn_block_colsum(s, red);
+    mean = s / (float)M;
+    float q = 0.f;
+    if (cv) for (int r = w; r < M; r += 8) { float d = Z[r * ldz + col] - mean; q += d * d; }
+    q = bn_block_colsum(q, red);
+    invstd = 1.f / sqrtf(q / (float)M + eps);
+    if (cv && w == 0) {
+      save_mean[col] = mean;
+      save_invstd[col] = invstd;
+      float unbiased = M > 1 ? q / (float)(M - 1) : q;
+      running_mean[col] = (1.f - momentum) * running_mean[col] + momentum * mean;
+      running_var[col] = (1.f - momentum) * running_var[col] + momentum * unbiased;
+    }
+    if (blockIdx.x == 0 && nbt && threadIdx.x < n_tracked) nbt[threadIdx.x] += 1;
+  } else {
+    mean = cv ? running_mean[col] : 0.f;
+    invstd = cv ? 1.f / sqrtf(running_var[col] + eps) : 0.f;
+  }
+  if (!cv) return;
+  const float g = gamma[col], b = beta[col];
+  for (int r = w; r < M; r += 8) {
+    float y = apply_act((Z[r * ldz + col] - mean) * invstd * g + b, act);
+    if (Y) Y[r * ldy + col] = y;
+    if (Yb) Yb[r * ldyb + col] = float_to_bf16_bits(y);
+  }
+}
+
+__global__ void __launch_bounds__(kBnThreads)
+bn_backward_kernel(const float* dY, int64_t lddy, const float* Z, int64_t ldz, int M, int N, const float* gamma,
+                   const float* save_mean, const float* save_invstd, float* dZ, int64_t lddz,
+                   uint16_t* dZb, int64_t lddzb, float* dgamma, float* dbeta) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  const bool cv = col < N;
+  const float mean = cv ? save_mean[col] : 0.f, invstd = cv ? save_invstd[col] : 0.f;
+  float s1 = 0.f, s2 = 0.f;
+  if (cv) for (int r = w; r < M; r += 8) {
+    float dy = dY[r * lddy + col];
+    s1 += dy;
+    s2 += dy * (Z[r * ldz + col] - mean) * invstd;
+  }
+  s1 = bn_block_colsum(s1, red);
+  s2 = bn_block_colsum(s2, red);
+  if (!cv) return;
+  if (w == 0) { dgamma[col] = s2; dbeta[col] = s1; }
+  const float g = gamma[col], inv_m = 1.f / (float)M;
+  for (int r = w; r < M; r += 8) {
+    float xh = (Z[r * ldz + col] - mean) * invstd;
+    float dz = g * invstd * (dY[r * lddy + col] - s1 * inv_m - xh * s2 * inv_m);
+    if (dZ) dZ[r * lddz + col] = dz;
+    if (dZb) dZb[r * lddzb + col] = float_to_bf16_bits(dz);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// gate head + softmax + mixture, forward.  grid = (ceil(B/8), n_gates), one warp per sample.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gate_mix_forward_kernel(const MmlrecGate* gates, int B) {
+  __shared__ MmlrecGate G;
+  if (threadIdx.x == 0) G = gates[blockIdx.y];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int b = blockIdx.x * 8 + w;
+  if (b >= B) return;
+  const float* gin = G.gate_in + (int64_t)b * G.ld_gate_in;
+  float logit = -INFINITY;  // lane e holds logit e
+  for (int e = 0; e < G.n_e; ++e) {
+    const float* wr = G.Wg + (int64_t)e * G.ld_Wg;
+    float s = 0.f;
+    for (int h = lane; h < G.Hg; h += 32) s = fmaf(gin[h], __ldg(wr + h), s);
+    s = warp_sum(s);
+    if (lane == e) logit = s;
+  }
+  float mx = logit;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float ex = lane < G.n_e ? expf(logit - mx) : 0.f;
+  float den = warp_sum(ex);
+  float p = ex / den;
+  if (lane < G.n_e) G.probs[(int64_t)b * G.n_e + lane] = p;
+  for (int h = lane; h < G.H; h += 32) {
+    float acc = 0.f;
+    for (int e = 0; e < G.n_e; ++e) {
+      float pe = __shfl_sync(0xffffffffu, p, e);
+      acc = fmaf(pe, G.expert[e][(int64_t)b * G.ld_expert + h], acc);
+    }
+    G.mix[(int64_t)b * G.ld_mix + h] = acc;
+    if (G.mix_bf16) G.mix_bf16[(int64_t)b * G.ld_mix_bf16 + h] = float_to_bf16_bits(acc);
+  }
+}
+
+// backward A: per gate.  grid = (ceil(B/64), n_gates); 8 warps x 8 samples; smem holds the gate
+// inputs and dlogits of the 64 samples for the deterministic dWg partial.
+constexpr int kGateRows = 64;
+__global__ void __launch_bounds__(256)
+gate_mix_backward_gate_kernel(const MmlrecGate* gates, int n_gates, int B, float* scratch, int64_t per_gate_scratch,
+                              int32_t* counters) {
+  extern __shared__ __align__(16) float smem_f[];
+  __shared__ MmlrecGate G;
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int r0 = blockIdx.x * kGateRows;
+  const int rows = min(kGateRows, B - r0);
+  for (int gi = blockIdx.y; gi < n_gates; gi += gridDim.y) {
+    __syncthreads();
+    if (threadIdx.x == 0) G = gates[gi];
+    __syncthreads();
+    if (G.d_mix == nullptr) continue;
+    float* gin_s = smem_f;                         // [64][Hg]
+    float* dl_s = smem_f + kGateRows * G.Hg;       // [64][n_e]
+    for (int i = threadIdx.x; i < kGateRows * G.Hg; i += 256) {
+      int r = i / G.Hg, h = i - r * G.Hg;
+      gin_s[i] = r < rows ? G.gate_in[(int64_t)(r0 + r) * G.ld_gate_in + h] : 0.f;
+    }
+    __syncthreads();
+    for (int rr = 0; rr < 8; ++rr) {
+      const int r = w * 8 + rr;
+      const int b = r0 + r;
+      float dl = 0.f;
+      if (r < rows) {
+        const float* dm = G.d_mix + (int64_t)b * G.ld_d_mix;
+        float dp = 0.f;
+        for (int e = 0; e < G.n_e; ++e) {
+          const float* eo = G.expert[e] + (int64_t)b * G.ld_expert;
+          float s = 0.f;
+          for (int h = lane; h < G.H; h += 32) s = fmaf(dm[h], eo[h], s);
+          s = warp_sum(s);
+          if (lane == e) dp = s;
+        }
+        float p = lane < G.n_e ? G.probs[(int64_t)b * G.n_e + lane] : 0.f;
+        float dot = warp_sum(p * dp);
+        dl = p * (dp - dot);
+        // d(gate_in)
+        for (int h = lane; h < G.Hg; h += 32) {
+          float acc = 0.f;
+          for (int e = 0; e < G.n_e; ++e)
+            acc = fmaf(__shfl_sync(0xffffffffu, dl, e), __ldg(G.Wg + (int64_t)e * G.ld_Wg + h), acc);
+          if (G.relu_mask_gate_in && !(gin_s[r * G.Hg + h] > 0.f)) acc = 0.f;
+          if (G.d_gate_in) {
+            float* dst = G.d_gate_in + (int64_t)b * G.ld_d_gate_in + h;
+            if (G.accumulate_d_gate_in) acc += *dst;
+            *dst = acc;
+          }
+          if (G.d_gate_in_bf16) G.d_gate_in_bf16[(int64_t)b * G.ld_d_gate_in_bf16 + h] = float_to_bf16_bits(acc);
+        }
+      }
+      if (lane < G.n_e) dl_s[r * G.n_e + lane] = dl;
+    }
+    __syncthreads();
+    // per-CTA partial of dWg[e][h] = sum_r dl[r][e] * gin[r][h]
+    float* part = scratch + (int64_t)gi * per_gate_scratch + (int64_t)blockIdx.x * G.n_e * G.Hg;
+    for (int i = threadIdx.x; i < G.n_e * G.Hg; i += 256) {
+      int e = i / G.Hg, h = i - e * G.Hg;
+      float acc = 0.f;
+      for (int r = 0; r < kGateRows; ++r) acc = fmaf(dl_s[r * G.n_e + e], gin_s[r * G.Hg + h], acc);
+      part[i] = acc;
+    }
+    if (last_block_ticket(counters + gi, gridDim.x)) {
+      const float* base = scratch + (int64_t)gi * per_gate_scratch;
+      for (int i = threadIdx.x; i < G.n_e * G.Hg; i += 256) {
+        float acc = 0.f;
+        for (int c = 0; c < (int)gridDim.x; ++c) acc += base[(int64_t)c * G.n_e * G.Hg + i];
+        G.dWg[(int64_t)(i / G.Hg) * G.ld_Wg + (i % G.Hg)] = acc;
+      }
+    }
+  }
+}
+
+// backward B: per expert.  grid = (ceil(B/8), n_experts), one warp per sample.
+__global__ void __launch_bounds__(256) gate_mix_backward_expert_kernel(const MmlrecExpertGrad* experts, int B) {
+  __shared__ MmlrecExpertGrad E;
+  if (threadIdx.x == 0) E = experts[blockIdx.y];
+  __syncthreads();
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int b = blockIdx.x * 8 + w;
+  if (b >= B) return;
+  float pu = 0.f;  // lane u holds the probability user u assigns to this expert
+  if (lane < E.n_users) pu = E.user_probs[lane][(int64_t)b * E.user_prob_ld[lane] + E.user_prob_col[lane]];
+  for (int h = lane; h < E.H; h += 32) {
+    float acc = 0.f;
+    for (int u = 0; u < E.n_users; ++u)
+      acc = fmaf(__shfl_sync(0xffffffffu, pu, u), E.user_d_mix[u][(int64_t)b * E.user_d_mix_ld[u] + h], acc);
+    if (E.relu_mask && !(E.expert[(int64_t)b * E.ld_expert + h] > 0.f)) acc = 0.f;
+    if (E.d_expert) E.d_expert[(int64_t)b * E.ld_d_expert + h] = acc;
+    if (E.d_expert_bf16) E.d_expert_bf16[(int64_t)b * E.ld_d_expert_bf16 + h] = float_to_bf16_bits(acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// heads + loss (forward + backward).  grid = ceil(B/64); 8 warps x 8 samples.
+// ------------------------------------------------------------------------------------------------
+constexpr int kHeadRows = 64;
+constexpr int kHeadMaxK = 8;  // H <= 256
+
+__global__ void __launch_bounds__(256)
+heads_kernel(const MmlrecHead* heads, int T, int B, const float* y, int64_t ldy, float* pred, int64_t ld_pred,
+             float* loss, int esmm, int training, float* scratch, int stride_cta, int32_t* counter) {
+  __shared__ MmlrecHead Hd[MMLREC_MAX_TASKS];
+  __shared__ float z_s[kHeadRows][MMLREC_MAX_TASKS];
+  __shared__ float dz_s[kHeadRows][MMLREC_MAX_TASKS];
+  __shared__ float l_s[kHeadRows][MMLREC_MAX_TASKS];
+  __shared__ float x_s[kHeadRows];
+  __shared__ float wred[8][32 * kHeadMaxK];
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid < T) Hd[tid] = heads[tid];
+  __syncthreads();
+  const int r0 = blockIdx.x * kHeadRows;
+  // phase 1: logits
+  for (int rr = 0; rr < 8; ++rr) {
+    const int r = w * 8 + rr, b = r0 + r;
+    for (int t = 0; t < T; ++t) {
+      float s = 0.f;
+      if (b < B) {
+        const float* hrow = Hd[t].h + (int64_t)b * Hd[t].ld_h;
+        for (int h = lane; h < Hd[t].H; h += 32) s = fmaf(hrow[h], __ldg(Hd[t].w + h), s);
+      }
+      s = warp_sum(s);
+      if (lane == 0) z_s[r][t] = s + (Hd[t].bias ? *Hd[t].bias : 0.f);
+    }
+  }
+  __syncthreads();
+  // phase 2: probabilities, loss terms, dz  (thread <-> (row, task))
+  for (int i = tid; i < kHeadRows * T; i += 256) {
+    const int r = i / T, t = i - r * T, b = r0 + r;
+    float dz = 0.f, l = 0.f, cross = 0.f;
+    if (b < B) {
+      const float z = z_s[r][t];
+      if (Hd[t].kind == MMLREC_HEAD_SIGMOID_BCE) {
+        const float p = 1.f / (1.f + expf(-z));
+        float out = p, scale = 1.f;  // scale = d(out)/dp
+        if (esmm && t == 1) {        // esmm.py:59  ctcvr = ctr * cvr
+          const float p0 = 1.f / (1.f + expf(-z_s[r][0]));
+          out = p0 * p;
+          scale = p0;
+        }
+        pred[(int64_t)b * ld_pred + t] = out;
+        if (y) {
+          const float yy = y[(int64_t)b * ldy + t];
+          // F.binary_cross_entropy: (y-1)*max(log1p(-x),-100) - y*max(log(x),-100)
+          l = (yy - 1.f) * fmaxf(log1pf(-out), -100.f) - yy * fmaxf(logf(out), -100.f);
+          // binary_cross_entropy_backward: (x-y)/max((1-x)*x, 1e-12); sigmoid_backward: g*(1-p)*p
+          const float gout = (out - yy) / fmaxf((1.f - out) * out, 1e-12f);
+          dz = gout * scale * (1.f - p) * p;
+          if (esmm && t == 1) cross = gout * p;  // d loss_1 / d p0
+        }
+      } else {  // identity + MSE (F.mse_loss, reduction='sum')
+        pred[(int64_t)b * ld_pred + t] = z;
+        if (y) {
+          const float d = z - y[(int64_t)b * ldy + t];
+          l = d * d;
+          dz = 2.f * d;
+        }
+      }
+    }
+    dz_s[r][t] = dz;
+    l_s[r][t] = l;
+    if (esmm && t == 1) x_s[r] = cross;
+  }
+  __syncthreads();
+  if (esmm && y) {  // head 0 also receives gradient through out1 = p0*p1
+    for (int r = tid; r < kHeadRows; r += 256) {
+      if (r0 + r < B) {
+        const float p0 = 1.f / (1.f + expf(-z_s[r][0]));
+        dz_s[r][0] += x_s[r] * (1.f - p0) * p0;
+      }
+    }
+    __syncthreads();
+  }
+  if (!training || y == nullptr) return;
+  // loss + dbias partials per task: warp t sums column t over the 64 rows (fixed order)
+  float* cta_out = scratch + (int64_t)blockIdx.x * stride_cta;  // [T][2 + Hmax]
+  const int hmax = (stride_cta / T) - 2;
+  for (int t = w; t < T; t += 8) {
+    float l = 0.f, d = 0.f;
+    for (int r = lane; r < kHeadRows; r += 32) { l += l_s[r][t]; d += dz_s[r][t]; }
+    l = warp_sum(l); d = warp_sum(d);
+    if (lane == 0) { cta_out[t * (2 + hmax)] = l; cta_out[t * (2 + hmax) + 1] = d; }
+  }
+  // phase 3: d_h and dw partials
+  for (int t = 0; t < T; ++t) {
+    const MmlrecHead& hd = Hd[t];
+    float acc[kHeadMaxK];
+#pragma unroll
+    for (int k = 0; k < kHeadMaxK; ++k) acc[k] = 0.f;
+    for (int rr = 0; rr < 8; ++rr) {
+      const int r = w * 8 + rr, b = r0 + r;
+      if (b >= B) continue;
+      const float dz = dz_s[r][t];
+      const float* hrow = hd.h + (int64_t)b * hd.ld_h;
+#pragma unroll
+      for (int k = 0; k < kHeadMaxK; ++k) {
+        int h = lane + 32 * k;
+        if (h < hd.H) {
+          float hv = hrow[h];
+          acc[k] = fmaf(dz, hv, acc[k]);
+          float g = dz * __ldg(hd.w + h);
+          if (hd.relu_mask && !(hv > 0.f)) g = 0.f;
+          if (hd.d_h) hd.d_h[(int64_t)b * hd.ld_d_h + h] = g;
+          if (hd.d_h_bf16) hd.d_h_bf16[(int64_t)b * hd.ld_d_h_bf16 + h] = float_to_bf16_bits(g);
+        }
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < kHeadMaxK; ++k) wred[w][lane + 32 * k] = acc[k];
+    __syncthreads();
+    for (int h = tid; h < hd.H; h += 256) {
+      float s = 0.f;
+#pragma unroll
+      for (int ww = 0; ww < 8; ++ww) s += wred[ww][h];
+      cta_out[t * (2 + hmax) + 2 + h] = s;
+    }
+  }
+  if (last_block_ticket(counter, gridDim.x)) {
+    const int per_t = 2 + hmax;
+    float total = 0.f;
+    for (int t = 0; t < T; ++t) {
+      for (int i = tid; i < 2 + Hd[t].H; i += 256) {
+        float s = 0.f;
+        for (int c = 0; c < (int)gridDim.x; ++c) s += scratch[(int64_t)c * stride_cta + t * per_t + i];
+        if (i == 0) loss[t] = s;
+        else if (i == 1) { if (!(esmm && t == 1)) { if (Hd[t].dbias) *Hd[t].dbias = s; } else x_s[0] = s; }
+        else Hd[t].dw[i - 2] = s;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int t = 0; t < T; ++t) total += loss[t];
+      loss[T] = total;
+      if (esmm && Hd[0].dbias) *Hd[0].dbias += x_s[0];  // one shared bias gets both heads' gradient
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// flat dense optimizer + element-wise utilities
+// ------------------------------------------------------------------------------------------------
+__global__ void dense_optimizer_kernel(float* p, const float* g, float* s1, float* s2, int64_t n,
+                                       const MmlrecHyper* hyper, uint16_t* shadow) {
+  const MmlrecHyper hp = *hyper;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float pv = p[i], a = s1 ? s1[i] : 0.f, b = s2 ? s2[i] : 0.f;
+    optimizer_update(pv, g[i], a, b, hp);
+    p[i] = pv;
+    if (s1) s1[i] = a;
+    if (s2) s2[i] = b;
+    if (shadow) shadow[i] = float_to_bf16_bits(pv);
+  }
+}
+
+__global__ void fill_kernel(float* p, int64_t n, float v) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
+}
+
+__global__ void cast_f32_bf16_kernel(const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst, int rows, int cols,
+                                     int cols_pad) {
+  const int64_t n = (int64_t)rows * cols_pad;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int r = (int)(i / cols_pad), c = (int)(i - (int64_t)r * cols_pad);
+    dst[r * ld_dst + c] = c < cols ? float_to_bf16_bits(src[r * ld_src + c]) : (uint16_t)0;
+  }
+}
+
+__global__ void cast_bf16_f32_kernel(const uint16_t* src, int64_t ld_src, float* dst, int64_t ld_dst, int rows, int cols) {
+  const int64_t n = (int64_t)rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+    dst[r * ld_dst + c] = bf16_bits_to_float(src[r * ld_src + c]);
+  }
+}
+
+__global__ void mul_kernel(const float* a, int64_t lda, const float* b, int64_t ldb, float* out, int64_t ldo, int rows,
+                           int cols, int accumulate) {
+  const int64_t n = (int64_t)rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+    float v = a[r * lda + c] * b[r * ldb + c];
+    if (accumulate) v += out[r * ldo + c];
+    out[r * ldo + c] = v;
+  }
+}
+
+static inline int grid_for(int64_t n) {
+  int64_t g = (n + 255) / 256;
+  return (int)(g < 148 * 8 ? (g < 1 ? 1 : g) : 148 * 8);
+}
+
+}  // namespace mmlrec
+
+using namespace mmlrec;
+
+extern "C" int mmlrec_bn_forward(const float* Z, int64_t ldz, int32_t M, int32_t N, const float* gamma,
+                                 const float* beta, float* running_mean, float* running_var,
+                                 int64_t* num_batches_tracked, int32_t n_tracked, float* save_mean,
+                                 float* save_invstd, float* Y, int64_t ldy, uint16_t* Y_bf16, int64_t ldy_bf16,
+                                 int32_t act, int32_t training, void* stream) {
+  MMLREC_CHECK_ARG(M > 0 && N > 0, "bad sizes");
+  MMLREC_CHECK_ARG(n_tracked <= 256, "too many tracked counters");
+  MMLREC_CHECK_ARG(Y || Y_bf16, "no output");
+  bn_forward_kernel<<<cdiv(N, 32), kBnThreads, 0, (cudaStream_t)stream>>>(
+      Z, ldz, M, N, gamma, beta, running_mean, running_var, num_batches_tracked, n_tracked, save_mean, save_invstd, Y,
+      ldy, Y_bf16, ldy_bf16, act, training);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_bn_backward(const float* dY, int64_t lddy, const float* Z, int64_t ldz, int32_t M, int32_t N,
+                                  const float* gamma, const float* save_mean, const float* save_invstd, float* dZ,
+                                  int64_t lddz, uint16_t* dZ_bf16, int64_t lddz_bf16, float* dgamma, float* dbeta,
+                                  void* stream) {
+  MMLREC_CHECK_ARG(M > 0 && N > 0, "bad sizes");
+  bn_backward_kernel<<<cdiv(N, 32), kBnThreads, 0, (cudaStream_t)stream>>>(
+      dY, lddy, Z, ldz, M, N, gamma, save_mean, save_invstd, dZ, lddz, dZ_bf16, lddz_bf16, dgamma, dbeta);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_gate_mix_forward(const MmlrecGate* gates, int32_t n_gates, int32_t B, void* stream) {
+  MMLREC_CHECK_ARG(n_gates > 0 && B > 0, "bad sizes");
+  dim3 grid(cdiv(B, 8), n_gates);
+  gate_mix_forward_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(gates, B);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int64_t mmlrec_gate_mix_backward_scratch(int32_t n_gates, int32_t max_ne, int32_t max_hg, int32_t B) {
+  return (int64_t)n_gates * cdiv(B, kGateRows) * max_ne * max_hg;
+}
+
+extern "C" int mmlrec_gate_mix_backward(const MmlrecGate* gates, int32_t n_gates, const MmlrecExpertGrad* experts,
+                                        int32_t n_experts, int32_t B, int32_t max_ne, int32_t max_hg,
+                                        int32_t serialize_gates, float* scratch, int32_t* counters, void* stream) {
+  MMLREC_CHECK_ARG(n_gates > 0 && B > 0 && max_ne > 0 && max_ne <= MMLREC_MAX_GATE_EXPERTS && max_hg > 0, "bad sizes");
+  const int n_cta = cdiv(B, kGateRows);
+  const int64_t per_gate = (int64_t)n_cta * max_ne * max_hg;
+  size_t smem = (size_t)kGateRows * (size_t)(max_hg + max_ne) * sizeof(float);
+  MMLREC_CHECK_ARG(smem <= 200 * 1024, "gate input too wide for the shared-memory tile");
+  static size_t opted = 0;
+  if (smem > 48 * 1024 && smem > opted) {
+    cudaError_t e = cudaFuncSetAttribute(gate_mix_backward_gate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("gate_mix_backward: smem opt-in failed"); return (int)e; }
+    opted = smem;
+  }
+  dim3 grid(n_cta, serialize_gates ? 1 : n_gates);
+  gate_mix_backward_gate_kernel<<<grid, 256, smem, (cudaStream_t)stream>>>(gates, n_gates, B, scratch, per_gate, counters);
+  MMLREC_CHECK_LAUNCH(1);
+  if (n_experts > 0) {
+    dim3 g2(cdiv(B, 8), n_experts);
+    gate_mix_backward_expert_kernel<<<g2, 256, 0, (cudaStream_t)stream>>>(experts, B);
+    MMLREC_CHECK_LAUNCH(1);
+  }
+  return 0;
+}
+
+extern "C" int64_t mmlrec_heads_scratch(int32_t T, int32_t max_h, int32_t B) {
+  return (int64_t)cdiv(B, kHeadRows) * T * (2 + max_h);
+}
+
+extern "C" int mmlrec_heads_forward_backward(const MmlrecHead* heads, int32_t T, int32_t B, const float* y, int64_t ldy,
+                                             float* pred, int64_t ld_pred, float* loss, int32_t esmm, int32_t training,
+                                             float* scratch, int64_t scratch_floats, int32_t* counters, void* stream) {
+  MMLREC_CHECK_ARG(T > 0 && T < MMLREC_MAX_TASKS && B > 0, "bad sizes");
+  MMLREC_CHECK_ARG(!esmm || T == 2, "esmm needs exactly two heads");
+  const int n_cta = cdiv(B, kHeadRows);
+  int stride_cta = 0;
+  if (training) {
+    MMLREC_CHECK_ARG(scratch && counters && scratch_floats > 0 && scratch_floats % n_cta == 0, "bad scratch");
+    stride_cta = (int)(scratch_floats / n_cta);
+    MMLREC_CHECK_ARG(stride_cta % T == 0 && stride_cta / T - 2 <= 32 * kHeadMaxK, "head width > 256 unsupported");
+  }
+  heads_kernel<<<n_cta, 256, 0, (cudaStream_t)stream>>>(heads, T, B, y, ldy, pred, ld_pred, loss, esmm, training, scratch,
+                                                        stride_cta, counters);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_dense_optimizer_step(float* param, const float* grad, float* state1, float* state2, int64_t n,
+                                           const MmlrecHyper* hyper, uint16_t* bf16_shadow, void* stream) {
+  MMLREC_CHECK_ARG(n >= 0 && hyper, "bad args");
+  if (n == 0) return 0;
+  dense_optimizer_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(param, grad, state1, state2, n, hyper, bf16_shadow);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_fill_f32(float* p, int64_t n, float v, void* stream) {
+  if (n <= 0) return 0;
+  fill_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(p, n, v);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_cast_f32_to_bf16(const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst, int32_t rows,
+                                       int32_t cols, int32_t cols_pad, void* stream) {
+  MMLREC_CHECK_ARG(rows >= 0 && cols >= 0 && cols_pad >= cols, "bad sizes");
+  if (rows == 0 || cols_pad == 0) return 0;
+  cast_f32_bf16_kernel<<<grid_for((int64_t)rows * cols_pad), 256, 0, (cudaStream_t)stream>>>(src, ld_src, dst, ld_dst, rows,
+                                                                                           cols, cols_pad);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_cast_bf16_to_f32(const uint16_t* src, int64_t ld_src, float* dst, int64_t ld_dst, int32_t rows,
+                                       int32_t cols, void* stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  cast_bf16_f32_kernel<<<grid_for((int64_t)rows * cols), 256, 0, (cudaStream_t)stream>>>(src, ld_src, dst, ld_dst, rows, cols);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_mul_f32(const float* a, int64_t lda, const float* b, int64_t ldb, float* out, int64_t ldo,
+                              int32_t rows, int32_t cols, int32_t accumulate, void* stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  mul_kernel<<<grid_for((int64_t)rows * cols), 256, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, out, ldo, rows, cols, accumulate);
+  MMLREC_RETURN_LAUNCH(1);
+}

@@ -1,0 +1,386 @@
+"""Training runtime with the reference's ``BaseModel`` surface (``/root/reference/model/basemodel.py``):
+constructor signature (:69-71), ``compile`` (:557-567), ``fit`` (:135-371), ``evaluate`` (:373-393),
+``predict`` (:395-457), ``input_from_feature_columns`` / ``compute_input_dim`` (:461-507).
+
+What differs underneath: the step body (``basemodel.py:262-313``) is not a chain of ATen calls but a
+static program of hand-written sm_100a kernels (``engine/core.py``) replayed as one CUDA graph;
+parameters live in flat device buffers (``engine/store.py``); the embedding tables are updated by
+the fused sort + segmented-reduce kernel instead of dense [V,D] gradients; per-batch metrics are
+computed after the epoch from predictions kept on the device instead of forcing a host sync every
+step.  There is no CPU execution path: any compute call without CUDA + the library raises.
+"""
+from __future__ import annotations
+
+import copy
+import time
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import lib as L
+from ..engine.core import Builder, StepPlan
+from ..engine.store import FlatStore
+from .utils import (DenseFeat, PredictionLayer, SparseFeat, VarLenSparseFeat, build_input_features,
+                    create_embedding_matrix, get_mask)
+
+
+class BaseModel(nn.Module):
+    def __init__(self, linear_feature_columns, dnn_feature_columns, init_std=0.0001, device="cpu", gpus=None,
+                 config=None):
+        super().__init__()
+        if config is None:
+            raise ValueError("config is required")
+        self.dnn_feature_columns = dnn_feature_columns
+        self.config = config
+        self.data_config = config["data_config"]
+        self.model_config = config["model_config"]
+        self.optim_config = config["optim_config"]
+        self.training_config = config["training_config"]
+        self.b200_config = config.get("b200_config", {})
+        self.save_layer_output = False
+        self.use_cka_loss = self.model_config.get("use_cka_loss", False)
+        if self.use_cka_loss:
+            raise NotImplementedError("use_cka_loss: utils.CKA does not exist in the reference either (SURVEY Q14)")
+        self.device = device
+        self.device_obj = torch.device(device)
+        self.gpus = gpus
+        if gpus and str(gpus[0]) not in str(device):
+            raise ValueError("`gpus[0]` should be the same gpu with `device`")
+
+        self.task_name = self.model_config.get("task_name", "mtl")
+        self.task_names = self.model_config.get("task_names", ["ctr", "ctcvr"])
+        self.task_types = self.model_config.get("task_types", ["binary", "binary"])
+        self.num_domains = self.data_config.get("num_domains", 1)
+        if self.task_name == "msl":
+            self.num_tasks = self.num_domains
+        elif self.task_name == "mtmsl":
+            self.num_tasks = len(self.data_config["label_columns"])
+        else:
+            self.num_tasks = len(self.task_names)
+        if self.num_tasks <= 1:
+            raise ValueError("num_tasks must be greater than 1!")
+        if len(dnn_feature_columns) == 0:
+            raise ValueError("dnn_feature_columns is null!")
+        if len(self.task_types) != self.num_tasks:
+            raise ValueError("num_tasks must be equal to the length of task_types")
+        for task_type in self.task_types:
+            if task_type not in ["binary", "regression"]:
+                raise ValueError("task must be binary or regression, {} is illegal".format(task_type))
+        for key in ("l2_reg_linear", "l2_reg_embedding", "l2_reg_dnn"):
+            # the reference defaults l2_reg_linear/embedding to 1e-5 when the key is absent; every
+            # shipped config sets all three to 0 and the fused step implements only that case
+            if self.model_config.get(key, 0) not in (0, 0.0):
+                raise NotImplementedError(f"{key} > 0 is not implemented in the fused step")
+
+        self.feature_index = build_input_features(list(linear_feature_columns) + list(dnn_feature_columns))
+        self.embedding_dict = create_embedding_matrix(dnn_feature_columns, init_std, sparse=False, device="cpu")
+        self.out = PredictionLayer(self.model_config.get("task", "binary"))
+        self.init_std = init_std
+        self.store: Optional[FlatStore] = None
+        self._plans: Dict[int, StepPlan] = {}
+        self._steps_on_plan: Dict[int, int] = {}
+        self.use_cuda_graph = bool(self.b200_config.get("cuda_graph", True))
+        self.precision = self.b200_config.get("precision", "fp32")
+        self.optimizer_name: Optional[str] = None
+        self.hyper_dev: Optional[torch.Tensor] = None
+        self.metrics, self.metrics_names = {}, ["loss"]
+
+    # ------------------------------------------------------------------ feature bookkeeping
+    def compute_input_dim(self, feature_columns, include_sparse=True, include_dense=True, feature_group=False):
+        sparse = [fc for fc in feature_columns if isinstance(fc, (SparseFeat, VarLenSparseFeat))]
+        dense = [fc for fc in feature_columns if isinstance(fc, DenseFeat)]
+        total = 0
+        if include_sparse:
+            total += len(sparse) if feature_group else sum(fc.embedding_dim for fc in sparse)
+        if include_dense:
+            total += sum(fc.dimension for fc in dense)
+        return total
+
+    @property
+    def embedding_size(self):
+        dims = {fc.embedding_dim for fc in self.dnn_feature_columns if isinstance(fc, (SparseFeat, VarLenSparseFeat))}
+        if len(dims) > 1:
+            raise ValueError("embedding_dim of SparseFeat and VarlenSparseFeat must be same in this model!")
+        return list(dims)[0]
+
+    def _index_features(self):
+        """Column bookkeeping for K1: (table param, vocab, X column, output column) per sparse field
+        in list order, then the X columns of the dense features (model/utils.py:434-446 layout)."""
+        sparse = [fc for fc in self.dnn_feature_columns if isinstance(fc, SparseFeat)]
+        dense = [fc for fc in self.dnn_feature_columns if isinstance(fc, DenseFeat)]
+        if any(isinstance(fc, VarLenSparseFeat) for fc in self.dnn_feature_columns):
+            raise NotImplementedError("VarLenSparseFeat is outside the B200 hot path")
+        dims = {fc.embedding_dim for fc in sparse}
+        if len(dims) > 1:
+            raise NotImplementedError("the gather kernel needs one embedding_dim for all sparse fields")
+        self.emb_dim = dims.pop() if dims else 4
+        if self.emb_dim % 4 != 0:
+            raise NotImplementedError("embedding_dim must be a multiple of 4 (128-bit row chunks)")
+        self.embedding_layout = []
+        for j, fc in enumerate(sparse):
+            self.embedding_layout.append((self.embedding_dict[fc.embedding_name].weight, fc.vocabulary_size,
+                                          self.feature_index[fc.name][0], j * self.emb_dim))
+        self.dense_x_cols = []
+        for fc in dense:
+            a, e = self.feature_index[fc.name]
+            self.dense_x_cols.extend(range(a, e))
+        self.input_dim_total = len(sparse) * self.emb_dim + len(self.dense_x_cols)
+        self.num_x_cols = max(e for _, e in self.feature_index.values())
+
+    # ------------------------------------------------------------------ program construction
+    def build_graph(self, b: Builder) -> None:  # pragma: no cover - abstract
+        raise NotImplementedError
+
+    def _finalize(self) -> None:
+        """End of construction (the reference's ``self.to(device)``): lay the parameters out in the
+        order the step program consumes them and move everything into the flat device store."""
+        self._index_features()
+        if self.device_obj.type != "cuda":
+            return  # parameters stay ordinary CPU tensors; any compute call raises (no CPU path)
+        dry = Builder(2, self.device_obj, None, dry=True)
+        self.build_graph(dry)
+        emb_params = [t[0] for t in self.embedding_layout]
+        self.store = FlatStore(self, dry.param_order, emb_params, self.device_obj, want_bf16=self.precision == "bf16")
+        self._index_features()  # re-read the re-pointed table parameters
+
+    def _require_cuda(self):
+        if self.store is None:
+            raise RuntimeError("mmlrec_b200 models compute only on a CUDA device through libmmlrec_b200.so; "
+                               f"this model was built for device={self.device!r} (there is no CPU fallback)")
+        L.load()
+
+    def plan(self, B: int) -> StepPlan:
+        self._require_cuda()
+        p = self._plans.get(B)
+        if p is None:
+            with torch.cuda.device(self.device_obj):
+                p = StepPlan(self, B)
+            self._plans[B] = p
+            self._steps_on_plan[B] = 0
+        return p
+
+    # ------------------------------------------------------------------ compile
+    def compile(self, optimizer, loss=None, metrics=None):
+        self.metrics_names = ["loss"]
+        if not isinstance(optimizer, str):
+            raise NotImplementedError("pass the optimizer by name: the update is fused into the CUDA step")
+        if optimizer not in ("sgd", "adam", "adagrad", "rmsprop"):
+            raise NotImplementedError
+        if self.model_config["model_name"] == "pcg":
+            raise NotImplementedError("PCGrad (model_name='pcg') is outside the fused hot path")
+        losses = [loss] * self.num_tasks if isinstance(loss, str) else list(loss or [])
+        for t, (lname, ttype) in enumerate(zip(losses, self.task_types)):
+            ok = (lname == "binary_crossentropy" and ttype == "binary") or (lname == "mse" and ttype == "regression")
+            if not ok:
+                raise NotImplementedError(f"loss {lname!r} with task type {ttype!r} is not fused")
+        self.loss_names = losses
+        self.optimizer_name = optimizer
+        self.metrics = self._get_metrics(metrics)
+        if self.store is not None:
+            lr = self.optim_config.get("lr", 1e-3)
+            self.store.ensure_optimizer_state(optimizer)
+            self.store.reset_optimizer_state()
+            h = L.make_hyper(optimizer, lr)
+            self.hyper_dev = torch.frombuffer(bytearray(bytes(h)), dtype=torch.uint8).to(self.device_obj)
+            self._plans.clear()
+        self.optim = self  # callers only ever pass it back to fit()
+
+    def _get_metrics(self, metrics):
+        from sklearn.metrics import accuracy_score, log_loss, mean_squared_error, roc_auc_score
+        table = {}
+        for m in metrics or []:
+            if m in ("binary_crossentropy", "logloss"):
+                table[m] = log_loss
+            if m == "auc":
+                table[m] = roc_auc_score
+            if m == "mse":
+                table[m] = mean_squared_error
+            if m in ("accuracy", "acc"):
+                table[m] = lambda y_true, y_pred: accuracy_score(y_true, np.where(y_pred > 0.5, 1, 0))
+            self.metrics_names.append(m)
+        return table
+
+    # ------------------------------------------------------------------ one step
+    def train_on_batch(self, X, y) -> torch.Tensor:
+        """One optimizer step on a batch (host or device tensors / arrays).  Returns the device
+        tensor ``[T+1]`` of per-task BCE sums and their total (no host synchronisation)."""
+        if self.hyper_dev is None:
+            raise RuntimeError("call compile() before training")
+        X = torch.as_tensor(X)
+        y = torch.as_tensor(y)
+        p = self.plan(X.shape[0])
+        p.X.copy_(X, non_blocking=True)
+        p.y.copy_(y.reshape(X.shape[0], -1), non_blocking=True)
+        self._run_train(p)
+        return p.loss
+
+    def _run_train(self, p: StepPlan) -> None:
+        n = self._steps_on_plan[p.B]
+        if not self.use_cuda_graph:
+            p.train_step()
+        elif p.graph is not None:
+            p.replay()
+        elif n == 0:
+            p.train_step()          # eager warm-up (also the step that surfaces launch errors)
+        else:
+            p.capture()
+            p.replay()
+        self._steps_on_plan[p.B] = n + 1
+
+    def forward(self, X, domain_mask=None):
+        """Probabilities ``[B, T]`` (sigmoid applied for 'binary' heads).  Inference-only: the result
+        carries no autograd graph (training goes through ``fit`` / ``train_on_batch``)."""
+        X = torch.as_tensor(X)
+        p = self.plan(X.shape[0])
+        p.X.copy_(X, non_blocking=True)
+        p.forward(training=self.training)
+        out = p.pred.clone()
+        if domain_mask is not None:
+            dm = torch.as_tensor(domain_mask).to(out)
+            if self.task_name == "msl":
+                out = out * dm
+            elif self.task_name == "mtmsl":
+                out = out * dm[:, [i % self.num_domains for i in range(self.num_tasks)]]
+        return out
+
+    # ------------------------------------------------------------------ data plumbing
+    def _stack_inputs(self, x) -> np.ndarray:
+        if isinstance(x, dict):
+            x = [x[name] for name in self.feature_index]
+        cols = []
+        for a in x:
+            a = np.asarray(a.values if hasattr(a, "values") else a)
+            cols.append(a.reshape(len(a), -1))
+        return np.concatenate(cols, axis=-1).astype(np.float32)
+
+    # ------------------------------------------------------------------ fit / evaluate / predict
+    def fit(self, x=None, y=None, batch_size=None, epochs=1, initial_epoch=0, validation_split=0.,
+            validation_data=None, shuffle=True):
+        self._require_cuda()
+        from torch.utils.data import DataLoader, TensorDataset
+        X = self._stack_inputs(x)
+        y = np.asarray(y, dtype=np.float32).reshape(len(X), self.num_tasks)
+        val = None
+        if validation_data:
+            if len(validation_data) not in (2, 3):
+                raise ValueError("validation_data must be (x_val, y_val) or (x_val, y_val, sample_weights)")
+            val = (self._stack_inputs(validation_data[0]),
+                   np.asarray(validation_data[1], dtype=np.float32).reshape(-1, self.num_tasks))
+        elif validation_split and 0. < validation_split < 1.:
+            cut = int(len(X) * (1. - validation_split))
+            X, y, val = X[:cut], y[:cut], (X[cut:], y[cut:])
+        batch_size = 256 if batch_size is None else batch_size
+        dev = self.device_obj
+        Xd, yd = torch.from_numpy(X).to(dev), torch.from_numpy(y).to(dev)
+        n = len(X)
+        steps = (n - 1) // batch_size + 1
+        # the reference's DataLoader(shuffle=True) consumes the global torch RNG; iterating a DataLoader
+        # over the row indices reproduces its batch order exactly
+        loader = DataLoader(TensorDataset(torch.arange(n)), shuffle=shuffle, batch_size=batch_size)
+        print("Train on {0} samples, validate on {1} samples, {2} steps per epoch".format(
+            n, 0 if val is None else len(val[1]), steps))
+        self.train()
+        best_auc, stall, best_model = 0, 0, None
+        for epoch in range(initial_epoch, epochs):
+            t0 = time.time()
+            preds, idxs, losses = [], [], []
+            for (idx,) in loader:
+                idx_d = idx.to(dev, non_blocking=True)
+                p = self.plan(len(idx))
+                torch.index_select(Xd, 0, idx_d, out=p.X)
+                torch.index_select(yd, 0, idx_d, out=p.y)
+                self._run_train(p)
+                preds.append(p.pred.clone())
+                losses.append(p.loss[self.num_tasks].clone())
+                idxs.append(idx)
+            total = float(torch.stack(losses).sum().item())
+            logs = {"loss": total / n, "cka_loss": 0.0}
+            if self.metrics:
+                sums = {k: 0.0 for k in self.metrics}
+                for idx, pr in zip(idxs, preds):
+                    yt, yp = y[idx.numpy()], pr.cpu().numpy().astype("float64")
+                    for name, fn in self.metrics.items():
+                        try:
+                            sums[name] += self._train_metric(fn, yt, yp)
+                        except ValueError:
+                            pass  # a batch with a single class has no AUC
+                for k, v in sums.items():
+                    logs[k] = v / steps
+            if val is not None:
+                res = self.evaluate(val[0], val[1], batch_size)
+                print(res)
+                if res.get("auc", 0) > best_auc:
+                    best_auc, best_model, stall = res["auc"], copy.deepcopy(self), 0
+                else:
+                    stall += 1
+                for k, v in res.items():
+                    logs["val_" + k] = v
+                self.train()
+            print("Epoch {0}/{1}".format(epoch + 1, epochs))
+            line = "{0}s - loss: {1: .4f} - cka_loss: {2: .4f}".format(int(time.time() - t0), logs["loss"], 0.0)
+            for name in self.metrics:
+                line += " - {0}: {1: .4f}".format(name, logs.get(name, float("nan")))
+                if val is not None:
+                    line += " - val_{0}: {1: .4f}".format(name, logs.get("val_" + name, float("nan")))
+            print(line)
+            if stall >= self.optim_config.get("early_stop", 3):
+                break
+        return best_model if best_model is not None else self
+
+    def _train_metric(self, fn, y_true, y_pred):
+        if self.task_name == "msl":
+            return fn(y_true[:, 0], y_pred.sum(axis=-1))
+        if self.task_name == "mtmsl":
+            d = self.num_domains
+            return fn(y_true[:, [0, d]], np.stack([y_pred[:, :d].sum(-1), y_pred[:, d:].sum(-1)], axis=-1))
+        return fn(y_true, y_pred)
+
+    def evaluate(self, x, y, batch_size=256, domain_mask=None):
+        pred = self.predict(x, batch_size, domain_mask)
+        y = np.asarray(y)
+        return {name: self._train_metric(fn, y, pred) for name, fn in self.metrics.items()}
+
+    def predict(self, x, batch_size=256, domain_mask=None):
+        self._require_cuda()
+        was_training = self.training
+        self.eval()
+        arr = x.astype(np.float32) if isinstance(x, np.ndarray) and x.ndim == 2 else self._stack_inputs(x)
+        X = torch.from_numpy(np.ascontiguousarray(arr)).to(self.device_obj)
+        out = []
+        for a in range(0, len(X), batch_size):
+            xb = X[a:a + batch_size]
+            p = self.plan(len(xb))
+            p.X.copy_(xb)
+            p.forward(training=False)
+            out.append(p.pred.clone())
+        self.train(was_training)
+        return torch.cat(out).cpu().numpy().astype("float64")
+
+    def update_save(self, value=True):
+        self.save_layer_output = value
+
+    # ------------------------------------------------------------------ copies / checkpoints
+    def __deepcopy__(self, memo):
+        """``fit`` keeps the best epoch as ``deepcopy(model)`` (basemodel.py:344).  Parameters are
+        views of flat buffers, so the copy is rebuilt through the constructor and the flat buffers
+        are cloned wholesale."""
+        clone = type(self)(self.dnn_feature_columns, init_std=self.init_std, device=self.device, gpus=self.gpus,
+                           config=copy.deepcopy(self.config))
+        if self.store is not None:
+            for name in ("dense", "emb", "stats", "counts"):
+                getattr(clone.store, name).copy_(getattr(self.store, name))
+            clone.store.refresh_bf16()
+        else:
+            clone.load_state_dict(self.state_dict())
+        if self.optimizer_name is not None:
+            clone.compile(self.optimizer_name, self.loss_names, [m for m in self.metrics_names if m != "loss"])
+        clone.train(self.training)
+        return clone
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        out = super().load_state_dict(state_dict, strict=strict, assign=False)
+        if self.store is not None:
+            self.store.refresh_bf16()
+        return out
