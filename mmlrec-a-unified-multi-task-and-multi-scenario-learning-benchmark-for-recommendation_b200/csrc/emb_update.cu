@@ -170,6 +170,7 @@ __device__ void seg_pass(const SegArgs& a, int d0, int f, int64_t table_off, int
     for (int q = 0; q < W; ++q) v[q] += carry_s[w][q];
   }
   // run leaves the chunk: the whole CTA scans the remainder forward (block-uniform branch)
+  int n_beyond = 0;  // elements of the chunk's last run that lie beyond the chunk
   if (chunk_open_owned) {
     const int tail_id2 = chunk_tail_id;
     float acc[W];
@@ -186,7 +187,9 @@ __device__ void seg_pass(const SegArgs& a, int d0, int f, int64_t table_off, int
 #pragma unroll
         for (int q = 0; q < W; ++q) acc[q] += t[q];
       }
-      all_match = __syncthreads_and(m ? 1 : 0);
+      const int n_match = __syncthreads_count(m ? 1 : 0);
+      n_beyond += n_match;
+      all_match = n_match == kSegThreads;
       base += kSegThreads;
     }
 #pragma unroll
@@ -210,9 +213,10 @@ __device__ void seg_pass(const SegArgs& a, int d0, int f, int64_t table_off, int
   const bool apply = valid && owned && (true_tail || (chunk_open_owned && tid == last_tid));
   if (apply) {
     const int64_t off = table_off + (int64_t)my_id * a.D + d0;
-    if (a.grad_rows_out) {
+    if (a.grad_rows_out) {  // reported at the run's last sorted position
+      const int p_tail = true_tail ? p : p + n_beyond;
 #pragma unroll
-      for (int q = 0; q < W; ++q) a.grad_rows_out[((int64_t)f * a.B + p) * a.D + d0 + q] = v[q];
+      for (int q = 0; q < W; ++q) a.grad_rows_out[((int64_t)f * a.B + p_tail) * a.D + d0 + q] = v[q];
     }
     if (a.emb) {
       float pr[W], s1[W], s2[W];

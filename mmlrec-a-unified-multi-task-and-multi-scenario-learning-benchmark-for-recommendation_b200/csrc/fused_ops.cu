@@ -135,14 +135,19 @@ __global__ void __launch_bounds__(256) gate_mix_forward_kernel(const MmlrecGate*
   float den = warp_sum(ex);
   float p = ex / den;
   if (lane < G.n_e) G.probs[(int64_t)b * G.n_e + lane] = p;
-  for (int h = lane; h < G.H; h += 32) {
+  // uniform trip count: every lane reaches the shuffles, only loads / stores are guarded
+  for (int h0 = 0; h0 < G.H; h0 += 32) {
+    const int h = h0 + lane;
+    const bool hv = h < G.H;
     float acc = 0.f;
     for (int e = 0; e < G.n_e; ++e) {
       float pe = __shfl_sync(0xffffffffu, p, e);
-      acc = fmaf(pe, G.expert[e][(int64_t)b * G.ld_expert + h], acc);
+      if (hv) acc = fmaf(pe, G.expert[e][(int64_t)b * G.ld_expert + h], acc);
     }
-    G.mix[(int64_t)b * G.ld_mix + h] = acc;
-    if (G.mix_bf16) G.mix_bf16[(int64_t)b * G.ld_mix_bf16 + h] = float_to_bf16_bits(acc);
+    if (hv) {
+      G.mix[(int64_t)b * G.ld_mix + h] = acc;
+      if (G.mix_bf16) G.mix_bf16[(int64_t)b * G.ld_mix_bf16 + h] = float_to_bf16_bits(acc);
+    }
   }
 }
 
@@ -187,17 +192,23 @@ gate_mix_backward_gate_kernel(const MmlrecGate* gates, int n_gates, int B, float
         float dot = warp_sum(p * dp);
         dl = p * (dp - dot);
         // d(gate_in)
-        for (int h = lane; h < G.Hg; h += 32) {
+        for (int h0 = 0; h0 < G.Hg; h0 += 32) {  // uniform trip count (shuffles inside)
+          const int h = h0 + lane;
+          const bool hv = h < G.Hg;
           float acc = 0.f;
-          for (int e = 0; e < G.n_e; ++e)
-            acc = fmaf(__shfl_sync(0xffffffffu, dl, e), __ldg(G.Wg + (int64_t)e * G.ld_Wg + h), acc);
-          if (G.relu_mask_gate_in && !(gin_s[r * G.Hg + h] > 0.f)) acc = 0.f;
-          if (G.d_gate_in) {
-            float* dst = G.d_gate_in + (int64_t)b * G.ld_d_gate_in + h;
-            if (G.accumulate_d_gate_in) acc += *dst;
-            *dst = acc;
+          for (int e = 0; e < G.n_e; ++e) {
+            const float de = __shfl_sync(0xffffffffu, dl, e);
+            if (hv) acc = fmaf(de, __ldg(G.Wg + (int64_t)e * G.ld_Wg + h), acc);
           }
-          if (G.d_gate_in_bf16) G.d_gate_in_bf16[(int64_t)b * G.ld_d_gate_in_bf16 + h] = float_to_bf16_bits(acc);
+          if (hv) {
+            if (G.relu_mask_gate_in && !(gin_s[r * G.Hg + h] > 0.f)) acc = 0.f;
+            if (G.d_gate_in) {
+              float* dst = G.d_gate_in + (int64_t)b * G.ld_d_gate_in + h;
+              if (G.accumulate_d_gate_in) acc += *dst;
+              *dst = acc;
+            }
+            if (G.d_gate_in_bf16) G.d_gate_in_bf16[(int64_t)b * G.ld_d_gate_in_bf16 + h] = float_to_bf16_bits(acc);
+          }
         }
       }
       if (lane < G.n_e) dl_s[r * G.n_e + lane] = dl;
@@ -232,13 +243,19 @@ __global__ void __launch_bounds__(256) gate_mix_backward_expert_kernel(const Mml
   if (b >= B) return;
   float pu = 0.f;  // lane u holds the probability user u assigns to this expert
   if (lane < E.n_users) pu = E.user_probs[lane][(int64_t)b * E.user_prob_ld[lane] + E.user_prob_col[lane]];
-  for (int h = lane; h < E.H; h += 32) {
+  for (int h0 = 0; h0 < E.H; h0 += 32) {  // uniform trip count (shuffles inside)
+    const int h = h0 + lane;
+    const bool hv = h < E.H;
     float acc = 0.f;
-    for (int u = 0; u < E.n_users; ++u)
-      acc = fmaf(__shfl_sync(0xffffffffu, pu, u), E.user_d_mix[u][(int64_t)b * E.user_d_mix_ld[u] + h], acc);
-    if (E.relu_mask && !(E.expert[(int64_t)b * E.ld_expert + h] > 0.f)) acc = 0.f;
-    if (E.d_expert) E.d_expert[(int64_t)b * E.ld_d_expert + h] = acc;
-    if (E.d_expert_bf16) E.d_expert_bf16[(int64_t)b * E.ld_d_expert_bf16 + h] = float_to_bf16_bits(acc);
+    for (int u = 0; u < E.n_users; ++u) {
+      const float pw = __shfl_sync(0xffffffffu, pu, u);
+      if (hv) acc = fmaf(pw, E.user_d_mix[u][(int64_t)b * E.user_d_mix_ld[u] + h], acc);
+    }
+    if (hv) {
+      if (E.relu_mask && !(E.expert[(int64_t)b * E.ld_expert + h] > 0.f)) acc = 0.f;
+      if (E.d_expert) E.d_expert[(int64_t)b * E.ld_d_expert + h] = acc;
+      if (E.d_expert_bf16) E.d_expert_bf16[(int64_t)b * E.ld_d_expert_bf16 + h] = float_to_bf16_bits(acc);
+    }
   }
 }
 

@@ -76,6 +76,7 @@ class Builder:
         self.B, self.device, self.store, self.dry = B, device, store, dry
         self.stages: List["Stage"] = []
         self.param_order: List[nn.Parameter] = []
+        self.buffer_order: List[torch.Tensor] = []
         self.keep: List[object] = []       # tensors whose addresses are baked into tables
         self.lib = None if dry else L.load()
 
@@ -115,6 +116,9 @@ class Builder:
 
     def note_params(self, params: Sequence[Optional[nn.Parameter]]) -> None:
         self.param_order.extend(p for p in params if p is not None)
+
+    def note_buffers(self, bufs: Sequence[Optional[torch.Tensor]]) -> None:
+        self.buffer_order.extend(t for t in bufs if t is not None)
 
     def add(self, stage: "Stage") -> "Stage":
         self.stages.append(stage)
@@ -236,6 +240,9 @@ class LinearStage(Stage):
         if self.use_bn:
             b.note_params([s.bn.weight for s in specs])
             b.note_params([s.bn.bias for s in specs])
+            b.note_buffers([s.bn.running_mean for s in specs])
+            b.note_buffers([s.bn.running_var for s in specs])
+            b.note_buffers([s.bn.num_batches_tracked for s in specs])
         relu = act == "relu"
         self.outs = b.new_act_buffer([s.N for s in specs], relu=relu, name=f"{label}.y")
         self.zs = b.new_act_buffer([s.N for s in specs], relu=False, name=f"{label}.z") if self.use_bn else None

@@ -28,7 +28,7 @@ def _align(n: int, a: int) -> int:
 
 class FlatStore:
     def __init__(self, model: nn.Module, ordered: Iterable[nn.Parameter], emb_params: List[nn.Parameter],
-                 device: torch.device, want_bf16: bool):
+                 device: torch.device, want_bf16: bool, ordered_buffers: Iterable[torch.Tensor] = ()):
         self.device = device
         emb_ids = {id(p) for p in emb_params}
         seen, order = set(), []
@@ -73,11 +73,13 @@ class FlatStore:
         self.emb_dim = emb_params[0].shape[1] if emb_params else 4
         self.emb_offset: Dict[int, int] = {}
         # ---- buffers (BatchNorm statistics)
-        fbufs = [(m, n, b) for m in model.modules() for n, b in m._buffers.items()
-                 if b is not None and b.dtype == torch.float32]
-        ibufs = [(m, n, b) for m in model.modules() for n, b in m._buffers.items()
-                 if b is not None and b.dtype == torch.int64]
-        self.stats = torch.zeros(max(sum(_align(b.numel(), 4) for _, _, b in fbufs), 4), dtype=torch.float32, device=device)
+        # statistics of layers fused into one stage are adjacent: [means...][vars...]
+        rank = {id(t): i for i, t in enumerate(ordered_buffers)}
+        allb = [(m, n, b) for m in model.modules() for n, b in m._buffers.items() if b is not None]
+        allb.sort(key=lambda e: rank.get(id(e[2]), len(rank)))
+        fbufs = [e for e in allb if e[2].dtype == torch.float32]
+        ibufs = [e for e in allb if e[2].dtype == torch.int64]
+        self.stats = torch.zeros(max(sum(b.numel() for _, _, b in fbufs), 4), dtype=torch.float32, device=device)
         self.counts = torch.zeros(max(sum(b.numel() for _, _, b in ibufs), 1), dtype=torch.int64, device=device)
 
         # ---- re-point the module tree
@@ -122,7 +124,7 @@ class FlatStore:
                 view.copy_(b.to(device))
                 view._mm_off = at
                 m._buffers[n] = view
-                at += _align(b.numel(), 4)
+                at += b.numel()
             at = 0
             for m, n, b in ibufs:
                 view = self.counts[at:at + b.numel()].view(b.shape)

@@ -26,6 +26,16 @@ from .utils import (DenseFeat, PredictionLayer, SparseFeat, VarLenSparseFeat, bu
                     create_embedding_matrix, get_mask)
 
 
+class _FusedOptimizerHandle:
+    """What ``model.optim`` holds: the update itself is fused into the CUDA step, so this only names it."""
+
+    def __init__(self, name: str, lr: float):
+        self.name, self.lr = name, lr
+
+    def __repr__(self):
+        return f"FusedOptimizer({self.name}, lr={self.lr})"
+
+
 class BaseModel(nn.Module):
     def __init__(self, linear_feature_columns, dnn_feature_columns, init_std=0.0001, device="cpu", gpus=None,
                  config=None):
@@ -142,7 +152,8 @@ class BaseModel(nn.Module):
         dry = Builder(2, self.device_obj, None, dry=True)
         self.build_graph(dry)
         emb_params = [t[0] for t in self.embedding_layout]
-        self.store = FlatStore(self, dry.param_order, emb_params, self.device_obj, want_bf16=self.precision == "bf16")
+        self.store = FlatStore(self, dry.param_order, emb_params, self.device_obj, want_bf16=self.precision == "bf16",
+                               ordered_buffers=dry.buffer_order)
         self._index_features()  # re-read the re-pointed table parameters
 
     def _require_cuda(self):
@@ -185,7 +196,7 @@ class BaseModel(nn.Module):
             h = L.make_hyper(optimizer, lr)
             self.hyper_dev = torch.frombuffer(bytearray(bytes(h)), dtype=torch.uint8).to(self.device_obj)
             self._plans.clear()
-        self.optim = self  # callers only ever pass it back to fit()
+        self.optim = _FusedOptimizerHandle(optimizer, self.optim_config.get("lr", 1e-3))
 
     def _get_metrics(self, metrics):
         from sklearn.metrics import accuracy_score, log_loss, mean_squared_error, roc_auc_score

@@ -33,11 +33,18 @@ BATCH = 48
 # case -> (workload name, workload kwargs, model_config overrides, optim overrides)
 SMALL = dict(expert_dnn_hidden_units=[16, 8], gate_dnn_hidden_units=[8], tower_dnn_hidden_units=[8],
              bottom_dnn_hidden_units=[16, 8], dnn_hidden_units=[16, 8])
+# BatchNorm cases are built with init_std=0.05 (the constructor argument every reference model takes):
+# at the default 1e-4 the Linear output is "bias + 1e-5-scale signal", `z - mean` keeps 3-4 digits and
+# any 1-ulp difference in GEMM summation order moves gradients by ~1e-2 (true for torch-CPU vs
+# torch-CUDA as well), so such a case can only pin predictions / losses; see *_default_init below.
+INIT_STD = {"mmoe_census_bn_adam": 0.05, "mmoe_census_bn_adagrad": 0.05}
 CASES = {
     "mmoe_census_bn_adam": ("census_mmoe", {}, dict(expert_dnn_hidden_units=[16], gate_dnn_hidden_units=[16],
                                                     tower_dnn_hidden_units=[16]), {}),
     "mmoe_census_bn_adagrad": ("census_mmoe", {}, dict(expert_dnn_hidden_units=[16], gate_dnn_hidden_units=[16],
                                                        tower_dnn_hidden_units=[16]), dict(optimizer="adagrad", lr=1e-2)),
+    "mmoe_census_bn_default_init_adam": ("census_mmoe", {}, dict(expert_dnn_hidden_units=[16], gate_dnn_hidden_units=[16],
+                                                                 tower_dnn_hidden_units=[16]), {}),
     "ple_ae_t4_adam": ("ae_ple_t4", dict(max_vocab=300), SMALL, {}),
     "ple_ae_t2_adam": ("ae_ple_t2", dict(max_vocab=300), SMALL, {}),
     "sharedbottom_kuairec_adam": ("kuairec_sharedbottom", dict(max_vocab=200), SMALL, {}),
@@ -50,7 +57,7 @@ CASES = {
 }
 
 
-def build_reference(cfg, fields):
+def build_reference(cfg, fields, init_std=0.0001):
     from model.utils import SparseFeat, DenseFeat
     from model.mmoe import MMOE
     from model.ple import PLE
@@ -64,7 +71,7 @@ def build_reference(cfg, fields):
     cls = {"mmoe": MMOE, "ple": PLE, "sharedbottom": SharedBottom, "esmm": ESMM, "star": STAR,
            "pepnet": PepNet}[cfg["model_config"]["model_name"].lower()]
     with contextlib.redirect_stdout(io.StringIO()):
-        model = cls(cols, device="cpu", config=cfg)
+        model = cls(cols, init_std=init_std, device="cpu", config=cfg)
         model.compile(optimizer=cfg["optim_config"]["optimizer"], loss=cfg["optim_config"]["loss"],
                       metrics=cfg["optim_config"]["metrics"])
     return model
@@ -106,7 +113,7 @@ def main():
         cfg["optim_config"].update(oc_over)
         torch.manual_seed(1234)
         np.random.seed(1234)
-        model = build_reference(cfg, fields)
+        model = build_reference(cfg, fields, INIT_STD.get(case, 0.0001))
         model.train()
         blob = {}
         for k, v in model.state_dict().items():
@@ -134,6 +141,7 @@ def main():
         for k, v in model.state_dict().items():
             blob["final/" + k] = v.detach().numpy().copy()
         import json
+        blob["meta/init_std"] = np.array(INIT_STD.get(case, 0.0001))
         blob["meta/config"] = np.array(json.dumps(cfg))
         blob["meta/fields"] = np.array(json.dumps(fields))
         path = os.path.join(HERE, case + ".npz")

@@ -283,4 +283,4 @@ def test_dense_optimizer_matches_torch(opt):
         ro.step()
         ops.hyper_advance(hy)
         ops.dense_optimizer_step(p, grad.to(dev), s1 if opt != "sgd" else None, s2 if opt == "adam" else None, hy)
-    assert rel_err(p, ref.detach()) < 1e-6
+    assert rel_err(p.cpu(), ref.detach()) < 1e-6

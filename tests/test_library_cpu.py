@@ -57,7 +57,8 @@ def _build_cpu(case):
     emb = cfg["model_config"]["emb"]
     cols = [SparseFeat(n, v, emb) if k == "sparse" else DenseFeat(n, 1) for n, k, v in fields]
     torch.manual_seed(1234)
-    return get_model_class(cfg["model_config"]["model_name"])(cols, device="cpu", config=cfg), z, cfg
+    return get_model_class(cfg["model_config"]["model_name"])(cols, init_std=float(z["meta/init_std"]), device="cpu",
+                                                              config=cfg), z, cfg
 
 
 def _implemented_cases():

