@@ -6,7 +6,14 @@ buffers).  Building the program allocates every workspace buffer and uploads eve
 problem table; running it is a fixed sequence of C-ABI launches with no allocation, no host
 synchronisation and no Python-side tensor math, so the whole step is captured in one CUDA graph.
 
-Gradient convention: ``Act.gbuf`` holds dL/d(pre-activation) of the stage that PRODUCED the
+Two arithmetic modes share the program:
+  * ``fp32``  every GEMM on the CUDA cores (gemm_simt.cu) -- the parity mode (1e-5 vs the reference);
+  * ``bf16``  every GEMM on the tcgen05 tensor cores (gemm_tc.cu): bf16 operands, fp32 accumulation
+              in TMEM, fp32 master weights + bf16 shadow; activations that feed a GEMM are kept in
+              bf16, activations that feed the gate / head / BatchNorm kernels in fp32 (a buffer gets
+              exactly the copies its consumers asked for).
+
+Gradient convention: a gradient buffer holds dL/d(pre-activation) of the stage that PRODUCED the
 activation -- every kernel that writes an input gradient applies the producer's ReLU mask itself
 (``Act.relu``), which fuses ``threshold_backward`` into the GEMM / gate / head epilogues.  The first
 writer of a gradient assigns, later writers accumulate (``Act.grad_written``).
@@ -14,7 +21,7 @@ writer of a gradient assigns, later writers accumulate (``Act.grad_written``).
 from __future__ import annotations
 
 import ctypes as C
-from typing import Callable, Dict, List, Optional, Sequence, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 import torch.nn as nn
@@ -23,36 +30,72 @@ from .. import lib as L
 from .store import FlatStore, _align
 
 
-class Act:
-    """[B, width] activation = columns [col, col+width) of ``buf`` (fp32 [B, ld]); ``gbuf`` is its
-    gradient twin with the same geometry."""
+class ActGroup:
+    """One wide buffer family [B, sum(widths)]: forward values and gradients, each optionally in
+    fp32 and/or bf16 (decided by the consumers before ``materialize``)."""
 
-    def __init__(self, buf: Optional[torch.Tensor], gbuf: Optional[torch.Tensor], col: int, width: int,
-                 relu: bool = False, needs_grad: bool = True, name: str = ""):
-        self.buf, self.gbuf, self.col, self.width = buf, gbuf, col, width
-        self.relu, self.needs_grad, self.name = relu, needs_grad, name
+    def __init__(self, widths: Sequence[int], relu: bool, name: str, grad_dtype: str):
+        self.widths, self.relu, self.name, self.grad_dtype = list(widths), relu, name, grad_dtype
+        self.need_f32 = self.need_bf16 = False
+        self.need_grad = True
+        self.buf = self.buf16 = self.gbuf = self.gbuf16 = None
+        self.acts: List["Act"] = []
+        at = 0
+        for i, w in enumerate(widths):
+            self.acts.append(Act(self, at, w, f"{name}[{i}]"))
+            at += w
+        self.total = at
+
+    def materialize(self, b: "Builder") -> None:
+        if not (self.need_f32 or self.need_bf16):  # produced but never consumed: keep one copy
+            self.need_f32, self.need_bf16 = (not b.tc), b.tc
+        if self.need_f32:
+            self.buf = b.zeros(b.B, _align(self.total, 4))
+        if self.need_bf16:
+            self.buf16 = b.zeros(b.B, _align(self.total, 8), dtype=torch.bfloat16)
+        if self.need_grad:
+            if self.grad_dtype == "f32":
+                self.gbuf = b.zeros(b.B, _align(self.total, 4))
+            else:
+                self.gbuf16 = b.zeros(b.B, _align(self.total, 8), dtype=torch.bfloat16)
+
+
+class Act:
+    """[B, width] activation = columns [col, col+width) of its group's buffers."""
+
+    def __init__(self, group: ActGroup, col: int, width: int, name: str):
+        self.group, self.col, self.width, self.name = group, col, width, name
         self.grad_written = False
 
-    @property
-    def ld(self) -> int:
-        return self.buf.stride(0)
-
-    @property
-    def ptr(self) -> int:
-        return self.buf.data_ptr() + 4 * self.col
-
-    @property
-    def gptr(self) -> int:
-        return self.gbuf.data_ptr() + 4 * self.col
+    relu = property(lambda self: self.group.relu)
+    # fp32 view
+    ld = property(lambda self: self.group.buf.stride(0))
+    ptr = property(lambda self: self.group.buf.data_ptr() + 4 * self.col)
+    has_f32 = property(lambda self: self.group.buf is not None)
+    # bf16 view
+    ld16 = property(lambda self: self.group.buf16.stride(0))
+    ptr16 = property(lambda self: self.group.buf16.data_ptr() + 2 * self.col)
+    has_bf16 = property(lambda self: self.group.buf16 is not None)
+    # gradients
+    grad_is_f32 = property(lambda self: self.group.grad_dtype == "f32")
+    gld = property(lambda self: (self.group.gbuf if self.grad_is_f32 else self.group.gbuf16).stride(0))
+    gptr = property(lambda self: (self.group.gbuf.data_ptr() + 4 * self.col) if self.grad_is_f32
+                    else (self.group.gbuf16.data_ptr() + 2 * self.col))
 
     def same_as(self, o: "Act") -> bool:
-        return self.buf is o.buf and self.col == o.col and self.width == o.width
+        return self.group is o.group and self.col == o.col and self.width == o.width
 
     def tensor(self) -> torch.Tensor:
-        return self.buf[:, self.col:self.col + self.width]
+        return self.group.buf[:, self.col:self.col + self.width]
 
     def grad_tensor(self) -> torch.Tensor:
-        return self.gbuf[:, self.col:self.col + self.width]
+        g = self.group.gbuf if self.grad_is_f32 else self.group.gbuf16
+        return g[:, self.col:self.col + self.width]
+
+    def want(self, f32: bool = False, bf16: bool = False) -> "Act":
+        self.group.need_f32 |= f32
+        self.group.need_bf16 |= bf16
+        return self
 
 
 class LinearSpec:
@@ -64,55 +107,55 @@ class LinearSpec:
         self.b: Optional[nn.Parameter] = getattr(linear, "bias", None)
         self.N, self.K = self.W.shape
 
-    def params(self) -> List[nn.Parameter]:
-        return [self.W] + ([self.b] if self.b is not None else [])
-
 
 class Builder:
     """Collects stages.  In ``dry`` mode nothing is allocated: only the order in which parameters
-    are consumed is recorded (it becomes the flat-store layout)."""
+    and buffers are consumed is recorded (it becomes the flat-store layout)."""
 
-    def __init__(self, B: int, device, store: Optional[FlatStore], dry: bool):
+    def __init__(self, B: int, device, store: Optional[FlatStore], dry: bool, precision: str = "fp32"):
         self.B, self.device, self.store, self.dry = B, device, store, dry
+        self.tc = precision == "bf16"
         self.stages: List["Stage"] = []
+        self.groups: List[ActGroup] = []
         self.param_order: List[nn.Parameter] = []
         self.buffer_order: List[torch.Tensor] = []
         self.keep: List[object] = []       # tensors whose addresses are baked into tables
         self.lib = None if dry else L.load()
 
     # ---- allocation helpers
-    def zeros(self, *shape, dtype=torch.float32) -> Optional[torch.Tensor]:
-        if self.dry:
-            return None
+    def zeros(self, *shape, dtype=torch.float32) -> torch.Tensor:
         t = torch.zeros(*shape, dtype=dtype, device=self.device)
         self.keep.append(t)
         return t
 
-    def table(self, structs: Sequence[C.Structure]) -> Optional[torch.Tensor]:
-        if self.dry:
-            return None
-        raw = L.struct_bytes(structs)
-        t = torch.frombuffer(bytearray(raw), dtype=torch.uint8).to(self.device)
+    def table(self, structs: Sequence[C.Structure]) -> torch.Tensor:
+        t = torch.frombuffer(bytearray(L.struct_bytes(structs)), dtype=torch.uint8).to(self.device)
         self.keep.append(t)
         return t
 
-    def ints(self, values: Sequence[int], dtype=torch.int32) -> Optional[torch.Tensor]:
-        if self.dry:
-            return None
+    def ints(self, values: Sequence[int], dtype=torch.int32) -> torch.Tensor:
         t = torch.tensor(list(values), dtype=dtype, device=self.device)
         self.keep.append(t)
         return t
 
-    def new_act_buffer(self, widths: Sequence[int], relu: bool, name: str, needs_grad: bool = True) -> List[Act]:
-        """One wide buffer (and its gradient twin) holding several activations side by side."""
-        total = _align(sum(widths), 4)
-        buf = self.zeros(self.B, total)
-        gbuf = self.zeros(self.B, total) if needs_grad else None
-        acts, at = [], 0
-        for i, w in enumerate(widths):
-            acts.append(Act(buf, gbuf, at, w, relu=relu, needs_grad=needs_grad, name=f"{name}[{i}]"))
-            at += w
-        return acts
+    def tc_table(self, descs: Sequence[L.GemmTcDesc]):
+        """Encode tensor-core problems (tensor maps built on the host) -> (records, prefix, n, tiles)."""
+        rb = int(self.lib.mmlrec_tc_record_bytes())
+        host = (C.c_uint8 * (rb * len(descs)))()
+        pre, at = [0], 0
+        for i, d in enumerate(descs):
+            L.check(self.lib.mmlrec_tc_encode_problem(C.byref(d), C.addressof(host) + i * rb), "tc_encode_problem")
+            at += int(self.lib.mmlrec_tc_num_tiles(d.M, d.N))
+            pre.append(at)
+        rec = torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8).to(self.device)
+        assert rec.data_ptr() % 128 == 0
+        self.keep.append(rec)
+        return rec, self.ints(pre), len(descs), at
+
+    def new_group(self, widths: Sequence[int], relu: bool, name: str, grad_dtype: str = "f32") -> List[Act]:
+        g = ActGroup(widths, relu, name, grad_dtype if self.tc else "f32")
+        self.groups.append(g)
+        return g.acts
 
     def note_params(self, params: Sequence[Optional[nn.Parameter]]) -> None:
         self.param_order.extend(p for p in params if p is not None)
@@ -124,9 +167,18 @@ class Builder:
         self.stages.append(stage)
         return stage
 
+    def materialize(self) -> None:
+        for g in self.groups:
+            g.materialize(self)
+        for s in self.stages:
+            s.finalize()
+
 
 class Stage:
     name = "stage"
+
+    def finalize(self) -> None:
+        """Called once after every buffer exists: build the forward tables."""
 
     def forward(self, stream: int, training: bool) -> None:
         raise NotImplementedError
@@ -149,19 +201,18 @@ class GatherStage(Stage):
     def __init__(self, b: Builder, model):
         self.b, self.model = b, model
         self.in_dim = model.input_dim_total
-        (self.out,) = b.new_act_buffer([self.in_dim], relu=False, name="dnn_input")
-        if b.dry:
-            return
-        st = b.store
-        emb, D = model.embedding_layout, model.emb_dim
+        (self.out,) = b.new_group([self.in_dim], relu=False, name="dnn_input", grad_dtype="f32")
+
+    def finalize(self):
+        b, model = self.b, self.model
         meta = []
-        for f in emb:  # (param, vocab, x_col, out_col)
+        for f in model.embedding_layout:  # (param, vocab, x_col, out_col)
             meta += [f[0]._mm_off, f[1], f[2], f[3]]
-        self.F_s, self.D = len(emb), D
+        self.F_s, self.D = len(model.embedding_layout), model.emb_dim
         self.meta = b.ints(meta if meta else [0, 0, 0, 0], dtype=torch.int64)
         self.dense_cols = b.ints(model.dense_x_cols if model.dense_x_cols else [0])
         self.F_d = len(model.dense_x_cols)
-        self.dense_out_col = self.F_s * D
+        self.dense_out_col = self.F_s * self.D
         self.X = b.zeros(b.B, model.num_x_cols)
         self.oob = b.zeros(1, dtype=torch.int32)
         if self.F_s:
@@ -173,10 +224,12 @@ class GatherStage(Stage):
             self.keys_ws = b.zeros(self.F_s * n_pad, dtype=torch.int64)
 
     def forward(self, stream, training):
-        b, st = self.b, self.b.store
+        b, st, o = self.b, self.b.store, self.out
         L.check(b.lib.mmlrec_gather_concat(
             self.X.data_ptr(), self.X.stride(0), b.B, st.emb.data_ptr(), self.meta.data_ptr(), self.F_s, self.D,
-            self.dense_cols.data_ptr(), self.F_d, self.dense_out_col, self.out.ptr, self.out.ld, None, 0,
+            self.dense_cols.data_ptr(), self.F_d, self.dense_out_col,
+            o.ptr if o.has_f32 else None, o.ld if o.has_f32 else 0,
+            o.ptr16 if o.has_bf16 else None, o.ld16 if o.has_bf16 else 0,
             self.oob.data_ptr(), stream), "gather_concat")
 
     def sort(self, stream):
@@ -192,7 +245,7 @@ class GatherStage(Stage):
         b, st, hy = self.b, self.b.store, self.model.hyper_dev
         p = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
         L.check(b.lib.mmlrec_emb_backward_update(
-            self.out.gptr, self.out.gbuf.stride(0), b.B, self.sorted_ids.data_ptr(), self.sorted_pos.data_ptr(),
+            self.out.gptr, self.out.gld, b.B, self.sorted_ids.data_ptr(), self.sorted_pos.data_ptr(),
             self.meta.data_ptr(), self.F_s, self.D, st.emb.data_ptr(), p(st.emb_s1), p(st.emb_s2), p(st.row_touch),
             hy.data_ptr(), None, stream), "emb_backward_update")
         if self.model.optimizer_name == "adam":
@@ -208,16 +261,16 @@ class _Group:
     """Adjacent members of a stage that read the same input and whose parameters are contiguous:
     executed as one wide problem."""
 
-    def __init__(self, members: List[LinearSpec], y_col: int):
-        self.members, self.y_col = members, y_col
+    def __init__(self, members: List[LinearSpec], outs: List[Act]):
+        self.members, self.outs = members, outs
+        self.y_col = outs[0].col
         self.x = members[0].x
         self.K = members[0].K
         self.N = sum(m.N for m in members)
         self.W, self.b = members[0].W, members[0].b
-        self.has_bn = members[0].bn is not None
 
 
-def _tile_prefix(problems: Sequence[L.GemmF32]) -> Tuple[List[int], int]:
+def _tile_prefix_f32(problems: Sequence[L.GemmF32]) -> Tuple[List[int], int]:
     pre, at = [0], 0
     for p in problems:
         at += ((p.M + 63) // 64) * ((p.N + 63) // 64)
@@ -243,128 +296,185 @@ class LinearStage(Stage):
             b.note_buffers([s.bn.running_mean for s in specs])
             b.note_buffers([s.bn.running_var for s in specs])
             b.note_buffers([s.bn.num_batches_tracked for s in specs])
-        relu = act == "relu"
-        self.outs = b.new_act_buffer([s.N for s in specs], relu=relu, name=f"{label}.y")
-        self.zs = b.new_act_buffer([s.N for s in specs], relu=False, name=f"{label}.z") if self.use_bn else None
-        if b.dry:
-            return
-        st = b.store
-        # ---- merge adjacent members sharing x with contiguous parameters
+        widths = [s.N for s in specs]
+        # without BatchNorm the backward GEMMs read dZ = d(out) directly (bf16 in tensor-core mode);
+        # with BatchNorm d(out) feeds the BN backward kernel (fp32) which emits dZ
+        self.outs = b.new_group(widths, relu=(act == "relu"), name=f"{label}.y",
+                                grad_dtype="f32" if self.use_bn else "bf16")
+        self.zs = b.new_group(widths, relu=False, name=f"{label}.z", grad_dtype="bf16") if self.use_bn else None
+        if self.use_bn:
+            self.zs[0].want(f32=True)
+        for s in specs:
+            s.x.want(f32=not b.tc, bf16=b.tc)
+
+    # ---- forward tables
+    def finalize(self):
+        b, st, specs = self.b, self.b.store, self.specs
         self.groups: List[_Group] = []
         cur: List[LinearSpec] = []
+
+        def flush():
+            if cur:
+                self.groups.append(_Group(list(cur), [self.outs[specs.index(m)] for m in cur]))
+
         for s in specs:
             ok = bool(cur) and s.x.same_as(cur[-1].x) and s.K == cur[-1].K and st.contiguous_after(cur[-1].W, s.W) \
                 and ((s.b is None) == (cur[-1].b is None)) and (s.b is None or st.contiguous_after(cur[-1].b, s.b))
             if ok and self.use_bn:
-                ok = st.contiguous_after(cur[-1].bn.weight, s.bn.weight) and st.contiguous_after(cur[-1].bn.bias, s.bn.bias) \
-                    and cur[-1].bn.running_mean._mm_off + cur[-1].N == s.bn.running_mean._mm_off \
-                    and cur[-1].bn.running_var._mm_off + cur[-1].N == s.bn.running_var._mm_off
-            if ok:
-                cur.append(s)
-            else:
-                if cur:
-                    self.groups.append(_Group(cur, self.outs[specs.index(cur[0])].col))
-                cur = [s]
-        self.groups.append(_Group(cur, self.outs[specs.index(cur[0])].col))
-        ybuf = self.outs[0].buf
-        fwd_target = self.zs[0].buf if self.use_bn else ybuf
-        probs = []
-        for g in self.groups:
-            p = L.GemmF32()
-            p.A, p.a_rs, p.a_cs = g.x.ptr, g.x.ld, 1
-            p.B, p.b_rs, p.b_cs = g.W.data_ptr(), g.W._mm_ld, 1
-            p.C, p.ldc = fwd_target.data_ptr() + 4 * g.y_col, fwd_target.stride(0)
-            p.bias = g.b.data_ptr() if g.b is not None else None
-            p.M, p.N, p.K = b.B, g.N, g.K
-            p.act = L.ACT_NONE if self.use_bn else L.ACT_CODES[act]
-            probs.append(p)
-        self.fwd_table = b.table(probs)
-        pre, self.fwd_tiles = _tile_prefix(probs)
-        self.fwd_prefix = b.ints(pre)
-        self.n_fwd = len(probs)
+                p, q = cur[-1].bn, s.bn
+                ok = st.contiguous_after(p.weight, q.weight) and st.contiguous_after(p.bias, q.bias) \
+                    and p.running_mean._mm_off + cur[-1].N == q.running_mean._mm_off \
+                    and p.running_var._mm_off + cur[-1].N == q.running_var._mm_off \
+                    and p.num_batches_tracked._mm_off + 1 == q.num_batches_tracked._mm_off
+            if not ok:
+                flush()
+                cur.clear()
+            cur.append(s)
+        flush()
+        yg = self.outs[0].group
+        tgt = self.zs[0].group if self.use_bn else yg
+        act_code = L.ACT_NONE if self.use_bn else L.ACT_CODES[self.act]
+        if not b.tc:
+            probs = []
+            for g in self.groups:
+                p = L.GemmF32()
+                p.A, p.a_rs, p.a_cs = g.x.ptr, g.x.ld, 1
+                p.B, p.b_rs, p.b_cs = g.W.data_ptr(), g.W._mm_ld, 1
+                p.C, p.ldc = tgt.buf.data_ptr() + 4 * g.y_col, tgt.buf.stride(0)
+                p.bias = g.b.data_ptr() if g.b is not None else None
+                p.M, p.N, p.K, p.act = b.B, g.N, g.K, act_code
+                probs.append(p)
+            pre, tiles = _tile_prefix_f32(probs)
+            self.fwd = (b.table(probs), b.ints(pre), len(probs), tiles)
+        else:
+            descs = []
+            for g in self.groups:
+                d = L.GemmTcDesc()
+                d.A, d.lda, d.a_mn_major = g.x.ptr16, g.x.ld16, 0
+                d.B, d.ldb, d.b_mn_major = st.bf16_ptr(g.W), g.W._mm_ld, 0
+                d.M, d.N, d.K = b.B, g.N, g.K
+                if tgt.buf is not None:
+                    d.C_f32, d.ldc_f32 = tgt.buf.data_ptr() + 4 * g.y_col, tgt.buf.stride(0)
+                if tgt.buf16 is not None:
+                    d.C_bf16, d.ldc_bf16 = tgt.buf16.data_ptr() + 2 * g.y_col, tgt.buf16.stride(0)
+                d.bias = g.b.data_ptr() if g.b is not None else None
+                d.act = act_code
+                descs.append(d)
+            self.fwd = b.tc_table(descs)
         if self.use_bn:
-            n_total = sum(g.N for g in self.groups)
-            self.save_mean = b.zeros(_align(n_total, 4))
-            self.save_invstd = b.zeros(_align(n_total, 4))
+            n_total = _align(yg.total, 4)
+            self.save_mean, self.save_invstd = b.zeros(n_total), b.zeros(n_total)
 
-    # ---- forward
+    def _launch(self, tbl, stream, what):
+        fn = self.b.lib.mmlrec_gemm_grouped_tc if self.b.tc else self.b.lib.mmlrec_gemm_grouped_f32
+        L.check(fn(tbl[0].data_ptr(), tbl[1].data_ptr(), tbl[2], tbl[3], stream), f"{what} {self.label}")
+
     def forward(self, stream, training):
         b = self.b
-        L.check(b.lib.mmlrec_gemm_grouped_f32(self.fwd_table.data_ptr(), self.fwd_prefix.data_ptr(), self.n_fwd,
-                                              self.fwd_tiles, stream), f"linear fwd {self.label}")
+        self._launch(self.fwd, stream, "linear fwd")
         if self.use_bn:
-            zbuf, ybuf = self.zs[0].buf, self.outs[0].buf
+            zg, yg = self.zs[0].group, self.outs[0].group
             for g in self.groups:
-                bn0 = g.members[0].bn
+                bn0, c = g.members[0].bn, g.y_col
                 L.check(b.lib.mmlrec_bn_forward(
-                    zbuf.data_ptr() + 4 * g.y_col, zbuf.stride(0), b.B, g.N, bn0.weight.data_ptr(), bn0.bias.data_ptr(),
+                    zg.buf.data_ptr() + 4 * c, zg.buf.stride(0), b.B, g.N, bn0.weight.data_ptr(), bn0.bias.data_ptr(),
                     bn0.running_mean.data_ptr(), bn0.running_var.data_ptr(), bn0.num_batches_tracked.data_ptr(),
-                    len(g.members), self.save_mean.data_ptr() + 4 * g.y_col, self.save_invstd.data_ptr() + 4 * g.y_col,
-                    ybuf.data_ptr() + 4 * g.y_col, ybuf.stride(0), None, 0, L.ACT_CODES[self.act], 1 if training else 0,
-                    stream), f"bn fwd {self.label}")
+                    len(g.members), self.save_mean.data_ptr() + 4 * c, self.save_invstd.data_ptr() + 4 * c,
+                    (yg.buf.data_ptr() + 4 * c) if yg.buf is not None else None,
+                    yg.buf.stride(0) if yg.buf is not None else 0,
+                    (yg.buf16.data_ptr() + 2 * c) if yg.buf16 is not None else None,
+                    yg.buf16.stride(0) if yg.buf16 is not None else 0,
+                    L.ACT_CODES[self.act], 1 if training else 0, stream), f"bn fwd {self.label}")
 
     # ---- backward
     def plan_backward(self):
         b, st = self.b, self.b.store
         self.live_groups: List[_Group] = []
-        waves: List[List[L.GemmF32]] = [[]]
-        gy, gz = self.outs[0].gbuf, (self.zs[0].gbuf if self.use_bn else None)
+        waves: List[list] = [[]]
+        dzg = self.zs[0].group if self.use_bn else self.outs[0].group   # where dZ lives
         for g in self.groups:
-            outs = [self.outs[self.specs.index(m)] for m in g.members]
-            if not any(o.grad_written for o in outs):
-                continue  # nothing flows into this group: parameters keep a zero gradient
-            for o in outs:
+            if not any(o.grad_written for o in g.outs):
+                continue  # nothing flows into this group: its parameters keep a zero gradient
+            for o in g.outs:
                 if not o.grad_written:
                     o.grad_tensor().zero_()  # stays zero: the buffer is never written afterwards
             self.live_groups.append(g)
-            dz = gz if self.use_bn else gy
-            dz_ptr, dz_ld = dz.data_ptr() + 4 * g.y_col, dz.stride(0)
-            # wgrad: dW[n,k] = sum_b dZ[b,n] X[b,k]; rowsum_a = bias gradient
-            p = L.GemmF32()
-            p.A, p.a_rs, p.a_cs = dz_ptr, 1, dz_ld
-            p.B, p.b_rs, p.b_cs = g.x.ptr, 1, g.x.ld
-            p.C, p.ldc = st.grad_ptr(g.W), g.W._mm_ld
-            p.rowsum_a = st.grad_ptr(g.b) if g.b is not None else None
-            p.M, p.N, p.K = g.N, g.K, b.B
-            waves[0].append(p)
-            # dgrad: dX[b,k] = sum_n dZ[b,n] W[n,k]  (masked by the producer's ReLU)
-            if g.x.needs_grad and g.x.gbuf is not None:
-                q = L.GemmF32()
-                q.A, q.a_rs, q.a_cs = dz_ptr, dz_ld, 1
-                q.B, q.b_rs, q.b_cs = g.W.data_ptr(), 1, g.W._mm_ld
-                q.C, q.ldc = g.x.gptr, g.x.gbuf.stride(0)
-                q.M, q.N, q.K = b.B, g.K, g.N
-                if g.x.relu:
-                    q.mask, q.ldmask = g.x.ptr, g.x.ld
-                q.accumulate = 1 if g.x.grad_written else 0
-                # two problems of one launch must not write the same gradient: later ones wait a wave
-                w = sum(1 for gg in self.live_groups[:-1] if gg.x.same_as(g.x) and gg.x.needs_grad)
-                while len(waves) <= w:
-                    waves.append([])
-                if w > 0:
-                    q.accumulate = 1
-                waves[w].append(q)
-                g.x.grad_written = True
+            x = g.x
+            want_dx = x.group.need_grad
+            wave = sum(1 for gg in self.live_groups[:-1] if gg.x.same_as(x)) if want_dx else 0
+            while len(waves) <= wave:
+                waves.append([])
+            accumulate = 1 if (want_dx and (x.grad_written or wave > 0)) else 0
+            if not b.tc:
+                dz_ptr, dz_ld = dzg.gbuf.data_ptr() + 4 * g.y_col, dzg.gbuf.stride(0)
+                p = L.GemmF32()   # wgrad: dW[n,k] = sum_b dZ[b,n] X[b,k]; rowsum_a = bias gradient
+                p.A, p.a_rs, p.a_cs = dz_ptr, 1, dz_ld
+                p.B, p.b_rs, p.b_cs = x.ptr, 1, x.ld
+                p.C, p.ldc = st.grad_ptr(g.W), g.W._mm_ld
+                p.rowsum_a = st.grad_ptr(g.b) if g.b is not None else None
+                p.M, p.N, p.K = g.N, g.K, b.B
+                waves[0].append(p)
+                if want_dx:
+                    q = L.GemmF32()   # dgrad: dX[b,k] = sum_n dZ[b,n] W[n,k], masked by the producer's ReLU
+                    q.A, q.a_rs, q.a_cs = dz_ptr, dz_ld, 1
+                    q.B, q.b_rs, q.b_cs = g.W.data_ptr(), 1, g.W._mm_ld
+                    q.C, q.ldc = x.gptr, x.gld
+                    q.M, q.N, q.K = b.B, g.K, g.N
+                    if x.relu:
+                        q.mask, q.ldmask = x.ptr, x.ld
+                    q.accumulate = accumulate
+                    waves[wave].append(q)
+            else:
+                dz16, dz_ld = dzg.gbuf16.data_ptr() + 2 * g.y_col, dzg.gbuf16.stride(0)
+                d = L.GemmTcDesc()   # wgrad: both operands MN-major (no transposed copies)
+                d.A, d.lda, d.a_mn_major = dz16, dz_ld, 1
+                d.B, d.ldb, d.b_mn_major = x.ptr16, x.ld16, 1
+                d.M, d.N, d.K = g.N, g.K, b.B
+                d.C_f32, d.ldc_f32 = st.grad_ptr(g.W), g.W._mm_ld
+                d.colsum = st.grad_ptr(g.b) if g.b is not None else None
+                waves[0].append(d)
+                if want_dx:
+                    e = L.GemmTcDesc()   # dgrad: A = dZ (K-major), B = W read MN-major
+                    e.A, e.lda, e.a_mn_major = dz16, dz_ld, 0
+                    e.B, e.ldb, e.b_mn_major = st.bf16_ptr(g.W), g.W._mm_ld, 1
+                    e.M, e.N, e.K = b.B, g.K, g.N
+                    if x.grad_is_f32:
+                        e.C_f32, e.ldc_f32 = x.gptr, x.gld
+                        e.accumulate = accumulate
+                    else:
+                        assert not accumulate, "a bf16 gradient buffer cannot be accumulated into"
+                        e.C_bf16, e.ldc_bf16 = x.gptr, x.gld
+                    if x.relu:
+                        e.mask, e.ldmask = x.ptr16, x.ld16
+                    waves[wave].append(e)
+            if want_dx:
+                x.grad_written = True
         self.bwd = []
         for wv in waves:
-            if wv:
-                pre, tiles = _tile_prefix(wv)
+            if not wv:
+                continue
+            if b.tc:
+                self.bwd.append(b.tc_table(wv))
+            else:
+                pre, tiles = _tile_prefix_f32(wv)
                 self.bwd.append((b.table(wv), b.ints(pre), len(wv), tiles))
 
     def backward(self, stream):
         b = self.b
         if self.use_bn:
-            zbuf, gy, gz = self.zs[0].buf, self.outs[0].gbuf, self.zs[0].gbuf
+            zg, yg = self.zs[0].group, self.outs[0].group
             for g in self.live_groups:
-                bn0 = g.members[0].bn
+                bn0, c = g.members[0].bn, g.y_col
                 L.check(b.lib.mmlrec_bn_backward(
-                    gy.data_ptr() + 4 * g.y_col, gy.stride(0), zbuf.data_ptr() + 4 * g.y_col, zbuf.stride(0), b.B, g.N,
-                    bn0.weight.data_ptr(), self.save_mean.data_ptr() + 4 * g.y_col,
-                    self.save_invstd.data_ptr() + 4 * g.y_col, gz.data_ptr() + 4 * g.y_col, gz.stride(0), None, 0,
+                    yg.gbuf.data_ptr() + 4 * c, yg.gbuf.stride(0), zg.buf.data_ptr() + 4 * c, zg.buf.stride(0), b.B, g.N,
+                    bn0.weight.data_ptr(), self.save_mean.data_ptr() + 4 * c, self.save_invstd.data_ptr() + 4 * c,
+                    (zg.gbuf.data_ptr() + 4 * c) if zg.gbuf is not None else None,
+                    zg.gbuf.stride(0) if zg.gbuf is not None else 0,
+                    (zg.gbuf16.data_ptr() + 2 * c) if zg.gbuf16 is not None else None,
+                    zg.gbuf16.stride(0) if zg.gbuf16 is not None else 0,
                     b.store.grad_ptr(bn0.weight), b.store.grad_ptr(bn0.bias), stream), f"bn bwd {self.label}")
-        for table, prefix, n, tiles in self.bwd:
-            L.check(b.lib.mmlrec_gemm_grouped_f32(table.data_ptr(), prefix.data_ptr(), n, tiles, stream),
-                    f"linear bwd {self.label}")
+        for tbl in self.bwd:
+            self._launch(tbl, stream, "linear bwd")
 
 
 def mlp_stages(b: Builder, items: Sequence[Tuple[Act, nn.Module]], label: str) -> List[Act]:
@@ -401,14 +511,20 @@ class GateMixStage(Stage):
         H = gates[0].experts[0].width
         assert all(e.width == H for g in gates for e in g.experts)
         self.H = H
-        self.outs = b.new_act_buffer([H] * len(gates), relu=False, name=f"{label}.mix")
-        if b.dry:
-            return
-        self.probs = [b.zeros(b.B, len(g.experts)) for g in gates]
-        self._fill_tables(backward=False)
+        self.outs = b.new_group([H] * len(gates), relu=False, name=f"{label}.mix", grad_dtype="f32")
+        self.outs[0].want(f32=True)
+        for g in gates:
+            g.gate_in.want(f32=True)
+            for e in g.experts:
+                e.want(f32=True)
+        self.any_live = False
+
+    def finalize(self):
+        self.probs = [self.b.zeros(self.b.B, len(g.experts)) for g in self.gates]
+        self.gate_table = self.b.table([self._gate_record(i, False) for i in range(len(self.gates))])
 
     def _gate_record(self, i: int, backward: bool) -> L.Gate:
-        g, st = self.gates[i], self.b.store
+        g, st, o = self.gates[i], self.b.store, self.outs[i]
         r = L.Gate()
         r.gate_in, r.ld_gate_in, r.Hg, r.n_e = g.gate_in.ptr, g.gate_in.ld, g.gate_in.width, len(g.experts)
         assert r.n_e <= L.MAX_GATE_EXPERTS
@@ -418,20 +534,23 @@ class GateMixStage(Stage):
         assert all(a.ld == g.experts[0].ld for a in g.experts)
         r.ld_expert, r.H = g.experts[0].ld, self.H
         r.probs = self.probs[i].data_ptr()
-        r.mix, r.ld_mix = self.outs[i].ptr, self.outs[i].ld
-        if backward and self.outs[i].grad_written:
-            r.d_mix, r.ld_d_mix = self.outs[i].gptr, self.outs[i].gbuf.stride(0)
+        r.mix, r.ld_mix = o.ptr, o.ld
+        if o.has_bf16:
+            r.mix_bf16, r.ld_mix_bf16 = o.ptr16, o.ld16
+        if backward and o.grad_written:
+            r.d_mix, r.ld_d_mix = o.gptr, o.gld
             gi = g.gate_in
-            if gi.needs_grad and gi.gbuf is not None:
-                r.d_gate_in, r.ld_d_gate_in = gi.gptr, gi.gbuf.stride(0)
+            if gi.group.need_grad:
+                if gi.grad_is_f32:
+                    r.d_gate_in, r.ld_d_gate_in = gi.gptr, gi.gld
+                    r.accumulate_d_gate_in = 1 if gi.grad_written else 0
+                else:
+                    assert not gi.grad_written, "a bf16 gradient buffer cannot be accumulated into"
+                    r.d_gate_in_bf16, r.ld_d_gate_in_bf16 = gi.gptr, gi.gld
                 r.relu_mask_gate_in = 1 if gi.relu else 0
-                r.accumulate_d_gate_in = 1 if gi.grad_written else 0
                 gi.grad_written = True
             r.dWg = st.grad_ptr(g.head.weight)
         return r
-
-    def _fill_tables(self, backward: bool):
-        self.gate_table = self.b.table([self._gate_record(i, backward) for i in range(len(self.gates))])
 
     def forward(self, stream, training):
         L.check(self.b.lib.mmlrec_gate_mix_forward(self.gate_table.data_ptr(), len(self.gates), self.b.B, stream),
@@ -451,7 +570,7 @@ class GateMixStage(Stage):
             if any(gi.same_as(o) for o in seen):
                 self.serialize = 1
             seen.append(gi)
-        self._fill_tables(backward=True)
+        self.gate_table = b.table([self._gate_record(i, True) for i in range(len(self.gates))])
         # experts: every distinct expert activation gets d = sum over its user gates of p * d_mix
         recs, uniq = [], []
         for i in live:
@@ -461,8 +580,11 @@ class GateMixStage(Stage):
         for a in uniq:
             r = L.ExpertGrad()
             assert not a.grad_written, "an expert output consumed elsewhere must be accumulated"
-            r.expert, r.ld_expert = a.ptr, a.ld
-            r.d_expert, r.ld_d_expert, r.H = a.gptr, a.gbuf.stride(0), self.H
+            r.expert, r.ld_expert, r.H = a.ptr, a.ld, self.H
+            if a.grad_is_f32:
+                r.d_expert, r.ld_d_expert = a.gptr, a.gld
+            else:
+                r.d_expert_bf16, r.ld_d_expert_bf16 = a.gptr, a.gld
             r.relu_mask = 1 if a.relu else 0
             n = 0
             for i in live:
@@ -470,7 +592,7 @@ class GateMixStage(Stage):
                     if ea.same_as(a):
                         r.user_probs[n] = self.probs[i].data_ptr()
                         r.user_prob_ld[n], r.user_prob_col[n] = self.probs[i].stride(0), e
-                        r.user_d_mix[n], r.user_d_mix_ld[n] = self.outs[i].gptr, self.outs[i].gbuf.stride(0)
+                        r.user_d_mix[n], r.user_d_mix_ld[n] = self.outs[i].gptr, self.outs[i].gld
                         n += 1
             assert n <= L.MAX_TASKS + 1
             r.n_users = n
@@ -511,28 +633,34 @@ class HeadStage(Stage):
         b.note_params([h.final.weight for h in heads])
         b.note_params([h.bias for h in heads])
         self.T = len(heads)
-        if b.dry:
-            return
-        st = b.store
+        for h in heads:
+            h.h.want(f32=True)
+
+    def finalize(self):
+        b, st = self.b, self.b.store
         self.y = b.zeros(b.B, self.T)
         self.pred = b.zeros(b.B, self.T)
         self.loss = b.zeros(self.T + 1)
         recs = []
-        for h in heads:
+        for h in self.heads:
             r = L.Head()
             r.h, r.ld_h, r.H = h.h.ptr, h.h.ld, h.h.width
             r.kind = L.HEAD_SIGMOID_BCE if h.task == "binary" else L.HEAD_IDENTITY_MSE
             r.w = h.final.weight.data_ptr()
             r.bias = h.bias.data_ptr() if h.bias is not None else None
-            if h.h.needs_grad and h.h.gbuf is not None:
+            if h.h.group.need_grad:
                 assert not h.h.grad_written
-                r.d_h, r.ld_d_h, r.relu_mask = h.h.gptr, h.h.gbuf.stride(0), 1 if h.h.relu else 0
+                if h.h.grad_is_f32:
+                    r.d_h, r.ld_d_h = h.h.gptr, h.h.gld
+                else:
+                    r.d_h_bf16, r.ld_d_h_bf16 = h.h.gptr, h.h.gld
+                r.relu_mask = 1 if h.h.relu else 0
                 h.h.grad_written = True
             r.dw = st.grad_ptr(h.final.weight)
             r.dbias = st.grad_ptr(h.bias) if h.bias is not None else None
             recs.append(r)
         self.table = b.table(recs)
-        max_h = max(h.h.width for h in heads)
+        max_h = max(h.h.width for h in self.heads)
         self.scratch = b.zeros(int(b.lib.mmlrec_heads_scratch(self.T, max_h, b.B)))
         self.counter = b.zeros(1, dtype=torch.int32)
 
@@ -552,8 +680,9 @@ class StepPlan:
 
     def __init__(self, model, B: int):
         self.model, self.B = model, B
-        self.b = Builder(B, model.device_obj, model.store, dry=False)
+        self.b = Builder(B, model.device_obj, model.store, dry=False, precision=model.precision)
         model.build_graph(self.b)
+        self.b.materialize()
         self.stages = self.b.stages
         self.gather: GatherStage = next(s for s in self.stages if isinstance(s, GatherStage))
         self.heads: HeadStage = next(s for s in self.stages if isinstance(s, HeadStage))
@@ -562,21 +691,10 @@ class StepPlan:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
 
     # ---- static inputs / outputs
-    @property
-    def X(self) -> torch.Tensor:
-        return self.gather.X
-
-    @property
-    def y(self) -> torch.Tensor:
-        return self.heads.y
-
-    @property
-    def pred(self) -> torch.Tensor:
-        return self.heads.pred
-
-    @property
-    def loss(self) -> torch.Tensor:
-        return self.heads.loss
+    X = property(lambda self: self.gather.X)
+    y = property(lambda self: self.heads.y)
+    pred = property(lambda self: self.heads.pred)
+    loss = property(lambda self: self.heads.loss)
 
     def forward(self, training: bool, stream: Optional[int] = None) -> None:
         stream = torch.cuda.current_stream().cuda_stream if stream is None else stream

@@ -149,7 +149,7 @@ class BaseModel(nn.Module):
         self._index_features()
         if self.device_obj.type != "cuda":
             return  # parameters stay ordinary CPU tensors; any compute call raises (no CPU path)
-        dry = Builder(2, self.device_obj, None, dry=True)
+        dry = Builder(2, self.device_obj, None, dry=True, precision=self.precision)
         self.build_graph(dry)
         emb_params = [t[0] for t in self.embedding_layout]
         self.store = FlatStore(self, dry.param_order, emb_params, self.device_obj, want_bf16=self.precision == "bf16",
