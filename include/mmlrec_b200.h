@@ -162,6 +162,12 @@ int64_t mmlrec_tc_record_bytes(void);
 int mmlrec_tc_encode_problem(const MmlrecGemmTcDesc* desc_host, void* record_host);
 int mmlrec_gemm_grouped_tc(const void* records, const int32_t* tile_prefix, int32_t n_problems,
                            int32_t total_tiles, void* stream);
+/* same launch, plus per-tile clock64() stamps of CTA 0 into stamps[64][16] (int64, device): slots 0-3 TMA
+ * producer (tile start, table read, first slot free, last load issued), 4-7 MMA issuer (tile start,
+ * accumulator free, first operands landed, last commit), 8-11 epilogue (tile start, bias staged,
+ * accumulator ready, tile stored).  Profiling aid. */
+int mmlrec_gemm_grouped_tc_debug(const void* records, const int32_t* tile_prefix, int32_t n_problems,
+                                 int32_t total_tiles, int64_t* stamps, void* stream);
 /* tiles a problem occupies (BLOCK_M=128 x BLOCK_N=128) */
 int32_t mmlrec_tc_num_tiles(int32_t M, int32_t N);
 

@@ -3,7 +3,8 @@
 // persistent CTAs (1 per SM):
 //   warp 0        TMA producer (one elected lane)
 //   warp 1        TMEM allocator + tcgen05.mma issuer (one elected lane)
-//   warps 2..5    epilogue: tcgen05.ld -> bias / activation / ReLU-mask -> fp32 and/or bf16 stores
+//   warps 2..9    epilogue: tcgen05.ld -> bias (smem) / activation -> smem transpose -> ReLU-mask /
+//                 accumulate -> coalesced fp32 and/or bf16 stores
 // D[M,N] = A * B^T.  Each operand is either K-major (row-major [rows,K]) or MN-major ([K,rows]);
 // the MN-major form is what wgrad needs (dW = dZ^T X reads both activations "transposed"), so no
 // transposed copy of any activation is ever written.  The bias gradient of a wgrad problem
@@ -19,11 +20,17 @@ constexpr int TC_STAGES = 4;
 constexpr int TC_ACC_STAGES = 2;
 constexpr int TC_ACC_COLS = 256;                 // TMEM columns per accumulator stage (128 main + 16 row-sum, padded)
 constexpr int TC_TMEM_COLS = 512;
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;                 // two warps per TMEM lane quarter, 64 columns each
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
+constexpr int TC_MAX_PROBLEMS = 96;              // tile table cached in shared memory
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;    // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;    // 16 KB
 constexpr int TC_ONES_BYTES = 16 * 128;          // 16 rows x 128 B of bf16 1.0
-constexpr int TC_SMEM_BYTES = 1024 /*align slack*/ + TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + TC_ONES_BYTES + 256;
+constexpr int TC_STAGE_LD = 34;                  // transpose tile row stride: even (64-bit accesses), conflict-free per half-warp
+constexpr int TC_STAGE_TILE_FLOATS = 32 * TC_STAGE_LD;
+constexpr int TC_SMEM_BYTES = 1024 /*align slack*/ + TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + TC_ONES_BYTES + 256 +
+                              TC_EPI_WARPS * TC_STAGE_TILE_FLOATS * 4 + 2 * TC_BN * 4 +
+                              (2 * TC_MAX_PROBLEMS + 2) * 4;
 
 struct alignas(128) TcRecord {
   CUtensorMap tmA;
@@ -58,7 +65,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n"
       ".reg .pred p;\n"
       "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"
       "@p bra WAIT_DONE;\n"
       "bra WAIT_LOOP;\n"
       "WAIT_DONE:\n"
@@ -127,39 +134,73 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N, bool a_mn, bool b_m
   return d;
 }
 
+// Branch-free store of one full 32x32 chunk from the transpose tile (lane = column pair, lanes 0-15 even
+// rows, lanes 16-31 odd rows): bias (+ReLU), optional read-modify-write, 8-byte fp32 / 4-byte bf16x2 stores.
+template <bool RELU, bool F32, bool BF16, bool ACC>
+__device__ __forceinline__ void store_chunk_fast(const float2* __restrict__ sread, float* __restrict__ pf, int64_t ldcf,
+                                                 uint16_t* __restrict__ pb, int64_t ldcb, float bx, float by) {
+  float2 old[16];
+  if (F32 && ACC) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) old[i] = *reinterpret_cast<const float2*>(pf + (int64_t)(2 * i) * ldcf);
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    float2 x = sread[i * TC_STAGE_LD];
+    x.x += bx; x.y += by;
+    if (RELU) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); }
+    if (F32) {
+      if (ACC) { x.x += old[i].x; x.y += old[i].y; }
+      *reinterpret_cast<float2*>(pf + (int64_t)(2 * i) * ldcf) = x;
+    }
+    if (BF16) *reinterpret_cast<uint32_t*>(pb + (int64_t)(2 * i) * ldcb) = pack_bf16x2(x.x, x.y);
+  }
+}
+
 struct TileCoord { int pi, tm, tn; };
-__device__ __forceinline__ TileCoord locate_tile(int t, const int32_t* __restrict__ prefix, int n_problems,
-                                                 const TcRecord* __restrict__ recs) {
-  int pi = 0;
-  while (pi + 1 < n_problems && prefix[pi + 1] <= t) ++pi;
-  int local = t - prefix[pi];
-  int tiles_n = recs[pi].tiles_n;
+// prefix / tiles_n live in shared memory (copied once per CTA): the lookup costs no global latency
+__device__ __forceinline__ TileCoord locate_tile(int t, const int32_t* s_prefix, const int32_t* s_tiles_n, int n_problems) {
+  int lo = 0, hi = n_problems - 1;
+  while (lo < hi) {  // last problem whose first tile is <= t
+    int mid = (lo + hi + 1) >> 1;
+    if (s_prefix[mid] <= t) lo = mid; else hi = mid - 1;
+  }
+  const int local = t - s_prefix[lo];
+  const int tiles_n = s_tiles_n[lo];
   TileCoord c;
-  c.pi = pi; c.tm = local / tiles_n; c.tn = local - c.tm * tiles_n;
+  c.pi = lo; c.tm = local / tiles_n; c.tn = local - c.tm * tiles_n;
   return c;
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
-gemm_grouped_tc_kernel(const TcRecord* __restrict__ recs, const int32_t* __restrict__ prefix, int n_problems, int total_tiles) {
+gemm_grouped_tc_kernel(const TcRecord* __restrict__ recs, const int32_t* __restrict__ prefix, int n_problems, int total_tiles,
+                       long long* __restrict__ dbg) {
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte alignment is required by the 128B swizzle atom
-  unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+  // (offset arithmetic on the shared array itself, so the compiler keeps emitting LDS/STS, not generic LD/ST)
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* sA = smem;
   unsigned char* sB = smem + TC_STAGES * TC_A_BYTES;
   unsigned char* sOnes = smem + TC_STAGES * (TC_A_BYTES + TC_B_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + TC_ONES_BYTES);
   // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty, then tmem base slot
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 2 * TC_ACC_STAGES);
+  float* stage_s = reinterpret_cast<float*>(sOnes + TC_ONES_BYTES + 256);           // [EPI_WARPS][32][33]
+  float* bias_s = stage_s + TC_EPI_WARPS * TC_STAGE_TILE_FLOATS;                     // [2][128]
+  int32_t* s_prefix = reinterpret_cast<int32_t*>(bias_s + 2 * TC_BN);                // [MAX_PROBLEMS + 1]
+  int32_t* s_tiles_n = s_prefix + TC_MAX_PROBLEMS + 1;                               // [MAX_PROBLEMS]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t full_bar = smem_u32(bars), empty_bar = smem_u32(bars + TC_STAGES);
   const uint32_t tfull_bar = smem_u32(bars + 2 * TC_STAGES), tempty_bar = smem_u32(bars + 2 * TC_STAGES + TC_ACC_STAGES);
 
-  // all-ones B tile for the row-sum MMA
+  // all-ones B tile for the row-sum MMA; tile table -> shared memory
   for (int i = threadIdx.x; i < TC_ONES_BYTES / 4; i += TC_THREADS) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
+  for (int i = threadIdx.x; i <= n_problems; i += TC_THREADS) s_prefix[i] = prefix[i];
+  for (int i = threadIdx.x; i < n_problems; i += TC_THREADS) s_tiles_n[i] = recs[i].tiles_n;
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
-    for (int s = 0; s < TC_ACC_STAGES; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, 4); }
+    for (int s = 0; s < TC_ACC_STAGES; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // ones tile (generic writes) -> async proxy
@@ -171,19 +212,26 @@ gemm_grouped_tc_kernel(const TcRecord* __restrict__ recs, const int32_t* __restr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // optional per-tile clock stamps of CTA 0 (debug timeline): dbg[tile_iter * 16 + slot]
+  const bool stamp = dbg != nullptr && blockIdx.x == 0;
+#define TC_STAMP(iter, slot) do { if (stamp && (iter) < 64) dbg[(iter) * 16 + (slot)] = clock64(); } while (0)
 
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileCoord tc = locate_tile(t, prefix, n_problems, recs);
+      int pit = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++pit) {
+        TC_STAMP(pit, 0);
+        const TileCoord tc = locate_tile(t, s_prefix, s_tiles_n, n_problems);
         const TcRecord* R = recs + tc.pi;
         const int K = R->K, a_mn = R->a_mn, b_mn = R->b_mn;
         const int m0 = tc.tm * TC_BM, n0 = tc.tn * TC_BN;
         const int num_kb = (K + TC_BK - 1) / TC_BK;
+        TC_STAMP(pit, 1);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          if (kb == 0) TC_STAMP(pit, 2);
           const uint32_t fb = full_bar + 8 * stage;
           mbar_expect_tx(fb, TC_A_BYTES + TC_B_BYTES);
           const uint32_t a_dst = smem_u32(sA + stage * TC_A_BYTES), b_dst = smem_u32(sB + stage * TC_B_BYTES);
@@ -202,6 +250,7 @@ gemm_grouped_tc_kernel(const TcRecord* __restrict__ recs, const int32_t* __restr
           }
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
+        TC_STAMP(pit, 3);
       }
     }
   } else if (warp == 1) {
@@ -210,8 +259,9 @@ gemm_grouped_tc_kernel(const TcRecord* __restrict__ recs, const int32_t* __restr
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       const uint64_t ones_desc = make_smem_desc(smem_u32(sOnes), false);
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-        const TileCoord tc = locate_tile(t, prefix, n_problems, recs);
+      int mit = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++mit) {
+        const TileCoord tc = locate_tile(t, s_prefix, s_tiles_n, n_problems);
         const TcRecord* R = recs + tc.pi;
         const int K = R->K;
         const bool a_mn = R->a_mn != 0, b_mn = R->b_mn != 0;
@@ -219,12 +269,15 @@ gemm_grouped_tc_kernel(const TcRecord* __restrict__ recs, const int32_t* __restr
         const uint32_t idesc = make_idesc(TC_BM, TC_BN, a_mn, b_mn);
         const uint32_t idesc_ones = make_idesc(TC_BM, 16, a_mn, false);
         const int num_kb = (K + TC_BK - 1) / TC_BK;
+        TC_STAMP(mit, 4);
         mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
+        TC_STAMP(mit, 5);
         const uint32_t d_tmem = tmem_base + acc * TC_ACC_COLS;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar + 8 * stage, phase);
           tc_fence_after();
+          if (kb == 0) TC_STAMP(mit, 6);
           const uint32_t a_addr = smem_u32(sA + stage * TC_A_BYTES), b_addr = smem_u32(sB + stage * TC_B_BYTES);
           const uint64_t a_desc = make_smem_desc(a_addr, a_mn), b_desc = make_smem_desc(b_addr, b_mn);
           // advancing K by 16 elements: 32 B inside the swizzle row (K-major) or two 8-row groups (MN-major)
@@ -239,104 +292,159 @@ gemm_grouped_tc_kernel(const TcRecord* __restrict__ recs, const int32_t* __restr
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
         tc_commit(tfull_bar + 8 * acc);       // accumulator ready for the epilogue
+        TC_STAMP(mit, 7);
         if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int q = warp & 3;                  // TMEM lane quarter this warp may access
+    // ===================== epilogue (warps 2..9) =====================
+    // warp -> TMEM lane quarter q (rows 32q..32q+31 of the tile) and column half (64 columns).
+    // Per 32-column chunk: tcgen05.ld (thread = row) -> + bias (smem) -> activation -> transpose through a
+    // padded smem tile -> (thread = column) ReLU-mask / accumulate / fp32 + bf16 stores, all coalesced.
+    const int q = warp & 3;
+    const int ew = warp - 2;                   // 0..7
+    const int half = ew >> 2;                  // 0: columns [0,64)  1: columns [64,128)
+    float* my_stage = stage_s + ew * TC_STAGE_TILE_FLOATS;
     int acc = 0; uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
-      const TileCoord tc = locate_tile(t, prefix, n_problems, recs);
+    int it = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+      const TileCoord tc = locate_tile(t, s_prefix, s_tiles_n, n_problems);
       const TcRecord* R = recs + tc.pi;
       const int M = R->M, N = R->N;
-      const int m = tc.tm * TC_BM + q * 32 + lane;
+      const int m_base = tc.tm * TC_BM + q * 32;
       const int n0 = tc.tn * TC_BN;
       float* const cf = R->C_f32; const int64_t ldcf = R->ldc_f32;
       uint16_t* const cb = R->C_bf16; const int64_t ldcb = R->ldc_bf16;
       const float* const bias = R->bias;
       const uint16_t* const mask = R->mask; const int64_t ldmask = R->ldmask;
       const int act = R->act, accumulate = R->accumulate;
-      mbar_wait(tfull_bar + 8 * acc, acc_phase);
-      tc_fence_after();
-      const uint32_t t_row = tmem_base + acc * TC_ACC_COLS + ((uint32_t)(q * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < TC_BN / 32; ++c) {
-        const int nc = n0 + c * 32;
-        if (nc >= N) break;                  // warp-uniform
-        uint32_t r[32];
-        tc_ld32(t_row + c * 32, r);
-        tc_wait_ld();
-        if (m < M) {
-          const bool full = nc + 32 <= N;
-          float v[32];
+      float* const rowsum_out = (tc.tn == 0) ? R->rowsum_a : nullptr;
+      const bool estamp = stamp && ew == 0 && lane == 0;
+      if (estamp && it < 64) dbg[it * 16 + 8] = clock64();
+      const int my_m = m_base + lane;
+      const bool row_ok = my_m < M;
+      const int rows_valid = min(32, M - m_base);              // warp-uniform (may be <= 0)
+      // Operands the epilogue needs from global memory are fetched NOW (128-bit loads, all in flight
+      // together) so that their latency hides behind this tile's MMAs:
+      //  * the ReLU mask, in row layout (thread = row), 64 B per thread per chunk
+      //  * the bias of "my" two columns per chunk (column layout is used for bias + activation)
+      uint4 mk[2][4];
+      float2 bcol[2];
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float x = __uint_as_float(r[j]);
-            if (bias && (full || nc + j < N)) x += __ldg(bias + nc + j);
-            v[j] = apply_act(x, act);
-          }
-          if (mask) {
-            const uint16_t* mrow = mask + (int64_t)m * ldmask + nc;
-            if (full) {
+      for (int c = 0; c < 2; ++c) {
+        const int nc = n0 + half * 64 + c * 32;
+        const int col = nc + 2 * (lane & 15);
+        bcol[c].x = (bias != nullptr && col < N) ? __ldg(bias + col) : 0.f;
+        bcol[c].y = (bias != nullptr && col + 1 < N) ? __ldg(bias + col + 1) : 0.f;
+        if (mask != nullptr) {
 #pragma unroll
-              for (int j8 = 0; j8 < 4; ++j8) {
-                uint4 mv = __ldg(reinterpret_cast<const uint4*>(mrow) + j8);
-                uint32_t w4[4] = {mv.x, mv.y, mv.z, mv.w};
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-                  uint32_t lo = w4[u] & 0xFFFFu, hi = w4[u] >> 16;
-                  if (!((lo & 0x8000u) == 0 && (lo & 0x7FFFu) != 0)) v[j8 * 8 + u * 2] = 0.f;
-                  if (!((hi & 0x8000u) == 0 && (hi & 0x7FFFu) != 0)) v[j8 * 8 + u * 2 + 1] = 0.f;
-                }
-              }
-            } else {
-              for (int j = 0; j < 32 && nc + j < N; ++j) {
-                uint32_t b = mrow[j];
-                if (!((b & 0x8000u) == 0 && (b & 0x7FFFu) != 0)) v[j] = 0.f;
-              }
-            }
-          }
-          if (cf) {
-            float* crow = cf + (int64_t)m * ldcf + nc;
-            if (full) {
-#pragma unroll
-              for (int j4 = 0; j4 < 8; ++j4) {
-                float4 o = make_float4(v[4 * j4], v[4 * j4 + 1], v[4 * j4 + 2], v[4 * j4 + 3]);
-                if (accumulate) {
-                  float4 old = reinterpret_cast<float4*>(crow)[j4];
-                  o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w;
-                }
-                reinterpret_cast<float4*>(crow)[j4] = o;
-              }
-            } else {
-              for (int j = 0; j < 32 && nc + j < N; ++j) crow[j] = accumulate ? crow[j] + v[j] : v[j];
-            }
-          }
-          if (cb) {
-            uint16_t* brow = cb + (int64_t)m * ldcb + nc;
-            if (full) {
-#pragma unroll
-              for (int j8 = 0; j8 < 4; ++j8) {
-                uint4 o;
-                o.x = pack_bf16x2(v[8 * j8], v[8 * j8 + 1]);
-                o.y = pack_bf16x2(v[8 * j8 + 2], v[8 * j8 + 3]);
-                o.z = pack_bf16x2(v[8 * j8 + 4], v[8 * j8 + 5]);
-                o.w = pack_bf16x2(v[8 * j8 + 6], v[8 * j8 + 7]);
-                reinterpret_cast<uint4*>(brow)[j8] = o;
-              }
-            } else {
-              for (int j = 0; j < 32 && nc + j < N; ++j) brow[j] = float_to_bf16_bits(v[j]);
+          for (int v4 = 0; v4 < 4; ++v4) {
+            mk[c][v4] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+            if (row_ok && nc + v4 * 8 + 8 <= N)
+              mk[c][v4] = __ldg(reinterpret_cast<const uint4*>(mask + (int64_t)my_m * ldmask + nc) + v4);
+            else if (row_ok && nc + v4 * 8 < N) {  // ragged tail: element-wise
+              uint32_t w[4] = {0, 0, 0, 0};
+              for (int e = 0; e < 8 && nc + v4 * 8 + e < N; ++e)
+                w[e >> 1] |= (uint32_t)mask[(int64_t)my_m * ldmask + nc + v4 * 8 + e] << ((e & 1) * 16);
+              mk[c][v4] = make_uint4(w[0], w[1], w[2], w[3]);
             }
           }
         }
       }
-      if (R->rowsum_a != nullptr && tc.tn == 0) {
+      if (estamp && it < 64) dbg[it * 16 + 9] = clock64();
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      tc_fence_after();
+      if (estamp && it < 64) dbg[it * 16 + 10] = clock64();
+      const uint32_t t_row = tmem_base + acc * TC_ACC_COLS + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int cc = half * 64 + c * 32;     // column offset inside the tile
+        const int nc = n0 + cc;
+        if (nc >= N || rows_valid <= 0) break; // warp-uniform
+        uint32_t r[32];
+        tc_ld32(t_row + cc, r);
+        tc_wait_ld();
+        if (estamp && it < 64 && c == 0) dbg[it * 16 + 12] = clock64();
+        // phase 1 (thread = row): ReLU mask on the raw accumulator, then 16 x STS.64 into the tile
+        if (mask != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {       // keep where the bf16 mask value is > 0
+            const uint4 w4 = mk[c][j >> 3];
+            const uint32_t word = ((j >> 1) & 3) == 0 ? w4.x : ((j >> 1) & 3) == 1 ? w4.y : ((j >> 1) & 3) == 2 ? w4.z : w4.w;
+            const uint32_t mb = (j & 1) ? (word >> 16) : (word & 0xFFFFu);
+            if (!((mb & 0x8000u) == 0 && (mb & 0x7FFFu) != 0)) r[j] = 0u;
+          }
+        }
+        float2* srow = reinterpret_cast<float2*>(my_stage + lane * TC_STAGE_LD);
+#pragma unroll
+        for (int j2 = 0; j2 < 16; ++j2) srow[j2] = make_float2(__uint_as_float(r[2 * j2]), __uint_as_float(r[2 * j2 + 1]));
+        __syncwarp();
+        if (estamp && it < 64 && c == 0) dbg[it * 16 + 13] = clock64();
+        // phase 2 (thread = column pair; lanes 0-15 row 2i, lanes 16-31 row 2i+1): bias + activation,
+        // read-modify-write, coalesced 8-byte fp32 / 4-byte bf16x2 stores
+        const int sub = lane >> 4;
+        const int col = nc + 2 * (lane & 15);
+        const float2* sread = reinterpret_cast<const float2*>(my_stage + sub * TC_STAGE_LD + 2 * (lane & 15));
+        float* pf = cf ? cf + (int64_t)(m_base + sub) * ldcf + col : nullptr;
+        uint16_t* pb = cb ? cb + (int64_t)(m_base + sub) * ldcb + col : nullptr;
+        const float bx = bcol[c].x, by = bcol[c].y;
+        const bool fast = rows_valid == 32 && nc + 32 <= N && (act == MMLREC_ACT_NONE || act == MMLREC_ACT_RELU) &&
+                          (cf == nullptr || (ldcf & 1) == 0) && (cb == nullptr || (ldcb & 1) == 0);   // warp-uniform
+        if (fast) {
+          const int kind = (act == MMLREC_ACT_RELU ? 8 : 0) | (cf ? 4 : 0) | (cb ? 2 : 0) | ((cf && accumulate) ? 1 : 0);
+          switch (kind) {
+            case 4:  store_chunk_fast<false, true, false, false>(sread, pf, ldcf, pb, ldcb, bx, by); break;
+            case 5:  store_chunk_fast<false, true, false, true>(sread, pf, ldcf, pb, ldcb, bx, by); break;
+            case 2:  store_chunk_fast<false, false, true, false>(sread, pf, ldcf, pb, ldcb, bx, by); break;
+            case 6:  store_chunk_fast<false, true, true, false>(sread, pf, ldcf, pb, ldcb, bx, by); break;
+            case 7:  store_chunk_fast<false, true, true, true>(sread, pf, ldcf, pb, ldcb, bx, by); break;
+            case 12: store_chunk_fast<true, true, false, false>(sread, pf, ldcf, pb, ldcb, bx, by); break;
+            case 10: store_chunk_fast<true, false, true, false>(sread, pf, ldcf, pb, ldcb, bx, by); break;
+            case 14: store_chunk_fast<true, true, true, false>(sread, pf, ldcf, pb, ldcb, bx, by); break;
+            case 13: store_chunk_fast<true, true, false, true>(sread, pf, ldcf, pb, ldcb, bx, by); break;
+            case 15: store_chunk_fast<true, true, true, true>(sread, pf, ldcf, pb, ldcb, bx, by); break;
+            default: break;  // unreachable: a problem always has at least one output
+          }
+        } else {
+          const bool c0 = col < N, c1 = col + 1 < N;
+          const bool vec_f = c1 && ((ldcf & 1) == 0), vec_b = c1 && ((ldcb & 1) == 0);
+#pragma unroll 1
+          for (int i = 0; i < 16; ++i) {
+            const int rr = 2 * i + sub;
+            float2 x = sread[i * TC_STAGE_LD];
+            x.x += bx; x.y += by;
+            if (act == MMLREC_ACT_RELU) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); }
+            else if (act != MMLREC_ACT_NONE) { x.x = apply_act(x.x, act); x.y = apply_act(x.y, act); }
+            if (rr < rows_valid && c0) {
+              if (pf) {
+                if (vec_f) {
+                  float2* d = reinterpret_cast<float2*>(pf);
+                  if (accumulate) { const float2 o = *d; x.x += o.x; x.y += o.y; }
+                  *d = x;
+                } else {
+                  if (accumulate) { x.x += pf[0]; if (c1) x.y += pf[1]; }
+                  pf[0] = x.x;
+                  if (c1) pf[1] = x.y;
+                }
+              }
+              if (pb) {
+                if (vec_b) *reinterpret_cast<uint32_t*>(pb) = pack_bf16x2(x.x, x.y);
+                else { pb[0] = float_to_bf16_bits(x.x); if (c1) pb[1] = float_to_bf16_bits(x.y); }
+              }
+            }
+            if (pf) pf += 2 * ldcf;
+            if (pb) pb += 2 * ldcb;
+          }
+        }
+        __syncwarp();
+        if (estamp && it < 64 && c == 0) dbg[it * 16 + 14] = clock64();
+      }
+      if (estamp && it < 64) dbg[it * 16 + 11] = clock64();
+      if (rowsum_out != nullptr && half == 0) {
         uint32_t rs;
         tc_ld1(t_row + TC_BN, rs);
         tc_wait_ld();
-        if (m < M) R->rowsum_a[m] = __uint_as_float(rs);
+        if (m_base + lane < M) rowsum_out[m_base + lane] = __uint_as_float(rs);
       }
       tc_fence_before();
       __syncwarp();
@@ -419,10 +527,11 @@ extern "C" int mmlrec_tc_encode_problem(const MmlrecGemmTcDesc* d, void* record_
   return 0;
 }
 
-extern "C" int mmlrec_gemm_grouped_tc(const void* records, const int32_t* tile_prefix, int32_t n_problems,
-                                      int32_t total_tiles, void* stream) {
+static int launch_tc(const void* records, const int32_t* tile_prefix, int32_t n_problems, int32_t total_tiles,
+                     long long* dbg, void* stream) {
   MMLREC_CHECK_ARG(records && tile_prefix && n_problems > 0 && total_tiles >= 0, "bad args");
   MMLREC_CHECK_ARG(((uintptr_t)records & 127) == 0, "record table must be 128-byte aligned");
+  MMLREC_CHECK_ARG(n_problems <= TC_MAX_PROBLEMS, "too many problems in one launch (split the table)");
   if (total_tiles == 0) return 0;
   static int sm_count = 0;
   static bool opted = false;
@@ -436,6 +545,16 @@ extern "C" int mmlrec_gemm_grouped_tc(const void* records, const int32_t* tile_p
   }
   int grid = total_tiles < sm_count ? total_tiles : sm_count;
   gemm_grouped_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(
-      reinterpret_cast<const TcRecord*>(records), tile_prefix, n_problems, total_tiles);
+      reinterpret_cast<const TcRecord*>(records), tile_prefix, n_problems, total_tiles, dbg);
   MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_gemm_grouped_tc(const void* records, const int32_t* tile_prefix, int32_t n_problems,
+                                      int32_t total_tiles, void* stream) {
+  return launch_tc(records, tile_prefix, n_problems, total_tiles, nullptr, stream);
+}
+
+extern "C" int mmlrec_gemm_grouped_tc_debug(const void* records, const int32_t* tile_prefix, int32_t n_problems,
+                                            int32_t total_tiles, int64_t* stamps, void* stream) {
+  return launch_tc(records, tile_prefix, n_problems, total_tiles, reinterpret_cast<long long*>(stamps), stream);
 }

@@ -345,7 +345,7 @@ class LinearStage(Stage):
                 p.M, p.N, p.K, p.act = b.B, g.N, g.K, act_code
                 probs.append(p)
             pre, tiles = _tile_prefix_f32(probs)
-            self.fwd = (b.table(probs), b.ints(pre), len(probs), tiles)
+            self.fwd = [(b.table(probs), b.ints(pre), len(probs), tiles)]
         else:
             descs = []
             for g in self.groups:
@@ -360,10 +360,15 @@ class LinearStage(Stage):
                 d.bias = g.b.data_ptr() if g.b is not None else None
                 d.act = act_code
                 descs.append(d)
-            self.fwd = b.tc_table(descs)
+            self.fwd = self._tc_tables(descs)
         if self.use_bn:
             n_total = _align(yg.total, 4)
             self.save_mean, self.save_invstd = b.zeros(n_total), b.zeros(n_total)
+
+    MAX_TC_PROBLEMS = 96  # the tensor-core kernel caches its tile table in shared memory
+
+    def _tc_tables(self, descs):
+        return [self.b.tc_table(descs[i:i + self.MAX_TC_PROBLEMS]) for i in range(0, len(descs), self.MAX_TC_PROBLEMS)]
 
     def _launch(self, tbl, stream, what):
         fn = self.b.lib.mmlrec_gemm_grouped_tc if self.b.tc else self.b.lib.mmlrec_gemm_grouped_f32
@@ -371,7 +376,8 @@ class LinearStage(Stage):
 
     def forward(self, stream, training):
         b = self.b
-        self._launch(self.fwd, stream, "linear fwd")
+        for tbl in self.fwd:
+            self._launch(tbl, stream, "linear fwd")
         if self.use_bn:
             zg, yg = self.zs[0].group, self.outs[0].group
             for g in self.groups:
@@ -454,7 +460,7 @@ class LinearStage(Stage):
             if not wv:
                 continue
             if b.tc:
-                self.bwd.append(b.tc_table(wv))
+                self.bwd.extend(self._tc_tables(wv))
             else:
                 pre, tiles = _tile_prefix_f32(wv)
                 self.bwd.append((b.table(wv), b.ints(pre), len(wv), tiles))
