@@ -36,7 +36,7 @@ int         mmlrec_abi_version(void);
 const char* mmlrec_last_error(void);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 int64_t     mmlrec_launch_count(void);
-/* sizeof of ABI struct `which` (0 Hyper, 1 GemmF32, 2 GemmTcDesc, 3 Gate, 4 ExpertGrad, 5 Head) */
+/* sizeof of ABI struct `which` (0 Hyper, 1 GemmF32, 2 GemmTcDesc, 3 Gate, 4 ExpertGrad, 5 Head, 6 GateLevel) */
 int64_t     mmlrec_struct_size(int32_t which);
 
 /* ---------------------------------------------------------------------------------------------
@@ -228,6 +228,40 @@ int mmlrec_gate_mix_backward(const MmlrecGate* gates, int32_t n_gates,
                              void* stream);
 /* scratch floats needed by mmlrec_gate_mix_backward (max_ne / max_hg: maxima over the gate table) */
 int64_t mmlrec_gate_mix_backward_scratch(int32_t n_gates, int32_t max_ne, int32_t max_hg, int32_t B);
+
+/* Row-fused variant of the same stage (the fast path): one record describes ALL gates of a level and
+ * the level's distinct expert activations; a warp owns a sample, reads every expert row exactly once
+ * and produces every gate's mixture (forward) or every d(expert), d(gate_in) and dWg contribution
+ * (backward) in one pass.  Limits: n_gates <= 8, n_experts <= 32, H % 4 == 0, and
+ * sum_g n_e[g]*Hg[g] <= MMLREC_LEVEL_MAX_WG floats (gate-head weights are staged in shared memory);
+ * callers fall back to mmlrec_gate_mix_* otherwise. */
+#define MMLREC_LEVEL_MAX_GATES 8
+#define MMLREC_LEVEL_MAX_EXPERTS 32
+#define MMLREC_LEVEL_MAX_WG 3072
+typedef struct MmlrecGateLevel {
+  int32_t n_gates, n_experts, H, expert_relu;                     /* expert_relu: mask d(expert) by expert > 0 */
+  const float* expert[MMLREC_LEVEL_MAX_EXPERTS]; int64_t ld_expert;
+  float* d_expert[MMLREC_LEVEL_MAX_EXPERTS]; int64_t ld_d_expert;            /* backward outputs: fp32 ... */
+  uint16_t* d_expert_bf16[MMLREC_LEVEL_MAX_EXPERTS]; int64_t ld_d_expert_bf16; /* ... or bf16 (either may be NULL) */
+  int8_t slot[MMLREC_LEVEL_MAX_EXPERTS][MMLREC_LEVEL_MAX_GATES];  /* position of expert u in gate g's softmax, -1 if unused */
+  const float* gate_in[MMLREC_LEVEL_MAX_GATES]; int64_t ld_gate_in[MMLREC_LEVEL_MAX_GATES];
+  const float* Wg[MMLREC_LEVEL_MAX_GATES]; int64_t ld_Wg[MMLREC_LEVEL_MAX_GATES];
+  int32_t Hg[MMLREC_LEVEL_MAX_GATES]; int32_t n_e[MMLREC_LEVEL_MAX_GATES];
+  float* probs[MMLREC_LEVEL_MAX_GATES];
+  float* mix[MMLREC_LEVEL_MAX_GATES]; int64_t ld_mix[MMLREC_LEVEL_MAX_GATES];
+  uint16_t* mix_bf16[MMLREC_LEVEL_MAX_GATES]; int64_t ld_mix_bf16[MMLREC_LEVEL_MAX_GATES];
+  const float* d_mix[MMLREC_LEVEL_MAX_GATES]; int64_t ld_d_mix[MMLREC_LEVEL_MAX_GATES];   /* NULL: gate gets no gradient */
+  float* d_gate_in[MMLREC_LEVEL_MAX_GATES]; int64_t ld_d_gate_in[MMLREC_LEVEL_MAX_GATES];
+  uint16_t* d_gate_in_bf16[MMLREC_LEVEL_MAX_GATES]; int64_t ld_d_gate_in_bf16[MMLREC_LEVEL_MAX_GATES];
+  int32_t relu_mask_gate_in[MMLREC_LEVEL_MAX_GATES]; int32_t accumulate_d_gate_in[MMLREC_LEVEL_MAX_GATES];
+  float* dWg[MMLREC_LEVEL_MAX_GATES];
+} MmlrecGateLevel;
+int mmlrec_gate_level_forward(const MmlrecGateLevel* level, int32_t B, void* stream);
+int mmlrec_gate_level_backward(const MmlrecGateLevel* level, int32_t B, int32_t total_wg /* sum_g n_e[g]*Hg[g] */,
+                               int32_t total_ne /* sum_g n_e[g] */, int32_t total_hg /* sum_g Hg[g] */,
+                               float* scratch, int32_t* counter /* one int32, zero-initialised once */, void* stream);
+/* scratch floats for mmlrec_gate_level_backward */
+int64_t mmlrec_gate_level_backward_scratch(int32_t total_wg, int32_t B);
 
 /* ---------------------------------------------------------------------------------------------
  * Heads + loss, forward and backward in one pass (training) or forward only (predict).

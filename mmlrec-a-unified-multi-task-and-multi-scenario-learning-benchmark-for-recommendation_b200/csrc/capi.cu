@@ -33,6 +33,7 @@ extern "C" int64_t mmlrec_struct_size(int32_t which) {
     case 3: return sizeof(MmlrecGate);
     case 4: return sizeof(MmlrecExpertGrad);
     case 5: return sizeof(MmlrecHead);
+    case 6: return sizeof(MmlrecGateLevel);
     default: return -1;
   }
 }

@@ -1,0 +1,326 @@
+// Row-fused gate stage (fast path of model/mmoe.py:80-88 / model/ple.py:127-152 and their backward).
+// A warp owns one sample.  Forward: logits of every gate of the level against gate-head weights staged
+// in shared memory, softmax in registers (lane e <-> expert slot e), then ONE pass over the level's
+// distinct expert rows (128-bit loads) accumulating every gate's mixture.  Backward: ONE pass over the
+// expert rows produces d(expert) (sum over the gates that use it, ReLU-masked) and the softmax input
+// gradients; d(gate_in) and the per-warp dWg slabs follow; CTA partials of dWg are reduced by the last
+// CTA in a fixed order (deterministic, no float atomics).  HBM/L2-bound: every activation row of the
+// level is read once and every output row written once.
+#include "common.cuh"
+
+namespace mmlrec {
+
+constexpr int GL_MAXG = MMLREC_LEVEL_MAX_GATES;
+constexpr int GL_FWD_WARPS = 8;            // forward: 8 warps x 1 sample
+constexpr int GL_BWD_WARPS = 16;           // backward: 16 warps x 2 samples = 32 samples per CTA
+constexpr int GL_BWD_ROWS = 32;
+constexpr int GL_BATCH = 8;                // expert rows fetched together (8 x 128-bit loads in flight per lane)
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+
+// logits + softmax of gate g for sample b: returns this lane's probability (lane e <-> slot e)
+__device__ __forceinline__ float gate_probs(const MmlrecGateLevel& L, int g, int b, const float* wg_s, int lane) {
+  const int Hg = L.Hg[g], ne = L.n_e[g];
+  const float* gin = L.gate_in[g] + (int64_t)b * L.ld_gate_in[g];
+  float logit = -INFINITY;
+  for (int e0 = 0; e0 < ne; e0 += 4) {      // four independent dot products in flight
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    const int e1 = min(e0 + 1, ne - 1), e2 = min(e0 + 2, ne - 1), e3 = min(e0 + 3, ne - 1);
+    for (int h = lane; h < Hg; h += 32) {
+      const float x = gin[h];
+      s0 = fmaf(x, wg_s[e0 * Hg + h], s0);
+      s1 = fmaf(x, wg_s[e1 * Hg + h], s1);
+      s2 = fmaf(x, wg_s[e2 * Hg + h], s2);
+      s3 = fmaf(x, wg_s[e3 * Hg + h], s3);
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1); s2 = warp_sum(s2); s3 = warp_sum(s3);
+    if (lane == e0) logit = s0;
+    if (lane == e0 + 1 && e0 + 1 < ne) logit = s1;
+    if (lane == e0 + 2 && e0 + 2 < ne) logit = s2;
+    if (lane == e0 + 3 && e0 + 3 < ne) logit = s3;
+  }
+  float mx = logit;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  const float ex = lane < ne ? expf(logit - mx) : 0.f;
+  return ex / warp_sum(ex);
+}
+
+__device__ __forceinline__ void stage_level(const MmlrecGateLevel* lv, MmlrecGateLevel& L, float* wg_s, int* wg_off) {
+  const int n_words = sizeof(MmlrecGateLevel) / 4;
+  for (int i = threadIdx.x; i < n_words; i += blockDim.x)
+    reinterpret_cast<uint32_t*>(&L)[i] = reinterpret_cast<const uint32_t*>(lv)[i];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    int at = 0;
+    for (int g = 0; g < L.n_gates; ++g) { wg_off[g] = at; at += L.n_e[g] * L.Hg[g]; }
+    wg_off[L.n_gates] = at;
+  }
+  __syncthreads();
+  for (int g = 0; g < L.n_gates; ++g) {
+    const int Hg = L.Hg[g];
+    for (int i = threadIdx.x; i < L.n_e[g] * Hg; i += blockDim.x)
+      wg_s[wg_off[g] + i] = L.Wg[g][(int64_t)(i / Hg) * L.ld_Wg[g] + (i % Hg)];
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(GL_FWD_WARPS * 32) gate_level_forward_kernel(const MmlrecGateLevel* lv, int B) {
+  __shared__ MmlrecGateLevel L;
+  __shared__ float wg_s[MMLREC_LEVEL_MAX_WG];
+  __shared__ int wg_off[GL_MAXG + 1];
+  stage_level(lv, L, wg_s, wg_off);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int G = L.n_gates, H = L.H;
+  const int b = blockIdx.x * GL_FWD_WARPS + w;
+  if (b >= B) return;  // warp-uniform; no block-level sync follows
+  float pg[GL_MAXG];
+#pragma unroll
+  for (int g = 0; g < GL_MAXG; ++g) {
+    pg[g] = 0.f;
+    if (g < G) {
+      pg[g] = gate_probs(L, g, b, wg_s + wg_off[g], lane);
+      if (lane < L.n_e[g]) L.probs[g][(int64_t)b * L.n_e[g] + lane] = pg[g];
+    }
+  }
+  for (int h0 = 0; h0 < H; h0 += 128) {
+    const int h = h0 + lane * 4;
+    const bool hv = h < H;
+    float4 acc[GL_MAXG];
+#pragma unroll
+    for (int g = 0; g < GL_MAXG; ++g) acc[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int u0 = 0; u0 < L.n_experts; u0 += GL_BATCH) {
+      float4 eo[GL_BATCH];
+#pragma unroll
+      for (int k = 0; k < GL_BATCH; ++k)   // all loads of the batch are issued before any use
+        eo[k] = (hv && u0 + k < L.n_experts) ? ld4(L.expert[u0 + k] + (int64_t)b * L.ld_expert + h)
+                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int k = 0; k < GL_BATCH; ++k) {
+        if (u0 + k >= L.n_experts) break;  // warp-uniform
+#pragma unroll
+        for (int g = 0; g < GL_MAXG; ++g) {
+          const int slot = g < G ? L.slot[u0 + k][g] : -1;  // warp-uniform
+          if (slot >= 0) {
+            const float p = __shfl_sync(0xffffffffu, pg[g], slot);
+            acc[g].x = fmaf(p, eo[k].x, acc[g].x); acc[g].y = fmaf(p, eo[k].y, acc[g].y);
+            acc[g].z = fmaf(p, eo[k].z, acc[g].z); acc[g].w = fmaf(p, eo[k].w, acc[g].w);
+          }
+        }
+      }
+    }
+    if (hv) {
+#pragma unroll
+      for (int g = 0; g < GL_MAXG; ++g) {
+        if (g < G) {
+          *reinterpret_cast<float4*>(L.mix[g] + (int64_t)b * L.ld_mix[g] + h) = acc[g];
+          if (L.mix_bf16[g]) {
+            uint2 o;
+            o.x = pack_bf16x2(acc[g].x, acc[g].y);
+            o.y = pack_bf16x2(acc[g].z, acc[g].w);
+            *reinterpret_cast<uint2*>(L.mix_bf16[g] + (int64_t)b * L.ld_mix_bf16[g] + h) = o;
+          }
+        }
+      }
+    }
+  }
+}
+
+// dynamic smem: dl_s [32 rows][total_ne] + gin_s [32 rows][total_hg]   (total_ne = sum n_e, total_hg = sum Hg)
+__global__ void __launch_bounds__(GL_BWD_WARPS * 32)
+gate_level_backward_kernel(const MmlrecGateLevel* lv, int B, float* scratch, int32_t* counter) {
+  extern __shared__ __align__(16) float dyn_s[];
+  __shared__ MmlrecGateLevel L;
+  __shared__ float wg_s[MMLREC_LEVEL_MAX_WG];
+  __shared__ int wg_off[GL_MAXG + 1], ne_off[GL_MAXG + 1], hg_off[GL_MAXG + 1];
+  __shared__ int s_last;
+  stage_level(lv, L, wg_s, wg_off);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int G = L.n_gates, H = L.H;
+  if (threadIdx.x == 0) {
+    int a = 0, c = 0;
+    for (int g = 0; g < G; ++g) { ne_off[g] = a; hg_off[g] = c; a += L.n_e[g]; c += L.Hg[g]; }
+    ne_off[G] = a; hg_off[G] = c;
+  }
+  __syncthreads();
+  const int total_wg = wg_off[G], total_ne = ne_off[G], total_hg = hg_off[G];
+  float* dl_s = dyn_s;                            // [32][total_ne]
+  float* gin_s = dyn_s + GL_BWD_ROWS * total_ne;  // [32][total_hg]
+  const int r0 = blockIdx.x * GL_BWD_ROWS;
+  for (int rr = 0; rr < 2; ++rr) {
+    const int r = w * 2 + rr;
+    const int b = r0 + r;
+    if (b >= B) {  // rows past the batch contribute zeros to the CTA partial
+      for (int i = lane; i < total_ne; i += 32) dl_s[r * total_ne + i] = 0.f;
+      for (int i = lane; i < total_hg; i += 32) gin_s[r * total_hg + i] = 0.f;
+      continue;
+    }
+    float pg[GL_MAXG], dp[GL_MAXG];
+    bool live[GL_MAXG];
+#pragma unroll
+    for (int g = 0; g < GL_MAXG; ++g) {
+      live[g] = g < G && L.d_mix[g] != nullptr;
+      pg[g] = (live[g] && lane < L.n_e[g]) ? L.probs[g][(int64_t)b * L.n_e[g] + lane] : 0.f;
+      dp[g] = 0.f;
+    }
+    // one pass over the expert rows: d(expert) and the softmax-input dot products
+    for (int h0 = 0; h0 < H; h0 += 128) {
+      const int h = h0 + lane * 4;
+      const bool hv = h < H;
+      float4 dm[GL_MAXG];
+#pragma unroll
+      for (int g = 0; g < GL_MAXG; ++g)
+        dm[g] = (live[g] && hv) ? ld4(L.d_mix[g] + (int64_t)b * L.ld_d_mix[g] + h) : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int u0 = 0; u0 < L.n_experts; u0 += GL_BATCH) {
+        float4 eo[GL_BATCH];
+#pragma unroll
+        for (int k = 0; k < GL_BATCH; ++k)
+          eo[k] = (hv && u0 + k < L.n_experts) ? ld4(L.expert[u0 + k] + (int64_t)b * L.ld_expert + h)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int k = 0; k < GL_BATCH; ++k) {
+          const int u = u0 + k;
+          if (u >= L.n_experts) break;  // warp-uniform
+          float4 de = make_float4(0.f, 0.f, 0.f, 0.f);
+          bool used = false;
+#pragma unroll
+          for (int g = 0; g < GL_MAXG; ++g) {
+            const int slot = live[g] ? L.slot[u][g] : -1;  // warp-uniform
+            if (slot >= 0) {
+              used = true;
+              const float p = __shfl_sync(0xffffffffu, pg[g], slot);
+              de.x = fmaf(p, dm[g].x, de.x); de.y = fmaf(p, dm[g].y, de.y);
+              de.z = fmaf(p, dm[g].z, de.z); de.w = fmaf(p, dm[g].w, de.w);
+              const float s = warp_sum(dot4(dm[g], eo[k]));
+              if (lane == slot) dp[g] += s;
+            }
+          }
+          if (used && hv) {
+            if (L.expert_relu) {
+              if (!(eo[k].x > 0.f)) de.x = 0.f;
+              if (!(eo[k].y > 0.f)) de.y = 0.f;
+              if (!(eo[k].z > 0.f)) de.z = 0.f;
+              if (!(eo[k].w > 0.f)) de.w = 0.f;
+            }
+            if (L.d_expert[u]) *reinterpret_cast<float4*>(L.d_expert[u] + (int64_t)b * L.ld_d_expert + h) = de;
+            if (L.d_expert_bf16[u]) {
+              uint2 o;
+              o.x = pack_bf16x2(de.x, de.y);
+              o.y = pack_bf16x2(de.z, de.w);
+              *reinterpret_cast<uint2*>(L.d_expert_bf16[u] + (int64_t)b * L.ld_d_expert_bf16 + h) = o;
+            }
+          }
+        }
+      }
+    }
+    // softmax backward, d(gate_in); dlogits and gate inputs are staged for the CTA-wide dWg partial
+#pragma unroll
+    for (int g = 0; g < GL_MAXG; ++g) {
+      if (g >= G) continue;
+      const int Hg = L.Hg[g], ne = L.n_e[g];
+      float dl = 0.f;
+      if (live[g]) {
+        const float dot = warp_sum(pg[g] * dp[g]);
+        dl = pg[g] * (dp[g] - dot);   // lane e <-> d logit e (0 for lanes >= n_e)
+      }
+      if (lane < ne) dl_s[r * total_ne + ne_off[g] + lane] = dl;
+      const float* gin = L.gate_in[g] + (int64_t)b * L.ld_gate_in[g];
+      const float* wg = wg_s + wg_off[g];
+      for (int h0 = 0; h0 < Hg; h0 += 32) {   // uniform trip count (shuffles inside)
+        const int h = h0 + lane;
+        const bool hv = h < Hg;
+        const float gv = hv ? gin[h] : 0.f;
+        if (hv) gin_s[r * total_hg + hg_off[g] + h] = gv;
+        if (!live[g]) continue;  // warp-uniform
+        float acc = 0.f;
+        for (int e = 0; e < ne; ++e) {
+          const float de = __shfl_sync(0xffffffffu, dl, e);
+          if (hv) acc = fmaf(de, wg[e * Hg + h], acc);
+        }
+        if (hv) {
+          if (L.relu_mask_gate_in[g] && !(gv > 0.f)) acc = 0.f;
+          if (L.d_gate_in[g]) {
+            float* dst = L.d_gate_in[g] + (int64_t)b * L.ld_d_gate_in[g] + h;
+            if (L.accumulate_d_gate_in[g]) acc += *dst;
+            *dst = acc;
+          }
+          if (L.d_gate_in_bf16[g]) L.d_gate_in_bf16[g][(int64_t)b * L.ld_d_gate_in_bf16[g] + h] = float_to_bf16_bits(acc);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // CTA partial of dWg[g][e][h] = sum over the 32 staged samples of dl[r][e] * gin[r][h]  (fixed order)
+  float* part = scratch + (int64_t)blockIdx.x * total_wg;
+  for (int i = threadIdx.x; i < total_wg; i += blockDim.x) {
+    int g = 0;
+    while (g + 1 < G && wg_off[g + 1] <= i) ++g;
+    const int local = i - wg_off[g], Hg = L.Hg[g];
+    const int e = local / Hg, h = local - e * Hg;
+    const float* dlp = dl_s + ne_off[g] + e;
+    const float* gp = gin_s + hg_off[g] + h;
+    float s = 0.f;
+#pragma unroll 8
+    for (int r = 0; r < GL_BWD_ROWS; ++r) s = fmaf(dlp[r * total_ne], gp[r * total_hg], s);
+    part[i] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int t = atomicAdd(counter, 1);
+    s_last = (t == (int)gridDim.x - 1) ? 1 : 0;
+    if (s_last) *counter = 0;
+  }
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  for (int i = threadIdx.x; i < total_wg; i += blockDim.x) {
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // four independent chains (fixed association)
+    int c = 0;
+    for (; c + 3 < (int)gridDim.x; c += 4) {
+      s0 += scratch[(int64_t)c * total_wg + i];
+      s1 += scratch[(int64_t)(c + 1) * total_wg + i];
+      s2 += scratch[(int64_t)(c + 2) * total_wg + i];
+      s3 += scratch[(int64_t)(c + 3) * total_wg + i];
+    }
+    for (; c < (int)gridDim.x; ++c) s0 += scratch[(int64_t)c * total_wg + i];
+    const float s = (s0 + s1) + (s2 + s3);
+    int g = 0;
+    while (g + 1 < G && wg_off[g + 1] <= i) ++g;
+    if (L.d_mix[g] != nullptr) {
+      const int local = i - wg_off[g], Hg = L.Hg[g];
+      L.dWg[g][(int64_t)(local / Hg) * L.ld_Wg[g] + (local % Hg)] = s;
+    }
+  }
+}
+
+}  // namespace mmlrec
+
+using namespace mmlrec;
+
+extern "C" int mmlrec_gate_level_forward(const MmlrecGateLevel* level, int32_t B, void* stream) {
+  MMLREC_CHECK_ARG(level && B > 0, "bad args");
+  gate_level_forward_kernel<<<cdiv(B, GL_FWD_WARPS), GL_FWD_WARPS * 32, 0, (cudaStream_t)stream>>>(level, B);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int64_t mmlrec_gate_level_backward_scratch(int32_t total_wg, int32_t B) {
+  return (int64_t)cdiv(B, GL_BWD_ROWS) * total_wg;
+}
+
+extern "C" int mmlrec_gate_level_backward(const MmlrecGateLevel* level, int32_t B, int32_t total_wg, int32_t total_ne,
+                                          int32_t total_hg, float* scratch, int32_t* counter, void* stream) {
+  MMLREC_CHECK_ARG(level && B > 0 && scratch && counter, "bad args");
+  MMLREC_CHECK_ARG(total_wg > 0 && total_wg <= MMLREC_LEVEL_MAX_WG && total_ne > 0 && total_hg > 0, "sizes out of range");
+  const size_t smem = (size_t)GL_BWD_ROWS * (total_ne + total_hg) * sizeof(float);   // staged dlogits + gate inputs
+  MMLREC_CHECK_ARG(smem <= 160 * 1024, "gate inputs too wide for the fused kernel");
+  static size_t opted = 0;   // static (record + staged weights) + dynamic shared memory can exceed 48 KB
+  if (smem + 16 * 1024 > 48 * 1024 && smem > opted) {
+    cudaError_t e = cudaFuncSetAttribute(gate_level_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("gate_level_backward: smem opt-in failed"); return (int)e; }
+    opted = smem;
+  }
+  gate_level_backward_kernel<<<cdiv(B, GL_BWD_ROWS), GL_BWD_WARPS * 32, smem, (cudaStream_t)stream>>>(level, B, scratch, counter);
+  MMLREC_RETURN_LAUNCH(1);
+}

@@ -136,24 +136,39 @@ __device__ __forceinline__ uint32_t make_idesc(int M, int N, bool a_mn, bool b_m
 
 // Branch-free store of one full 32x32 chunk from the transpose tile (lane = column pair, lanes 0-15 even
 // rows, lanes 16-31 odd rows): bias (+ReLU), optional read-modify-write, 8-byte fp32 / 4-byte bf16x2 stores.
+__device__ __forceinline__ void st_global_f2(float* p, float2 v) {
+  asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
+}
+__device__ __forceinline__ void st_global_u32(void* p, uint32_t v) {
+  asm volatile("st.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ float2 ld_global_f2(const float* p) {
+  float2 v;
+  asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
+  return v;
+}
+
 template <bool RELU, bool F32, bool BF16, bool ACC>
 __device__ __forceinline__ void store_chunk_fast(const float2* __restrict__ sread, float* __restrict__ pf, int64_t ldcf,
                                                  uint16_t* __restrict__ pb, int64_t ldcb, float bx, float by) {
+  // all shared-memory reads first (explicit global-space stores below cannot alias them, but a generic
+  // store would make the compiler serialise LDS -> math -> store per row)
+  float2 x[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) x[i] = sread[i * TC_STAGE_LD];
   float2 old[16];
   if (F32 && ACC) {
 #pragma unroll
-    for (int i = 0; i < 16; ++i) old[i] = *reinterpret_cast<const float2*>(pf + (int64_t)(2 * i) * ldcf);
+    for (int i = 0; i < 16; ++i) old[i] = ld_global_f2(pf + (int64_t)(2 * i) * ldcf);
   }
 #pragma unroll
   for (int i = 0; i < 16; ++i) {
-    float2 x = sread[i * TC_STAGE_LD];
-    x.x += bx; x.y += by;
-    if (RELU) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); }
-    if (F32) {
-      if (ACC) { x.x += old[i].x; x.y += old[i].y; }
-      *reinterpret_cast<float2*>(pf + (int64_t)(2 * i) * ldcf) = x;
-    }
-    if (BF16) *reinterpret_cast<uint32_t*>(pb + (int64_t)(2 * i) * ldcb) = pack_bf16x2(x.x, x.y);
+    float2 v = x[i];
+    v.x += bx; v.y += by;
+    if (RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
+    if (F32 && ACC) { v.x += old[i].x; v.y += old[i].y; }
+    if (F32) st_global_f2(pf + (int64_t)(2 * i) * ldcf, v);
+    if (BF16) st_global_u32(pb + (int64_t)(2 * i) * ldcb, pack_bf16x2(v.x, v.y));
   }
 }
 

@@ -66,6 +66,7 @@ class Act:
     def __init__(self, group: ActGroup, col: int, width: int, name: str):
         self.group, self.col, self.width, self.name = group, col, width, name
         self.grad_written = False
+        self.need_f32 = self.need_bf16 = False   # which copies THIS activation's consumers read
 
     relu = property(lambda self: self.group.relu)
     # fp32 view
@@ -93,6 +94,8 @@ class Act:
         return g[:, self.col:self.col + self.width]
 
     def want(self, f32: bool = False, bf16: bool = False) -> "Act":
+        self.need_f32 |= f32
+        self.need_bf16 |= bf16
         self.group.need_f32 |= f32
         self.group.need_bf16 |= bf16
         return self
@@ -347,19 +350,37 @@ class LinearStage(Stage):
             pre, tiles = _tile_prefix_f32(probs)
             self.fwd = [(b.table(probs), b.ints(pre), len(probs), tiles)]
         else:
+            # forward problems may be narrower than the merged group: a run of members whose consumers
+            # read the same copies (e.g. expert hidden -> bf16 only, gate hidden -> fp32 only) becomes one
+            # problem, so no column is written in a precision nobody reads
             descs = []
             for g in self.groups:
-                d = L.GemmTcDesc()
-                d.A, d.lda, d.a_mn_major = g.x.ptr16, g.x.ld16, 0
-                d.B, d.ldb, d.b_mn_major = st.bf16_ptr(g.W), g.W._mm_ld, 0
-                d.M, d.N, d.K = b.B, g.N, g.K
-                if tgt.buf is not None:
-                    d.C_f32, d.ldc_f32 = tgt.buf.data_ptr() + 4 * g.y_col, tgt.buf.stride(0)
-                if tgt.buf16 is not None:
-                    d.C_bf16, d.ldc_bf16 = tgt.buf16.data_ptr() + 2 * g.y_col, tgt.buf16.stride(0)
-                d.bias = g.b.data_ptr() if g.b is not None else None
-                d.act = act_code
-                descs.append(d)
+                runs, at = [], 0
+                for m, o in zip(g.members, g.outs):
+                    if self.use_bn:
+                        key = (True, False)  # the pre-BatchNorm buffer is fp32
+                    else:
+                        key = (o.need_f32, o.need_bf16)
+                        if not (key[0] or key[1]):  # produced but never read: write whichever copy exists
+                            key = (tgt.buf16 is None, tgt.buf16 is not None)
+                    if runs and runs[-1][0] == key:
+                        runs[-1][2] += m.N
+                    else:
+                        runs.append([key, at, m.N])
+                    at += m.N
+                for (f32, bf16), off, n in runs:
+                    d = L.GemmTcDesc()
+                    d.A, d.lda, d.a_mn_major = g.x.ptr16, g.x.ld16, 0
+                    d.B, d.ldb, d.b_mn_major = st.bf16_ptr(g.W) + 2 * off * g.W._mm_ld, g.W._mm_ld, 0
+                    d.M, d.N, d.K = b.B, n, g.K
+                    col = g.y_col + off
+                    if f32:
+                        d.C_f32, d.ldc_f32 = tgt.buf.data_ptr() + 4 * col, tgt.buf.stride(0)
+                    if bf16:
+                        d.C_bf16, d.ldc_bf16 = tgt.buf16.data_ptr() + 2 * col, tgt.buf16.stride(0)
+                    d.bias = (g.b.data_ptr() + 4 * off) if g.b is not None else None
+                    d.act = act_code
+                    descs.append(d)
             self.fwd = self._tc_tables(descs)
         if self.use_bn:
             n_total = _align(yg.total, 4)
@@ -527,7 +548,69 @@ class GateMixStage(Stage):
 
     def finalize(self):
         self.probs = [self.b.zeros(self.b.B, len(g.experts)) for g in self.gates]
-        self.gate_table = self.b.table([self._gate_record(i, False) for i in range(len(self.gates))])
+        # distinct expert activations of the level, in first-use order
+        self.uniq: List[Act] = []
+        for g in self.gates:
+            for a in g.experts:
+                if not any(a.same_as(u) for u in self.uniq):
+                    self.uniq.append(a)
+        self.total_wg = sum(len(g.experts) * g.gate_in.width for g in self.gates)
+        self.fused = (len(self.gates) <= L.LEVEL_MAX_GATES and len(self.uniq) <= L.LEVEL_MAX_EXPERTS
+                      and self.H % 4 == 0 and self.total_wg <= L.LEVEL_MAX_WG
+                      and all(a.col % 4 == 0 for a in self.uniq) and all(o.col % 4 == 0 for o in self.outs))
+        if self.fused:
+            self.level_table = self.b.table([self._level_record(False)])
+        else:
+            self.gate_table = self.b.table([self._gate_record(i, False) for i in range(len(self.gates))])
+
+    def _level_record(self, backward: bool) -> L.GateLevel:
+        """Record of the row-fused kernels.  In backward mode also claims the gradient buffers
+        (assign / accumulate bookkeeping identical to the per-gate path)."""
+        st = self.b.store
+        r = L.GateLevel()
+        r.n_gates, r.n_experts, r.H = len(self.gates), len(self.uniq), self.H
+        r.expert_relu = 1 if self.uniq[0].relu else 0
+        assert all(a.relu == self.uniq[0].relu and a.ld == self.uniq[0].ld for a in self.uniq)
+        r.ld_expert = self.uniq[0].ld
+        for u, a in enumerate(self.uniq):
+            r.expert[u] = a.ptr
+            for g in range(L.LEVEL_MAX_GATES):
+                r.slot[u][g] = -1
+        live = [backward and self.outs[i].grad_written for i in range(len(self.gates))]
+        for i, g in enumerate(self.gates):
+            o, gi = self.outs[i], g.gate_in
+            r.gate_in[i], r.ld_gate_in[i], r.Hg[i], r.n_e[i] = gi.ptr, gi.ld, gi.width, len(g.experts)
+            r.Wg[i], r.ld_Wg[i] = g.head.weight.data_ptr(), g.head.weight._mm_ld
+            r.probs[i] = self.probs[i].data_ptr()
+            r.mix[i], r.ld_mix[i] = o.ptr, o.ld
+            if o.has_bf16:
+                r.mix_bf16[i], r.ld_mix_bf16[i] = o.ptr16, o.ld16
+            for e, a in enumerate(g.experts):
+                u = next(k for k, x in enumerate(self.uniq) if x.same_as(a))
+                r.slot[u][i] = e
+            if live[i]:
+                r.d_mix[i], r.ld_d_mix[i] = o.gptr, o.gld
+                if gi.group.need_grad:
+                    if gi.grad_is_f32:
+                        r.d_gate_in[i], r.ld_d_gate_in[i] = gi.gptr, gi.gld
+                        r.accumulate_d_gate_in[i] = 1 if gi.grad_written else 0
+                    else:
+                        assert not gi.grad_written, "a bf16 gradient buffer cannot be accumulated into"
+                        r.d_gate_in_bf16[i], r.ld_d_gate_in_bf16[i] = gi.gptr, gi.gld
+                    r.relu_mask_gate_in[i] = 1 if gi.relu else 0
+                    gi.grad_written = True
+                r.dWg[i] = st.grad_ptr(g.head.weight)
+        if backward:
+            for u, a in enumerate(self.uniq):
+                if not any(live[i] and any(a.same_as(x) for x in g.experts) for i, g in enumerate(self.gates)):
+                    continue
+                assert not a.grad_written, "an expert output consumed elsewhere must be accumulated"
+                if a.grad_is_f32:
+                    r.d_expert[u], r.ld_d_expert = a.gptr, a.gld
+                else:
+                    r.d_expert_bf16[u], r.ld_d_expert_bf16 = a.gptr, a.gld
+                a.grad_written = True
+        return r
 
     def _gate_record(self, i: int, backward: bool) -> L.Gate:
         g, st, o = self.gates[i], self.b.store, self.outs[i]
@@ -559,14 +642,24 @@ class GateMixStage(Stage):
         return r
 
     def forward(self, stream, training):
-        L.check(self.b.lib.mmlrec_gate_mix_forward(self.gate_table.data_ptr(), len(self.gates), self.b.B, stream),
-                f"gate_mix fwd {self.label}")
+        if self.fused:
+            L.check(self.b.lib.mmlrec_gate_level_forward(self.level_table.data_ptr(), self.b.B, stream),
+                    f"gate_level fwd {self.label}")
+        else:
+            L.check(self.b.lib.mmlrec_gate_mix_forward(self.gate_table.data_ptr(), len(self.gates), self.b.B, stream),
+                    f"gate_mix fwd {self.label}")
 
     def plan_backward(self):
         b = self.b
         live = [i for i in range(len(self.gates)) if self.outs[i].grad_written]
         self.any_live = bool(live)
         if not live:
+            return
+        if self.fused:
+            self.level_table = b.table([self._level_record(True)])
+            n = b.lib.mmlrec_gate_level_backward_scratch(self.total_wg, b.B)
+            self.scratch = b.zeros(int(n))
+            self.counters = b.zeros(1, dtype=torch.int32)
             return
         # gates that share an input (no gate DNN: every head reads the level input) must not race on
         # d(gate_in): the kernel then walks the gates in order inside each CTA
@@ -615,6 +708,13 @@ class GateMixStage(Stage):
         if not self.any_live:
             return
         b = self.b
+        if self.fused:
+            L.check(b.lib.mmlrec_gate_level_backward(self.level_table.data_ptr(), b.B, self.total_wg,
+                                                     sum(len(g.experts) for g in self.gates),
+                                                     sum(g.gate_in.width for g in self.gates),
+                                                     self.scratch.data_ptr(), self.counters.data_ptr(), stream),
+                    f"gate_level bwd {self.label}")
+            return
         L.check(b.lib.mmlrec_gate_mix_backward(self.gate_table.data_ptr(), len(self.gates), self.expert_table.data_ptr(),
                                                self.n_expert_recs, b.B, self.max_ne, self.max_hg, self.serialize,
                                                self.scratch.data_ptr(), self.counters.data_ptr(), stream),
@@ -695,6 +795,8 @@ class StepPlan:
         for s in reversed(self.stages):
             s.plan_backward()
         self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.side = torch.cuda.Stream(device=model.device_obj)
+        self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
 
     # ---- static inputs / outputs
     X = property(lambda self: self.gather.X)
@@ -713,10 +815,18 @@ class StepPlan:
         stream = torch.cuda.current_stream().cuda_stream if stream is None else stream
         lib = self.b.lib
         L.check(lib.mmlrec_hyper_advance(m.hyper_dev.data_ptr(), stream), "hyper_advance")
-        self.gather.sort(stream)
+        # the id sort only feeds the last backward kernel (K2): fork it onto a side stream so it overlaps
+        # the whole forward / backward (a parallel branch of the captured graph)
+        main = torch.cuda.current_stream()
+        self.ev_fork.record(main)
+        self.side.wait_event(self.ev_fork)
+        self.gather.sort(self.side.cuda_stream)
+        self.ev_join.record(self.side)
         for s in self.stages:
             s.forward(stream, True)
         for s in reversed(self.stages):
+            if s is self.gather:
+                main.wait_event(self.ev_join)
             s.backward(stream)
         st = m.store
         p = lambda t: t.data_ptr() if t is not None else None  # noqa: E731

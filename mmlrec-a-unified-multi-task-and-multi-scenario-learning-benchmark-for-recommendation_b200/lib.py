@@ -61,6 +61,22 @@ class ExpertGrad(C.Structure):
                 ("d_expert_bf16", vp), ("ld_d_expert_bf16", i64)]
 
 
+LEVEL_MAX_GATES, LEVEL_MAX_EXPERTS, LEVEL_MAX_WG = 8, 32, 3072
+
+
+class GateLevel(C.Structure):
+    _G, _E = LEVEL_MAX_GATES, LEVEL_MAX_EXPERTS
+    _fields_ = [("n_gates", i32), ("n_experts", i32), ("H", i32), ("expert_relu", i32),
+                ("expert", vp * _E), ("ld_expert", i64), ("d_expert", vp * _E), ("ld_d_expert", i64),
+                ("d_expert_bf16", vp * _E), ("ld_d_expert_bf16", i64), ("slot", (C.c_int8 * _G) * _E),
+                ("gate_in", vp * _G), ("ld_gate_in", i64 * _G), ("Wg", vp * _G), ("ld_Wg", i64 * _G),
+                ("Hg", i32 * _G), ("n_e", i32 * _G), ("probs", vp * _G), ("mix", vp * _G), ("ld_mix", i64 * _G),
+                ("mix_bf16", vp * _G), ("ld_mix_bf16", i64 * _G), ("d_mix", vp * _G), ("ld_d_mix", i64 * _G),
+                ("d_gate_in", vp * _G), ("ld_d_gate_in", i64 * _G), ("d_gate_in_bf16", vp * _G),
+                ("ld_d_gate_in_bf16", i64 * _G), ("relu_mask_gate_in", i32 * _G), ("accumulate_d_gate_in", i32 * _G),
+                ("dWg", vp * _G)]
+
+
 class Head(C.Structure):
     _fields_ = [("h", vp), ("ld_h", i64), ("H", i32), ("kind", i32), ("w", vp), ("bias", vp),
                 ("d_h", vp), ("ld_d_h", i64), ("relu_mask", i32), ("pad0", i32), ("dw", vp), ("dbias", vp),
@@ -88,6 +104,9 @@ _SIGNATURES = {
     "mmlrec_gate_mix_forward": (C.c_int, [vp, i32, i32, vp]),
     "mmlrec_gate_mix_backward": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
     "mmlrec_gate_mix_backward_scratch": (i64, [i32, i32, i32, i32]),
+    "mmlrec_gate_level_forward": (C.c_int, [vp, i32, vp]),
+    "mmlrec_gate_level_backward": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, vp]),
+    "mmlrec_gate_level_backward_scratch": (i64, [i32, i32]),
     "mmlrec_heads_forward_backward": (C.c_int, [vp, i32, i32, vp, i64, vp, i64, vp, i32, i32, vp, i64, vp, vp]),
     "mmlrec_heads_scratch": (i64, [i32, i32, i32]),
     "mmlrec_dense_optimizer_step": (C.c_int, [vp, vp, vp, vp, i64, vp, vp, vp]),

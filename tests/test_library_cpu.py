@@ -35,7 +35,7 @@ def test_library_loads_and_exports_every_declared_symbol():
 def test_ctypes_structs_match_c_layout():
     from mmlrec_b200 import lib
     L = lib.load()
-    for i, s in enumerate([lib.Hyper, lib.GemmF32, lib.GemmTcDesc, lib.Gate, lib.ExpertGrad, lib.Head]):
+    for i, s in enumerate([lib.Hyper, lib.GemmF32, lib.GemmTcDesc, lib.Gate, lib.ExpertGrad, lib.Head, lib.GateLevel]):
         assert ctypes.sizeof(s) == L.mmlrec_struct_size(i), s.__name__
     assert L.mmlrec_tc_record_bytes() % 128 == 0
     assert L.mmlrec_tc_num_tiles(4096, 3904) == 32 * 31
