@@ -105,6 +105,10 @@ int mmlrec_emb_backward_update(const float* d_input, int64_t ld, int32_t B,
                                const int64_t* field_meta, int32_t F_s, int32_t D,
                                float* emb, float* state1, float* state2, int32_t* row_touch,
                                const MmlrecHyper* hyper, float* grad_rows_out, void* stream);
+/* stamp row_touch[row] = hyper->step for every row the sorted batch ids name (lets the sweep below run
+ * BEFORE / concurrently with the backward pass: untouched rows need no gradient) */
+int mmlrec_emb_stamp_rows(const int32_t* sorted_ids, const int64_t* field_meta, int32_t F_s, int32_t B, int32_t D,
+                          int32_t* row_touch, const MmlrecHyper* hyper, void* stream);
 int mmlrec_emb_adam_dense_sweep(float* emb, float* exp_avg, float* exp_avg_sq, const int32_t* row_touch,
                                 int64_t total_rows, int32_t D, const MmlrecHyper* hyper, void* stream);
 

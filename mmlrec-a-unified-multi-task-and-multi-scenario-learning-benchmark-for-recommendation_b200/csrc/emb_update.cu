@@ -297,6 +297,18 @@ __global__ void __launch_bounds__(kSegThreads) emb_seg_update_kernel(const SegAr
   }
 }
 
+// Stamp every row the batch touches with the current step, straight from the sorted ids.  Lets the
+// dense-Adam sweep of the UNtouched rows start before the backward pass (it needs no gradient).
+__global__ void emb_stamp_rows_kernel(const int32_t* sorted_ids, const int64_t* field_meta, int F_s, int B, int D,
+                                      int32_t* row_touch, const MmlrecHyper* hyper) {
+  const int step = hyper->step;
+  const int64_t n = (int64_t)F_s * B;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int f = (int)(i / B);
+    row_touch[field_meta[f * 4 + 0] / D + sorted_ids[i]] = step;
+  }
+}
+
 // Adam's zero-gradient update for every row not touched in this step (dense-Adam semantics).
 __global__ void emb_adam_sweep_kernel(float* emb, float* m, float* v, const int32_t* row_touch,
                                       int64_t total_rows, int D, const MmlrecHyper* hyper) {
@@ -367,6 +379,16 @@ extern "C" int mmlrec_emb_backward_update(const float* d_input, int64_t ld, int3
   SegArgs a{d_input, ld, B, sorted_ids, sorted_pos, field_meta, D, emb, state1, state2, row_touch, hyper, grad_rows_out};
   dim3 grid(cdiv(B, kSegThreads), F_s);
   emb_seg_update_kernel<<<grid, kSegThreads, 0, (cudaStream_t)stream>>>(a);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_emb_stamp_rows(const int32_t* sorted_ids, const int64_t* field_meta, int32_t F_s, int32_t B, int32_t D,
+                                     int32_t* row_touch, const MmlrecHyper* hyper, void* stream) {
+  using namespace mmlrec;
+  MMLREC_CHECK_ARG(F_s > 0 && B > 0 && D > 0 && row_touch && hyper, "bad args");
+  const int64_t n = (int64_t)F_s * B;
+  int grid = (int)((n + 255) / 256 < 1184 ? (n + 255) / 256 : 1184);
+  emb_stamp_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(sorted_ids, field_meta, F_s, B, D, row_touch, hyper);
   MMLREC_RETURN_LAUNCH(1);
 }
 

@@ -260,49 +260,50 @@ __global__ void __launch_bounds__(256) gate_mix_backward_expert_kernel(const Mml
 }
 
 // ------------------------------------------------------------------------------------------------
-// heads + loss (forward + backward).  grid = ceil(B/64); 8 warps x 8 samples.
+// heads + loss (forward + backward).  grid = ceil(B/16); 8 warps x 2 samples; a warp owns a sample:
+// per task a coalesced row load + warp reduction gives the logit (lane t keeps task t), lanes 0..T-1
+// evaluate sigmoid / BCE / dz, then the row is revisited for d_h and the per-warp dw slab.  CTA
+// partials (loss, dbias, dw) go to scratch; the last CTA reduces them in a fixed order.
 // ------------------------------------------------------------------------------------------------
-constexpr int kHeadRows = 64;
+constexpr int kHeadRows = 16;
 constexpr int kHeadMaxK = 8;  // H <= 256
 
 __global__ void __launch_bounds__(256)
 heads_kernel(const MmlrecHead* heads, int T, int B, const float* y, int64_t ldy, float* pred, int64_t ld_pred,
              float* loss, int esmm, int training, float* scratch, int stride_cta, int32_t* counter) {
+  extern __shared__ __align__(16) float dw_s[];            // [8 warps][T][hmax]
   __shared__ MmlrecHead Hd[MMLREC_MAX_TASKS];
-  __shared__ float z_s[kHeadRows][MMLREC_MAX_TASKS];
-  __shared__ float dz_s[kHeadRows][MMLREC_MAX_TASKS];
-  __shared__ float l_s[kHeadRows][MMLREC_MAX_TASKS];
-  __shared__ float x_s[kHeadRows];
-  __shared__ float wred[8][32 * kHeadMaxK];
+  __shared__ float part_s[8][MMLREC_MAX_TASKS][2];         // per warp: loss, dbias partials
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   if (tid < T) Hd[tid] = heads[tid];
   __syncthreads();
-  const int r0 = blockIdx.x * kHeadRows;
-  // phase 1: logits
-  for (int rr = 0; rr < 8; ++rr) {
-    const int r = w * 8 + rr, b = r0 + r;
+  const bool bwd = training && y != nullptr;
+  const int hmax = bwd ? (stride_cta / T) - 2 : 0;
+  float* my_dw = dw_s + (size_t)w * T * hmax;
+  if (bwd) for (int i = lane; i < T * hmax; i += 32) my_dw[i] = 0.f;
+  float loss_acc = 0.f, dz_acc = 0.f;                       // lane t accumulates task t over this warp's rows
+  for (int rr = 0; rr < 2; ++rr) {
+    const int b = blockIdx.x * kHeadRows + w * 2 + rr;
+    if (b >= B) break;  // warp-uniform
+    // logits: lane t keeps z_t
+    float z = 0.f;
     for (int t = 0; t < T; ++t) {
+      const float* hrow = Hd[t].h + (int64_t)b * Hd[t].ld_h;
       float s = 0.f;
-      if (b < B) {
-        const float* hrow = Hd[t].h + (int64_t)b * Hd[t].ld_h;
-        for (int h = lane; h < Hd[t].H; h += 32) s = fmaf(hrow[h], __ldg(Hd[t].w + h), s);
-      }
+      for (int h = lane; h < Hd[t].H; h += 32) s = fmaf(hrow[h], __ldg(Hd[t].w + h), s);
       s = warp_sum(s);
-      if (lane == 0) z_s[r][t] = s + (Hd[t].bias ? *Hd[t].bias : 0.f);
+      if (lane == t) z = s + (Hd[t].bias ? *Hd[t].bias : 0.f);
     }
-  }
-  __syncthreads();
-  // phase 2: probabilities, loss terms, dz  (thread <-> (row, task))
-  for (int i = tid; i < kHeadRows * T; i += 256) {
-    const int r = i / T, t = i - r * T, b = r0 + r;
+    // probabilities, loss terms, dz (lanes < T)
+    const float z0 = __shfl_sync(0xffffffffu, z, 0);
     float dz = 0.f, l = 0.f, cross = 0.f;
-    if (b < B) {
-      const float z = z_s[r][t];
+    if (lane < T) {
+      const int t = lane;
       if (Hd[t].kind == MMLREC_HEAD_SIGMOID_BCE) {
         const float p = 1.f / (1.f + expf(-z));
         float out = p, scale = 1.f;  // scale = d(out)/dp
         if (esmm && t == 1) {        // esmm.py:59  ctcvr = ctr * cvr
-          const float p0 = 1.f / (1.f + expf(-z_s[r][0]));
+          const float p0 = 1.f / (1.f + expf(-z0));
           out = p0 * p;
           scale = p0;
         }
@@ -325,82 +326,76 @@ heads_kernel(const MmlrecHead* heads, int T, int B, const float* y, int64_t ldy,
         }
       }
     }
-    dz_s[r][t] = dz;
-    l_s[r][t] = l;
-    if (esmm && t == 1) x_s[r] = cross;
-  }
-  __syncthreads();
-  if (esmm && y) {  // head 0 also receives gradient through out1 = p0*p1
-    for (int r = tid; r < kHeadRows; r += 256) {
-      if (r0 + r < B) {
-        const float p0 = 1.f / (1.f + expf(-z_s[r][0]));
-        dz_s[r][0] += x_s[r] * (1.f - p0) * p0;
+    if (esmm) {  // head 0 also receives gradient through out1 = p0*p1
+      const float c1 = __shfl_sync(0xffffffffu, cross, 1);
+      if (lane == 0 && y) {
+        const float p0 = 1.f / (1.f + expf(-z));
+        dz += c1 * (1.f - p0) * p0;
       }
     }
-    __syncthreads();
-  }
-  if (!training || y == nullptr) return;
-  // loss + dbias partials per task: warp t sums column t over the 64 rows (fixed order)
-  float* cta_out = scratch + (int64_t)blockIdx.x * stride_cta;  // [T][2 + Hmax]
-  const int hmax = (stride_cta / T) - 2;
-  for (int t = w; t < T; t += 8) {
-    float l = 0.f, d = 0.f;
-    for (int r = lane; r < kHeadRows; r += 32) { l += l_s[r][t]; d += dz_s[r][t]; }
-    l = warp_sum(l); d = warp_sum(d);
-    if (lane == 0) { cta_out[t * (2 + hmax)] = l; cta_out[t * (2 + hmax) + 1] = d; }
-  }
-  // phase 3: d_h and dw partials
-  for (int t = 0; t < T; ++t) {
-    const MmlrecHead& hd = Hd[t];
-    float acc[kHeadMaxK];
-#pragma unroll
-    for (int k = 0; k < kHeadMaxK; ++k) acc[k] = 0.f;
-    for (int rr = 0; rr < 8; ++rr) {
-      const int r = w * 8 + rr, b = r0 + r;
-      if (b >= B) continue;
-      const float dz = dz_s[r][t];
+    if (!bwd) continue;
+    loss_acc += l;
+    dz_acc += dz;
+    // d_h and the dw slab
+    for (int t = 0; t < T; ++t) {
+      const MmlrecHead& hd = Hd[t];
+      const float dzt = __shfl_sync(0xffffffffu, dz, t);
       const float* hrow = hd.h + (int64_t)b * hd.ld_h;
-#pragma unroll
-      for (int k = 0; k < kHeadMaxK; ++k) {
-        int h = lane + 32 * k;
-        if (h < hd.H) {
-          float hv = hrow[h];
-          acc[k] = fmaf(dz, hv, acc[k]);
-          float g = dz * __ldg(hd.w + h);
-          if (hd.relu_mask && !(hv > 0.f)) g = 0.f;
-          if (hd.d_h) hd.d_h[(int64_t)b * hd.ld_d_h + h] = g;
-          if (hd.d_h_bf16) hd.d_h_bf16[(int64_t)b * hd.ld_d_h_bf16 + h] = float_to_bf16_bits(g);
-        }
+      for (int h = lane; h < hd.H; h += 32) {
+        const float hv = hrow[h];
+        my_dw[t * hmax + h] = fmaf(dzt, hv, my_dw[t * hmax + h]);
+        float g = dzt * __ldg(hd.w + h);
+        if (hd.relu_mask && !(hv > 0.f)) g = 0.f;
+        if (hd.d_h) hd.d_h[(int64_t)b * hd.ld_d_h + h] = g;
+        if (hd.d_h_bf16) hd.d_h_bf16[(int64_t)b * hd.ld_d_h_bf16 + h] = float_to_bf16_bits(g);
       }
     }
-    __syncthreads();
+  }
+  if (!bwd) return;
+  if (lane < T) { part_s[w][lane][0] = loss_acc; part_s[w][lane][1] = dz_acc; }
+  __syncthreads();
+  // CTA partial -> scratch [cta][T][2 + hmax]  (warps summed in fixed order)
+  float* cta_out = scratch + (int64_t)blockIdx.x * stride_cta;
+  const int per_t = 2 + hmax;
+  for (int i = tid; i < T * per_t; i += 256) {
+    const int t = i / per_t, k = i - t * per_t;
+    float s = 0.f;
+    if (k < 2) {
 #pragma unroll
-    for (int k = 0; k < kHeadMaxK; ++k) wred[w][lane + 32 * k] = acc[k];
-    __syncthreads();
-    for (int h = tid; h < hd.H; h += 256) {
-      float s = 0.f;
+      for (int ww = 0; ww < 8; ++ww) s += part_s[ww][t][k];
+    } else {
 #pragma unroll
-      for (int ww = 0; ww < 8; ++ww) s += wred[ww][h];
-      cta_out[t * (2 + hmax) + 2 + h] = s;
+      for (int ww = 0; ww < 8; ++ww) s += dw_s[((size_t)ww * T + t) * hmax + (k - 2)];
     }
+    cta_out[i] = s;
   }
   if (last_block_ticket(counter, gridDim.x)) {
-    const int per_t = 2 + hmax;
-    float total = 0.f;
-    for (int t = 0; t < T; ++t) {
-      for (int i = tid; i < 2 + Hd[t].H; i += 256) {
-        float s = 0.f;
-        for (int c = 0; c < (int)gridDim.x; ++c) s += scratch[(int64_t)c * stride_cta + t * per_t + i];
-        if (i == 0) loss[t] = s;
-        else if (i == 1) { if (!(esmm && t == 1)) { if (Hd[t].dbias) *Hd[t].dbias = s; } else x_s[0] = s; }
-        else Hd[t].dw[i - 2] = s;
+    __shared__ float tot_s[MMLREC_MAX_TASKS][2];
+    for (int i = tid; i < T * per_t; i += 256) {
+      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+      int c = 0;
+      for (; c + 3 < (int)gridDim.x; c += 4) {
+        s0 += scratch[(int64_t)c * stride_cta + i];
+        s1 += scratch[(int64_t)(c + 1) * stride_cta + i];
+        s2 += scratch[(int64_t)(c + 2) * stride_cta + i];
+        s3 += scratch[(int64_t)(c + 3) * stride_cta + i];
       }
+      for (; c < (int)gridDim.x; ++c) s0 += scratch[(int64_t)c * stride_cta + i];
+      const float s = (s0 + s1) + (s2 + s3);
+      const int t = i / per_t, k = i - t * per_t;
+      if (k < 2) tot_s[t][k] = s;
+      else if (k - 2 < Hd[t].H) Hd[t].dw[k - 2] = s;
     }
     __syncthreads();
     if (tid == 0) {
-      for (int t = 0; t < T; ++t) total += loss[t];
+      float total = 0.f;
+      for (int t = 0; t < T; ++t) { loss[t] = tot_s[t][0]; total += tot_s[t][0]; }
       loss[T] = total;
-      if (esmm && Hd[0].dbias) *Hd[0].dbias += x_s[0];  // one shared bias gets both heads' gradient
+      if (esmm) {  // one shared bias receives both heads' gradient
+        if (Hd[0].dbias) *Hd[0].dbias = tot_s[0][1] + tot_s[1][1];
+      } else {
+        for (int t = 0; t < T; ++t) if (Hd[t].dbias) *Hd[t].dbias = tot_s[t][1];
+      }
     }
   }
 }
@@ -533,13 +528,22 @@ extern "C" int mmlrec_heads_forward_backward(const MmlrecHead* heads, int32_t T,
   MMLREC_CHECK_ARG(!esmm || T == 2, "esmm needs exactly two heads");
   const int n_cta = cdiv(B, kHeadRows);
   int stride_cta = 0;
-  if (training) {
+  size_t smem = 0;
+  if (training && y != nullptr) {
     MMLREC_CHECK_ARG(scratch && counters && scratch_floats > 0 && scratch_floats % n_cta == 0, "bad scratch");
     stride_cta = (int)(scratch_floats / n_cta);
     MMLREC_CHECK_ARG(stride_cta % T == 0 && stride_cta / T - 2 <= 32 * kHeadMaxK, "head width > 256 unsupported");
+    smem = (size_t)8 * T * (stride_cta / T - 2) * sizeof(float);
+    MMLREC_CHECK_ARG(smem <= 160 * 1024, "too many / too wide heads for the per-warp dw slabs");
+    static size_t opted = 0;
+    if (smem > 40 * 1024 && smem > opted) {
+      cudaError_t e = cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) { set_error("heads: smem opt-in failed"); return (int)e; }
+      opted = smem;
+    }
   }
-  heads_kernel<<<n_cta, 256, 0, (cudaStream_t)stream>>>(heads, T, B, y, ldy, pred, ld_pred, loss, esmm, training, scratch,
-                                                        stride_cta, counters);
+  heads_kernel<<<n_cta, 256, smem, (cudaStream_t)stream>>>(heads, T, B, y, ldy, pred, ld_pred, loss, esmm, training, scratch,
+                                                           stride_cta, counters);
   MMLREC_RETURN_LAUNCH(1);
 }
 

@@ -236,11 +236,21 @@ class GatherStage(Stage):
             self.oob.data_ptr(), stream), "gather_concat")
 
     def sort(self, stream):
-        if self.F_s:
-            b = self.b
-            L.check(b.lib.mmlrec_sort_field_ids(self.X.data_ptr(), self.X.stride(0), b.B, self.meta.data_ptr(),
-                                                self.F_s, self.sorted_ids.data_ptr(), self.sorted_pos.data_ptr(),
-                                                self.keys_ws.data_ptr(), stream), "sort_field_ids")
+        """Side branch of the step: sort the batch ids; with Adam also stamp the touched rows and run
+        the dense-Adam sweep of all UNtouched rows (zero-gradient update: needs no gradient, and the
+        gather only reads touched rows, which the sweep skips)."""
+        if not self.F_s:
+            return
+        b, st, hy = self.b, self.b.store, self.model.hyper_dev
+        L.check(b.lib.mmlrec_sort_field_ids(self.X.data_ptr(), self.X.stride(0), b.B, self.meta.data_ptr(),
+                                            self.F_s, self.sorted_ids.data_ptr(), self.sorted_pos.data_ptr(),
+                                            self.keys_ws.data_ptr(), stream), "sort_field_ids")
+        if self.model.optimizer_name == "adam":
+            L.check(b.lib.mmlrec_emb_stamp_rows(self.sorted_ids.data_ptr(), self.meta.data_ptr(), self.F_s, b.B, self.D,
+                                                st.row_touch.data_ptr(), hy.data_ptr(), stream), "emb_stamp_rows")
+            L.check(b.lib.mmlrec_emb_adam_dense_sweep(st.emb.data_ptr(), st.emb_s1.data_ptr(), st.emb_s2.data_ptr(),
+                                                      st.row_touch.data_ptr(), st.n_emb // self.D, self.D,
+                                                      hy.data_ptr(), stream), "emb_adam_dense_sweep")
 
     def backward(self, stream):
         if not self.F_s or not self.out.grad_written:
@@ -251,10 +261,6 @@ class GatherStage(Stage):
             self.out.gptr, self.out.gld, b.B, self.sorted_ids.data_ptr(), self.sorted_pos.data_ptr(),
             self.meta.data_ptr(), self.F_s, self.D, st.emb.data_ptr(), p(st.emb_s1), p(st.emb_s2), p(st.row_touch),
             hy.data_ptr(), None, stream), "emb_backward_update")
-        if self.model.optimizer_name == "adam":
-            L.check(b.lib.mmlrec_emb_adam_dense_sweep(st.emb.data_ptr(), st.emb_s1.data_ptr(), st.emb_s2.data_ptr(),
-                                                      st.row_touch.data_ptr(), st.n_emb // self.D, self.D,
-                                                      hy.data_ptr(), stream), "emb_adam_dense_sweep")
 
 
 # ----------------------------------------------------------------------------------------------

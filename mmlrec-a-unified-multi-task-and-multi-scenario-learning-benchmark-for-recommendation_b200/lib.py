@@ -92,6 +92,7 @@ _SIGNATURES = {
     "mmlrec_gather_concat": (C.c_int, [vp, i64, i32, vp, vp, i32, i32, vp, i32, i32, vp, i64, vp, i64, vp, vp]),
     "mmlrec_sort_field_ids": (C.c_int, [vp, i64, i32, vp, i32, vp, vp, vp, vp]),
     "mmlrec_emb_backward_update": (C.c_int, [vp, i64, i32, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp, vp]),
+    "mmlrec_emb_stamp_rows": (C.c_int, [vp, vp, i32, i32, i32, vp, vp, vp]),
     "mmlrec_emb_adam_dense_sweep": (C.c_int, [vp, vp, vp, vp, i64, i32, vp, vp]),
     "mmlrec_gemm_grouped_f32": (C.c_int, [vp, vp, i32, i32, vp]),
     "mmlrec_tc_record_bytes": (i64, []),
