@@ -218,12 +218,20 @@ class GatherStage(Stage):
         self.dense_out_col = self.F_s * self.D
         self.X = b.zeros(b.B, model.num_x_cols)
         self.oob = b.zeros(1, dtype=torch.int32)
+        # data parallel: ids and d(dnn_input) of ALL ranks (the embedding update runs on the global batch)
+        self.dp = getattr(model, "dp", None)
+        self.B_all = self.dp.global_batch(b.B) if self.dp else b.B
+        if self.dp:
+            self.X_all = b.zeros(self.B_all, model.num_x_cols)
+            self.dgrad_all = b.zeros(self.B_all, self.out.group.gbuf.shape[1])
+        else:
+            self.X_all = self.X
         if self.F_s:
             n_pad = 32
-            while n_pad < b.B:
+            while n_pad < self.B_all:
                 n_pad <<= 1
-            self.sorted_ids = b.zeros(self.F_s, b.B, dtype=torch.int32)
-            self.sorted_pos = b.zeros(self.F_s, b.B, dtype=torch.int32)
+            self.sorted_ids = b.zeros(self.F_s, self.B_all, dtype=torch.int32)
+            self.sorted_pos = b.zeros(self.F_s, self.B_all, dtype=torch.int32)
             self.keys_ws = b.zeros(self.F_s * n_pad, dtype=torch.int64)
 
     def forward(self, stream, training):
@@ -242,11 +250,11 @@ class GatherStage(Stage):
         if not self.F_s:
             return
         b, st, hy = self.b, self.b.store, self.model.hyper_dev
-        L.check(b.lib.mmlrec_sort_field_ids(self.X.data_ptr(), self.X.stride(0), b.B, self.meta.data_ptr(),
+        L.check(b.lib.mmlrec_sort_field_ids(self.X_all.data_ptr(), self.X_all.stride(0), self.B_all, self.meta.data_ptr(),
                                             self.F_s, self.sorted_ids.data_ptr(), self.sorted_pos.data_ptr(),
                                             self.keys_ws.data_ptr(), stream), "sort_field_ids")
         if self.model.optimizer_name == "adam":
-            L.check(b.lib.mmlrec_emb_stamp_rows(self.sorted_ids.data_ptr(), self.meta.data_ptr(), self.F_s, b.B, self.D,
+            L.check(b.lib.mmlrec_emb_stamp_rows(self.sorted_ids.data_ptr(), self.meta.data_ptr(), self.F_s, self.B_all, self.D,
                                                 st.row_touch.data_ptr(), hy.data_ptr(), stream), "emb_stamp_rows")
             L.check(b.lib.mmlrec_emb_adam_dense_sweep(st.emb.data_ptr(), st.emb_s1.data_ptr(), st.emb_s2.data_ptr(),
                                                       st.row_touch.data_ptr(), st.n_emb // self.D, self.D,
@@ -257,8 +265,12 @@ class GatherStage(Stage):
             return
         b, st, hy = self.b, self.b.store, self.model.hyper_dev
         p = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+        d_ptr, d_ld = self.out.gptr, self.out.gld
+        if self.dp:  # every rank reduces the gradient rows of the GLOBAL batch
+            self.dp.gather_rows(self.out.group.gbuf, self.dgrad_all)
+            d_ptr, d_ld = self.dgrad_all.data_ptr(), self.dgrad_all.stride(0)
         L.check(b.lib.mmlrec_emb_backward_update(
-            self.out.gptr, self.out.gld, b.B, self.sorted_ids.data_ptr(), self.sorted_pos.data_ptr(),
+            d_ptr, d_ld, self.B_all, self.sorted_ids.data_ptr(), self.sorted_pos.data_ptr(),
             self.meta.data_ptr(), self.F_s, self.D, st.emb.data_ptr(), p(st.emb_s1), p(st.emb_s2), p(st.row_touch),
             hy.data_ptr(), None, stream), "emb_backward_update")
 
@@ -824,6 +836,9 @@ class StepPlan:
         # the id sort only feeds the last backward kernel (K2): fork it onto a side stream so it overlaps
         # the whole forward / backward (a parallel branch of the captured graph)
         main = torch.cuda.current_stream()
+        dp = getattr(m, "dp", None)
+        if dp is not None:
+            dp.gather_rows(self.gather.X, self.gather.X_all)
         self.ev_fork.record(main)
         self.side.wait_event(self.ev_fork)
         self.gather.sort(self.side.cuda_stream)
@@ -835,6 +850,8 @@ class StepPlan:
                 main.wait_event(self.ev_join)
             s.backward(stream)
         st = m.store
+        if dp is not None:
+            dp.sum_gradients(st.dense_grad)
         p = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
         L.check(lib.mmlrec_dense_optimizer_step(st.dense.data_ptr(), st.dense_grad.data_ptr(), p(st.dense_s1),
                                                 p(st.dense_s2), st.n_dense, m.hyper_dev.data_ptr(), p(st.dense_bf16),

@@ -93,6 +93,7 @@ class BaseModel(nn.Module):
         self._steps_on_plan: Dict[int, int] = {}
         self.use_cuda_graph = bool(self.b200_config.get("cuda_graph", True))
         self.precision = self.b200_config.get("precision", "fp32")
+        self.dp = None  # set by mmlrec_b200.parallel.attach()
         self.optimizer_name: Optional[str] = None
         self.hyper_dev: Optional[torch.Tensor] = None
         self.metrics, self.metrics_names = {}, ["loss"]

@@ -1,0 +1,57 @@
+"""Run under torchrun on R GPUs: R ranks x per-rank batch b must equal ONE process at the global batch R*b
+(fp32 mode: parameters after 3 steps agree to rounding).  Rank 0 also runs the single-process model."""
+import os, sys, copy
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import torch, torch.distributed as dist
+from helpers import load_golden
+from test_step_gpu import build_model, load_init
+from mmlrec_b200 import synthetic, parallel
+
+rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+ok = True
+for case, graph in (("ple_ae_t4_adam", False), ("ple_ae_t4_adam", True), ("mmoe_synth26_adagrad", True), ("esmm_kuairec_adam", True)):
+    z, cfg, fields = load_golden(case)
+    b = 96
+    model, cfg2 = build_model(cfg, fields, device=f"cuda:{local}", cuda_graph=graph)
+    load_init(model, z)
+    model.compile(cfg["optim_config"]["optimizer"], cfg["optim_config"]["loss"], [])
+    parallel.attach(model, rank, world)
+    model.train()
+    single = None
+    if rank == 0:
+        single, _ = build_model(cfg, fields, device=f"cuda:{local}", cuda_graph=graph)
+        load_init(single, z)
+        single.compile(cfg["optim_config"]["optimizer"], cfg["optim_config"]["loss"], [])
+        single.train()
+    for s in range(3):
+        X, y = synthetic.make_batch(cfg, fields, b * world, seed=40 + s)
+        lo, hi = model.dp.shard(b * world)
+        model.train_on_batch(X[lo:hi], y[lo:hi])
+        if single is not None:
+            single.train_on_batch(X, y)
+    torch.cuda.synchronize()
+    dist.barrier()
+    if rank == 0:
+        worst = 0.0
+        sd_dp, sd_1 = model.state_dict(), single.state_dict()
+        for k, v in sd_1.items():
+            if v.dtype != torch.float32:
+                continue
+            ref_scale = float(v.abs().max()) + 1e-12
+            worst = max(worst, float((sd_dp[k] - v).abs().max()) / ref_scale)
+        print(f"{case} graph={graph}: max rel param diff DP({world}x{b}) vs single({world * b}) = {worst:.3e}", flush=True)
+        ok &= worst < 2e-5
+    # replicas must stay bit-identical
+    chk = model.store.emb.double().sum() + model.store.dense.double().sum()
+    allc = [torch.zeros_like(chk) for _ in range(world)]
+    dist.all_gather(allc, chk)
+    if rank == 0:
+        same = all(float(c) == float(allc[0]) for c in allc)
+        print(f"   replicas identical: {same}", flush=True)
+        ok &= same
+if rank == 0:
+    print("DP_EQUIVALENCE", "OK" if ok else "FAILED", flush=True)
+dist.destroy_process_group()
