@@ -280,6 +280,8 @@ typedef struct MmlrecHead {
   float* d_h; int64_t ld_d_h; int32_t relu_mask; int32_t pad0; /* d(tower output), nullable */
   float* dw; float* dbias;                                    /* [H], [1] */
   uint16_t* d_h_bf16; int64_t ld_d_h_bf16;                    /* nullable bf16 copy of d_h */
+  const float* bias2; float* dbias2;                          /* optional second scalar bias (PEPNet: the final
+                                                                 Linear's own bias next to the PredictionLayer's) */
 } MmlrecHead;
 int mmlrec_heads_forward_backward(const MmlrecHead* heads, int32_t T, int32_t B,
                                   const float* y, int64_t ldy,
@@ -295,6 +297,35 @@ int64_t mmlrec_heads_scratch(int32_t T, int32_t max_h, int32_t B);
  * ------------------------------------------------------------------------------------------- */
 int mmlrec_dense_optimizer_step(float* param, const float* grad, float* state1, float* state2, int64_t n,
                                 const MmlrecHyper* hyper, uint16_t* bf16_shadow, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Element-wise stages used by STAR (model/star.py + SharedSpecificLinear, model/utils.py:163-223) and
+ * PEPNet (model/pepnet.py).  "dkind" selects the derivative folded into a gradient write:
+ * 0 none, 1 ReLU (keep where value > 0), 2 "2*sigmoid" (times y*(1 - y/2), GateNN's output).
+ * ------------------------------------------------------------------------------------------- */
+/* dst[:, :cols] = src[:, :cols]  (fp32 and/or bf16 destination): the concat of detached inputs */
+int mmlrec_copy_cols(const float* src, int64_t ld_src, float* dst_f32, int64_t ld_f32, uint16_t* dst_bf16,
+                     int64_t ld_bf16, int32_t rows, int32_t cols, void* stream);
+/* out = a * b  (fp32 and/or bf16 copy) */
+int mmlrec_mul_forward(const float* a, int64_t lda, const float* b, int64_t ldb, float* out_f32, int64_t ld_f32,
+                       uint16_t* out_bf16, int64_t ld_bf16, int32_t rows, int32_t cols, void* stream);
+/* da (+)= dkind_a(d_out * b, a) ; db (+)= dkind_b(d_out * a, b); each side optional, fp32 or bf16 */
+int mmlrec_mul_backward(const float* d_out, int64_t ld_dout, const float* a, int64_t lda, const float* b, int64_t ldb,
+                        float* da_f32, uint16_t* da_bf16, int64_t ld_da, int32_t dkind_a, int32_t acc_a,
+                        float* db_f32, uint16_t* db_bf16, int64_t ld_db, int32_t dkind_b, int32_t acc_b,
+                        int32_t rows, int32_t cols, void* stream);
+/* STAR: effective weights of all T domains in nn.Linear layout:
+ *   w_eff[t*N + n, k] = spec[t][k, n] * shared[k, n];  b_eff[t*N + n] = spec_b[t][n] + shared_b[n]
+ * spec / spec_b: T device pointers (int64 array on device); bf16 shadow optional. */
+int mmlrec_star_weights(const int64_t* spec_ptrs, const int64_t* spec_b_ptrs, const float* shared, const float* shared_b,
+                        int32_t T, int32_t K, int32_t N, float* w_eff, int64_t ld_w, uint16_t* w_eff_bf16, float* b_eff,
+                        void* stream);
+/* STAR backward fold: d_shared[k,n] = sum_t d_w_eff[t*N+n,k] * spec[t][k,n]; d_spec_last[k,n] = d_w_eff[(T-1)*N+n,k] *
+ * shared[k,n]; d_shared_b[n] = sum_t d_b_eff[t*N+n]; d_spec_b_last[n] = d_b_eff[(T-1)*N+n].  live[t]=0 skips a domain
+ * whose effective weight received no gradient. */
+int mmlrec_star_fold(const float* d_w_eff, int64_t ld_w, const float* d_b_eff, const int64_t* spec_ptrs,
+                     const float* shared, const int32_t* live, int32_t T, int32_t K, int32_t N, float* d_shared,
+                     float* d_shared_b, float* d_spec_last, float* d_spec_b_last, void* stream);
 
 /* small utilities */
 int mmlrec_fill_f32(float* p, int64_t n, float v, void* stream);

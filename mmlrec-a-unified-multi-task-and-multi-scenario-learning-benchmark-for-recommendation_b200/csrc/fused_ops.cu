@@ -292,7 +292,7 @@ heads_kernel(const MmlrecHead* heads, int T, int B, const float* y, int64_t ldy,
       float s = 0.f;
       for (int h = lane; h < Hd[t].H; h += 32) s = fmaf(hrow[h], __ldg(Hd[t].w + h), s);
       s = warp_sum(s);
-      if (lane == t) z = s + (Hd[t].bias ? *Hd[t].bias : 0.f);
+      if (lane == t) z = s + (Hd[t].bias ? *Hd[t].bias : 0.f) + (Hd[t].bias2 ? *Hd[t].bias2 : 0.f);
     }
     // probabilities, loss terms, dz (lanes < T)
     const float z0 = __shfl_sync(0xffffffffu, z, 0);
@@ -396,6 +396,7 @@ heads_kernel(const MmlrecHead* heads, int T, int B, const float* y, int64_t ldy,
       } else {
         for (int t = 0; t < T; ++t) if (Hd[t].dbias) *Hd[t].dbias = tot_s[t][1];
       }
+      for (int t = 0; t < T; ++t) if (Hd[t].dbias2) *Hd[t].dbias2 = tot_s[t][1];
     }
   }
 }
@@ -445,6 +446,94 @@ __global__ void mul_kernel(const float* a, int64_t lda, const float* b, int64_t 
     float v = a[r * lda + c] * b[r * ldb + c];
     if (accumulate) v += out[r * ldo + c];
     out[r * ldo + c] = v;
+  }
+}
+
+__device__ __forceinline__ float apply_dkind(float g, float v, int dkind) {
+  if (dkind == 1) return v > 0.f ? g : 0.f;
+  if (dkind == 2) return g * v * (1.f - 0.5f * v);   // d/dz [2*sigmoid(z)] = y * (1 - y/2)
+  return g;
+}
+
+__global__ void copy_cols_kernel(const float* src, int64_t ld_src, float* d32, int64_t ld32, uint16_t* d16, int64_t ld16,
+                                 int rows, int cols) {
+  const int64_t n = (int64_t)rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+    const float v = src[r * ld_src + c];
+    if (d32) d32[r * ld32 + c] = v;
+    if (d16) d16[r * ld16 + c] = float_to_bf16_bits(v);
+  }
+}
+
+__global__ void mul_forward_kernel(const float* a, int64_t lda, const float* b, int64_t ldb, float* o32, int64_t ld32,
+                                   uint16_t* o16, int64_t ld16, int rows, int cols) {
+  const int64_t n = (int64_t)rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+    const float v = a[r * lda + c] * b[r * ldb + c];
+    if (o32) o32[r * ld32 + c] = v;
+    if (o16) o16[r * ld16 + c] = float_to_bf16_bits(v);
+  }
+}
+
+__global__ void mul_backward_kernel(const float* d_out, int64_t ld_dout, const float* a, int64_t lda, const float* b,
+                                    int64_t ldb, float* da32, uint16_t* da16, int64_t ld_da, int dkind_a, int acc_a,
+                                    float* db32, uint16_t* db16, int64_t ld_db, int dkind_b, int acc_b, int rows, int cols) {
+  const int64_t n = (int64_t)rows * cols;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i - (int64_t)r * cols);
+    const float g = d_out[r * ld_dout + c], av = a[r * lda + c], bv = b[r * ldb + c];
+    if (da32 || da16) {
+      float v = apply_dkind(g * bv, av, dkind_a);
+      if (da32) { if (acc_a) v += da32[r * ld_da + c]; da32[r * ld_da + c] = v; }
+      if (da16) da16[r * ld_da + c] = float_to_bf16_bits(v);
+    }
+    if (db32 || db16) {
+      float v = apply_dkind(g * av, bv, dkind_b);
+      if (db32) { if (acc_b) v += db32[r * ld_db + c]; db32[r * ld_db + c] = v; }
+      if (db16) db16[r * ld_db + c] = float_to_bf16_bits(v);
+    }
+  }
+}
+
+// i indexes (t, n, k) of w_eff [T*N, ld_w]; spec[t] and shared are [K, N] row-major
+__global__ void star_weights_kernel(const int64_t* spec_ptrs, const int64_t* spec_b_ptrs, const float* shared,
+                                    const float* shared_b, int T, int K, int N, float* w_eff, int64_t ld_w,
+                                    uint16_t* w16, float* b_eff) {
+  const int64_t n = (int64_t)T * N * K;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const int64_t tn = i / K;
+    const int nn = (int)(tn % N), t = (int)(tn / N);
+    const float* sp = reinterpret_cast<const float*>(spec_ptrs[t]);
+    const float v = sp[(int64_t)k * N + nn] * shared[(int64_t)k * N + nn];
+    w_eff[tn * ld_w + k] = v;
+    if (w16) w16[tn * ld_w + k] = float_to_bf16_bits(v);
+    if (k == 0) b_eff[tn] = reinterpret_cast<const float*>(spec_b_ptrs[t])[nn] + shared_b[nn];
+  }
+}
+
+__global__ void star_fold_kernel(const float* d_w_eff, int64_t ld_w, const float* d_b_eff, const int64_t* spec_ptrs,
+                                 const float* shared, const int32_t* live, int T, int K, int N, float* d_shared,
+                                 float* d_shared_b, float* d_spec_last, float* d_spec_b_last) {
+  const int64_t n = (int64_t)K * N;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int k = (int)(i / N), nn = (int)(i - (int64_t)k * N);
+    float acc = 0.f;
+    for (int t = 0; t < T; ++t) {
+      if (!live[t]) continue;
+      const float g = d_w_eff[((int64_t)t * N + nn) * ld_w + k];
+      acc = fmaf(g, reinterpret_cast<const float*>(spec_ptrs[t])[i], acc);
+      if (t == T - 1 && d_spec_last) d_spec_last[i] = g * shared[i];
+    }
+    d_shared[i] = acc;
+    if (k == 0) {
+      float bacc = 0.f;
+      for (int t = 0; t < T; ++t) if (live[t]) bacc += d_b_eff[(int64_t)t * N + nn];
+      d_shared_b[nn] = bacc;
+      if (d_spec_b_last && live[T - 1]) d_spec_b_last[nn] = d_b_eff[(int64_t)(T - 1) * N + nn];
+    }
   }
 }
 
@@ -581,5 +670,51 @@ extern "C" int mmlrec_mul_f32(const float* a, int64_t lda, const float* b, int64
                               int32_t rows, int32_t cols, int32_t accumulate, void* stream) {
   if (rows <= 0 || cols <= 0) return 0;
   mul_kernel<<<grid_for((int64_t)rows * cols), 256, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, out, ldo, rows, cols, accumulate);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_copy_cols(const float* src, int64_t ld_src, float* dst_f32, int64_t ld_f32, uint16_t* dst_bf16,
+                                int64_t ld_bf16, int32_t rows, int32_t cols, void* stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  copy_cols_kernel<<<grid_for((int64_t)rows * cols), 256, 0, (cudaStream_t)stream>>>(src, ld_src, dst_f32, ld_f32, dst_bf16,
+                                                                                   ld_bf16, rows, cols);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_mul_forward(const float* a, int64_t lda, const float* b, int64_t ldb, float* out_f32, int64_t ld_f32,
+                                  uint16_t* out_bf16, int64_t ld_bf16, int32_t rows, int32_t cols, void* stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  mul_forward_kernel<<<grid_for((int64_t)rows * cols), 256, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, out_f32, ld_f32,
+                                                                                     out_bf16, ld_bf16, rows, cols);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_mul_backward(const float* d_out, int64_t ld_dout, const float* a, int64_t lda, const float* b,
+                                   int64_t ldb, float* da_f32, uint16_t* da_bf16, int64_t ld_da, int32_t dkind_a,
+                                   int32_t acc_a, float* db_f32, uint16_t* db_bf16, int64_t ld_db, int32_t dkind_b,
+                                   int32_t acc_b, int32_t rows, int32_t cols, void* stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  mul_backward_kernel<<<grid_for((int64_t)rows * cols), 256, 0, (cudaStream_t)stream>>>(
+      d_out, ld_dout, a, lda, b, ldb, da_f32, da_bf16, ld_da, dkind_a, acc_a, db_f32, db_bf16, ld_db, dkind_b, acc_b, rows,
+      cols);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_star_weights(const int64_t* spec_ptrs, const int64_t* spec_b_ptrs, const float* shared,
+                                   const float* shared_b, int32_t T, int32_t K, int32_t N, float* w_eff, int64_t ld_w,
+                                   uint16_t* w_eff_bf16, float* b_eff, void* stream) {
+  MMLREC_CHECK_ARG(T > 0 && K > 0 && N > 0 && ld_w >= K, "bad sizes");
+  star_weights_kernel<<<grid_for((int64_t)T * N * K), 256, 0, (cudaStream_t)stream>>>(spec_ptrs, spec_b_ptrs, shared, shared_b,
+                                                                                    T, K, N, w_eff, ld_w, w_eff_bf16, b_eff);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_star_fold(const float* d_w_eff, int64_t ld_w, const float* d_b_eff, const int64_t* spec_ptrs,
+                                const float* shared, const int32_t* live, int32_t T, int32_t K, int32_t N, float* d_shared,
+                                float* d_shared_b, float* d_spec_last, float* d_spec_b_last, void* stream) {
+  MMLREC_CHECK_ARG(T > 0 && K > 0 && N > 0 && ld_w >= K, "bad sizes");
+  star_fold_kernel<<<grid_for((int64_t)K * N), 256, 0, (cudaStream_t)stream>>>(d_w_eff, ld_w, d_b_eff, spec_ptrs, shared, live,
+                                                                             T, K, N, d_shared, d_shared_b, d_spec_last,
+                                                                             d_spec_b_last);
   MMLREC_RETURN_LAUNCH(1);
 }

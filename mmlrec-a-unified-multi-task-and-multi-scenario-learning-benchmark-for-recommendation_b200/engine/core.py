@@ -34,8 +34,9 @@ class ActGroup:
     """One wide buffer family [B, sum(widths)]: forward values and gradients, each optionally in
     fp32 and/or bf16 (decided by the consumers before ``materialize``)."""
 
-    def __init__(self, widths: Sequence[int], relu: bool, name: str, grad_dtype: str):
+    def __init__(self, widths: Sequence[int], relu: bool, name: str, grad_dtype: str, act: Optional[str] = None):
         self.widths, self.relu, self.name, self.grad_dtype = list(widths), relu, name, grad_dtype
+        self.act = act if act is not None else ("relu" if relu else None)   # activation that produced the values
         self.need_f32 = self.need_bf16 = False
         self.need_grad = True
         self.buf = self.buf16 = self.gbuf = self.gbuf16 = None
@@ -69,6 +70,13 @@ class Act:
         self.need_f32 = self.need_bf16 = False   # which copies THIS activation's consumers read
 
     relu = property(lambda self: self.group.relu)
+    # derivative folded into gradient writes: 0 none, 1 ReLU, 2 "2*sigmoid" (GateNN output)
+    dkind = property(lambda self: {"relu": 1, "sigmoid2": 2}.get(self.group.act, 0))
+
+    def sub(self, col: int, width: int) -> "Act":
+        """A column sub-range of this activation (e.g. one field's embedding inside dnn_input)."""
+        a = Act(self.group, self.col + col, width, f"{self.name}[{col}:{col + width}]")
+        return a
     # fp32 view
     ld = property(lambda self: self.group.buf.stride(0))
     ptr = property(lambda self: self.group.buf.data_ptr() + 4 * self.col)
@@ -123,7 +131,10 @@ class Builder:
         self.param_order: List[nn.Parameter] = []
         self.buffer_order: List[torch.Tensor] = []
         self.keep: List[object] = []       # tensors whose addresses are baked into tables
+        self.aux_floats = 0                # dry run: size of the derived-weight region
         self.lib = None if dry else L.load()
+        if store is not None:
+            store.reset_aux()
 
     # ---- allocation helpers
     def zeros(self, *shape, dtype=torch.float32) -> torch.Tensor:
@@ -155,13 +166,26 @@ class Builder:
         self.keep.append(rec)
         return rec, self.ints(pre), len(descs), at
 
-    def new_group(self, widths: Sequence[int], relu: bool, name: str, grad_dtype: str = "f32") -> List[Act]:
-        g = ActGroup(widths, relu, name, grad_dtype if self.tc else "f32")
+    def aux_matrix(self, rows: int, cols: int):
+        if self.dry:
+            self.aux_floats = _align(self.aux_floats, 8) + rows * _align(cols, 8)
+            return None
+        return self.store.aux_matrix(rows, cols)
+
+    def aux_vector(self, n: int):
+        if self.dry:
+            self.aux_floats += n
+            return None
+        return self.store.aux_vector(n)
+
+    def new_group(self, widths: Sequence[int], relu: bool, name: str, grad_dtype: str = "f32",
+                  act: Optional[str] = None) -> List[Act]:
+        g = ActGroup(widths, relu, name, grad_dtype if self.tc else "f32", act)
         self.groups.append(g)
         return g.acts
 
     def note_params(self, params: Sequence[Optional[nn.Parameter]]) -> None:
-        self.param_order.extend(p for p in params if p is not None)
+        self.param_order.extend(p for p in params if isinstance(p, nn.Parameter))
 
     def note_buffers(self, bufs: Sequence[Optional[torch.Tensor]]) -> None:
         self.buffer_order.extend(t for t in bufs if t is not None)
@@ -321,7 +345,7 @@ class LinearStage(Stage):
         # without BatchNorm the backward GEMMs read dZ = d(out) directly (bf16 in tensor-core mode);
         # with BatchNorm d(out) feeds the BN backward kernel (fp32) which emits dZ
         self.outs = b.new_group(widths, relu=(act == "relu"), name=f"{label}.y",
-                                grad_dtype="f32" if self.use_bn else "bf16")
+                                grad_dtype="f32" if self.use_bn else "bf16", act=act)
         self.zs = b.new_group(widths, relu=False, name=f"{label}.z", grad_dtype="bf16") if self.use_bn else None
         if self.use_bn:
             self.zs[0].want(f32=True)
@@ -465,6 +489,7 @@ class LinearStage(Stage):
                     q.B, q.b_rs, q.b_cs = g.W.data_ptr(), 1, g.W._mm_ld
                     q.C, q.ldc = x.gptr, x.gld
                     q.M, q.N, q.K = b.B, g.K, g.N
+                    assert x.dkind in (0, 1), "a GEMM cannot back-propagate into a sigmoid output directly"
                     if x.relu:
                         q.mask, q.ldmask = x.ptr, x.ld
                     q.accumulate = accumulate
@@ -535,6 +560,164 @@ def mlp_stages(b: Builder, items: Sequence[Tuple[Act, nn.Module]], label: str) -
         for i, o in zip(idx, stage.outs):
             cur[i] = o
     return cur
+
+
+# ----------------------------------------------------------------------------------------------
+# element-wise stages (PEPNet) and derived weights (STAR)
+# ----------------------------------------------------------------------------------------------
+class ConcatStage(Stage):
+    """cat(sources, -1) of DETACHED inputs into a fresh buffer without a gradient
+    (pepnet.py:73, :139: ``torch.cat([x.detach(), emb], -1)``)."""
+    name = "concat"
+
+    def __init__(self, b: Builder, sources: List[Act], label: str = ""):
+        self.b, self.sources, self.label = b, sources, label
+        for a in sources:
+            a.want(f32=True)
+        (self.out,) = b.new_group([sum(a.width for a in sources)], relu=False, name=f"{label}.cat")
+        self.out.group.need_grad = False
+
+    def forward(self, stream, training):
+        b, o, at = self.b, self.out, 0
+        for a in self.sources:
+            L.check(b.lib.mmlrec_copy_cols(a.ptr, a.ld, (o.ptr + 4 * at) if o.has_f32 else None, o.ld if o.has_f32 else 0,
+                                           (o.ptr16 + 2 * at) if o.has_bf16 else None, o.ld16 if o.has_bf16 else 0,
+                                           b.B, a.width, stream), f"concat {self.label}")
+            at += a.width
+
+
+class MulStage(Stage):
+    """out_i = a_i * b_i for a list of pairs (pepnet.py:78 ``hidden * gw``, :140 ``feature_gate * dnn_input``);
+    backward writes d(a), d(b) with the producers' activation derivatives folded in."""
+    name = "mul"
+
+    def __init__(self, b: Builder, pairs: List[Tuple[Act, Act]], label: str = ""):
+        self.b, self.pairs, self.label = b, pairs, label
+        for a, c in pairs:
+            assert a.width == c.width
+            a.want(f32=True)
+            c.want(f32=True)
+        self.outs = b.new_group([a.width for a, _ in pairs], relu=False, name=f"{label}.mul", grad_dtype="f32")
+
+    def forward(self, stream, training):
+        b = self.b
+        for (a, c), o in zip(self.pairs, self.outs):
+            L.check(b.lib.mmlrec_mul_forward(a.ptr, a.ld, c.ptr, c.ld, o.ptr if o.has_f32 else None,
+                                             o.ld if o.has_f32 else 0, o.ptr16 if o.has_bf16 else None,
+                                             o.ld16 if o.has_bf16 else 0, b.B, a.width, stream), f"mul fwd {self.label}")
+
+    def plan_backward(self):
+        self.bwd_args = []
+        for (a, c), o in zip(self.pairs, self.outs):
+            if not o.grad_written:
+                continue
+            side = []
+            for t in (a, c):
+                if not t.group.need_grad:
+                    side.append((None, None, 0, 0, 0))
+                    continue
+                f32 = t.grad_is_f32
+                acc = 1 if t.grad_written else 0
+                assert f32 or not acc, "a bf16 gradient buffer cannot be accumulated into"
+                side.append((t.gptr if f32 else None, None if f32 else t.gptr, t.gld, t.dkind, acc))
+                t.grad_written = True
+            self.bwd_args.append((o, a, c, side))
+
+    def backward(self, stream):
+        b = self.b
+        for o, a, c, (sa, sc) in self.bwd_args:
+            L.check(b.lib.mmlrec_mul_backward(o.gptr, o.gld, a.ptr, a.ld, c.ptr, c.ld, sa[0], sa[1], sa[2], sa[3], sa[4],
+                                              sc[0], sc[1], sc[2], sc[3], sc[4], b.B, a.width, stream),
+                    f"mul bwd {self.label}")
+
+
+class DerivedLinear:
+    """Quacks like nn.Linear for LinearSpec / HeadSpec: weight [N,K] (+ bias [N]) living in the aux region."""
+
+    def __init__(self, weight, bias):
+        self.weight, self.bias = weight, bias
+
+
+class StarWeightStage(Stage):
+    """SharedSpecificLinear (model/utils.py:163-223): effective weights W_eff[t] = W_spec[t] * W_shared and
+    biases b_spec[t] + b_shared of ALL domains, materialised once per step in nn.Linear layout
+    ([T*out, in]) so the ordinary grouped-GEMM stages run the layers; backward folds d(W_eff) back into
+    d(W_shared), d(b_shared) and the one registered specific weight (index T-1).  Placed right
+    after the gather so that its backward runs after every wgrad."""
+    name = "star_weights"
+
+    def __init__(self, b: Builder, layers: List[nn.Module], label: str = ""):
+        self.b, self.layers, self.label = b, layers, label
+        self.live_flags = {}
+        self.derived: List[Optional[DerivedLinear]] = []
+        for m in layers:
+            b.note_params([m.shared_weight, m.shared_bias, m.specific_weight, m.specific_bias])
+            K, N = m.in_features, m.out_features
+            T = len(m.spec_weights())
+            w = b.aux_matrix(T * N, K)
+            bias = b.aux_vector(T * N)
+            self.derived.append(None if b.dry else DerivedLinear(w, bias))
+
+    def linear(self, layer: int, t: int) -> Optional[DerivedLinear]:
+        """nn.Linear-like view of domain t of layer `layer` (rows [t*N, (t+1)*N) of the derived matrix)."""
+        if self.b.dry:
+            m = self.layers[layer]
+            return _DryLinear(m.out_features, m.in_features)
+        d, m = self.derived[layer], self.layers[layer]
+        N = m.out_features
+        w = d.weight[t * N:(t + 1) * N]
+        w._mm_off, w._mm_ld, w._mm_span, w._mm_kind = d.weight._mm_off + t * N * d.weight._mm_ld, d.weight._mm_ld, \
+            N * d.weight._mm_ld, "dense"
+        bb = d.bias[t * N:(t + 1) * N]
+        bb._mm_off, bb._mm_ld, bb._mm_span, bb._mm_kind = d.bias._mm_off + t * N, 0, N, "dense"
+        return DerivedLinear(w, bb)
+
+    def finalize(self):
+        b = self.b
+        self.ptrs = []
+        for m in self.layers:
+            sw = b.ints([w.data_ptr() for w in m.spec_weights()], dtype=torch.int64)
+            sb = b.ints([w.data_ptr() for w in m.spec_biases()], dtype=torch.int64)
+            self.ptrs.append((sw, sb))
+        self.live = [b.ints(self.live_flags.get(i, [1] * len(m.spec_weights()))) for i, m in enumerate(self.layers)]
+
+    def set_live(self, layer: int, flags: List[int]):
+        """Domains of `layer` whose effective weight receives a gradient (a per-domain head only uses its own)."""
+        self.live_flags[layer] = list(flags)
+
+    def forward(self, stream, training):
+        b, st = self.b, self.b.store
+        for m, d, (sw, sb) in zip(self.layers, self.derived, self.ptrs):
+            T = len(m.spec_weights())
+            L.check(b.lib.mmlrec_star_weights(sw.data_ptr(), sb.data_ptr(), m.shared_weight.data_ptr(),
+                                              m.shared_bias.data_ptr(), T, m.in_features, m.out_features,
+                                              d.weight.data_ptr(), d.weight._mm_ld,
+                                              st.bf16_ptr(d.weight) if st.dense_bf16 is not None else None,
+                                              d.bias.data_ptr(), stream), f"star weights {self.label}")
+
+    def backward(self, stream):
+        b, st = self.b, self.b.store
+        for i, (m, d, (sw, sb)) in enumerate(zip(self.layers, self.derived, self.ptrs)):
+            T = len(m.spec_weights())
+            live = self.live[i]
+            L.check(b.lib.mmlrec_star_fold(st.grad_ptr(d.weight), d.weight._mm_ld, st.grad_ptr(d.bias), sw.data_ptr(),
+                                           m.shared_weight.data_ptr(), live.data_ptr(), T, m.in_features, m.out_features,
+                                           st.grad_ptr(m.shared_weight), st.grad_ptr(m.shared_bias),
+                                           st.grad_ptr(m.specific_weight), st.grad_ptr(m.specific_bias), stream),
+                    f"star fold {self.label}")
+
+
+class _DryLinear:
+    """Shape-only stand-in used while recording the parameter order."""
+
+    def __init__(self, n, k):
+        self.weight = _DryTensor((n, k))
+        self.bias = _DryTensor((n,))
+
+
+class _DryTensor:
+    def __init__(self, shape):
+        self.shape = shape
 
 
 # ----------------------------------------------------------------------------------------------
@@ -743,8 +926,8 @@ class GateMixStage(Stage):
 # heads + loss
 # ----------------------------------------------------------------------------------------------
 class HeadSpec:
-    def __init__(self, h: Act, final: nn.Module, bias: Optional[nn.Parameter], task: str):
-        self.h, self.final, self.bias, self.task = h, final, bias, task
+    def __init__(self, h: Act, final: nn.Module, bias: Optional[nn.Parameter], task: str, bias2=None):
+        self.h, self.final, self.bias, self.task, self.bias2 = h, final, bias, task, bias2
 
 
 class HeadStage(Stage):
@@ -756,6 +939,7 @@ class HeadStage(Stage):
         self.b, self.heads, self.esmm = b, heads, esmm
         b.note_params([h.final.weight for h in heads])
         b.note_params([h.bias for h in heads])
+        b.note_params([h.bias2 for h in heads])
         self.T = len(heads)
         for h in heads:
             h.h.want(f32=True)
@@ -782,6 +966,8 @@ class HeadStage(Stage):
                 h.h.grad_written = True
             r.dw = st.grad_ptr(h.final.weight)
             r.dbias = st.grad_ptr(h.bias) if h.bias is not None else None
+            if h.bias2 is not None:
+                r.bias2, r.dbias2 = h.bias2.data_ptr(), st.grad_ptr(h.bias2)
             recs.append(r)
         self.table = b.table(recs)
         max_h = max(h.h.width for h in self.heads)

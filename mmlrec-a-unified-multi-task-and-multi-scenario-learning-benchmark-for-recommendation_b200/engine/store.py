@@ -28,7 +28,8 @@ def _align(n: int, a: int) -> int:
 
 class FlatStore:
     def __init__(self, model: nn.Module, ordered: Iterable[nn.Parameter], emb_params: List[nn.Parameter],
-                 device: torch.device, want_bf16: bool, ordered_buffers: Iterable[torch.Tensor] = ()):
+                 device: torch.device, want_bf16: bool, ordered_buffers: Iterable[torch.Tensor] = (),
+                 aux_floats: int = 0):
         self.device = device
         emb_ids = {id(p) for p in emb_params}
         seen, order = set(), []
@@ -47,19 +48,24 @@ class FlatStore:
         for p in order:
             if p.dim() == 2:
                 at = _align(at, 8)
-                lds[id(p)] = _align(p.shape[1], 8)
+                # `_mm_nopad`: matrices only touched by element-wise kernels (STAR's [in,out] tensors) stay dense
+                lds[id(p)] = p.shape[1] if getattr(p, "_mm_nopad", False) else _align(p.shape[1], 8)
                 offs[id(p)] = at
                 at += p.shape[0] * lds[id(p)]
             else:
                 lds[id(p)] = 0
                 offs[id(p)] = at
                 at += p.numel()
-        self.n_dense = _align(max(at, 8), 8)
-        self.dense = torch.zeros(self.n_dense, dtype=torch.float32, device=device)
+        self.n_dense = _align(max(at, 8), 8)          # what the optimizer owns
+        # aux region behind the parameters: derived weights recomputed every step (STAR's spec*shared) and
+        # their gradients; same offsets in dense / dense_grad / dense_bf16, never touched by the optimizer
+        self.aux_base, self.aux_floats, self._aux_at = self.n_dense, _align(aux_floats, 8), 0
+        self.dense = torch.zeros(self.n_dense + self.aux_floats, dtype=torch.float32, device=device)
         self.dense_grad = torch.zeros_like(self.dense)
         self.dense_s1: Optional[torch.Tensor] = None
         self.dense_s2: Optional[torch.Tensor] = None
-        self.dense_bf16 = torch.zeros(self.n_dense, dtype=torch.bfloat16, device=device) if want_bf16 else None
+        self.dense_bf16 = (torch.zeros(self.n_dense + self.aux_floats, dtype=torch.bfloat16, device=device)
+                           if want_bf16 else None)
         # ---- embedding tables
         eoffs, at = {}, 0
         for p in emb_params:
@@ -135,6 +141,31 @@ class FlatStore:
         if self.dense_bf16 is not None:
             self.refresh_bf16()
 
+    # ------------------------------------------------------------------ derived weights
+    def reset_aux(self) -> None:
+        self._aux_at = 0
+
+    def aux_matrix(self, rows: int, cols: int) -> torch.Tensor:
+        """[rows, cols] fp32 view (row stride padded to 8) in the aux region, tagged like a parameter so the
+        GEMM stages can use it as a weight; every step program asks for its derived tensors in the same
+        order, so all programs of a model share them."""
+        ld = _align(cols, 8) if rows > 1 or cols > 1 else 1
+        self._aux_at = _align(self._aux_at, 8)
+        off = self.aux_base + self._aux_at
+        assert self._aux_at + rows * ld <= self.aux_floats, "aux region too small"
+        self._aux_at += rows * ld
+        t = self.dense[off:off + rows * ld].view(rows, ld)[:, :cols]
+        t._mm_off, t._mm_ld, t._mm_span, t._mm_kind = off, ld, rows * ld, "dense"
+        return t
+
+    def aux_vector(self, n: int) -> torch.Tensor:
+        off = self.aux_base + self._aux_at
+        assert self._aux_at + n <= self.aux_floats, "aux region too small"
+        self._aux_at += n
+        t = self.dense[off:off + n]
+        t._mm_off, t._mm_ld, t._mm_span, t._mm_kind = off, 0, n, "dense"
+        return t
+
     # ------------------------------------------------------------------ views / pointers
     def ptr(self, p: torch.Tensor) -> int:
         return p.data_ptr()
@@ -160,17 +191,17 @@ class FlatStore:
 
     def refresh_bf16(self) -> None:
         if self.dense_bf16 is not None:
-            self.dense_bf16.copy_(self.dense)
+            self.dense_bf16[:self.n_dense].copy_(self.dense[:self.n_dense])
 
     # ------------------------------------------------------------------ optimizer state
     def ensure_optimizer_state(self, optimizer: str) -> None:
         need1 = optimizer in ("adagrad", "adam", "rmsprop")
         need2 = optimizer == "adam"
         if need1 and self.dense_s1 is None:
-            self.dense_s1 = torch.zeros_like(self.dense)
+            self.dense_s1 = torch.zeros(self.n_dense, dtype=torch.float32, device=self.device)
             self.emb_s1 = torch.zeros_like(self.emb)
         if need2 and self.dense_s2 is None:
-            self.dense_s2 = torch.zeros_like(self.dense)
+            self.dense_s2 = torch.zeros(self.n_dense, dtype=torch.float32, device=self.device)
             self.emb_s2 = torch.zeros_like(self.emb)
             self.row_touch = torch.full((max(self.n_emb // max(self.emb_dim, 1), 1),), -1, dtype=torch.int32,
                                         device=self.device)

@@ -80,7 +80,7 @@ class GateLevel(C.Structure):
 class Head(C.Structure):
     _fields_ = [("h", vp), ("ld_h", i64), ("H", i32), ("kind", i32), ("w", vp), ("bias", vp),
                 ("d_h", vp), ("ld_d_h", i64), ("relu_mask", i32), ("pad0", i32), ("dw", vp), ("dbias", vp),
-                ("d_h_bf16", vp), ("ld_d_h_bf16", i64)]
+                ("d_h_bf16", vp), ("ld_d_h_bf16", i64), ("bias2", vp), ("dbias2", vp)]
 
 
 _SIGNATURES = {
@@ -111,6 +111,11 @@ _SIGNATURES = {
     "mmlrec_heads_forward_backward": (C.c_int, [vp, i32, i32, vp, i64, vp, i64, vp, i32, i32, vp, i64, vp, vp]),
     "mmlrec_heads_scratch": (i64, [i32, i32, i32]),
     "mmlrec_dense_optimizer_step": (C.c_int, [vp, vp, vp, vp, i64, vp, vp, vp]),
+    "mmlrec_copy_cols": (C.c_int, [vp, i64, vp, i64, vp, i64, i32, i32, vp]),
+    "mmlrec_mul_forward": (C.c_int, [vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, vp]),
+    "mmlrec_mul_backward": (C.c_int, [vp, i64, vp, i64, vp, i64, vp, vp, i64, i32, i32, vp, vp, i64, i32, i32, i32, i32, vp]),
+    "mmlrec_star_weights": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, vp, i64, vp, vp, vp]),
+    "mmlrec_star_fold": (C.c_int, [vp, i64, vp, vp, vp, vp, i32, i32, i32, vp, vp, vp, vp, vp]),
     "mmlrec_fill_f32": (C.c_int, [vp, i64, f32, vp]),
     "mmlrec_cast_f32_to_bf16": (C.c_int, [vp, i64, vp, i64, i32, i32, i32, vp]),
     "mmlrec_cast_bf16_to_f32": (C.c_int, [vp, i64, vp, i64, i32, i32, vp]),

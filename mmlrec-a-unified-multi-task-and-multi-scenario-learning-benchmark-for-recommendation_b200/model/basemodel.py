@@ -154,7 +154,7 @@ class BaseModel(nn.Module):
         self.build_graph(dry)
         emb_params = [t[0] for t in self.embedding_layout]
         self.store = FlatStore(self, dry.param_order, emb_params, self.device_obj, want_bf16=self.precision == "bf16",
-                               ordered_buffers=dry.buffer_order)
+                               ordered_buffers=dry.buffer_order, aux_floats=dry.aux_floats + 64)
         self._index_features()  # re-read the re-pointed table parameters
 
     def _require_cuda(self):

@@ -77,6 +77,12 @@ def test_same_state_dict_keys_and_seeded_init_as_reference(case):
     assert set(sd) == set(ref)
     for k, v in ref.items():
         assert np.array_equal(sd[k].numpy(), v), k
+    # STAR: the unregistered per-domain tensors must come out of the same RNG draws too
+    for k in z.files:
+        if ".specific_weights." in k or ".specific_biases." in k:
+            prefix, kind, idx = k[5:].rsplit(".", 2)
+            name = ("frozen_weight_" if kind == "specific_weights" else "frozen_bias_") + idx
+            assert np.array_equal(getattr(model.get_submodule(prefix), name).numpy(), z[k]), k
 
 
 def test_no_cpu_compute_path():
