@@ -235,8 +235,17 @@ def gemm_roofline(model, plan, tf_burst, which, iters=20):
             total_flops += flops
             per.append({"launch": f"{label}:{s.label}", "ms": ms, "tflops": flops / (ms * 1e-3) / 1e12})
     ach = total_flops / (total_ms * 1e-3) / 1e12
+    # DRAM bytes per launch (read + write) from the committed `ncu --set full` capture of this workload
+    traffic, traffic_src = None, None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "tc_gemm_traffic_r01.json")
+    if plan.b.tc and os.path.exists(tpath) and per:
+        t = json.load(open(tpath))
+        if len(t["dram_bytes_per_launch"]) == len(per):
+            traffic = t["dram_bytes_per_step"] / len(per)
+            traffic_src = "profiles/tc_gemm_traffic_r01.json (ncu --set full, mean over the step's launches)"
     return {"kernel": "gemm_grouped_tc_kernel" if plan.b.tc else "gemm_grouped_f32_kernel", "bound": "tensor",
-            "achieved": ach, "peak": tf_burst, "unit": "TFLOP/s", "frac": ach / tf_burst, "traffic": None,
+            "achieved": ach, "peak": tf_burst, "unit": "TFLOP/s", "frac": ach / tf_burst, "traffic": traffic,
+            "traffic_unit": "bytes/launch", "traffic_source": traffic_src,
             "peak_source": which + " (bf16 cuBLAS burst)", "launches_per_step": len(per),
             "flops_per_step": total_flops, "ms_per_step_in_gemm": total_ms, "per_launch": per}
 

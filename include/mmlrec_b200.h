@@ -166,6 +166,14 @@ int64_t mmlrec_tc_record_bytes(void);
 int mmlrec_tc_encode_problem(const MmlrecGemmTcDesc* desc_host, void* record_host);
 int mmlrec_gemm_grouped_tc(const void* records, const int32_t* tile_prefix, int32_t n_problems,
                            int32_t total_tiles, void* stream);
+/* same launch with a caller-supplied static schedule: CTA b (of n_ctas) executes tiles
+ * tile_order[cta_start[b] .. cta_start[b+1]) in that order (int32 device arrays).  Lets the host balance long
+ * (wgrad, K = batch) and short (dgrad, K = layer width) tiles across the SMs; deterministic, no atomics. */
+int mmlrec_gemm_grouped_tc_scheduled(const void* records, const int32_t* tile_prefix, int32_t n_problems,
+                                     int32_t total_tiles, const int32_t* tile_order, const int32_t* cta_start,
+                                     int32_t n_ctas, void* stream);
+/* SM count of the current device (the scheduler's CTA budget); 0 without a device */
+int32_t mmlrec_tc_sm_count(void);
 /* same launch, plus per-tile clock64() stamps of CTA 0 into stamps[64][16] (int64, device): slots 0-3 TMA
  * producer (tile start, table read, first slot free, last load issued), 4-7 MMA issuer (tile start,
  * accumulator free, first operands landed, last commit), 8-11 epilogue (tile start, bias staged,

@@ -10,11 +10,11 @@
 
 namespace mmlrec {
 
-constexpr int GL_MAXG = MMLREC_LEVEL_MAX_GATES;
+constexpr int GL_MAXG = MMLREC_LEVEL_MAX_GATES;   // register arrays are sized by this
 constexpr int GL_FWD_WARPS = 8;            // forward: 8 warps x 1 sample
-constexpr int GL_BWD_WARPS = 16;           // backward: 16 warps x 2 samples = 32 samples per CTA
-constexpr int GL_BWD_ROWS = 32;
-constexpr int GL_BATCH = 8;                // expert rows fetched together (8 x 128-bit loads in flight per lane)
+constexpr int GL_BWD_WARPS = 8;            // backward: 8 warps x 1 sample = 8 samples per CTA
+constexpr int GL_BWD_ROWS = 8;
+constexpr int GL_BATCH = 4;                // expert rows fetched together (4 x 128-bit loads in flight per lane)
 
 __device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 __device__ __forceinline__ float dot4(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
@@ -66,7 +66,7 @@ __device__ __forceinline__ void stage_level(const MmlrecGateLevel* lv, MmlrecGat
   __syncthreads();
 }
 
-__global__ void __launch_bounds__(GL_FWD_WARPS * 32) gate_level_forward_kernel(const MmlrecGateLevel* lv, int B) {
+__global__ void __launch_bounds__(GL_FWD_WARPS * 32, 4) gate_level_forward_kernel(const MmlrecGateLevel* lv, int B) {
   __shared__ MmlrecGateLevel L;
   __shared__ float wg_s[MMLREC_LEVEL_MAX_WG];
   __shared__ int wg_off[GL_MAXG + 1];
@@ -128,13 +128,12 @@ __global__ void __launch_bounds__(GL_FWD_WARPS * 32) gate_level_forward_kernel(c
 }
 
 // dynamic smem: dl_s [32 rows][total_ne] + gin_s [32 rows][total_hg]   (total_ne = sum n_e, total_hg = sum Hg)
-__global__ void __launch_bounds__(GL_BWD_WARPS * 32)
-gate_level_backward_kernel(const MmlrecGateLevel* lv, int B, float* scratch, int32_t* counter) {
+__global__ void __launch_bounds__(GL_BWD_WARPS * 32, 3)
+gate_level_backward_kernel(const MmlrecGateLevel* lv, int B, float* scratch) {
   extern __shared__ __align__(16) float dyn_s[];
   __shared__ MmlrecGateLevel L;
   __shared__ float wg_s[MMLREC_LEVEL_MAX_WG];
   __shared__ int wg_off[GL_MAXG + 1], ne_off[GL_MAXG + 1], hg_off[GL_MAXG + 1];
-  __shared__ int s_last;
   stage_level(lv, L, wg_s, wg_off);
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int G = L.n_gates, H = L.H;
@@ -148,8 +147,8 @@ gate_level_backward_kernel(const MmlrecGateLevel* lv, int B, float* scratch, int
   float* dl_s = dyn_s;                            // [32][total_ne]
   float* gin_s = dyn_s + GL_BWD_ROWS * total_ne;  // [32][total_hg]
   const int r0 = blockIdx.x * GL_BWD_ROWS;
-  for (int rr = 0; rr < 2; ++rr) {
-    const int r = w * 2 + rr;
+  for (int rr = 0; rr < 1; ++rr) {
+    const int r = w;
     const int b = r0 + r;
     if (b >= B) {  // rows past the batch contribute zeros to the CTA partial
       for (int i = lane; i < total_ne; i += 32) dl_s[r * total_ne + i] = 0.f;
@@ -265,33 +264,28 @@ gate_level_backward_kernel(const MmlrecGateLevel* lv, int B, float* scratch, int
     for (int r = 0; r < GL_BWD_ROWS; ++r) s = fmaf(dlp[r * total_ne], gp[r * total_hg], s);
     part[i] = s;
   }
-  __threadfence();
+}
+
+// deterministic reduction of the CTA partials: 32 outputs x 8 partial-groups per CTA; each thread sums every
+// 8th partial of its output (coalesced across outputs), the 8 group sums are added in a fixed order
+__global__ void __launch_bounds__(256)
+gate_level_dwg_reduce_kernel(const MmlrecGateLevel* lv, const float* scratch, int n_cta, int total_wg) {
+  __shared__ float red[8][33];
+  const int ix = threadIdx.x & 31, iy = threadIdx.x >> 5;
+  const int i = blockIdx.x * 32 + ix;
+  float s = 0.f;
+  if (i < total_wg) for (int c = iy; c < n_cta; c += 8) s += scratch[(int64_t)c * total_wg + i];
+  red[iy][ix] = s;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    const int t = atomicAdd(counter, 1);
-    s_last = (t == (int)gridDim.x - 1) ? 1 : 0;
-    if (s_last) *counter = 0;
-  }
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  for (int i = threadIdx.x; i < total_wg; i += blockDim.x) {
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;  // four independent chains (fixed association)
-    int c = 0;
-    for (; c + 3 < (int)gridDim.x; c += 4) {
-      s0 += scratch[(int64_t)c * total_wg + i];
-      s1 += scratch[(int64_t)(c + 1) * total_wg + i];
-      s2 += scratch[(int64_t)(c + 2) * total_wg + i];
-      s3 += scratch[(int64_t)(c + 3) * total_wg + i];
-    }
-    for (; c < (int)gridDim.x; ++c) s0 += scratch[(int64_t)c * total_wg + i];
-    const float s = (s0 + s1) + (s2 + s3);
-    int g = 0;
-    while (g + 1 < G && wg_off[g + 1] <= i) ++g;
-    if (L.d_mix[g] != nullptr) {
-      const int local = i - wg_off[g], Hg = L.Hg[g];
-      L.dWg[g][(int64_t)(local / Hg) * L.ld_Wg[g] + (local % Hg)] = s;
-    }
+  if (iy != 0 || i >= total_wg) return;
+  float t = 0.f;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) t += red[k][ix];
+  int g = 0, off = 0;
+  while (g + 1 < lv->n_gates && off + lv->n_e[g] * lv->Hg[g] <= i) { off += lv->n_e[g] * lv->Hg[g]; ++g; }
+  if (lv->d_mix[g] != nullptr) {
+    const int local = i - off, Hg = lv->Hg[g];
+    lv->dWg[g][(int64_t)(local / Hg) * lv->ld_Wg[g] + (local % Hg)] = t;
   }
 }
 
@@ -321,6 +315,9 @@ extern "C" int mmlrec_gate_level_backward(const MmlrecGateLevel* level, int32_t 
     if (e != cudaSuccess) { set_error("gate_level_backward: smem opt-in failed"); return (int)e; }
     opted = smem;
   }
-  gate_level_backward_kernel<<<cdiv(B, GL_BWD_ROWS), GL_BWD_WARPS * 32, smem, (cudaStream_t)stream>>>(level, B, scratch, counter);
+  const int n_cta = cdiv(B, GL_BWD_ROWS);
+  gate_level_backward_kernel<<<n_cta, GL_BWD_WARPS * 32, smem, (cudaStream_t)stream>>>(level, B, scratch);
+  MMLREC_CHECK_LAUNCH(1);
+  gate_level_dwg_reduce_kernel<<<cdiv(total_wg, 32), 256, 0, (cudaStream_t)stream>>>(level, scratch, n_cta, total_wg);
   MMLREC_RETURN_LAUNCH(1);
 }

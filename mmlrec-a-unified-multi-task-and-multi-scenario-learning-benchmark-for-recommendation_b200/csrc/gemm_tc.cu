@@ -16,7 +16,7 @@
 namespace mmlrec {
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64;
-constexpr int TC_STAGES = 4;
+constexpr int TC_STAGES = 5;
 constexpr int TC_ACC_STAGES = 2;
 constexpr int TC_ACC_COLS = 256;                 // TMEM columns per accumulator stage (128 main + 16 row-sum, padded)
 constexpr int TC_TMEM_COLS = 512;
@@ -189,6 +189,7 @@ __device__ __forceinline__ TileCoord locate_tile(int t, const int32_t* s_prefix,
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_grouped_tc_kernel(const TcRecord* __restrict__ recs, const int32_t* __restrict__ prefix, int n_problems, int total_tiles,
+                       const int32_t* __restrict__ tile_order, const int32_t* __restrict__ cta_start,
                        long long* __restrict__ dbg) {
   extern __shared__ unsigned char smem_dyn[];
   // 1024-byte alignment is required by the 128B swizzle atom
@@ -227,6 +228,11 @@ gemm_grouped_tc_kernel(const TcRecord* __restrict__ recs, const int32_t* __restr
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // this CTA's tiles: a host-computed balanced schedule (tile_order[cta_start[b] .. cta_start[b+1])) or,
+  // without one, round-robin over the tile index space
+  const int sched_begin = tile_order ? cta_start[blockIdx.x] : (int)blockIdx.x;
+  const int sched_end = tile_order ? cta_start[blockIdx.x + 1] : total_tiles;
+  const int sched_step = tile_order ? 1 : (int)gridDim.x;
   // optional per-tile clock stamps of CTA 0 (debug timeline): dbg[tile_iter * 16 + slot]
   const bool stamp = dbg != nullptr && blockIdx.x == 0;
 #define TC_STAMP(iter, slot) do { if (stamp && (iter) < 64) dbg[(iter) * 16 + (slot)] = clock64(); } while (0)
@@ -236,7 +242,8 @@ gemm_grouped_tc_kernel(const TcRecord* __restrict__ recs, const int32_t* __restr
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
       int pit = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++pit) {
+      for (int ti = sched_begin; ti < sched_end; ti += sched_step, ++pit) {
+        const int t = tile_order ? __ldg(tile_order + ti) : ti;
         TC_STAMP(pit, 0);
         const TileCoord tc = locate_tile(t, s_prefix, s_tiles_n, n_problems);
         const TcRecord* R = recs + tc.pi;
@@ -275,7 +282,8 @@ gemm_grouped_tc_kernel(const TcRecord* __restrict__ recs, const int32_t* __restr
       int acc = 0; uint32_t acc_phase = 0;
       const uint64_t ones_desc = make_smem_desc(smem_u32(sOnes), false);
       int mit = 0;
-      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++mit) {
+      for (int ti = sched_begin; ti < sched_end; ti += sched_step, ++mit) {
+        const int t = tile_order ? __ldg(tile_order + ti) : ti;
         const TileCoord tc = locate_tile(t, s_prefix, s_tiles_n, n_problems);
         const TcRecord* R = recs + tc.pi;
         const int K = R->K;
@@ -322,7 +330,8 @@ gemm_grouped_tc_kernel(const TcRecord* __restrict__ recs, const int32_t* __restr
     float* my_stage = stage_s + ew * TC_STAGE_TILE_FLOATS;
     int acc = 0; uint32_t acc_phase = 0;
     int it = 0;
-    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x, ++it) {
+    for (int ti = sched_begin; ti < sched_end; ti += sched_step, ++it) {
+      const int t = tile_order ? __ldg(tile_order + ti) : ti;
       const TileCoord tc = locate_tile(t, s_prefix, s_tiles_n, n_problems);
       const TcRecord* R = recs + tc.pi;
       const int M = R->M, N = R->N;
@@ -542,34 +551,51 @@ extern "C" int mmlrec_tc_encode_problem(const MmlrecGemmTcDesc* d, void* record_
   return 0;
 }
 
-static int launch_tc(const void* records, const int32_t* tile_prefix, int32_t n_problems, int32_t total_tiles,
-                     long long* dbg, void* stream) {
-  MMLREC_CHECK_ARG(records && tile_prefix && n_problems > 0 && total_tiles >= 0, "bad args");
-  MMLREC_CHECK_ARG(((uintptr_t)records & 127) == 0, "record table must be 128-byte aligned");
-  MMLREC_CHECK_ARG(n_problems <= TC_MAX_PROBLEMS, "too many problems in one launch (split the table)");
-  if (total_tiles == 0) return 0;
+static int tc_sm_count() {
   static int sm_count = 0;
-  static bool opted = false;
-  if (!opted) {
+  if (!sm_count) {
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
+  }
+  return sm_count;
+}
+
+static int launch_tc(const void* records, const int32_t* tile_prefix, int32_t n_problems, int32_t total_tiles,
+                     const int32_t* tile_order, const int32_t* cta_start, int32_t n_ctas, long long* dbg, void* stream) {
+  MMLREC_CHECK_ARG(records && tile_prefix && n_problems > 0 && total_tiles >= 0, "bad args");
+  MMLREC_CHECK_ARG(((uintptr_t)records & 127) == 0, "record table must be 128-byte aligned");
+  MMLREC_CHECK_ARG(n_problems <= TC_MAX_PROBLEMS, "too many problems in one launch (split the table)");
+  MMLREC_CHECK_ARG((tile_order == nullptr) == (cta_start == nullptr), "tile_order and cta_start come together");
+  if (total_tiles == 0) return 0;
+  static bool opted = false;
+  if (!opted) {
     cudaError_t e = cudaFuncSetAttribute(gemm_grouped_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
     if (e != cudaSuccess) { set_error("gemm_tc: smem opt-in failed: %s", cudaGetErrorString(e)); return (int)e; }
     opted = true;
   }
-  int grid = total_tiles < sm_count ? total_tiles : sm_count;
+  int grid = tile_order ? n_ctas : (total_tiles < tc_sm_count() ? total_tiles : tc_sm_count());
+  MMLREC_CHECK_ARG(grid > 0, "empty grid");
   gemm_grouped_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, (cudaStream_t)stream>>>(
-      reinterpret_cast<const TcRecord*>(records), tile_prefix, n_problems, total_tiles, dbg);
+      reinterpret_cast<const TcRecord*>(records), tile_prefix, n_problems, total_tiles, tile_order, cta_start, dbg);
   MMLREC_RETURN_LAUNCH(1);
 }
 
+extern "C" int32_t mmlrec_tc_sm_count(void) { return tc_sm_count(); }
+
 extern "C" int mmlrec_gemm_grouped_tc(const void* records, const int32_t* tile_prefix, int32_t n_problems,
                                       int32_t total_tiles, void* stream) {
-  return launch_tc(records, tile_prefix, n_problems, total_tiles, nullptr, stream);
+  return launch_tc(records, tile_prefix, n_problems, total_tiles, nullptr, nullptr, 0, nullptr, stream);
+}
+
+extern "C" int mmlrec_gemm_grouped_tc_scheduled(const void* records, const int32_t* tile_prefix, int32_t n_problems,
+                                                int32_t total_tiles, const int32_t* tile_order,
+                                                const int32_t* cta_start, int32_t n_ctas, void* stream) {
+  return launch_tc(records, tile_prefix, n_problems, total_tiles, tile_order, cta_start, n_ctas, nullptr, stream);
 }
 
 extern "C" int mmlrec_gemm_grouped_tc_debug(const void* records, const int32_t* tile_prefix, int32_t n_problems,
                                             int32_t total_tiles, int64_t* stamps, void* stream) {
-  return launch_tc(records, tile_prefix, n_problems, total_tiles, reinterpret_cast<long long*>(stamps), stream);
+  return launch_tc(records, tile_prefix, n_problems, total_tiles, nullptr, nullptr, 0,
+                   reinterpret_cast<long long*>(stamps), stream);
 }

@@ -164,7 +164,31 @@ class Builder:
         rec = torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8).to(self.device)
         assert rec.data_ptr() % 128 == 0
         self.keep.append(rec)
-        return rec, self.ints(pre), len(descs), at
+        order, starts, n_ctas = self._tc_schedule(descs, pre)
+        return rec, self.ints(pre), len(descs), at, self.ints(order), self.ints(starts), n_ctas
+
+    def _tc_schedule(self, descs, pre):
+        """Static longest-processing-time schedule of the launch's 128x128 tiles over the SMs.  Tile cost model
+        (cycles, from profiles/tc_epilogue_timeline_r01.txt): ~750 per 64-wide k-block + ~3000 per epilogue."""
+        import heapq
+        n_sm = max(int(self.lib.mmlrec_tc_sm_count()), 1)
+        tiles = []
+        for i, d in enumerate(descs):
+            cost = 750 * ((d.K + 63) // 64) + 3000
+            tiles.extend((cost, t) for t in range(pre[i], pre[i + 1]))
+        n_ctas = min(n_sm, len(tiles))
+        tiles.sort(key=lambda ct: (-ct[0], ct[1]))
+        heap = [(0, c) for c in range(n_ctas)]
+        lists = [[] for _ in range(n_ctas)]
+        for cost, t in tiles:
+            load, c = heapq.heappop(heap)
+            lists[c].append(t)
+            heapq.heappush(heap, (load + cost, c))
+        order, starts = [], [0]
+        for lst in lists:
+            order.extend(lst)
+            starts.append(len(order))
+        return order, starts, n_ctas
 
     def aux_matrix(self, rows: int, cols: int):
         if self.dry:
@@ -434,8 +458,13 @@ class LinearStage(Stage):
         return [self.b.tc_table(descs[i:i + self.MAX_TC_PROBLEMS]) for i in range(0, len(descs), self.MAX_TC_PROBLEMS)]
 
     def _launch(self, tbl, stream, what):
-        fn = self.b.lib.mmlrec_gemm_grouped_tc if self.b.tc else self.b.lib.mmlrec_gemm_grouped_f32
-        L.check(fn(tbl[0].data_ptr(), tbl[1].data_ptr(), tbl[2], tbl[3], stream), f"{what} {self.label}")
+        lib = self.b.lib
+        if self.b.tc:
+            rc = lib.mmlrec_gemm_grouped_tc_scheduled(tbl[0].data_ptr(), tbl[1].data_ptr(), tbl[2], tbl[3],
+                                                      tbl[4].data_ptr(), tbl[5].data_ptr(), tbl[6], stream)
+        else:
+            rc = lib.mmlrec_gemm_grouped_f32(tbl[0].data_ptr(), tbl[1].data_ptr(), tbl[2], tbl[3], stream)
+        L.check(rc, f"{what} {self.label}")
 
     def forward(self, stream, training):
         b = self.b

@@ -98,6 +98,8 @@ _SIGNATURES = {
     "mmlrec_tc_record_bytes": (i64, []),
     "mmlrec_tc_encode_problem": (C.c_int, [C.POINTER(GemmTcDesc), vp]),
     "mmlrec_gemm_grouped_tc": (C.c_int, [vp, vp, i32, i32, vp]),
+    "mmlrec_gemm_grouped_tc_scheduled": (C.c_int, [vp, vp, i32, i32, vp, vp, i32, vp]),
+    "mmlrec_tc_sm_count": (i32, []),
     "mmlrec_gemm_grouped_tc_debug": (C.c_int, [vp, vp, i32, i32, vp, vp]),
     "mmlrec_tc_num_tiles": (i32, [i32, i32]),
     "mmlrec_bn_forward": (C.c_int, [vp, i64, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, i64, vp, i64, i32, i32, vp]),
