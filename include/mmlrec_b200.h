@@ -274,6 +274,15 @@ int mmlrec_gate_level_backward(const MmlrecGateLevel* level, int32_t B, int32_t 
                                float* scratch, int32_t* counter /* one int32, zero-initialised once */, void* stream);
 /* scratch floats for mmlrec_gate_level_backward */
 int64_t mmlrec_gate_level_backward_scratch(int32_t total_wg, int32_t B);
+/* Tiled backward of the same stage (default when it fits): a CTA stages the rows of 8 samples in shared
+ * memory (cp.async) and runs the five phases from there.  Extra requirements: every Hg % 4 == 0, gate_in /
+ * d_gate_in / Wg rows 16-byte aligned (pointer and row stride), and the _smem() figure <= 110 KB. */
+int mmlrec_gate_level_backward_tiled(const MmlrecGateLevel* level, int32_t B, int32_t n_gates, int32_t n_experts,
+                                     int32_t H, int32_t total_wg, int32_t total_ne, int32_t total_hg,
+                                     float* scratch, void* stream);
+int64_t mmlrec_gate_level_backward_tiled_scratch(int32_t total_wg, int32_t B);
+int64_t mmlrec_gate_level_backward_tiled_smem(int32_t n_gates, int32_t n_experts, int32_t H, int32_t total_wg,
+                                              int32_t total_ne, int32_t total_hg);
 
 /* ---------------------------------------------------------------------------------------------
  * Heads + loss, forward and backward in one pass (training) or forward only (predict).

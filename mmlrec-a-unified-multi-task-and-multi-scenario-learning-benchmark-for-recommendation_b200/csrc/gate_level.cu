@@ -266,6 +266,271 @@ gate_level_backward_kernel(const MmlrecGateLevel* lv, int B, float* scratch) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Tiled backward (the default): a CTA owns GT_ROWS samples.  Every row it needs -- d(mix) of the live
+// gates, the level's expert activations, the gate inputs, the gate-head weights -- is brought into
+// shared memory once with cp.async; the five phases then run from shared memory with work mapped so
+// that almost every issued instruction is a 128-bit LDS or an FMA:
+//   P1  dp[r][g][e]   = <d_mix[r][g], expert[r][u(g,e)]>        8 lanes per dot product
+//   P2  dlogit        = p * (dp - <p, dp>)                       thread <-> (sample, gate)
+//   P3  d_expert[r][u]= relu'(.) sum_{g uses u} p * d_mix[r][g]   warp <-> (sample, expert), lane <-> 4 columns
+//   P4  d_gate_in[r][g]= dlogit Wg                                warp <-> sample, gates in order (shared inputs accumulate)
+//   P5  CTA partial of dWg = sum_r dlogit[r] (x) gate_in[r]       thread <-> 4 columns of one (gate, expert) row
+// dynamic smem (floats): Wg [total_wg] | d_mix [R][G][H] | expert [R][E][H] | gate_in [R][total_hg]
+//                        | p [R][total_ne] | dp/dlogit [R][total_ne]
+// ------------------------------------------------------------------------------------------------
+constexpr int GT_ROWS = 8;
+constexpr int GT_THREADS = 256;
+constexpr int GT_WARPS = GT_THREADS / 32;
+constexpr int GT_MAXP = GL_MAXG * MMLREC_LEVEL_MAX_EXPERTS;
+
+struct GtTables {
+  int wg_off[GL_MAXG + 1], ne_off[GL_MAXG + 1], hg_off[GL_MAXG + 1], pair_off[GL_MAXG + 1];
+  uint8_t live[GL_MAXG];
+  uint8_t pair_g[GT_MAXP], pair_u[GT_MAXP];
+  uint16_t pair_col[GT_MAXP];                       // column of the pair in the [total_ne] rows
+  uint8_t ucnt[MMLREC_LEVEL_MAX_EXPERTS], ug[MMLREC_LEVEL_MAX_EXPERTS][GL_MAXG];
+  uint16_t ucol[MMLREC_LEVEL_MAX_EXPERTS][GL_MAXG];
+  // rows to stage: d_mix of the live gates, used experts, gate inputs of the live gates
+  const float* src[2 * GL_MAXG + MMLREC_LEVEL_MAX_EXPERTS];
+  int64_t src_ld[2 * GL_MAXG + MMLREC_LEVEL_MAX_EXPERTS];
+  int dst_off[2 * GL_MAXG + MMLREC_LEVEL_MAX_EXPERTS], dst_stride[2 * GL_MAXG + MMLREC_LEVEL_MAX_EXPERTS];
+  int n4[2 * GL_MAXG + MMLREC_LEVEL_MAX_EXPERTS];
+};
+
+__device__ __forceinline__ void fma4(float4& acc, float s, const float4& v) {
+  acc.x = fmaf(s, v.x, acc.x); acc.y = fmaf(s, v.y, acc.y); acc.z = fmaf(s, v.z, acc.z); acc.w = fmaf(s, v.w, acc.w);
+}
+
+__global__ void __launch_bounds__(GT_THREADS, 2)
+gate_level_backward_tiled_kernel(const MmlrecGateLevel* lv, int B, float* scratch) {
+  extern __shared__ __align__(16) float dyn_s[];
+  __shared__ __align__(16) MmlrecGateLevel L;
+  __shared__ GtTables T;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  for (int i = tid; i < (int)(sizeof(MmlrecGateLevel) / 4); i += GT_THREADS)
+    reinterpret_cast<uint32_t*>(&L)[i] = reinterpret_cast<const uint32_t*>(lv)[i];
+  __syncthreads();
+  const int G = L.n_gates, E = L.n_experts, H = L.H, H4 = H >> 2;
+  if (tid == 0) {
+    int a = 0, c = 0, d = 0, p = 0;
+    for (int g = 0; g < G; ++g) {
+      T.wg_off[g] = a; T.ne_off[g] = c; T.hg_off[g] = d; T.pair_off[g] = p;
+      const bool lv_g = L.d_mix[g] != nullptr;
+      T.live[g] = lv_g ? 1 : 0;
+      a += L.n_e[g] * L.Hg[g]; c += L.n_e[g]; d += L.Hg[g];
+      if (lv_g) p += L.n_e[g];
+    }
+    T.wg_off[G] = a; T.ne_off[G] = c; T.hg_off[G] = d; T.pair_off[G] = p;
+  }
+  __syncthreads();
+  // pair table (thread <-> (gate, slot)) and per-expert user lists (thread <-> expert)
+  for (int i = tid; i < G * 32; i += GT_THREADS) {
+    const int g = i >> 5, e = i & 31;
+    if (T.live[g] && e < L.n_e[g]) {
+      int u = 0;
+      while (u + 1 < E && L.slot[u][g] != e) ++u;
+      const int p = T.pair_off[g] + e;
+      T.pair_g[p] = (uint8_t)g; T.pair_u[p] = (uint8_t)u; T.pair_col[p] = (uint16_t)(T.ne_off[g] + e);
+    }
+  }
+  if (tid < E) {
+    int n = 0;
+    for (int g = 0; g < G; ++g) {
+      const int sl = L.slot[tid][g];
+      if (T.live[g] && sl >= 0) { T.ug[tid][n] = (uint8_t)g; T.ucol[tid][n] = (uint16_t)(T.ne_off[g] + sl); ++n; }
+    }
+    T.ucnt[tid] = (uint8_t)n;
+  }
+  __syncthreads();
+  const int total_wg = T.wg_off[G], total_ne = T.ne_off[G], total_hg = T.hg_off[G], n_pairs = T.pair_off[G];
+  float* wg_s = dyn_s;
+  float* dm_s = wg_s + total_wg;
+  float* eo_s = dm_s + GT_ROWS * G * H;
+  float* gin_s = eo_s + GT_ROWS * E * H;
+  float* p_s = gin_s + GT_ROWS * total_hg;
+  float* dl_s = p_s + GT_ROWS * total_ne;
+  const int r0 = blockIdx.x * GT_ROWS;
+
+  // ---- stage: source list (thread <-> source), then a warp per source walks the CTA's samples;
+  // one cp.async per lane and 16 bytes
+  const int per_row = 2 * G + E;
+  if (tid < per_row) {
+    const int v = tid;
+    const float* src = nullptr; int64_t ld = 0; int off = 0, stride = 0, n4 = 0;
+    if (v < G) {
+      if (T.live[v]) { src = L.d_mix[v]; ld = L.ld_d_mix[v]; off = (int)(dm_s - dyn_s) + v * H; stride = G * H; n4 = H4; }
+    } else if (v < G + E) {
+      const int u = v - G;
+      if (T.ucnt[u]) { src = L.expert[u]; ld = L.ld_expert; off = (int)(eo_s - dyn_s) + u * H; stride = E * H; n4 = H4; }
+    } else {
+      const int g = v - G - E;
+      if (T.live[g]) { src = L.gate_in[g]; ld = L.ld_gate_in[g]; off = (int)(gin_s - dyn_s) + T.hg_off[g]; stride = total_hg; n4 = L.Hg[g] >> 2; }
+    }
+    T.src[v] = src; T.src_ld[v] = ld; T.dst_off[v] = off; T.dst_stride[v] = stride; T.n4[v] = n4;
+  }
+  __syncthreads();
+  for (int v = w; v < per_row; v += GT_WARPS) {
+    const int n4 = T.n4[v];
+    if (n4 == 0) continue;
+    const int64_t ld = T.src_ld[v];
+    const float* src = T.src[v] + (int64_t)r0 * ld + 4 * lane;
+    float* dst = dyn_s + T.dst_off[v] + 4 * lane;
+    const int stride = T.dst_stride[v];
+    const bool zero_tail = v >= G + E;   // gate inputs of rows past the batch add zeros to the dWg partial
+#pragma unroll
+    for (int r = 0; r < GT_ROWS; ++r) {
+      if (r0 + r < B) {
+        for (int q = lane; q < n4; q += 32) cp_async_16(dst + r * stride + 4 * (q - lane), src + r * ld + 4 * (q - lane));
+      } else if (zero_tail) {
+        for (int q = lane; q < n4; q += 32) *reinterpret_cast<float4*>(dst + r * stride + 4 * (q - lane)) = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+  }
+  for (int g = 0; g < G; ++g) {   // gate-head weights, row by row (row stride ld_Wg)
+    const int Hg4 = L.Hg[g] >> 2;
+    for (int e = w; e < L.n_e[g]; e += GT_WARPS)
+      for (int q = lane; q < Hg4; q += 32)
+        cp_async_16(wg_s + T.wg_off[g] + e * L.Hg[g] + 4 * q, L.Wg[g] + (int64_t)e * L.ld_Wg[g] + 4 * q);
+  }
+  for (int r = w; r < GT_ROWS; r += GT_WARPS) {
+    const int b = r0 + r;
+    for (int c = lane; c < total_ne; c += 32) {
+      int g = 0;
+      while (g + 1 < G && T.ne_off[g + 1] <= c) ++g;
+      p_s[r * total_ne + c] = (T.live[g] && b < B) ? L.probs[g][(int64_t)b * L.n_e[g] + (c - T.ne_off[g])] : 0.f;
+    }
+  }
+  cp_async_commit_wait_all();
+  __syncthreads();
+
+  // ---- P1: softmax-input dot products; a warp owns a sample, 8 lanes share one (gate, expert) pair
+  {
+    const int sub = lane & 7, pl = lane >> 3;
+    for (int r = w; r < GT_ROWS; r += GT_WARPS) {
+      if (r0 + r >= B) continue;  // warp-uniform
+      for (int p0 = 0; p0 < n_pairs; p0 += 4) {   // uniform trip count: shuffles inside
+        const int p = p0 + pl;
+        const bool pv = p < n_pairs;
+        float s = 0.f;
+        if (pv) {
+          const float4* a = reinterpret_cast<const float4*>(dm_s + (r * G + T.pair_g[p]) * H);
+          const float4* c = reinterpret_cast<const float4*>(eo_s + (r * E + T.pair_u[p]) * H);
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+          for (int q = sub; q < H4; q += 8) {
+            const float4 x = a[q], y = c[q];
+            acc.x = fmaf(x.x, y.x, acc.x); acc.y = fmaf(x.y, y.y, acc.y);
+            acc.z = fmaf(x.z, y.z, acc.z); acc.w = fmaf(x.w, y.w, acc.w);
+          }
+          s = (acc.x + acc.y) + (acc.z + acc.w);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (pv && sub == 0) dl_s[r * total_ne + T.pair_col[p]] = s;
+      }
+    }
+  }
+  // ---- P3: d(expert) (needs only p and d_mix: runs before the softmax backward to share its barrier);
+  // a warp owns an expert and walks the CTA's samples, lane <-> 4 columns
+  for (int u = w; u < E; u += GT_WARPS) {
+    const int cnt = T.ucnt[u];
+    if (cnt == 0) continue;  // warp-uniform
+    float* out32 = L.d_expert[u] ? L.d_expert[u] + (int64_t)r0 * L.ld_d_expert : nullptr;
+    uint16_t* out16 = L.d_expert_bf16[u] ? L.d_expert_bf16[u] + (int64_t)r0 * L.ld_d_expert_bf16 : nullptr;
+    const bool relu = L.expert_relu != 0;
+    for (int q = lane; q < H4; q += 32) {
+#pragma unroll 2
+      for (int r = 0; r < GT_ROWS; ++r) {
+        if (r0 + r >= B) break;  // warp-uniform
+        float4 de = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int k = 0; k < cnt; ++k)
+          fma4(de, p_s[r * total_ne + T.ucol[u][k]], reinterpret_cast<const float4*>(dm_s + (r * G + T.ug[u][k]) * H)[q]);
+        if (relu) {
+          const float4 x = reinterpret_cast<const float4*>(eo_s + (r * E + u) * H)[q];
+          if (!(x.x > 0.f)) de.x = 0.f;
+          if (!(x.y > 0.f)) de.y = 0.f;
+          if (!(x.z > 0.f)) de.z = 0.f;
+          if (!(x.w > 0.f)) de.w = 0.f;
+        }
+        if (out32) *reinterpret_cast<float4*>(out32 + (int64_t)r * L.ld_d_expert + 4 * q) = de;
+        if (out16) {
+          uint2 o;
+          o.x = pack_bf16x2(de.x, de.y);
+          o.y = pack_bf16x2(de.z, de.w);
+          *reinterpret_cast<uint2*>(out16 + (int64_t)r * L.ld_d_expert_bf16 + 4 * q) = o;
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // ---- P2: softmax backward in place (dp -> dlogit); zero for dead gates and rows past the batch
+  for (int it = tid; it < GT_ROWS * G; it += GT_THREADS) {
+    const int r = it / G, g = it - r * G;
+    const int ne = L.n_e[g], base = r * total_ne + T.ne_off[g];
+    if (!T.live[g] || r0 + r >= B) {
+      for (int e = 0; e < ne; ++e) dl_s[base + e] = 0.f;
+      continue;
+    }
+    float dot = 0.f;
+    for (int e = 0; e < ne; ++e) dot = fmaf(p_s[base + e], dl_s[base + e], dot);
+    for (int e = 0; e < ne; ++e) dl_s[base + e] = p_s[base + e] * (dl_s[base + e] - dot);
+  }
+  __syncthreads();
+  // ---- P4: d(gate_in); a warp owns a sample and walks the gates in order, so gates that share an
+  // input (MMoE: every head reads the level input) accumulate without a race
+  for (int r = w; r < GT_ROWS; r += GT_WARPS) {
+    const int b = r0 + r;
+    if (b >= B) continue;
+    for (int g = 0; g < G; ++g) {
+      if (!T.live[g] || (!L.d_gate_in[g] && !L.d_gate_in_bf16[g])) continue;
+      const int Hg = L.Hg[g], ne = L.n_e[g];
+      const float* wg = wg_s + T.wg_off[g];
+      const float* dl = dl_s + r * total_ne + T.ne_off[g];
+      for (int q = lane; q < (Hg >> 2); q += 32) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int e = 0; e < ne; ++e) fma4(acc, dl[e], reinterpret_cast<const float4*>(wg + e * Hg)[q]);
+        if (L.relu_mask_gate_in[g]) {
+          const float4 x = reinterpret_cast<const float4*>(gin_s + r * total_hg + T.hg_off[g])[q];
+          if (!(x.x > 0.f)) acc.x = 0.f;
+          if (!(x.y > 0.f)) acc.y = 0.f;
+          if (!(x.z > 0.f)) acc.z = 0.f;
+          if (!(x.w > 0.f)) acc.w = 0.f;
+        }
+        if (L.d_gate_in[g]) {
+          float4* dst = reinterpret_cast<float4*>(L.d_gate_in[g] + (int64_t)b * L.ld_d_gate_in[g]) + q;
+          if (L.accumulate_d_gate_in[g]) { const float4 o = *dst; acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w; }
+          *dst = acc;
+        }
+        if (L.d_gate_in_bf16[g]) {
+          uint2 o;
+          o.x = pack_bf16x2(acc.x, acc.y);
+          o.y = pack_bf16x2(acc.z, acc.w);
+          reinterpret_cast<uint2*>(L.d_gate_in_bf16[g] + (int64_t)b * L.ld_d_gate_in_bf16[g])[q] = o;
+        }
+      }
+    }
+  }
+  // ---- P5: CTA partial of dWg (fixed order over the CTA's samples)
+  float* part = scratch + (int64_t)blockIdx.x * total_wg;
+  for (int i4 = tid; i4 < (total_wg >> 2); i4 += GT_THREADS) {
+    const int i = i4 << 2;
+    int g = 0;
+    while (g + 1 < G && T.wg_off[g + 1] <= i) ++g;
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (T.live[g]) {
+      const int local = i - T.wg_off[g], Hg = L.Hg[g];
+      const int e = local / Hg, h = local - e * Hg;
+      const float* dlp = dl_s + T.ne_off[g] + e;
+      const float* gp = gin_s + T.hg_off[g] + h;
+#pragma unroll
+      for (int r = 0; r < GT_ROWS; ++r) fma4(s, dlp[r * total_ne], *reinterpret_cast<const float4*>(gp + r * total_hg));
+    }
+    *reinterpret_cast<float4*>(part + i) = s;
+  }
+}
+
 // deterministic reduction of the CTA partials: 32 outputs x 8 partial-groups per CTA; each thread sums every
 // 8th partial of its output (coalesced across outputs), the 8 group sums are added in a fixed order
 __global__ void __launch_bounds__(256)
@@ -317,6 +582,38 @@ extern "C" int mmlrec_gate_level_backward(const MmlrecGateLevel* level, int32_t 
   }
   const int n_cta = cdiv(B, GL_BWD_ROWS);
   gate_level_backward_kernel<<<n_cta, GL_BWD_WARPS * 32, smem, (cudaStream_t)stream>>>(level, B, scratch);
+  MMLREC_CHECK_LAUNCH(1);
+  gate_level_dwg_reduce_kernel<<<cdiv(total_wg, 32), 256, 0, (cudaStream_t)stream>>>(level, scratch, n_cta, total_wg);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int64_t mmlrec_gate_level_backward_tiled_scratch(int32_t total_wg, int32_t B) {
+  return (int64_t)cdiv(B, GT_ROWS) * total_wg;
+}
+
+/* shared memory (bytes) the tiled backward needs; callers use the warp-per-sample kernel when it does not fit */
+extern "C" int64_t mmlrec_gate_level_backward_tiled_smem(int32_t n_gates, int32_t n_experts, int32_t H, int32_t total_wg,
+                                                         int32_t total_ne, int32_t total_hg) {
+  return ((int64_t)total_wg + (int64_t)GT_ROWS * ((int64_t)(n_gates + n_experts) * H + total_hg + 2 * total_ne)) * 4;
+}
+
+extern "C" int mmlrec_gate_level_backward_tiled(const MmlrecGateLevel* level, int32_t B, int32_t n_gates, int32_t n_experts,
+                                                int32_t H, int32_t total_wg, int32_t total_ne, int32_t total_hg,
+                                                float* scratch, void* stream) {
+  MMLREC_CHECK_ARG(level && B > 0 && scratch, "bad args");
+  MMLREC_CHECK_ARG(n_gates > 0 && n_gates <= GL_MAXG && n_experts > 0 && n_experts <= MMLREC_LEVEL_MAX_EXPERTS &&
+                   H > 0 && H % 4 == 0 && total_wg > 0 && total_wg % 4 == 0 && total_hg % 4 == 0 && total_ne > 0,
+                   "sizes out of range");
+  const int64_t smem = mmlrec_gate_level_backward_tiled_smem(n_gates, n_experts, H, total_wg, total_ne, total_hg);
+  MMLREC_CHECK_ARG(smem <= 110 * 1024, "level too large for the tiled kernel");
+  static int64_t opted = 0;
+  if (smem > opted) {
+    cudaError_t e = cudaFuncSetAttribute(gate_level_backward_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("gate_level_backward_tiled: smem opt-in failed"); return (int)e; }
+    opted = smem;
+  }
+  const int n_cta = cdiv(B, GT_ROWS);
+  gate_level_backward_tiled_kernel<<<n_cta, GT_THREADS, (size_t)smem, (cudaStream_t)stream>>>(level, B, scratch);
   MMLREC_CHECK_LAUNCH(1);
   gate_level_dwg_reduce_kernel<<<cdiv(total_wg, 32), 256, 0, (cudaStream_t)stream>>>(level, scratch, n_cta, total_wg);
   MMLREC_RETURN_LAUNCH(1);

@@ -886,8 +886,25 @@ class GateMixStage(Stage):
         if not live:
             return
         if self.fused:
-            self.level_table = b.table([self._level_record(True)])
-            n = b.lib.mmlrec_gate_level_backward_scratch(self.total_wg, b.B)
+            rec = self._level_record(True)
+            self.level_table = b.table([rec])
+            G, E = len(self.gates), len(self.uniq)
+            self.total_ne = sum(len(g.experts) for g in self.gates)
+            self.total_hg = sum(g.gate_in.width for g in self.gates)
+
+            def ok16(ptr, ld):
+                return (ptr or 0) % 16 == 0 and ld % 4 == 0
+            # the tiled kernel moves whole rows with 16-byte cp.async / vector stores
+            self.tiled = (all(rec.Hg[i] % 4 == 0 and ok16(rec.gate_in[i], rec.ld_gate_in[i])
+                              and ok16(rec.Wg[i], rec.ld_Wg[i]) and ok16(rec.d_gate_in[i], rec.ld_d_gate_in[i])
+                              and (rec.d_gate_in_bf16[i] or 0) % 8 == 0 and rec.ld_d_gate_in_bf16[i] % 4 == 0
+                              for i in range(G))
+                          and b.lib.mmlrec_gate_level_backward_tiled_smem(G, E, self.H, self.total_wg, self.total_ne,
+                                                                          self.total_hg) <= 110 * 1024)
+            if self.tiled:
+                n = b.lib.mmlrec_gate_level_backward_tiled_scratch(self.total_wg, b.B)
+            else:
+                n = b.lib.mmlrec_gate_level_backward_scratch(self.total_wg, b.B)
             self.scratch = b.zeros(int(n))
             self.counters = b.zeros(1, dtype=torch.int32)
             return
@@ -938,11 +955,16 @@ class GateMixStage(Stage):
         if not self.any_live:
             return
         b = self.b
+        if self.fused and self.tiled:
+            L.check(b.lib.mmlrec_gate_level_backward_tiled(self.level_table.data_ptr(), b.B, len(self.gates),
+                                                           len(self.uniq), self.H, self.total_wg, self.total_ne,
+                                                           self.total_hg, self.scratch.data_ptr(), stream),
+                    f"gate_level bwd (tiled) {self.label}")
+            return
         if self.fused:
-            L.check(b.lib.mmlrec_gate_level_backward(self.level_table.data_ptr(), b.B, self.total_wg,
-                                                     sum(len(g.experts) for g in self.gates),
-                                                     sum(g.gate_in.width for g in self.gates),
-                                                     self.scratch.data_ptr(), self.counters.data_ptr(), stream),
+            L.check(b.lib.mmlrec_gate_level_backward(self.level_table.data_ptr(), b.B, self.total_wg, self.total_ne,
+                                                     self.total_hg, self.scratch.data_ptr(), self.counters.data_ptr(),
+                                                     stream),
                     f"gate_level bwd {self.label}")
             return
         L.check(b.lib.mmlrec_gate_mix_backward(self.gate_table.data_ptr(), len(self.gates), self.expert_table.data_ptr(),
