@@ -39,6 +39,8 @@ def measured_peaks():
 
 def workload_config(args):
     kw = {}
+    if args.vocab and args.workload == "synth26_mmoe":
+        kw["vocab"] = args.vocab
     cfg, fields = synthetic.workload(args.workload, **kw)
     return cfg, fields
 
@@ -97,11 +99,13 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_ours(cfg, fields, device, precision):
+def build_ours(cfg, fields, device, precision, shard=None):
     from mmlrec_b200.model import get_model_class
     from mmlrec_b200.model.utils import DenseFeat, SparseFeat
     cfg = copy.deepcopy(cfg)
     cfg["b200_config"] = {"precision": precision, "cuda_graph": True}
+    if shard:
+        cfg["b200_config"]["shard_tables"] = {"rank": shard[0], "world": shard[1]}
     emb = cfg["model_config"]["emb"]
     cols = [SparseFeat(n, v, emb) if k == "sparse" else DenseFeat(n, 1) for n, k, v in fields]
     torch.manual_seed(0)
@@ -293,10 +297,14 @@ def run_ours(args, rank, world):
         dist.init_process_group("nccl", device_id=torch.device(device))
     from mmlrec_b200 import lib as L
     cfg, fields = workload_config(args)
-    model = build_ours(cfg, fields, device, args.precision)
+    sharded = world > 1 and (args.tables == "sharded" or (args.tables == "auto" and args.workload == "synth26_mmoe"))
+    model = build_ours(cfg, fields, device, args.precision, shard=(rank, world) if sharded else None)
     if world > 1:
         from mmlrec_b200 import parallel
-        parallel.attach(model, rank, world)
+        if sharded:
+            parallel.attach_sharded(model)
+        else:
+            parallel.attach(model, rank, world)
     B = args.batch
     pool = 8
     host = [synthetic.make_batch(cfg, fields, B, seed=1000 * rank + s) for s in range(pool)]
@@ -366,7 +374,10 @@ def run_ours(args, rank, world):
             "dtype": "f32" if args.precision == "fp32" else "bf16", "data": "synthetic",
             "config": {"workload": args.workload, "batch_per_gpu": B, "global_batch": B * world,
                        "model": cfg["model_config"]["model_name"], "optimizer": cfg["optim_config"]["optimizer"],
-                       "precision": args.precision, "parallelism": f"dp{world}",
+                       "precision": args.precision,
+                       "parallelism": f"dp{world}" + (" + row-sharded tables (owner = id mod R, NVLink peer memory)"
+                                                      if sharded else ""),
+                       "vocab_override": args.vocab or None,
                        "l2": "tables + Adam state (>0.25 GB) exceed the 126 MB L2 and are streamed by the dense-Adam "
                              "sweep every step; batches rotate through a pool of 8"},
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(Xh[0].numel() * 4 + yh[0].numel() * 4),
@@ -405,6 +416,9 @@ def main():
     ap.add_argument("--workload", default="ae_ple_t4")
     ap.add_argument("--batch", type=int, default=4096)
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"])
+    ap.add_argument("--vocab", type=int, default=0, help="rows per table for synth26_mmoe (default 10M)")
+    ap.add_argument("--tables", default="auto", choices=["auto", "replicated", "sharded"],
+                    help="multi-GPU table placement; auto = row-sharded for synth26_mmoe, replicated otherwise")
     ap.add_argument("--no-extras", action="store_true", help="skip breakdown / roofline / cpu baseline")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))

@@ -105,6 +105,48 @@ int mmlrec_emb_backward_update(const float* d_input, int64_t ld, int32_t B,
                                const int64_t* field_meta, int32_t F_s, int32_t D,
                                float* emb, float* state1, float* state2, int32_t* row_touch,
                                const MmlrecHyper* hyper, float* grad_rows_out, void* stream);
+/* ---------------------------------------------------------------------------------------------
+ * Row-sharded tables over NVLink peer memory (BASELINE config 5: 26 x 10M-row tables on
+ * 8 GPUs).  owner(id) = id mod R keeps row id at local row id / R; every rank lays its shard out with
+ * the same per-field offsets (field_meta[f*4+0], rows = ceil(vocabulary / R)).  The reference has no
+ * multi-GPU path: the contract is the single-process step at the global batch.
+ *   mmlrec_peer_*                 cudaMalloc + CUDA IPC export / import of shards and receive buffers.
+ *   mmlrec_gather_concat_sharded  K1 with every row read from its owner's shard (shards[o], device
+ *                                 array of R base pointers); replaces the id + row all-to-all.
+ *   mmlrec_emb_push_rows          backward: for every (sample i, field j) of the LOCAL batch write
+ *                                 key (id / R) << 32 | pos and the D gradient floats into the OWNER's
+ *                                 receive buffer at pos = rank * b + i.  rx_keys[o]: [2][F_s][B_all]
+ *                                 uint64 (sentinel ~0), rx_grad[o]: [2][B_all][F_s*D]; the half is
+ *                                 hyper->step & 1.  Replaces the row-gradient all-to-all.
+ *   mmlrec_sort_field_keys        owner: per-field sort of the received keys (sentinels last, id -1),
+ *                                 resetting the consumed half to the sentinel.
+ *   mmlrec_emb_backward_update_sharded   K2 over the receive buffer (negative ids skipped).
+ * A collective (the dense-gradient all-reduce) must separate the pushes from the owner's sort.
+ * ------------------------------------------------------------------------------------------- */
+int mmlrec_peer_alloc(void** ptr, int64_t bytes);                 /* zero-filled */
+int mmlrec_peer_free(void* ptr);
+int mmlrec_peer_export(void* ptr, unsigned char* handle64);       /* 64-byte cudaIpcMemHandle_t */
+int mmlrec_peer_import(const unsigned char* handle64, void** ptr);
+int mmlrec_peer_close(void* ptr);
+int mmlrec_peer_fill_u64(uint64_t* p, int64_t n, uint64_t v /* 0 or ~0 */, void* stream);
+int mmlrec_gather_concat_sharded(const float* X, int64_t ldx, int32_t B,
+                                 const float* const* shards, int32_t n_shards,
+                                 const int64_t* field_meta, int32_t F_s, int32_t D,
+                                 const int32_t* dense_xcol, int32_t F_d, int32_t dense_out_col,
+                                 float* out_f32, int64_t ld_f32, uint16_t* out_bf16, int64_t ld_bf16,
+                                 int32_t* oob_flag, void* stream);
+int mmlrec_emb_push_rows(const float* X, int64_t ldx, int32_t b, const float* d_input, int64_t ld,
+                         const int64_t* field_meta, int32_t F_s, int32_t D, int32_t rank, int32_t R,
+                         int32_t B_all, uint64_t* const* rx_keys, float* const* rx_grad,
+                         const MmlrecHyper* hyper, void* stream);
+int mmlrec_sort_field_keys(uint64_t* rx_keys, int32_t B_all, int32_t F_s, const MmlrecHyper* hyper,
+                           int32_t* sorted_ids, int32_t* sorted_pos, uint64_t* keys_ws, void* stream);
+int mmlrec_emb_backward_update_sharded(const float* d_rx, int64_t ld, int32_t B_all,
+                                       const int32_t* sorted_ids, const int32_t* sorted_pos,
+                                       const int64_t* field_meta, int32_t F_s, int32_t D,
+                                       float* emb, float* state1, float* state2, int32_t* row_touch,
+                                       const MmlrecHyper* hyper, void* stream);
+
 /* stamp row_touch[row] = hyper->step for every row the sorted batch ids name (lets the sweep below run
  * BEFORE / concurrently with the backward pass: untouched rows need no gradient) */
 int mmlrec_emb_stamp_rows(const int32_t* sorted_ids, const int64_t* field_meta, int32_t F_s, int32_t B, int32_t D,

@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["capi.cu", "gather.cu", "emb_update.cu", "gemm_simt.cu", "gemm_tc.cu", "fused_ops.cu", "gate_level.cu"]
+SOURCES = ["capi.cu", "gather.cu", "emb_update.cu", "gemm_simt.cu", "gemm_tc.cu", "fused_ops.cu", "gate_level.cu", "peer.cu"]
 LIB = os.path.join(HERE, "libmmlrec_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]

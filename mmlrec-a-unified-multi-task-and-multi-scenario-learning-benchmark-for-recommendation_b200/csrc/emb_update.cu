@@ -36,7 +36,8 @@ __device__ __forceinline__ void cmp_swap(uint64_t& a, uint64_t& b, bool asc) {
 // `k_fixed` (strides chunk/2 .. 1).  When `emit` the sorted ids / positions are written out.
 __global__ void __launch_bounds__(kSortThreads)
 sort_local_kernel(const float* X, int64_t ldx, int B, const int64_t* field_meta, uint64_t* keys, int n_pad,
-                  int chunk, int mode, int k_fixed, int emit, int32_t* sorted_ids, int32_t* sorted_pos) {
+                  int chunk, int mode, int k_fixed, int emit, int32_t* sorted_ids, int32_t* sorted_pos,
+                  uint64_t* rx_keys = nullptr, const MmlrecHyper* hyper = nullptr) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   uint64_t* s = reinterpret_cast<uint64_t*>(smem_raw);
   const int f = blockIdx.y;
@@ -54,12 +55,21 @@ sort_local_kernel(const float* X, int64_t ldx, int B, const int64_t* field_meta,
       }
       s[i] = key;
     }
+  } else if (mode == 2) {
+    // keys were pushed by the peers into this rank's receive buffer [parity][F_s][B]; consume and reset
+    uint64_t* rx = rx_keys + ((int64_t)(hyper->step & 1) * gridDim.y + f) * B;
+    for (int i = tid; i < chunk; i += kSortThreads) {
+      int gi = base + i;
+      uint64_t key = ~0ull;
+      if (gi < B) { key = rx[gi]; rx[gi] = ~0ull; }
+      s[i] = key;
+    }
   } else {
     for (int i = tid; i < chunk; i += kSortThreads) s[i] = kf[base + i];
   }
   __syncthreads();
-  const int k_lo = mode == 0 ? 2 : k_fixed;
-  const int k_hi = mode == 0 ? chunk : k_fixed;
+  const int k_lo = mode != 1 ? 2 : k_fixed;
+  const int k_hi = mode != 1 ? chunk : k_fixed;
   for (int k = k_lo; k <= k_hi; k <<= 1) {
     int j0 = k >> 1;
     if (j0 > (chunk >> 1)) j0 = chunk >> 1;
@@ -111,6 +121,7 @@ struct SegArgs {
   const int32_t* sorted_ids; const int32_t* sorted_pos; const int64_t* field_meta; int D;
   float* emb; float* state1; float* state2; int32_t* row_touch; const MmlrecHyper* hyper;
   float* grad_rows_out;
+  int64_t parity_stride;   // sharded tables: d_input += (hyper->step & 1) * parity_stride (double-buffered receive rows)
 };
 
 template <int W>
@@ -241,7 +252,8 @@ __device__ void seg_pass(const SegArgs& a, int d0, int f, int64_t table_off, int
   __syncthreads();  // shared scratch is reused by the next pass
 }
 
-__global__ void __launch_bounds__(kSegThreads) emb_seg_update_kernel(const SegArgs a) {
+__global__ void __launch_bounds__(kSegThreads) emb_seg_update_kernel(SegArgs a) {
+  if (a.parity_stride) a.d_input += (int64_t)(a.hyper->step & 1) * a.parity_stride;
   __shared__ float tail_s[kSegWarps][8];
   __shared__ float carry_s[kSegWarps][8];
   __shared__ float flag_s[kSegWarps][8];   // [w][0] = open, [w][1] = whole, [w][2] = has true head
@@ -249,9 +261,10 @@ __global__ void __launch_bounds__(kSegThreads) emb_seg_update_kernel(const SegAr
   const int f = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int p = blockIdx.x * kSegThreads + tid;
-  const bool valid = p < a.B;
   const int32_t* ids_f = a.sorted_ids + (int64_t)f * a.B;
   if (tid == 0) hp_s = *a.hyper;
+  // negative ids are the sort's sentinels (slots of the receive buffer this rank does not own)
+  const bool valid = p < a.B && ids_f[p] >= 0;
   const int my_id = valid ? ids_f[p] : -1;
   const int my_pos = valid ? a.sorted_pos[(int64_t)f * a.B + p] : 0;
   const int prev_id = (valid && p > 0) ? ids_f[p - 1] : -2;
@@ -367,6 +380,35 @@ extern "C" int mmlrec_sort_field_ids(const float* X, int64_t ldx, int32_t B, con
   return 0;
 }
 
+// sort of the keys the peers pushed into this rank's receive buffer (peer.cu); slots nobody wrote hold the
+// sentinel ~0 and sort to the end (sorted id -1); the consumed half of the buffer is reset to the sentinel
+extern "C" int mmlrec_sort_field_keys(uint64_t* rx_keys, int32_t B_all, int32_t F_s, const MmlrecHyper* hyper,
+                                      int32_t* sorted_ids, int32_t* sorted_pos, uint64_t* keys_ws, void* stream) {
+  using namespace mmlrec;
+  MMLREC_CHECK_ARG(rx_keys && hyper && B_all > 0 && F_s > 0, "bad args");
+  int n_pad = 32;
+  while (n_pad < B_all) n_pad <<= 1;
+  const int chunk = n_pad < kSortChunk ? n_pad : kSortChunk;
+  const size_t smem = (size_t)chunk * sizeof(uint64_t);
+  cudaStream_t st = (cudaStream_t)stream;
+  dim3 grid(n_pad / chunk, F_s);
+  const bool single = n_pad <= kSortChunk;
+  sort_local_kernel<<<grid, kSortThreads, smem, st>>>(nullptr, 0, B_all, nullptr, keys_ws, n_pad, chunk, 2, 0,
+                                                      single ? 1 : 0, sorted_ids, sorted_pos, rx_keys, hyper);
+  MMLREC_CHECK_LAUNCH(1);
+  for (int k = chunk << 1; k <= n_pad && !single; k <<= 1) {
+    for (int j = k >> 1; j >= chunk; j >>= 1) {
+      dim3 g2(cdiv(n_pad >> 1, 256) < 1184 ? cdiv(n_pad >> 1, 256) : 1184, F_s);
+      sort_global_step_kernel<<<g2, 256, 0, st>>>(keys_ws, n_pad, j, k);
+      MMLREC_CHECK_LAUNCH(1);
+    }
+    sort_local_kernel<<<grid, kSortThreads, smem, st>>>(nullptr, 0, B_all, nullptr, keys_ws, n_pad, chunk, 1, k,
+                                                        k == n_pad ? 1 : 0, sorted_ids, sorted_pos);
+    MMLREC_CHECK_LAUNCH(1);
+  }
+  return 0;
+}
+
 extern "C" int mmlrec_emb_backward_update(const float* d_input, int64_t ld, int32_t B, const int32_t* sorted_ids,
                                           const int32_t* sorted_pos, const int64_t* field_meta, int32_t F_s, int32_t D,
                                           float* emb, float* state1, float* state2, int32_t* row_touch,
@@ -376,8 +418,24 @@ extern "C" int mmlrec_emb_backward_update(const float* d_input, int64_t ld, int3
   MMLREC_CHECK_ARG((ld & 3) == 0, "d_input row stride must be a multiple of 4 floats");
   MMLREC_CHECK_ARG(hyper != nullptr, "null hyper");
   MMLREC_CHECK_ARG(emb != nullptr || grad_rows_out != nullptr, "nothing to do");
-  SegArgs a{d_input, ld, B, sorted_ids, sorted_pos, field_meta, D, emb, state1, state2, row_touch, hyper, grad_rows_out};
+  SegArgs a{d_input, ld, B, sorted_ids, sorted_pos, field_meta, D, emb, state1, state2, row_touch, hyper, grad_rows_out, 0};
   dim3 grid(cdiv(B, kSegThreads), F_s);
+  emb_seg_update_kernel<<<grid, kSegThreads, 0, (cudaStream_t)stream>>>(a);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+// owner side of the row-sharded tables (peer.cu): same kernel over the receive buffer; d_rx is the base of
+// [2][B_all][ld] and the step parity selects the half that was filled this step
+extern "C" int mmlrec_emb_backward_update_sharded(const float* d_rx, int64_t ld, int32_t B_all, const int32_t* sorted_ids,
+                                                  const int32_t* sorted_pos, const int64_t* field_meta, int32_t F_s,
+                                                  int32_t D, float* emb, float* state1, float* state2, int32_t* row_touch,
+                                                  const MmlrecHyper* hyper, void* stream) {
+  using namespace mmlrec;
+  MMLREC_CHECK_ARG(B_all > 0 && F_s > 0 && D > 0 && (D & 3) == 0 && (ld & 3) == 0, "bad sizes");
+  MMLREC_CHECK_ARG(d_rx && emb && hyper, "null argument");
+  SegArgs a{d_rx, ld, B_all, sorted_ids, sorted_pos, field_meta, D, emb, state1, state2, row_touch, hyper, nullptr,
+            (int64_t)B_all * ld};
+  dim3 grid(cdiv(B_all, kSegThreads), F_s);
   emb_seg_update_kernel<<<grid, kSegThreads, 0, (cudaStream_t)stream>>>(a);
   MMLREC_RETURN_LAUNCH(1);
 }

@@ -21,6 +21,8 @@ struct GatherArgs {
   int in_dim;   // F_s*D + F_d
   int W;        // shared tile row width in floats (multiple of 4, >= in_dim, >= ld_bf16 if bf16 out)
   int n_tiles;
+  const float* const* shards;  // non-null: row-sharded tables, shards[o] = base of rank o's shard (peer memory)
+  int n_shards;
 };
 
 constexpr int kGatherThreads = 256;
@@ -64,7 +66,13 @@ __global__ void __launch_bounds__(kGatherThreads) gather_concat_kernel(const Gat
       const int64_t* m = meta_s + f * 4;
       int64_t id = (int64_t)x_s[r * a.x_cols + (int)m[2]];  // fp32 -> int64 truncation == .long()
       if (id < 0 || id >= m[1]) { oob = true; id = id < 0 ? 0 : m[1] - 1; }
-      const float* src = a.emb + m[0] + id * a.D + (part << 2);
+      const float* src;
+      if (a.shards) {   // owner = id mod R holds the row at local row id / R (same table offsets on every rank)
+        const int64_t q = id / a.n_shards;
+        src = a.shards[(int)(id - q * a.n_shards)] + m[0] + q * a.D + (part << 2);
+      } else {
+        src = a.emb + m[0] + id * a.D + (part << 2);
+      }
       cp_async_16(out_s + r * a.W + (int)m[3] + (part << 2), src);
     }
     for (int i = tid; i < rows * a.F_d; i += kGatherThreads) {
@@ -105,17 +113,44 @@ __global__ void __launch_bounds__(kGatherThreads) gather_concat_kernel(const Gat
 
 }  // namespace mmlrec
 
+static int gather_launch(const float* X, int64_t ldx, int32_t B, const float* emb, const float* const* shards,
+                         int32_t n_shards, const int64_t* field_meta, int32_t F_s, int32_t D,
+                         const int32_t* dense_xcol, int32_t F_d, int32_t dense_out_col,
+                         float* out_f32, int64_t ld_f32, uint16_t* out_bf16, int64_t ld_bf16,
+                         int32_t* oob_flag, void* stream);
+
 extern "C" int mmlrec_gather_concat(const float* X, int64_t ldx, int32_t B, const float* emb,
                                     const int64_t* field_meta, int32_t F_s, int32_t D,
                                     const int32_t* dense_xcol, int32_t F_d, int32_t dense_out_col,
                                     float* out_f32, int64_t ld_f32, uint16_t* out_bf16, int64_t ld_bf16,
                                     int32_t* oob_flag, void* stream) {
+  return gather_launch(X, ldx, B, emb, nullptr, 0, field_meta, F_s, D, dense_xcol, F_d, dense_out_col, out_f32, ld_f32,
+                       out_bf16, ld_bf16, oob_flag, stream);
+}
+
+extern "C" int mmlrec_gather_concat_sharded(const float* X, int64_t ldx, int32_t B, const float* const* shards,
+                                            int32_t n_shards, const int64_t* field_meta, int32_t F_s, int32_t D,
+                                            const int32_t* dense_xcol, int32_t F_d, int32_t dense_out_col,
+                                            float* out_f32, int64_t ld_f32, uint16_t* out_bf16, int64_t ld_bf16,
+                                            int32_t* oob_flag, void* stream) {
+  using namespace mmlrec;
+  MMLREC_CHECK_ARG(shards != nullptr && n_shards > 0, "no shards");
+  return gather_launch(X, ldx, B, nullptr, shards, n_shards, field_meta, F_s, D, dense_xcol, F_d, dense_out_col, out_f32,
+                       ld_f32, out_bf16, ld_bf16, oob_flag, stream);
+}
+
+static int gather_launch(const float* X, int64_t ldx, int32_t B, const float* emb, const float* const* shards,
+                         int32_t n_shards, const int64_t* field_meta, int32_t F_s, int32_t D,
+                         const int32_t* dense_xcol, int32_t F_d, int32_t dense_out_col,
+                         float* out_f32, int64_t ld_f32, uint16_t* out_bf16, int64_t ld_bf16,
+                         int32_t* oob_flag, void* stream) {
   using namespace mmlrec;
   MMLREC_CHECK_ARG(B >= 0 && F_s >= 0 && F_d >= 0 && F_s + F_d > 0, "bad sizes");
   MMLREC_CHECK_ARG(F_s == 0 || (D > 0 && (D & 3) == 0), "embedding dim must be a positive multiple of 4");
   MMLREC_CHECK_ARG(out_f32 || out_bf16, "no output");
   if (B == 0) return 0;
   GatherArgs a;
+  a.shards = shards; a.n_shards = n_shards;
   a.X = X; a.ldx = ldx; a.B = B; a.emb = emb; a.field_meta = field_meta; a.F_s = F_s; a.D = D;
   a.dense_xcol = dense_xcol; a.F_d = F_d; a.dense_out_col = dense_out_col;
   a.out_f32 = out_f32; a.ld_f32 = ld_f32; a.out_bf16 = out_bf16; a.ld_bf16 = ld_bf16; a.oob_flag = oob_flag;

@@ -268,8 +268,21 @@ class GatherStage(Stage):
         self.oob = b.zeros(1, dtype=torch.int32)
         # data parallel: ids and d(dnn_input) of ALL ranks (the embedding update runs on the global batch)
         self.dp = getattr(model, "dp", None)
+        self.sh = getattr(model, "shard", None)
+        if self.sh is not None and (self.dp is None or self.sh.emb is None or self.sh.emb.peer_table is None):
+            raise RuntimeError("row-sharded tables: call mmlrec_b200.parallel.attach_sharded(model, group) on every rank")
         self.B_all = self.dp.global_batch(b.B) if self.dp else b.B
-        if self.dp:
+        if self.sh is not None and self.F_s:
+            # receive buffers of the one-sided row-gradient exchange (csrc/peer.cu), double-buffered by step parity
+            self.X_all = self.X
+            row_w = self.F_s * self.D
+            self.rx_keys = self.sh.alloc_exchanged(2 * self.F_s * self.B_all * 8, b.device)
+            self.rx_grad = self.sh.alloc_exchanged(2 * self.B_all * row_w * 4, b.device)
+            L.check(b.lib.mmlrec_peer_fill_u64(self.rx_keys.ptr, 2 * self.F_s * self.B_all, (1 << 64) - 1, None), "rx fill")
+            torch.cuda.synchronize()
+            self.sh.barrier()   # every rank's sentinel fill is complete before anyone pushes
+            torch.cuda.synchronize()
+        elif self.dp:
             self.X_all = b.zeros(self.B_all, model.num_x_cols)
             self.dgrad_all = b.zeros(self.B_all, self.out.group.gbuf.shape[1])
         else:
@@ -284,6 +297,14 @@ class GatherStage(Stage):
 
     def forward(self, stream, training):
         b, st, o = self.b, self.b.store, self.out
+        if self.sh is not None:
+            L.check(b.lib.mmlrec_gather_concat_sharded(
+                self.X.data_ptr(), self.X.stride(0), b.B, self.sh.emb.peer_table.data_ptr(), self.sh.world,
+                self.meta.data_ptr(), self.F_s, self.D, self.dense_cols.data_ptr(), self.F_d, self.dense_out_col,
+                o.ptr if o.has_f32 else None, o.ld if o.has_f32 else 0,
+                o.ptr16 if o.has_bf16 else None, o.ld16 if o.has_bf16 else 0,
+                self.oob.data_ptr(), stream), "gather_concat_sharded")
+            return
         L.check(b.lib.mmlrec_gather_concat(
             self.X.data_ptr(), self.X.stride(0), b.B, st.emb.data_ptr(), self.meta.data_ptr(), self.F_s, self.D,
             self.dense_cols.data_ptr(), self.F_d, self.dense_out_col,
@@ -295,7 +316,7 @@ class GatherStage(Stage):
         """Side branch of the step: sort the batch ids; with Adam also stamp the touched rows and run
         the dense-Adam sweep of all UNtouched rows (zero-gradient update: needs no gradient, and the
         gather only reads touched rows, which the sweep skips)."""
-        if not self.F_s:
+        if not self.F_s or self.sh is not None:   # sharded: the owner sorts what it RECEIVED (post_reduce)
             return
         b, st, hy = self.b, self.b.store, self.model.hyper_dev
         L.check(b.lib.mmlrec_sort_field_ids(self.X_all.data_ptr(), self.X_all.stride(0), self.B_all, self.meta.data_ptr(),
@@ -314,6 +335,12 @@ class GatherStage(Stage):
         b, st, hy = self.b, self.b.store, self.model.hyper_dev
         p = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
         d_ptr, d_ld = self.out.gptr, self.out.gld
+        if self.sh is not None:  # push (key, gradient row) of every local (sample, field) to the row's owner
+            L.check(b.lib.mmlrec_emb_push_rows(
+                self.X.data_ptr(), self.X.stride(0), b.B, d_ptr, d_ld, self.meta.data_ptr(), self.F_s, self.D,
+                self.sh.rank, self.sh.world, self.B_all, self.rx_keys.peer_table.data_ptr(),
+                self.rx_grad.peer_table.data_ptr(), hy.data_ptr(), stream), "emb_push_rows")
+            return
         if self.dp:  # every rank reduces the gradient rows of the GLOBAL batch
             self.dp.gather_rows(self.out.group.gbuf, self.dgrad_all)
             d_ptr, d_ld = self.dgrad_all.data_ptr(), self.dgrad_all.stride(0)
@@ -321,6 +348,26 @@ class GatherStage(Stage):
             d_ptr, d_ld, self.B_all, self.sorted_ids.data_ptr(), self.sorted_pos.data_ptr(),
             self.meta.data_ptr(), self.F_s, self.D, st.emb.data_ptr(), p(st.emb_s1), p(st.emb_s2), p(st.row_touch),
             hy.data_ptr(), None, stream), "emb_backward_update")
+
+
+    def post_reduce(self, stream):
+        """Sharded tables, after the dense-gradient all-reduce (= all pushes have landed): sort the received
+        keys, segmented reduce + fused row update on the rows this rank owns (+ dense-Adam sweep)."""
+        if self.sh is None or not self.F_s or not self.out.grad_written:
+            return
+        b, st, hy = self.b, self.b.store, self.model.hyper_dev
+        p = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+        L.check(b.lib.mmlrec_sort_field_keys(self.rx_keys.ptr, self.B_all, self.F_s, hy.data_ptr(),
+                                             self.sorted_ids.data_ptr(), self.sorted_pos.data_ptr(),
+                                             self.keys_ws.data_ptr(), stream), "sort_field_keys")
+        L.check(b.lib.mmlrec_emb_backward_update_sharded(
+            self.rx_grad.ptr, self.F_s * self.D, self.B_all, self.sorted_ids.data_ptr(), self.sorted_pos.data_ptr(),
+            self.meta.data_ptr(), self.F_s, self.D, st.emb.data_ptr(), p(st.emb_s1), p(st.emb_s2), p(st.row_touch),
+            hy.data_ptr(), stream), "emb_backward_update_sharded")
+        if self.model.optimizer_name == "adam":
+            L.check(b.lib.mmlrec_emb_adam_dense_sweep(st.emb.data_ptr(), st.emb_s1.data_ptr(), st.emb_s2.data_ptr(),
+                                                      st.row_touch.data_ptr(), st.n_emb // self.D, self.D,
+                                                      hy.data_ptr(), stream), "emb_adam_dense_sweep")
 
 
 # ----------------------------------------------------------------------------------------------
@@ -1074,7 +1121,10 @@ class StepPlan:
         # the whole forward / backward (a parallel branch of the captured graph)
         main = torch.cuda.current_stream()
         dp = getattr(m, "dp", None)
-        if dp is not None:
+        sh = getattr(m, "shard", None)
+        if sh is not None:
+            sh.barrier()   # every owner has finished the previous step's row updates before anyone reads rows
+        elif dp is not None:
             dp.gather_rows(self.gather.X, self.gather.X_all)
         self.ev_fork.record(main)
         self.side.wait_event(self.ev_fork)
@@ -1088,7 +1138,8 @@ class StepPlan:
             s.backward(stream)
         st = m.store
         if dp is not None:
-            dp.sum_gradients(st.dense_grad)
+            dp.sum_gradients(st.dense_grad)   # sharded tables: also the barrier between the pushes and the owners' sort
+        self.gather.post_reduce(stream)
         p = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
         L.check(lib.mmlrec_dense_optimizer_step(st.dense.data_ptr(), st.dense_grad.data_ptr(), p(st.dense_s1),
                                                 p(st.dense_s2), st.n_dense, m.hyper_dev.data_ptr(), p(st.dense_bf16),

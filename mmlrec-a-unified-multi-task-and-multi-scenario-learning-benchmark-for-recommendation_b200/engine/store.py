@@ -29,7 +29,7 @@ def _align(n: int, a: int) -> int:
 class FlatStore:
     def __init__(self, model: nn.Module, ordered: Iterable[nn.Parameter], emb_params: List[nn.Parameter],
                  device: torch.device, want_bf16: bool, ordered_buffers: Iterable[torch.Tensor] = (),
-                 aux_floats: int = 0):
+                 aux_floats: int = 0, emb_alloc=None):
         self.device = device
         emb_ids = {id(p) for p in emb_params}
         seen, order = set(), []
@@ -72,7 +72,9 @@ class FlatStore:
             eoffs[id(p)] = at
             at += p.numel()
         self.n_emb = at
-        self.emb = torch.zeros(max(at, 4), dtype=torch.float32, device=device)
+        # `emb_alloc`: row-sharded tables live in IPC-exported memory the peers can address (parallel.ShardContext)
+        self.emb = (emb_alloc(max(at, 4), device) if emb_alloc is not None
+                    else torch.zeros(max(at, 4), dtype=torch.float32, device=device))
         self.emb_s1: Optional[torch.Tensor] = None
         self.emb_s2: Optional[torch.Tensor] = None
         self.row_touch: Optional[torch.Tensor] = None

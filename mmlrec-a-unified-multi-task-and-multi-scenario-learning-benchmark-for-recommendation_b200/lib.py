@@ -110,6 +110,16 @@ _SIGNATURES = {
     "mmlrec_gate_level_forward": (C.c_int, [vp, i32, vp]),
     "mmlrec_gate_level_backward": (C.c_int, [vp, i32, i32, i32, i32, vp, vp, vp]),
     "mmlrec_gate_level_backward_scratch": (i64, [i32, i32]),
+    "mmlrec_peer_alloc": (C.c_int, [C.POINTER(C.c_void_p), i64]),
+    "mmlrec_peer_free": (C.c_int, [vp]),
+    "mmlrec_peer_export": (C.c_int, [vp, C.c_char_p]),
+    "mmlrec_peer_import": (C.c_int, [C.c_char_p, C.POINTER(C.c_void_p)]),
+    "mmlrec_peer_close": (C.c_int, [vp]),
+    "mmlrec_peer_fill_u64": (C.c_int, [vp, i64, C.c_uint64, vp]),
+    "mmlrec_gather_concat_sharded": (C.c_int, [vp, i64, i32, vp, i32, vp, i32, i32, vp, i32, i32, vp, i64, vp, i64, vp, vp]),
+    "mmlrec_emb_push_rows": (C.c_int, [vp, i64, i32, vp, i64, vp, i32, i32, i32, i32, i32, vp, vp, vp, vp]),
+    "mmlrec_sort_field_keys": (C.c_int, [vp, i32, i32, vp, vp, vp, vp, vp]),
+    "mmlrec_emb_backward_update_sharded": (C.c_int, [vp, i64, i32, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]),
     "mmlrec_gate_level_backward_tiled": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
     "mmlrec_gate_level_backward_tiled_scratch": (i64, [i32, i32]),
     "mmlrec_gate_level_backward_tiled_smem": (i64, [i32, i32, i32, i32, i32, i32]),

@@ -85,7 +85,14 @@ class BaseModel(nn.Module):
                 raise NotImplementedError(f"{key} > 0 is not implemented in the fused step")
 
         self.feature_index = build_input_features(list(linear_feature_columns) + list(dnn_feature_columns))
-        self.embedding_dict = create_embedding_matrix(dnn_feature_columns, init_std, sparse=False, device="cpu")
+        # row-sharded tables (BASELINE config 5): this process holds rows rank::world of every table
+        self.shard = None
+        sh = self.b200_config.get("shard_tables")
+        if sh:
+            from ..parallel import ShardContext
+            self.shard = ShardContext(int(sh["rank"]), int(sh["world"]))
+        self.embedding_dict = create_embedding_matrix(dnn_feature_columns, init_std, sparse=False, device="cpu",
+                                                      shard_world=self.shard.world if self.shard else 1)
         self.out = PredictionLayer(self.model_config.get("task", "binary"))
         self.init_std = init_std
         self.store: Optional[FlatStore] = None
@@ -154,7 +161,8 @@ class BaseModel(nn.Module):
         self.build_graph(dry)
         emb_params = [t[0] for t in self.embedding_layout]
         self.store = FlatStore(self, dry.param_order, emb_params, self.device_obj, want_bf16=self.precision == "bf16",
-                               ordered_buffers=dry.buffer_order, aux_floats=dry.aux_floats + 64)
+                               ordered_buffers=dry.buffer_order, aux_floats=dry.aux_floats + 64,
+                               emb_alloc=self.shard.alloc_emb if self.shard else None)
         self._index_features()  # re-read the re-pointed table parameters
 
     def _require_cuda(self):

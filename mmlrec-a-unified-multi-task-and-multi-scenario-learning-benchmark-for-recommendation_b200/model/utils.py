@@ -92,12 +92,21 @@ def get_feature_names(feature_columns) -> List[str]:
     return list(build_input_features(feature_columns).keys())
 
 
-def create_embedding_matrix(feature_columns, init_std=0.0001, linear=False, sparse=False, device="cpu") -> nn.ModuleDict:
+def create_embedding_matrix(feature_columns, init_std=0.0001, linear=False, sparse=False, device="cpu",
+                            shard_world: int = 1) -> nn.ModuleDict:
     """One nn.Embedding per sparse column keyed by embedding_name; all tables are constructed first
-    (default N(0,1) draw) and then re-drawn N(0, init_std) in a second pass, like the reference."""
+    (default N(0,1) draw) and then re-drawn N(0, init_std) in a second pass, like the reference.
+    ``shard_world > 1``: only this rank's shard (ceil(V / world) rows) is built; the draw then differs from
+    the reference's RNG stream (same distribution) -- parity tests load full tables explicitly."""
     sparse_cols = [fc for fc in feature_columns if isinstance(fc, SparseFeat)]
     tables = nn.ModuleDict()
     for fc in sparse_cols:
+        if shard_world > 1:
+            emb = nn.Embedding((fc.vocabulary_size + shard_world - 1) // shard_world, 1 if linear else fc.embedding_dim,
+                               sparse=sparse, _weight=torch.empty((fc.vocabulary_size + shard_world - 1) // shard_world,
+                                                                  1 if linear else fc.embedding_dim))
+            tables[fc.embedding_name] = emb
+            continue
         tables[fc.embedding_name] = nn.Embedding(fc.vocabulary_size, 1 if linear else fc.embedding_dim, sparse=sparse)
     for emb in tables.values():
         nn.init.normal_(emb.weight, mean=0, std=init_std)

@@ -11,12 +11,19 @@ b produce exactly the single-process step at the global batch R*b drawn in rank-
   * BatchNorm statistics are per rank (no Sync-BN yet; only the census shape uses BatchNorm).
 
 All collectives are issued on the step's stream through ``torch.distributed`` so they are captured in the
-step's CUDA graph.  Row-sharded tables with id / row / row-gradient all-to-all (BASELINE config 5) are the next
-item of SURVEY section 8(e) and are not implemented here.
+step's CUDA graph.
+
+Row-sharded tables (BASELINE config 5): ``b200_config["shard_tables"] = {"rank": r, "world": R}``
+builds every table as the shard ``rows r::R`` in IPC-exported device memory; ``attach_sharded`` opens the peers'
+shards.  The id / row / row-gradient exchange is one-sided over NVLink peer memory (csrc/peer.cu): K1 reads rows
+straight from the owner's shard, the backward pushes (key, gradient row) pairs into the owner's receive buffer, the
+dense-gradient all-reduce is the barrier between the pushes and the owner's sort + K2, and a 4-byte all-reduce at
+the start of the step orders "all owners updated" before the next forward's peer reads.
 """
 from __future__ import annotations
 
-from typing import Optional
+import ctypes as C
+from typing import List, Optional
 
 import torch
 import torch.distributed as dist
@@ -64,3 +71,124 @@ def broadcast_parameters(model, src: int = 0, group: Optional[dist.ProcessGroup]
     for t in (st.dense, st.emb, st.stats, st.counts):
         dist.broadcast(t, src=src, group=group)
     st.refresh_bf16()
+
+
+# ----------------------------------------------------------------------------------------------
+# row-sharded tables over NVLink peer memory
+# ----------------------------------------------------------------------------------------------
+class _RawCuda:
+    def __init__(self, ptr: int, n: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": typestr, "data": (ptr, False), "version": 2}
+
+
+class PeerBuffer:
+    """A cudaMalloc allocation exported with CUDA IPC (``mmlrec_peer_*``).  ``tensor()`` is a zero-copy torch view of
+    the local memory; after ``exchange()`` ``peer_table`` is a device int64 vector with every rank's base pointer
+    (this rank's own pointer at index ``rank``) that the kernels index by owner."""
+
+    def __init__(self, nbytes: int, device: torch.device):
+        from . import lib as L
+        self._L, self.lib = L, L.load()
+        self.nbytes, self.device = int(nbytes), device
+        ptr = C.c_void_p()
+        with torch.cuda.device(device):
+            L.check(self.lib.mmlrec_peer_alloc(C.byref(ptr), self.nbytes), "peer_alloc")
+        self.ptr = int(ptr.value)
+        self.peer_ptrs: Optional[List[int]] = None
+        self.peer_table: Optional[torch.Tensor] = None
+
+    def tensor(self, dtype: torch.dtype) -> torch.Tensor:
+        typestr, size = {torch.float32: ("<f4", 4), torch.int64: ("<i8", 8), torch.int32: ("<i4", 4)}[dtype]
+        return torch.as_tensor(_RawCuda(self.ptr, self.nbytes // size, typestr), device=self.device)
+
+    def exchange(self, rank: int, world: int, group=None) -> None:
+        handle = C.create_string_buffer(64)
+        with torch.cuda.device(self.device):
+            self._L.check(self.lib.mmlrec_peer_export(self.ptr, handle), "peer_export")
+            torch.cuda.synchronize()
+            mine = torch.tensor(list(handle.raw), dtype=torch.uint8, device=self.device)
+            every = torch.empty(world * 64, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(every, mine, group=group)
+            raw = bytes(every.cpu().tolist())
+            ptrs = []
+            for r in range(world):
+                if r == rank:
+                    ptrs.append(self.ptr)
+                    continue
+                out = C.c_void_p()
+                self._L.check(self.lib.mmlrec_peer_import(raw[r * 64:(r + 1) * 64], C.byref(out)), f"peer_import rank {r}")
+                ptrs.append(int(out.value))
+            self.peer_ptrs = ptrs
+            self.peer_table = torch.tensor(ptrs, dtype=torch.int64, device=self.device)
+
+
+class ShardContext:
+    """owner(id) = id mod world; the owner keeps row ``id`` at local row ``id // world``."""
+
+    def __init__(self, rank: int, world: int, group=None):
+        if not (0 <= rank < world):
+            raise ValueError(f"shard_tables: rank {rank} outside world {world}")
+        self.rank, self.world, self.group = rank, world, group
+        self.emb: Optional[PeerBuffer] = None
+        self._token: Optional[torch.Tensor] = None
+
+    def local_rows(self, vocabulary: int) -> int:
+        return (vocabulary + self.world - 1) // self.world
+
+    def owned_ids(self, vocabulary: int) -> torch.Tensor:
+        """Global ids stored by this rank, in local-row order."""
+        return torch.arange(self.rank, vocabulary, self.world)
+
+    def alloc_emb(self, n_floats: int, device: torch.device) -> torch.Tensor:
+        self.emb = PeerBuffer(4 * n_floats, device)
+        return self.emb.tensor(torch.float32)
+
+    def alloc_exchanged(self, nbytes: int, device: torch.device) -> PeerBuffer:
+        buf = PeerBuffer(nbytes, device)
+        buf.exchange(self.rank, self.world, self.group)
+        return buf
+
+    def connect(self) -> None:
+        if self.emb is not None and self.emb.peer_table is None:
+            self.emb.exchange(self.rank, self.world, self.group)
+            self._token = torch.zeros(1, device=self.emb.device)
+
+    def barrier(self) -> None:
+        """Stream-ordered cross-rank barrier (captured in the step's graph): 4-byte all-reduce."""
+        dist.all_reduce(self._token, group=self.group)
+
+
+def attach_sharded(model, group: Optional[dist.ProcessGroup] = None) -> ShardContext:
+    """Connect a model built with ``b200_config["shard_tables"]`` to its peers (collective: every rank calls it).
+    Dense parameters are data-parallel exactly like ``attach``; the tables are row-sharded."""
+    sh = model.shard
+    if sh is None:
+        raise ValueError('the model was not built with b200_config["shard_tables"]')
+    sh.group = group
+    model.dp = DataParallelContext(sh.rank, sh.world, group)
+    sh.connect()
+    model._plans.clear()
+    return sh
+
+
+def load_full_tables(model, tables) -> None:
+    """Fill the local shards from full ``[V, D]`` tables keyed by embedding name (tests / checkpoints)."""
+    sh = model.shard
+    with torch.no_grad():
+        for name, full in tables.items():
+            w = model.embedding_dict[name].weight
+            rows = full[sh.rank::sh.world]
+            w[:rows.shape[0]].copy_(rows.to(w.device))
+
+
+def full_table(model, name: str) -> torch.Tensor:
+    """All-gather one sharded table back into its ``[V, D]`` form (collective; tests / checkpoints)."""
+    sh = model.shard
+    w = model.embedding_dict[name].weight.detach()
+    parts = [torch.empty_like(w) for _ in range(sh.world)]
+    dist.all_gather(parts, w.contiguous(), group=sh.group)
+    vocab = next(fc.vocabulary_size for fc in model.dnn_feature_columns if getattr(fc, "embedding_name", None) == name)
+    out = torch.empty(sh.local_rows(vocab) * sh.world, w.shape[1], device=w.device)
+    for r, part in enumerate(parts):
+        out[r::sh.world] = part
+    return out[:vocab]
