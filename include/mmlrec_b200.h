@@ -110,18 +110,22 @@ int mmlrec_emb_backward_update(const float* d_input, int64_t ld, int32_t B,
  * 8 GPUs).  owner(id) = id mod R keeps row id at local row id / R; every rank lays its shard out with
  * the same per-field offsets (field_meta[f*4+0], rows = ceil(vocabulary / R)).  The reference has no
  * multi-GPU path: the contract is the single-process step at the global batch.
- *   mmlrec_peer_*                 cudaMalloc + CUDA IPC export / import of shards and receive buffers.
- *   mmlrec_gather_concat_sharded  K1 with every row read from its owner's shard (shards[o], device
- *                                 array of R base pointers); replaces the id + row all-to-all.
- *   mmlrec_emb_push_rows          backward: for every (sample i, field j) of the LOCAL batch write
- *                                 key (id / R) << 32 | pos and the D gradient floats into the OWNER's
- *                                 receive buffer at pos = rank * b + i.  rx_keys[o]: [2][F_s][B_all]
- *                                 uint64 (sentinel ~0), rx_grad[o]: [2][B_all][F_s*D]; the half is
- *                                 hyper->step & 1.  Replaces the row-gradient all-to-all.
- *   mmlrec_sort_field_keys        owner: per-field sort of the received keys (sentinels last, id -1),
- *                                 resetting the consumed half to the sentinel.
- *   mmlrec_emb_backward_update_sharded   K2 over the receive buffer (negative ids skipped).
- * A collective (the dense-gradient all-reduce) must separate the pushes from the owner's sort.
+ * Every exchange is a one-sided store into a peer's buffer at a slot fixed by (rank, sample, field):
+ *   mmlrec_peer_*             cudaMalloc + CUDA IPC export / import; mmlrec_peer_barrier = flag exchange
+ *                             through peer memory (err_flag := 2 after ~10 s without the peers).
+ *   mmlrec_emb_push_ids       [ids all-to-all] key (id / R) << 32 | pos, pos = rank * b + i, into the
+ *                             OWNER's rq_keys [2][F_s][B_all] uint64 (sentinel ~0; half = hyper->step & 1).
+ *   mmlrec_emb_serve_rows     [rows all-to-all] owner: every received key -> its local row, stored into the
+ *                             REQUESTER's staging rows rows_in[r] [b][F_s*D].
+ *   mmlrec_gather_concat_staged   K1 assembling dnn_input from the staging rows (+ dense columns).
+ *   mmlrec_gather_concat_sharded  alternative forward without barriers: K1 reads every row straight from
+ *                             its owner's shard (fast while the shards fit the peer TLB reach).
+ *   mmlrec_sort_field_keys    owner: per-field sort of the received keys (sentinels last, id -1),
+ *                             resetting the consumed half to the sentinel.
+ *   mmlrec_emb_push_grads     [row-grad all-to-all] D gradient floats of every local (sample, field) into
+ *                             the owner's rx_grad [B_all][F_s*D] at row pos.
+ *   mmlrec_emb_backward_update_sharded   K2 over rx_grad with the sorted received ids (negative skipped).
+ * Order per step: push_ids, barrier, serve_rows, barrier, K1 ... push_grads, dense all-reduce (barrier), K2.
  * ------------------------------------------------------------------------------------------- */
 int mmlrec_peer_alloc(void** ptr, int64_t bytes);                 /* zero-filled */
 int mmlrec_peer_free(void* ptr);
@@ -129,17 +133,28 @@ int mmlrec_peer_export(void* ptr, unsigned char* handle64);       /* 64-byte cud
 int mmlrec_peer_import(const unsigned char* handle64, void** ptr);
 int mmlrec_peer_close(void* ptr);
 int mmlrec_peer_fill_u64(uint64_t* p, int64_t n, uint64_t v /* 0 or ~0 */, void* stream);
+int mmlrec_peer_barrier(int32_t* const* peer_flags /* [R] -> int32 [R] */, int32_t* local_epoch, int32_t rank,
+                        int32_t R, int32_t* err_flag, void* stream);
+int mmlrec_emb_push_ids(const float* X, int64_t ldx, int32_t b, const int64_t* field_meta, int32_t F_s,
+                        int32_t rank, int32_t R, int32_t B_all, uint64_t* const* rq_keys,
+                        const MmlrecHyper* hyper, int32_t step_offset, int32_t* oob_flag, void* stream);
+int mmlrec_emb_serve_rows(const uint64_t* rq_keys, const float* emb, const int64_t* field_meta, int32_t F_s,
+                          int32_t D, int32_t b, int32_t B_all, float* const* rows_in,
+                          const MmlrecHyper* hyper, int32_t step_offset, void* stream);
+int mmlrec_gather_concat_staged(const float* X, int64_t ldx, int32_t B, const float* staged_rows,
+                                const int64_t* field_meta, int32_t F_s, int32_t D,
+                                const int32_t* dense_xcol, int32_t F_d, int32_t dense_out_col,
+                                float* out_f32, int64_t ld_f32, uint16_t* out_bf16, int64_t ld_bf16, void* stream);
 int mmlrec_gather_concat_sharded(const float* X, int64_t ldx, int32_t B,
                                  const float* const* shards, int32_t n_shards,
                                  const int64_t* field_meta, int32_t F_s, int32_t D,
                                  const int32_t* dense_xcol, int32_t F_d, int32_t dense_out_col,
                                  float* out_f32, int64_t ld_f32, uint16_t* out_bf16, int64_t ld_bf16,
                                  int32_t* oob_flag, void* stream);
-int mmlrec_emb_push_rows(const float* X, int64_t ldx, int32_t b, const float* d_input, int64_t ld,
-                         const int64_t* field_meta, int32_t F_s, int32_t D, int32_t rank, int32_t R,
-                         int32_t B_all, uint64_t* const* rx_keys, float* const* rx_grad,
-                         const MmlrecHyper* hyper, void* stream);
-int mmlrec_sort_field_keys(uint64_t* rx_keys, int32_t B_all, int32_t F_s, const MmlrecHyper* hyper,
+int mmlrec_emb_push_grads(const float* X, int64_t ldx, int32_t b, const float* d_input, int64_t ld,
+                          const int64_t* field_meta, int32_t F_s, int32_t D, int32_t rank, int32_t R,
+                          int32_t B_all, float* const* rx_grad, void* stream);
+int mmlrec_sort_field_keys(uint64_t* rq_keys, int32_t B_all, int32_t F_s, const MmlrecHyper* hyper,
                            int32_t* sorted_ids, int32_t* sorted_pos, uint64_t* keys_ws, void* stream);
 int mmlrec_emb_backward_update_sharded(const float* d_rx, int64_t ld, int32_t B_all,
                                        const int32_t* sorted_ids, const int32_t* sorted_pos,

@@ -318,7 +318,7 @@ __global__ void emb_stamp_rows_kernel(const int32_t* sorted_ids, const int64_t* 
   const int64_t n = (int64_t)F_s * B;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int f = (int)(i / B);
-    row_touch[field_meta[f * 4 + 0] / D + sorted_ids[i]] = step;
+    if (sorted_ids[i] >= 0) row_touch[field_meta[f * 4 + 0] / D + sorted_ids[i]] = step;   // < 0: sort sentinel
   }
 }
 
@@ -424,8 +424,8 @@ extern "C" int mmlrec_emb_backward_update(const float* d_input, int64_t ld, int3
   MMLREC_RETURN_LAUNCH(1);
 }
 
-// owner side of the row-sharded tables (peer.cu): same kernel over the receive buffer; d_rx is the base of
-// [2][B_all][ld] and the step parity selects the half that was filled this step
+// owner side of the row-sharded tables (peer.cu): same kernel over the receive rows d_rx [B_all][ld] the peers
+// filled with gradient rows; slots this rank does not own carry sentinel ids (< 0) and are skipped
 extern "C" int mmlrec_emb_backward_update_sharded(const float* d_rx, int64_t ld, int32_t B_all, const int32_t* sorted_ids,
                                                   const int32_t* sorted_pos, const int64_t* field_meta, int32_t F_s,
                                                   int32_t D, float* emb, float* state1, float* state2, int32_t* row_touch,
@@ -433,8 +433,7 @@ extern "C" int mmlrec_emb_backward_update_sharded(const float* d_rx, int64_t ld,
   using namespace mmlrec;
   MMLREC_CHECK_ARG(B_all > 0 && F_s > 0 && D > 0 && (D & 3) == 0 && (ld & 3) == 0, "bad sizes");
   MMLREC_CHECK_ARG(d_rx && emb && hyper, "null argument");
-  SegArgs a{d_rx, ld, B_all, sorted_ids, sorted_pos, field_meta, D, emb, state1, state2, row_touch, hyper, nullptr,
-            (int64_t)B_all * ld};
+  SegArgs a{d_rx, ld, B_all, sorted_ids, sorted_pos, field_meta, D, emb, state1, state2, row_touch, hyper, nullptr, 0};
   dim3 grid(cdiv(B_all, kSegThreads), F_s);
   emb_seg_update_kernel<<<grid, kSegThreads, 0, (cudaStream_t)stream>>>(a);
   MMLREC_RETURN_LAUNCH(1);

@@ -23,6 +23,7 @@ struct GatherArgs {
   int n_tiles;
   const float* const* shards;  // non-null: row-sharded tables, shards[o] = base of rank o's shard (peer memory)
   int n_shards;
+  const float* staged;   // non-null: rows were delivered by their owners into [B][F_s*D] staging rows (peer.cu)
 };
 
 constexpr int kGatherThreads = 256;
@@ -67,6 +68,11 @@ __global__ void __launch_bounds__(kGatherThreads) gather_concat_kernel(const Gat
       int64_t id = (int64_t)x_s[r * a.x_cols + (int)m[2]];  // fp32 -> int64 truncation == .long()
       if (id < 0 || id >= m[1]) { oob = true; id = id < 0 ? 0 : m[1] - 1; }
       const float* src;
+      if (a.staged) {
+        cp_async_16(out_s + r * a.W + (int)m[3] + (part << 2),
+                    a.staged + (int64_t)(r0 + r) * ((int64_t)a.F_s * a.D) + (int64_t)f * a.D + (part << 2));
+        continue;
+      }
       if (a.shards) {   // owner = id mod R holds the row at local row id / R (same table offsets on every rank)
         const int64_t q = id / a.n_shards;
         src = a.shards[(int)(id - q * a.n_shards)] + m[0] + q * a.D + (part << 2);
@@ -114,7 +120,7 @@ __global__ void __launch_bounds__(kGatherThreads) gather_concat_kernel(const Gat
 }  // namespace mmlrec
 
 static int gather_launch(const float* X, int64_t ldx, int32_t B, const float* emb, const float* const* shards,
-                         int32_t n_shards, const int64_t* field_meta, int32_t F_s, int32_t D,
+                         int32_t n_shards, const float* staged, const int64_t* field_meta, int32_t F_s, int32_t D,
                          const int32_t* dense_xcol, int32_t F_d, int32_t dense_out_col,
                          float* out_f32, int64_t ld_f32, uint16_t* out_bf16, int64_t ld_bf16,
                          int32_t* oob_flag, void* stream);
@@ -124,7 +130,7 @@ extern "C" int mmlrec_gather_concat(const float* X, int64_t ldx, int32_t B, cons
                                     const int32_t* dense_xcol, int32_t F_d, int32_t dense_out_col,
                                     float* out_f32, int64_t ld_f32, uint16_t* out_bf16, int64_t ld_bf16,
                                     int32_t* oob_flag, void* stream) {
-  return gather_launch(X, ldx, B, emb, nullptr, 0, field_meta, F_s, D, dense_xcol, F_d, dense_out_col, out_f32, ld_f32,
+  return gather_launch(X, ldx, B, emb, nullptr, 0, nullptr, field_meta, F_s, D, dense_xcol, F_d, dense_out_col, out_f32, ld_f32,
                        out_bf16, ld_bf16, oob_flag, stream);
 }
 
@@ -135,12 +141,23 @@ extern "C" int mmlrec_gather_concat_sharded(const float* X, int64_t ldx, int32_t
                                             int32_t* oob_flag, void* stream) {
   using namespace mmlrec;
   MMLREC_CHECK_ARG(shards != nullptr && n_shards > 0, "no shards");
-  return gather_launch(X, ldx, B, nullptr, shards, n_shards, field_meta, F_s, D, dense_xcol, F_d, dense_out_col, out_f32,
+  return gather_launch(X, ldx, B, nullptr, shards, n_shards, nullptr, field_meta, F_s, D, dense_xcol, F_d, dense_out_col, out_f32,
                        ld_f32, out_bf16, ld_bf16, oob_flag, stream);
 }
 
+extern "C" int mmlrec_gather_concat_staged(const float* X, int64_t ldx, int32_t B, const float* staged_rows,
+                                           const int64_t* field_meta, int32_t F_s, int32_t D,
+                                           const int32_t* dense_xcol, int32_t F_d, int32_t dense_out_col,
+                                           float* out_f32, int64_t ld_f32, uint16_t* out_bf16, int64_t ld_bf16,
+                                           void* stream) {
+  using namespace mmlrec;
+  MMLREC_CHECK_ARG(staged_rows != nullptr, "no staging rows");
+  return gather_launch(X, ldx, B, nullptr, nullptr, 0, staged_rows, field_meta, F_s, D, dense_xcol, F_d, dense_out_col,
+                       out_f32, ld_f32, out_bf16, ld_bf16, nullptr, stream);
+}
+
 static int gather_launch(const float* X, int64_t ldx, int32_t B, const float* emb, const float* const* shards,
-                         int32_t n_shards, const int64_t* field_meta, int32_t F_s, int32_t D,
+                         int32_t n_shards, const float* staged, const int64_t* field_meta, int32_t F_s, int32_t D,
                          const int32_t* dense_xcol, int32_t F_d, int32_t dense_out_col,
                          float* out_f32, int64_t ld_f32, uint16_t* out_bf16, int64_t ld_bf16,
                          int32_t* oob_flag, void* stream) {
@@ -151,6 +168,7 @@ static int gather_launch(const float* X, int64_t ldx, int32_t B, const float* em
   if (B == 0) return 0;
   GatherArgs a;
   a.shards = shards; a.n_shards = n_shards;
+  a.staged = staged;
   a.X = X; a.ldx = ldx; a.B = B; a.emb = emb; a.field_meta = field_meta; a.F_s = F_s; a.D = D;
   a.dense_xcol = dense_xcol; a.F_d = F_d; a.dense_out_col = dense_out_col;
   a.out_f32 = out_f32; a.ld_f32 = ld_f32; a.out_bf16 = out_bf16; a.ld_bf16 = ld_bf16; a.oob_flag = oob_flag;

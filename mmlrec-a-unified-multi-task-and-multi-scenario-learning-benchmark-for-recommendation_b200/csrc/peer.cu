@@ -1,53 +1,123 @@
 // Row-sharded embedding tables over NVLink peer memory (BASELINE config 5).
 //
 // owner(id) = id mod R; the owner stores row id at local row id / R of its shard.  Every shard and
-// every receive buffer is a cudaMalloc allocation exported with CUDA IPC, so a kernel on rank r can
-// address rank o's memory directly through NVSwitch:
-//   forward   K1 reads each row straight from its owner's shard (gather.cu, `shards` path): the
-//             id / row all-to-all of a two-sided design collapses into 16-byte peer loads;
-//   backward  the push kernel below writes every (key, gradient row) of the local batch into the
-//             OWNER's receive buffer at a slot fixed by (rank, sample) -- only owned entries cross
-//             the wire (all-to-all volume), nothing is atomically appended, so the owner's sort +
-//             segmented reduce (K2) sees a deterministic order;
-//   barrier   the dense-gradient all-reduce that follows the push orders "all pushes done" before
-//             "owner sorts"; receive buffers are double-buffered by step parity so a fast rank's next
-//             push never lands in a buffer a slow owner is still reading.
+// every exchange buffer is a cudaMalloc allocation exported with CUDA IPC, so a kernel on rank r can
+// address rank o's memory directly through NVSwitch.  All exchanges are ONE-SIDED stores into small,
+// dense buffers at slots fixed by (rank, sample, field) -- only owned entries cross the wire (all-to-all
+// volume), nothing is appended atomically, so every reduction order is deterministic:
+//   forward   push_ids: key (id / R) << 32 | pos into the OWNER's request buffer        [ids all-to-all]
+//             barrier; serve_rows: the owner reads its LOCAL rows (2 MB pages, full HBM speed -- random
+//             16-byte reads of a multi-GB PEER mapping run ~10x slower, profiles/sharded_timeline_r01.txt)
+//             and stores them into the REQUESTER's staging rows                          [rows all-to-all]
+//             barrier; K1 assembles dnn_input from the staging rows (gather.cu, `staged` path).
+//             The owner sorts the request keys on a side stream while forward/backward run.
+//   backward  push_grads: the D gradient floats of every (sample, field) into the owner's receive rows
+//             [row-grad all-to-all]; the dense-gradient all-reduce is the barrier; K2 on the owner.
+//   (`shards` path of gather.cu: K1 reading rows straight from the owners' shards -- no barriers, the
+//   better choice while the tables fit the peer TLB reach.)
+// The barrier is a flag exchange through peer memory (one CTA, ~3 us) instead of a collective launch.
 #include "common.cuh"
 
 namespace mmlrec {
 
-// rx_keys of one owner: [2 parities][F_s][B_all] uint64, sentinel ~0 (nothing received for that slot)
-// rx_grad of one owner: [2 parities][B_all][F_s*D] float
+// rq_keys of one owner: [2 parities][F_s][B_all] uint64, sentinel ~0 (slot not owned by this rank)
+// rows_in of one requester: [b][F_s*D] float;  rx_grad of one owner: [B_all][F_s*D] float
 struct PushArgs {
   const float* X; int64_t ldx; int b;
   const float* d_input; int64_t ld;
   const int64_t* field_meta; int F_s; int D;
   int rank; int R; int B_all;
-  uint64_t* const* rx_keys; float* const* rx_grad;
-  const MmlrecHyper* hyper;
+  uint64_t* const* rq_keys; float* const* rx_grad;
+  const MmlrecHyper* hyper; int32_t* oob_flag;
 };
 
-__global__ void __launch_bounds__(256) emb_push_rows_kernel(const PushArgs a) {
-  const int par = a.hyper->step & 1;
+__device__ __forceinline__ int64_t clamp_id(const float* X, int64_t ldx, int i, const int64_t* m, bool& oob) {
+  int64_t id = (int64_t)__ldg(X + (int64_t)i * ldx + (int)m[2]);   // fp32 carrier, truncation == .long()
+  if (id < 0 || id >= m[1]) { oob = true; id = id < 0 ? 0 : m[1] - 1; }
+  return id;
+}
+
+__global__ void __launch_bounds__(256) emb_push_ids_kernel(const PushArgs a, int step_offset) {
+  const int par = (a.hyper->step + step_offset) & 1;
+  const int64_t n = (int64_t)a.b * a.F_s;
+  bool oob = false;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int j = (int)(t % a.F_s);
+    const int i = (int)(t / a.F_s);
+    const int64_t id = clamp_id(a.X, a.ldx, i, a.field_meta + j * 4, oob);
+    const int64_t q = id / a.R;
+    const int64_t pos = (int64_t)a.rank * a.b + i;
+    a.rq_keys[(int)(id - q * a.R)][((int64_t)par * a.F_s + j) * a.B_all + pos] = ((uint64_t)(uint32_t)q << 32) | (uint32_t)pos;
+  }
+  if (oob && a.oob_flag) *a.oob_flag = 1;
+}
+
+__global__ void __launch_bounds__(256) emb_push_grads_kernel(const PushArgs a) {
   const int dv = a.D >> 2;
   const int64_t n = (int64_t)a.b * a.F_s * dv;
   const int64_t row_w = (int64_t)a.F_s * a.D;
+  bool oob = false;
   for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
     const int part = (int)(t % dv);
     const int64_t ij = t / dv;
     const int j = (int)(ij % a.F_s);
     const int i = (int)(ij / a.F_s);
     const int64_t* m = a.field_meta + j * 4;
-    int64_t id = (int64_t)__ldg(a.X + (int64_t)i * a.ldx + (int)m[2]);
-    id = id < 0 ? 0 : (id >= m[1] ? m[1] - 1 : id);   // same clamp as the gather
+    const int64_t id = clamp_id(a.X, a.ldx, i, m, oob);
     const int o = (int)(id % a.R);
     const int64_t pos = (int64_t)a.rank * a.b + i;
     const float4 g = __ldg(reinterpret_cast<const float4*>(a.d_input + (int64_t)i * a.ld + (int)m[3]) + part);
-    float* dst = a.rx_grad[o] + ((int64_t)par * a.B_all + pos) * row_w + (int64_t)j * a.D;
-    reinterpret_cast<float4*>(dst)[part] = g;
-    if (part == 0)
-      a.rx_keys[o][((int64_t)par * a.F_s + j) * a.B_all + pos] = ((uint64_t)(uint32_t)(id / a.R) << 32) | (uint32_t)pos;
+    reinterpret_cast<float4*>(a.rx_grad[o] + pos * row_w + (int64_t)j * a.D)[part] = g;
   }
+}
+
+// owner: answer every request that landed in rq_keys with the local row, stored into the requester's staging rows
+struct ServeArgs {
+  const uint64_t* rq_keys; const float* emb; const int64_t* field_meta; int F_s; int D; int b; int B_all;
+  float* const* rows_in; const MmlrecHyper* hyper;
+};
+
+__global__ void __launch_bounds__(256) emb_serve_rows_kernel(const ServeArgs a, int step_offset) {
+  const int par = (a.hyper->step + step_offset) & 1;
+  const int dv = a.D >> 2;
+  const int64_t n = (int64_t)a.F_s * a.B_all * dv;
+  const int64_t row_w = (int64_t)a.F_s * a.D;
+  const uint64_t* keys = a.rq_keys + (int64_t)par * a.F_s * a.B_all;
+  for (int64_t t = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+    const int part = (int)(t % dv);
+    const int64_t jp = t / dv;           // = j * B_all + pos: consecutive threads walk one field's slots
+    const uint64_t key = keys[jp];
+    if (key == ~0ull) continue;
+    const int j = (int)(jp / a.B_all);
+    const int pos = (int)(jp - (int64_t)j * a.B_all);
+    const int r = pos / a.b, i = pos - r * a.b;
+    const float4 v = __ldg(reinterpret_cast<const float4*>(a.emb + a.field_meta[j * 4] + (int64_t)(key >> 32) * a.D) + part);
+    reinterpret_cast<float4*>(a.rows_in[r] + (int64_t)i * row_w + (int64_t)j * a.D)[part] = v;
+  }
+}
+
+// Cross-GPU barrier through peer memory: every rank stores its new epoch into slot [rank] of every peer's
+// flag vector and waits until all R slots of its own vector reached that epoch.  Work queued on the stream
+// before the barrier (peer stores of earlier kernels) is complete and system-visible when it starts.
+__global__ void peer_barrier_kernel(int32_t* const* peer_flags, int32_t* local_epoch, int rank, int R, int32_t* err_flag) {
+  __shared__ int s_e;
+  if (threadIdx.x == 0) { s_e = *local_epoch + 1; *local_epoch = s_e; }
+  __syncthreads();
+  const int e = s_e;
+  __threadfence_system();
+  if ((int)threadIdx.x < R) {
+    volatile int32_t* theirs = peer_flags[threadIdx.x] + rank;
+    *theirs = e;
+    volatile int32_t* mine = peer_flags[rank] + threadIdx.x;
+    const long long t0 = clock64();
+    while (*mine < e) {
+      if (clock64() - t0 > 20000000000ll) {   // ~10 s: a peer died; fail loudly instead of hanging the GPU
+        if (err_flag) *err_flag = 2;
+        break;
+      }
+    }
+  }
+  __threadfence_system();
 }
 
 }  // namespace mmlrec
@@ -105,16 +175,42 @@ extern "C" int mmlrec_peer_fill_u64(uint64_t* p, int64_t n, uint64_t v, void* st
   return 1;
 }
 
-extern "C" int mmlrec_emb_push_rows(const float* X, int64_t ldx, int32_t b, const float* d_input, int64_t ld,
-                                    const int64_t* field_meta, int32_t F_s, int32_t D, int32_t rank, int32_t R,
-                                    int32_t B_all, uint64_t* const* rx_keys, float* const* rx_grad,
-                                    const MmlrecHyper* hyper, void* stream) {
-  MMLREC_CHECK_ARG(X && d_input && field_meta && rx_keys && rx_grad && hyper, "null argument");
+static int push_grid(int64_t n) { return (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8); }
+
+extern "C" int mmlrec_emb_push_ids(const float* X, int64_t ldx, int32_t b, const int64_t* field_meta, int32_t F_s,
+                                   int32_t rank, int32_t R, int32_t B_all, uint64_t* const* rq_keys,
+                                   const MmlrecHyper* hyper, int32_t step_offset, int32_t* oob_flag, void* stream) {
+  MMLREC_CHECK_ARG(X && field_meta && rq_keys && hyper, "null argument");
+  MMLREC_CHECK_ARG(b > 0 && F_s > 0 && R > 0 && rank >= 0 && rank < R && B_all >= (int64_t)R * b, "bad sizes");
+  PushArgs a{X, ldx, b, nullptr, 0, field_meta, F_s, 0, rank, R, B_all, rq_keys, nullptr, hyper, oob_flag};
+  emb_push_ids_kernel<<<push_grid((int64_t)b * F_s), 256, 0, (cudaStream_t)stream>>>(a, step_offset);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_emb_serve_rows(const uint64_t* rq_keys, const float* emb, const int64_t* field_meta, int32_t F_s,
+                                     int32_t D, int32_t b, int32_t B_all, float* const* rows_in,
+                                     const MmlrecHyper* hyper, int32_t step_offset, void* stream) {
+  MMLREC_CHECK_ARG(rq_keys && emb && field_meta && rows_in && hyper, "null argument");
+  MMLREC_CHECK_ARG(b > 0 && F_s > 0 && D > 0 && (D & 3) == 0 && B_all >= b, "bad sizes");
+  ServeArgs a{rq_keys, emb, field_meta, F_s, D, b, B_all, rows_in, hyper};
+  emb_serve_rows_kernel<<<push_grid((int64_t)F_s * B_all * (D >> 2)), 256, 0, (cudaStream_t)stream>>>(a, step_offset);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_emb_push_grads(const float* X, int64_t ldx, int32_t b, const float* d_input, int64_t ld,
+                                     const int64_t* field_meta, int32_t F_s, int32_t D, int32_t rank, int32_t R,
+                                     int32_t B_all, float* const* rx_grad, void* stream) {
+  MMLREC_CHECK_ARG(X && d_input && field_meta && rx_grad, "null argument");
   MMLREC_CHECK_ARG(b > 0 && F_s > 0 && D > 0 && (D & 3) == 0 && (ld & 3) == 0, "bad sizes");
   MMLREC_CHECK_ARG(R > 0 && rank >= 0 && rank < R && B_all >= (int64_t)R * b, "bad rank / world / B_all");
-  PushArgs a{X, ldx, b, d_input, ld, field_meta, F_s, D, rank, R, B_all, rx_keys, rx_grad, hyper};
-  const int64_t n = (int64_t)b * F_s * (D >> 2);
-  const int grid = (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8);
-  emb_push_rows_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  PushArgs a{X, ldx, b, d_input, ld, field_meta, F_s, D, rank, R, B_all, nullptr, rx_grad, nullptr, nullptr};
+  emb_push_grads_kernel<<<push_grid((int64_t)b * F_s * (D >> 2)), 256, 0, (cudaStream_t)stream>>>(a);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_peer_barrier(int32_t* const* peer_flags, int32_t* local_epoch, int32_t rank, int32_t R,
+                                   int32_t* err_flag, void* stream) {
+  MMLREC_CHECK_ARG(peer_flags && local_epoch && R > 0 && R <= 32 && rank >= 0 && rank < R, "bad args");
+  peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(peer_flags, local_epoch, rank, R, err_flag);
   MMLREC_RETURN_LAUNCH(1);
 }

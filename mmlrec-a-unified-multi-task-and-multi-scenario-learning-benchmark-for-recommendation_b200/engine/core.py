@@ -273,15 +273,18 @@ class GatherStage(Stage):
             raise RuntimeError("row-sharded tables: call mmlrec_b200.parallel.attach_sharded(model, group) on every rank")
         self.B_all = self.dp.global_batch(b.B) if self.dp else b.B
         if self.sh is not None and self.F_s:
-            # receive buffers of the one-sided row-gradient exchange (csrc/peer.cu), double-buffered by step parity
+            # exchange buffers of the one-sided all-to-alls (csrc/peer.cu); collective: every rank builds its plan
             self.X_all = self.X
             row_w = self.F_s * self.D
-            self.rx_keys = self.sh.alloc_exchanged(2 * self.F_s * self.B_all * 8, b.device)
-            self.rx_grad = self.sh.alloc_exchanged(2 * self.B_all * row_w * 4, b.device)
-            L.check(b.lib.mmlrec_peer_fill_u64(self.rx_keys.ptr, 2 * self.F_s * self.B_all, (1 << 64) - 1, None), "rx fill")
+            self.peer_read = self.sh.gather_mode == "peer_read"
+            self.rq_keys = self.sh.alloc_exchanged(2 * self.F_s * self.B_all * 8, b.device)   # [2][F_s][B_all] u64
+            self.rx_grad = self.sh.alloc_exchanged(self.B_all * row_w * 4, b.device)          # [B_all][F_s*D]
+            self.rows_in = self.sh.alloc_exchanged(b.B * row_w * 4, b.device)                 # [b][F_s*D]
+            L.check(b.lib.mmlrec_peer_fill_u64(self.rq_keys.ptr, 2 * self.F_s * self.B_all, (1 << 64) - 1, None), "rq fill")
             torch.cuda.synchronize()
             self.sh.barrier()   # every rank's sentinel fill is complete before anyone pushes
             torch.cuda.synchronize()
+            self.ev_served = torch.cuda.Event()
         elif self.dp:
             self.X_all = b.zeros(self.B_all, model.num_x_cols)
             self.dgrad_all = b.zeros(self.B_all, self.out.group.gbuf.shape[1])
@@ -297,13 +300,36 @@ class GatherStage(Stage):
 
     def forward(self, stream, training):
         b, st, o = self.b, self.b.store, self.out
-        if self.sh is not None:
-            L.check(b.lib.mmlrec_gather_concat_sharded(
-                self.X.data_ptr(), self.X.stride(0), b.B, self.sh.emb.peer_table.data_ptr(), self.sh.world,
-                self.meta.data_ptr(), self.F_s, self.D, self.dense_cols.data_ptr(), self.F_d, self.dense_out_col,
-                o.ptr if o.has_f32 else None, o.ld if o.has_f32 else 0,
-                o.ptr16 if o.has_bf16 else None, o.ld16 if o.has_bf16 else 0,
-                self.oob.data_ptr(), stream), "gather_concat_sharded")
+        if self.sh is not None and self.F_s:
+            sh, hy = self.sh, self.model.hyper_dev
+            outs = (o.ptr if o.has_f32 else None, o.ld if o.has_f32 else 0,
+                    o.ptr16 if o.has_bf16 else None, o.ld16 if o.has_bf16 else 0)
+            # [ids all-to-all] every (sample, field) key goes to the row's owner (also feeds the owner's sort)
+            L.check(b.lib.mmlrec_emb_push_ids(self.X.data_ptr(), self.X.stride(0), b.B, self.meta.data_ptr(), self.F_s,
+                                              sh.rank, sh.world, self.B_all, self.rq_keys.peer_table.data_ptr(),
+                                              hy.data_ptr(), 0, self.oob.data_ptr(), stream), "emb_push_ids")
+            sh.flag_barrier(stream)
+            if self.peer_read:   # K1 reads the rows straight from the owners' shards
+                L.check(b.lib.mmlrec_gather_concat_sharded(
+                    self.X.data_ptr(), self.X.stride(0), b.B, sh.emb.peer_table.data_ptr(), sh.world,
+                    self.meta.data_ptr(), self.F_s, self.D, self.dense_cols.data_ptr(), self.F_d, self.dense_out_col,
+                    *outs, self.oob.data_ptr(), stream), "gather_concat_sharded")
+            else:                # [rows all-to-all] the owner serves its local rows into the requesters' staging rows
+                L.check(b.lib.mmlrec_emb_serve_rows(self.rq_keys.ptr, st.emb.data_ptr(), self.meta.data_ptr(), self.F_s,
+                                                    self.D, b.B, self.B_all, self.rows_in.peer_table.data_ptr(),
+                                                    hy.data_ptr(), 0, stream), "emb_serve_rows")
+            self.ev_served.record(torch.cuda.current_stream())
+            if not training:     # nobody sorts (= consumes) the keys outside a training step: reset this half now
+                half = self.F_s * self.B_all
+                par = int(self.model.hyper_host_step()) & 1
+                L.check(b.lib.mmlrec_peer_fill_u64(self.rq_keys.ptr + par * half * 8, half, (1 << 64) - 1, stream), "rq reset")
+            if not self.peer_read:
+                sh.flag_barrier(stream)
+                L.check(b.lib.mmlrec_gather_concat_staged(
+                    self.X.data_ptr(), self.X.stride(0), b.B, self.rows_in.ptr, self.meta.data_ptr(), self.F_s, self.D,
+                    self.dense_cols.data_ptr(), self.F_d, self.dense_out_col, *outs, stream), "gather_concat_staged")
+            elif not training:
+                sh.flag_barrier(stream)   # the reset above must not race with the peers' next push
             return
         L.check(b.lib.mmlrec_gather_concat(
             self.X.data_ptr(), self.X.stride(0), b.B, st.emb.data_ptr(), self.meta.data_ptr(), self.F_s, self.D,
@@ -316,12 +342,18 @@ class GatherStage(Stage):
         """Side branch of the step: sort the batch ids; with Adam also stamp the touched rows and run
         the dense-Adam sweep of all UNtouched rows (zero-gradient update: needs no gradient, and the
         gather only reads touched rows, which the sweep skips)."""
-        if not self.F_s or self.sh is not None:   # sharded: the owner sorts what it RECEIVED (post_reduce)
+        if not self.F_s:
             return
         b, st, hy = self.b, self.b.store, self.model.hyper_dev
-        L.check(b.lib.mmlrec_sort_field_ids(self.X_all.data_ptr(), self.X_all.stride(0), self.B_all, self.meta.data_ptr(),
-                                            self.F_s, self.sorted_ids.data_ptr(), self.sorted_pos.data_ptr(),
-                                            self.keys_ws.data_ptr(), stream), "sort_field_ids")
+        if self.sh is not None:   # the owner sorts the request keys it received in the forward exchange
+            L.check(b.lib.mmlrec_sort_field_keys(self.rq_keys.ptr, self.B_all, self.F_s, hy.data_ptr(),
+                                                 self.sorted_ids.data_ptr(), self.sorted_pos.data_ptr(),
+                                                 self.keys_ws.data_ptr(), stream), "sort_field_keys")
+        else:
+            L.check(b.lib.mmlrec_sort_field_ids(self.X_all.data_ptr(), self.X_all.stride(0), self.B_all,
+                                                self.meta.data_ptr(), self.F_s, self.sorted_ids.data_ptr(),
+                                                self.sorted_pos.data_ptr(), self.keys_ws.data_ptr(), stream),
+                    "sort_field_ids")
         if self.model.optimizer_name == "adam":
             L.check(b.lib.mmlrec_emb_stamp_rows(self.sorted_ids.data_ptr(), self.meta.data_ptr(), self.F_s, self.B_all, self.D,
                                                 st.row_touch.data_ptr(), hy.data_ptr(), stream), "emb_stamp_rows")
@@ -335,11 +367,10 @@ class GatherStage(Stage):
         b, st, hy = self.b, self.b.store, self.model.hyper_dev
         p = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
         d_ptr, d_ld = self.out.gptr, self.out.gld
-        if self.sh is not None:  # push (key, gradient row) of every local (sample, field) to the row's owner
-            L.check(b.lib.mmlrec_emb_push_rows(
+        if self.sh is not None:  # [row-grad all-to-all] every local (sample, field) gradient row goes to its owner
+            L.check(b.lib.mmlrec_emb_push_grads(
                 self.X.data_ptr(), self.X.stride(0), b.B, d_ptr, d_ld, self.meta.data_ptr(), self.F_s, self.D,
-                self.sh.rank, self.sh.world, self.B_all, self.rx_keys.peer_table.data_ptr(),
-                self.rx_grad.peer_table.data_ptr(), hy.data_ptr(), stream), "emb_push_rows")
+                self.sh.rank, self.sh.world, self.B_all, self.rx_grad.peer_table.data_ptr(), stream), "emb_push_grads")
             return
         if self.dp:  # every rank reduces the gradient rows of the GLOBAL batch
             self.dp.gather_rows(self.out.group.gbuf, self.dgrad_all)
@@ -351,23 +382,16 @@ class GatherStage(Stage):
 
 
     def post_reduce(self, stream):
-        """Sharded tables, after the dense-gradient all-reduce (= all pushes have landed): sort the received
-        keys, segmented reduce + fused row update on the rows this rank owns (+ dense-Adam sweep)."""
+        """Sharded tables, after the dense-gradient all-reduce (= every gradient row has landed): segmented
+        reduce + fused row update of the rows this rank owns, over the ids it sorted during forward/backward."""
         if self.sh is None or not self.F_s or not self.out.grad_written:
             return
         b, st, hy = self.b, self.b.store, self.model.hyper_dev
         p = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
-        L.check(b.lib.mmlrec_sort_field_keys(self.rx_keys.ptr, self.B_all, self.F_s, hy.data_ptr(),
-                                             self.sorted_ids.data_ptr(), self.sorted_pos.data_ptr(),
-                                             self.keys_ws.data_ptr(), stream), "sort_field_keys")
         L.check(b.lib.mmlrec_emb_backward_update_sharded(
             self.rx_grad.ptr, self.F_s * self.D, self.B_all, self.sorted_ids.data_ptr(), self.sorted_pos.data_ptr(),
             self.meta.data_ptr(), self.F_s, self.D, st.emb.data_ptr(), p(st.emb_s1), p(st.emb_s2), p(st.row_touch),
             hy.data_ptr(), stream), "emb_backward_update_sharded")
-        if self.model.optimizer_name == "adam":
-            L.check(b.lib.mmlrec_emb_adam_dense_sweep(st.emb.data_ptr(), st.emb_s1.data_ptr(), st.emb_s2.data_ptr(),
-                                                      st.row_touch.data_ptr(), st.n_emb // self.D, self.D,
-                                                      hy.data_ptr(), stream), "emb_adam_dense_sweep")
 
 
 # ----------------------------------------------------------------------------------------------
@@ -1122,16 +1146,24 @@ class StepPlan:
         main = torch.cuda.current_stream()
         dp = getattr(m, "dp", None)
         sh = getattr(m, "shard", None)
-        if sh is not None:
-            sh.barrier()   # every owner has finished the previous step's row updates before anyone reads rows
+        if sh is not None and self.gather.F_s:
+            if self.gather.peer_read:
+                sh.flag_barrier(stream)   # every owner finished the previous step's row updates before rows are read
         elif dp is not None:
             dp.gather_rows(self.gather.X, self.gather.X_all)
-        self.ev_fork.record(main)
-        self.side.wait_event(self.ev_fork)
-        self.gather.sort(self.side.cuda_stream)
-        self.ev_join.record(self.side)
+        if sh is None or not self.gather.F_s:
+            self.ev_fork.record(main)
+            self.side.wait_event(self.ev_fork)
+            self.gather.sort(self.side.cuda_stream)
+            self.ev_join.record(self.side)
         for s in self.stages:
             s.forward(stream, True)
+            if s is self.gather and sh is not None and self.gather.F_s:
+                # sharded tables: the keys to sort arrived in the forward exchange; the sort (+ stamp + dense-Adam
+                # sweep) runs beside the rest of forward / backward once the owner has served them
+                self.side.wait_event(self.gather.ev_served)
+                self.gather.sort(self.side.cuda_stream)
+                self.ev_join.record(self.side)
         for s in reversed(self.stages):
             if s is self.gather:
                 main.wait_event(self.ev_join)

@@ -91,6 +91,9 @@ class BaseModel(nn.Module):
         if sh:
             from ..parallel import ShardContext
             self.shard = ShardContext(int(sh["rank"]), int(sh["world"]))
+            self.shard.gather_mode = sh.get("gather", "owner_serve")
+            if self.shard.gather_mode not in ("owner_serve", "peer_read"):
+                raise ValueError('shard_tables["gather"] must be "owner_serve" or "peer_read"')
         self.embedding_dict = create_embedding_matrix(dnn_feature_columns, init_std, sparse=False, device="cpu",
                                                       shard_world=self.shard.world if self.shard else 1)
         self.out = PredictionLayer(self.model_config.get("task", "binary"))
@@ -164,6 +167,12 @@ class BaseModel(nn.Module):
                                ordered_buffers=dry.buffer_order, aux_floats=dry.aux_floats + 64,
                                emb_alloc=self.shard.alloc_emb if self.shard else None)
         self._index_features()  # re-read the re-pointed table parameters
+
+    def hyper_host_step(self) -> int:
+        """Optimizer step count read back from the device clock (synchronises; evaluation paths only)."""
+        if self.hyper_dev is None:
+            return 0
+        return int(self.hyper_dev[:4].view(torch.int32).item())
 
     def _require_cuda(self):
         if self.store is None:

@@ -15,10 +15,12 @@ step's CUDA graph.
 
 Row-sharded tables (BASELINE config 5): ``b200_config["shard_tables"] = {"rank": r, "world": R}``
 builds every table as the shard ``rows r::R`` in IPC-exported device memory; ``attach_sharded`` opens the peers'
-shards.  The id / row / row-gradient exchange is one-sided over NVLink peer memory (csrc/peer.cu): K1 reads rows
-straight from the owner's shard, the backward pushes (key, gradient row) pairs into the owner's receive buffer, the
-dense-gradient all-reduce is the barrier between the pushes and the owner's sort + K2, and a 4-byte all-reduce at
-the start of the step orders "all owners updated" before the next forward's peer reads.
+shards.  The id / row / row-gradient all-to-all exchanges are one-sided stores over NVLink peer memory
+(csrc/peer.cu): ids are pushed to their owner, the owner serves its local rows into the requester's staging rows,
+the backward pushes gradient rows to the owner, which sorted the request keys on a side stream meanwhile; barriers
+are a flag exchange through peer memory, and the dense-gradient all-reduce doubles as the barrier before the
+owner's K2.  ``shard_tables["gather"] = "peer_read"`` selects the barrier-free forward in which K1 reads rows
+straight from the owners' shards (faster while the tables fit the peer TLB reach).
 """
 from __future__ import annotations
 
@@ -131,6 +133,9 @@ class ShardContext:
         self.rank, self.world, self.group = rank, world, group
         self.emb: Optional[PeerBuffer] = None
         self._token: Optional[torch.Tensor] = None
+        self.flags: Optional[PeerBuffer] = None      # int32 [world]: barrier epochs written by the peers
+        self.epoch: Optional[torch.Tensor] = None
+        self.err: Optional[torch.Tensor] = None
 
     def local_rows(self, vocabulary: int) -> int:
         return (vocabulary + self.world - 1) // self.world
@@ -150,12 +155,27 @@ class ShardContext:
 
     def connect(self) -> None:
         if self.emb is not None and self.emb.peer_table is None:
+            dev = self.emb.device
             self.emb.exchange(self.rank, self.world, self.group)
-            self._token = torch.zeros(1, device=self.emb.device)
+            self._token = torch.zeros(1, device=dev)
+            self.flags = self.alloc_exchanged(4 * max(self.world, 4), dev)
+            self.epoch = torch.zeros(1, dtype=torch.int32, device=dev)
+            self.err = torch.zeros(1, dtype=torch.int32, device=dev)
 
     def barrier(self) -> None:
-        """Stream-ordered cross-rank barrier (captured in the step's graph): 4-byte all-reduce."""
+        """Stream-ordered cross-rank barrier as a collective (4-byte all-reduce); set-up paths."""
         dist.all_reduce(self._token, group=self.group)
+
+    def flag_barrier(self, stream: int) -> None:
+        """Stream-ordered cross-rank barrier through peer memory (one tiny kernel, graph-capturable)."""
+        self.emb._L.check(self.emb.lib.mmlrec_peer_barrier(self.flags.peer_table.data_ptr(), self.epoch.data_ptr(),
+                                                           self.rank, self.world, self.err.data_ptr(), stream),
+                          "peer_barrier")
+
+    def check(self) -> None:
+        """Raise if a barrier gave up waiting for a peer (host-side, outside the captured step)."""
+        if int(self.err.item()) != 0:
+            raise RuntimeError("row-sharded tables: a peer never reached the barrier (err flag set by mmlrec_peer_barrier)")
 
 
 def attach_sharded(model, group: Optional[dist.ProcessGroup] = None) -> ShardContext:
