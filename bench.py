@@ -297,7 +297,9 @@ def run_ours(args, rank, world):
         dist.init_process_group("nccl", device_id=torch.device(device))
     from mmlrec_b200 import lib as L
     cfg, fields = workload_config(args)
-    sharded = world > 1 and (args.tables == "sharded" or (args.tables == "auto" and args.workload == "synth26_mmoe"))
+    # multi-GPU default: row-sharded tables (every rank sorts / updates / sweeps only the rows it owns; measured
+    # faster than replicated tables already at 2 GPUs, profiles/bench_ple_dp2_*_r01.json)
+    sharded = world > 1 and args.tables in ("sharded", "auto")
     model = build_ours(cfg, fields, device, args.precision, shard=(rank, world) if sharded else None)
     if world > 1:
         from mmlrec_b200 import parallel
@@ -418,7 +420,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--vocab", type=int, default=0, help="rows per table for synth26_mmoe (default 10M)")
     ap.add_argument("--tables", default="auto", choices=["auto", "replicated", "sharded"],
-                    help="multi-GPU table placement; auto = row-sharded for synth26_mmoe, replicated otherwise")
+                    help="multi-GPU table placement; auto = row-sharded")
     ap.add_argument("--no-extras", action="store_true", help="skip breakdown / roofline / cpu baseline")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
