@@ -338,6 +338,11 @@ int mmlrec_gate_level_backward_tiled(const MmlrecGateLevel* level, int32_t B, in
                                      int32_t H, int32_t total_wg, int32_t total_ne, int32_t total_hg,
                                      float* scratch, void* stream);
 int64_t mmlrec_gate_level_backward_tiled_scratch(int32_t total_wg, int32_t B);
+/* Tiled forward (same staging, same extra requirements as the tiled backward) */
+int mmlrec_gate_level_forward_tiled(const MmlrecGateLevel* level, int32_t B, int32_t n_experts, int32_t H,
+                                    int32_t total_wg, int32_t total_ne, int32_t total_hg, void* stream);
+int64_t mmlrec_gate_level_forward_tiled_smem(int32_t n_experts, int32_t H, int32_t total_wg, int32_t total_ne,
+                                             int32_t total_hg);
 int64_t mmlrec_gate_level_backward_tiled_smem(int32_t n_gates, int32_t n_experts, int32_t H, int32_t total_wg,
                                               int32_t total_ne, int32_t total_hg);
 

@@ -50,7 +50,9 @@ __device__ __forceinline__ uint16_t float_to_bf16_bits(float f) {
   return *reinterpret_cast<uint16_t*>(&h);
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
-  return (uint32_t)float_to_bf16_bits(lo) | ((uint32_t)float_to_bf16_bits(hi) << 16);
+  uint32_t r;   // one F2FP: d = {hi, lo}, round to nearest even (same result as two scalar conversions)
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
 }
 
 __device__ __forceinline__ float apply_act(float v, int act) {

@@ -369,35 +369,56 @@ heads_kernel(const MmlrecHead* heads, int T, int B, const float* y, int64_t ldy,
     }
     cta_out[i] = s;
   }
-  if (last_block_ticket(counter, gridDim.x)) {
-    __shared__ float tot_s[MMLREC_MAX_TASKS][2];
-    for (int i = tid; i < T * per_t; i += 256) {
-      float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-      int c = 0;
-      for (; c + 3 < (int)gridDim.x; c += 4) {
-        s0 += scratch[(int64_t)c * stride_cta + i];
-        s1 += scratch[(int64_t)(c + 1) * stride_cta + i];
-        s2 += scratch[(int64_t)(c + 2) * stride_cta + i];
-        s3 += scratch[(int64_t)(c + 3) * stride_cta + i];
-      }
-      for (; c < (int)gridDim.x; ++c) s0 += scratch[(int64_t)c * stride_cta + i];
-      const float s = (s0 + s1) + (s2 + s3);
-      const int t = i / per_t, k = i - t * per_t;
-      if (k < 2) tot_s[t][k] = s;
-      else if (k - 2 < Hd[t].H) Hd[t].dw[k - 2] = s;
+}
+
+// Deterministic reduction of the per-CTA partials [n_cta][T][2 + hmax]: 32 outputs x 8 partial-groups per CTA
+// (each thread sums every 8th partial, the 8 group sums are added in a fixed order).  Outputs are re-indexed so
+// that the 2T scalars (loss_t, dbias_t) are outputs 0..2T-1 and land in CTA 0, which also forms the total loss.
+__global__ void __launch_bounds__(256)
+heads_reduce_kernel(const MmlrecHead* heads, int T, float* loss, int esmm, const float* scratch, int stride_cta, int n_cta) {
+  __shared__ float red[8][33];
+  __shared__ float tot_s[MMLREC_MAX_TASKS][2];
+  const int ix = threadIdx.x & 31, iy = threadIdx.x >> 5;
+  const int per_t = stride_cta / T, hmax = per_t - 2;
+  const int n_out = T * per_t;
+  const int j = blockIdx.x * 32 + ix;
+  int t = 0, k = 0;
+  if (j < 2 * T) { t = j >> 1; k = j & 1; }
+  else { const int jj = j - 2 * T; t = jj / hmax; k = 2 + (jj - t * hmax); }
+  const int i = t * per_t + k;
+  float s = 0.f;
+  if (j < n_out) {   // 8 independent loads in flight per thread (the loop is L2-latency bound), fixed order
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f;
+    int c = iy;
+    for (; c + 56 < n_cta; c += 64) {
+      const float* q = scratch + (int64_t)c * stride_cta + i;
+      a0 += q[0]; a1 += q[(int64_t)8 * stride_cta]; a2 += q[(int64_t)16 * stride_cta]; a3 += q[(int64_t)24 * stride_cta];
+      a4 += q[(int64_t)32 * stride_cta]; a5 += q[(int64_t)40 * stride_cta]; a6 += q[(int64_t)48 * stride_cta]; a7 += q[(int64_t)56 * stride_cta];
     }
-    __syncthreads();
-    if (tid == 0) {
-      float total = 0.f;
-      for (int t = 0; t < T; ++t) { loss[t] = tot_s[t][0]; total += tot_s[t][0]; }
-      loss[T] = total;
-      if (esmm) {  // one shared bias receives both heads' gradient
-        if (Hd[0].dbias) *Hd[0].dbias = tot_s[0][1] + tot_s[1][1];
-      } else {
-        for (int t = 0; t < T; ++t) if (Hd[t].dbias) *Hd[t].dbias = tot_s[t][1];
-      }
-      for (int t = 0; t < T; ++t) if (Hd[t].dbias2) *Hd[t].dbias2 = tot_s[t][1];
+    for (; c < n_cta; c += 8) a0 += scratch[(int64_t)c * stride_cta + i];
+    s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  }
+  red[iy][ix] = s;
+  __syncthreads();
+  if (iy == 0 && j < n_out) {
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v += red[q][ix];
+    if (k < 2) tot_s[t][k] = v;
+    else if (k - 2 < heads[t].H) heads[t].dw[k - 2] = v;
+  }
+  if (blockIdx.x != 0) return;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float total = 0.f;
+    for (int q = 0; q < T; ++q) { loss[q] = tot_s[q][0]; total += tot_s[q][0]; }
+    loss[T] = total;
+    if (esmm) {  // one shared bias receives both heads' gradient
+      if (heads[0].dbias) *heads[0].dbias = tot_s[0][1] + tot_s[1][1];
+    } else {
+      for (int q = 0; q < T; ++q) if (heads[q].dbias) *heads[q].dbias = tot_s[q][1];
     }
+    for (int q = 0; q < T; ++q) if (heads[q].dbias2) *heads[q].dbias2 = tot_s[q][1];
   }
 }
 
@@ -633,6 +654,9 @@ extern "C" int mmlrec_heads_forward_backward(const MmlrecHead* heads, int32_t T,
   }
   heads_kernel<<<n_cta, 256, smem, (cudaStream_t)stream>>>(heads, T, B, y, ldy, pred, ld_pred, loss, esmm, training, scratch,
                                                            stride_cta, counters);
+  if (!(training && y != nullptr)) { MMLREC_RETURN_LAUNCH(1); }
+  MMLREC_CHECK_LAUNCH(1);
+  heads_reduce_kernel<<<cdiv(stride_cta, 32), 256, 0, (cudaStream_t)stream>>>(heads, T, loss, esmm, scratch, stride_cta, n_cta);
   MMLREC_RETURN_LAUNCH(1);
 }
 

@@ -267,56 +267,81 @@ gate_level_backward_kernel(const MmlrecGateLevel* lv, int B, float* scratch) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// Tiled backward (the default): a CTA owns GT_ROWS samples.  Every row it needs -- d(mix) of the live
-// gates, the level's expert activations, the gate inputs, the gate-head weights -- is brought into
-// shared memory once with cp.async; the five phases then run from shared memory with work mapped so
-// that almost every issued instruction is a 128-bit LDS or an FMA:
-//   P1  dp[r][g][e]   = <d_mix[r][g], expert[r][u(g,e)]>        8 lanes per dot product
-//   P2  dlogit        = p * (dp - <p, dp>)                       thread <-> (sample, gate)
-//   P3  d_expert[r][u]= relu'(.) sum_{g uses u} p * d_mix[r][g]   warp <-> (sample, expert), lane <-> 4 columns
-//   P4  d_gate_in[r][g]= dlogit Wg                                warp <-> sample, gates in order (shared inputs accumulate)
-//   P5  CTA partial of dWg = sum_r dlogit[r] (x) gate_in[r]       thread <-> 4 columns of one (gate, expert) row
-// dynamic smem (floats): Wg [total_wg] | d_mix [R][G][H] | expert [R][E][H] | gate_in [R][total_hg]
-//                        | p [R][total_ne] | dp/dlogit [R][total_ne]
+// Tiled kernels (the default).  A CTA owns GT_ROWS samples.  Every row it needs -- expert activations,
+// gate inputs, gate-head weights, and in backward d(mix) of the live gates -- is brought into shared
+// memory ONCE with bulk async copies (cp.async.bulk, one per row, issued by one thread each and tracked
+// by an mbarrier); the phases then run from shared memory with work mapped so that almost every issued
+// instruction is a 128-bit LDS or an FMA.
+//   forward   F1 logits: 8 lanes per (gate, expert) dot product   F2 softmax: thread <-> (sample, gate)
+//             F3 mixtures: warp <-> sample, lane <-> 4 columns
+//   backward  P1 dp[r][g][e] = <d_mix[r][g], expert[r][u(g,e)]>    8 lanes per dot product
+//             P3 d_expert[r][u] = relu'(.) sum_{g uses u} p * d_mix[r][g]   warp <-> expert, lane <-> 4 columns
+//             P2 dlogit = p * (dp - <p, dp>)                        thread <-> (sample, gate)
+//             P4 d_gate_in[r][g] = dlogit Wg     warp <-> sample, gates in order (shared inputs accumulate)
+//             P5 CTA partial of dWg = sum_r dlogit[r] (x) gate_in[r]   thread <-> 4 columns of a (gate, expert) row
+// dynamic smem (floats): Wg [total_wg] | d_mix [R][G][H] (backward) | expert [R][E][H] | gate_in [R][total_hg]
+//                        | p [R][total_ne] | dp/dlogit [R][total_ne] (backward)
 // ------------------------------------------------------------------------------------------------
 constexpr int GT_ROWS = 8;
 constexpr int GT_THREADS = 256;
 constexpr int GT_WARPS = GT_THREADS / 32;
 constexpr int GT_MAXP = GL_MAXG * MMLREC_LEVEL_MAX_EXPERTS;
+constexpr int GT_MAXSRC = 2 * GL_MAXG + MMLREC_LEVEL_MAX_EXPERTS;
+
+struct __align__(8) GtPair { uint16_t a, c, n4, col; };   // operand offsets (floats), length in float4, column in [total_ne]
 
 struct GtTables {
   int wg_off[GL_MAXG + 1], ne_off[GL_MAXG + 1], hg_off[GL_MAXG + 1], pair_off[GL_MAXG + 1];
   uint8_t live[GL_MAXG];
-  uint8_t pair_g[GT_MAXP], pair_u[GT_MAXP];
-  uint16_t pair_col[GT_MAXP];                       // column of the pair in the [total_ne] rows
+  GtPair pair[GT_MAXP];                 // live (gate, expert) pairs, grouped by gate
+  uint16_t pair_eo[GT_MAXP];            // expert row offset (float4) of the pair inside one sample's expert block
+  uint8_t pair_g[GT_MAXP], pair_e[GT_MAXP];
   uint8_t ucnt[MMLREC_LEVEL_MAX_EXPERTS], ug[MMLREC_LEVEL_MAX_EXPERTS][GL_MAXG];
   uint16_t ucol[MMLREC_LEVEL_MAX_EXPERTS][GL_MAXG];
-  // rows to stage: d_mix of the live gates, used experts, gate inputs of the live gates
-  const float* src[2 * GL_MAXG + MMLREC_LEVEL_MAX_EXPERTS];
-  int64_t src_ld[2 * GL_MAXG + MMLREC_LEVEL_MAX_EXPERTS];
-  int dst_off[2 * GL_MAXG + MMLREC_LEVEL_MAX_EXPERTS], dst_stride[2 * GL_MAXG + MMLREC_LEVEL_MAX_EXPERTS];
-  int n4[2 * GL_MAXG + MMLREC_LEVEL_MAX_EXPERTS];
+  // rows to stage per sample
+  const float* src[GT_MAXSRC];
+  int64_t src_ld[GT_MAXSRC];
+  int dst_off[GT_MAXSRC], dst_stride[GT_MAXSRC], n4[GT_MAXSRC];
 };
 
 __device__ __forceinline__ void fma4(float4& acc, float s, const float4& v) {
   acc.x = fmaf(s, v.x, acc.x); acc.y = fmaf(s, v.y, acc.y); acc.z = fmaf(s, v.z, acc.z); acc.w = fmaf(s, v.w, acc.w);
 }
+__device__ __forceinline__ uint32_t gt_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void gt_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(gt_smem_u32(dst)), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void gt_bar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "GT_WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"
+      "@p bra GT_WAIT_DONE;\n"
+      "bra GT_WAIT_LOOP;\n"
+      "GT_WAIT_DONE:\n"
+      "}\n" ::"r"(bar), "r"(parity) : "memory");
+}
 
-__global__ void __launch_bounds__(GT_THREADS, 2)
-gate_level_backward_tiled_kernel(const MmlrecGateLevel* lv, int B, float* scratch) {
-  extern __shared__ __align__(16) float dyn_s[];
-  __shared__ __align__(16) MmlrecGateLevel L;
-  __shared__ GtTables T;
-  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+// record -> shared memory, offsets, pair table, per-expert user lists.  `backward`: only gates that receive a
+// gradient are live; forward: all gates.
+__device__ __forceinline__ void gt_setup(const MmlrecGateLevel* lv, MmlrecGateLevel& L, GtTables& T, bool backward,
+                                         uint64_t* bar) {
+  const int tid = threadIdx.x;
   for (int i = tid; i < (int)(sizeof(MmlrecGateLevel) / 4); i += GT_THREADS)
     reinterpret_cast<uint32_t*>(&L)[i] = reinterpret_cast<const uint32_t*>(lv)[i];
+  if (tid == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gt_smem_u32(bar)), "r"(GT_THREADS));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
-  const int G = L.n_gates, E = L.n_experts, H = L.H, H4 = H >> 2;
+  const int G = L.n_gates, E = L.n_experts, H = L.H;
   if (tid == 0) {
     int a = 0, c = 0, d = 0, p = 0;
     for (int g = 0; g < G; ++g) {
       T.wg_off[g] = a; T.ne_off[g] = c; T.hg_off[g] = d; T.pair_off[g] = p;
-      const bool lv_g = L.d_mix[g] != nullptr;
+      const bool lv_g = !backward || L.d_mix[g] != nullptr;
       T.live[g] = lv_g ? 1 : 0;
       a += L.n_e[g] * L.Hg[g]; c += L.n_e[g]; d += L.Hg[g];
       if (lv_g) p += L.n_e[g];
@@ -324,15 +349,18 @@ gate_level_backward_tiled_kernel(const MmlrecGateLevel* lv, int B, float* scratc
     T.wg_off[G] = a; T.ne_off[G] = c; T.hg_off[G] = d; T.pair_off[G] = p;
   }
   __syncthreads();
-  // pair table (thread <-> (gate, slot)) and per-expert user lists (thread <-> expert)
-  for (int i = tid; i < G * 32; i += GT_THREADS) {
-    const int g = i >> 5, e = i & 31;
-    if (T.live[g] && e < L.n_e[g]) {
-      int u = 0;
-      while (u + 1 < E && L.slot[u][g] != e) ++u;
-      const int p = T.pair_off[g] + e;
-      T.pair_g[p] = (uint8_t)g; T.pair_u[p] = (uint8_t)u; T.pair_col[p] = (uint16_t)(T.ne_off[g] + e);
-    }
+  for (int i = tid; i < E * G; i += GT_THREADS) {   // thread <-> (expert, gate)
+    const int u = i / G, g = i - u * G;
+    const int e = L.slot[u][g];
+    if (e < 0 || !T.live[g]) continue;
+    const int p = T.pair_off[g] + e;
+    GtPair d;
+    if (backward) { d.a = (uint16_t)(g * H); d.c = (uint16_t)(u * H); d.n4 = (uint16_t)(H >> 2); }
+    else { d.a = (uint16_t)T.hg_off[g]; d.c = (uint16_t)(T.wg_off[g] + e * L.Hg[g]); d.n4 = (uint16_t)(L.Hg[g] >> 2); }
+    d.col = (uint16_t)(T.ne_off[g] + e);
+    T.pair[p] = d;
+    T.pair_eo[p] = (uint16_t)(u * (H >> 2));
+    T.pair_g[p] = (uint8_t)g; T.pair_e[p] = (uint8_t)e;
   }
   if (tid < E) {
     int n = 0;
@@ -343,6 +371,148 @@ gate_level_backward_tiled_kernel(const MmlrecGateLevel* lv, int B, float* scratc
     T.ucnt[tid] = (uint8_t)n;
   }
   __syncthreads();
+}
+
+// Issue one bulk copy per (source, sample) row and per live gate-head weight row; every thread arrives on the
+// mbarrier once (with the bytes it asked for), then waits for the whole tile.
+__device__ __forceinline__ void gt_stage(const MmlrecGateLevel& L, const GtTables& T, int n_src, int n_rows, int r0,
+                                         float* dyn_s, float* wg_s, int n_pairs, uint64_t* bar) {
+  const int tid = threadIdx.x;
+  const uint32_t b32 = gt_smem_u32(bar);
+  const int n_items = n_src * GT_ROWS;
+  uint32_t bytes = 0;
+  for (int it = tid; it < n_items + n_pairs; it += GT_THREADS) {
+    if (it < n_items) {
+      const int v = it >> 3, r = it & (GT_ROWS - 1);
+      if (r < n_rows) bytes += (uint32_t)T.n4[v] << 4;
+    } else {
+      bytes += (uint32_t)L.Hg[T.pair_g[it - n_items]] << 2;
+    }
+  }
+  if (bytes) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b32), "r"(bytes) : "memory");
+  else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b32) : "memory");
+  for (int it = tid; it < n_items + n_pairs; it += GT_THREADS) {
+    if (it < n_items) {
+      const int v = it >> 3, r = it & (GT_ROWS - 1);
+      const int n4 = T.n4[v];
+      if (r < n_rows && n4)
+        gt_bulk_g2s(dyn_s + T.dst_off[v] + r * T.dst_stride[v], T.src[v] + (int64_t)(r0 + r) * T.src_ld[v], (uint32_t)n4 << 4, b32);
+    } else {
+      const int p = it - n_items, g = T.pair_g[p], e = T.pair_e[p], Hg = L.Hg[g];
+      gt_bulk_g2s(wg_s + T.wg_off[g] + e * Hg, L.Wg[g] + (int64_t)e * L.ld_Wg[g], (uint32_t)Hg << 2, b32);
+    }
+  }
+  gt_bar_wait(b32, 0);
+}
+
+__global__ void __launch_bounds__(GT_THREADS, 2)
+gate_level_forward_tiled_kernel(const MmlrecGateLevel* lv, int B) {
+  extern __shared__ __align__(128) float dyn_s[];
+  __shared__ __align__(16) MmlrecGateLevel L;
+  __shared__ GtTables T;
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  gt_setup(lv, L, T, false, &bar);
+  const int G = L.n_gates, E = L.n_experts, H = L.H, H4 = H >> 2;
+  const int total_wg = T.wg_off[G], total_ne = T.ne_off[G], total_hg = T.hg_off[G];
+  float* wg_s = dyn_s;
+  float* eo_s = wg_s + total_wg;
+  float* gin_s = eo_s + GT_ROWS * E * H;
+  float* p_s = gin_s + GT_ROWS * total_hg;
+  const int r0 = blockIdx.x * GT_ROWS;
+  const int n_rows = min(GT_ROWS, B - r0);
+  if (tid < E + G) {
+    const int v = tid;
+    const float* src = nullptr; int64_t ld = 0; int off = 0, stride = 0, n4 = 0;
+    if (v < E) {
+      if (T.ucnt[v]) { src = L.expert[v]; ld = L.ld_expert; off = (int)(eo_s - dyn_s) + v * H; stride = E * H; n4 = H4; }
+    } else {
+      const int g = v - E;
+      src = L.gate_in[g]; ld = L.ld_gate_in[g]; off = (int)(gin_s - dyn_s) + T.hg_off[g]; stride = total_hg; n4 = L.Hg[g] >> 2;
+    }
+    T.src[v] = src; T.src_ld[v] = ld; T.dst_off[v] = off; T.dst_stride[v] = stride; T.n4[v] = n4;
+  }
+  __syncthreads();
+  gt_stage(L, T, E + G, n_rows, r0, dyn_s, wg_s, total_ne, &bar);
+  // ---- F1: logits; a warp owns a sample, 8 lanes share one (gate, expert) dot product
+  {
+    const int sub = lane & 7, pl = lane >> 3;
+    for (int r = w; r < n_rows; r += GT_WARPS) {
+      const float* gin_r = gin_s + r * total_hg;
+#pragma unroll 3
+      for (int p0 = 0; p0 < total_ne; p0 += 4) {   // uniform trip count: shuffles inside
+        const int p = p0 + pl;
+        const bool pv = p < total_ne;
+        float s = 0.f;
+        if (pv) {
+          const GtPair d = T.pair[p];
+          const float4* a = reinterpret_cast<const float4*>(gin_r + d.a);
+          const float4* c = reinterpret_cast<const float4*>(wg_s + d.c);
+          float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 2
+          for (int q = sub; q < d.n4; q += 8) {
+            const float4 x = a[q], y = c[q];
+            acc.x = fmaf(x.x, y.x, acc.x); acc.y = fmaf(x.y, y.y, acc.y);
+            acc.z = fmaf(x.z, y.z, acc.z); acc.w = fmaf(x.w, y.w, acc.w);
+          }
+          s = (acc.x + acc.y) + (acc.z + acc.w);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (pv && sub == 0) p_s[r * total_ne + p] = s;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- F2: softmax per (sample, gate); probabilities are saved for the backward pass
+  for (int it = tid; it < n_rows * G; it += GT_THREADS) {
+    const int r = it / G, g = it - r * G;
+    const int ne = L.n_e[g];
+    float* pr = p_s + r * total_ne + T.ne_off[g];
+    float mx = -INFINITY;
+    for (int e = 0; e < ne; ++e) mx = fmaxf(mx, pr[e]);
+    float sum = 0.f;
+    for (int e = 0; e < ne; ++e) { const float x = expf(pr[e] - mx); pr[e] = x; sum += x; }
+    float* out = L.probs[g] + (int64_t)(r0 + r) * ne;
+    for (int e = 0; e < ne; ++e) { const float x = pr[e] / sum; pr[e] = x; out[e] = x; }
+  }
+  __syncthreads();
+  // ---- F3: mixtures; a warp owns a sample, lane <-> 4 columns
+  for (int r = w; r < n_rows; r += GT_WARPS) {
+    const int b = r0 + r;
+    const float4* eo = reinterpret_cast<const float4*>(eo_s + r * E * H);
+    for (int g = 0; g < G; ++g) {
+      const int ne = L.n_e[g], off = T.ne_off[g];
+      const float* pr = p_s + r * total_ne + off;
+      const uint16_t* eoff = T.pair_eo + off;
+      float* out32 = L.mix[g] + (int64_t)b * L.ld_mix[g];
+      uint16_t* out16 = L.mix_bf16[g] ? L.mix_bf16[g] + (int64_t)b * L.ld_mix_bf16[g] : nullptr;
+      for (int q = lane; q < H4; q += 32) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+        for (int e = 0; e < ne; ++e) fma4(acc, pr[e], eo[eoff[e] + q]);
+        reinterpret_cast<float4*>(out32)[q] = acc;
+        if (out16) {
+          uint2 o;
+          o.x = pack_bf16x2(acc.x, acc.y);
+          o.y = pack_bf16x2(acc.z, acc.w);
+          reinterpret_cast<uint2*>(out16)[q] = o;
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(GT_THREADS, 2)
+gate_level_backward_tiled_kernel(const MmlrecGateLevel* lv, int B, float* scratch) {
+  extern __shared__ __align__(128) float dyn_s[];
+  __shared__ __align__(16) MmlrecGateLevel L;
+  __shared__ GtTables T;
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  gt_setup(lv, L, T, true, &bar);
+  const int G = L.n_gates, E = L.n_experts, H = L.H, H4 = H >> 2;
   const int total_wg = T.wg_off[G], total_ne = T.ne_off[G], total_hg = T.hg_off[G], n_pairs = T.pair_off[G];
   float* wg_s = dyn_s;
   float* dm_s = wg_s + total_wg;
@@ -351,9 +521,7 @@ gate_level_backward_tiled_kernel(const MmlrecGateLevel* lv, int B, float* scratc
   float* p_s = gin_s + GT_ROWS * total_hg;
   float* dl_s = p_s + GT_ROWS * total_ne;
   const int r0 = blockIdx.x * GT_ROWS;
-
-  // ---- stage: source list (thread <-> source), then a warp per source walks the CTA's samples;
-  // one cp.async per lane and 16 bytes
+  const int n_rows = min(GT_ROWS, B - r0);
   const int per_row = 2 * G + E;
   if (tid < per_row) {
     const int v = tid;
@@ -369,30 +537,7 @@ gate_level_backward_tiled_kernel(const MmlrecGateLevel* lv, int B, float* scratc
     }
     T.src[v] = src; T.src_ld[v] = ld; T.dst_off[v] = off; T.dst_stride[v] = stride; T.n4[v] = n4;
   }
-  __syncthreads();
-  for (int v = w; v < per_row; v += GT_WARPS) {
-    const int n4 = T.n4[v];
-    if (n4 == 0) continue;
-    const int64_t ld = T.src_ld[v];
-    const float* src = T.src[v] + (int64_t)r0 * ld + 4 * lane;
-    float* dst = dyn_s + T.dst_off[v] + 4 * lane;
-    const int stride = T.dst_stride[v];
-    const bool zero_tail = v >= G + E;   // gate inputs of rows past the batch add zeros to the dWg partial
-#pragma unroll
-    for (int r = 0; r < GT_ROWS; ++r) {
-      if (r0 + r < B) {
-        for (int q = lane; q < n4; q += 32) cp_async_16(dst + r * stride + 4 * (q - lane), src + r * ld + 4 * (q - lane));
-      } else if (zero_tail) {
-        for (int q = lane; q < n4; q += 32) *reinterpret_cast<float4*>(dst + r * stride + 4 * (q - lane)) = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-  }
-  for (int g = 0; g < G; ++g) {   // gate-head weights, row by row (row stride ld_Wg)
-    const int Hg4 = L.Hg[g] >> 2;
-    for (int e = w; e < L.n_e[g]; e += GT_WARPS)
-      for (int q = lane; q < Hg4; q += 32)
-        cp_async_16(wg_s + T.wg_off[g] + e * L.Hg[g] + 4 * q, L.Wg[g] + (int64_t)e * L.ld_Wg[g] + 4 * q);
-  }
+  // probabilities, and zeros for the gate inputs of rows past the batch (they enter the CTA's dWg partial)
   for (int r = w; r < GT_ROWS; r += GT_WARPS) {
     const int b = r0 + r;
     for (int c = lane; c < total_ne; c += 32) {
@@ -400,22 +545,29 @@ gate_level_backward_tiled_kernel(const MmlrecGateLevel* lv, int B, float* scratc
       while (g + 1 < G && T.ne_off[g + 1] <= c) ++g;
       p_s[r * total_ne + c] = (T.live[g] && b < B) ? L.probs[g][(int64_t)b * L.n_e[g] + (c - T.ne_off[g])] : 0.f;
     }
+    if (b >= B) for (int c = lane; c < total_hg; c += 32) gin_s[r * total_hg + c] = 0.f;
   }
-  cp_async_commit_wait_all();
   __syncthreads();
+  gt_stage(L, T, per_row, n_rows, r0, dyn_s, wg_s, n_pairs, &bar);
+  __syncthreads();   // p_s / zero rows written with ordinary stores by other warps
 
   // ---- P1: softmax-input dot products; a warp owns a sample, 8 lanes share one (gate, expert) pair
   {
     const int sub = lane & 7, pl = lane >> 3;
-    for (int r = w; r < GT_ROWS; r += GT_WARPS) {
-      if (r0 + r >= B) continue;  // warp-uniform
+    for (int r = w; r < n_rows; r += GT_WARPS) {
+      const float* dm_r = dm_s + r * G * H;
+      const float* eo_r = eo_s + r * E * H;
+#pragma unroll 3
       for (int p0 = 0; p0 < n_pairs; p0 += 4) {   // uniform trip count: shuffles inside
         const int p = p0 + pl;
         const bool pv = p < n_pairs;
         float s = 0.f;
+        int col = 0;
         if (pv) {
-          const float4* a = reinterpret_cast<const float4*>(dm_s + (r * G + T.pair_g[p]) * H);
-          const float4* c = reinterpret_cast<const float4*>(eo_s + (r * E + T.pair_u[p]) * H);
+          const GtPair d = T.pair[p];
+          col = d.col;
+          const float4* a = reinterpret_cast<const float4*>(dm_r + d.a);
+          const float4* c = reinterpret_cast<const float4*>(eo_r + d.c);
           float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
           for (int q = sub; q < H4; q += 8) {
@@ -428,7 +580,7 @@ gate_level_backward_tiled_kernel(const MmlrecGateLevel* lv, int B, float* scratc
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         s += __shfl_xor_sync(0xffffffffu, s, 4);
-        if (pv && sub == 0) dl_s[r * total_ne + T.pair_col[p]] = s;
+        if (pv && sub == 0) dl_s[r * total_ne + col] = s;
       }
     }
   }
@@ -441,24 +593,31 @@ gate_level_backward_tiled_kernel(const MmlrecGateLevel* lv, int B, float* scratc
     uint16_t* out16 = L.d_expert_bf16[u] ? L.d_expert_bf16[u] + (int64_t)r0 * L.ld_d_expert_bf16 : nullptr;
     const bool relu = L.expert_relu != 0;
     for (int q = lane; q < H4; q += 32) {
-#pragma unroll 2
+      float4 de[GT_ROWS];
+#pragma unroll
+      for (int r = 0; r < GT_ROWS; ++r) de[r] = make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int k = 0; k < cnt; ++k) {   // user gates outer, the CTA's samples inner: table lookups amortised
+        const float* pk = p_s + T.ucol[u][k];
+        const float4* dk = reinterpret_cast<const float4*>(dm_s + T.ug[u][k] * H) + q;
+#pragma unroll
+        for (int r = 0; r < GT_ROWS; ++r) fma4(de[r], pk[r * total_ne], dk[r * G * H4]);
+      }
+#pragma unroll
       for (int r = 0; r < GT_ROWS; ++r) {
-        if (r0 + r >= B) break;  // warp-uniform
-        float4 de = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int k = 0; k < cnt; ++k)
-          fma4(de, p_s[r * total_ne + T.ucol[u][k]], reinterpret_cast<const float4*>(dm_s + (r * G + T.ug[u][k]) * H)[q]);
+        if (r >= n_rows) break;  // warp-uniform (rows past the batch hold stale smem: never stored)
+        float4 d = de[r];
         if (relu) {
           const float4 x = reinterpret_cast<const float4*>(eo_s + (r * E + u) * H)[q];
-          if (!(x.x > 0.f)) de.x = 0.f;
-          if (!(x.y > 0.f)) de.y = 0.f;
-          if (!(x.z > 0.f)) de.z = 0.f;
-          if (!(x.w > 0.f)) de.w = 0.f;
+          if (!(x.x > 0.f)) d.x = 0.f;
+          if (!(x.y > 0.f)) d.y = 0.f;
+          if (!(x.z > 0.f)) d.z = 0.f;
+          if (!(x.w > 0.f)) d.w = 0.f;
         }
-        if (out32) *reinterpret_cast<float4*>(out32 + (int64_t)r * L.ld_d_expert + 4 * q) = de;
+        if (out32) *reinterpret_cast<float4*>(out32 + (int64_t)r * L.ld_d_expert + 4 * q) = d;
         if (out16) {
           uint2 o;
-          o.x = pack_bf16x2(de.x, de.y);
-          o.y = pack_bf16x2(de.z, de.w);
+          o.x = pack_bf16x2(d.x, d.y);
+          o.y = pack_bf16x2(d.z, d.w);
           *reinterpret_cast<uint2*>(out16 + (int64_t)r * L.ld_d_expert_bf16 + 4 * q) = o;
         }
       }
@@ -469,7 +628,7 @@ gate_level_backward_tiled_kernel(const MmlrecGateLevel* lv, int B, float* scratc
   for (int it = tid; it < GT_ROWS * G; it += GT_THREADS) {
     const int r = it / G, g = it - r * G;
     const int ne = L.n_e[g], base = r * total_ne + T.ne_off[g];
-    if (!T.live[g] || r0 + r >= B) {
+    if (!T.live[g] || r >= n_rows) {
       for (int e = 0; e < ne; ++e) dl_s[base + e] = 0.f;
       continue;
     }
@@ -480,17 +639,17 @@ gate_level_backward_tiled_kernel(const MmlrecGateLevel* lv, int B, float* scratc
   __syncthreads();
   // ---- P4: d(gate_in); a warp owns a sample and walks the gates in order, so gates that share an
   // input (MMoE: every head reads the level input) accumulate without a race
-  for (int r = w; r < GT_ROWS; r += GT_WARPS) {
+  for (int r = w; r < n_rows; r += GT_WARPS) {
     const int b = r0 + r;
-    if (b >= B) continue;
     for (int g = 0; g < G; ++g) {
       if (!T.live[g] || (!L.d_gate_in[g] && !L.d_gate_in_bf16[g])) continue;
       const int Hg = L.Hg[g], ne = L.n_e[g];
-      const float* wg = wg_s + T.wg_off[g];
+      const float4* wg = reinterpret_cast<const float4*>(wg_s + T.wg_off[g]);
       const float* dl = dl_s + r * total_ne + T.ne_off[g];
       for (int q = lane; q < (Hg >> 2); q += 32) {
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-        for (int e = 0; e < ne; ++e) fma4(acc, dl[e], reinterpret_cast<const float4*>(wg + e * Hg)[q]);
+#pragma unroll 4
+        for (int e = 0; e < ne; ++e) fma4(acc, dl[e], wg[e * (Hg >> 2) + q]);
         if (L.relu_mask_gate_in[g]) {
           const float4 x = reinterpret_cast<const float4*>(gin_s + r * total_hg + T.hg_off[g])[q];
           if (!(x.x > 0.f)) acc.x = 0.f;
@@ -539,7 +698,17 @@ gate_level_dwg_reduce_kernel(const MmlrecGateLevel* lv, const float* scratch, in
   const int ix = threadIdx.x & 31, iy = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + ix;
   float s = 0.f;
-  if (i < total_wg) for (int c = iy; c < n_cta; c += 8) s += scratch[(int64_t)c * total_wg + i];
+  if (i < total_wg) {   // 8 independent loads in flight per thread (the loop is L2-latency bound), fixed order
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f;
+    int c = iy;
+    for (; c + 56 < n_cta; c += 64) {
+      const float* q = scratch + (int64_t)c * total_wg + i;
+      a0 += q[0]; a1 += q[(int64_t)8 * total_wg]; a2 += q[(int64_t)16 * total_wg]; a3 += q[(int64_t)24 * total_wg];
+      a4 += q[(int64_t)32 * total_wg]; a5 += q[(int64_t)40 * total_wg]; a6 += q[(int64_t)48 * total_wg]; a7 += q[(int64_t)56 * total_wg];
+    }
+    for (; c < n_cta; c += 8) a0 += scratch[(int64_t)c * total_wg + i];
+    s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  }
   red[iy][ix] = s;
   __syncthreads();
   if (iy != 0 || i >= total_wg) return;
@@ -616,5 +785,27 @@ extern "C" int mmlrec_gate_level_backward_tiled(const MmlrecGateLevel* level, in
   gate_level_backward_tiled_kernel<<<n_cta, GT_THREADS, (size_t)smem, (cudaStream_t)stream>>>(level, B, scratch);
   MMLREC_CHECK_LAUNCH(1);
   gate_level_dwg_reduce_kernel<<<cdiv(total_wg, 32), 256, 0, (cudaStream_t)stream>>>(level, scratch, n_cta, total_wg);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int64_t mmlrec_gate_level_forward_tiled_smem(int32_t n_experts, int32_t H, int32_t total_wg, int32_t total_ne,
+                                                        int32_t total_hg) {
+  return ((int64_t)total_wg + (int64_t)GT_ROWS * ((int64_t)n_experts * H + total_hg + total_ne)) * 4;
+}
+
+extern "C" int mmlrec_gate_level_forward_tiled(const MmlrecGateLevel* level, int32_t B, int32_t n_experts, int32_t H,
+                                               int32_t total_wg, int32_t total_ne, int32_t total_hg, void* stream) {
+  MMLREC_CHECK_ARG(level && B > 0, "bad args");
+  MMLREC_CHECK_ARG(n_experts > 0 && n_experts <= MMLREC_LEVEL_MAX_EXPERTS && H > 0 && H % 4 == 0 && total_wg > 0 &&
+                   total_wg % 4 == 0 && total_hg % 4 == 0 && total_ne > 0 && total_ne <= GT_MAXP, "sizes out of range");
+  const int64_t smem = mmlrec_gate_level_forward_tiled_smem(n_experts, H, total_wg, total_ne, total_hg);
+  MMLREC_CHECK_ARG(smem <= 110 * 1024, "level too large for the tiled kernel");
+  static int64_t opted = 0;
+  if (smem > opted) {
+    cudaError_t e = cudaFuncSetAttribute(gate_level_forward_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { set_error("gate_level_forward_tiled: smem opt-in failed"); return (int)e; }
+    opted = smem;
+  }
+  gate_level_forward_tiled_kernel<<<cdiv(B, GT_ROWS), GT_THREADS, (size_t)smem, (cudaStream_t)stream>>>(level, B);
   MMLREC_RETURN_LAUNCH(1);
 }

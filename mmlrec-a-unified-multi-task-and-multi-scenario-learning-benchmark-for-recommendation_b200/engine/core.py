@@ -860,7 +860,17 @@ class GateMixStage(Stage):
                       and self.H % 4 == 0 and self.total_wg <= L.LEVEL_MAX_WG
                       and all(a.col % 4 == 0 for a in self.uniq) and all(o.col % 4 == 0 for o in self.outs))
         if self.fused:
-            self.level_table = self.b.table([self._level_record(False)])
+            rec = self._level_record(False)
+            self.level_table = self.b.table([rec])
+            self.total_ne = sum(len(g.experts) for g in self.gates)
+            self.total_hg = sum(g.gate_in.width for g in self.gates)
+            # the tiled kernels move whole rows with 16-byte cp.async / vector stores
+            self.tiled_fwd = (all(rec.Hg[i] % 4 == 0 and (rec.gate_in[i] or 0) % 16 == 0 and rec.ld_gate_in[i] % 4 == 0
+                                  and (rec.Wg[i] or 0) % 16 == 0 and rec.ld_Wg[i] % 4 == 0
+                                  for i in range(len(self.gates)))
+                              and not self.b.dry and self.total_ne <= 256
+                              and self.b.lib.mmlrec_gate_level_forward_tiled_smem(
+                                  len(self.uniq), self.H, self.total_wg, self.total_ne, self.total_hg) <= 110 * 1024)
         else:
             self.gate_table = self.b.table([self._gate_record(i, False) for i in range(len(self.gates))])
 
@@ -943,7 +953,11 @@ class GateMixStage(Stage):
         return r
 
     def forward(self, stream, training):
-        if self.fused:
+        if self.fused and self.tiled_fwd:
+            L.check(self.b.lib.mmlrec_gate_level_forward_tiled(self.level_table.data_ptr(), self.b.B, len(self.uniq), self.H,
+                                                               self.total_wg, self.total_ne, self.total_hg, stream),
+                    f"gate_level fwd (tiled) {self.label}")
+        elif self.fused:
             L.check(self.b.lib.mmlrec_gate_level_forward(self.level_table.data_ptr(), self.b.B, stream),
                     f"gate_level fwd {self.label}")
         else:
@@ -1123,6 +1137,7 @@ class StepPlan:
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.side = torch.cuda.Stream(device=model.device_obj)
         self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
+        self.ev_bwd, self.ev_join2 = torch.cuda.Event(), torch.cuda.Event()
 
     # ---- static inputs / outputs
     X = property(lambda self: self.gather.X)
@@ -1165,17 +1180,37 @@ class StepPlan:
                 self.gather.sort(self.side.cuda_stream)
                 self.ev_join.record(self.side)
         for s in reversed(self.stages):
-            if s is self.gather:
-                main.wait_event(self.ev_join)
-            s.backward(stream)
+            if s is not self.gather:
+                s.backward(stream)
         st = m.store
-        if dp is not None:
-            dp.sum_gradients(st.dense_grad)   # sharded tables: also the barrier between the pushes and the owners' sort
-        self.gather.post_reduce(stream)
         p = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
-        L.check(lib.mmlrec_dense_optimizer_step(st.dense.data_ptr(), st.dense_grad.data_ptr(), p(st.dense_s1),
-                                                p(st.dense_s2), st.n_dense, m.hyper_dev.data_ptr(), p(st.dense_bf16),
-                                                stream), "dense_optimizer_step")
+
+        def dense_step():
+            L.check(lib.mmlrec_dense_optimizer_step(st.dense.data_ptr(), st.dense_grad.data_ptr(), p(st.dense_s1),
+                                                    p(st.dense_s2), st.n_dense, m.hyper_dev.data_ptr(), p(st.dense_bf16),
+                                                    stream), "dense_optimizer_step")
+
+        if dp is not None and sh is None:
+            # replicated tables: collectives stay on the main stream in program order
+            main.wait_event(self.ev_join)
+            self.gather.backward(stream)
+            dp.sum_gradients(st.dense_grad)
+            dense_step()
+            return
+        # the table update (K2) and the dense optimizer touch disjoint buffers: K2 runs on the side stream, behind the
+        # sort / sweep it depends on, while the main stream runs the dense optimizer
+        if sh is not None:
+            self.gather.backward(stream)        # push gradient rows to their owners
+            dp.sum_gradients(st.dense_grad)     # also the barrier between the pushes and the owners' K2
+        self.ev_bwd.record(main)
+        self.side.wait_event(self.ev_bwd)
+        if sh is not None:
+            self.gather.post_reduce(self.side.cuda_stream)
+        else:
+            self.gather.backward(self.side.cuda_stream)
+        self.ev_join2.record(self.side)
+        dense_step()
+        main.wait_event(self.ev_join2)
 
     def capture(self) -> None:
         """Capture train_step into a CUDA graph (after one eager warm-up run has happened)."""
