@@ -698,16 +698,9 @@ gate_level_dwg_reduce_kernel(const MmlrecGateLevel* lv, const float* scratch, in
   const int ix = threadIdx.x & 31, iy = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + ix;
   float s = 0.f;
-  if (i < total_wg) {   // 8 independent loads in flight per thread (the loop is L2-latency bound), fixed order
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f, a5 = 0.f, a6 = 0.f, a7 = 0.f;
-    int c = iy;
-    for (; c + 56 < n_cta; c += 64) {
-      const float* q = scratch + (int64_t)c * total_wg + i;
-      a0 += q[0]; a1 += q[(int64_t)8 * total_wg]; a2 += q[(int64_t)16 * total_wg]; a3 += q[(int64_t)24 * total_wg];
-      a4 += q[(int64_t)32 * total_wg]; a5 += q[(int64_t)40 * total_wg]; a6 += q[(int64_t)48 * total_wg]; a7 += q[(int64_t)56 * total_wg];
-    }
-    for (; c < n_cta; c += 8) a0 += scratch[(int64_t)c * total_wg + i];
-    s = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  if (i < total_wg) {
+#pragma unroll 4
+    for (int c = iy; c < n_cta; c += 8) s += scratch[(int64_t)c * total_wg + i];
   }
   red[iy][ix] = s;
   __syncthreads();
