@@ -407,6 +407,11 @@ int mmlrec_star_fold(const float* d_w_eff, int64_t ld_w, const float* d_b_eff, c
                      float* d_shared_b, float* d_spec_last, float* d_spec_b_last, void* stream);
 
 /* small utilities */
+/* Deterministic split-K for the batch-contraction wgrad GEMMs: the S partial problems write their tiles into S
+ * scratch slices; this sums the slices in a fixed order into the gradient buffer.
+ * segments: int64 [n_segments][3] = {dst element offset, src element offset inside a slice, element count}. */
+int mmlrec_sum_slices(const int64_t* segments, int32_t n_segments, int64_t max_n, float* dst, const float* src,
+                      int32_t S, int64_t slice_stride, void* stream);
 int mmlrec_fill_f32(float* p, int64_t n, float v, void* stream);
 int mmlrec_cast_f32_to_bf16(const float* src, int64_t ld_src, uint16_t* dst, int64_t ld_dst,
                             int32_t rows, int32_t cols, int32_t cols_pad, void* stream);

@@ -668,6 +668,29 @@ extern "C" int mmlrec_dense_optimizer_step(float* param, const float* grad, floa
   MMLREC_RETURN_LAUNCH(1);
 }
 
+namespace mmlrec {
+// dst[seg.dst + i] = sum_{s < S} src[s * slice_stride + seg.src + i]   (fixed order: deterministic split-K wgrad)
+__global__ void __launch_bounds__(256) sum_slices_kernel(const int64_t* seg, float* dst, const float* src, int S,
+                                                         int64_t slice_stride) {
+  const int64_t d0 = seg[blockIdx.y * 3 + 0], s0 = seg[blockIdx.y * 3 + 1], n = seg[blockIdx.y * 3 + 2];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    float acc = src[s0 + i];
+    for (int k = 1; k < S; ++k) acc += src[(int64_t)k * slice_stride + s0 + i];
+    dst[d0 + i] = acc;
+  }
+}
+}  // namespace mmlrec
+
+extern "C" int mmlrec_sum_slices(const int64_t* segments, int32_t n_segments, int64_t max_n, float* dst, const float* src,
+                                 int32_t S, int64_t slice_stride, void* stream) {
+  MMLREC_CHECK_ARG(segments && dst && src && n_segments > 0 && S > 0 && max_n > 0, "bad args");
+  int gx = (int)((max_n + 255) / 256);
+  if (gx > 592) gx = 592;
+  dim3 grid(gx, n_segments);
+  mmlrec::sum_slices_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(segments, dst, src, S, slice_stride);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
 extern "C" int mmlrec_fill_f32(float* p, int64_t n, float v, void* stream) {
   if (n <= 0) return 0;
   fill_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(p, n, v);

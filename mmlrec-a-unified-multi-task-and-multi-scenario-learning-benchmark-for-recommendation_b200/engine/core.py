@@ -560,6 +560,19 @@ class LinearStage(Stage):
         b, st = self.b, self.b.store
         self.live_groups: List[_Group] = []
         waves: List[list] = [[]]
+        # deterministic split-K of the wgrad problems (tensor-core mode): 1024 samples per slice, at most 4 slices
+        # -- only where the launch would otherwise be a handful of very long tiles (e.g. the towers: 4 tiles of 64
+        # k-blocks -> 33 us; split 4 ways 16 us + 4 us sum).  With tens of wgrad tiles the extra partial-tile
+        # epilogues cost more than the shorter critical path saves (measured, profiles/splitk_r01.txt).
+        self.split_k = 1
+        if b.tc and b.B % 1024 == 0:
+            wg_tiles = sum(((g.N + 127) // 128) * ((g.K + 127) // 128)
+                           for g in self.groups if any(o.grad_written for o in g.outs))
+            for cand in (4, 2):
+                if cand <= b.B // 1024 and 0 < wg_tiles * cand <= 32:
+                    self.split_k = cand
+                    break
+        split_segments, split_descs, split_at = [], [], 0
         dzg = self.zs[0].group if self.use_bn else self.outs[0].group   # where dZ lives
         for g in self.groups:
             if not any(o.grad_written for o in g.outs):
@@ -596,13 +609,30 @@ class LinearStage(Stage):
                     waves[wave].append(q)
             else:
                 dz16, dz_ld = dzg.gbuf16.data_ptr() + 2 * g.y_col, dzg.gbuf16.stride(0)
-                d = L.GemmTcDesc()   # wgrad: both operands MN-major (no transposed copies)
-                d.A, d.lda, d.a_mn_major = dz16, dz_ld, 1
-                d.B, d.ldb, d.b_mn_major = x.ptr16, x.ld16, 1
-                d.M, d.N, d.K = g.N, g.K, b.B
-                d.C_f32, d.ldc_f32 = st.grad_ptr(g.W), g.W._mm_ld
-                d.colsum = st.grad_ptr(g.b) if g.b is not None else None
-                waves[0].append(d)
+                # wgrad: both operands MN-major (no transposed copies).  The contraction runs over the batch, so a
+                # tile is B/64 k-blocks long; it is split into S batch slices whose partial tiles go to scratch
+                # slices and are summed in a fixed order afterwards (deterministic split-K)
+                S = self.split_k
+                w_span = g.N * g.W._mm_ld
+                w_at, b_at = split_at, split_at + w_span
+                if S > 1:
+                    split_segments.append((g.W._mm_off, w_at, w_span))
+                    if g.b is not None:
+                        split_segments.append((g.b._mm_off, b_at, g.N))
+                    split_at = _align(b_at + (g.N if g.b is not None else 0), 8)
+                for k in range(S):
+                    rows = b.B // S
+                    d = L.GemmTcDesc()
+                    d.A, d.lda, d.a_mn_major = dz16 + 2 * k * rows * dz_ld, dz_ld, 1
+                    d.B, d.ldb, d.b_mn_major = x.ptr16 + 2 * k * rows * x.ld16, x.ld16, 1
+                    d.M, d.N, d.K = g.N, g.K, rows
+                    if S > 1:   # scratch pointers are filled in once the slice size is known
+                        d.ldc_f32 = g.W._mm_ld
+                        split_descs.append((d, k, w_at, b_at if g.b is not None else None))
+                    else:
+                        d.C_f32, d.ldc_f32 = st.grad_ptr(g.W), g.W._mm_ld
+                        d.colsum = st.grad_ptr(g.b) if g.b is not None else None
+                    waves[0].append(d)
                 if want_dx:
                     e = L.GemmTcDesc()   # dgrad: A = dZ (K-major), B = W read MN-major
                     e.A, e.lda, e.a_mn_major = dz16, dz_ld, 0
@@ -619,6 +649,18 @@ class LinearStage(Stage):
                     waves[wave].append(e)
             if want_dx:
                 x.grad_written = True
+        self.split_sum = None
+        if split_descs:
+            slice_floats = _align(split_at, 8)
+            self.split_scratch = b.zeros(self.split_k * slice_floats)
+            base = self.split_scratch.data_ptr()
+            for d, k, w_at, b_at in split_descs:
+                d.C_f32 = base + 4 * (k * slice_floats + w_at)
+                if b_at is not None:
+                    d.colsum = base + 4 * (k * slice_floats + b_at)
+            seg = [v for t in split_segments for v in t]
+            self.split_sum = (b.ints(seg, dtype=torch.int64), len(split_segments), max(t[2] for t in split_segments),
+                              slice_floats)
         self.bwd = []
         for wv in waves:
             if not wv:
@@ -645,6 +687,11 @@ class LinearStage(Stage):
                     b.store.grad_ptr(bn0.weight), b.store.grad_ptr(bn0.bias), stream), f"bn bwd {self.label}")
         for tbl in self.bwd:
             self._launch(tbl, stream, "linear bwd")
+        if self.split_sum is not None:
+            seg, n_seg, max_n, slice_floats = self.split_sum
+            L.check(b.lib.mmlrec_sum_slices(seg.data_ptr(), n_seg, max_n, b.store.dense_grad.data_ptr(),
+                                            self.split_scratch.data_ptr(), self.split_k, slice_floats, stream),
+                    f"split-K sum {self.label}")
 
 
 def mlp_stages(b: Builder, items: Sequence[Tuple[Act, nn.Module]], label: str) -> List[Act]:

@@ -124,6 +124,7 @@ _SIGNATURES = {
     "mmlrec_emb_push_grads": (C.c_int, [vp, i64, i32, vp, i64, vp, i32, i32, i32, i32, i32, vp, vp]),
     "mmlrec_sort_field_keys": (C.c_int, [vp, i32, i32, vp, vp, vp, vp, vp]),
     "mmlrec_emb_backward_update_sharded": (C.c_int, [vp, i64, i32, vp, vp, vp, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "mmlrec_sum_slices": (C.c_int, [vp, i32, i64, vp, vp, i32, i64, vp]),
     "mmlrec_gate_level_backward_tiled": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, i32, vp, vp]),
     "mmlrec_gate_level_backward_tiled_scratch": (i64, [i32, i32]),
     "mmlrec_gate_level_forward_tiled": (C.c_int, [vp, i32, i32, i32, i32, i32, i32, vp]),
