@@ -322,7 +322,8 @@ __global__ void emb_stamp_rows_kernel(const int32_t* sorted_ids, const int64_t* 
   }
 }
 
-// Adam's zero-gradient update for every row not touched in this step (dense-Adam semantics).
+// Zero-gradient update for every row not touched in this step (dense optimizer semantics of nn.Embedding(sparse=False):
+// Adam rows keep moving by their momentum, RMSprop's square_avg keeps decaying; Adagrad / SGD rows are unaffected).
 __global__ void emb_adam_sweep_kernel(float* emb, float* m, float* v, const int32_t* row_touch,
                                       int64_t total_rows, int D, const MmlrecHyper* hyper) {
   const MmlrecHyper hp = *hyper;
@@ -331,6 +332,12 @@ __global__ void emb_adam_sweep_kernel(float* emb, float* m, float* v, const int3
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     int64_t row = i / dv;
     if (row_touch[row] == hp.step) continue;
+    if (hp.optimizer == MMLREC_OPT_RMSPROP) {   // zero gradient: square_avg *= alpha, the row itself does not move
+      float4 q = reinterpret_cast<float4*>(m)[i];
+      q.x *= hp.alpha; q.y *= hp.alpha; q.z *= hp.alpha; q.w *= hp.alpha;
+      reinterpret_cast<float4*>(m)[i] = q;
+      continue;
+    }
     float4 p4 = reinterpret_cast<float4*>(emb)[i];
     float4 m4 = reinterpret_cast<float4*>(m)[i];
     float4 v4 = reinterpret_cast<float4*>(v)[i];

@@ -354,10 +354,11 @@ class GatherStage(Stage):
                                                 self.meta.data_ptr(), self.F_s, self.sorted_ids.data_ptr(),
                                                 self.sorted_pos.data_ptr(), self.keys_ws.data_ptr(), stream),
                     "sort_field_ids")
-        if self.model.optimizer_name == "adam":
+        if self.model.optimizer_name in ("adam", "rmsprop"):   # optimizers whose zero-gradient update is not a no-op
             L.check(b.lib.mmlrec_emb_stamp_rows(self.sorted_ids.data_ptr(), self.meta.data_ptr(), self.F_s, self.B_all, self.D,
                                                 st.row_touch.data_ptr(), hy.data_ptr(), stream), "emb_stamp_rows")
-            L.check(b.lib.mmlrec_emb_adam_dense_sweep(st.emb.data_ptr(), st.emb_s1.data_ptr(), st.emb_s2.data_ptr(),
+            L.check(b.lib.mmlrec_emb_adam_dense_sweep(st.emb.data_ptr(), st.emb_s1.data_ptr(),
+                                                      st.emb_s2.data_ptr() if st.emb_s2 is not None else None,
                                                       st.row_touch.data_ptr(), st.n_emb // self.D, self.D,
                                                       hy.data_ptr(), stream), "emb_adam_dense_sweep")
 

@@ -205,6 +205,8 @@ class FlatStore:
         if need2 and self.dense_s2 is None:
             self.dense_s2 = torch.zeros(self.n_dense, dtype=torch.float32, device=self.device)
             self.emb_s2 = torch.zeros_like(self.emb)
+
+        if optimizer in ("adam", "rmsprop") and self.row_touch is None:   # dense zero-gradient sweep (K2 stamps rows)
             self.row_touch = torch.full((max(self.n_emb // max(self.emb_dim, 1), 1),), -1, dtype=torch.int32,
                                         device=self.device)
 

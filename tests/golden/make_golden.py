@@ -52,6 +52,8 @@ CASES = {
     "star_movielens_adam": ("movielens_star", dict(vocab_scale=0.02), dict(dnn_hidden_units=[16, 16]), {}),
     "pepnet_movielens_adam": ("movielens_pepnet", dict(vocab_scale=0.02), dict(dnn_hidden_units=[16, 16]), {}),
     "mmoe_synth26_adagrad": ("synth26_mmoe", dict(vocab=97), SMALL, {}),
+    "sharedbottom_kuairec_sgd": ("kuairec_sharedbottom", dict(max_vocab=200), SMALL, dict(optimizer="sgd", lr=1e-2)),
+    "esmm_kuairec_rmsprop": ("kuairec_esmm", dict(max_vocab=200), SMALL, dict(optimizer="rmsprop", lr=1e-3)),
     "mmoe_nogate_notower_adam": ("movielens_star", dict(vocab_scale=0.02),
                                  dict(model_name="mmoe", expert_dnn_hidden_units=[16, 16]), {}),
 }
@@ -107,7 +109,10 @@ def reference_step(model, X, y):
 
 
 def main():
+    only = set(sys.argv[1:])   # optional: regenerate only the named cases
     for case, (wl, kw, mc_over, oc_over) in CASES.items():
+        if only and case not in only:
+            continue
         cfg, fields = synthetic.workload(wl, **kw)
         cfg["model_config"].update(mc_over)
         cfg["optim_config"].update(oc_over)
