@@ -329,10 +329,10 @@ __device__ __forceinline__ void gt_bar_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void gt_setup(const MmlrecGateLevel* lv, MmlrecGateLevel& L, GtTables& T, bool backward,
                                          uint64_t* bar) {
   const int tid = threadIdx.x;
-  for (int i = tid; i < (int)(sizeof(MmlrecGateLevel) / 4); i += GT_THREADS)
+  for (int i = tid; i < (int)(sizeof(MmlrecGateLevel) / 4); i += (int)blockDim.x)
     reinterpret_cast<uint32_t*>(&L)[i] = reinterpret_cast<const uint32_t*>(lv)[i];
   if (tid == 0) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gt_smem_u32(bar)), "r"(GT_THREADS));
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(gt_smem_u32(bar)), "r"((int)blockDim.x));
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
@@ -349,7 +349,7 @@ __device__ __forceinline__ void gt_setup(const MmlrecGateLevel* lv, MmlrecGateLe
     T.wg_off[G] = a; T.ne_off[G] = c; T.hg_off[G] = d; T.pair_off[G] = p;
   }
   __syncthreads();
-  for (int i = tid; i < E * G; i += GT_THREADS) {   // thread <-> (expert, gate)
+  for (int i = tid; i < E * G; i += (int)blockDim.x) {   // thread <-> (expert, gate)
     const int u = i / G, g = i - u * G;
     const int e = L.slot[u][g];
     if (e < 0 || !T.live[g]) continue;
@@ -381,7 +381,7 @@ __device__ __forceinline__ void gt_stage(const MmlrecGateLevel& L, const GtTable
   const uint32_t b32 = gt_smem_u32(bar);
   const int n_items = n_src * GT_ROWS;
   uint32_t bytes = 0;
-  for (int it = tid; it < n_items + n_pairs; it += GT_THREADS) {
+  for (int it = tid; it < n_items + n_pairs; it += (int)blockDim.x) {
     if (it < n_items) {
       const int v = it >> 3, r = it & (GT_ROWS - 1);
       if (r < n_rows) bytes += (uint32_t)T.n4[v] << 4;
@@ -391,7 +391,7 @@ __device__ __forceinline__ void gt_stage(const MmlrecGateLevel& L, const GtTable
   }
   if (bytes) asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b32), "r"(bytes) : "memory");
   else asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(b32) : "memory");
-  for (int it = tid; it < n_items + n_pairs; it += GT_THREADS) {
+  for (int it = tid; it < n_items + n_pairs; it += (int)blockDim.x) {
     if (it < n_items) {
       const int v = it >> 3, r = it & (GT_ROWS - 1);
       const int n4 = T.n4[v];
@@ -405,8 +405,13 @@ __device__ __forceinline__ void gt_stage(const MmlrecGateLevel& L, const GtTable
   gt_bar_wait(b32, 0);
 }
 
-__global__ void __launch_bounds__(GT_THREADS, 2)
+// NT = 256: one warp per sample.  NT = 512: two warps per sample (pairs / gates split between them) -- the phases are
+// chains of dependent LDS -> FMA -> SHFL, so twice the resident warps hide twice the latency.
+template <int NT>
+__global__ void __launch_bounds__(NT, 2)
 gate_level_forward_tiled_kernel(const MmlrecGateLevel* lv, int B) {
+  constexpr int NW = NT / 32, PARTS = NW / GT_ROWS;
+  static_assert(NW % GT_ROWS == 0, "warps must be a multiple of the samples per CTA");
   extern __shared__ __align__(128) float dyn_s[];
   __shared__ __align__(16) MmlrecGateLevel L;
   __shared__ GtTables T;
@@ -437,10 +442,13 @@ gate_level_forward_tiled_kernel(const MmlrecGateLevel* lv, int B) {
   // ---- F1: logits; a warp owns a sample, 8 lanes share one (gate, expert) dot product
   {
     const int sub = lane & 7, pl = lane >> 3;
-    for (int r = w; r < n_rows; r += GT_WARPS) {
+    const int r = w % GT_ROWS, part = w / GT_ROWS;
+    const int q_per = ((total_ne + 3) / 4 + PARTS - 1) / PARTS;           // pair-quads per part
+    const int p_lo = 4 * q_per * part, p_hi = min(total_ne, p_lo + 4 * q_per);
+    if (r < n_rows) {
       const float* gin_r = gin_s + r * total_hg;
 #pragma unroll 3
-      for (int p0 = 0; p0 < total_ne; p0 += 4) {   // uniform trip count: shuffles inside
+      for (int p0 = p_lo; p0 < p_hi; p0 += 4) {   // uniform trip count: shuffles inside
         const int p = p0 + pl;
         const bool pv = p < total_ne;
         float s = 0.f;
@@ -466,7 +474,7 @@ gate_level_forward_tiled_kernel(const MmlrecGateLevel* lv, int B) {
   }
   __syncthreads();
   // ---- F2: softmax per (sample, gate); probabilities are saved for the backward pass
-  for (int it = tid; it < n_rows * G; it += GT_THREADS) {
+  for (int it = tid; it < n_rows * G; it += NT) {
     const int r = it / G, g = it - r * G;
     const int ne = L.n_e[g];
     float* pr = p_s + r * total_ne + T.ne_off[g];
@@ -479,10 +487,11 @@ gate_level_forward_tiled_kernel(const MmlrecGateLevel* lv, int B) {
   }
   __syncthreads();
   // ---- F3: mixtures; a warp owns a sample, lane <-> 4 columns
-  for (int r = w; r < n_rows; r += GT_WARPS) {
+  if (w % GT_ROWS < n_rows) {
+    const int r = w % GT_ROWS;
     const int b = r0 + r;
     const float4* eo = reinterpret_cast<const float4*>(eo_s + r * E * H);
-    for (int g = 0; g < G; ++g) {
+    for (int g = w / GT_ROWS; g < G; g += PARTS) {
       const int ne = L.n_e[g], off = T.ne_off[g];
       const float* pr = p_s + r * total_ne + off;
       const uint16_t* eoff = T.pair_eo + off;
@@ -795,10 +804,17 @@ extern "C" int mmlrec_gate_level_forward_tiled(const MmlrecGateLevel* level, int
   MMLREC_CHECK_ARG(smem <= 110 * 1024, "level too large for the tiled kernel");
   static int64_t opted = 0;
   if (smem > opted) {
-    cudaError_t e = cudaFuncSetAttribute(gate_level_forward_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(gate_level_forward_tiled_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+      e = cudaFuncSetAttribute(gate_level_forward_tiled_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { set_error("gate_level_forward_tiled: smem opt-in failed"); return (int)e; }
     opted = smem;
   }
-  gate_level_forward_tiled_kernel<<<cdiv(B, GT_ROWS), GT_THREADS, (size_t)smem, (cudaStream_t)stream>>>(level, B);
+  static int threads = 0;
+  if (!threads) { const char* e = getenv("MMLREC_GATE_FWD_THREADS"); threads = (e && atoi(e) == 256) ? 256 : 512; }
+  if (threads == 256)
+    gate_level_forward_tiled_kernel<256><<<cdiv(B, GT_ROWS), 256, (size_t)smem, (cudaStream_t)stream>>>(level, B);
+  else
+    gate_level_forward_tiled_kernel<512><<<cdiv(B, GT_ROWS), 512, (size_t)smem, (cudaStream_t)stream>>>(level, B);
   MMLREC_RETURN_LAUNCH(1);
 }
