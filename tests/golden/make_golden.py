@@ -52,6 +52,9 @@ CASES = {
     "star_movielens_adam": ("movielens_star", dict(vocab_scale=0.02), dict(dnn_hidden_units=[16, 16]), {}),
     "pepnet_movielens_adam": ("movielens_pepnet", dict(vocab_scale=0.02), dict(dnn_hidden_units=[16, 16]), {}),
     "mmoe_synth26_adagrad": ("synth26_mmoe", dict(vocab=97), SMALL, {}),
+    "ple_ae_t2_l3_adam": ("ae_ple_t2", dict(max_vocab=300), dict(SMALL, num_levels=3), {}),
+    "sharedbottom_kuairec_adagrad": ("kuairec_sharedbottom", dict(max_vocab=200), SMALL, dict(optimizer="adagrad", lr=1e-2)),
+    "mmoe_synth26_adam": ("synth26_mmoe", dict(vocab=97), SMALL, dict(optimizer="adam", lr=1e-3)),
     "sharedbottom_kuairec_sgd": ("kuairec_sharedbottom", dict(max_vocab=200), SMALL, dict(optimizer="sgd", lr=1e-2)),
     "esmm_kuairec_rmsprop": ("kuairec_esmm", dict(max_vocab=200), SMALL, dict(optimizer="rmsprop", lr=1e-3)),
     "mmoe_nogate_notower_adam": ("movielens_star", dict(vocab_scale=0.02),
