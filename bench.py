@@ -166,8 +166,9 @@ def run_reference(args, rank, world):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, "batch": args.batch, "model": cfg["model_config"]["model_name"],
-                       "optimizer": cfg["optim_config"]["optimizer"]},
+            "config": {"workload": args.workload, "batch_per_gpu": args.batch, "global_batch": args.batch * max(args.gpus, 1),
+                       "model": cfg["model_config"]["model_name"], "optimizer": cfg["optim_config"]["optimizer"],
+                       "precision": "fp32", "parallelism": "host cpu (each step = one per-GPU batch of the workload)"},
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{args.steps} full training steps of batch {args.batch} "
                                        "(oracle/mmlrec_oracle.py: the reference's step body on torch CPU)"},
