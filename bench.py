@@ -361,6 +361,8 @@ def run_ours(args, rank, world):
     barrier()
     ms_e2e = max(a2.elapsed_time(b2), 1e3 * (time.perf_counter() - t0))
     clocks = sampler.stop() if sampler else None
+    if sharded:
+        model.shard.check()   # raises if a peer-memory barrier ever gave up waiting (a rank died)
     if world > 1:
         import torch.distributed as dist
         t = torch.tensor([ms, ms_e2e], device=device, dtype=torch.float64)
