@@ -1,11 +1,11 @@
-// Row-fused gate stage (fast path of model/mmoe.py:80-88 / model/ple.py:127-152 and their backward).
-// A warp owns one sample.  Forward: logits of every gate of the level against gate-head weights staged
-// in shared memory, softmax in registers (lane e <-> expert slot e), then ONE pass over the level's
-// distinct expert rows (128-bit loads) accumulating every gate's mixture.  Backward: ONE pass over the
-// expert rows produces d(expert) (sum over the gates that use it, ReLU-masked) and the softmax input
-// gradients; d(gate_in) and the per-warp dWg slabs follow; CTA partials of dWg are reduced by the last
-// CTA in a fixed order (deterministic, no float atomics).  HBM/L2-bound: every activation row of the
-// level is read once and every output row written once.
+// Level-fused gate stage (model/mmoe.py:80-88 / model/ple.py:127-152 and their backward): one record describes
+// ALL gates of a level and the level's distinct expert activations.
+//   * tiled kernels (default, second half of this file): a CTA stages the rows of 8 samples in shared memory;
+//   * warp-per-sample kernels (first half; fallback for unaligned rows or levels whose tile exceeds 110 KB): a warp
+//     owns one sample, softmax in registers (lane e <-> expert slot e), ONE pass over the expert rows with
+//     batched 128-bit loads.
+// Either way every activation row of the level is read once and every output row written once, and the CTA
+// partials of dWg are reduced in a fixed order by gate_level_dwg_reduce_kernel (deterministic, no float atomics).
 #include "common.cuh"
 
 namespace mmlrec {
@@ -127,7 +127,7 @@ __global__ void __launch_bounds__(GL_FWD_WARPS * 32, 4) gate_level_forward_kerne
   }
 }
 
-// dynamic smem: dl_s [32 rows][total_ne] + gin_s [32 rows][total_hg]   (total_ne = sum n_e, total_hg = sum Hg)
+// dynamic smem: dl_s [GL_BWD_ROWS][total_ne] + gin_s [GL_BWD_ROWS][total_hg]   (total_ne = sum n_e, total_hg = sum Hg)
 __global__ void __launch_bounds__(GL_BWD_WARPS * 32, 3)
 gate_level_backward_kernel(const MmlrecGateLevel* lv, int B, float* scratch) {
   extern __shared__ __align__(16) float dyn_s[];
@@ -144,8 +144,8 @@ gate_level_backward_kernel(const MmlrecGateLevel* lv, int B, float* scratch) {
   }
   __syncthreads();
   const int total_wg = wg_off[G], total_ne = ne_off[G], total_hg = hg_off[G];
-  float* dl_s = dyn_s;                            // [32][total_ne]
-  float* gin_s = dyn_s + GL_BWD_ROWS * total_ne;  // [32][total_hg]
+  float* dl_s = dyn_s;                            // [GL_BWD_ROWS][total_ne]
+  float* gin_s = dyn_s + GL_BWD_ROWS * total_ne;  // [GL_BWD_ROWS][total_hg]
   const int r0 = blockIdx.x * GL_BWD_ROWS;
   for (int rr = 0; rr < 1; ++rr) {
     const int r = w;
