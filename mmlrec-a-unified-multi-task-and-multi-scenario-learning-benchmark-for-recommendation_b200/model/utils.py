@@ -124,7 +124,9 @@ class DNN(nn.Module):
             raise ValueError("hidden_units is empty!!")
         if dropout_rate and dropout_rate > 0:
             raise NotImplementedError("dnn_dropout > 0 is not supported by the fused step (all shipped configs use 0)")
-        if activation not in ("relu", "sigmoid", None):
+        if activation not in ("relu", None):
+            # 'sigmoid' / 'prelu' hidden layers: the fused gradient writers fold only the ReLU mask (and GateNN's
+            # 2*sigmoid) into their epilogues; no shipped config asks for anything else (dnn_activation = relu)
             raise NotImplementedError(f"activation {activation!r} is not supported by the fused step")
         self.activation, self.use_bn, self.l2_reg, self.dropout_rate = activation, use_bn, l2_reg, dropout_rate
         dims = [inputs_dim] + list(hidden_units)

@@ -139,6 +139,15 @@ def bce_sum(pred: Tensor, y: Tensor) -> Tensor:
     return sum(F.binary_cross_entropy(pred[:, t], y[:, t], reduction="sum") for t in range(pred.shape[1]))
 
 
+def loss_sum(pred: Tensor, y: Tensor, loss_names: Optional[Sequence[str]] = None) -> Tensor:
+    """basemodel.py:294-296 with the per-task loss functions of ``_get_loss_func_single`` (:595-604):
+    'binary_crossentropy' -> F.binary_cross_entropy, 'mse' -> F.mse_loss, 'mae' -> F.l1_loss, all reduction='sum'."""
+    if loss_names is None:
+        return bce_sum(pred, y)
+    fns = {"binary_crossentropy": F.binary_cross_entropy, "mse": F.mse_loss, "mae": F.l1_loss}
+    return sum(fns[loss_names[t]](pred[:, t], y[:, t], reduction="sum") for t in range(pred.shape[1]))
+
+
 def _gate_mix(gate_logits: Tensor, experts: List[Tensor]) -> Tensor:
     """softmax(gate) @ stack(experts)  (mmoe.py:86, ple.py:139)."""
     stack = torch.stack(experts, 1)  # [B,E,H]
@@ -335,6 +344,8 @@ class OracleTrainer:
         self.buffers = {k: v.detach().clone() for k, v in (buffers or {}).items()}
         oc = config["optim_config"]
         lr, name = oc.get("lr", 1e-3), oc.get("optimizer", "adagrad")
+        loss = oc.get("loss", "binary_crossentropy")
+        self.loss_names = [loss] * self.spec.num_tasks if isinstance(loss, str) else list(loss)
         leaves = [self.params[k] for k in keys]
         if name == "adam":  # basemodel.py:569-584
             self.optim = torch.optim.Adam(leaves, lr=lr)
@@ -353,7 +364,7 @@ class OracleTrainer:
     def loss_and_grads(self, X: Tensor, y: Tensor) -> Tuple[Tensor, Tensor, Dict[str, Optional[Tensor]]]:
         pred = self.forward(X, training=True)
         self.optim.zero_grad()
-        loss = bce_sum(pred, y.float())
+        loss = loss_sum(pred, y.float(), self.loss_names)
         loss.backward()
         grads = {k: (None if self.params[k].grad is None else self.params[k].grad.detach().clone())
                  for k in self.trainable}

@@ -59,7 +59,32 @@ CASES = {
     "esmm_kuairec_rmsprop": ("kuairec_esmm", dict(max_vocab=200), SMALL, dict(optimizer="rmsprop", lr=1e-3)),
     "mmoe_nogate_notower_adam": ("movielens_star", dict(vocab_scale=0.02),
                                  dict(model_name="mmoe", expert_dnn_hidden_units=[16, 16]), {}),
+    # regression head: PredictionLayer('regression') is the identity and the task's loss is F.mse_loss(sum)
+    # (model/utils.py:246-247, model/basemodel.py:595-604); labels of task 1 are continuous
+    "sharedbottom_kuairec_mse_adam": ("kuairec_sharedbottom", dict(max_vocab=200),
+                                      dict(SMALL, task_types=["binary", "regression"]),
+                                      dict(loss=["binary_crossentropy", "mse"])),
+    # saturated logits: head bias 30 -> sigmoid == 1.0f: BCE-on-probabilities gives loss 100 per
+    # negative sample (log clamp at -100) and a ZERO gradient, unlike bce_with_logits
+    "sharedbottom_kuairec_saturated_sgd": ("kuairec_sharedbottom", dict(max_vocab=200), SMALL,
+                                           dict(optimizer="sgd", lr=1e-2)),
 }
+
+
+def post_build(case, model):
+    """Edits of the seeded initial state; returns the names touched (stored as meta/init_overridden)."""
+    if case == "sharedbottom_kuairec_saturated_sgd":
+        with torch.no_grad():
+            model.out[0].bias.fill_(30.0)
+        return ["out.0.bias"]
+    return []
+
+
+def make_labels(case, y, seed):
+    if case == "sharedbottom_kuairec_mse_adam":
+        y = y.copy()
+        y[:, 1] = np.random.default_rng(5000 + seed).normal(0.3, 1.0, size=len(y)).astype(np.float32)
+    return y
 
 
 def build_reference(cfg, fields, init_std=0.0001):
@@ -103,7 +128,8 @@ def reference_step(model, X, y):
     y = y.float()
     y_pred = model(x, None).squeeze()
     model.optim.zero_grad()
-    loss = sum(F.binary_cross_entropy(y_pred[:, i], y[:, i], reduction="sum") for i in range(model.num_tasks))
+    # model.loss_func is the list compile() built through _get_loss_func_single (basemodel.py:595-604)
+    loss = sum(model.loss_func[i](y_pred[:, i], y[:, i], reduction="sum") for i in range(model.num_tasks))
     total = loss + model.get_regularization_loss() + model.aux_loss + torch.zeros((1,))
     total.backward()
     grads = {n: (None if p.grad is None else p.grad.detach().clone()) for n, p in model.named_parameters()}
@@ -122,8 +148,9 @@ def main():
         torch.manual_seed(1234)
         np.random.seed(1234)
         model = build_reference(cfg, fields, INIT_STD.get(case, 0.0001))
+        overridden = post_build(case, model)
         model.train()
-        blob = {}
+        blob = {"meta/init_overridden": np.array(overridden, dtype=str)}
         for k, v in model.state_dict().items():
             blob["init/" + k] = v.detach().numpy().copy()
         for k, v in unregistered_star_tensors(model).items():
@@ -132,6 +159,7 @@ def main():
         blob["meta/buffers"] = np.array([n for n, _ in model.named_buffers()])
         for s in range(STEPS):
             X, y = synthetic.make_batch(cfg, fields, BATCH, seed=100 + s)
+            y = make_labels(case, y, s)
             blob[f"step{s}/X"], blob[f"step{s}/y"] = X, y
             pred, loss, grads = reference_step(model, torch.from_numpy(X), torch.from_numpy(y))
             blob[f"step{s}/pred"] = pred.numpy()

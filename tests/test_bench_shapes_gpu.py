@@ -1,0 +1,230 @@
+"""GPU parity AT THE SHAPES bench.py MEASURES (BASELINE.json configs, unshrunk): the full training step through
+the public API against the oracle on the same seeded state and batches, in both arithmetic modes.
+
+What only these shapes exercise: the 992-tile level-0 GEMM under the static tile schedule, K=4096
+batch-contraction wgrad tiles (both operands MN-major) incl. the deterministic split-K + ``sum_slices_kernel``,
+``gate_level_*_tiled`` at H=128 with 5- and 14-expert gates, gather -> K2 at B=4096 inside a step, BatchNorm at
+B=1024.  Tolerances are BASELINE.json's: fp32 1e-5 relative on predictions / loss / gradients, bf16 2e-2."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from helpers import build_pair, rel_err  # noqa: E402
+
+# workload, kwargs, batch, init_std.  init_std=1e-4 is what bench.py runs (the reference default);
+# 0.05 makes every hidden activation O(1) so that a wrong tile / mask / gate would move the result.
+FULL = [
+    ("ae_ple_t4", dict(max_vocab=100_000), 4096, 1e-4),
+    ("ae_ple_t4", dict(max_vocab=100_000), 4096, 0.05),
+    ("synth26_mmoe", dict(vocab=100_000), 4096, 0.05),
+    ("census_mmoe", {}, 1024, 0.05),
+    ("kuairec_sharedbottom", {}, 4096, 0.05),
+    ("kuairec_esmm", {}, 4096, 0.05),
+    ("movielens_star", {}, 4096, 0.05),
+    ("movielens_pepnet", {}, 4096, 0.05),
+]
+
+
+def _ids(v):
+    return f"{v[0]}-B{v[2]}-std{v[3]}"
+
+
+def _dense_grads(model):
+    return {n: model.store.grad_view(p).detach().cpu().clone() for n, p in model.named_parameters()
+            if getattr(p, "_mm_kind", "") == "dense"}
+
+
+@pytest.mark.parametrize("case", FULL, ids=_ids)
+def test_fp32_full_shape_step_matches_oracle(case):
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from mmlrec_b200 import synthetic
+    wl, kw, B, init_std = case
+    model, oracle, cfg, fields, sd0 = build_pair(wl, kw, "fp32", init_std)
+    use_bn = cfg["model_config"].get("dnn_use_bn", False)
+    for s in range(3):   # eager, capture + replay, replay
+        X, y = synthetic.make_batch(cfg, fields, B, seed=40 + s)
+        pred_o, loss_o, grads_o = oracle.loss_and_grads(torch.from_numpy(X), torch.from_numpy(y))
+        oracle.optim.step()
+        loss = model.train_on_batch(X, y)
+        torch.cuda.synchronize()
+        pred = model.plan(B).pred.cpu()
+        assert rel_err(pred, pred_o) < 1e-5, f"step {s} predictions {rel_err(pred, pred_o):.3e}"
+        assert abs(float(loss[-1]) - float(loss_o)) <= 2e-5 * abs(float(loss_o)), f"step {s} loss"
+        if s == 0:
+            bad = []
+            for name, g in _dense_grads(model).items():
+                want = grads_o.get(name)
+                if want is None:
+                    assert float(g.abs().max()) == 0.0, f"{name} must not receive a gradient"
+                    continue
+                if use_bn and ".linears." in name and name.endswith(".bias"):
+                    continue   # exactly-zero true gradient: rounding noise on both sides (profiles/bn_conditioning_r01.txt)
+                scale, err = float(want.abs().max()), float((g - want).abs().max())
+                # element-wise against the tensor's largest entry (a B=4096 fp32 sum runs in another order than ATen's)
+                if err > 2e-5 * scale + 1e-9:
+                    bad.append(f"{name}: err {err:.3e} scale {scale:.3e}")
+            assert not bad, "gradients off: " + "; ".join(bad[:8])
+    want = oracle.state()
+    factor = 2e-3 if cfg["optim_config"]["optimizer"] in ("adam", "sgd") else 1e-2
+    for name, got in model.state_dict().items():
+        if got.dtype != torch.float32 or "embedding_dict" not in name:
+            continue
+        moved = float((want[name] - sd0[name]).abs().max())
+        assert float((got.cpu() - want[name]).abs().max()) <= factor * moved + 1e-7, f"table {name}"
+
+
+@pytest.mark.parametrize("case", [c for c in FULL if c[0] != "census_mmoe"], ids=_ids)
+def test_bf16_full_shape_step_matches_oracle(case):
+    """tcgen05 mode at the benchmarked shapes: predictions, loss and the dense gradient vector within 2e-2."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from mmlrec_b200 import synthetic
+    from mmlrec_b200.engine.core import GateMixStage
+    wl, kw, B, init_std = case
+    model, oracle, cfg, fields, sd0 = build_pair(wl, kw, "bf16", init_std)
+    for s in range(3):
+        X, y = synthetic.make_batch(cfg, fields, B, seed=40 + s)
+        pred_o, loss_o, grads_o = oracle.loss_and_grads(torch.from_numpy(X), torch.from_numpy(y))
+        oracle.optim.step()
+        loss = model.train_on_batch(X, y)
+        torch.cuda.synchronize()
+        assert torch.isfinite(loss).all()
+        if s > 0:
+            continue   # later steps inherit the bf16 rounding of the earlier updates
+        pred = model.plan(B).pred.cpu()
+        assert rel_err(pred, pred_o) < 2e-2, f"predictions {rel_err(pred, pred_o):.3e}"
+        assert abs(float(loss[-1]) - float(loss_o)) <= 2e-2 * abs(float(loss_o)), "loss"
+        got_all, want_all = [], []
+        for name, g in _dense_grads(model).items():
+            want = grads_o.get(name)
+            if want is None:
+                assert float(g.abs().max()) == 0.0, f"{name} must not receive a gradient"
+                continue
+            got_all.append(g.flatten())
+            want_all.append(want.flatten())
+        flat = rel_err(torch.cat(got_all), torch.cat(want_all))
+        assert flat < 2e-2, f"dense gradient vector rel err {flat:.3e}"
+    plan = model.plan(B)
+    if wl == "ae_ple_t4":
+        # the launch shapes this test exists for really ran
+        gates = [st for st in plan.stages if isinstance(st, GateMixStage)]
+        assert all(st.fused and st.tiled_fwd and st.tiled for st in gates if st.any_live), "tiled gate kernels"
+        assert sorted({len(g.experts) for st in gates for g in st.gates}) == [5, 14]
+        assert gates[0].H == 128
+
+
+def test_bf16_census_batchnorm_full_shape():
+    """Census MMoE, BatchNorm, B=1024 in bf16 mode.  BatchNorm centring amplifies the bf16 rounding of z
+    (DESIGN section 2): predictions / loss are held to 5e-2, the documented deviation from north_star's 2e-2."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from mmlrec_b200 import synthetic
+    model, oracle, cfg, fields, _ = build_pair("census_mmoe", {}, "bf16", 0.05)
+    X, y = synthetic.make_batch(cfg, fields, 1024, seed=40)
+    pred_o, loss_o = oracle.step(torch.from_numpy(X), torch.from_numpy(y))
+    loss = model.train_on_batch(X, y)
+    torch.cuda.synchronize()
+    assert rel_err(model.plan(1024).pred.cpu(), pred_o) < 5e-2
+    assert abs(float(loss[-1]) - float(loss_o)) <= 5e-2 * abs(float(loss_o))
+
+
+# ------------------------------------------------------------------------------------------------ kernels at full size
+@pytest.mark.parametrize("splits", [1, 2, 4])
+@pytest.mark.parametrize("M,N", [(256, 128), (64, 128), (3904, 199)])
+def test_tc_wgrad_k4096_mn_major_split_k(M, N, splits):
+    """dW[M,N] = dZ^T X with the contraction over a batch of 4096 (both operands MN-major, 64 k-blocks per tile),
+    plain and as deterministic split-K: S partial problems into scratch slices + sum_slices, vs fp32 torch."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from mmlrec_b200 import lib as L, ops
+    dev = torch.device("cuda:0")
+    g = torch.Generator().manual_seed(M + N + splits)
+    Bt = 4096
+    pad = lambda n: (n + 7) // 8 * 8  # noqa: E731
+    dz = torch.zeros(Bt, pad(M), dtype=torch.bfloat16, device=dev)
+    x = torch.zeros(Bt, pad(N), dtype=torch.bfloat16, device=dev)
+    dz[:, :M] = torch.randn(Bt, M, generator=g).to(torch.bfloat16).to(dev)
+    x[:, :N] = torch.randn(Bt, N, generator=g).to(torch.bfloat16).to(dev)
+    want = dz[:, :M].float().T @ x[:, :N].float()
+    want_b = dz[:, :M].float().sum(0)
+    ldw = pad(N)
+    span = M * ldw
+    slice_floats = (span + M + 7) // 8 * 8
+    if splits == 1:
+        out = torch.full((slice_floats,), float("nan"), device=dev)
+        d = ops.tc_desc(dz[:, :M], x[:, :N], M, N, Bt, a_mn=True, b_mn=True, C_f32=out[:span].view(M, ldw),
+                        rowsum_a=out[span:span + M])
+        ops.TcProblemTable([d], dev).launch()
+        torch.cuda.synchronize()
+        W, b = out[:span].view(M, ldw)[:, :N], out[span:span + M]
+    else:
+        rows = Bt // splits
+        scratch = torch.full((splits * slice_floats,), float("nan"), device=dev)
+        descs = []
+        for k in range(splits):
+            sl = scratch[k * slice_floats:(k + 1) * slice_floats]
+            descs.append(ops.tc_desc(dz[k * rows:(k + 1) * rows, :M], x[k * rows:(k + 1) * rows, :N], M, N, rows,
+                                     a_mn=True, b_mn=True, C_f32=sl[:span].view(M, ldw), rowsum_a=sl[span:span + M]))
+        ops.TcProblemTable(descs, dev).launch()
+        grad = torch.full((slice_floats,), float("nan"), device=dev)
+        seg = torch.tensor([0, 0, span, span, span, M], dtype=torch.int64, device=dev)   # (dst, src, n) x 2
+        L.check(L.load().mmlrec_sum_slices(seg.data_ptr(), 2, span, grad.data_ptr(), scratch.data_ptr(), splits,
+                                           slice_floats, torch.cuda.current_stream().cuda_stream), "sum_slices")
+        torch.cuda.synchronize()
+        W, b = grad[:span].view(M, ldw)[:, :N], grad[span:span + M]
+    assert rel_err(W, want) < 1e-5
+    assert rel_err(b, want_b) < 1e-5
+
+
+def test_sort_and_k2_at_global_batch_32768():
+    """The 8-GPU global batch (8 x 4096): multi-CTA bitonic passes of the sort and K2 runs that cross many chunks."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from mmlrec_b200 import ops
+    from oracle.mmlrec_oracle import Column, embedding_row_grads
+    dev = torch.device("cuda:0")
+    B, D, vocabs = 32768, 8, [2, 300, 1_000_000]
+    F = len(vocabs)
+    g = torch.Generator().manual_seed(9)
+    X = torch.stack([torch.randint(0, v, (B,), generator=g).float() for v in vocabs], 1)
+    d_input = torch.randn(B, F * D, generator=g)
+    meta = ops.field_meta([0] * F, vocabs, list(range(F)), D, dev)
+    ids, pos = ops.sort_field_ids(X.to(dev), meta)
+    for f in range(F):
+        col = X[:, f].long()
+        order = torch.argsort(col, stable=True)
+        assert torch.equal(pos[f].cpu().long(), order)
+        assert torch.equal(ids[f].cpu().long(), col[order])
+    out = torch.zeros(F, B, D, device=dev)
+    ops.emb_backward_update(d_input.to(dev), ids, pos, meta, D, ops.hyper_tensor("sgd", 0.1, dev), grad_rows_out=out)
+    cols = [Column(f"s{j}", "sparse", v, D) for j, v in enumerate(vocabs)]
+    want = embedding_row_grads(X, d_input, cols)
+    ids_c, out_c = ids.cpu().long(), out.cpu()
+    for f in range(F):
+        uniq, rows = want[f"s{f}"]
+        tail = torch.ones(B, dtype=torch.bool)
+        tail[:-1] = ids_c[f][1:] != ids_c[f][:-1]
+        assert torch.equal(ids_c[f][tail], uniq)
+        assert rel_err(out_c[f][tail], rows) < 5e-6
+
+
+def test_gather_ids_at_the_fp32_carrier_limit():
+    """ids travel as fp32, exact up to 2^24; 2^24 + 1 is not representable and rounds to 2^24 on the way
+    in (x.float()), so both read row 2^24 -- like the reference's ``X[:, j].long()``."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from mmlrec_b200 import ops
+    dev = torch.device("cuda:0")
+    V, D = (1 << 24) + 2, 4
+    emb = (torch.arange(V, device=dev, dtype=torch.int32).repeat_interleave(D) % 65521).float()   # row r holds r % 65521
+    ids = np.array([(1 << 24) - 1, 1 << 24, (1 << 24) + 1, 12345678], dtype=np.int64)
+    X = torch.from_numpy(ids.astype(np.float32)).view(-1, 1)
+    meta = ops.field_meta([0], [V], [0], D, dev)
+    out, _, oob = ops.gather_concat(X.to(dev), emb, meta, D)
+    want_rows = X[:, 0].long()                    # the reference's truncation of the fp32 carrier
+    assert want_rows.tolist() == [(1 << 24) - 1, 1 << 24, 1 << 24, 12345678]
+    assert int(oob.item()) == 0
+    assert torch.equal(out[:, 0].cpu(), (want_rows % 65521).float())

@@ -75,7 +75,10 @@ def test_same_state_dict_keys_and_seeded_init_as_reference(case):
     ref = {k[5:]: z[k] for k in z.files if k.startswith("init/") and ".specific_weights." not in k
            and ".specific_biases." not in k}
     assert set(sd) == set(ref)
+    edited = set(str(s) for s in z["meta/init_overridden"]) if "meta/init_overridden" in z.files else set()
     for k, v in ref.items():
+        if k in edited:
+            continue  # the golden script edited this entry after the seeded construction
         assert np.array_equal(sd[k].numpy(), v), k
     # STAR: the unregistered per-domain tensors must come out of the same RNG draws too
     for k in z.files:
