@@ -231,12 +231,27 @@ int mmlrec_gemm_grouped_tc_scheduled(const void* records, const int32_t* tile_pr
                                      int32_t n_ctas, void* stream);
 /* SM count of the current device (the scheduler's CTA budget); 0 without a device */
 int32_t mmlrec_tc_sm_count(void);
-/* same launch, plus per-tile clock64() stamps of CTA 0 into stamps[64][16] (int64, device): slots 0-3 TMA
- * producer (tile start, table read, first slot free, last load issued), 4-7 MMA issuer (tile start,
- * accumulator free, first operands landed, last commit), 8-11 epilogue (tile start, bias staged,
- * accumulator ready, tile stored).  Profiling aid. */
+/* same launch (tile_order / cta_start may be NULL = round-robin), plus profiling stamps (int64, device,
+ * 1024 + 8 * n_ctas entries): stamps[i*16 + slot] = clock64() of CTA 0 at its i-th tile (i < 64): slots 0-3 TMA
+ * producer (tile start, table read, first slot free, last load issued), 4-7 MMA issuer (tile start, accumulator
+ * free, first operands landed, last commit), 8-12 epilogue warp 0 (tile start, bias staged, accumulator ready, tile
+ * stored, accumulator released); stamps[1024 + cta*8 + k] = %globaltimer (ns) of every CTA: 0 setup done, 1 producer
+ * done, 2 MMA issuer done, 3 epilogue done, and [4] = its number of tiles.  Profiling aid. */
 int mmlrec_gemm_grouped_tc_debug(const void* records, const int32_t* tile_prefix, int32_t n_problems,
-                                 int32_t total_tiles, int64_t* stamps, void* stream);
+                                 int32_t total_tiles, const int32_t* tile_order, const int32_t* cta_start,
+                                 int32_t n_ctas, int64_t* stamps, void* stream);
+/* CTA-pair version of the same grouped GEMM (csrc/gemm_tc2.cu): clusters of two CTAs run tcgen05.mma.cta_group::2 on
+ * 256 x BN tiles (BN = 256, or 128 for narrow problems / bias-gradient problems wider than 240 columns), which halves
+ * the operand bytes each SM pulls from L2 per output element.  Same problem description, its own record format.
+ * The schedule arrays are per PAIR: pair p executes tiles tile_order[pair_start[p] .. pair_start[p+1]); NULL =
+ * round-robin.  `stamps` (nullable, 1024 + 8 * 2 * n_pairs int64) receives the per-CTA %globaltimer stamps described
+ * at mmlrec_gemm_grouped_tc_debug. */
+int64_t mmlrec_tc2_record_bytes(void);
+int32_t mmlrec_tc2_num_tiles(const MmlrecGemmTcDesc* desc_host);
+int mmlrec_tc2_encode_problem(const MmlrecGemmTcDesc* desc_host, void* record_host);
+int mmlrec_gemm_grouped_tc2(const void* records, const int32_t* tile_prefix, int32_t n_problems, int32_t total_tiles,
+                            const int32_t* tile_order, const int32_t* pair_start, int32_t n_pairs, int64_t* stamps,
+                            void* stream);
 /* tiles a problem occupies (BLOCK_M=128 x BLOCK_N=128) */
 int32_t mmlrec_tc_num_tiles(int32_t M, int32_t N);
 

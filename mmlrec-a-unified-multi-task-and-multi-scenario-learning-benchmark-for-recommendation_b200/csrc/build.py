@@ -7,7 +7,7 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SOURCES = ["capi.cu", "gather.cu", "emb_update.cu", "gemm_simt.cu", "gemm_tc.cu", "fused_ops.cu", "gate_level.cu", "peer.cu"]
+SOURCES = ["capi.cu", "gather.cu", "emb_update.cu", "gemm_simt.cu", "gemm_tc.cu", "gemm_tc2.cu", "fused_ops.cu", "gate_level.cu", "peer.cu"]
 LIB = os.path.join(HERE, "libmmlrec_b200.so")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--use_fast_math=false"]
@@ -24,7 +24,7 @@ def needs_build() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = SOURCES + ["common.cuh", os.path.join("..", "..", "include", "mmlrec_b200.h")]
+    deps = SOURCES + ["common.cuh", "tc_common.cuh", os.path.join("..", "..", "include", "mmlrec_b200.h")]
     return any(os.path.getmtime(os.path.join(HERE, d)) > t for d in deps)
 
 

@@ -1,24 +1,24 @@
 // K3, bf16 throughput mode: grouped GEMM on the 5th-generation tensor cores (tcgen05), operands
 // staged by TMA into 128B-swizzled shared memory, fp32 accumulators in TMEM, warp-specialised
 // persistent CTAs (1 per SM):
-//   warp 0        TMA producer (one elected lane)
-//   warp 1        TMEM allocator + tcgen05.mma issuer (one elected lane)
-//   warps 2..9    epilogue: tcgen05.ld -> bias (smem) / activation -> smem transpose -> ReLU-mask /
-//                 accumulate -> coalesced fp32 and/or bf16 stores
+//   warp 0        TMA producer (one elected lane), 4-stage mbarrier ring of {A 16 KB, B 16 KB} k-blocks
+//   warp 1        TMEM allocator + tcgen05.mma issuer (one elected lane), 3 accumulator stages
+//   warps 2..9    epilogue: tcgen05.ld (thread = row) -> ReLU-mask / bias / activation in registers ->
+//                 128B-swizzled shared-memory box -> ONE bulk tensor store per box (cp.async.bulk.tensor,
+//                 fp32 and/or bf16; `accumulate` = cp.reduce.async.bulk.tensor .add).  The TMA unit clips
+//                 rows >= M / columns >= N, so ragged tiles take the same path as full ones.
 // D[M,N] = A * B^T.  Each operand is either K-major (row-major [rows,K]) or MN-major ([K,rows]);
 // the MN-major form is what wgrad needs (dW = dZ^T X reads both activations "transposed"), so no
 // transposed copy of any activation is ever written.  The bias gradient of a wgrad problem
 // (row sums of A) is produced by one extra N=16 MMA per k-step against a constant all-ones B tile.
-#include <cuda.h>
-
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace mmlrec {
 
 constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 64;
-constexpr int TC_STAGES = 5;
-constexpr int TC_ACC_STAGES = 2;
-constexpr int TC_ACC_COLS = 256;                 // TMEM columns per accumulator stage (128 main + 16 row-sum, padded)
+constexpr int TC_STAGES = 4;
+constexpr int TC_ACC_STAGES = 3;
+constexpr int TC_ACC_COLS = 160;                 // TMEM columns per accumulator stage (128 main + 16 row-sum, padded to 32)
 constexpr int TC_TMEM_COLS = 512;
 constexpr int TC_EPI_WARPS = 8;                 // two warps per TMEM lane quarter, 64 columns each
 constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;
@@ -26,17 +26,17 @@ constexpr int TC_MAX_PROBLEMS = 96;              // tile table cached in shared 
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 2;    // 16 KB
 constexpr int TC_B_BYTES = TC_BN * TC_BK * 2;    // 16 KB
 constexpr int TC_ONES_BYTES = 16 * 128;          // 16 rows x 128 B of bf16 1.0
-constexpr int TC_STAGE_LD = 34;                  // transpose tile row stride: even (64-bit accesses), conflict-free per half-warp
-constexpr int TC_STAGE_TILE_FLOATS = 32 * TC_STAGE_LD;
-constexpr int TC_SMEM_BYTES = 1024 /*align slack*/ + TC_STAGES * (TC_A_BYTES + TC_B_BYTES) + TC_ONES_BYTES + 256 +
-                              TC_EPI_WARPS * TC_STAGE_TILE_FLOATS * 4 + 2 * TC_BN * 4 +
-                              (2 * TC_MAX_PROBLEMS + 2) * 4;
+constexpr int TC_OUT_BUF_BYTES = 32 * 128;       // one TMA-store box: 32 rows x 128 B (32 fp32 or 64 bf16 columns), 128B-swizzled
+constexpr int TC_OUT_BUFS = 2;                   // per epilogue warp (a store reads one while the next chunk fills the other)
+constexpr int TC_SMEM_BYTES = 1024 /*align slack*/ + TC_STAGES * (TC_A_BYTES + TC_B_BYTES) +
+                              TC_EPI_WARPS * TC_OUT_BUFS * TC_OUT_BUF_BYTES + TC_ONES_BYTES + 256 +
+                              TC_EPI_WARPS * 64 * 4 + (2 * TC_MAX_PROBLEMS + 2) * 4;
 
 struct alignas(128) TcRecord {
   CUtensorMap tmA;
   CUtensorMap tmB;
-  float* C_f32; int64_t ldc_f32;
-  uint16_t* C_bf16; int64_t ldc_bf16;
+  CUtensorMap tmC32;                            // fp32 output, box {32 cols, 32 rows}
+  CUtensorMap tmC16;                            // bf16 output, box {64 cols, 32 rows}
   const float* bias;
   const uint16_t* mask; int64_t ldmask;
   float* rowsum_a;
@@ -44,166 +44,29 @@ struct alignas(128) TcRecord {
   int32_t act, accumulate;
   int32_t a_mn, b_mn;
   int32_t tiles_n;
+  int32_t has_f32, has_bf16;
 };
-
-// ---------------------------------------------------------------------------------------------
-// PTX wrappers
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(bar), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"((uint64_t)tmap), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* tmap) {
-  asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)tmap) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc) : "memory");
-}
-__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
-        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
-        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
-        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-}
-__device__ __forceinline__ void tc_ld1(uint32_t taddr, uint32_t& r) {
-  asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r) : "r"(taddr));
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// UMMA shared-memory descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): 128B swizzle.
-//  K-major : rows of 128 B (64 bf16 of K), 8-row groups 1024 B apart (SBO); LBO unused.
-//  MN-major: K-rows of 128 B (64 bf16 of M/N), 8-row groups 1024 B apart (SBO); the next 64 M/N
-//            elements live in the next TMA box, 8192 B further (LBO).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, bool mn_major) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);                       // start address  [0,14)
-  d |= (uint64_t)(mn_major ? (8192 >> 4) : 1) << 16;             // leading byte offset [16,30)
-  d |= (uint64_t)(1024 >> 4) << 32;                              // stride byte offset  [32,46)
-  d |= (uint64_t)1 << 46;                                        // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;                                        // SWIZZLE_128B
-  return d;
-}
-// instruction descriptor (InstrDescriptor): bf16 x bf16 -> fp32
-__device__ __forceinline__ uint32_t make_idesc(int M, int N, bool a_mn, bool b_mn) {
-  uint32_t d = 0;
-  d |= 1u << 4;                    // c_format = F32
-  d |= 1u << 7;                    // a_format = BF16
-  d |= 1u << 10;                   // b_format = BF16
-  d |= (a_mn ? 1u : 0u) << 15;     // a_major
-  d |= (b_mn ? 1u : 0u) << 16;     // b_major
-  d |= (uint32_t)(N >> 3) << 17;
-  d |= (uint32_t)(M >> 4) << 24;
-  return d;
-}
-
-// Branch-free store of one full 32x32 chunk from the transpose tile (lane = column pair, lanes 0-15 even
-// rows, lanes 16-31 odd rows): bias (+ReLU), optional read-modify-write, 8-byte fp32 / 4-byte bf16x2 stores.
-__device__ __forceinline__ void st_global_f2(float* p, float2 v) {
-  asm volatile("st.global.v2.f32 [%0], {%1, %2};" ::"l"(p), "f"(v.x), "f"(v.y) : "memory");
-}
-__device__ __forceinline__ void st_global_u32(void* p, uint32_t v) {
-  asm volatile("st.global.b32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-__device__ __forceinline__ float2 ld_global_f2(const float* p) {
-  float2 v;
-  asm volatile("ld.global.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(p));
-  return v;
-}
-
-template <bool RELU, bool F32, bool BF16, bool ACC>
-__device__ __forceinline__ void store_chunk_fast(const float2* __restrict__ sread, float* __restrict__ pf, int64_t ldcf,
-                                                 uint16_t* __restrict__ pb, int64_t ldcb, float bx, float by) {
-  // all shared-memory reads first (explicit global-space stores below cannot alias them, but a generic
-  // store would make the compiler serialise LDS -> math -> store per row)
-  float2 x[16];
-#pragma unroll
-  for (int i = 0; i < 16; ++i) x[i] = sread[i * TC_STAGE_LD];
-  float2 old[16];
-  if (F32 && ACC) {
-#pragma unroll
-    for (int i = 0; i < 16; ++i) old[i] = ld_global_f2(pf + (int64_t)(2 * i) * ldcf);
-  }
-#pragma unroll
-  for (int i = 0; i < 16; ++i) {
-    float2 v = x[i];
-    v.x += bx; v.y += by;
-    if (RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); }
-    if (F32 && ACC) { v.x += old[i].x; v.y += old[i].y; }
-    if (F32) st_global_f2(pf + (int64_t)(2 * i) * ldcf, v);
-    if (BF16) st_global_u32(pb + (int64_t)(2 * i) * ldcb, pack_bf16x2(v.x, v.y));
-  }
-}
-
-struct TileCoord { int pi, tm, tn; };
-// prefix / tiles_n live in shared memory (copied once per CTA): the lookup costs no global latency
-__device__ __forceinline__ TileCoord locate_tile(int t, const int32_t* s_prefix, const int32_t* s_tiles_n, int n_problems) {
-  int lo = 0, hi = n_problems - 1;
-  while (lo < hi) {  // last problem whose first tile is <= t
-    int mid = (lo + hi + 1) >> 1;
-    if (s_prefix[mid] <= t) lo = mid; else hi = mid - 1;
-  }
-  const int local = t - s_prefix[lo];
-  const int tiles_n = s_tiles_n[lo];
-  TileCoord c;
-  c.pi = lo; c.tm = local / tiles_n; c.tn = local - c.tm * tiles_n;
-  return c;
-}
 
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_grouped_tc_kernel(const TcRecord* __restrict__ recs, const int32_t* __restrict__ prefix, int n_problems, int total_tiles,
                        const int32_t* __restrict__ tile_order, const int32_t* __restrict__ cta_start,
                        long long* __restrict__ dbg) {
   extern __shared__ unsigned char smem_dyn[];
+  if (dbg != nullptr && threadIdx.x == 0) {   // profiling: kernel entry of this CTA on the global timer
+    unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt)); dbg[1024 + blockIdx.x * 8 + 5] = (long long)gt;
+  }
   // 1024-byte alignment is required by the 128B swizzle atom
   // (offset arithmetic on the shared array itself, so the compiler keeps emitting LDS/STS, not generic LD/ST)
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* sA = smem;
   unsigned char* sB = smem + TC_STAGES * TC_A_BYTES;
-  unsigned char* sOnes = smem + TC_STAGES * (TC_A_BYTES + TC_B_BYTES);
+  unsigned char* sOut = smem + TC_STAGES * (TC_A_BYTES + TC_B_BYTES);                    // [EPI_WARPS][OUT_BUFS][4096], 1024-aligned
+  unsigned char* sOnes = sOut + TC_EPI_WARPS * TC_OUT_BUFS * TC_OUT_BUF_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + TC_ONES_BYTES);
-  // bars: [0,S) full, [S,2S) empty, [2S,2S+2) tmem_full, [2S+2,2S+4) tmem_empty, then tmem base slot
+  // bars: [0,S) full, [S,2S) empty, [2S,2S+ACC) tmem_full, [2S+ACC,2S+2ACC) tmem_empty, then tmem base slot
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * TC_STAGES + 2 * TC_ACC_STAGES);
-  float* stage_s = reinterpret_cast<float*>(sOnes + TC_ONES_BYTES + 256);           // [EPI_WARPS][32][33]
-  float* bias_s = stage_s + TC_EPI_WARPS * TC_STAGE_TILE_FLOATS;                     // [2][128]
-  int32_t* s_prefix = reinterpret_cast<int32_t*>(bias_s + 2 * TC_BN);                // [MAX_PROBLEMS + 1]
+  float* bias_s = reinterpret_cast<float*>(sOnes + TC_ONES_BYTES + 256);             // [EPI_WARPS][64]
+  int32_t* s_prefix = reinterpret_cast<int32_t*>(bias_s + TC_EPI_WARPS * 64);        // [MAX_PROBLEMS + 1]
   int32_t* s_tiles_n = s_prefix + TC_MAX_PROBLEMS + 1;                               // [MAX_PROBLEMS]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -219,7 +82,7 @@ gemm_grouped_tc_kernel(const TcRecord* __restrict__ recs, const int32_t* __restr
     for (int s = 0; s < TC_ACC_STAGES; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // ones tile (generic writes) -> async proxy
+  fence_async_smem();  // ones tile (generic writes) -> async proxy
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(TC_TMEM_COLS));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
@@ -236,6 +99,11 @@ gemm_grouped_tc_kernel(const TcRecord* __restrict__ recs, const int32_t* __restr
   // optional per-tile clock stamps of CTA 0 (debug timeline): dbg[tile_iter * 16 + slot]
   const bool stamp = dbg != nullptr && blockIdx.x == 0;
 #define TC_STAMP(iter, slot) do { if (stamp && (iter) < 64) dbg[(iter) * 16 + (slot)] = clock64(); } while (0)
+  // ... and of every CTA on the global timer (ns): dbg[1024 + cta * 8 + {0 setup done, 1 producer done, 2 MMA issuer
+  // done, 3 epilogue warp 0 done, 4 number of tiles, 5 kernel entry, 6 TMEM released}]
+#define TC_CTA_STAMP(slot) do { if (dbg != nullptr) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); \
+                                  dbg[1024 + blockIdx.x * 8 + (slot)] = (long long)gt_; } } while (0)
+  if (threadIdx.x == 0) { TC_CTA_STAMP(0); if (dbg != nullptr) dbg[1024 + blockIdx.x * 8 + 4] = (sched_end - sched_begin + sched_step - 1) / sched_step; }
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -247,6 +115,7 @@ gemm_grouped_tc_kernel(const TcRecord* __restrict__ recs, const int32_t* __restr
         TC_STAMP(pit, 0);
         const TileCoord tc = locate_tile(t, s_prefix, s_tiles_n, n_problems);
         const TcRecord* R = recs + tc.pi;
+        if (pit == 0) { tma_prefetch_desc(&R->tmA); tma_prefetch_desc(&R->tmB); }
         const int K = R->K, a_mn = R->a_mn, b_mn = R->b_mn;
         const int m0 = tc.tm * TC_BM, n0 = tc.tn * TC_BN;
         const int num_kb = (K + TC_BK - 1) / TC_BK;
@@ -273,7 +142,15 @@ gemm_grouped_tc_kernel(const TcRecord* __restrict__ recs, const int32_t* __restr
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
         }
         TC_STAMP(pit, 3);
+        // descriptors of the next tile's problem (a descriptor fetch is otherwise exposed in front of its first load)
+        const int tn_i = ti + sched_step;
+        if (tn_i < sched_end) {
+          const int t2 = tile_order ? __ldg(tile_order + tn_i) : tn_i;
+          const TileCoord tc2 = locate_tile(t2, s_prefix, s_tiles_n, n_problems);
+          if (tc2.pi != tc.pi) { tma_prefetch_desc(&recs[tc2.pi].tmA); tma_prefetch_desc(&recs[tc2.pi].tmB); }
+        }
       }
+      TC_CTA_STAMP(1);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
@@ -305,11 +182,15 @@ gemm_grouped_tc_kernel(const TcRecord* __restrict__ recs, const int32_t* __restr
           const uint64_t a_desc = make_smem_desc(a_addr, a_mn), b_desc = make_smem_desc(b_addr, b_mn);
           // advancing K by 16 elements: 32 B inside the swizzle row (K-major) or two 8-row groups (MN-major)
           const uint64_t a_step = a_mn ? (2048 >> 4) : (32 >> 4), b_step = b_mn ? (2048 >> 4) : (32 >> 4);
+          // 16-wide k-slices that lie entirely beyond K hold only TMA zero fill: skip their MMAs
+          const int k_left = K - kb * TC_BK;
 #pragma unroll
           for (int k = 0; k < TC_BK / 16; ++k) {
-            const uint32_t accumulate = (kb | k) != 0 ? 1u : 0u;
-            tc_mma(d_tmem, a_desc + a_step * k, b_desc + b_step * k, idesc, accumulate);
-            if (rowsum) tc_mma(d_tmem + TC_BN, a_desc + a_step * k, ones_desc + 2 * k, idesc_ones, accumulate);
+            if (k * 16 < k_left) {
+              const uint32_t accumulate = (kb | k) != 0 ? 1u : 0u;
+              tc_mma(d_tmem, a_desc + a_step * k, b_desc + b_step * k, idesc, accumulate);
+              if (rowsum) tc_mma(d_tmem + TC_BN, a_desc + a_step * k, ones_desc + 2 * k, idesc_ones, accumulate);
+            }
           }
           tc_commit(empty_bar + 8 * stage);   // frees the smem slot when these MMAs retire
           if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
@@ -318,49 +199,61 @@ gemm_grouped_tc_kernel(const TcRecord* __restrict__ recs, const int32_t* __restr
         TC_STAMP(mit, 7);
         if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
+      TC_CTA_STAMP(2);
     }
   } else {
     // ===================== epilogue (warps 2..9) =====================
-    // warp -> TMEM lane quarter q (rows 32q..32q+31 of the tile) and column half (64 columns).
-    // Per 32-column chunk: tcgen05.ld (thread = row) -> + bias (smem) -> activation -> transpose through a
-    // padded smem tile -> (thread = column) ReLU-mask / accumulate / fp32 + bf16 stores, all coalesced.
+    // warp -> TMEM lane quarter q (rows 32q..32q+31 of the tile) and column half (64 columns = two 32-column
+    // chunks).  Both chunks are pulled out of TMEM at once (thread = row), after which the accumulator stage is
+    // handed back to the MMA warp; mask / bias / activation run on registers; each finished box (32 rows x 128 B)
+    // is written to a 128B-swizzled staging buffer with conflict-free 16-byte stores and leaves with one bulk
+    // tensor store issued by lane 0.
     const int q = warp & 3;
     const int ew = warp - 2;                   // 0..7
     const int half = ew >> 2;                  // 0: columns [0,64)  1: columns [64,128)
-    float* my_stage = stage_s + ew * TC_STAGE_TILE_FLOATS;
+    float* bias_w = bias_s + ew * 64;
+    const uint32_t out_base = smem_u32(sOut + ew * TC_OUT_BUFS * TC_OUT_BUF_BYTES);
+    const uint32_t row_off = (uint32_t)lane * 128u;
+    const uint32_t sw = (uint32_t)(lane & 7);
     int acc = 0; uint32_t acc_phase = 0;
     int it = 0;
+    uint32_t buf_i = 0;                        // staging buffers are used round-robin
     for (int ti = sched_begin; ti < sched_end; ti += sched_step, ++it) {
       const int t = tile_order ? __ldg(tile_order + ti) : ti;
       const TileCoord tc = locate_tile(t, s_prefix, s_tiles_n, n_problems);
       const TcRecord* R = recs + tc.pi;
       const int M = R->M, N = R->N;
       const int m_base = tc.tm * TC_BM + q * 32;
-      const int n0 = tc.tn * TC_BN;
-      float* const cf = R->C_f32; const int64_t ldcf = R->ldc_f32;
-      uint16_t* const cb = R->C_bf16; const int64_t ldcb = R->ldc_bf16;
+      const int n0 = tc.tn * TC_BN + half * 64;
+      const bool has_f32 = R->has_f32 != 0, has_bf16 = R->has_bf16 != 0;
       const float* const bias = R->bias;
       const uint16_t* const mask = R->mask; const int64_t ldmask = R->ldmask;
       const int act = R->act, accumulate = R->accumulate;
-      float* const rowsum_out = (tc.tn == 0) ? R->rowsum_a : nullptr;
+      float* const rowsum_out = (tc.tn == 0 && half == 0) ? R->rowsum_a : nullptr;
       const bool estamp = stamp && ew == 0 && lane == 0;
       if (estamp && it < 64) dbg[it * 16 + 8] = clock64();
       const int my_m = m_base + lane;
       const bool row_ok = my_m < M;
-      const int rows_valid = min(32, M - m_base);              // warp-uniform (may be <= 0)
-      // Operands the epilogue needs from global memory are fetched NOW (128-bit loads, all in flight
-      // together) so that their latency hides behind this tile's MMAs:
-      //  * the ReLU mask, in row layout (thread = row), 64 B per thread per chunk
-      //  * the bias of "my" two columns per chunk (column layout is used for bias + activation)
+      const bool rows_any = m_base < M;                        // warp-uniform
+      const bool c_ok[2] = {rows_any && n0 < N, rows_any && n0 + 32 < N};   // warp-uniform
+      if (lane == 0) {
+        if (has_f32) tma_prefetch_desc(&R->tmC32);
+        if (has_bf16) tma_prefetch_desc(&R->tmC16);
+      }
+      // Operands the epilogue needs from global memory are fetched NOW so that their latency hides behind this
+      // tile's MMAs: the bias of the warp's 64 columns (-> shared-memory slot, read back as broadcasts) and the
+      // ReLU mask in row layout (thread = row, 64 B per chunk)
+      __syncwarp();                                            // the previous tile's reads of the slot are done
+      {
+        const int c_lo = n0 + lane, c_hi = n0 + 32 + lane;
+        bias_w[lane] = (bias != nullptr && c_lo < N) ? __ldg(bias + c_lo) : 0.f;
+        bias_w[32 + lane] = (bias != nullptr && c_hi < N) ? __ldg(bias + c_hi) : 0.f;
+      }
       uint4 mk[2][4];
-      float2 bcol[2];
+      if (mask != nullptr) {
 #pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int nc = n0 + half * 64 + c * 32;
-        const int col = nc + 2 * (lane & 15);
-        bcol[c].x = (bias != nullptr && col < N) ? __ldg(bias + col) : 0.f;
-        bcol[c].y = (bias != nullptr && col + 1 < N) ? __ldg(bias + col + 1) : 0.f;
-        if (mask != nullptr) {
+        for (int c = 0; c < 2; ++c) {
+          const int nc = n0 + c * 32;
 #pragma unroll
           for (int v4 = 0; v4 < 4; ++v4) {
             mk[c][v4] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
@@ -375,147 +268,96 @@ gemm_grouped_tc_kernel(const TcRecord* __restrict__ recs, const int32_t* __restr
           }
         }
       }
+      __syncwarp();                                            // bias slot visible to the whole warp
       if (estamp && it < 64) dbg[it * 16 + 9] = clock64();
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
       if (estamp && it < 64) dbg[it * 16 + 10] = clock64();
       const uint32_t t_row = tmem_base + acc * TC_ACC_COLS + ((uint32_t)(q * 32) << 16);
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        const int cc = half * 64 + c * 32;     // column offset inside the tile
-        const int nc = n0 + cc;
-        if (nc >= N || rows_valid <= 0) break; // warp-uniform
-        uint32_t r[32];
-        tc_ld32(t_row + cc, r);
-        tc_wait_ld();
-        if (estamp && it < 64 && c == 0) dbg[it * 16 + 12] = clock64();
-        // phase 1 (thread = row): ReLU mask on the raw accumulator, then 16 x STS.64 into the tile
-        if (mask != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) {       // keep where the bf16 mask value is > 0
-            const uint4 w4 = mk[c][j >> 3];
-            const uint32_t word = ((j >> 1) & 3) == 0 ? w4.x : ((j >> 1) & 3) == 1 ? w4.y : ((j >> 1) & 3) == 2 ? w4.z : w4.w;
-            const uint32_t mb = (j & 1) ? (word >> 16) : (word & 0xFFFFu);
-            if (!((mb & 0x8000u) == 0 && (mb & 0x7FFFu) != 0)) r[j] = 0u;
-          }
-        }
-        float2* srow = reinterpret_cast<float2*>(my_stage + lane * TC_STAGE_LD);
-#pragma unroll
-        for (int j2 = 0; j2 < 16; ++j2) srow[j2] = make_float2(__uint_as_float(r[2 * j2]), __uint_as_float(r[2 * j2 + 1]));
-        __syncwarp();
-        if (estamp && it < 64 && c == 0) dbg[it * 16 + 13] = clock64();
-        // phase 2 (thread = column pair; lanes 0-15 row 2i, lanes 16-31 row 2i+1): bias + activation,
-        // read-modify-write, coalesced 8-byte fp32 / 4-byte bf16x2 stores
-        const int sub = lane >> 4;
-        const int col = nc + 2 * (lane & 15);
-        const float2* sread = reinterpret_cast<const float2*>(my_stage + sub * TC_STAGE_LD + 2 * (lane & 15));
-        float* pf = cf ? cf + (int64_t)(m_base + sub) * ldcf + col : nullptr;
-        uint16_t* pb = cb ? cb + (int64_t)(m_base + sub) * ldcb + col : nullptr;
-        const float bx = bcol[c].x, by = bcol[c].y;
-        const bool fast = rows_valid == 32 && nc + 32 <= N && (act == MMLREC_ACT_NONE || act == MMLREC_ACT_RELU) &&
-                          (cf == nullptr || (ldcf & 1) == 0) && (cb == nullptr || (ldcb & 1) == 0);   // warp-uniform
-        if (fast) {
-          const int kind = (act == MMLREC_ACT_RELU ? 8 : 0) | (cf ? 4 : 0) | (cb ? 2 : 0) | ((cf && accumulate) ? 1 : 0);
-          switch (kind) {
-            case 4:  store_chunk_fast<false, true, false, false>(sread, pf, ldcf, pb, ldcb, bx, by); break;
-            case 5:  store_chunk_fast<false, true, false, true>(sread, pf, ldcf, pb, ldcb, bx, by); break;
-            case 2:  store_chunk_fast<false, false, true, false>(sread, pf, ldcf, pb, ldcb, bx, by); break;
-            case 6:  store_chunk_fast<false, true, true, false>(sread, pf, ldcf, pb, ldcb, bx, by); break;
-            case 7:  store_chunk_fast<false, true, true, true>(sread, pf, ldcf, pb, ldcb, bx, by); break;
-            case 12: store_chunk_fast<true, true, false, false>(sread, pf, ldcf, pb, ldcb, bx, by); break;
-            case 10: store_chunk_fast<true, false, true, false>(sread, pf, ldcf, pb, ldcb, bx, by); break;
-            case 14: store_chunk_fast<true, true, true, false>(sread, pf, ldcf, pb, ldcb, bx, by); break;
-            case 13: store_chunk_fast<true, true, false, true>(sread, pf, ldcf, pb, ldcb, bx, by); break;
-            case 15: store_chunk_fast<true, true, true, true>(sread, pf, ldcf, pb, ldcb, bx, by); break;
-            default: break;  // unreachable: a problem always has at least one output
-          }
-        } else {
-          const bool c0 = col < N, c1 = col + 1 < N;
-          const bool vec_f = c1 && ((ldcf & 1) == 0), vec_b = c1 && ((ldcb & 1) == 0);
-#pragma unroll 1
-          for (int i = 0; i < 16; ++i) {
-            const int rr = 2 * i + sub;
-            float2 x = sread[i * TC_STAGE_LD];
-            x.x += bx; x.y += by;
-            if (act == MMLREC_ACT_RELU) { x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); }
-            else if (act != MMLREC_ACT_NONE) { x.x = apply_act(x.x, act); x.y = apply_act(x.y, act); }
-            if (rr < rows_valid && c0) {
-              if (pf) {
-                if (vec_f) {
-                  float2* d = reinterpret_cast<float2*>(pf);
-                  if (accumulate) { const float2 o = *d; x.x += o.x; x.y += o.y; }
-                  *d = x;
-                } else {
-                  if (accumulate) { x.x += pf[0]; if (c1) x.y += pf[1]; }
-                  pf[0] = x.x;
-                  if (c1) pf[1] = x.y;
-                }
-              }
-              if (pb) {
-                if (vec_b) *reinterpret_cast<uint32_t*>(pb) = pack_bf16x2(x.x, x.y);
-                else { pb[0] = float_to_bf16_bits(x.x); if (c1) pb[1] = float_to_bf16_bits(x.y); }
-              }
-            }
-            if (pf) pf += 2 * ldcf;
-            if (pb) pb += 2 * ldcb;
-          }
-        }
-        __syncwarp();
-        if (estamp && it < 64 && c == 0) dbg[it * 16 + 14] = clock64();
-      }
-      if (estamp && it < 64) dbg[it * 16 + 11] = clock64();
-      if (rowsum_out != nullptr && half == 0) {
-        uint32_t rs;
-        tc_ld1(t_row + TC_BN, rs);
-        tc_wait_ld();
-        if (m_base + lane < M) rowsum_out[m_base + lane] = __uint_as_float(rs);
-      }
+      uint32_t r0[32], r1[32];
+      uint32_t rs = 0;
+      if (c_ok[0]) tc_ld32(t_row + half * 64, r0);
+      if (c_ok[1]) tc_ld32(t_row + half * 64 + 32, r1);
+      if (rowsum_out != nullptr) tc_ld1(t_row + TC_BN, rs);
+      tc_wait_ld();
+      // the accumulator stage is free as soon as this warp's values sit in registers
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(tempty_bar + 8 * acc);
       if (++acc == TC_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      if (estamp && it < 64) dbg[it * 16 + 12] = clock64();
+      if (rowsum_out != nullptr && row_ok) rowsum_out[my_m] = __uint_as_float(rs);
+      uint32_t packed[2][16];
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        if (!c_ok[c]) continue;                                // warp-uniform
+        uint32_t (&r)[32] = c == 0 ? r0 : r1;
+        epilogue_math(r, mk[c], mask != nullptr, smem_u32(bias_w) + c * 128, act);
+        if (estamp && it < 64 && c == 0) dbg[it * 16 + 13] = clock64();
+        if (has_bf16) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) packed[c][j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+        }
+        if (has_f32) {
+          // staging buffer: wait until the store issued two boxes ago has finished reading it
+          if (lane == 0) bulk_wait_read<TC_OUT_BUFS - 1>();
+          __syncwarp();
+          if (estamp && it < 64 && c == 0) dbg[it * 16 + 14] = clock64();
+          const uint32_t buf = out_base + (buf_i & (TC_OUT_BUFS - 1)) * TC_OUT_BUF_BYTES;
+          ++buf_i;
+#pragma unroll
+          for (int c16 = 0; c16 < 8; ++c16)                    // 16-byte chunk c16 of the row lands at chunk (c16 ^ row%8)
+            st_shared_v4(buf + row_off + (((uint32_t)c16 ^ sw) << 4), r[4 * c16], r[4 * c16 + 1], r[4 * c16 + 2], r[4 * c16 + 3]);
+          fence_async_smem();
+          __syncwarp();
+          if (estamp && it < 64 && c == 0) dbg[it * 16 + 15] = clock64();
+          if (lane == 0) {
+            if (accumulate) tma_reduce_add_2d(&R->tmC32, buf, n0 + c * 32, m_base);
+            else tma_store_2d(&R->tmC32, buf, n0 + c * 32, m_base);
+            bulk_commit();
+          }
+        }
+      }
+      if (has_bf16 && c_ok[0]) {
+        if (lane == 0) bulk_wait_read<TC_OUT_BUFS - 1>();
+        __syncwarp();
+        const uint32_t buf = out_base + (buf_i & (TC_OUT_BUFS - 1)) * TC_OUT_BUF_BYTES;
+        ++buf_i;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (!c_ok[c]) continue;                              // columns >= N are clipped by the store
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            st_shared_v4(buf + row_off + (((uint32_t)(4 * c + i) ^ sw) << 4), packed[c][4 * i], packed[c][4 * i + 1],
+                         packed[c][4 * i + 2], packed[c][4 * i + 3]);
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&R->tmC16, buf, n0, m_base);
+          bulk_commit();
+        }
+      }
+      if (estamp && it < 64) dbg[it * 16 + 11] = clock64();
     }
+    if (lane == 0) bulk_wait_all();            // the staging buffers must outlive the last stores
+    if (ew == 0 && lane == 0) TC_CTA_STAMP(3);
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS));
+    if (lane == 0) TC_CTA_STAMP(6);
   }
 }
 
 // ---------------------------------------------------------------------------------------------
-// host side: tensor-map encoding through the driver entry point (no link-time libcuda dependency)
+// host side
 // ---------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (!fn) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
-    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
-  }
-  return fn;
-}
-
-// operand stored as row-major [outer, inner] with row stride ld (elements)
 static int encode_operand(CUtensorMap* tm, const uint16_t* base, int64_t ld, int64_t inner, int64_t outer,
                           int box_inner, int box_outer) {
-  EncodeTiledFn fn = get_encode_fn();
-  if (!fn) { set_error("cuTensorMapEncodeTiled entry point unavailable (no driver?)"); return -2; }
-  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return -3; }
-  return 0;
+  return tc_encode_map(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, ld, inner, outer, box_inner, box_outer);
 }
 
 }  // namespace mmlrec
@@ -534,6 +376,7 @@ extern "C" int mmlrec_tc_encode_problem(const MmlrecGemmTcDesc* d, void* record_
   MMLREC_CHECK_ARG(d->C_bf16 == nullptr || ((d->ldc_bf16 & 7) == 0 && ((uintptr_t)d->C_bf16 & 15) == 0), "C_bf16 alignment");
   MMLREC_CHECK_ARG(d->mask == nullptr || ((d->ldmask & 7) == 0 && ((uintptr_t)d->mask & 15) == 0), "mask alignment");
   MMLREC_CHECK_ARG(d->C_f32 || d->C_bf16, "no output");
+  MMLREC_CHECK_ARG(!(d->accumulate && d->C_bf16), "accumulate applies to an fp32-only output (the sum is formed in memory)");
   TcRecord rec;
   memset(&rec, 0, sizeof(rec));
   int rc;
@@ -543,22 +386,20 @@ extern "C" int mmlrec_tc_encode_problem(const MmlrecGemmTcDesc* d, void* record_
   if (!d->b_mn_major) rc = encode_operand(&rec.tmB, d->B, d->ldb, d->K, d->N, TC_BK, TC_BN);
   else                rc = encode_operand(&rec.tmB, d->B, d->ldb, d->N, d->K, 64, TC_BK);
   if (rc) return rc;
-  rec.C_f32 = d->C_f32; rec.ldc_f32 = d->ldc_f32; rec.C_bf16 = d->C_bf16; rec.ldc_bf16 = d->ldc_bf16;
+  if (d->C_f32) {
+    rc = tc_encode_map(&rec.tmC32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d->C_f32, d->ldc_f32, d->N, d->M, 32, 32);
+    if (rc) return rc;
+  }
+  if (d->C_bf16) {
+    rc = tc_encode_map(&rec.tmC16, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d->C_bf16, d->ldc_bf16, d->N, d->M, 64, 32);
+    if (rc) return rc;
+  }
+  rec.has_f32 = d->C_f32 != nullptr; rec.has_bf16 = d->C_bf16 != nullptr;
   rec.bias = d->bias; rec.mask = d->mask; rec.ldmask = d->ldmask; rec.rowsum_a = d->colsum;
   rec.M = d->M; rec.N = d->N; rec.K = d->K; rec.act = d->act; rec.accumulate = d->accumulate;
   rec.a_mn = d->a_mn_major; rec.b_mn = d->b_mn_major; rec.tiles_n = cdiv(d->N, TC_BN);
   memcpy(record_host, &rec, sizeof(rec));
   return 0;
-}
-
-static int tc_sm_count() {
-  static int sm_count = 0;
-  if (!sm_count) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev);
-  }
-  return sm_count;
 }
 
 static int launch_tc(const void* records, const int32_t* tile_prefix, int32_t n_problems, int32_t total_tiles,
@@ -595,7 +436,8 @@ extern "C" int mmlrec_gemm_grouped_tc_scheduled(const void* records, const int32
 }
 
 extern "C" int mmlrec_gemm_grouped_tc_debug(const void* records, const int32_t* tile_prefix, int32_t n_problems,
-                                            int32_t total_tiles, int64_t* stamps, void* stream) {
-  return launch_tc(records, tile_prefix, n_problems, total_tiles, nullptr, nullptr, 0,
+                                            int32_t total_tiles, const int32_t* tile_order, const int32_t* cta_start,
+                                            int32_t n_ctas, int64_t* stamps, void* stream) {
+  return launch_tc(records, tile_prefix, n_problems, total_tiles, tile_order, cta_start, n_ctas,
                    reinterpret_cast<long long*>(stamps), stream);
 }

@@ -1,0 +1,458 @@
+// K3, bf16 throughput mode, CTA-pair version: the same grouped GEMM as gemm_tc.cu, executed by clusters of two
+// CTAs (two SMs of one TPC) with `tcgen05.mma.cta_group::2`.  A pair computes one 256 x BN tile (BN = 256 or 128):
+// each CTA stages ITS 128 rows of A and ITS half of the BN rows of B (TMA, 128B swizzle), the leader CTA issues
+// one MMA that reads both CTAs' shared memory, and each CTA's TMEM receives the accumulator of its own 128 rows.
+// Per 128 x 128 of output a CTA therefore pulls half the operand bytes of the one-CTA kernel (16 KB of A per
+// 256 columns instead of per 128, B split between the two) -- these problems are bound by L2 -> SM operand
+// traffic (K <= 256 forward, batch-contraction backward), not by the tensor pipe, so that is what counts.
+//   warp 0        TMA producer (both CTAs; completion bytes of both land on the LEADER's full barrier)
+//   warp 1        TMEM allocator (both CTAs, cta_group::2) + MMA issuer (leader only; commits are multicast to
+//                 the barriers of both CTAs)
+//   warps 2..9    epilogue of the CTA's own 128 x BN accumulator: tcgen05.ld -> mask / bias / activation ->
+//                 128B-swizzled staging box -> bulk tensor store (or .add reduction); the accumulator stage is
+//                 released by an mbarrier arrive on the leader (remote for the peer CTA)
+// D[M,N] = A * B^T, operands K-major or MN-major, bias gradient by an extra N=16 MMA against an all-ones tile,
+// exactly as in gemm_tc.cu; split-K is expressed by the caller as several problems over K slices.
+#include "tc_common.cuh"
+
+namespace mmlrec {
+
+constexpr int T2_BM = 128;                       // rows per CTA; a pair covers 256
+constexpr int T2_BK = 64;
+constexpr int T2_STAGES = 4;
+constexpr int T2_ACC_STAGES = 2;
+constexpr int T2_ACC_COLS = 256;                 // TMEM columns per accumulator stage
+constexpr int T2_TMEM_COLS = 512;
+constexpr int T2_EPI_WARPS = 8;
+constexpr int T2_THREADS = 64 + 32 * T2_EPI_WARPS;
+constexpr int T2_MAX_PROBLEMS = 96;
+constexpr int T2_A_BYTES = T2_BM * T2_BK * 2;    // 16 KB: this CTA's 128 rows of A
+constexpr int T2_B_BYTES = 128 * T2_BK * 2;      // 16 KB: this CTA's half of B (BN/2 <= 128 rows)
+constexpr int T2_ONES_BYTES = 16 * 128;
+constexpr int T2_OUT_BUF_BYTES = 32 * 128;
+constexpr int T2_OUT_BUFS = 2;
+constexpr int T2_SMEM_BYTES = 1024 + T2_STAGES * (T2_A_BYTES + T2_B_BYTES) + T2_EPI_WARPS * T2_OUT_BUFS * T2_OUT_BUF_BYTES +
+                              T2_ONES_BYTES + 256 + T2_EPI_WARPS * 128 * 4 + (2 * T2_MAX_PROBLEMS + 2) * 4;
+
+struct alignas(128) Tc2Record {
+  CUtensorMap tmA;                              // K-major: box {64 k, 128 rows}; MN-major: box {64 m, 64 k}
+  CUtensorMap tmB;                              // K-major: box {64 k, BN/2 rows}; MN-major: box {64 n, 64 k}
+  CUtensorMap tmC32;                            // fp32 output, box {32 cols, 32 rows}
+  CUtensorMap tmC16;                            // bf16 output, box {64 cols, 32 rows}
+  const float* bias;
+  const uint16_t* mask; int64_t ldmask;
+  float* rowsum_a;
+  int32_t M, N, K;
+  int32_t act, accumulate;
+  int32_t a_mn, b_mn;
+  int32_t tiles_n;
+  int32_t has_f32, has_bf16;
+  int32_t bn;                                   // 256 or 128
+  int32_t rowsum_col;                           // TMEM column (inside the stage) that receives the row sums
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load of this CTA's box whose completion bytes are credited to the LEADER CTA's mbarrier
+// (cute SM100_TMA_2SM_LOAD_2D: the barrier address with the peer bit cleared names CTA 0 of the pair)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tmap, uint32_t bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"((uint64_t)tmap), "r"(bar & 0xFEFFFFFFu), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tc2_mma(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t acc) {
+  const uint32_t z = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc), "r"(z) : "memory");
+}
+// completion of all MMAs issued so far -> one arrive on the barrier at this address in BOTH CTAs of the pair
+__device__ __forceinline__ void tc2_commit(uint32_t bar) {
+  const uint16_t mask = 3;
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"(mask) : "memory");
+}
+// arrive on the barrier at local address `bar` of CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 remAddr32;\n"
+      "mapa.shared::cluster.u32 remAddr32, %0, %1;\n"
+      "mbarrier.arrive.shared::cluster.b64 _, [remAddr32];\n"
+      "}\n" ::"r"(bar), "r"(cta) : "memory");
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
+gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __restrict__ prefix, int n_problems, int total_tiles,
+                        const int32_t* __restrict__ tile_order, const int32_t* __restrict__ pair_start,
+                        long long* __restrict__ dbg) {
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+  unsigned char* sA = smem;
+  unsigned char* sB = smem + T2_STAGES * T2_A_BYTES;
+  unsigned char* sOut = smem + T2_STAGES * (T2_A_BYTES + T2_B_BYTES);
+  unsigned char* sOnes = sOut + T2_EPI_WARPS * T2_OUT_BUFS * T2_OUT_BUF_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + T2_ONES_BYTES);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * T2_STAGES + 2 * T2_ACC_STAGES);
+  float* bias_s = reinterpret_cast<float*>(sOnes + T2_ONES_BYTES + 256);             // [EPI_WARPS][128]
+  int32_t* s_prefix = reinterpret_cast<int32_t*>(bias_s + T2_EPI_WARPS * 128);
+  int32_t* s_tiles_n = s_prefix + T2_MAX_PROBLEMS + 1;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();               // 0 = leader (issues the MMAs)
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const uint32_t full_bar = smem_u32(bars), empty_bar = smem_u32(bars + T2_STAGES);
+  const uint32_t tfull_bar = smem_u32(bars + 2 * T2_STAGES), tempty_bar = smem_u32(bars + 2 * T2_STAGES + T2_ACC_STAGES);
+
+  for (int i = threadIdx.x; i < T2_ONES_BYTES / 4; i += T2_THREADS) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
+  for (int i = threadIdx.x; i <= n_problems; i += T2_THREADS) s_prefix[i] = prefix[i];
+  for (int i = threadIdx.x; i < n_problems; i += T2_THREADS) s_tiles_n[i] = recs[i].tiles_n;
+  if (threadIdx.x == 0) {
+    // full: one arrive (the leader's expect_tx) + the bytes of both CTAs; empty / tmem_full: one multicast commit;
+    // tmem_empty (used on the leader only): every epilogue warp of both CTAs
+    for (int s = 0; s < T2_STAGES; ++s) { mbar_init(full_bar + 8 * s, 1); mbar_init(empty_bar + 8 * s, 1); }
+    for (int s = 0; s < T2_ACC_STAGES; ++s) { mbar_init(tfull_bar + 8 * s, 1); mbar_init(tempty_bar + 8 * s, 2 * T2_EPI_WARPS); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  fence_async_smem();
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "n"(T2_TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  __syncwarp();
+  cluster_sync_all();                                     // the peer's barriers / ones tile / TMEM exist before anyone uses them
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const int sched_begin = tile_order ? pair_start[pair] : pair;
+  const int sched_end = tile_order ? pair_start[pair + 1] : total_tiles;
+  const int sched_step = tile_order ? 1 : n_pairs;
+#define T2_CTA_STAMP(slot) do { if (dbg != nullptr) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); \
+                                  dbg[1024 + blockIdx.x * 8 + (slot)] = (long long)gt_; } } while (0)
+  if (threadIdx.x == 0) { T2_CTA_STAMP(0); if (dbg != nullptr) dbg[1024 + blockIdx.x * 8 + 4] = (sched_end - sched_begin + sched_step - 1) / sched_step; }
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs) =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int ti = sched_begin; ti < sched_end; ti += sched_step) {
+        const int t = tile_order ? __ldg(tile_order + ti) : ti;
+        const TileCoord tc = locate_tile(t, s_prefix, s_tiles_n, n_problems);
+        const Tc2Record* R = recs + tc.pi;
+        const int K = R->K, a_mn = R->a_mn, b_mn = R->b_mn, bn = R->bn;
+        const int half_n = bn >> 1;
+        const int m0 = tc.tm * 256 + (int)rank * T2_BM;             // this CTA's rows of A
+        const int n0 = tc.tn * bn + (int)rank * half_n;             // this CTA's rows of B
+        const uint32_t stage_bytes = 2u * (uint32_t)(T2_A_BYTES + half_n * 128);   // both CTAs' boxes
+        const int num_kb = (K + T2_BK - 1) / T2_BK;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          const uint32_t fb = full_bar + 8 * stage;
+          if (rank == 0) mbar_expect_tx(fb, stage_bytes);
+          const uint32_t a_dst = smem_u32(sA + stage * T2_A_BYTES), b_dst = smem_u32(sB + stage * T2_B_BYTES);
+          const int k0 = kb * T2_BK;
+          if (!a_mn) {
+            tma_load_2d_pair(a_dst, &R->tmA, fb, k0, m0);
+          } else {
+            tma_load_2d_pair(a_dst, &R->tmA, fb, m0, k0);
+            tma_load_2d_pair(a_dst + 8192, &R->tmA, fb, m0 + 64, k0);
+          }
+          if (!b_mn) {
+            tma_load_2d_pair(b_dst, &R->tmB, fb, k0, n0);           // box {64 k, BN/2 rows}
+          } else {
+            tma_load_2d_pair(b_dst, &R->tmB, fb, n0, k0);
+            if (half_n == 128) tma_load_2d_pair(b_dst + 8192, &R->tmB, fb, n0 + 64, k0);
+          }
+          if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        const int tn_i = ti + sched_step;
+        if (tn_i < sched_end) {
+          const int t2 = tile_order ? __ldg(tile_order + tn_i) : tn_i;
+          const TileCoord tc2 = locate_tile(t2, s_prefix, s_tiles_n, n_problems);
+          if (tc2.pi != tc.pi) { tma_prefetch_desc(&recs[tc2.pi].tmA); tma_prefetch_desc(&recs[tc2.pi].tmB); }
+        }
+      }
+      T2_CTA_STAMP(1);
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (lane == 0 && rank == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      const uint64_t ones_desc = make_smem_desc(smem_u32(sOnes), false);
+      for (int ti = sched_begin; ti < sched_end; ti += sched_step) {
+        const int t = tile_order ? __ldg(tile_order + ti) : ti;
+        const TileCoord tc = locate_tile(t, s_prefix, s_tiles_n, n_problems);
+        const Tc2Record* R = recs + tc.pi;
+        const int K = R->K, bn = R->bn;
+        const bool a_mn = R->a_mn != 0, b_mn = R->b_mn != 0;
+        const bool rowsum = (R->rowsum_a != nullptr) && tc.tn == 0;
+        const int rowsum_col = R->rowsum_col;
+        const bool rowsum_shared = rowsum_col < bn;      // the row sums live in unused columns of the main accumulator
+        const uint32_t idesc = make_idesc(256, bn, a_mn, b_mn);
+        const uint32_t idesc_ones = make_idesc(256, 16, a_mn, false);
+        const int num_kb = (K + T2_BK - 1) / T2_BK;
+        mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * T2_ACC_COLS;
+        for (int kb = 0; kb < num_kb; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(sA + stage * T2_A_BYTES), b_addr = smem_u32(sB + stage * T2_B_BYTES);
+          const uint64_t a_desc = make_smem_desc(a_addr, a_mn), b_desc = make_smem_desc(b_addr, b_mn);
+          const uint64_t a_step = a_mn ? (2048 >> 4) : (32 >> 4), b_step = b_mn ? (2048 >> 4) : (32 >> 4);
+          const int k_left = K - kb * T2_BK;
+#pragma unroll
+          for (int k = 0; k < T2_BK / 16; ++k) {
+            if (k * 16 < k_left) {
+              const uint32_t accumulate = (kb | k) != 0 ? 1u : 0u;
+              tc2_mma(d_tmem, a_desc + a_step * k, b_desc + b_step * k, idesc, accumulate);
+              // (shared columns were just zeroed / kept by the main MMA: B rows >= N are TMA zero fill)
+              if (rowsum) tc2_mma(d_tmem + rowsum_col, a_desc + a_step * k, ones_desc + 2 * k, idesc_ones,
+                                  rowsum_shared ? 1u : accumulate);
+            }
+          }
+          tc2_commit(empty_bar + 8 * stage);             // frees the stage in both CTAs
+          if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
+        }
+        tc2_commit(tfull_bar + 8 * acc);                 // accumulator ready, both CTAs
+        if (++acc == T2_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+      }
+      T2_CTA_STAMP(2);
+    }
+  } else {
+    // ===================== epilogue (warps 2..9, both CTAs) =====================
+    // warp -> TMEM lane quarter q (rows 32q.. of this CTA's 128) and column half (BN/2 columns = BN/128 groups of
+    // 64 columns).  Per 64-column group the flow is the one of gemm_tc.cu.
+    const int q = warp & 3;
+    const int ew = warp - 2;
+    const int half = ew >> 2;
+    float* bias_w = bias_s + ew * 128;
+    const uint32_t bias_addr = smem_u32(bias_w);
+    const uint32_t out_base = smem_u32(sOut + ew * T2_OUT_BUFS * T2_OUT_BUF_BYTES);
+    const uint32_t row_off = (uint32_t)lane * 128u;
+    const uint32_t sw = (uint32_t)(lane & 7);
+    int acc = 0; uint32_t acc_phase = 0;
+    uint32_t buf_i = 0;
+    for (int ti = sched_begin; ti < sched_end; ti += sched_step) {
+      const int t = tile_order ? __ldg(tile_order + ti) : ti;
+      const TileCoord tc = locate_tile(t, s_prefix, s_tiles_n, n_problems);
+      const Tc2Record* R = recs + tc.pi;
+      const int M = R->M, N = R->N, bn = R->bn;
+      const int groups = bn >> 7;                               // 64-column groups per warp: 2 (BN=256) or 1
+      const int m_base = tc.tm * 256 + (int)rank * T2_BM + q * 32;
+      const int col0 = half * (bn >> 1);                        // first accumulator column of this warp
+      const int n_first = tc.tn * bn + col0;
+      const bool has_f32 = R->has_f32 != 0, has_bf16 = R->has_bf16 != 0;
+      const float* const bias = R->bias;
+      const uint16_t* const mask = R->mask; const int64_t ldmask = R->ldmask;
+      const int act = R->act, accumulate = R->accumulate;
+      float* const rowsum_out = (tc.tn == 0 && half == 0) ? R->rowsum_a : nullptr;
+      const int rowsum_col = R->rowsum_col;
+      const int my_m = m_base + lane;
+      const bool row_ok = my_m < M;
+      const bool rows_any = m_base < M;
+      if (lane == 0) {
+        if (has_f32) tma_prefetch_desc(&R->tmC32);
+        if (has_bf16) tma_prefetch_desc(&R->tmC16);
+      }
+      __syncwarp();                                            // the previous tile's reads of the bias slot are done
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int cn = n_first + j * 32 + lane;
+        bias_w[j * 32 + lane] = (bias != nullptr && j * 32 < (bn >> 1) && cn < N) ? __ldg(bias + cn) : 0.f;
+      }
+      __syncwarp();
+      mbar_wait(tfull_bar + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * T2_ACC_COLS + ((uint32_t)(q * 32) << 16);
+      if (rowsum_out != nullptr) {
+        uint32_t rs;
+        tc_ld1(t_row + rowsum_col, rs);
+        tc_wait_ld();
+        if (row_ok) rowsum_out[my_m] = __uint_as_float(rs);
+      }
+      for (int g = 0; g < groups; ++g) {
+        const int n0 = n_first + g * 64;
+        const bool c_ok[2] = {rows_any && n0 < N, rows_any && n0 + 32 < N};   // warp-uniform
+        uint4 mk[2][4];
+        if (mask != nullptr) {
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            const int nc = n0 + c * 32;
+#pragma unroll
+            for (int v4 = 0; v4 < 4; ++v4) {
+              mk[c][v4] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+              if (row_ok && nc + v4 * 8 + 8 <= N)
+                mk[c][v4] = __ldg(reinterpret_cast<const uint4*>(mask + (int64_t)my_m * ldmask + nc) + v4);
+              else if (row_ok && nc + v4 * 8 < N) {
+                uint32_t w[4] = {0, 0, 0, 0};
+                for (int e = 0; e < 8 && nc + v4 * 8 + e < N; ++e)
+                  w[e >> 1] |= (uint32_t)mask[(int64_t)my_m * ldmask + nc + v4 * 8 + e] << ((e & 1) * 16);
+                mk[c][v4] = make_uint4(w[0], w[1], w[2], w[3]);
+              }
+            }
+          }
+        }
+        uint32_t r0[32], r1[32];
+        if (c_ok[0]) tc_ld32(t_row + col0 + g * 64, r0);
+        if (c_ok[1]) tc_ld32(t_row + col0 + g * 64 + 32, r1);
+        tc_wait_ld();
+        if (g == groups - 1) {
+          // the accumulator stage is free once this warp's last values sit in registers: tell the leader
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty_bar + 8 * acc, 0);
+        }
+        uint32_t packed[2][16];
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          if (!c_ok[c]) continue;
+          uint32_t (&r)[32] = c == 0 ? r0 : r1;
+          epilogue_math(r, mk[c], mask != nullptr, bias_addr + (uint32_t)(g * 64 + c * 32) * 4u, act);
+          if (has_bf16) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) packed[c][j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+          }
+          if (has_f32) {
+            if (lane == 0) bulk_wait_read<T2_OUT_BUFS - 1>();
+            __syncwarp();
+            const uint32_t buf = out_base + (buf_i & (T2_OUT_BUFS - 1)) * T2_OUT_BUF_BYTES;
+            ++buf_i;
+#pragma unroll
+            for (int c16 = 0; c16 < 8; ++c16)
+              st_shared_v4(buf + row_off + (((uint32_t)c16 ^ sw) << 4), r[4 * c16], r[4 * c16 + 1], r[4 * c16 + 2], r[4 * c16 + 3]);
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              if (accumulate) tma_reduce_add_2d(&R->tmC32, buf, n0 + c * 32, m_base);
+              else tma_store_2d(&R->tmC32, buf, n0 + c * 32, m_base);
+              bulk_commit();
+            }
+          }
+        }
+        if (has_bf16 && c_ok[0]) {
+          if (lane == 0) bulk_wait_read<T2_OUT_BUFS - 1>();
+          __syncwarp();
+          const uint32_t buf = out_base + (buf_i & (T2_OUT_BUFS - 1)) * T2_OUT_BUF_BYTES;
+          ++buf_i;
+#pragma unroll
+          for (int c = 0; c < 2; ++c) {
+            if (!c_ok[c]) continue;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+              st_shared_v4(buf + row_off + (((uint32_t)(4 * c + i) ^ sw) << 4), packed[c][4 * i], packed[c][4 * i + 1],
+                           packed[c][4 * i + 2], packed[c][4 * i + 3]);
+          }
+          fence_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&R->tmC16, buf, n0, m_base);
+            bulk_commit();
+          }
+        }
+      }
+      if (++acc == T2_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
+    }
+    if (lane == 0) bulk_wait_all();
+    if (ew == 0 && lane == 0) T2_CTA_STAMP(3);
+  }
+  tc_fence_before();
+  __syncthreads();
+  __syncwarp();
+  cluster_sync_all();                                     // nobody leaves while the peer may still read its smem / signal its barriers
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(T2_TMEM_COLS));
+    if (lane == 0) T2_CTA_STAMP(6);
+  }
+}
+
+}  // namespace mmlrec
+
+using namespace mmlrec;
+
+extern "C" int64_t mmlrec_tc2_record_bytes(void) { return (int64_t)sizeof(Tc2Record); }
+
+// tile width of a problem: 256 columns where that halves the passes over A, unless the bias-gradient row sums then
+// have no spare accumulator columns (a stage is 256 TMEM columns wide)
+static int tc2_pick_bn(const MmlrecGemmTcDesc* d) {
+  if (d->N <= 128) return 128;
+  if (d->colsum != nullptr && d->N > 240) return 128;
+  return 256;
+}
+extern "C" int32_t mmlrec_tc2_num_tiles(const MmlrecGemmTcDesc* d) {
+  return cdiv(d->M, 256) * cdiv(d->N, tc2_pick_bn(d));
+}
+
+extern "C" int mmlrec_tc2_encode_problem(const MmlrecGemmTcDesc* d, void* record_host) {
+  MMLREC_CHECK_ARG(d && record_host, "null argument");
+  MMLREC_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0, "bad sizes");
+  MMLREC_CHECK_ARG(((uintptr_t)d->A & 15) == 0 && ((uintptr_t)d->B & 15) == 0, "operands must be 16-byte aligned");
+  MMLREC_CHECK_ARG((d->lda & 7) == 0 && (d->ldb & 7) == 0, "operand row strides must be multiples of 8 elements");
+  MMLREC_CHECK_ARG(d->C_f32 == nullptr || ((d->ldc_f32 & 3) == 0 && ((uintptr_t)d->C_f32 & 15) == 0), "C_f32 alignment");
+  MMLREC_CHECK_ARG(d->C_bf16 == nullptr || ((d->ldc_bf16 & 7) == 0 && ((uintptr_t)d->C_bf16 & 15) == 0), "C_bf16 alignment");
+  MMLREC_CHECK_ARG(d->mask == nullptr || ((d->ldmask & 7) == 0 && ((uintptr_t)d->mask & 15) == 0), "mask alignment");
+  MMLREC_CHECK_ARG(d->C_f32 || d->C_bf16, "no output");
+  MMLREC_CHECK_ARG(!(d->accumulate && d->C_bf16), "accumulate applies to an fp32-only output (the sum is formed in memory)");
+  Tc2Record rec;
+  memset(&rec, 0, sizeof(rec));
+  const int bn = tc2_pick_bn(d);
+  const CUtensorMapDataType BF = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  int rc;
+  if (!d->a_mn_major) rc = tc_encode_map(&rec.tmA, BF, 2, d->A, d->lda, d->K, d->M, T2_BK, T2_BM);
+  else                rc = tc_encode_map(&rec.tmA, BF, 2, d->A, d->lda, d->M, d->K, 64, T2_BK);
+  if (rc) return rc;
+  if (!d->b_mn_major) rc = tc_encode_map(&rec.tmB, BF, 2, d->B, d->ldb, d->K, d->N, T2_BK, bn / 2);
+  else                rc = tc_encode_map(&rec.tmB, BF, 2, d->B, d->ldb, d->N, d->K, 64, T2_BK);
+  if (rc) return rc;
+  if (d->C_f32) {
+    rc = tc_encode_map(&rec.tmC32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d->C_f32, d->ldc_f32, d->N, d->M, 32, 32);
+    if (rc) return rc;
+  }
+  if (d->C_bf16) {
+    rc = tc_encode_map(&rec.tmC16, BF, 2, d->C_bf16, d->ldc_bf16, d->N, d->M, 64, 32);
+    if (rc) return rc;
+  }
+  rec.has_f32 = d->C_f32 != nullptr; rec.has_bf16 = d->C_bf16 != nullptr;
+  rec.bias = d->bias; rec.mask = d->mask; rec.ldmask = d->ldmask; rec.rowsum_a = d->colsum;
+  rec.M = d->M; rec.N = d->N; rec.K = d->K; rec.act = d->act; rec.accumulate = d->accumulate;
+  rec.a_mn = d->a_mn_major; rec.b_mn = d->b_mn_major; rec.bn = bn; rec.tiles_n = cdiv(d->N, bn);
+  rec.rowsum_col = bn == 128 ? 128 : 240;
+  memcpy(record_host, &rec, sizeof(rec));
+  return 0;
+}
+
+extern "C" int mmlrec_gemm_grouped_tc2(const void* records, const int32_t* tile_prefix, int32_t n_problems,
+                                       int32_t total_tiles, const int32_t* tile_order, const int32_t* pair_start,
+                                       int32_t n_pairs, int64_t* stamps, void* stream) {
+  MMLREC_CHECK_ARG(records && tile_prefix && n_problems > 0 && total_tiles >= 0, "bad args");
+  MMLREC_CHECK_ARG(((uintptr_t)records & 127) == 0, "record table must be 128-byte aligned");
+  MMLREC_CHECK_ARG(n_problems <= T2_MAX_PROBLEMS, "too many problems in one launch (split the table)");
+  MMLREC_CHECK_ARG((tile_order == nullptr) == (pair_start == nullptr), "tile_order and pair_start come together");
+  if (total_tiles == 0) return 0;
+  static bool opted = false;
+  if (!opted) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_grouped_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, T2_SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("gemm_tc2: smem opt-in failed: %s", cudaGetErrorString(e)); return (int)e; }
+    opted = true;
+  }
+  const int max_pairs = tc_sm_count() / 2;
+  int pairs = tile_order ? n_pairs : (total_tiles < max_pairs ? total_tiles : max_pairs);
+  MMLREC_CHECK_ARG(pairs > 0 && pairs <= max_pairs, "bad pair count");
+  gemm_grouped_tc2_kernel<<<2 * pairs, T2_THREADS, T2_SMEM_BYTES, (cudaStream_t)stream>>>(
+      reinterpret_cast<const Tc2Record*>(records), tile_prefix, n_problems, total_tiles, tile_order, pair_start,
+      reinterpret_cast<long long*>(stamps));
+  MMLREC_RETURN_LAUNCH(1);
+}

@@ -126,6 +126,9 @@ class Builder:
     def __init__(self, B: int, device, store: Optional[FlatStore], dry: bool, precision: str = "fp32"):
         self.B, self.device, self.store, self.dry = B, device, store, dry
         self.tc = precision == "bf16"
+        # tensor-core kernel: 2 = CTA pairs (tcgen05 cta_group::2, 256-wide tiles), 1 = one CTA per 128x128 tile
+        import os
+        self.tc_kernel = int(os.environ.get("MMLREC_TC_KERNEL", "2"))
         self.stages: List["Stage"] = []
         self.groups: List[ActGroup] = []
         self.param_order: List[nn.Parameter] = []
@@ -153,42 +156,66 @@ class Builder:
         return t
 
     def tc_table(self, descs: Sequence[L.GemmTcDesc]):
-        """Encode tensor-core problems (tensor maps built on the host) -> (records, prefix, n, tiles)."""
-        rb = int(self.lib.mmlrec_tc_record_bytes())
+        """Encode tensor-core problems (tensor maps built on the host) -> launch tuple
+        (records, prefix, n, tiles, tile order, per-unit starts, units); a unit is a CTA or a CTA pair."""
+        pairs = self.tc_kernel == 2
+        rb = int(self.lib.mmlrec_tc2_record_bytes() if pairs else self.lib.mmlrec_tc_record_bytes())
         host = (C.c_uint8 * (rb * len(descs)))()
         pre, at = [0], 0
         for i, d in enumerate(descs):
-            L.check(self.lib.mmlrec_tc_encode_problem(C.byref(d), C.addressof(host) + i * rb), "tc_encode_problem")
-            at += int(self.lib.mmlrec_tc_num_tiles(d.M, d.N))
+            if pairs:
+                L.check(self.lib.mmlrec_tc2_encode_problem(C.byref(d), C.addressof(host) + i * rb), "tc2_encode_problem")
+                at += int(self.lib.mmlrec_tc2_num_tiles(C.byref(d)))
+            else:
+                L.check(self.lib.mmlrec_tc_encode_problem(C.byref(d), C.addressof(host) + i * rb), "tc_encode_problem")
+                at += int(self.lib.mmlrec_tc_num_tiles(d.M, d.N))
             pre.append(at)
         rec = torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8).to(self.device)
         assert rec.data_ptr() % 128 == 0
         self.keep.append(rec)
-        order, starts, n_ctas = self._tc_schedule(descs, pre)
-        return rec, self.ints(pre), len(descs), at, self.ints(order), self.ints(starts), n_ctas
+        order, starts, n_units = self._tc_schedule(descs, pre)
+        return rec, self.ints(pre), len(descs), at, self.ints(order), self.ints(starts), n_units
+
+    def tc_launch(self, tbl, stream, stamps=None):
+        if self.tc_kernel == 2:
+            return self.lib.mmlrec_gemm_grouped_tc2(tbl[0].data_ptr(), tbl[1].data_ptr(), tbl[2], tbl[3], tbl[4].data_ptr(),
+                                                    tbl[5].data_ptr(), tbl[6], stamps, stream)
+        if stamps is not None:
+            return self.lib.mmlrec_gemm_grouped_tc_debug(tbl[0].data_ptr(), tbl[1].data_ptr(), tbl[2], tbl[3],
+                                                         tbl[4].data_ptr(), tbl[5].data_ptr(), tbl[6], stamps, stream)
+        return self.lib.mmlrec_gemm_grouped_tc_scheduled(tbl[0].data_ptr(), tbl[1].data_ptr(), tbl[2], tbl[3],
+                                                         tbl[4].data_ptr(), tbl[5].data_ptr(), tbl[6], stream)
 
     def _tc_schedule(self, descs, pre):
-        """Static longest-processing-time schedule of the launch's 128x128 tiles over the SMs.  Tile cost model
-        (cycles, from profiles/tc_epilogue_timeline_r01.txt): ~750 per 64-wide k-block + ~3000 per epilogue."""
+        """Static longest-processing-time schedule of the launch's tiles over the SMs (CTA pairs for kernel 2).  Tile
+        cost model in cycles, from the per-tile timelines under profiles/: a 64-wide k-block costs what its operand
+        bytes cost at the L2 -> SM rate (~37 B/cycle/SM with every SM pulling), plus the epilogue of the tile."""
         import heapq
         n_sm = max(int(self.lib.mmlrec_tc_sm_count()), 1)
+        pairs = self.tc_kernel == 2
+        n_units = max(n_sm // 2, 1) if pairs else n_sm
         tiles = []
         for i, d in enumerate(descs):
-            cost = 750 * ((d.K + 63) // 64) + 3000
+            kb = (d.K + 63) // 64
+            if pairs:
+                bn = 128 if (d.N <= 128 or (d.colsum and d.N > 240)) else 256
+                cost = kb * (900 if bn == 256 else 700) + 650 * (bn // 32)
+            else:
+                cost = 900 * kb + 2600
             tiles.extend((cost, t) for t in range(pre[i], pre[i + 1]))
-        n_ctas = min(n_sm, len(tiles))
+        n_units = min(n_units, len(tiles))
         tiles.sort(key=lambda ct: (-ct[0], ct[1]))
-        heap = [(0, c) for c in range(n_ctas)]
-        lists = [[] for _ in range(n_ctas)]
+        heap = [(0, c) for c in range(n_units)]
+        lists = [[] for _ in range(n_units)]
         for cost, t in tiles:
             load, c = heapq.heappop(heap)
             lists[c].append(t)
             heapq.heappush(heap, (load + cost, c))
         order, starts = [], [0]
         for lst in lists:
-            order.extend(lst)
+            order.extend(sorted(lst))   # ascending tile index: consecutive tiles of a problem share operand rows in L2
             starts.append(len(order))
-        return order, starts, n_ctas
+        return order, starts, n_units
 
     def aux_matrix(self, rows: int, cols: int):
         if self.dry:
@@ -532,8 +559,7 @@ class LinearStage(Stage):
     def _launch(self, tbl, stream, what):
         lib = self.b.lib
         if self.b.tc:
-            rc = lib.mmlrec_gemm_grouped_tc_scheduled(tbl[0].data_ptr(), tbl[1].data_ptr(), tbl[2], tbl[3],
-                                                      tbl[4].data_ptr(), tbl[5].data_ptr(), tbl[6], stream)
+            rc = self.b.tc_launch(tbl, stream)
         else:
             rc = lib.mmlrec_gemm_grouped_f32(tbl[0].data_ptr(), tbl[1].data_ptr(), tbl[2], tbl[3], stream)
         L.check(rc, f"{what} {self.label}")

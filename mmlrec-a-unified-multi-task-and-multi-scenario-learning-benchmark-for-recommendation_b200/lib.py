@@ -100,7 +100,11 @@ _SIGNATURES = {
     "mmlrec_gemm_grouped_tc": (C.c_int, [vp, vp, i32, i32, vp]),
     "mmlrec_gemm_grouped_tc_scheduled": (C.c_int, [vp, vp, i32, i32, vp, vp, i32, vp]),
     "mmlrec_tc_sm_count": (i32, []),
-    "mmlrec_gemm_grouped_tc_debug": (C.c_int, [vp, vp, i32, i32, vp, vp]),
+    "mmlrec_tc2_record_bytes": (C.c_int64, []),
+    "mmlrec_tc2_num_tiles": (C.c_int32, [vp]),
+    "mmlrec_tc2_encode_problem": (C.c_int, [vp, vp]),
+    "mmlrec_gemm_grouped_tc2": (C.c_int, [vp, vp, i32, i32, vp, vp, i32, vp, vp]),
+    "mmlrec_gemm_grouped_tc_debug": (C.c_int, [vp, vp, i32, i32, vp, vp, i32, vp, vp]),
     "mmlrec_tc_num_tiles": (i32, [i32, i32]),
     "mmlrec_bn_forward": (C.c_int, [vp, i64, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, i64, vp, i64, i32, i32, vp]),
     "mmlrec_bn_backward": (C.c_int, [vp, i64, vp, i64, i32, i32, vp, vp, vp, vp, i64, vp, i64, vp, vp, vp]),

@@ -146,16 +146,25 @@ def gemm_grouped_f32(problems: List[Dict]) -> None:
 
 
 class TcProblemTable:
-    """Device-resident table of tensor-core GEMM problems (tensor maps encoded on the host once)."""
+    """Device-resident table of tensor-core GEMM problems (tensor maps encoded on the host once).
+    ``kernel``: 1 = one CTA per 128x128 tile (gemm_tc.cu), 2 = CTA pairs on 256-wide tiles (gemm_tc2.cu);
+    default from ``MMLREC_TC_KERNEL`` (2)."""
 
-    def __init__(self, descs: Sequence[L.GemmTcDesc], device):
+    def __init__(self, descs: Sequence[L.GemmTcDesc], device, kernel: Optional[int] = None):
+        import os
         lib = L.load()
-        rb = int(lib.mmlrec_tc_record_bytes())
+        self.kernel = int(os.environ.get("MMLREC_TC_KERNEL", "2")) if kernel is None else kernel
+        pairs = self.kernel == 2
+        rb = int(lib.mmlrec_tc2_record_bytes() if pairs else lib.mmlrec_tc_record_bytes())
         host = (C.c_uint8 * (rb * len(descs)))()
         pre, at = [0], 0
         for i, d in enumerate(descs):
-            L.check(lib.mmlrec_tc_encode_problem(C.byref(d), C.addressof(host) + i * rb), "tc_encode_problem")
-            at += int(lib.mmlrec_tc_num_tiles(d.M, d.N))
+            if pairs:
+                L.check(lib.mmlrec_tc2_encode_problem(C.byref(d), C.addressof(host) + i * rb), "tc2_encode_problem")
+                at += int(lib.mmlrec_tc2_num_tiles(C.byref(d)))
+            else:
+                L.check(lib.mmlrec_tc_encode_problem(C.byref(d), C.addressof(host) + i * rb), "tc_encode_problem")
+                at += int(lib.mmlrec_tc_num_tiles(d.M, d.N))
             pre.append(at)
         # 128-byte aligned device copy
         raw = torch.frombuffer(bytearray(bytes(host)), dtype=torch.uint8)
@@ -168,8 +177,13 @@ class TcProblemTable:
         self.n, self.tiles = len(descs), at
 
     def launch(self, stream: Optional[int] = None) -> None:
-        L.check(L.load().mmlrec_gemm_grouped_tc(self.records.data_ptr(), self.prefix.data_ptr(), self.n, self.tiles,
-                                                _stream() if stream is None else stream), "gemm_grouped_tc")
+        st = _stream() if stream is None else stream
+        if self.kernel == 2:
+            L.check(L.load().mmlrec_gemm_grouped_tc2(self.records.data_ptr(), self.prefix.data_ptr(), self.n, self.tiles,
+                                                     None, None, 0, None, st), "gemm_grouped_tc2")
+        else:
+            L.check(L.load().mmlrec_gemm_grouped_tc(self.records.data_ptr(), self.prefix.data_ptr(), self.n, self.tiles,
+                                                    st), "gemm_grouped_tc")
 
 
 def tc_desc(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, a_mn: bool = False, b_mn: bool = False,

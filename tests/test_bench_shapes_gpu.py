@@ -141,9 +141,10 @@ def test_bf16_census_batchnorm_full_shape():
 
 
 # ------------------------------------------------------------------------------------------------ kernels at full size
+@pytest.mark.parametrize("kernel", [1, 2])
 @pytest.mark.parametrize("splits", [1, 2, 4])
-@pytest.mark.parametrize("M,N", [(256, 128), (64, 128), (3904, 199)])
-def test_tc_wgrad_k4096_mn_major_split_k(M, N, splits):
+@pytest.mark.parametrize("M,N", [(256, 128), (64, 128), (3904, 199), (128, 256)])
+def test_tc_wgrad_k4096_mn_major_split_k(M, N, splits, kernel):
     """dW[M,N] = dZ^T X with the contraction over a batch of 4096 (both operands MN-major, 64 k-blocks per tile),
     plain and as deterministic split-K: S partial problems into scratch slices + sum_slices, vs fp32 torch."""
     if not torch.cuda.is_available():
@@ -166,7 +167,7 @@ def test_tc_wgrad_k4096_mn_major_split_k(M, N, splits):
         out = torch.full((slice_floats,), float("nan"), device=dev)
         d = ops.tc_desc(dz[:, :M], x[:, :N], M, N, Bt, a_mn=True, b_mn=True, C_f32=out[:span].view(M, ldw),
                         rowsum_a=out[span:span + M])
-        ops.TcProblemTable([d], dev).launch()
+        ops.TcProblemTable([d], dev, kernel=kernel).launch()
         torch.cuda.synchronize()
         W, b = out[:span].view(M, ldw)[:, :N], out[span:span + M]
     else:
@@ -177,7 +178,7 @@ def test_tc_wgrad_k4096_mn_major_split_k(M, N, splits):
             sl = scratch[k * slice_floats:(k + 1) * slice_floats]
             descs.append(ops.tc_desc(dz[k * rows:(k + 1) * rows, :M], x[k * rows:(k + 1) * rows, :N], M, N, rows,
                                      a_mn=True, b_mn=True, C_f32=sl[:span].view(M, ldw), rowsum_a=sl[span:span + M]))
-        ops.TcProblemTable(descs, dev).launch()
+        ops.TcProblemTable(descs, dev, kernel=kernel).launch()
         grad = torch.full((slice_floats,), float("nan"), device=dev)
         seg = torch.tensor([0, 0, span, span, span, M], dtype=torch.int64, device=dev)   # (dst, src, n) x 2
         L.check(L.load().mmlrec_sum_slices(seg.data_ptr(), 2, span, grad.data_ptr(), scratch.data_ptr(), splits,

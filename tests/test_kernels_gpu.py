@@ -198,9 +198,11 @@ def _bf16(t):
     return t.to(torch.bfloat16)
 
 
+@pytest.mark.parametrize("kernel", [1, 2])
 @pytest.mark.parametrize("a_mn,b_mn", [(False, False), (False, True), (True, False), (True, True)])
-@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 256), (300, 200, 199), (4096, 24, 130), (70, 520, 1000)])
-def test_gemm_tc_layouts(a_mn, b_mn, M, N, K):
+@pytest.mark.parametrize("M,N,K", [(128, 128, 64), (256, 128, 256), (300, 200, 199), (4096, 24, 130), (70, 520, 1000),
+                                   (520, 256, 320), (1000, 300, 72)])
+def test_gemm_tc_layouts(a_mn, b_mn, M, N, K, kernel):
     """bf16 tcgen05 GEMM, every combination of K-major / MN-major operands, ragged sizes.  Inputs are
     exact bf16 values, so against fp32 torch only the accumulation order differs."""
     from mmlrec_b200 import ops
@@ -230,7 +232,7 @@ def test_gemm_tc_layouts(a_mn, b_mn, M, N, K):
     C16 = torch.zeros(M, pad(N), dtype=torch.bfloat16, device=dev)
     rs = torch.full((M,), float("nan"), device=dev)
     d = ops.tc_desc(A_arg, B_arg, M, N, K, a_mn=a_mn, b_mn=b_mn, C_f32=C32, C_bf16=C16, rowsum_a=rs)
-    ops.TcProblemTable([d], dev).launch()
+    ops.TcProblemTable([d], dev, kernel=kernel).launch()
     torch.cuda.synchronize()
     assert rel_err(C32[:, :N], want) < 1e-5
     assert rel_err(C16[:, :N].float(), want) < 5e-3
@@ -238,7 +240,8 @@ def test_gemm_tc_layouts(a_mn, b_mn, M, N, K):
     assert torch.isnan(C32[:, N:]).all(), "columns beyond N are never written"
 
 
-def test_gemm_tc_epilogue_bias_relu_mask_accumulate_grouped():
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_gemm_tc_epilogue_bias_relu_mask_accumulate_grouped(kernel):
     from mmlrec_b200 import ops
     dev = _cuda()
     g = torch.Generator().manual_seed(11)
@@ -252,7 +255,7 @@ def test_gemm_tc_epilogue_bias_relu_mask_accumulate_grouped():
     out2 = prev.clone()
     descs = [ops.tc_desc(A, W, M, N, K, C_f32=out1, bias=bias, act="relu"),
              ops.tc_desc(A, W, M, N, K, C_f32=out2, mask=mask, accumulate=True)]
-    tbl = ops.TcProblemTable(descs, dev)
+    tbl = ops.TcProblemTable(descs, dev, kernel=kernel)
     tbl.launch()
     torch.cuda.synchronize()
     base = A.float() @ W.float().T

@@ -126,28 +126,39 @@ def test_constructor_errors_match_reference():
         MMOE([SparseFeat("a", 3, 4)], device="cpu", config=bad)
 
 
-def test_static_tile_schedule_is_a_balanced_partition():
-    """engine/core.py Builder._tc_schedule: longest-processing-time assignment of the grouped GEMM's 128x128 tiles to
-    the persistent CTAs.  Every tile exactly once, contiguous per-CTA ranges, makespan within LPT's 4/3 bound."""
+@pytest.mark.parametrize("kernel", [1, 2])
+def test_static_tile_schedule_is_a_balanced_partition(kernel):
+    """engine/core.py Builder._tc_schedule: longest-processing-time assignment of the grouped GEMM's tiles to the
+    persistent CTAs (kernel 1) or CTA pairs (kernel 2).  Every tile exactly once, contiguous per-unit ranges, makespan
+    within LPT's 4/3 bound under the scheduler's own cost model."""
     import types
     import torch
     from mmlrec_b200.engine.core import Builder
     b = Builder(4096, torch.device("cpu"), None, dry=True)
     b.lib = types.SimpleNamespace(mmlrec_tc_sm_count=lambda: 148)
+    b.tc_kernel = kernel
+    units = 148 if kernel == 1 else 74
     # a backward launch: 28 long wgrad tiles (K = 4096) + 896 short dgrad tiles (K = 128) + one odd problem
-    descs = [types.SimpleNamespace(K=4096)] * 14 + [types.SimpleNamespace(K=128)] * 14 + [types.SimpleNamespace(K=199)]
+    mk = lambda K, N, cs: types.SimpleNamespace(K=K, N=N, colsum=cs)  # noqa: E731
+    descs = [mk(4096, 256, 1)] * 14 + [mk(128, 256, None)] * 14 + [mk(199, 3904, None)]
     tiles_per = [2] * 14 + [64] * 14 + [7]
     pre = [0]
     for n in tiles_per:
         pre.append(pre[-1] + n)
     order, starts, n_ctas = b._tc_schedule(descs, pre)
-    assert n_ctas == 148 and len(starts) == n_ctas + 1 and starts[0] == 0 and starts[-1] == pre[-1]
+    assert n_ctas == units and len(starts) == n_ctas + 1 and starts[0] == 0 and starts[-1] == pre[-1]
     assert sorted(order) == list(range(pre[-1])), "each tile is scheduled exactly once"
     assert all(starts[i] <= starts[i + 1] for i in range(n_ctas))
     cost = {}
     for i, d in enumerate(descs):
+        kb = (d.K + 63) // 64
+        if kernel == 2:
+            bn = 128 if (d.N <= 128 or (d.colsum and d.N > 240)) else 256
+            c = kb * (900 if bn == 256 else 700) + 650 * (bn // 32)
+        else:
+            c = 900 * kb + 2600
         for t in range(pre[i], pre[i + 1]):
-            cost[t] = 750 * ((d.K + 63) // 64) + 3000
+            cost[t] = c
     loads = [sum(cost[t] for t in order[starts[c]:starts[c + 1]]) for c in range(n_ctas)]
     lower = max(max(cost.values()), sum(cost.values()) / n_ctas)
     assert max(loads) <= 4 / 3 * lower + 1, (max(loads), lower)

@@ -1,12 +1,24 @@
-"""Per-tile timeline (clock64 stamps of CTA 0) of tensor-core GEMM launches inside the PLE-AE step."""
-import sys, os
+"""Timeline of the tcgen05 grouped-GEMM launches inside a training step (profiling aid, 1 GPU):
+per-tile clock64 stamps of CTA 0 (producer / MMA issuer / epilogue roles) and, for every CTA, global-timer stamps of
+setup / producer / MMA / epilogue completion.   python tools/tc_timeline.py [workload] [stage-label ...]"""
+import os
+import sys
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-import torch
-import bench
-from mmlrec_b200 import synthetic, lib as L
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
 
-class A: workload = "ae_ple_t4"
+import bench  # noqa: E402
+from mmlrec_b200 import lib as L, synthetic  # noqa: E402
+
+
+class A:
+    workload = sys.argv[1] if len(sys.argv) > 1 else "ae_ple_t4"
+    vocab = 0
+
+
+labels = set(sys.argv[2:])
 cfg, fields = bench.workload_config(A)
 model = bench.build_ours(cfg, fields, "cuda:0", "bf16")
 B = 4096
@@ -17,23 +29,47 @@ torch.cuda.synchronize()
 plan = model.plan(B)
 lib = L.load()
 st = torch.cuda.current_stream().cuda_stream
-names = ["P.start", "P.table", "P.slot0", "P.issued", "M.start", "M.accfree", "M.data0", "M.commit", "E.start", "E.bias", "E.accrdy", "E.done", "E.ld0", "E.ph1", "E.ph2"]
-def run(tag, tbl):
-    stamps = torch.zeros(64, 16, dtype=torch.int64, device="cuda")
-    for _ in range(2):
-        L.check(lib.mmlrec_gemm_grouped_tc_debug(tbl[0].data_ptr(), tbl[1].data_ptr(), tbl[2], tbl[3], stamps.data_ptr(), st))
+names = ["P.start", "P.table", "P.slot0", "P.issued", "M.start", "M.accfree", "M.data0", "M.commit", "E.start", "E.bias",
+         "E.accrdy", "E.done", "E.release", "E.math0", "E.waited0", "E.fenced0"]
+
+
+def run(tag, tbl, tiles_shown=10):
+    n_ctas = tbl[6] * (2 if plan.b.tc_kernel == 2 else 1)
+    stamps = torch.zeros(1024 + 8 * max(n_ctas, 148), dtype=torch.int64, device="cuda")
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    for i in range(3):
+        if i == 2:
+            ev[0].record()
+        L.check(plan.b.tc_launch(tbl, st, stamps.data_ptr()))
+    ev[1].record()
     torch.cuda.synchronize()
-    s = stamps.cpu()
-    t0 = int(s[0, 0])
-    print(f"=== {tag}: {tbl[2]} problems, {tbl[3]} tiles  (cycles relative to CTA0's first tile start)")
-    print("tile " + " ".join(f"{n:>9s}" for n in names))
-    for i in range(64):
-        if int(s[i, 0]) == 0:
+    s = stamps.cpu().numpy()
+    per_tile, cta = s[:1024].reshape(64, 16), s[1024:1024 + 8 * n_ctas].reshape(n_ctas, 8)
+    t0 = int(per_tile[0, 0])
+    print(f"=== {tag}: {tbl[2]} problems, {tbl[3]} tiles on {n_ctas} CTAs, launch {ev[0].elapsed_time(ev[1]) * 1e3:.1f} us")
+    print("tile " + " ".join(f"{n:>9s}" for n in names) + "   (CTA 0, cycles from its first tile start)")
+    for i in range(min(64, tiles_shown)):
+        if int(per_tile[i, 0]) == 0:
             break
-        print(f"{i:4d} " + " ".join(f"{int(s[i, k]) - t0:9d}" for k in range(15)))
-for idx, s in enumerate(plan.stages):
-    if s.name != "linear":
+        print(f"{i:4d} " + " ".join(f"{int(per_tile[i, k]) - t0:9d}" for k in range(16)))
+    g0 = cta[:, 0].min()
+    rel = (cta[:, :4] - g0) / 1e3
+    print(f"per CTA (us from the earliest setup-done): setup-done max {rel[:, 0].max():.2f}; producer done "
+          f"median {np.median(rel[:, 1]):.2f} max {rel[:, 1].max():.2f}; MMA done median {np.median(rel[:, 2]):.2f} "
+          f"max {rel[:, 2].max():.2f}; epilogue done median {np.median(rel[:, 3]):.2f} max {rel[:, 3].max():.2f}; "
+          f"tiles/CTA min {cta[:, 4].min()} max {cta[:, 4].max()}")
+    print(f"   kernel entry -> setup done: median {np.median(cta[:, 0] - cta[:, 5]) / 1e3:.2f} us max {(cta[:, 0] - cta[:, 5]).max() / 1e3:.2f}; "
+          f"entry spread {(cta[:, 5].max() - cta[:, 5].min()) / 1e3:.2f} us; first entry -> last exit {(cta[:, 6].max() - cta[:, 5].min()) / 1e3:.2f} us; "
+          f"epilogue done -> exit median {np.median(cta[:, 6] - cta[:, 3]) / 1e3:.2f} us")
+    dur = (cta[:, 3] - cta[:, 0]) / 1e3
+    per = dur / np.maximum(cta[:, 4], 1)
+    print(f"   busy time per CTA (setup-done -> epilogue done) median {np.median(dur):.2f} us, per tile median {np.median(per):.2f} us")
+
+
+for s in plan.stages:
+    if s.name != "linear" or (labels and s.label not in labels):
         continue
-    if s.label in ("cgc0.l0",):
-        run(f"fwd {s.label}", s.fwd[0])
-        run(f"bwd {s.label}", s.bwd[0])
+    for i, t in enumerate(s.fwd):
+        run(f"fwd {s.label}[{i}]", t)
+    for i, t in enumerate(s.bwd):
+        run(f"bwd {s.label}[{i}]", t)
