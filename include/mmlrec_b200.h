@@ -216,6 +216,14 @@ typedef struct MmlrecGemmTcDesc {           /* host-side description of one prob
   const uint16_t* mask; int64_t ldmask;     /* bf16 [M,N]: keep where mask > 0 */
   float* colsum;                            /* nullable [N]: column sums of the fp32 result, atomically accumulated */
   int32_t act, accumulate;                  /* accumulate applies to C_f32 only */
+  /* ReLU bit masks (1 bit per element, used by the CTA-pair kernel; the one-CTA kernel ignores them and needs `mask`).
+   * Layout of a bit array over a row-major [rows, 32 * chunks] activation: word ((row / 32) * chunks + col / 32) * 32
+   * + row % 32 holds the 32 columns [32 * (col / 32), +32) of that row, so the 32 rows a warp handles are 128
+   * contiguous bytes.  `relu_bits_out`: the epilogue also stores "result > 0" for its outputs (forward of a ReLU layer);
+   * `mask_bits`: applied instead of `mask` (dgrad through that ReLU).  *_chunks = words per row block, *_chunk0 = the
+   * chunk of this problem's column 0 (its first column must be a multiple of 32). */
+  uint32_t* relu_bits_out; int32_t bits_out_chunks, bits_out_chunk0;
+  const uint32_t* mask_bits; int32_t mask_bits_chunks, mask_bits_chunk0;
 } MmlrecGemmTcDesc;
 /* size in bytes of one device problem record; the table is `n * mmlrec_tc_record_bytes()` */
 int64_t mmlrec_tc_record_bytes(void);
@@ -391,6 +399,12 @@ int64_t mmlrec_heads_scratch(int32_t T, int32_t max_h, int32_t B);
  * ------------------------------------------------------------------------------------------- */
 int mmlrec_dense_optimizer_step(float* param, const float* grad, float* state1, float* state2, int64_t n,
                                 const MmlrecHyper* hyper, uint16_t* bf16_shadow, void* stream);
+/* Same step, 128-bit accesses (n, slice_stride multiples of 4; buffers 16-byte aligned), with the gradient given as
+ * `n_slices` partial buffers `slice_stride` floats apart, added in slice order before the update: split-K wgrad problems
+ * write their partial tiles into slices 1..S-1 (slice 0 = the ordinary gradient buffer), so no separate reduction pass. */
+int mmlrec_dense_optimizer_step_sliced(float* param, const float* grad, float* state1, float* state2, int64_t n,
+                                       const MmlrecHyper* hyper, uint16_t* bf16_shadow, int32_t n_slices,
+                                       int64_t slice_stride, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Element-wise stages used by STAR (model/star.py + SharedSpecificLinear, model/utils.py:163-223) and

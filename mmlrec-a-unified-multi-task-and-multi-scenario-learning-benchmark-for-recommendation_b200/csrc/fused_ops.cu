@@ -438,6 +438,33 @@ __global__ void dense_optimizer_kernel(float* p, const float* g, float* s1, floa
   }
 }
 
+// Same update over 4 elements per thread (128-bit accesses), with the gradient given as `n_slices` partial buffers
+// `slice_stride` floats apart that are added in slice order: the split-K wgrad problems write their partial tiles
+// straight into gradient slices 1..S-1 (slice 0 is the ordinary gradient buffer every other kernel writes), so the
+// split needs no separate reduction pass and stays deterministic.
+__global__ void __launch_bounds__(256)
+dense_optimizer_sliced_kernel(float4* p, const float4* g, float4* s1, float4* s2, int64_t n4, const MmlrecHyper* hyper,
+                              uint2* shadow, int n_slices, int64_t slice_stride4) {
+  const MmlrecHyper hp = *hyper;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 gv = g[i];
+    for (int k = 1; k < n_slices; ++k) {
+      const float4 t = g[(int64_t)k * slice_stride4 + i];
+      gv.x += t.x; gv.y += t.y; gv.z += t.z; gv.w += t.w;
+    }
+    float4 pv = p[i];
+    float4 a = s1 ? s1[i] : make_float4(0.f, 0.f, 0.f, 0.f), b = s2 ? s2[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    optimizer_update(pv.x, gv.x, a.x, b.x, hp);
+    optimizer_update(pv.y, gv.y, a.y, b.y, hp);
+    optimizer_update(pv.z, gv.z, a.z, b.z, hp);
+    optimizer_update(pv.w, gv.w, a.w, b.w, hp);
+    p[i] = pv;
+    if (s1) s1[i] = a;
+    if (s2) s2[i] = b;
+    if (shadow) shadow[i] = make_uint2(pack_bf16x2(pv.x, pv.y), pack_bf16x2(pv.z, pv.w));
+  }
+}
+
 __global__ void fill_kernel(float* p, int64_t n, float v) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
@@ -665,6 +692,20 @@ extern "C" int mmlrec_dense_optimizer_step(float* param, const float* grad, floa
   MMLREC_CHECK_ARG(n >= 0 && hyper, "bad args");
   if (n == 0) return 0;
   dense_optimizer_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(param, grad, state1, state2, n, hyper, bf16_shadow);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_dense_optimizer_step_sliced(float* param, const float* grad, float* state1, float* state2, int64_t n,
+                                                  const MmlrecHyper* hyper, uint16_t* bf16_shadow, int32_t n_slices,
+                                                  int64_t slice_stride, void* stream) {
+  MMLREC_CHECK_ARG(n >= 0 && hyper && n_slices >= 1, "bad args");
+  MMLREC_CHECK_ARG((n & 3) == 0 && (slice_stride & 3) == 0, "n and slice_stride must be multiples of 4");
+  MMLREC_CHECK_ARG((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)state1 | (uintptr_t)state2) & 15) == 0 &&
+                   ((uintptr_t)bf16_shadow & 7) == 0, "buffers must be 16-byte aligned");
+  if (n == 0) return 0;
+  dense_optimizer_sliced_kernel<<<grid_for(n / 4), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<float4*>(param), reinterpret_cast<const float4*>(grad), reinterpret_cast<float4*>(state1),
+      reinterpret_cast<float4*>(state2), n / 4, hyper, reinterpret_cast<uint2*>(bf16_shadow), n_slices, slice_stride / 4);
   MMLREC_RETURN_LAUNCH(1);
 }
 

@@ -23,16 +23,13 @@ constexpr int T2_STAGES = 4;
 constexpr int T2_ACC_STAGES = 2;
 constexpr int T2_ACC_COLS = 256;                 // TMEM columns per accumulator stage
 constexpr int T2_TMEM_COLS = 512;
-constexpr int T2_EPI_WARPS = 8;
+constexpr int T2_EPI_WARPS = 16;                 // four per TMEM lane quarter: each owns 32 rows x BN/4 columns of a tile
 constexpr int T2_THREADS = 64 + 32 * T2_EPI_WARPS;
 constexpr int T2_MAX_PROBLEMS = 96;
 constexpr int T2_A_BYTES = T2_BM * T2_BK * 2;    // 16 KB: this CTA's 128 rows of A
 constexpr int T2_B_BYTES = 128 * T2_BK * 2;      // 16 KB: this CTA's half of B (BN/2 <= 128 rows)
 constexpr int T2_ONES_BYTES = 16 * 128;
-constexpr int T2_OUT_BUF_BYTES = 32 * 128;
-constexpr int T2_OUT_BUFS = 2;
-constexpr int T2_SMEM_BYTES = 1024 + T2_STAGES * (T2_A_BYTES + T2_B_BYTES) + T2_EPI_WARPS * T2_OUT_BUFS * T2_OUT_BUF_BYTES +
-                              T2_ONES_BYTES + 256 + T2_EPI_WARPS * 128 * 4 + (2 * T2_MAX_PROBLEMS + 2) * 4;
+constexpr int T2_OUT_BUF_BYTES = 32 * 128;       // one staging box per epilogue warp
 
 struct alignas(128) Tc2Record {
   CUtensorMap tmA;                              // K-major: box {64 k, 128 rows}; MN-major: box {64 m, 64 k}
@@ -49,7 +46,28 @@ struct alignas(128) Tc2Record {
   int32_t has_f32, has_bf16;
   int32_t bn;                                   // 256 or 128
   int32_t rowsum_col;                           // TMEM column (inside the stage) that receives the row sums
+  uint32_t* bits_out; const uint32_t* mask_bits; // ReLU bit masks (see MmlrecGemmTcDesc)
+  int32_t bits_out_chunks, bits_out_chunk0, mask_bits_chunks, mask_bits_chunk0;
 };
+
+// the scalar part of a record, cached in shared memory once per CTA (every role reads it at every tile)
+struct Tc2Meta {
+  const float* bias;
+  const uint16_t* mask; int64_t ldmask;
+  float* rowsum_a;
+  int32_t M, N, K;
+  int32_t act, accumulate;
+  int32_t a_mn, b_mn;
+  int32_t has_f32, has_bf16;
+  int32_t bn, rowsum_col;
+  int32_t bits_out_chunks, bits_out_chunk0, mask_bits_chunks, mask_bits_chunk0;
+  int32_t pad_;
+  uint32_t* bits_out; const uint32_t* mask_bits;
+};
+
+constexpr int T2_SMEM_BYTES = 1024 + T2_STAGES * (T2_A_BYTES + T2_B_BYTES) + T2_EPI_WARPS * T2_OUT_BUF_BYTES +
+                              T2_ONES_BYTES + 256 + T2_EPI_WARPS * 64 * 4 + (2 * T2_MAX_PROBLEMS + 2) * 4 +
+                              T2_MAX_PROBLEMS * (int)sizeof(Tc2Meta);
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;
@@ -92,6 +110,36 @@ __device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) 
       "}\n" ::"r"(bar), "r"(cta) : "memory");
 }
 
+// ReLU mask of one 32-column chunk (thread = row): zero the accumulator where the bf16 mask value is not > 0.
+// __vcmpgts2 compares the two signed halfwords of a word with 0: a bf16 is > 0 iff its bits, read as int16, are > 0.
+__device__ __forceinline__ void apply_mask32(uint32_t (&r)[32], const uint4 (&mk)[4]) {
+#pragma unroll
+  for (int v4 = 0; v4 < 4; ++v4) {
+    const uint32_t w[4] = {mk[v4].x, mk[v4].y, mk[v4].z, mk[v4].w};
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const uint32_t m = __vcmpgts2(w[p], 0u);                       // 0xFFFF per halfword that is > 0
+      r[v4 * 8 + 2 * p] &= (uint32_t)((int32_t)(m << 16) >> 31);
+      r[v4 * 8 + 2 * p + 1] &= (uint32_t)((int32_t)m >> 31);
+    }
+  }
+}
+// 64 B of row `my_m` of the mask starting at column nc (columns >= N read as "keep")
+__device__ __forceinline__ void load_mask32(uint4 (&mk)[4], const uint16_t* mask, int64_t ldmask, int my_m, bool row_ok, int nc, int N) {
+#pragma unroll
+  for (int v4 = 0; v4 < 4; ++v4) {
+    mk[v4] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    if (row_ok && nc + v4 * 8 + 8 <= N)
+      mk[v4] = __ldg(reinterpret_cast<const uint4*>(mask + (int64_t)my_m * ldmask + nc) + v4);
+    else if (row_ok && nc + v4 * 8 < N) {   // ragged tail: element-wise
+      uint32_t w[4] = {0, 0, 0, 0};
+      for (int e = 0; e < 8 && nc + v4 * 8 + e < N; ++e)
+        w[e >> 1] |= (uint32_t)__ldg(mask + (int64_t)my_m * ldmask + nc + v4 * 8 + e) << ((e & 1) * 16);
+      mk[v4] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __restrict__ prefix, int n_problems, int total_tiles,
                         const int32_t* __restrict__ tile_order, const int32_t* __restrict__ pair_start,
@@ -101,12 +149,13 @@ gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __res
   unsigned char* sA = smem;
   unsigned char* sB = smem + T2_STAGES * T2_A_BYTES;
   unsigned char* sOut = smem + T2_STAGES * (T2_A_BYTES + T2_B_BYTES);
-  unsigned char* sOnes = sOut + T2_EPI_WARPS * T2_OUT_BUFS * T2_OUT_BUF_BYTES;
+  unsigned char* sOnes = sOut + T2_EPI_WARPS * T2_OUT_BUF_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sOnes + T2_ONES_BYTES);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * T2_STAGES + 2 * T2_ACC_STAGES);
-  float* bias_s = reinterpret_cast<float*>(sOnes + T2_ONES_BYTES + 256);             // [EPI_WARPS][128]
-  int32_t* s_prefix = reinterpret_cast<int32_t*>(bias_s + T2_EPI_WARPS * 128);
+  float* bias_s = reinterpret_cast<float*>(sOnes + T2_ONES_BYTES + 256);             // [EPI_WARPS][64]
+  int32_t* s_prefix = reinterpret_cast<int32_t*>(bias_s + T2_EPI_WARPS * 64);
   int32_t* s_tiles_n = s_prefix + T2_MAX_PROBLEMS + 1;
+  Tc2Meta* s_meta = reinterpret_cast<Tc2Meta*>(s_tiles_n + T2_MAX_PROBLEMS + 1);     // 8-byte aligned (offsets above are)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();               // 0 = leader (issues the MMAs)
@@ -116,7 +165,19 @@ gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __res
 
   for (int i = threadIdx.x; i < T2_ONES_BYTES / 4; i += T2_THREADS) reinterpret_cast<uint32_t*>(sOnes)[i] = 0x3F803F80u;
   for (int i = threadIdx.x; i <= n_problems; i += T2_THREADS) s_prefix[i] = prefix[i];
-  for (int i = threadIdx.x; i < n_problems; i += T2_THREADS) s_tiles_n[i] = recs[i].tiles_n;
+  for (int i = threadIdx.x; i < n_problems; i += T2_THREADS) {
+    const Tc2Record* R = recs + i;
+    s_tiles_n[i] = R->tiles_n;
+    Tc2Meta m;
+    m.bias = R->bias; m.mask = R->mask; m.ldmask = R->ldmask; m.rowsum_a = R->rowsum_a;
+    m.M = R->M; m.N = R->N; m.K = R->K; m.act = R->act; m.accumulate = R->accumulate;
+    m.a_mn = R->a_mn; m.b_mn = R->b_mn; m.has_f32 = R->has_f32; m.has_bf16 = R->has_bf16;
+    m.bn = R->bn; m.rowsum_col = R->rowsum_col; m.pad_ = 0;
+    m.bits_out = R->bits_out; m.mask_bits = R->mask_bits;
+    m.bits_out_chunks = R->bits_out_chunks; m.bits_out_chunk0 = R->bits_out_chunk0;
+    m.mask_bits_chunks = R->mask_bits_chunks; m.mask_bits_chunk0 = R->mask_bits_chunk0;
+    s_meta[i] = m;
+  }
   if (threadIdx.x == 0) {
     // full: one arrive (the leader's expect_tx) + the bytes of both CTAs; empty / tmem_full: one multicast commit;
     // tmem_empty (used on the leader only): every epilogue warp of both CTAs
@@ -138,6 +199,8 @@ gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __res
   const int sched_begin = tile_order ? pair_start[pair] : pair;
   const int sched_end = tile_order ? pair_start[pair + 1] : total_tiles;
   const int sched_step = tile_order ? 1 : n_pairs;
+  const bool stamp = dbg != nullptr && blockIdx.x == 0;   // per-tile clock64 stamps of CTA 0: dbg[tile_iter * 16 + slot]
+#define T2_STAMP(iter, slot) do { if (stamp && (iter) < 64) dbg[(iter) * 16 + (slot)] = clock64(); } while (0)
 #define T2_CTA_STAMP(slot) do { if (dbg != nullptr) { unsigned long long gt_; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_)); \
                                   dbg[1024 + blockIdx.x * 8 + (slot)] = (long long)gt_; } } while (0)
   if (threadIdx.x == 0) { T2_CTA_STAMP(0); if (dbg != nullptr) dbg[1024 + blockIdx.x * 8 + 4] = (sched_end - sched_begin + sched_step - 1) / sched_step; }
@@ -146,11 +209,16 @@ gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __res
     // ===================== TMA producer (both CTAs) =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int ti = sched_begin; ti < sched_end; ti += sched_step) {
+      int pit = 0;
+      for (int ti = sched_begin; ti < sched_end; ti += sched_step, ++pit) {
         const int t = tile_order ? __ldg(tile_order + ti) : ti;
+        T2_STAMP(pit, 0);
         const TileCoord tc = locate_tile(t, s_prefix, s_tiles_n, n_problems);
         const Tc2Record* R = recs + tc.pi;
-        const int K = R->K, a_mn = R->a_mn, b_mn = R->b_mn, bn = R->bn;
+        const Tc2Meta& mt = s_meta[tc.pi];
+        const int K = mt.K, a_mn = mt.a_mn, b_mn = mt.b_mn, bn = mt.bn;
+        if (stamp && pit < 64) dbg[pit * 16 + 1] = ((long long)tc.pi << 32) | (long long)((K + 63) / 64);
+        if (pit == 0) { tma_prefetch_desc(&R->tmA); tma_prefetch_desc(&R->tmB); }
         const int half_n = bn >> 1;
         const int m0 = tc.tm * 256 + (int)rank * T2_BM;             // this CTA's rows of A
         const int n0 = tc.tn * bn + (int)rank * half_n;             // this CTA's rows of B
@@ -176,6 +244,7 @@ gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __res
           }
           if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
         }
+        T2_STAMP(pit, 3);
         const int tn_i = ti + sched_step;
         if (tn_i < sched_end) {
           const int t2 = tile_order ? __ldg(tile_order + tn_i) : tn_i;
@@ -191,24 +260,29 @@ gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __res
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       const uint64_t ones_desc = make_smem_desc(smem_u32(sOnes), false);
+      int mit = -1;
       for (int ti = sched_begin; ti < sched_end; ti += sched_step) {
+        ++mit;
         const int t = tile_order ? __ldg(tile_order + ti) : ti;
         const TileCoord tc = locate_tile(t, s_prefix, s_tiles_n, n_problems);
-        const Tc2Record* R = recs + tc.pi;
-        const int K = R->K, bn = R->bn;
-        const bool a_mn = R->a_mn != 0, b_mn = R->b_mn != 0;
-        const bool rowsum = (R->rowsum_a != nullptr) && tc.tn == 0;
-        const int rowsum_col = R->rowsum_col;
+        const Tc2Meta& mt = s_meta[tc.pi];
+        const int K = mt.K, bn = mt.bn;
+        const bool a_mn = mt.a_mn != 0, b_mn = mt.b_mn != 0;
+        const bool rowsum = (mt.rowsum_a != nullptr) && tc.tn == 0;
+        const int rowsum_col = mt.rowsum_col;
         const bool rowsum_shared = rowsum_col < bn;      // the row sums live in unused columns of the main accumulator
         const uint32_t idesc = make_idesc(256, bn, a_mn, b_mn);
         const uint32_t idesc_ones = make_idesc(256, 16, a_mn, false);
         const int num_kb = (K + T2_BK - 1) / T2_BK;
+        T2_STAMP(mit, 4);
         mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
+        T2_STAMP(mit, 5);
         const uint32_t d_tmem = tmem_base + acc * T2_ACC_COLS;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(full_bar + 8 * stage, phase);
           tc_fence_after();
+          if (kb == 0) T2_STAMP(mit, 6);
           const uint32_t a_addr = smem_u32(sA + stage * T2_A_BYTES), b_addr = smem_u32(sB + stage * T2_B_BYTES);
           const uint64_t a_desc = make_smem_desc(a_addr, a_mn), b_desc = make_smem_desc(b_addr, b_mn);
           const uint64_t a_step = a_mn ? (2048 >> 4) : (32 >> 4), b_step = b_mn ? (2048 >> 4) : (32 >> 4);
@@ -227,142 +301,164 @@ gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __res
           if (++stage == T2_STAGES) { stage = 0; phase ^= 1; }
         }
         tc2_commit(tfull_bar + 8 * acc);                 // accumulator ready, both CTAs
+        T2_STAMP(mit, 7);
         if (++acc == T2_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
       }
       T2_CTA_STAMP(2);
     }
   } else {
-    // ===================== epilogue (warps 2..9, both CTAs) =====================
-    // warp -> TMEM lane quarter q (rows 32q.. of this CTA's 128) and column half (BN/2 columns = BN/128 groups of
-    // 64 columns).  Per 64-column group the flow is the one of gemm_tc.cu.
+    // ===================== epilogue (warps 2..17, both CTAs) =====================
+    // warp -> TMEM lane quarter q (rows 32q.. of this CTA's 128) and column quarter (BN/4 columns = one or two
+    // 32-column chunks).  Per chunk: tcgen05.ld (thread = row) -> ReLU mask / bias / activation in registers ->
+    // 128B-swizzled staging box (conflict-free 16-byte stores) -> one bulk tensor store (or .add reduction) by lane 0.
+    // The mask of the next chunk and the bias / first mask chunk of the NEXT tile are fetched while the current
+    // chunk is being processed, so no global latency sits between the accumulator becoming ready and the store.
     const int q = warp & 3;
     const int ew = warp - 2;
-    const int half = ew >> 2;
-    float* bias_w = bias_s + ew * 128;
+    const int cq = ew >> 2;                                     // column quarter
+    float* bias_w = bias_s + ew * 64;
     const uint32_t bias_addr = smem_u32(bias_w);
-    const uint32_t out_base = smem_u32(sOut + ew * T2_OUT_BUFS * T2_OUT_BUF_BYTES);
+    const uint32_t buf = smem_u32(sOut + ew * T2_OUT_BUF_BYTES);
     const uint32_t row_off = (uint32_t)lane * 128u;
     const uint32_t sw = (uint32_t)(lane & 7);
     int acc = 0; uint32_t acc_phase = 0;
-    uint32_t buf_i = 0;
+    int it = -1;
+    const bool estamp = stamp && ew == 0 && lane == 0;
+    // per-tile state that is prefetched one tile ahead
+    TileCoord tc{0, 0, 0};
+    float bv0 = 0.f, bv1 = 0.f;
+    uint32_t mbits0 = 0xFFFFFFFFu, mbits1 = 0xFFFFFFFFu;       // ReLU bit words of this row for the warp's two chunks
+    auto prefetch_tile = [&](int ti_) {
+      const int t_ = tile_order ? __ldg(tile_order + ti_) : ti_;
+      tc = locate_tile(t_, s_prefix, s_tiles_n, n_problems);
+      const Tc2Meta& m_ = s_meta[tc.pi];
+      const int nf = tc.tn * m_.bn + cq * 64;
+      const bool active_ = cq * 64 < m_.bn;
+      bv0 = (active_ && m_.bias != nullptr && nf + lane < m_.N) ? __ldg(m_.bias + nf + lane) : 0.f;
+      bv1 = (active_ && m_.bias != nullptr && nf + 32 + lane < m_.N) ? __ldg(m_.bias + nf + 32 + lane) : 0.f;
+      const int mm = tc.tm * 256 + (int)rank * T2_BM + q * 32 + lane;
+      if (active_ && m_.mask_bits != nullptr) {
+        // one coalesced 128-byte read per chunk: the words of the warp's 32 rows are adjacent
+        const int64_t w0 = ((int64_t)(mm >> 5) * m_.mask_bits_chunks + m_.mask_bits_chunk0 + (nf >> 5)) * 32 + (mm & 31);
+        mbits0 = (mm < m_.M && nf < m_.N) ? __ldg(m_.mask_bits + w0) : 0u;
+        mbits1 = (mm < m_.M && nf + 32 < m_.N) ? __ldg(m_.mask_bits + w0 + 32) : 0u;
+      }
+    };
+    if (sched_begin < sched_end) prefetch_tile(sched_begin);
     for (int ti = sched_begin; ti < sched_end; ti += sched_step) {
-      const int t = tile_order ? __ldg(tile_order + ti) : ti;
-      const TileCoord tc = locate_tile(t, s_prefix, s_tiles_n, n_problems);
+      ++it;
+      if (estamp && it < 64) dbg[it * 16 + 8] = clock64();
       const Tc2Record* R = recs + tc.pi;
-      const int M = R->M, N = R->N, bn = R->bn;
-      const int groups = bn >> 7;                               // 64-column groups per warp: 2 (BN=256) or 1
+      const Tc2Meta& mt = s_meta[tc.pi];
+      const int M = mt.M, N = mt.N, bn = mt.bn;
+      // a warp owns 64 columns (one bf16 store box); with BN = 128 the warps of column quarters 2 and 3 have none
+      const int nchunks = (cq * 64 < bn) ? 2 : 0;
       const int m_base = tc.tm * 256 + (int)rank * T2_BM + q * 32;
-      const int col0 = half * (bn >> 1);                        // first accumulator column of this warp
+      const int col0 = cq * 64;                                 // first accumulator column of this warp
       const int n_first = tc.tn * bn + col0;
-      const bool has_f32 = R->has_f32 != 0, has_bf16 = R->has_bf16 != 0;
-      const float* const bias = R->bias;
-      const uint16_t* const mask = R->mask; const int64_t ldmask = R->ldmask;
-      const int act = R->act, accumulate = R->accumulate;
-      float* const rowsum_out = (tc.tn == 0 && half == 0) ? R->rowsum_a : nullptr;
-      const int rowsum_col = R->rowsum_col;
+      const bool has_f32 = mt.has_f32 != 0, has_bf16 = mt.has_bf16 != 0;
+      const uint32_t* const mask_bits = mt.mask_bits;
+      const uint16_t* const mask = mask_bits != nullptr ? nullptr : mt.mask; const int64_t ldmask = mt.ldmask;
+      uint32_t* const bits_out = mt.bits_out;
+      const uint32_t mb[2] = {mbits0, mbits1};
+      const int act = mt.act, accumulate = mt.accumulate;
+      float* const rowsum_out = (tc.tn == 0 && cq == 0) ? mt.rowsum_a : nullptr;
+      const int rowsum_col = mt.rowsum_col;
       const int my_m = m_base + lane;
       const bool row_ok = my_m < M;
-      const bool rows_any = m_base < M;
-      if (lane == 0) {
-        if (has_f32) tma_prefetch_desc(&R->tmC32);
-        if (has_bf16) tma_prefetch_desc(&R->tmC16);
-      }
+      const bool rows_any = m_base < M && nchunks > 0;
       __syncwarp();                                            // the previous tile's reads of the bias slot are done
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int cn = n_first + j * 32 + lane;
-        bias_w[j * 32 + lane] = (bias != nullptr && j * 32 < (bn >> 1) && cn < N) ? __ldg(bias + cn) : 0.f;
-      }
+      bias_w[lane] = bv0;
+      bias_w[32 + lane] = bv1;
       __syncwarp();
+      if (estamp && it < 64) dbg[it * 16 + 9] = clock64();
       mbar_wait(tfull_bar + 8 * acc, acc_phase);
       tc_fence_after();
+      if (estamp && it < 64) dbg[it * 16 + 10] = clock64();
       const uint32_t t_row = tmem_base + acc * T2_ACC_COLS + ((uint32_t)(q * 32) << 16);
-      if (rowsum_out != nullptr) {
-        uint32_t rs;
-        tc_ld1(t_row + rowsum_col, rs);
-        tc_wait_ld();
-        if (row_ok) rowsum_out[my_m] = __uint_as_float(rs);
-      }
-      for (int g = 0; g < groups; ++g) {
-        const int n0 = n_first + g * 64;
-        const bool c_ok[2] = {rows_any && n0 < N, rows_any && n0 + 32 < N};   // warp-uniform
-        uint4 mk[2][4];
-        if (mask != nullptr) {
+      uint32_t rs = 0;
+      if (rowsum_out != nullptr) tc_ld1(t_row + rowsum_col, rs);
+      const bool first_ok = rows_any && n_first < N;
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            const int nc = n0 + c * 32;
-#pragma unroll
-            for (int v4 = 0; v4 < 4; ++v4) {
-              mk[c][v4] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
-              if (row_ok && nc + v4 * 8 + 8 <= N)
-                mk[c][v4] = __ldg(reinterpret_cast<const uint4*>(mask + (int64_t)my_m * ldmask + nc) + v4);
-              else if (row_ok && nc + v4 * 8 < N) {
-                uint32_t w[4] = {0, 0, 0, 0};
-                for (int e = 0; e < 8 && nc + v4 * 8 + e < N; ++e)
-                  w[e >> 1] |= (uint32_t)mask[(int64_t)my_m * ldmask + nc + v4 * 8 + e] << ((e & 1) * 16);
-                mk[c][v4] = make_uint4(w[0], w[1], w[2], w[3]);
-              }
-            }
-          }
-        }
-        uint32_t r0[32], r1[32];
-        if (c_ok[0]) tc_ld32(t_row + col0 + g * 64, r0);
-        if (c_ok[1]) tc_ld32(t_row + col0 + g * 64 + 32, r1);
+      for (int c = 0; c < 2; ++c) {
+        if (c >= nchunks) break;
+        const int nc = n_first + c * 32;
+        const bool c_ok = rows_any && nc < N;                  // warp-uniform
+        uint32_t r[32];
+        if (c_ok) tc_ld32(t_row + col0 + c * 32, r);
         tc_wait_ld();
-        if (g == groups - 1) {
+        if (c == 1) {
           // the accumulator stage is free once this warp's last values sit in registers: tell the leader
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive_cluster(tempty_bar + 8 * acc, 0);
+          if (estamp && it < 64) dbg[it * 16 + 12] = clock64();
+          if (rowsum_out != nullptr && row_ok) rowsum_out[my_m] = __uint_as_float(rs);
         }
-        uint32_t packed[2][16];
+        if (!c_ok) continue;
+        if (mask_bits != nullptr) {
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          if (!c_ok[c]) continue;
-          uint32_t (&r)[32] = c == 0 ? r0 : r1;
-          epilogue_math(r, mk[c], mask != nullptr, bias_addr + (uint32_t)(g * 64 + c * 32) * 4u, act);
-          if (has_bf16) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) packed[c][j] = pack_bf16x2(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
-          }
-          if (has_f32) {
-            if (lane == 0) bulk_wait_read<T2_OUT_BUFS - 1>();
-            __syncwarp();
-            const uint32_t buf = out_base + (buf_i & (T2_OUT_BUFS - 1)) * T2_OUT_BUF_BYTES;
-            ++buf_i;
-#pragma unroll
-            for (int c16 = 0; c16 < 8; ++c16)
-              st_shared_v4(buf + row_off + (((uint32_t)c16 ^ sw) << 4), r[4 * c16], r[4 * c16 + 1], r[4 * c16 + 2], r[4 * c16 + 3]);
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) {
-              if (accumulate) tma_reduce_add_2d(&R->tmC32, buf, n0 + c * 32, m_base);
-              else tma_store_2d(&R->tmC32, buf, n0 + c * 32, m_base);
-              bulk_commit();
-            }
-          }
+          for (int j = 0; j < 32; ++j) r[j] = (mb[c] >> j) & 1u ? r[j] : 0u;
+        } else if (mask != nullptr) {   // bf16 mask (no bit array for this activation): loaded at use
+          uint4 mk[4];
+          load_mask32(mk, mask, ldmask, my_m, row_ok, nc, N);
+          apply_mask32(r, mk);
         }
-        if (has_bf16 && c_ok[0]) {
-          if (lane == 0) bulk_wait_read<T2_OUT_BUFS - 1>();
+        {
+          uint4 unused[4];
+          epilogue_math(r, unused, false, bias_addr + (uint32_t)c * 128u, act);
+        }
+        if (bits_out != nullptr && row_ok) {
+          // "output > 0" of this row's 32 columns as one word (a float is > 0 iff its bits, read as int32, are > 0)
+          uint32_t w = 0;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) w |= ((int32_t)r[j] > 0 ? 1u : 0u) << j;
+          bits_out[((int64_t)(my_m >> 5) * mt.bits_out_chunks + mt.bits_out_chunk0 + (nc >> 5)) * 32 + (my_m & 31)] = w;
+        }
+        if (has_f32) {
+          if (lane == 0) bulk_wait_read<0>();                  // the staging box of the previous store has been read
           __syncwarp();
-          const uint32_t buf = out_base + (buf_i & (T2_OUT_BUFS - 1)) * T2_OUT_BUF_BYTES;
-          ++buf_i;
 #pragma unroll
-          for (int c = 0; c < 2; ++c) {
-            if (!c_ok[c]) continue;
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-              st_shared_v4(buf + row_off + (((uint32_t)(4 * c + i) ^ sw) << 4), packed[c][4 * i], packed[c][4 * i + 1],
-                           packed[c][4 * i + 2], packed[c][4 * i + 3]);
-          }
+          for (int c16 = 0; c16 < 8; ++c16)
+            st_shared_v4(buf + row_off + (((uint32_t)c16 ^ sw) << 4), r[4 * c16], r[4 * c16 + 1], r[4 * c16 + 2], r[4 * c16 + 3]);
           fence_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&R->tmC16, buf, n0, m_base);
+            if (accumulate) tma_reduce_add_2d(&R->tmC32, buf, nc, m_base);
+            else tma_store_2d(&R->tmC32, buf, nc, m_base);
             bulk_commit();
           }
+        } else {   // bf16 only: the chunk goes straight into its half of the 64-column box
+          if (c == 0) {
+            if (lane == 0) bulk_wait_read<0>();
+            __syncwarp();
+          }
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            st_shared_v4(buf + row_off + (((uint32_t)(4 * c + i) ^ sw) << 4),
+                         pack_bf16x2(__uint_as_float(r[8 * i]), __uint_as_float(r[8 * i + 1])),
+                         pack_bf16x2(__uint_as_float(r[8 * i + 2]), __uint_as_float(r[8 * i + 3])),
+                         pack_bf16x2(__uint_as_float(r[8 * i + 4]), __uint_as_float(r[8 * i + 5])),
+                         pack_bf16x2(__uint_as_float(r[8 * i + 6]), __uint_as_float(r[8 * i + 7])));
         }
       }
+      if (nchunks == 0) {                                      // a warp without columns only hands the stage back
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(tempty_bar + 8 * acc, 0);
+      }
+      // next tile's bias / first mask chunk: in flight while the bf16 box leaves and while waiting for its accumulator
+      const int m_base_cur = m_base, n_first_cur = n_first;
+      if (ti + sched_step < sched_end) prefetch_tile(ti + sched_step);
+      if (has_bf16 && first_ok) {
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&R->tmC16, buf, n_first_cur, m_base_cur);
+          bulk_commit();
+        }
+      }
+      if (estamp && it < 64) dbg[it * 16 + 11] = clock64();
       if (++acc == T2_ACC_STAGES) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) bulk_wait_all();
@@ -404,8 +500,8 @@ extern "C" int mmlrec_tc2_encode_problem(const MmlrecGemmTcDesc* d, void* record
   MMLREC_CHECK_ARG(d->C_f32 == nullptr || ((d->ldc_f32 & 3) == 0 && ((uintptr_t)d->C_f32 & 15) == 0), "C_f32 alignment");
   MMLREC_CHECK_ARG(d->C_bf16 == nullptr || ((d->ldc_bf16 & 7) == 0 && ((uintptr_t)d->C_bf16 & 15) == 0), "C_bf16 alignment");
   MMLREC_CHECK_ARG(d->mask == nullptr || ((d->ldmask & 7) == 0 && ((uintptr_t)d->mask & 15) == 0), "mask alignment");
-  MMLREC_CHECK_ARG(d->C_f32 || d->C_bf16, "no output");
-  MMLREC_CHECK_ARG(!(d->accumulate && d->C_bf16), "accumulate applies to an fp32-only output (the sum is formed in memory)");
+  MMLREC_CHECK_ARG((d->C_f32 != nullptr) != (d->C_bf16 != nullptr),
+                   "the CTA-pair kernel writes one output precision per problem (list the problem twice for both)");
   Tc2Record rec;
   memset(&rec, 0, sizeof(rec));
   const int bn = tc2_pick_bn(d);
@@ -430,6 +526,10 @@ extern "C" int mmlrec_tc2_encode_problem(const MmlrecGemmTcDesc* d, void* record
   rec.M = d->M; rec.N = d->N; rec.K = d->K; rec.act = d->act; rec.accumulate = d->accumulate;
   rec.a_mn = d->a_mn_major; rec.b_mn = d->b_mn_major; rec.bn = bn; rec.tiles_n = cdiv(d->N, bn);
   rec.rowsum_col = bn == 128 ? 128 : 240;
+  rec.bits_out = d->relu_bits_out; rec.bits_out_chunks = d->bits_out_chunks; rec.bits_out_chunk0 = d->bits_out_chunk0;
+  rec.mask_bits = d->mask_bits; rec.mask_bits_chunks = d->mask_bits_chunks; rec.mask_bits_chunk0 = d->mask_bits_chunk0;
+  MMLREC_CHECK_ARG(d->relu_bits_out == nullptr || d->bits_out_chunks > 0, "bits_out_chunks");
+  MMLREC_CHECK_ARG(d->mask_bits == nullptr || d->mask_bits_chunks > 0, "mask_bits_chunks");
   memcpy(record_host, &rec, sizeof(rec));
   return 0;
 }

@@ -39,6 +39,9 @@ class ActGroup:
         self.act = act if act is not None else ("relu" if relu else None)   # activation that produced the values
         self.need_f32 = self.need_bf16 = False
         self.need_grad = True
+        self.want_bits = False      # a tensor-core dgrad wants this (ReLU) activation as a 1-bit mask
+        self.bits = None            # int32 [ceil(B/32), chunks, 32]: layout of MmlrecGemmTcDesc.relu_bits_out
+        self.bits_written = False   # set by the producing stage when its GEMM epilogue really emits the bits
         self.buf = self.buf16 = self.gbuf = self.gbuf16 = None
         self.acts: List["Act"] = []
         at = 0
@@ -54,6 +57,9 @@ class ActGroup:
             self.buf = b.zeros(b.B, _align(self.total, 4))
         if self.need_bf16:
             self.buf16 = b.zeros(b.B, _align(self.total, 8), dtype=torch.bfloat16)
+        if self.want_bits and self.need_grad and all(a.col % 32 == 0 for a in self.acts):
+            self.bits_chunks = (self.total + 31) // 32
+            self.bits = b.zeros((b.B + 31) // 32 * self.bits_chunks * 32, dtype=torch.int32)
         if self.need_grad:
             if self.grad_dtype == "f32":
                 self.gbuf = b.zeros(b.B, _align(self.total, 4))
@@ -159,6 +165,8 @@ class Builder:
         """Encode tensor-core problems (tensor maps built on the host) -> launch tuple
         (records, prefix, n, tiles, tile order, per-unit starts, units); a unit is a CTA or a CTA pair."""
         pairs = self.tc_kernel == 2
+        if pairs:
+            descs = L.split_two_output_problems(descs)
         rb = int(self.lib.mmlrec_tc2_record_bytes() if pairs else self.lib.mmlrec_tc_record_bytes())
         host = (C.c_uint8 * (rb * len(descs)))()
         pre, at = [0], 0
@@ -474,6 +482,8 @@ class LinearStage(Stage):
             self.zs[0].want(f32=True)
         for s in specs:
             s.x.want(f32=not b.tc, bf16=b.tc)
+            if b.tc and b.tc_kernel == 2 and s.x.relu:
+                s.x.group.want_bits = True   # dgrad through the producer's ReLU reads 1 bit per element, not the bf16 value
 
     # ---- forward tables
     def finalize(self):
@@ -545,6 +555,9 @@ class LinearStage(Stage):
                         d.C_bf16, d.ldc_bf16 = tgt.buf16.data_ptr() + 2 * col, tgt.buf16.stride(0)
                     d.bias = (g.b.data_ptr() + 4 * off) if g.b is not None else None
                     d.act = act_code
+                    if tgt.bits is not None and self.act == "relu" and not self.use_bn and col % 32 == 0:
+                        d.relu_bits_out, d.bits_out_chunks, d.bits_out_chunk0 = tgt.bits.data_ptr(), tgt.bits_chunks, col // 32
+                        tgt.bits_written = True
                     descs.append(d)
             self.fwd = self._tc_tables(descs)
         if self.use_bn:
@@ -587,19 +600,26 @@ class LinearStage(Stage):
         b, st = self.b, self.b.store
         self.live_groups: List[_Group] = []
         waves: List[list] = [[]]
-        # deterministic split-K of the wgrad problems (tensor-core mode): 1024 samples per slice, at most 4 slices
-        # -- only where the launch would otherwise be a handful of very long tiles (e.g. the towers: 4 tiles of 64
-        # k-blocks -> 33 us; split 4 ways 16 us + 4 us sum).  With tens of wgrad tiles the extra partial-tile
-        # epilogues cost more than the shorter critical path saves (measured, profiles/splitk_r01.txt).
+        # deterministic split-K of the wgrad problems (tensor-core mode): the contraction runs over the batch, so an
+        # unsplit tile is B/64 k-blocks long while the launch has only a handful of them -- far fewer than SMs.  The batch
+        # is cut into S slices; every slice is its own problem that writes its partial tile into gradient slice k of the
+        # flat store (one bulk tensor store per box: a partial tile costs little) and the dense optimizer adds the
+        # slices up in slice order -- no reduction pass, no atomics.  Kernel 1 (one CTA per tile) keeps the old rule:
+        # only launches with a handful of tiles are split.  Derived weights (STAR) are consumed by a fold kernel that
+        # reads slice 0 only, so their stages are not split.
         self.split_k = 1
-        if b.tc and b.B % 1024 == 0:
-            wg_tiles = sum(((g.N + 127) // 128) * ((g.K + 127) // 128)
-                           for g in self.groups if any(o.grad_written for o in g.outs))
-            for cand in (4, 2):
-                if cand <= b.B // 1024 and 0 < wg_tiles * cand <= 32:
-                    self.split_k = cand
-                    break
-        split_segments, split_descs, split_at = [], [], 0
+        derived = any(g.W._mm_off >= st.aux_base for g in self.groups)
+        if b.tc and b.B % 1024 == 0 and b.B >= 2048 and not derived:
+            if b.tc_kernel == 2:
+                self.split_k = min(b.B // 1024, st.max_grad_slices)
+            else:
+                wg_tiles = sum(((g.N + 127) // 128) * ((g.K + 127) // 128)
+                               for g in self.groups if any(o.grad_written for o in g.outs))
+                for cand in (4, 2):
+                    if cand <= min(b.B // 1024, st.max_grad_slices) and 0 < wg_tiles * cand <= 32:
+                        self.split_k = cand
+                        break
+        self.zero_before_bwd = []   # gradient buffers a K-split dgrad accumulates into from zero
         dzg = self.zs[0].group if self.use_bn else self.outs[0].group   # where dZ lives
         for g in self.groups:
             if not any(o.grad_written for o in g.outs):
@@ -636,29 +656,16 @@ class LinearStage(Stage):
                     waves[wave].append(q)
             else:
                 dz16, dz_ld = dzg.gbuf16.data_ptr() + 2 * g.y_col, dzg.gbuf16.stride(0)
-                # wgrad: both operands MN-major (no transposed copies).  The contraction runs over the batch, so a
-                # tile is B/64 k-blocks long; it is split into S batch slices whose partial tiles go to scratch
-                # slices and are summed in a fixed order afterwards (deterministic split-K)
+                # wgrad: both operands MN-major (no transposed copies); batch slice k -> gradient slice k
                 S = self.split_k
-                w_span = g.N * g.W._mm_ld
-                w_at, b_at = split_at, split_at + w_span
-                if S > 1:
-                    split_segments.append((g.W._mm_off, w_at, w_span))
-                    if g.b is not None:
-                        split_segments.append((g.b._mm_off, b_at, g.N))
-                    split_at = _align(b_at + (g.N if g.b is not None else 0), 8)
                 for k in range(S):
                     rows = b.B // S
                     d = L.GemmTcDesc()
                     d.A, d.lda, d.a_mn_major = dz16 + 2 * k * rows * dz_ld, dz_ld, 1
                     d.B, d.ldb, d.b_mn_major = x.ptr16 + 2 * k * rows * x.ld16, x.ld16, 1
                     d.M, d.N, d.K = g.N, g.K, rows
-                    if S > 1:   # scratch pointers are filled in once the slice size is known
-                        d.ldc_f32 = g.W._mm_ld
-                        split_descs.append((d, k, w_at, b_at if g.b is not None else None))
-                    else:
-                        d.C_f32, d.ldc_f32 = st.grad_ptr(g.W), g.W._mm_ld
-                        d.colsum = st.grad_ptr(g.b) if g.b is not None else None
+                    d.C_f32, d.ldc_f32 = st.grad_ptr(g.W) + 4 * k * st.slice_stride, g.W._mm_ld
+                    d.colsum = (st.grad_ptr(g.b) + 4 * k * st.slice_stride) if g.b is not None else None
                     waves[0].append(d)
                 if want_dx:
                     e = L.GemmTcDesc()   # dgrad: A = dZ (K-major), B = W read MN-major
@@ -673,21 +680,28 @@ class LinearStage(Stage):
                         e.C_bf16, e.ldc_bf16 = x.gptr, x.gld
                     if x.relu:
                         e.mask, e.ldmask = x.ptr16, x.ld16
-                    waves[wave].append(e)
+                        xg = x.group
+                        if xg.bits is not None and xg.bits_written and x.col % 32 == 0:
+                            e.mask_bits, e.mask_bits_chunks, e.mask_bits_chunk0 = xg.bits.data_ptr(), xg.bits_chunks, x.col // 32
+                    if (b.tc_kernel == 2 and g.N >= 2048 and x.grad_is_f32 and not accumulate
+                            and x.width == x.group.total):
+                        # a very long contraction (K = the merged layer width) on a few tiles: two K halves as two
+                        # problems that ADD into the zeroed gradient buffer (0 + a + b is order-independent: deterministic)
+                        self.zero_before_bwd.append(x.group.gbuf)
+                        h0 = (g.N // 2 + 63) // 64 * 64
+                        for k0, kn in ((0, h0), (h0, g.N - h0)):
+                            e2 = L.GemmTcDesc()
+                            e2.A, e2.lda, e2.a_mn_major = dz16 + 2 * k0, dz_ld, 0
+                            e2.B, e2.ldb, e2.b_mn_major = st.bf16_ptr(g.W) + 2 * k0 * g.W._mm_ld, g.W._mm_ld, 1
+                            e2.M, e2.N, e2.K = b.B, g.K, kn
+                            e2.C_f32, e2.ldc_f32, e2.accumulate = x.gptr, x.gld, 1
+                            e2.mask, e2.ldmask = e.mask, e.ldmask
+                            e2.mask_bits, e2.mask_bits_chunks, e2.mask_bits_chunk0 = e.mask_bits, e.mask_bits_chunks, e.mask_bits_chunk0
+                            waves[wave].append(e2)
+                    else:
+                        waves[wave].append(e)
             if want_dx:
                 x.grad_written = True
-        self.split_sum = None
-        if split_descs:
-            slice_floats = _align(split_at, 8)
-            self.split_scratch = b.zeros(self.split_k * slice_floats)
-            base = self.split_scratch.data_ptr()
-            for d, k, w_at, b_at in split_descs:
-                d.C_f32 = base + 4 * (k * slice_floats + w_at)
-                if b_at is not None:
-                    d.colsum = base + 4 * (k * slice_floats + b_at)
-            seg = [v for t in split_segments for v in t]
-            self.split_sum = (b.ints(seg, dtype=torch.int64), len(split_segments), max(t[2] for t in split_segments),
-                              slice_floats)
         self.bwd = []
         for wv in waves:
             if not wv:
@@ -712,13 +726,10 @@ class LinearStage(Stage):
                     (zg.gbuf16.data_ptr() + 2 * c) if zg.gbuf16 is not None else None,
                     zg.gbuf16.stride(0) if zg.gbuf16 is not None else 0,
                     b.store.grad_ptr(bn0.weight), b.store.grad_ptr(bn0.bias), stream), f"bn bwd {self.label}")
+        for buf in self.zero_before_bwd:
+            L.check(b.lib.mmlrec_fill_f32(buf.data_ptr(), buf.numel(), 0.0, stream), f"zero d(input) {self.label}")
         for tbl in self.bwd:
             self._launch(tbl, stream, "linear bwd")
-        if self.split_sum is not None:
-            seg, n_seg, max_n, slice_floats = self.split_sum
-            L.check(b.lib.mmlrec_sum_slices(seg.data_ptr(), n_seg, max_n, b.store.dense_grad.data_ptr(),
-                                            self.split_scratch.data_ptr(), self.split_k, slice_floats, stream),
-                    f"split-K sum {self.label}")
 
 
 def mlp_stages(b: Builder, items: Sequence[Tuple[Act, nn.Module]], label: str) -> List[Act]:
@@ -1208,6 +1219,9 @@ class StepPlan:
         self.heads: HeadStage = next(s for s in self.stages if isinstance(s, HeadStage))
         for s in reversed(self.stages):
             s.plan_backward()
+        # gradient slices this program writes (split-K wgrad, see LinearStage.plan_backward)
+        self.grad_slices = max([getattr(s, "split_k", 1) for s in self.stages] + [1])
+        self.fold_seg = self.b.ints([0, 0, model.store.slice_stride], dtype=torch.int64)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.side = torch.cuda.Stream(device=model.device_obj)
         self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
@@ -1259,22 +1273,31 @@ class StepPlan:
         st = m.store
         p = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
 
-        def dense_step():
-            L.check(lib.mmlrec_dense_optimizer_step(st.dense.data_ptr(), st.dense_grad.data_ptr(), p(st.dense_s1),
-                                                    p(st.dense_s2), st.n_dense, m.hyper_dev.data_ptr(), p(st.dense_bf16),
-                                                    stream), "dense_optimizer_step")
+        def dense_step(n_slices):
+            L.check(lib.mmlrec_dense_optimizer_step_sliced(
+                st.dense.data_ptr(), st.dense_grad.data_ptr(), p(st.dense_s1), p(st.dense_s2), st.n_dense,
+                m.hyper_dev.data_ptr(), p(st.dense_bf16), n_slices, st.slice_stride, stream), "dense_optimizer_step")
+
+        def fold_slices():
+            """data parallel: the all-reduce wants ONE gradient buffer -> slice 0 += slices 1..S-1 (fixed order)"""
+            if self.grad_slices > 1:
+                L.check(lib.mmlrec_sum_slices(self.fold_seg.data_ptr(), 1, st.slice_stride, st.dense_grad.data_ptr(),
+                                              st.grad_slices.data_ptr(), self.grad_slices, st.slice_stride, stream),
+                        "fold gradient slices")
 
         if dp is not None and sh is None:
             # replicated tables: collectives stay on the main stream in program order
             main.wait_event(self.ev_join)
             self.gather.backward(stream)
+            fold_slices()
             dp.sum_gradients(st.dense_grad)
-            dense_step()
+            dense_step(1)
             return
         # the table update (K2) and the dense optimizer touch disjoint buffers: K2 runs on the side stream, behind the
         # sort / sweep it depends on, while the main stream runs the dense optimizer
         if sh is not None:
             self.gather.backward(stream)        # push gradient rows to their owners
+            fold_slices()
             dp.sum_gradients(st.dense_grad)     # also the barrier between the pushes and the owners' K2
         self.ev_bwd.record(main)
         self.side.wait_event(self.ev_bwd)
@@ -1283,7 +1306,7 @@ class StepPlan:
         else:
             self.gather.backward(self.side.cuda_stream)
         self.ev_join2.record(self.side)
-        dense_step()
+        dense_step(1 if sh is not None else self.grad_slices)
         main.wait_event(self.ev_join2)
 
     def capture(self) -> None:

@@ -27,6 +27,8 @@ def _align(n: int, a: int) -> int:
 
 
 class FlatStore:
+    MAX_GRAD_SLICES = 4
+
     def __init__(self, model: nn.Module, ordered: Iterable[nn.Parameter], emb_params: List[nn.Parameter],
                  device: torch.device, want_bf16: bool, ordered_buffers: Iterable[torch.Tensor] = (),
                  aux_floats: int = 0, emb_alloc=None):
@@ -61,7 +63,13 @@ class FlatStore:
         # their gradients; same offsets in dense / dense_grad / dense_bf16, never touched by the optimizer
         self.aux_base, self.aux_floats, self._aux_at = self.n_dense, _align(aux_floats, 8), 0
         self.dense = torch.zeros(self.n_dense + self.aux_floats, dtype=torch.float32, device=device)
-        self.dense_grad = torch.zeros_like(self.dense)
+        # gradient slices: slice 0 is THE gradient buffer; in tensor-core mode the split-K wgrad problems write the
+        # partial tiles of batch slices 1..S-1 into the further slices (same offsets) and the optimizer adds them up
+        self.max_grad_slices = self.MAX_GRAD_SLICES if want_bf16 else 1
+        self.slice_stride = self.n_dense + self.aux_floats
+        self.grad_slices = torch.zeros(self.max_grad_slices, self.slice_stride, dtype=torch.float32, device=device)
+        self.dense_grad = self.grad_slices[0]
+        self.live_slices = 1          # slices the last executed step program wrote (engine/core.py StepPlan)
         self.dense_s1: Optional[torch.Tensor] = None
         self.dense_s2: Optional[torch.Tensor] = None
         self.dense_bf16 = (torch.zeros(self.n_dense + self.aux_floats, dtype=torch.bfloat16, device=device)
@@ -177,10 +185,12 @@ class FlatStore:
         return self.dense_grad.data_ptr() + 4 * p._mm_off
 
     def grad_view(self, p: nn.Parameter) -> torch.Tensor:
+        """The gradient of `p` left by the last step (the sum of the live gradient slices)."""
         assert p._mm_kind == "dense"
+        g = self.dense_grad if self.live_slices == 1 else self.grad_slices[:self.live_slices].sum(0)
         if p.dim() == 2:
-            return self.dense_grad[p._mm_off:p._mm_off + p._mm_span].view(p.shape[0], p._mm_ld)[:, :p.shape[1]]
-        return self.dense_grad[p._mm_off:p._mm_off + p.numel()].view(p.shape)
+            return g[p._mm_off:p._mm_off + p._mm_span].view(p.shape[0], p._mm_ld)[:, :p.shape[1]]
+        return g[p._mm_off:p._mm_off + p.numel()].view(p.shape)
 
     def bf16_ptr(self, p: nn.Parameter) -> int:
         assert self.dense_bf16 is not None and p._mm_kind == "dense"

@@ -41,7 +41,24 @@ class GemmTcDesc(C.Structure):
     _fields_ = [("A", vp), ("B", vp), ("lda", i64), ("ldb", i64), ("a_mn_major", i32), ("b_mn_major", i32),
                 ("M", i32), ("N", i32), ("K", i32), ("C_f32", vp), ("ldc_f32", i64), ("C_bf16", vp),
                 ("ldc_bf16", i64), ("bias", vp), ("mask", vp), ("ldmask", i64), ("colsum", vp),
-                ("act", i32), ("accumulate", i32)]
+                ("act", i32), ("accumulate", i32),
+                ("relu_bits_out", vp), ("bits_out_chunks", i32), ("bits_out_chunk0", i32),
+                ("mask_bits", vp), ("mask_bits_chunks", i32), ("mask_bits_chunk0", i32)]
+
+
+def split_two_output_problems(descs):
+    """The CTA-pair kernel writes one output precision per problem: a problem that wants fp32 AND bf16 copies of its
+    result is listed twice (the bf16 copy keeps the ReLU bit output)."""
+    out = []
+    for d in descs:
+        if d.C_f32 and d.C_bf16:
+            a, b = GemmTcDesc.from_buffer_copy(bytes(d)), GemmTcDesc.from_buffer_copy(bytes(d))
+            a.C_bf16, a.ldc_bf16, a.relu_bits_out = None, 0, None
+            b.C_f32, b.ldc_f32, b.colsum = None, 0, None
+            out += [a, b]
+        else:
+            out.append(d)
+    return out
 
 
 class Gate(C.Structure):
@@ -137,6 +154,7 @@ _SIGNATURES = {
     "mmlrec_heads_forward_backward": (C.c_int, [vp, i32, i32, vp, i64, vp, i64, vp, i32, i32, vp, i64, vp, vp]),
     "mmlrec_heads_scratch": (i64, [i32, i32, i32]),
     "mmlrec_dense_optimizer_step": (C.c_int, [vp, vp, vp, vp, i64, vp, vp, vp]),
+    "mmlrec_dense_optimizer_step_sliced": (C.c_int, [vp, vp, vp, vp, i64, vp, vp, i32, i64, vp]),
     "mmlrec_copy_cols": (C.c_int, [vp, i64, vp, i64, vp, i64, i32, i32, vp]),
     "mmlrec_mul_forward": (C.c_int, [vp, i64, vp, i64, vp, i64, vp, i64, i32, i32, vp]),
     "mmlrec_mul_backward": (C.c_int, [vp, i64, vp, i64, vp, i64, vp, vp, i64, i32, i32, vp, vp, i64, i32, i32, i32, i32, vp]),

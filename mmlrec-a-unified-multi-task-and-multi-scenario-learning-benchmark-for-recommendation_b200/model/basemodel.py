@@ -247,6 +247,7 @@ class BaseModel(nn.Module):
 
     def _run_train(self, p: StepPlan) -> None:
         n = self._steps_on_plan[p.B]
+        self.store.live_slices = 1 if self.dp is not None else p.grad_slices
         if not self.use_cuda_graph:
             p.train_step()
         elif p.graph is not None:

@@ -155,6 +155,8 @@ class TcProblemTable:
         lib = L.load()
         self.kernel = int(os.environ.get("MMLREC_TC_KERNEL", "2")) if kernel is None else kernel
         pairs = self.kernel == 2
+        if pairs:
+            descs = L.split_two_output_problems(descs)
         rb = int(lib.mmlrec_tc2_record_bytes() if pairs else lib.mmlrec_tc_record_bytes())
         host = (C.c_uint8 * (rb * len(descs)))()
         pre, at = [0], 0
@@ -189,7 +191,9 @@ class TcProblemTable:
 def tc_desc(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, a_mn: bool = False, b_mn: bool = False,
             C_f32: Optional[torch.Tensor] = None, C_bf16: Optional[torch.Tensor] = None,
             bias: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
-            rowsum_a: Optional[torch.Tensor] = None, act: Optional[str] = None, accumulate: bool = False) -> L.GemmTcDesc:
+            rowsum_a: Optional[torch.Tensor] = None, act: Optional[str] = None, accumulate: bool = False,
+            relu_bits_out: Optional[torch.Tensor] = None, mask_bits: Optional[torch.Tensor] = None,
+            bits_chunks: int = 0, bits_chunk0: int = 0) -> L.GemmTcDesc:
     """D[M,N] = act(A B^T + bias).  ``A`` is a bf16 array [M,K] (or [K,M] when ``a_mn``); ``B`` is [N,K]
     (or [K,N] when ``b_mn``); both row-major with stride(1) == 1."""
     _need_cuda(A, B)
@@ -209,4 +213,8 @@ def tc_desc(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, a_mn: bool
     if rowsum_a is not None:
         d.colsum = rowsum_a.data_ptr()
     d.act, d.accumulate = L.ACT_CODES[act], int(accumulate)
+    if relu_bits_out is not None:   # int32 [ceil(M/32), bits_chunks, 32] (pair kernel only)
+        d.relu_bits_out, d.bits_out_chunks, d.bits_out_chunk0 = relu_bits_out.data_ptr(), bits_chunks, bits_chunk0
+    if mask_bits is not None:
+        d.mask_bits, d.mask_bits_chunks, d.mask_bits_chunk0 = mask_bits.data_ptr(), bits_chunks, bits_chunk0
     return d

@@ -66,8 +66,11 @@ def test_fp32_full_shape_step_matches_oracle(case):
                 # element-wise against the tensor's largest entry.  A weight / bias gradient is a sum over B=4096
                 # samples with cancellation; ATen's and this kernel's fp32 summation orders differ, which alone moves
                 # single elements by ~5e-5 of the largest entry (measured; predictions and the loss above stay at 1e-5,
-                # and the same comparison holds 1e-5 at B <= 1003 in test_step_gpu.py)
-                if err > 1e-4 * scale + 1e-9:
+                # and the same comparison holds 1e-5 at B <= 1003 in test_step_gpu.py).  With O(1) activations
+                # (init_std 0.05) a handful of the 14.7 M hidden units sit within rounding of zero, so their ReLU mask
+                # differs between the two fp32 forward passes: one flipped sample moves an element by 1/4096 of the sum
+                flips = 2e-3 if init_std > 1e-3 else 0.0
+                if err > (1e-4 + flips) * scale + 1e-9 or rel_err(g, want) > (2e-5 if flips == 0.0 else 1e-3):
                     bad.append(f"{name}: err {err:.3e} scale {scale:.3e}")
             assert not bad, "gradients off: " + "; ".join(bad[:8])
     # tables after 3 optimizer steps.  Adam / Adagrad divide by sqrt(v): an element whose gradient is itself a

@@ -267,6 +267,48 @@ def test_gemm_tc_epilogue_bias_relu_mask_accumulate_grouped(kernel):
     assert rel_err(out2, prev + 2 * base * (mask.float() > 0)) < 1e-5
 
 
+@pytest.mark.parametrize("M,N,col0", [(520, 192, 0), (4096, 256, 64), (77, 100, 32)])
+def test_gemm_tc_pair_relu_bitmask_roundtrip(M, N, col0):
+    """CTA-pair kernel: a ReLU forward problem also emits 1 bit per output ("> 0"), laid out so that the 32 rows of a
+    warp are contiguous; a dgrad problem masked by those bits equals the one masked by the bf16 activation itself."""
+    from mmlrec_b200 import ops
+    dev = _cuda()
+    g = torch.Generator().manual_seed(M + N)
+    K = 136
+    A = _bf16(torch.randn(M, K, generator=g)).to(dev)
+    W = _bf16(torch.randn(N, K, generator=g)).to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    chunks = (col0 + N + 31) // 32 + 1
+    bits = torch.zeros((M + 31) // 32 * chunks * 32, dtype=torch.int32, device=dev)
+    y16 = torch.zeros(M, (N + 7) // 8 * 8, dtype=torch.bfloat16, device=dev)
+    d = ops.tc_desc(A, W, M, N, K, C_bf16=y16, bias=bias, act="relu", relu_bits_out=bits, bits_chunks=chunks,
+                    bits_chunk0=col0 // 32)
+    ops.TcProblemTable([d], dev, kernel=2).launch()
+    torch.cuda.synchronize()
+    want = torch.relu(A.float() @ W.float().T + bias)
+    b3 = bits.view(-1, chunks, 32).cpu()
+    rows = torch.arange(M)
+    got = torch.zeros(M, N, dtype=torch.bool)
+    for c in range(N):
+        word = b3[rows // 32, (col0 + c) // 32, rows % 32]
+        got[:, c] = ((word >> ((col0 + c) % 32)) & 1).bool()
+    # the bit is taken from the fp32 value before the bf16 rounding: > 0 exactly where the fp32 result is > 0
+    near = want.cpu().abs() < 1e-3
+    assert torch.equal(got | near, (want.cpu() > 0) | near)
+    # dgrad through the ReLU: mask by bits == mask by the bf16 activation (wherever the bf16 value did not round to 0)
+    dz = _bf16(torch.randn(M, 72, generator=g)).to(dev)
+    W2 = _bf16(torch.randn(N, 72, generator=g)).to(dev)     # dX[M,N] = dz @ W2^T
+    out_bits = torch.empty(M, (N + 3) // 4 * 4, device=dev)
+    out_mask = torch.empty_like(out_bits)
+    d1 = ops.tc_desc(dz, W2, M, N, 72, C_f32=out_bits, mask_bits=bits, bits_chunks=chunks, bits_chunk0=col0 // 32)
+    d2 = ops.tc_desc(dz, W2, M, N, 72, C_f32=out_mask, mask=y16)
+    ops.TcProblemTable([d1, d2], dev, kernel=2).launch()
+    torch.cuda.synchronize()
+    base = dz.float() @ W2.float().T
+    assert rel_err(out_mask[:, :N], base * (y16[:, :N].float() > 0)) < 1e-5
+    assert rel_err(out_bits[:, :N], base * got.to(dev)) < 1e-5
+
+
 # ------------------------------------------------------------------------------------------------ dense optimizer
 @pytest.mark.parametrize("opt", ["adam", "adagrad", "sgd", "rmsprop"])
 def test_dense_optimizer_matches_torch(opt):

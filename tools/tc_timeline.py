@@ -30,7 +30,7 @@ plan = model.plan(B)
 lib = L.load()
 st = torch.cuda.current_stream().cuda_stream
 names = ["P.start", "P.table", "P.slot0", "P.issued", "M.start", "M.accfree", "M.data0", "M.commit", "E.start", "E.bias",
-         "E.accrdy", "E.done", "E.release", "E.math0", "E.waited0", "E.fenced0"]
+         "E.accrdy", "E.done", "E.release"]
 
 
 def run(tag, tbl, tiles_shown=10):
@@ -51,7 +51,10 @@ def run(tag, tbl, tiles_shown=10):
     for i in range(min(64, tiles_shown)):
         if int(per_tile[i, 0]) == 0:
             break
-        print(f"{i:4d} " + " ".join(f"{int(per_tile[i, k]) - t0:9d}" for k in range(16)))
+        cells = [f"{int(per_tile[i, k]) - t0:9d}" for k in range(13)]
+        if plan.b.tc_kernel == 2:   # slot 1 carries (problem << 32 | k-blocks)
+            cells[1] = f"p{int(per_tile[i, 1]) >> 32}k{int(per_tile[i, 1]) & 0xffff}".rjust(9)
+        print(f"{i:4d} " + " ".join(cells))
     g0 = cta[:, 0].min()
     rel = (cta[:, :4] - g0) / 1e3
     print(f"per CTA (us from the earliest setup-done): setup-done max {rel[:, 0].max():.2f}; producer done "
