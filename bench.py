@@ -321,8 +321,7 @@ def stage_breakdown(model, plan, iters=10):
 
     for it in range(iters + 2):
         evs = []
-        evs.append(timed("clock+sort", lambda: (L.check(plan.b.lib.mmlrec_hyper_advance(model.hyper_dev.data_ptr(), st)),
-                                                plan.gather.sort(st))))
+        evs.append(timed("clock+catch-up+sort", lambda: (plan.advance_clock(st), plan.gather.catch_up(st), plan.gather.sort(st))))
         for i, s in enumerate(plan.stages):
             evs.append(timed(f"fwd:{i}:{s.name}:{getattr(s, 'label', '')}", lambda s=s: s.forward(st, True)))
         for i, s in reversed(list(enumerate(plan.stages))):

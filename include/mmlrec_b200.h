@@ -56,6 +56,22 @@ typedef struct MmlrecHyper {
 } MmlrecHyper;
 /* step += 1 and refresh step_size / bc2_sqrt (double precision pow, like the host code it replaces) */
 int mmlrec_hyper_advance(MmlrecHyper* hyper, void* stream);
+/* same, and records {step_size, bc2_sqrt} of the new step t in hist[(t mod cap)] (float pairs, cap a power of two):
+ * the history the lazy dense-Adam catch-up replays */
+int mmlrec_hyper_advance_hist(MmlrecHyper* hyper, float* hist, int32_t cap, void* stream);
+/* Exact LAZY dense Adam on the embedding tables (the reference's nn.Embedding(sparse=False) + torch.optim.Adam moves
+ * EVERY row every step, model/utils.py:475-479; a row the batch does not touch still takes a zero-gradient
+ * step).  Instead of sweeping the whole table every step, a row remembers the step it is current for (row_touch) and
+ * the missed zero-gradient steps are replayed -- same fp32 operations, the recorded per-step factors -- when the row is
+ * next needed.  catch_up: at the start of step t (hyper already advanced) every row named by X's id columns is
+ * brought to step t-1 (the forward gather then reads exact values; K2 later applies step t and stamps the row).
+ * flush: every row is brought to the current step (before predict / state_dict / a checkpoint, and before the history
+ * ring wraps).  Bit-identical to mmlrec_emb_adam_dense_sweep after every step (tests/test_kernels_gpu.py). */
+int mmlrec_emb_adam_catch_up(const float* X, int64_t ldx, int32_t B, const int64_t* field_meta, int32_t F_s, int32_t D,
+                             float* emb, float* exp_avg, float* exp_avg_sq, int32_t* row_touch, const MmlrecHyper* hyper,
+                             const float* hist, int32_t cap, void* stream);
+int mmlrec_emb_adam_flush(float* emb, float* exp_avg, float* exp_avg_sq, int32_t* row_touch, int64_t total_rows, int32_t D,
+                          const MmlrecHyper* hyper, const float* hist, int32_t cap, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * K1: multi-field gather + concat.

@@ -9,7 +9,7 @@ namespace mmlrec {
 // ------------------------------------------------------------------------------------------------
 // optimizer clock (torch/optim/adam.py: bias_correction{1,2} = 1 - beta^step, formed in double)
 // ------------------------------------------------------------------------------------------------
-__global__ void hyper_advance_kernel(MmlrecHyper* h) {
+__global__ void hyper_advance_kernel(MmlrecHyper* h, float2* hist, int cap) {
   int t = h->step + 1;
   h->step = t;
   if (h->optimizer == MMLREC_OPT_ADAM) {
@@ -17,6 +17,78 @@ __global__ void hyper_advance_kernel(MmlrecHyper* h) {
     double bc2 = 1.0 - pow(h->beta2_d, (double)t);
     h->step_size = (float)(h->lr_d / bc1);
     h->bc2_sqrt = (float)sqrt(bc2);
+    // history of the per-step factors: the lazy catch-up of a row replays the steps it missed with exactly these
+    if (hist != nullptr) hist[t & (cap - 1)] = make_float2(h->step_size, h->bc2_sqrt);
+  }
+}
+
+// One Adam step with a zero gradient (what torch's dense Adam does to every row the batch did not touch), with the
+// step's own bias-correction factors.  Same operations as optimizer_update(p, 0, ...): the sweep and the lazy
+// catch-up both come through here, so they agree bit for bit.
+__device__ __forceinline__ void adam_zero_grad_step(float& p, float& s1, float& s2, float step_size, float bc2_sqrt,
+                                                    const MmlrecHyper& h) {
+  s1 = s1 + h.one_minus_beta1 * (0.f - s1);
+  s2 = s2 * h.beta2;
+  const float denom = sqrtf(s2) / bc2_sqrt + h.eps;
+  p = p - step_size * (s1 / denom);
+}
+
+// Bring one row (D floats at element offset `off`) from step `last` to step `upto` by replaying the zero-gradient
+// steps last+1 .. upto in registers.
+__device__ __forceinline__ void adam_replay_row(float* emb, float* m, float* v, int64_t off, int D, int last, int upto,
+                                                const float2* __restrict__ hist, int cap, const MmlrecHyper& hp) {
+  for (int d0 = 0; d0 < D; d0 += 4) {
+    float4 p4 = *reinterpret_cast<float4*>(emb + off + d0);
+    float4 m4 = *reinterpret_cast<float4*>(m + off + d0);
+    float4 v4 = *reinterpret_cast<float4*>(v + off + d0);
+    for (int j = last + 1; j <= upto; ++j) {
+      const float2 hj = __ldg(hist + (j & (cap - 1)));
+      adam_zero_grad_step(p4.x, m4.x, v4.x, hj.x, hj.y, hp);
+      adam_zero_grad_step(p4.y, m4.y, v4.y, hj.x, hj.y, hp);
+      adam_zero_grad_step(p4.z, m4.z, v4.z, hj.x, hj.y, hp);
+      adam_zero_grad_step(p4.w, m4.w, v4.w, hj.x, hj.y, hp);
+    }
+    *reinterpret_cast<float4*>(emb + off + d0) = p4;
+    *reinterpret_cast<float4*>(m + off + d0) = m4;
+    *reinterpret_cast<float4*>(v + off + d0) = v4;
+  }
+}
+
+// Exact lazy dense-Adam, part 1 (start of a training step, hyper already advanced to step t): every row the batch is
+// about to read is brought up to step t-1.  One thread per (sample, field); among the threads that name the same row
+// the one whose compare-and-swap moves row_touch from its old value to t-1 does the replay, the others do nothing
+// (nobody reads the row before this kernel has finished).  Rows never touched (row_touch < 0) have zero moments: a
+// zero-gradient step does not move them.
+__global__ void emb_adam_catch_up_kernel(const float* __restrict__ X, int64_t ldx, int B, const int64_t* __restrict__ field_meta,
+                                         int F_s, int D, float* emb, float* m, float* v, int32_t* row_touch,
+                                         const MmlrecHyper* hyper, const float2* hist, int cap) {
+  const MmlrecHyper hp = *hyper;
+  const int target = hp.step - 1;
+  const int64_t n = (int64_t)B * F_s;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int s = (int)(i / F_s), f = (int)(i - (int64_t)s * F_s);
+    const int64_t table_off = field_meta[f * 4 + 0], vocab = field_meta[f * 4 + 1];
+    int64_t id = (int64_t)X[(int64_t)s * ldx + field_meta[f * 4 + 2]];
+    if (id < 0 || id >= vocab) continue;                    // out of range: the gather flags it
+    const int64_t row = table_off / D + id;
+    const int last = row_touch[row];
+    if (last < 0 || last >= target) continue;
+    if (atomicCAS(row_touch + row, last, target) != last) continue;
+    adam_replay_row(emb, m, v, table_off + id * D, D, last, target, hist, cap, hp);
+  }
+}
+
+// part 2 (before anything reads the tables outside a training step -- predict, state_dict, a checkpoint -- and before
+// the history ring wraps): every row is brought up to the current step.
+__global__ void emb_adam_flush_kernel(float* emb, float* m, float* v, int32_t* row_touch, int64_t total_rows, int D,
+                                      const MmlrecHyper* hyper, const float2* hist, int cap) {
+  const MmlrecHyper hp = *hyper;
+  const int target = hp.step;
+  for (int64_t row = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; row < total_rows; row += (int64_t)gridDim.x * blockDim.x) {
+    const int last = row_touch[row];
+    if (last < 0 || last >= target) continue;
+    adam_replay_row(emb, m, v, row * D, D, last, target, hist, cap, hp);
+    row_touch[row] = target;
   }
 }
 
@@ -341,10 +413,10 @@ __global__ void emb_adam_sweep_kernel(float* emb, float* m, float* v, const int3
     float4 p4 = reinterpret_cast<float4*>(emb)[i];
     float4 m4 = reinterpret_cast<float4*>(m)[i];
     float4 v4 = reinterpret_cast<float4*>(v)[i];
-    optimizer_update(p4.x, 0.f, m4.x, v4.x, hp);
-    optimizer_update(p4.y, 0.f, m4.y, v4.y, hp);
-    optimizer_update(p4.z, 0.f, m4.z, v4.z, hp);
-    optimizer_update(p4.w, 0.f, m4.w, v4.w, hp);
+    adam_zero_grad_step(p4.x, m4.x, v4.x, hp.step_size, hp.bc2_sqrt, hp);
+    adam_zero_grad_step(p4.y, m4.y, v4.y, hp.step_size, hp.bc2_sqrt, hp);
+    adam_zero_grad_step(p4.z, m4.z, v4.z, hp.step_size, hp.bc2_sqrt, hp);
+    adam_zero_grad_step(p4.w, m4.w, v4.w, hp.step_size, hp.bc2_sqrt, hp);
     reinterpret_cast<float4*>(emb)[i] = p4;
     reinterpret_cast<float4*>(m)[i] = m4;
     reinterpret_cast<float4*>(v)[i] = v4;
@@ -355,8 +427,48 @@ __global__ void emb_adam_sweep_kernel(float* emb, float* m, float* v, const int3
 
 extern "C" int mmlrec_hyper_advance(MmlrecHyper* hyper, void* stream) {
   using namespace mmlrec;
-  MMLREC_CHECK_ARG(hyper != nullptr, "null hyper");
-  hyper_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyper);
+  MMLREC_CHECK_ARG(hyper, "null hyper");
+  hyper_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyper, nullptr, 1);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_hyper_advance_hist(MmlrecHyper* hyper, float* hist, int32_t cap, void* stream) {
+  using namespace mmlrec;
+  MMLREC_CHECK_ARG(hyper && hist && cap > 1 && (cap & (cap - 1)) == 0, "hist ring must have a power-of-two capacity");
+  hyper_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyper, reinterpret_cast<float2*>(hist), cap);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+static int emb_sm_count() {
+  static int n = 0;
+  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); }
+  return n > 0 ? n : 148;
+}
+
+extern "C" int mmlrec_emb_adam_catch_up(const float* X, int64_t ldx, int32_t B, const int64_t* field_meta, int32_t F_s,
+                                        int32_t D, float* emb, float* exp_avg, float* exp_avg_sq, int32_t* row_touch,
+                                        const MmlrecHyper* hyper, const float* hist, int32_t cap, void* stream) {
+  using namespace mmlrec;
+  MMLREC_CHECK_ARG(X && field_meta && emb && exp_avg && exp_avg_sq && row_touch && hyper && hist, "null argument");
+  MMLREC_CHECK_ARG(B > 0 && F_s > 0 && D > 0 && (D & 3) == 0 && cap > 1 && (cap & (cap - 1)) == 0, "bad sizes");
+  const int64_t n = (int64_t)B * F_s;
+  int grid = (int)((n + 255) / 256);
+  if (grid > 8 * emb_sm_count()) grid = 8 * emb_sm_count();
+  emb_adam_catch_up_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, ldx, B, field_meta, F_s, D, emb, exp_avg, exp_avg_sq,
+                                                                  row_touch, hyper, reinterpret_cast<const float2*>(hist), cap);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_emb_adam_flush(float* emb, float* exp_avg, float* exp_avg_sq, int32_t* row_touch, int64_t total_rows,
+                                     int32_t D, const MmlrecHyper* hyper, const float* hist, int32_t cap, void* stream) {
+  using namespace mmlrec;
+  MMLREC_CHECK_ARG(emb && exp_avg && exp_avg_sq && row_touch && hyper && hist, "null argument");
+  MMLREC_CHECK_ARG(total_rows >= 0 && D > 0 && (D & 3) == 0 && cap > 1 && (cap & (cap - 1)) == 0, "bad sizes");
+  if (total_rows == 0) return 0;
+  int grid = (int)((total_rows + 255) / 256);
+  if (grid > 8 * emb_sm_count()) grid = 8 * emb_sm_count();
+  emb_adam_flush_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(emb, exp_avg, exp_avg_sq, row_touch, total_rows, D, hyper,
+                                                               reinterpret_cast<const float2*>(hist), cap);
   MMLREC_RETURN_LAUNCH(1);
 }
 

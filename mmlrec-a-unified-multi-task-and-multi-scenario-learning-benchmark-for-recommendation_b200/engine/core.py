@@ -389,13 +389,23 @@ class GatherStage(Stage):
                                                 self.meta.data_ptr(), self.F_s, self.sorted_ids.data_ptr(),
                                                 self.sorted_pos.data_ptr(), self.keys_ws.data_ptr(), stream),
                     "sort_field_ids")
-        if self.model.optimizer_name in ("adam", "rmsprop"):   # optimizers whose zero-gradient update is not a no-op
+        if self.model.optimizer_name in ("adam", "rmsprop") and not self.model.lazy_adam:   # zero-gradient update is not a no-op
             L.check(b.lib.mmlrec_emb_stamp_rows(self.sorted_ids.data_ptr(), self.meta.data_ptr(), self.F_s, self.B_all, self.D,
                                                 st.row_touch.data_ptr(), hy.data_ptr(), stream), "emb_stamp_rows")
             L.check(b.lib.mmlrec_emb_adam_dense_sweep(st.emb.data_ptr(), st.emb_s1.data_ptr(),
                                                       st.emb_s2.data_ptr() if st.emb_s2 is not None else None,
                                                       st.row_touch.data_ptr(), st.n_emb // self.D, self.D,
                                                       hy.data_ptr(), stream), "emb_adam_dense_sweep")
+
+    def catch_up(self, stream):
+        """Lazy dense-Adam: the rows this step reads are brought up to the previous optimizer step (start of the step)."""
+        if not self.F_s or not self.model.lazy_adam:
+            return
+        b, st, m = self.b, self.b.store, self.model
+        L.check(b.lib.mmlrec_emb_adam_catch_up(self.X_all.data_ptr(), self.X_all.stride(0), self.B_all, self.meta.data_ptr(),
+                                               self.F_s, self.D, st.emb.data_ptr(), st.emb_s1.data_ptr(), st.emb_s2.data_ptr(),
+                                               st.row_touch.data_ptr(), m.hyper_dev.data_ptr(), m.adam_hist.data_ptr(),
+                                               m.adam_hist_cap, stream), "emb_adam_catch_up")
 
     def backward(self, stream):
         if not self.F_s or not self.out.grad_written:
@@ -1238,12 +1248,21 @@ class StepPlan:
         for s in self.stages:
             s.forward(stream, training)
 
+    def advance_clock(self, stream: int) -> None:
+        """step += 1 and the step's Adam bias corrections (recorded in the history ring when the tables are lazy)."""
+        m, lib = self.model, self.b.lib
+        if m.lazy_adam:
+            L.check(lib.mmlrec_hyper_advance_hist(m.hyper_dev.data_ptr(), m.adam_hist.data_ptr(), m.adam_hist_cap, stream),
+                    "hyper_advance")
+        else:
+            L.check(lib.mmlrec_hyper_advance(m.hyper_dev.data_ptr(), stream), "hyper_advance")
+
     def train_step(self, stream: Optional[int] = None) -> None:
         """advance clock -> sort ids -> forward (+ fused head backward) -> backward -> optimizer."""
         m = self.model
         stream = torch.cuda.current_stream().cuda_stream if stream is None else stream
         lib = self.b.lib
-        L.check(lib.mmlrec_hyper_advance(m.hyper_dev.data_ptr(), stream), "hyper_advance")
+        self.advance_clock(stream)
         # the id sort only feeds the last backward kernel (K2): fork it onto a side stream so it overlaps
         # the whole forward / backward (a parallel branch of the captured graph)
         main = torch.cuda.current_stream()
@@ -1254,6 +1273,7 @@ class StepPlan:
                 sh.flag_barrier(stream)   # every owner finished the previous step's row updates before rows are read
         elif dp is not None:
             dp.gather_rows(self.gather.X, self.gather.X_all)
+        self.gather.catch_up(stream)
         if sh is None or not self.gather.F_s:
             self.ev_fork.record(main)
             self.side.wait_event(self.ev_fork)

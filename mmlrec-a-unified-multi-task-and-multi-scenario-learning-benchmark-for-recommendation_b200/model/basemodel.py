@@ -105,6 +105,7 @@ class BaseModel(nn.Module):
         self.precision = self.b200_config.get("precision", "fp32")
         self.dp = None  # set by mmlrec_b200.parallel.attach()
         self.optimizer_name: Optional[str] = None
+        self.lazy_adam, self.adam_hist, self._steps_since_flush = False, None, 0
         self.hyper_dev: Optional[torch.Tensor] = None
         self.metrics, self.metrics_names = {}, ["loss"]
 
@@ -214,6 +215,15 @@ class BaseModel(nn.Module):
             h = L.make_hyper(optimizer, lr)
             self.hyper_dev = torch.frombuffer(bytearray(bytes(h)), dtype=torch.uint8).to(self.device_obj)
             self._plans.clear()
+            # exact lazy dense-Adam on the tables (csrc/emb_update.cu): rows catch up on the zero-gradient steps they
+            # missed when they are next read, instead of a sweep over every table every step.  Row-sharded tables keep
+            # the per-shard sweep (their rows are read on behalf of other ranks).
+            self.lazy_adam = (optimizer == "adam" and self.shard is None and bool(self.b200_config.get("lazy_adam", True))
+                              and self.store.n_emb > 0)
+            self.adam_hist_cap = 1 << 14
+            self.adam_hist = (torch.zeros(2 * self.adam_hist_cap, dtype=torch.float32, device=self.device_obj)
+                              if self.lazy_adam else None)
+            self._steps_since_flush = 0
         self.optim = _FusedOptimizerHandle(optimizer, self.optim_config.get("lr", 1e-3))
 
     def _get_metrics(self, metrics):
@@ -245,8 +255,29 @@ class BaseModel(nn.Module):
         self._run_train(p)
         return p.loss
 
+    def flush_tables(self) -> None:
+        """Lazy dense-Adam: bring every table row up to the current optimizer step (no-op otherwise).  Runs before the
+        tables are read outside a training step (eval forward, predict, state_dict, deepcopy)."""
+        if not self.lazy_adam or self._steps_since_flush == 0:
+            return
+        st = self.store
+        with torch.cuda.device(self.device_obj):
+            L.check(L.load().mmlrec_emb_adam_flush(st.emb.data_ptr(), st.emb_s1.data_ptr(), st.emb_s2.data_ptr(),
+                                                   st.row_touch.data_ptr(), st.n_emb // self.emb_dim, self.emb_dim,
+                                                   self.hyper_dev.data_ptr(), self.adam_hist.data_ptr(), self.adam_hist_cap,
+                                                   torch.cuda.current_stream().cuda_stream), "emb_adam_flush")
+        self._steps_since_flush = 0
+
+    def state_dict(self, *args, **kwargs):
+        self.flush_tables()
+        return super().state_dict(*args, **kwargs)
+
     def _run_train(self, p: StepPlan) -> None:
         n = self._steps_on_plan[p.B]
+        if self.lazy_adam:
+            if self._steps_since_flush >= self.adam_hist_cap - 2:   # the history ring is about to wrap
+                self.flush_tables()
+            self._steps_since_flush += 1
         self.store.live_slices = 1 if self.dp is not None else p.grad_slices
         if not self.use_cuda_graph:
             p.train_step()
@@ -263,6 +294,7 @@ class BaseModel(nn.Module):
         """Probabilities ``[B, T]`` (sigmoid applied for 'binary' heads).  Inference-only: the result
         carries no autograd graph (training goes through ``fit`` / ``train_on_batch``)."""
         X = torch.as_tensor(X)
+        self.flush_tables()
         p = self.plan(X.shape[0])
         p.X.copy_(X, non_blocking=True)
         p.forward(training=self.training)
@@ -374,6 +406,7 @@ class BaseModel(nn.Module):
 
     def predict(self, x, batch_size=256, domain_mask=None):
         self._require_cuda()
+        self.flush_tables()
         was_training = self.training
         self.eval()
         arr = x.astype(np.float32) if isinstance(x, np.ndarray) and x.ndim == 2 else self._stack_inputs(x)
@@ -396,8 +429,10 @@ class BaseModel(nn.Module):
         """``fit`` keeps the best epoch as ``deepcopy(model)`` (basemodel.py:344).  Parameters are
         views of flat buffers, so the copy is rebuilt through the constructor and the flat buffers
         are cloned wholesale."""
-        clone = type(self)(self.dnn_feature_columns, init_std=self.init_std, device=self.device, gpus=self.gpus,
-                           config=copy.deepcopy(self.config))
+        self.flush_tables()
+        with torch.random.fork_rng(devices=[]):   # the constructor draws (and discards) initial weights: keep the caller's RNG stream
+            clone = type(self)(self.dnn_feature_columns, init_std=self.init_std, device=self.device, gpus=self.gpus,
+                               config=copy.deepcopy(self.config))
         if self.store is not None:
             for name in ("dense", "emb", "stats", "counts"):
                 getattr(clone.store, name).copy_(getattr(self.store, name))

@@ -162,6 +162,56 @@ def test_emb_fused_update_matches_dense_torch_optimizer(opt):
         assert rel_err(g, ref_tables[f].detach()) < 1e-5, f"table {f}"
 
 
+def test_lazy_adam_catch_up_is_bit_identical_to_the_dense_sweep():
+    """Exact lazy dense-Adam: rows replay the zero-gradient steps they missed when they are next read (catch_up) or at
+    a flush; the tables, both moments and every later update must equal -- bit for bit -- the per-step sweep over all
+    untouched rows (the reference's nn.Embedding(sparse=False) + torch.optim.Adam semantics)."""
+    from mmlrec_b200 import lib as L, ops
+    dev = _cuda()
+    lib = L.load()
+    D, B, vocabs, lr, cap = 8, 256, [3, 40, 5000, 100000], 0.01, 64
+    emb0, offs, _ = _tables(vocabs, D, dev, seed=5)
+    meta = ops.field_meta(offs, vocabs, list(range(len(vocabs))), D, dev)
+    st = torch.cuda.current_stream().cuda_stream
+    state = {}
+    for mode in ("sweep", "lazy"):
+        emb = emb0.clone()
+        s1, s2 = torch.zeros_like(emb), torch.zeros_like(emb)
+        touch = torch.full((emb.numel() // D,), -1, dtype=torch.int32, device=dev)
+        hy = ops.hyper_tensor("adam", lr, dev)
+        hist = torch.zeros(2 * cap, device=dev)
+        seen = []
+        for step in range(150):           # > cap steps: a flush before the ring wraps, as the model does
+            X = _make_X(vocabs, 0, B, seed=20 + step).to(dev)
+            d_input = (torch.randn(B, len(vocabs) * D, generator=torch.Generator().manual_seed(50 + step)) * 0.01).to(dev)
+            if mode == "lazy":
+                if step % (cap - 2) == cap - 3:
+                    L.check(lib.mmlrec_emb_adam_flush(emb.data_ptr(), s1.data_ptr(), s2.data_ptr(), touch.data_ptr(),
+                                                      emb.numel() // D, D, hy.data_ptr(), hist.data_ptr(), cap, st))
+                L.check(lib.mmlrec_hyper_advance_hist(hy.data_ptr(), hist.data_ptr(), cap, st))
+                L.check(lib.mmlrec_emb_adam_catch_up(X.data_ptr(), X.stride(0), B, meta.data_ptr(), len(vocabs), D,
+                                                     emb.data_ptr(), s1.data_ptr(), s2.data_ptr(), touch.data_ptr(),
+                                                     hy.data_ptr(), hist.data_ptr(), cap, st))
+            else:
+                ops.hyper_advance(hy)
+            # what the forward gather of this step reads must already be exact
+            rows = torch.cat([emb[offs[f]:offs[f] + vocabs[f] * D].view(-1, D)[X[:, f].long()] for f in range(len(vocabs))], 1)
+            seen.append(rows.clone())
+            ids, pos = ops.sort_field_ids(X, meta)
+            ops.emb_backward_update(d_input, ids, pos, meta, D, hy, emb=emb, s1=s1, s2=s2, row_touch=touch)
+            if mode == "sweep":
+                ops.emb_adam_dense_sweep(emb, s1, s2, touch, D, hy)
+        if mode == "lazy":
+            L.check(lib.mmlrec_emb_adam_flush(emb.data_ptr(), s1.data_ptr(), s2.data_ptr(), touch.data_ptr(),
+                                              emb.numel() // D, D, hy.data_ptr(), hist.data_ptr(), cap, st))
+        torch.cuda.synchronize()
+        state[mode] = (emb.cpu(), s1.cpu(), s2.cpu(), [r.cpu() for r in seen])
+    for a, b, what in zip(state["sweep"][:3], state["lazy"][:3], ("table", "exp_avg", "exp_avg_sq")):
+        assert torch.equal(a, b), f"{what} differs between the sweep and the lazy catch-up"
+    for i, (a, b) in enumerate(zip(state["sweep"][3], state["lazy"][3])):
+        assert torch.equal(a, b), f"rows gathered at step {i} differ"
+
+
 # ------------------------------------------------------------------------------------------------ K3 fp32
 def test_gemm_grouped_f32_forward_dgrad_wgrad():
     from mmlrec_b200 import ops
