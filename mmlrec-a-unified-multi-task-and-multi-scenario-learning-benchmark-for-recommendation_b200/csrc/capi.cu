@@ -1,4 +1,5 @@
 // Process-wide bookkeeping of the C ABI: last-error text, launch counter, ABI version.
+#include <stdlib.h>
 #include <stdarg.h>
 #include <atomic>
 
@@ -22,6 +23,16 @@ void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 extern "C" int mmlrec_abi_version(void) { return MMLREC_ABI_VERSION; }
 extern "C" const char* mmlrec_last_error(void) { return mmlrec::g_err; }
+namespace mmlrec {
+int pdl_mode() {   // MMLREC_PDL: 0 off, 1 every patched kernel, 2 all but the GEMM, 3 the GEMM only (default)
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("MMLREC_PDL"); v = e ? atoi(e) : 3; }
+  return v;
+}
+bool pdl_enabled() { return pdl_mode() == 1 || pdl_mode() == 2; }
+bool pdl_enabled_gemm() { return pdl_mode() == 1 || pdl_mode() == 3; }
+}  // namespace mmlrec
+
 extern "C" int64_t mmlrec_launch_count(void) { return (int64_t)mmlrec::g_launches.load(); }
 
 // sizeof() of every ABI structure, so the ctypes mirror can be checked without a GPU.

@@ -44,6 +44,42 @@ void count_launch(int n = 1);
 
 static inline int cdiv(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
+// ---- programmatic dependent launch ---------------------------------------------------------------------------
+// A training step is ~25 short kernels in one stream / CUDA graph; a plain launch starts only after the previous
+// grid has drained completely.  Launched with the programmatic-stream-serialization attribute, the next grid is
+// scheduled as soon as every CTA of the previous one has started (each kernel begins with pdl_launch_dependents())
+// and its CTAs wait in pdl_wait() -- which returns when the previous grid has completed and its writes are visible
+// -- before touching any data a predecessor produced.  EVERY thread of such a kernel executes pdl_wait() before it
+// can exit, so completion stays transitive along the stream.  MMLREC_PDL selects who uses it (capi.cu): by default only the tensor-core GEMM, whose barrier / TMEM / table set-up then overlaps the previous kernel's tail (-4.5 % step time); kernels that can only wait at their very top lose by being scheduled early (profiles/pdl_r02.txt).
+bool pdl_enabled();
+bool pdl_enabled_gemm();
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() { pdl_launch_dependents(); pdl_wait(); }
+
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl_if(bool on, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, void* stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = on ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, void* stream, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float bf16_bits_to_float(uint16_t b) { return __uint_as_float(((uint32_t)b) << 16); }
 __device__ __forceinline__ uint16_t float_to_bf16_bits(float f) {
   __nv_bfloat16 h = __float2bfloat16_rn(f);

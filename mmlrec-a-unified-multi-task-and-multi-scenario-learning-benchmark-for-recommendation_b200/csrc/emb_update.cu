@@ -10,6 +10,7 @@ namespace mmlrec {
 // optimizer clock (torch/optim/adam.py: bias_correction{1,2} = 1 - beta^step, formed in double)
 // ------------------------------------------------------------------------------------------------
 __global__ void hyper_advance_kernel(MmlrecHyper* h, float2* hist, int cap) {
+  pdl_prologue();
   int t = h->step + 1;
   h->step = t;
   if (h->optimizer == MMLREC_OPT_ADAM) {
@@ -62,6 +63,7 @@ __device__ __forceinline__ void adam_replay_row(float* emb, float* m, float* v, 
 __global__ void emb_adam_catch_up_kernel(const float* __restrict__ X, int64_t ldx, int B, const int64_t* __restrict__ field_meta,
                                          int F_s, int D, float* emb, float* m, float* v, int32_t* row_touch,
                                          const MmlrecHyper* hyper, const float2* hist, int cap) {
+  pdl_prologue();
   const MmlrecHyper hp = *hyper;
   const int target = hp.step - 1;
   const int64_t n = (int64_t)B * F_s;
@@ -428,14 +430,14 @@ __global__ void emb_adam_sweep_kernel(float* emb, float* m, float* v, const int3
 extern "C" int mmlrec_hyper_advance(MmlrecHyper* hyper, void* stream) {
   using namespace mmlrec;
   MMLREC_CHECK_ARG(hyper, "null hyper");
-  hyper_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyper, nullptr, 1);
+  launch_pdl(hyper_advance_kernel, dim3(1), dim3(1), 0, stream, hyper, (float2*)nullptr, 1);
   MMLREC_RETURN_LAUNCH(1);
 }
 
 extern "C" int mmlrec_hyper_advance_hist(MmlrecHyper* hyper, float* hist, int32_t cap, void* stream) {
   using namespace mmlrec;
   MMLREC_CHECK_ARG(hyper && hist && cap > 1 && (cap & (cap - 1)) == 0, "hist ring must have a power-of-two capacity");
-  hyper_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(hyper, reinterpret_cast<float2*>(hist), cap);
+  launch_pdl(hyper_advance_kernel, dim3(1), dim3(1), 0, stream, hyper, reinterpret_cast<float2*>(hist), cap);
   MMLREC_RETURN_LAUNCH(1);
 }
 
@@ -454,8 +456,8 @@ extern "C" int mmlrec_emb_adam_catch_up(const float* X, int64_t ldx, int32_t B, 
   const int64_t n = (int64_t)B * F_s;
   int grid = (int)((n + 255) / 256);
   if (grid > 8 * emb_sm_count()) grid = 8 * emb_sm_count();
-  emb_adam_catch_up_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, ldx, B, field_meta, F_s, D, emb, exp_avg, exp_avg_sq,
-                                                                  row_touch, hyper, reinterpret_cast<const float2*>(hist), cap);
+  launch_pdl(emb_adam_catch_up_kernel, dim3(grid), dim3(256), 0, stream, X, ldx, B, field_meta, F_s, D, emb, exp_avg, exp_avg_sq,
+             row_touch, hyper, reinterpret_cast<const float2*>(hist), cap);
   MMLREC_RETURN_LAUNCH(1);
 }
 

@@ -271,6 +271,7 @@ constexpr int kHeadMaxK = 8;  // H <= 256
 __global__ void __launch_bounds__(256)
 heads_kernel(const MmlrecHead* heads, int T, int B, const float* y, int64_t ldy, float* pred, int64_t ld_pred,
              float* loss, int esmm, int training, float* scratch, int stride_cta, int32_t* counter) {
+  pdl_prologue();
   extern __shared__ __align__(16) float dw_s[];            // [8 warps][T][hmax]
   __shared__ MmlrecHead Hd[MMLREC_MAX_TASKS];
   __shared__ float part_s[8][MMLREC_MAX_TASKS][2];         // per warp: loss, dbias partials
@@ -376,6 +377,7 @@ heads_kernel(const MmlrecHead* heads, int T, int B, const float* y, int64_t ldy,
 // that the 2T scalars (loss_t, dbias_t) are outputs 0..2T-1 and land in CTA 0, which also forms the total loss.
 __global__ void __launch_bounds__(256)
 heads_reduce_kernel(const MmlrecHead* heads, int T, float* loss, int esmm, const float* scratch, int stride_cta, int n_cta) {
+  pdl_prologue();
   __shared__ float red[8][33];
   __shared__ float tot_s[MMLREC_MAX_TASKS][2];
   const int ix = threadIdx.x & 31, iy = threadIdx.x >> 5;
@@ -445,6 +447,7 @@ __global__ void dense_optimizer_kernel(float* p, const float* g, float* s1, floa
 __global__ void __launch_bounds__(256)
 dense_optimizer_sliced_kernel(float4* p, const float4* g, float4* s1, float4* s2, int64_t n4, const MmlrecHyper* hyper,
                               uint2* shadow, int n_slices, int64_t slice_stride4) {
+  pdl_prologue();
   const MmlrecHyper hp = *hyper;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n4; i += (int64_t)gridDim.x * blockDim.x) {
     float4 gv = g[i];
@@ -466,6 +469,7 @@ dense_optimizer_sliced_kernel(float4* p, const float4* g, float4* s1, float4* s2
 }
 
 __global__ void fill_kernel(float* p, int64_t n, float v) {
+  pdl_prologue();
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) p[i] = v;
 }
 
@@ -679,11 +683,11 @@ extern "C" int mmlrec_heads_forward_backward(const MmlrecHead* heads, int32_t T,
       opted = smem;
     }
   }
-  heads_kernel<<<n_cta, 256, smem, (cudaStream_t)stream>>>(heads, T, B, y, ldy, pred, ld_pred, loss, esmm, training, scratch,
+  launch_pdl(heads_kernel, dim3(n_cta), dim3(256), smem, stream, heads, T, B, y, ldy, pred, ld_pred, loss, esmm, training, scratch,
                                                            stride_cta, counters);
   if (!(training && y != nullptr)) { MMLREC_RETURN_LAUNCH(1); }
   MMLREC_CHECK_LAUNCH(1);
-  heads_reduce_kernel<<<cdiv(stride_cta, 32), 256, 0, (cudaStream_t)stream>>>(heads, T, loss, esmm, scratch, stride_cta, n_cta);
+  launch_pdl(heads_reduce_kernel, dim3(cdiv(stride_cta, 32)), dim3(256), 0, stream, heads, T, loss, esmm, scratch, stride_cta, n_cta);
   MMLREC_RETURN_LAUNCH(1);
 }
 
@@ -703,7 +707,7 @@ extern "C" int mmlrec_dense_optimizer_step_sliced(float* param, const float* gra
   MMLREC_CHECK_ARG((((uintptr_t)param | (uintptr_t)grad | (uintptr_t)state1 | (uintptr_t)state2) & 15) == 0 &&
                    ((uintptr_t)bf16_shadow & 7) == 0, "buffers must be 16-byte aligned");
   if (n == 0) return 0;
-  dense_optimizer_sliced_kernel<<<grid_for(n / 4), 256, 0, (cudaStream_t)stream>>>(
+  launch_pdl(dense_optimizer_sliced_kernel, dim3(grid_for(n / 4)), dim3(256), 0, stream,
       reinterpret_cast<float4*>(param), reinterpret_cast<const float4*>(grad), reinterpret_cast<float4*>(state1),
       reinterpret_cast<float4*>(state2), n / 4, hyper, reinterpret_cast<uint2*>(bf16_shadow), n_slices, slice_stride / 4);
   MMLREC_RETURN_LAUNCH(1);
@@ -713,6 +717,7 @@ namespace mmlrec {
 // dst[seg.dst + i] = sum_{s < S} src[s * slice_stride + seg.src + i]   (fixed order: deterministic split-K wgrad)
 __global__ void __launch_bounds__(256) sum_slices_kernel(const int64_t* seg, float* dst, const float* src, int S,
                                                          int64_t slice_stride) {
+  pdl_prologue();
   const int64_t d0 = seg[blockIdx.y * 3 + 0], s0 = seg[blockIdx.y * 3 + 1], n = seg[blockIdx.y * 3 + 2];
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     float acc = src[s0 + i];
@@ -728,13 +733,13 @@ extern "C" int mmlrec_sum_slices(const int64_t* segments, int32_t n_segments, in
   int gx = (int)((max_n + 255) / 256);
   if (gx > 592) gx = 592;
   dim3 grid(gx, n_segments);
-  mmlrec::sum_slices_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(segments, dst, src, S, slice_stride);
+  mmlrec::launch_pdl(mmlrec::sum_slices_kernel, grid, dim3(256), 0, stream, segments, dst, src, S, slice_stride);
   MMLREC_RETURN_LAUNCH(1);
 }
 
 extern "C" int mmlrec_fill_f32(float* p, int64_t n, float v, void* stream) {
   if (n <= 0) return 0;
-  fill_kernel<<<grid_for(n), 256, 0, (cudaStream_t)stream>>>(p, n, v);
+  launch_pdl(fill_kernel, dim3(grid_for(n)), dim3(256), 0, stream, p, n, v);
   MMLREC_RETURN_LAUNCH(1);
 }
 

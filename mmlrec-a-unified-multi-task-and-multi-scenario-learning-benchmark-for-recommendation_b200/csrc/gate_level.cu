@@ -410,6 +410,7 @@ __device__ __forceinline__ void gt_stage(const MmlrecGateLevel& L, const GtTable
 template <int NT>
 __global__ void __launch_bounds__(NT, 2)
 gate_level_forward_tiled_kernel(const MmlrecGateLevel* lv, int B) {
+  pdl_prologue();
   constexpr int NW = NT / 32, PARTS = NW / GT_ROWS;
   static_assert(NW % GT_ROWS == 0, "warps must be a multiple of the samples per CTA");
   extern __shared__ __align__(128) float dyn_s[];
@@ -515,6 +516,7 @@ gate_level_forward_tiled_kernel(const MmlrecGateLevel* lv, int B) {
 
 __global__ void __launch_bounds__(GT_THREADS, 2)
 gate_level_backward_tiled_kernel(const MmlrecGateLevel* lv, int B, float* scratch) {
+  pdl_prologue();
   extern __shared__ __align__(128) float dyn_s[];
   __shared__ __align__(16) MmlrecGateLevel L;
   __shared__ GtTables T;
@@ -703,6 +705,7 @@ gate_level_backward_tiled_kernel(const MmlrecGateLevel* lv, int B, float* scratc
 // 8th partial of its output (coalesced across outputs), the 8 group sums are added in a fixed order
 __global__ void __launch_bounds__(256)
 gate_level_dwg_reduce_kernel(const MmlrecGateLevel* lv, const float* scratch, int n_cta, int total_wg) {
+  pdl_prologue();
   __shared__ float red[8][33];
   const int ix = threadIdx.x & 31, iy = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + ix;
@@ -754,7 +757,7 @@ extern "C" int mmlrec_gate_level_backward(const MmlrecGateLevel* level, int32_t 
   const int n_cta = cdiv(B, GL_BWD_ROWS);
   gate_level_backward_kernel<<<n_cta, GL_BWD_WARPS * 32, smem, (cudaStream_t)stream>>>(level, B, scratch);
   MMLREC_CHECK_LAUNCH(1);
-  gate_level_dwg_reduce_kernel<<<cdiv(total_wg, 32), 256, 0, (cudaStream_t)stream>>>(level, scratch, n_cta, total_wg);
+  launch_pdl(gate_level_dwg_reduce_kernel, dim3(cdiv(total_wg, 32)), dim3(256), 0, stream, level, (const float*)scratch, n_cta, total_wg);
   MMLREC_RETURN_LAUNCH(1);
 }
 
@@ -784,9 +787,9 @@ extern "C" int mmlrec_gate_level_backward_tiled(const MmlrecGateLevel* level, in
     opted = smem;
   }
   const int n_cta = cdiv(B, GT_ROWS);
-  gate_level_backward_tiled_kernel<<<n_cta, GT_THREADS, (size_t)smem, (cudaStream_t)stream>>>(level, B, scratch);
+  launch_pdl(gate_level_backward_tiled_kernel, dim3(n_cta), dim3(GT_THREADS), (size_t)smem, stream, level, B, scratch);
   MMLREC_CHECK_LAUNCH(1);
-  gate_level_dwg_reduce_kernel<<<cdiv(total_wg, 32), 256, 0, (cudaStream_t)stream>>>(level, scratch, n_cta, total_wg);
+  launch_pdl(gate_level_dwg_reduce_kernel, dim3(cdiv(total_wg, 32)), dim3(256), 0, stream, level, (const float*)scratch, n_cta, total_wg);
   MMLREC_RETURN_LAUNCH(1);
 }
 
@@ -813,8 +816,8 @@ extern "C" int mmlrec_gate_level_forward_tiled(const MmlrecGateLevel* level, int
   static int threads = 0;
   if (!threads) { const char* e = getenv("MMLREC_GATE_FWD_THREADS"); threads = (e && atoi(e) == 256) ? 256 : 512; }
   if (threads == 256)
-    gate_level_forward_tiled_kernel<256><<<cdiv(B, GT_ROWS), 256, (size_t)smem, (cudaStream_t)stream>>>(level, B);
+    launch_pdl(gate_level_forward_tiled_kernel<256>, dim3(cdiv(B, GT_ROWS)), dim3(256), (size_t)smem, stream, level, B);
   else
-    gate_level_forward_tiled_kernel<512><<<cdiv(B, GT_ROWS), 512, (size_t)smem, (cudaStream_t)stream>>>(level, B);
+    launch_pdl(gate_level_forward_tiled_kernel<512>, dim3(cdiv(B, GT_ROWS)), dim3(512), (size_t)smem, stream, level, B);
   MMLREC_RETURN_LAUNCH(1);
 }

@@ -29,6 +29,7 @@ struct GatherArgs {
 constexpr int kGatherThreads = 256;
 
 __global__ void __launch_bounds__(kGatherThreads) gather_concat_kernel(const GatherArgs a) {
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* out_s = reinterpret_cast<float*>(smem_raw);                 // [R][W]
   float* x_s = out_s + (size_t)a.R * a.W;                            // [R][x_cols]
@@ -197,6 +198,6 @@ static int gather_launch(const float* X, int64_t ldx, int32_t B, const float* em
     smem_opt_in = (int)smem;
   }
   int grid = a.n_tiles < 148 * 16 ? a.n_tiles : 148 * 16;
-  gather_concat_kernel<<<grid, kGatherThreads, smem, (cudaStream_t)stream>>>(a);
+  launch_pdl(gather_concat_kernel, dim3(grid), dim3(kGatherThreads), smem, stream, a);
   MMLREC_RETURN_LAUNCH(1);
 }

@@ -144,6 +144,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __restrict__ prefix, int n_problems, int total_tiles,
                         const int32_t* __restrict__ tile_order, const int32_t* __restrict__ pair_start,
                         long long* __restrict__ dbg) {
+  // programmatic dependent launch: the next grid of the stream may be scheduled from now on; everything up to pdl_wait()
+  // below (barriers, TMEM, the problem tables -- written once at plan build, never by a predecessor) overlaps the tail
+  // of the previous kernel
+  pdl_launch_dependents();
   extern __shared__ unsigned char smem_dyn[];
   unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
   unsigned char* sA = smem;
@@ -195,6 +199,7 @@ gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __res
   __syncwarp();
   cluster_sync_all();                                     // the peer's barriers / ones tile / TMEM exist before anyone uses them
   tc_fence_after();
+  pdl_wait();                                             // the previous kernel's outputs (our operands, masks, biases) are final
   const uint32_t tmem_base = *tmem_slot;
   const int sched_begin = tile_order ? pair_start[pair] : pair;
   const int sched_end = tile_order ? pair_start[pair + 1] : total_tiles;
@@ -551,8 +556,8 @@ extern "C" int mmlrec_gemm_grouped_tc2(const void* records, const int32_t* tile_
   const int max_pairs = tc_sm_count() / 2;
   int pairs = tile_order ? n_pairs : (total_tiles < max_pairs ? total_tiles : max_pairs);
   MMLREC_CHECK_ARG(pairs > 0 && pairs <= max_pairs, "bad pair count");
-  gemm_grouped_tc2_kernel<<<2 * pairs, T2_THREADS, T2_SMEM_BYTES, (cudaStream_t)stream>>>(
-      reinterpret_cast<const Tc2Record*>(records), tile_prefix, n_problems, total_tiles, tile_order, pair_start,
-      reinterpret_cast<long long*>(stamps));
+  launch_pdl_if(pdl_enabled_gemm(), gemm_grouped_tc2_kernel, dim3(2 * pairs), dim3(T2_THREADS), (size_t)T2_SMEM_BYTES, stream,
+             reinterpret_cast<const Tc2Record*>(records), tile_prefix, n_problems, total_tiles, tile_order, pair_start,
+             reinterpret_cast<long long*>(stamps));
   MMLREC_RETURN_LAUNCH(1);
 }
