@@ -71,7 +71,8 @@ __global__ void emb_adam_catch_up_kernel(const float* __restrict__ X, int64_t ld
     const int s = (int)(i / F_s), f = (int)(i - (int64_t)s * F_s);
     const int64_t table_off = field_meta[f * 4 + 0], vocab = field_meta[f * 4 + 1];
     int64_t id = (int64_t)X[(int64_t)s * ldx + field_meta[f * 4 + 2]];
-    if (id < 0 || id >= vocab) continue;                    // out of range: the gather flags it
+    if (id < 0) id = 0;                                     // clamped like the gather (which flags it)
+    if (id >= vocab) id = vocab - 1;
     const int64_t row = table_off / D + id;
     const int last = row_touch[row];
     if (last < 0 || last >= target) continue;
@@ -120,11 +121,16 @@ sort_local_kernel(const float* X, int64_t ldx, int B, const int64_t* field_meta,
   const int tid = threadIdx.x;
   if (mode == 0) {
     const int xcol = (int)field_meta[f * 4 + 2];
+    const int64_t vocab = field_meta[f * 4 + 1];
     for (int i = tid; i < chunk; i += kSortThreads) {
       int gi = base + i;
       uint64_t key = ~0ull;
       if (gi < B) {
         int64_t id = (int64_t)__ldg(X + (int64_t)gi * ldx + xcol);
+        // out-of-range ids are clamped exactly like the gather clamps them (which also raises the oob flag the
+        // host turns into an IndexError): the update then goes to the row the forward pass read, never past a table
+        if (id < 0) id = 0;
+        if (id >= vocab) id = vocab - 1;
         key = ((uint64_t)(uint32_t)id << 32) | (uint32_t)gi;
       }
       s[i] = key;
@@ -576,7 +582,8 @@ extern "C" int mmlrec_emb_adam_dense_sweep(float* emb, float* exp_avg, float* ex
   MMLREC_CHECK_ARG(total_rows >= 0 && D > 0 && (D & 3) == 0, "bad sizes");
   if (total_rows == 0) return 0;
   int64_t n4 = total_rows * (D >> 2);
-  int grid = (int)((n4 + 255) / 256 < 148 * 8 ? (n4 + 255) / 256 : 148 * 8);
+  const int cap_grid = emb_sm_count() * 8;
+  int grid = (int)((n4 + 255) / 256 < cap_grid ? (n4 + 255) / 256 : cap_grid);
   emb_adam_sweep_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(emb, exp_avg, exp_avg_sq, row_touch, total_rows, D, hyper);
   MMLREC_RETURN_LAUNCH(1);
 }

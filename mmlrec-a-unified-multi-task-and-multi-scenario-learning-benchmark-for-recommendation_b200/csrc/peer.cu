@@ -111,7 +111,8 @@ __global__ void peer_barrier_kernel(int32_t* const* peer_flags, int32_t* local_e
     volatile int32_t* mine = peer_flags[rank] + threadIdx.x;
     const long long t0 = clock64();
     while (*mine < e) {
-      if (clock64() - t0 > 20000000000ll) {   // ~10 s: a peer died; fail loudly instead of hanging the GPU
+      if (clock64() - t0 > 120000000000ll) {   // ~60 s: a peer died (a slow one -- plan build, graph capture -- gets this long);
+                                              // fail loudly (err flag, read by BaseModel.check_ids) instead of hanging the GPU
         if (err_flag) *err_flag = 2;
         break;
       }
@@ -175,7 +176,11 @@ extern "C" int mmlrec_peer_fill_u64(uint64_t* p, int64_t n, uint64_t v, void* st
   return 1;
 }
 
-static int push_grid(int64_t n) { return (int)((n + 255) / 256 < 148 * 8 ? (n + 255) / 256 : 148 * 8); }
+static int push_grid(int64_t n) {
+  static int n_sm = 0;
+  if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 148; }
+  return (int)((n + 255) / 256 < n_sm * 8 ? (n + 255) / 256 : n_sm * 8);
+}
 
 extern "C" int mmlrec_emb_push_ids(const float* X, int64_t ldx, int32_t b, const int64_t* field_meta, int32_t F_s,
                                    int32_t rank, int32_t R, int32_t B_all, uint64_t* const* rq_keys,

@@ -255,6 +255,17 @@ class BaseModel(nn.Module):
         self._run_train(p)
         return p.loss
 
+    def check_ids(self) -> None:
+        """Raise IndexError if any batch so far carried an id outside its table (the reference's nn.Embedding raises at
+        the offending batch; the kernels clamp the id, set a device flag and go on -- read here, at host sync points)."""
+        for p in self._plans.values():
+            if p.gather.F_s and int(p.gather.oob.item()) != 0:
+                p.gather.oob.zero_()
+                raise IndexError("index out of range in self: a sparse feature id lies outside [0, vocabulary_size) "
+                                 "(ids are clamped on the device; the batch that carried it has already been processed)")
+        if self.shard is not None:
+            self.shard.check()   # a peer-memory barrier that gave up waiting means a rank is gone: stop, do not train on
+
     def flush_tables(self) -> None:
         """Lazy dense-Adam: bring every table row up to the current optimizer step (no-op otherwise).  Runs before the
         tables are read outside a training step (eval forward, predict, state_dict, deepcopy)."""
@@ -358,6 +369,7 @@ class BaseModel(nn.Module):
                 losses.append(p.loss[self.num_tasks].clone())
                 idxs.append(idx)
             total = float(torch.stack(losses).sum().item())
+            self.check_ids()
             logs = {"loss": total / n, "cka_loss": 0.0}
             if self.metrics:
                 sums = {k: 0.0 for k in self.metrics}
@@ -419,7 +431,9 @@ class BaseModel(nn.Module):
             p.forward(training=False)
             out.append(p.pred.clone())
         self.train(was_training)
-        return torch.cat(out).cpu().numpy().astype("float64")
+        res = torch.cat(out).cpu().numpy().astype("float64")
+        self.check_ids()
+        return res
 
     def update_save(self, value=True):
         self.save_layer_output = value

@@ -269,3 +269,30 @@ def test_step_matches_oracle_at_ragged_batches(case, B, precision):
                 continue
             moved = float((want[name] - torch.from_numpy(z["init/" + name])).abs().max())
             assert float((got.cpu() - want[name]).abs().max()) <= factor * moved + 1e-7, name
+
+
+def test_out_of_range_id_is_clamped_flagged_and_raised_on_the_host():
+    """An id >= vocabulary must not write past its table (the update goes to the clamped row the forward pass read) and
+    must surface as IndexError at the next host synchronisation point, like the reference's nn.Embedding."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    z, cfg, fields = load_golden("sharedbottom_kuairec_adam")
+    model, cfg = build_model(cfg, fields)
+    load_init(model, z)
+    model.compile("adam", cfg["optim_config"]["loss"], [])
+    model.train()
+    X, y = z["step0/X"].copy(), z["step0/y"]
+    before = {k: v.detach().clone() for k, v in model.state_dict().items() if "embedding_dict" in k}
+    names = [n for n, k, _ in fields if k == "sparse"]
+    vocab0 = [v for n, k, v in fields if k == "sparse"][0]
+    X[3, 0] = vocab0 + 5          # field 0: beyond its table -> would land in field 1's rows
+    model.train_on_batch(X, y)
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError):
+        model.check_ids()
+    after = model.state_dict()
+    ids1 = set(np.unique(X[:, 1].astype(np.int64)).tolist())
+    t1 = f"embedding_dict.{names[1]}.weight"
+    moved = (after[t1] != before[t1]).any(dim=1).nonzero().flatten().tolist()
+    assert set(moved) <= ids1, "rows of the next table that the batch did not touch were written"
+    model.check_ids()   # the flag was consumed
