@@ -406,6 +406,12 @@ int mmlrec_heads_forward_backward(const MmlrecHead* heads, int32_t T, int32_t B,
                                   float* pred, int64_t ld_pred, float* loss /*[T+1]: per task, total*/,
                                   int32_t esmm, int32_t training,
                                   float* scratch, int64_t scratch_floats, int32_t* counters, void* stream);
+/* Backward of the heads for an upstream gradient d_pred = dL/d(pred) [B, ld_d_pred] supplied by the caller instead of
+ * the fused BCE / MSE (the differentiable forward() of the model classes, model/mmoe.py:65: any loss built by autograd
+ * on the returned probabilities).  Recomputes the logits, writes d(tower output), dw, dbias; `loss` receives zeros. */
+int mmlrec_heads_backward_external(const MmlrecHead* heads, int32_t T, int32_t B, const float* d_pred, int64_t ld_d_pred,
+                                   float* pred, int64_t ld_pred, float* loss, int32_t esmm,
+                                   float* scratch, int64_t scratch_floats, int32_t* counters, void* stream);
 int64_t mmlrec_heads_scratch(int32_t T, int32_t max_h, int32_t B);
 
 /* ---------------------------------------------------------------------------------------------

@@ -270,7 +270,7 @@ constexpr int kHeadMaxK = 8;  // H <= 256
 
 __global__ void __launch_bounds__(256)
 heads_kernel(const MmlrecHead* heads, int T, int B, const float* y, int64_t ldy, float* pred, int64_t ld_pred,
-             float* loss, int esmm, int training, float* scratch, int stride_cta, int32_t* counter) {
+             float* loss, int esmm, int training, float* scratch, int stride_cta, int32_t* counter, int grad_mode) {
   pdl_prologue();
   extern __shared__ __align__(16) float dw_s[];            // [8 warps][T][hmax]
   __shared__ MmlrecHead Hd[MMLREC_MAX_TASKS];
@@ -311,19 +311,27 @@ heads_kernel(const MmlrecHead* heads, int T, int B, const float* y, int64_t ldy,
         pred[(int64_t)b * ld_pred + t] = out;
         if (y) {
           const float yy = y[(int64_t)b * ldy + t];
-          // F.binary_cross_entropy: (y-1)*max(log1p(-x),-100) - y*max(log(x),-100)
-          l = (yy - 1.f) * fmaxf(log1pf(-out), -100.f) - yy * fmaxf(logf(out), -100.f);
-          // binary_cross_entropy_backward: (x-y)/max((1-x)*x, 1e-12); sigmoid_backward: g*(1-p)*p
-          const float gout = (out - yy) / fmaxf((1.f - out) * out, 1e-12f);
+          float gout;
+          if (grad_mode) {   // y carries dL/d(pred) from autograd (differentiable forward()): no loss is formed here
+            gout = yy;
+          } else {
+            // F.binary_cross_entropy: (y-1)*max(log1p(-x),-100) - y*max(log(x),-100)
+            l = (yy - 1.f) * fmaxf(log1pf(-out), -100.f) - yy * fmaxf(logf(out), -100.f);
+            // binary_cross_entropy_backward: (x-y)/max((1-x)*x, 1e-12); sigmoid_backward: g*(1-p)*p
+            gout = (out - yy) / fmaxf((1.f - out) * out, 1e-12f);
+          }
           dz = gout * scale * (1.f - p) * p;
           if (esmm && t == 1) cross = gout * p;  // d loss_1 / d p0
         }
       } else {  // identity + MSE (F.mse_loss, reduction='sum')
         pred[(int64_t)b * ld_pred + t] = z;
         if (y) {
-          const float d = z - y[(int64_t)b * ldy + t];
-          l = d * d;
-          dz = 2.f * d;
+          if (grad_mode) { dz = y[(int64_t)b * ldy + t]; }
+          else {
+            const float d = z - y[(int64_t)b * ldy + t];
+            l = d * d;
+            dz = 2.f * d;
+          }
         }
       }
     }
@@ -662,9 +670,26 @@ extern "C" int64_t mmlrec_heads_scratch(int32_t T, int32_t max_h, int32_t B) {
   return (int64_t)cdiv(B, kHeadRows) * T * (2 + max_h);
 }
 
+static int heads_launch(const MmlrecHead* heads, int32_t T, int32_t B, const float* y, int64_t ldy,
+                        float* pred, int64_t ld_pred, float* loss, int32_t esmm, int32_t training,
+                        float* scratch, int64_t scratch_floats, int32_t* counters, int grad_mode, void* stream);
+
 extern "C" int mmlrec_heads_forward_backward(const MmlrecHead* heads, int32_t T, int32_t B, const float* y, int64_t ldy,
                                              float* pred, int64_t ld_pred, float* loss, int32_t esmm, int32_t training,
                                              float* scratch, int64_t scratch_floats, int32_t* counters, void* stream) {
+  return heads_launch(heads, T, B, y, ldy, pred, ld_pred, loss, esmm, training, scratch, scratch_floats, counters, 0, stream);
+}
+
+extern "C" int mmlrec_heads_backward_external(const MmlrecHead* heads, int32_t T, int32_t B, const float* d_pred, int64_t ld_d_pred,
+                                              float* pred, int64_t ld_pred, float* loss, int32_t esmm,
+                                              float* scratch, int64_t scratch_floats, int32_t* counters, void* stream) {
+  MMLREC_CHECK_ARG(d_pred != nullptr, "no upstream gradient");
+  return heads_launch(heads, T, B, d_pred, ld_d_pred, pred, ld_pred, loss, esmm, 1, scratch, scratch_floats, counters, 1, stream);
+}
+
+static int heads_launch(const MmlrecHead* heads, int32_t T, int32_t B, const float* y, int64_t ldy,
+                        float* pred, int64_t ld_pred, float* loss, int32_t esmm, int32_t training,
+                        float* scratch, int64_t scratch_floats, int32_t* counters, int grad_mode, void* stream) {
   MMLREC_CHECK_ARG(T > 0 && T < MMLREC_MAX_TASKS && B > 0, "bad sizes");
   MMLREC_CHECK_ARG(!esmm || T == 2, "esmm needs exactly two heads");
   const int n_cta = cdiv(B, kHeadRows);
@@ -684,7 +709,7 @@ extern "C" int mmlrec_heads_forward_backward(const MmlrecHead* heads, int32_t T,
     }
   }
   launch_pdl(heads_kernel, dim3(n_cta), dim3(256), smem, stream, heads, T, B, y, ldy, pred, ld_pred, loss, esmm, training, scratch,
-                                                           stride_cta, counters);
+             stride_cta, counters, grad_mode);
   if (!(training && y != nullptr)) { MMLREC_RETURN_LAUNCH(1); }
   MMLREC_CHECK_LAUNCH(1);
   launch_pdl(heads_reduce_kernel, dim3(cdiv(stride_cta, 32)), dim3(256), 0, stream, heads, T, loss, esmm, scratch, stride_cta, n_cta);

@@ -1178,6 +1178,7 @@ class HeadStage(Stage):
     def finalize(self):
         b, st = self.b, self.b.store
         self.y = b.zeros(b.B, self.T)
+        self.d_pred = b.zeros(b.B, self.T)
         self.pred = b.zeros(b.B, self.T)
         self.loss = b.zeros(self.T + 1)
         recs = []
@@ -1211,6 +1212,15 @@ class HeadStage(Stage):
             self.table.data_ptr(), self.T, b.B, self.y.data_ptr() if training else None, self.T, self.pred.data_ptr(),
             self.T, self.loss.data_ptr(), 1 if self.esmm else 0, 1 if training else 0, self.scratch.data_ptr(),
             self.scratch.numel(), self.counter.data_ptr(), stream), "heads")
+
+    def backward_external(self, stream, d_pred: torch.Tensor):
+        """Backward for an upstream gradient dL/d(pred) [B, T] handed in by autograd (differentiable forward())."""
+        b = self.b
+        self.d_pred.copy_(d_pred)
+        L.check(b.lib.mmlrec_heads_backward_external(
+            self.table.data_ptr(), self.T, b.B, self.d_pred.data_ptr(), self.T, self.pred.data_ptr(), self.T,
+            self.loss.data_ptr(), 1 if self.esmm else 0, self.scratch.data_ptr(), self.scratch.numel(),
+            self.counter.data_ptr(), stream), "heads (external gradient)")
 
 
 # ----------------------------------------------------------------------------------------------
@@ -1247,6 +1257,25 @@ class StepPlan:
         stream = torch.cuda.current_stream().cuda_stream if stream is None else stream
         for s in self.stages:
             s.forward(stream, training)
+
+    # ---- differentiable forward (autograd): model(x) -> probabilities with a grad_fn
+    def autograd_forward(self, training: bool) -> None:
+        """Forward of every stage; the heads only predict (their backward waits for autograd's upstream gradient)."""
+        stream = torch.cuda.current_stream().cuda_stream
+        for s in self.stages:
+            s.forward(stream, False if s is self.heads else training)
+
+    def autograd_backward(self, d_pred: torch.Tensor):
+        """Backward of every stage for dL/d(pred); leaves dense gradients in the flat store (gradient slices) and
+        returns d(dnn_input) [B, in_dim] for the embedding tables (None when nothing flows there)."""
+        stream = torch.cuda.current_stream().cuda_stream
+        self.model.store.grad_slices.zero_()
+        self.heads.backward_external(stream, d_pred)
+        for s in reversed(self.stages):
+            if s is not self.gather and s is not self.heads:
+                s.backward(stream)
+        self.model.store.live_slices = self.grad_slices
+        return self.gather.out.grad_tensor() if (self.gather.F_s and self.gather.out.grad_written) else None
 
     def advance_clock(self, stream: int) -> None:
         """step += 1 and the step's Adam bias corrections (recorded in the history ring when the tables are lazy)."""

@@ -155,6 +155,7 @@ _SIGNATURES = {
     "mmlrec_gate_level_forward_tiled_smem": (i64, [i32, i32, i32, i32, i32]),
     "mmlrec_gate_level_backward_tiled_smem": (i64, [i32, i32, i32, i32, i32, i32]),
     "mmlrec_heads_forward_backward": (C.c_int, [vp, i32, i32, vp, i64, vp, i64, vp, i32, i32, vp, i64, vp, vp]),
+    "mmlrec_heads_backward_external": (C.c_int, [vp, i32, i32, vp, i64, vp, i64, vp, i32, vp, i64, vp, vp]),
     "mmlrec_heads_scratch": (i64, [i32, i32, i32]),
     "mmlrec_dense_optimizer_step": (C.c_int, [vp, vp, vp, vp, i64, vp, vp, vp]),
     "mmlrec_dense_optimizer_step_sliced": (C.c_int, [vp, vp, vp, vp, i64, vp, vp, i32, i64, vp]),

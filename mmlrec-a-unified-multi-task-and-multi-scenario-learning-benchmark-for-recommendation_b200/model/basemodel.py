@@ -36,6 +36,43 @@ class _FusedOptimizerHandle:
         return f"FusedOptimizer({self.name}, lr={self.lr})"
 
 
+class _FusedForward(torch.autograd.Function):
+    """``model(X)`` as one autograd node: forward = the step program's forward kernels, backward = its backward kernels
+    fed with autograd's dL/d(pred).  Parameters enter as inputs so that their ``.grad`` is filled like the reference's
+    (dense ``[V, D]`` gradients for the embedding tables, as ``nn.Embedding(sparse=False)`` produces).  The program's
+    buffers are reused: call ``backward()`` before the next forward of the same batch size."""
+
+    @staticmethod
+    def forward(ctx, model, plan, X, *params):
+        plan.X.copy_(X, non_blocking=True)
+        plan.autograd_forward(model.training)
+        ctx.model, ctx.plan, ctx.params = model, plan, params
+        return plan.pred.clone()
+
+    @staticmethod
+    def backward(ctx, d_pred):
+        model, plan = ctx.model, ctx.plan
+        d_in = plan.autograd_backward(d_pred.contiguous())
+        st = model.store
+        emb_of = {id(t[0]): t for t in model.embedding_layout}
+        grads = []
+        for p in ctx.params:
+            if id(p) in emb_of:
+                if d_in is None:
+                    grads.append(None)
+                    continue
+                _, vocab, xcol, ocol = emb_of[id(p)]
+                ids = plan.X[:, xcol].long().clamp_(0, vocab - 1)
+                g = torch.zeros_like(p)
+                g.index_add_(0, ids, d_in[:, ocol:ocol + model.emb_dim].float())
+                grads.append(g)
+            elif getattr(p, "_mm_kind", "") == "dense":
+                grads.append(st.grad_view(p).clone())
+            else:
+                grads.append(None)
+        return (None, None, None, *grads)
+
+
 class BaseModel(nn.Module):
     def __init__(self, linear_feature_columns, dnn_feature_columns, init_std=0.0001, device="cpu", gpus=None,
                  config=None):
@@ -106,6 +143,7 @@ class BaseModel(nn.Module):
         self.dp = None  # set by mmlrec_b200.parallel.attach()
         self.optimizer_name: Optional[str] = None
         self.lazy_adam, self.adam_hist, self._steps_since_flush = False, None, 0
+        self._user_optimizer = None
         self.hyper_dev: Optional[torch.Tensor] = None
         self.metrics, self.metrics_names = {}, ["loss"]
 
@@ -194,8 +232,14 @@ class BaseModel(nn.Module):
     # ------------------------------------------------------------------ compile
     def compile(self, optimizer, loss=None, metrics=None):
         self.metrics_names = ["loss"]
-        if not isinstance(optimizer, str):
-            raise NotImplementedError("pass the optimizer by name: the update is fused into the CUDA step")
+        self._user_optimizer = None
+        if isinstance(optimizer, torch.optim.Optimizer):
+            # an optimizer INSTANCE (basemodel.py:557-567 accepts one): its update cannot be fused, so training goes
+            # through the differentiable forward + autograd + optimizer.step() -- the reference's own step body
+            self._user_optimizer = optimizer
+            optimizer = "sgd"   # (fused-state bookkeeping below; the fused update is not used)
+        elif not isinstance(optimizer, str):
+            raise NotImplementedError("optimizer must be a name or a torch.optim.Optimizer over model.parameters()")
         if optimizer not in ("sgd", "adam", "adagrad", "rmsprop"):
             raise NotImplementedError
         if self.model_config["model_name"] == "pcg":
@@ -224,7 +268,7 @@ class BaseModel(nn.Module):
             self.adam_hist = (torch.zeros(2 * self.adam_hist_cap, dtype=torch.float32, device=self.device_obj)
                               if self.lazy_adam else None)
             self._steps_since_flush = 0
-        self.optim = _FusedOptimizerHandle(optimizer, self.optim_config.get("lr", 1e-3))
+        self.optim = self._user_optimizer or _FusedOptimizerHandle(optimizer, self.optim_config.get("lr", 1e-3))
 
     def _get_metrics(self, metrics):
         from sklearn.metrics import accuracy_score, log_loss, mean_squared_error, roc_auc_score
@@ -266,6 +310,12 @@ class BaseModel(nn.Module):
         if self.shard is not None:
             self.shard.check()   # a peer-memory barrier that gave up waiting means a rank is gone: stop, do not train on
 
+    def sync_parameters(self) -> None:
+        """After parameters were changed from outside the fused step (an external optimizer, manual edits): refresh
+        the bf16 shadow of the dense parameters the tensor-core GEMMs read."""
+        if self.store is not None:
+            self.store.refresh_bf16()
+
     def flush_tables(self) -> None:
         """Lazy dense-Adam: bring every table row up to the current optimizer step (no-op otherwise).  Runs before the
         tables are read outside a training step (eval forward, predict, state_dict, deepcopy)."""
@@ -283,7 +333,25 @@ class BaseModel(nn.Module):
         self.flush_tables()
         return super().state_dict(*args, **kwargs)
 
+    def _autograd_step(self, p: StepPlan) -> None:
+        """The reference's step body (basemodel.py:262-313) with a user-supplied optimizer: forward -> sum of the
+        per-task losses -> backward -> optimizer.step(), on the fused forward / backward kernels."""
+        import torch.nn.functional as F
+        fns = {"binary_crossentropy": F.binary_cross_entropy, "mse": F.mse_loss, "mae": F.l1_loss}
+        with torch.enable_grad():
+            pred = _FusedForward.apply(self, p, p.X.clone(), *[q for q in self.parameters()])
+            self._user_optimizer.zero_grad()
+            per_task = [fns[self.loss_names[t]](pred[:, t], p.y[:, t], reduction="sum") for t in range(self.num_tasks)]
+            total = sum(per_task)
+            total.backward()
+        self._user_optimizer.step()
+        self.sync_parameters()
+        p.loss.copy_(torch.stack([v.detach() for v in per_task] + [total.detach()]))
+
     def _run_train(self, p: StepPlan) -> None:
+        if self._user_optimizer is not None:
+            self._autograd_step(p)
+            return
         n = self._steps_on_plan[p.B]
         if self.lazy_adam:
             if self._steps_since_flush >= self.adam_hist_cap - 2:   # the history ring is about to wrap
@@ -302,14 +370,20 @@ class BaseModel(nn.Module):
         self._steps_on_plan[p.B] = n + 1
 
     def forward(self, X, domain_mask=None):
-        """Probabilities ``[B, T]`` (sigmoid applied for 'binary' heads).  Inference-only: the result
-        carries no autograd graph (training goes through ``fit`` / ``train_on_batch``)."""
+        """Probabilities ``[B, T]`` (sigmoid applied for 'binary' heads), like the reference's ``forward``
+        (model/mmoe.py:65).  With autograd enabled the result is differentiable with respect to every parameter
+        (``loss.backward()`` fills ``.grad``; any ``torch.optim`` optimizer over ``model.parameters()`` then works --
+        call ``model.sync_parameters()`` after ``optimizer.step()`` in bf16 mode).  The fused training step of
+        ``fit`` / ``train_on_batch`` does not come through here."""
         X = torch.as_tensor(X)
         self.flush_tables()
         p = self.plan(X.shape[0])
-        p.X.copy_(X, non_blocking=True)
-        p.forward(training=self.training)
-        out = p.pred.clone()
+        if torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters()):
+            out = _FusedForward.apply(self, p, X.to(self.device_obj), *[q for q in self.parameters()])
+        else:
+            p.X.copy_(X, non_blocking=True)
+            p.forward(training=self.training)
+            out = p.pred.clone()
         if domain_mask is not None:
             dm = torch.as_tensor(domain_mask).to(out)
             if self.task_name == "msl":

@@ -296,3 +296,59 @@ def test_out_of_range_id_is_clamped_flagged_and_raised_on_the_host():
     moved = (after[t1] != before[t1]).any(dim=1).nonzero().flatten().tolist()
     assert set(moved) <= ids1, "rows of the next table that the batch did not touch were written"
     model.check_ids()   # the flag was consumed
+
+
+@pytest.mark.parametrize("case", ["ple_ae_t4_adam", "mmoe_census_bn_adam", "esmm_kuairec_adam", "pepnet_movielens_adam"])
+def test_forward_is_differentiable_like_the_reference(case):
+    """``model(X)`` returns probabilities with an autograd graph; a loss built on them by the caller
+    back-propagates into EVERY parameter's ``.grad`` (dense [V, D] gradients for the tables), equal to what the
+    reference's ``loss.backward()`` left (golden grad0/*)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import torch.nn.functional as F
+    z, cfg, fields = load_golden(case)
+    model, cfg = build_model(cfg, fields)
+    load_init(model, z)
+    model.compile(cfg["optim_config"]["optimizer"], cfg["optim_config"]["loss"], [])
+    model.train()
+    X, y = torch.from_numpy(z["step0/X"]).cuda(), torch.from_numpy(z["step0/y"]).cuda()
+    pred = model(X)
+    assert pred.requires_grad and rel_err(pred.detach().cpu(), z["step0/pred"]) < 1e-5
+    loss = sum(F.binary_cross_entropy(pred[:, t], y[:, t], reduction="sum") for t in range(y.shape[1]))
+    loss.backward()
+    assert abs(float(loss) - float(z["step0/loss"])) <= 2e-5 * abs(float(z["step0/loss"]))
+    gradless = set(str(n) for n in z["meta/gradless"])
+    use_bn = cfg["model_config"].get("dnn_use_bn", False)
+    checked = 0
+    for name, prm in model.named_parameters():
+        if name in gradless:
+            assert prm.grad is None or float(prm.grad.abs().max()) == 0.0, name
+            continue
+        want = torch.from_numpy(z["grad0/" + name])
+        assert prm.grad is not None, f"{name} received no gradient"
+        scale = float(want.abs().max())
+        floor = 1e-9
+        if use_bn and ".linears." in name and name.endswith(".bias"):
+            floor = 1e-4 * float(np.abs(z["grad0/" + name[:-4] + "weight"]).max())   # exactly-zero true gradient
+        assert float((prm.grad.cpu() - want).abs().max()) <= 1e-5 * scale + floor, name
+        checked += 1
+    assert checked > 5
+
+
+def test_compile_accepts_an_optimizer_instance():
+    """basemodel.py:557-567: ``compile`` takes an optimizer object too.  Training then runs the reference's own step
+    body (differentiable forward -> autograd -> optimizer.step()); with torch.optim.Adam it must track the golden run."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    z, cfg, fields = load_golden("sharedbottom_kuairec_adam")
+    model, cfg = build_model(cfg, fields)
+    load_init(model, z)
+    opt = torch.optim.Adam(model.parameters(), lr=cfg["optim_config"]["lr"])
+    model.compile(opt, cfg["optim_config"]["loss"], [])
+    assert model.optim is opt
+    model.train()
+    for s in range(3):
+        loss = model.train_on_batch(torch.from_numpy(z[f"step{s}/X"]), torch.from_numpy(z[f"step{s}/y"]))
+        want = float(z[f"step{s}/loss"])
+        assert abs(float(loss[-1]) - want) <= 2e-5 * abs(want), f"step {s}"
+        assert rel_err(model.plan(z[f"step{s}/X"].shape[0]).pred.cpu(), z[f"step{s}/pred"]) < 1e-5
