@@ -271,17 +271,19 @@ class BaseModel(nn.Module):
         self.optim = self._user_optimizer or _FusedOptimizerHandle(optimizer, self.optim_config.get("lr", 1e-3))
 
     def _get_metrics(self, metrics):
-        from sklearn.metrics import accuracy_score, log_loss, mean_squared_error, roc_auc_score
+        """Metric table with the reference's names (basemodel.py:616-635).  The functions are the device-side
+        equivalents of the sklearn calls (mmlrec_b200/metrics.py): they take CUDA tensors and return python floats."""
+        from .. import metrics as M
         table = {}
         for m in metrics or []:
             if m in ("binary_crossentropy", "logloss"):
-                table[m] = log_loss
+                table[m] = M.log_loss
             if m == "auc":
-                table[m] = roc_auc_score
+                table[m] = M.roc_auc_score
             if m == "mse":
-                table[m] = mean_squared_error
+                table[m] = M.mean_squared_error
             if m in ("accuracy", "acc"):
-                table[m] = lambda y_true, y_pred: accuracy_score(y_true, np.where(y_pred > 0.5, 1, 0))
+                table[m] = M.accuracy_score
             self.metrics_names.append(m)
         return table
 
@@ -420,7 +422,20 @@ class BaseModel(nn.Module):
             X, y, val = X[:cut], y[:cut], (X[cut:], y[cut:])
         batch_size = 256 if batch_size is None else batch_size
         dev = self.device_obj
-        Xd, yd = torch.from_numpy(X).to(dev), torch.from_numpy(y).to(dev)
+        # input pipeline.  A dataset that fits is kept in HBM and batches are index_select'ed on the
+        # device; a larger one stays in PINNED host memory and every batch is gathered on the host into one of two pinned
+        # staging buffers and copied on a side stream while the previous step is still running (double buffering).
+        resident = (X.nbytes + y.nbytes) <= int(self.b200_config.get("max_resident_bytes", 16 << 30))
+        if resident:
+            Xd, yd = torch.from_numpy(X).to(dev), torch.from_numpy(y).to(dev)
+        else:
+            Xh, yh = torch.from_numpy(X).pin_memory(), torch.from_numpy(y).pin_memory()
+            stage = [(torch.empty(batch_size, X.shape[1]).pin_memory(), torch.empty(batch_size, y.shape[1]).pin_memory())
+                     for _ in range(2)]
+            dstage = [(torch.empty(batch_size, X.shape[1], device=dev), torch.empty(batch_size, y.shape[1], device=dev))
+                      for _ in range(2)]
+            copy_stream = torch.cuda.Stream(device=dev)
+            copied, consumed = [torch.cuda.Event(), torch.cuda.Event()], [torch.cuda.Event(), torch.cuda.Event()]
         n = len(X)
         steps = (n - 1) // batch_size + 1
         # the reference's DataLoader(shuffle=True) consumes the global torch RNG; iterating a DataLoader
@@ -432,14 +447,31 @@ class BaseModel(nn.Module):
         best_auc, stall, best_model = 0, 0, None
         for epoch in range(initial_epoch, epochs):
             t0 = time.time()
-            preds, idxs, losses = [], [], []
-            for (idx,) in loader:
-                idx_d = idx.to(dev, non_blocking=True)
+            preds, idxs, losses, ys = [], [], [], []
+            for k, (idx,) in enumerate(loader):
                 p = self.plan(len(idx))
-                torch.index_select(Xd, 0, idx_d, out=p.X)
-                torch.index_select(yd, 0, idx_d, out=p.y)
+                if resident:
+                    idx_d = idx.to(dev, non_blocking=True)
+                    torch.index_select(Xd, 0, idx_d, out=p.X)
+                    torch.index_select(yd, 0, idx_d, out=p.y)
+                else:
+                    (sx, sy), (dx, dy), nb = stage[k & 1], dstage[k & 1], len(idx)
+                    copied[k & 1].synchronize()   # host: the H2D copy that last read this pinned pair (batch k-2) is done
+                    torch.index_select(Xh, 0, idx, out=sx[:nb])   # host gather -- the GPU is still busy with step k-1
+                    torch.index_select(yh, 0, idx, out=sy[:nb])
+                    with torch.cuda.stream(copy_stream):          # H2D beside the running step
+                        copy_stream.wait_event(consumed[k & 1])   # (batch k-2 has been moved out of this device pair)
+                        dx[:nb].copy_(sx[:nb], non_blocking=True)
+                        dy[:nb].copy_(sy[:nb], non_blocking=True)
+                        copied[k & 1].record()
+                    main = torch.cuda.current_stream()
+                    main.wait_event(copied[k & 1])
+                    p.X.copy_(dx[:nb], non_blocking=True)         # device -> device into the step program's input
+                    p.y.copy_(dy[:nb], non_blocking=True)
+                    consumed[k & 1].record(main)
                 self._run_train(p)
                 preds.append(p.pred.clone())
+                ys.append(p.y.clone())
                 losses.append(p.loss[self.num_tasks].clone())
                 idxs.append(idx)
             total = float(torch.stack(losses).sum().item())
@@ -447,8 +479,7 @@ class BaseModel(nn.Module):
             logs = {"loss": total / n, "cka_loss": 0.0}
             if self.metrics:
                 sums = {k: 0.0 for k in self.metrics}
-                for idx, pr in zip(idxs, preds):
-                    yt, yp = y[idx.numpy()], pr.cpu().numpy().astype("float64")
+                for yt, yp in zip(ys, preds):
                     for name, fn in self.metrics.items():
                         try:
                             sums[name] += self._train_metric(fn, yt, yp)
@@ -470,7 +501,8 @@ class BaseModel(nn.Module):
             line = "{0}s - loss: {1: .4f} - cka_loss: {2: .4f}".format(int(time.time() - t0), logs["loss"], 0.0)
             for name in self.metrics:
                 line += " - {0}: {1: .4f}".format(name, logs.get(name, float("nan")))
-                if val is not None:
+            if val is not None:
+                for name in self.metrics:
                     line += " - val_{0}: {1: .4f}".format(name, logs.get("val_" + name, float("nan")))
             print(line)
             if stall >= self.optim_config.get("early_stop", 3):
@@ -478,25 +510,31 @@ class BaseModel(nn.Module):
         return best_model if best_model is not None else self
 
     def _train_metric(self, fn, y_true, y_pred):
+        """The reference's metric inputs per task type (basemodel.py:316-331, :383-392); tensors on the device."""
         if self.task_name == "msl":
-            return fn(y_true[:, 0], y_pred.sum(axis=-1))
+            return fn(y_true[:, 0], y_pred.sum(dim=-1))
         if self.task_name == "mtmsl":
             d = self.num_domains
-            return fn(y_true[:, [0, d]], np.stack([y_pred[:, :d].sum(-1), y_pred[:, d:].sum(-1)], axis=-1))
+            return fn(y_true[:, [0, d]], torch.stack([y_pred[:, :d].sum(-1), y_pred[:, d:].sum(-1)], dim=-1))
         return fn(y_true, y_pred)
 
     def evaluate(self, x, y, batch_size=256, domain_mask=None):
-        pred = self.predict(x, batch_size, domain_mask)
-        y = np.asarray(y)
-        return {name: self._train_metric(fn, y, pred) for name, fn in self.metrics.items()}
+        pred = self.predict_device(x, batch_size, domain_mask)
+        yt = torch.as_tensor(np.asarray(y, dtype=np.float32)).reshape(pred.shape[0], -1).to(self.device_obj)
+        return {name: self._train_metric(fn, yt, pred) for name, fn in self.metrics.items()}
 
-    def predict(self, x, batch_size=256, domain_mask=None):
+    def predict_device(self, x, batch_size=256, domain_mask=None) -> torch.Tensor:
+        """``predict`` without the trip to the host: float32 ``[N, T]`` on the device."""
         self._require_cuda()
         self.flush_tables()
         was_training = self.training
         self.eval()
         arr = x.astype(np.float32) if isinstance(x, np.ndarray) and x.ndim == 2 else self._stack_inputs(x)
         X = torch.from_numpy(np.ascontiguousarray(arr)).to(self.device_obj)
+        # the reference iterates a DataLoader here (basemodel.py:425-426); creating its iterator draws one int64 from
+        # the global torch RNG (the loader's base seed) even without shuffling.  Drawing it too keeps the RNG stream
+        # -- hence the shuffle order of the NEXT training epoch -- identical to the reference's (SURVEY H7)
+        torch.empty((), dtype=torch.int64).random_()
         out = []
         for a in range(0, len(X), batch_size):
             xb = X[a:a + batch_size]
@@ -505,9 +543,18 @@ class BaseModel(nn.Module):
             p.forward(training=False)
             out.append(p.pred.clone())
         self.train(was_training)
-        res = torch.cat(out).cpu().numpy().astype("float64")
+        res = torch.cat(out)
+        if domain_mask is not None:
+            dm = torch.as_tensor(domain_mask).to(res)
+            if self.task_name == "msl":
+                res = res * dm
+            elif self.task_name == "mtmsl":
+                res = res * dm[:, [i % self.num_domains for i in range(self.num_tasks)]]
         self.check_ids()
         return res
+
+    def predict(self, x, batch_size=256, domain_mask=None):
+        return self.predict_device(x, batch_size, domain_mask).cpu().numpy().astype("float64")
 
     def update_save(self, value=True):
         self.save_layer_output = value
