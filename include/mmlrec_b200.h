@@ -234,8 +234,8 @@ typedef struct MmlrecGemmTcDesc {           /* host-side description of one prob
   int32_t act, accumulate;                  /* accumulate applies to C_f32 only */
   /* ReLU bit masks (1 bit per element, used by the CTA-pair kernel; the one-CTA kernel ignores them and needs `mask`).
    * Layout of a bit array over a row-major [rows, 32 * chunks] activation: word ((row / 32) * chunks + col / 32) * 32
-   * + row % 32 holds the 32 columns [32 * (col / 32), +32) of that row, so the 32 rows a warp handles are 128
-   * contiguous bytes.  `relu_bits_out`: the epilogue also stores "result > 0" for its outputs (forward of a ReLU layer);
+   * + row % 32 holds the 32 columns [32 * (col / 32), +32) of that row (column j of the chunk at bit j / 2 + 16 * (j % 2):
+   * the two halves of a packed bf16 pair sit 16 bits apart), so the 32 rows a warp handles are 128 contiguous bytes.  `relu_bits_out`: the epilogue also stores "result > 0" for its outputs (forward of a ReLU layer);
    * `mask_bits`: applied instead of `mask` (dgrad through that ReLU).  *_chunks = words per row block, *_chunk0 = the
    * chunk of this problem's column 0 (its first column must be a multiple of 32). */
   uint32_t* relu_bits_out; int32_t bits_out_chunks, bits_out_chunk0;

@@ -13,6 +13,9 @@
 //                 released by an mbarrier arrive on the leader (remote for the peer CTA)
 // D[M,N] = A * B^T, operands K-major or MN-major, bias gradient by an extra N=16 MMA against an all-ones tile,
 // exactly as in gemm_tc.cu; split-K is expressed by the caller as several problems over K slices.
+#include <cstdlib>
+#include <cstring>
+
 #include "tc_common.cuh"
 
 namespace mmlrec {
@@ -48,6 +51,7 @@ struct alignas(128) Tc2Record {
   int32_t rowsum_col;                           // TMEM column (inside the stage) that receives the row sums
   uint32_t* bits_out; const uint32_t* mask_bits; // ReLU bit masks (see MmlrecGemmTcDesc)
   int32_t bits_out_chunks, bits_out_chunk0, mask_bits_chunks, mask_bits_chunk0;
+  int32_t epi;                                  // epilogue variant (EPI_*), chosen at encode time
 };
 
 // the scalar part of a record, cached in shared memory once per CTA (every role reads it at every tile)
@@ -61,8 +65,21 @@ struct Tc2Meta {
   int32_t has_f32, has_bf16;
   int32_t bn, rowsum_col;
   int32_t bits_out_chunks, bits_out_chunk0, mask_bits_chunks, mask_bits_chunk0;
-  int32_t pad_;
+  int32_t epi;
   uint32_t* bits_out; const uint32_t* mask_bits;
+};
+
+// Epilogue variants.  The generic one handles every combination of mask / bias / activation / output precision at
+// ~10 instructions per accumulator element; the step's hot problems (K <= 256 forward layers, K = 128 dgrad) are bound
+// by exactly that instruction stream, so the common combinations get straight-line variants of 1.5-3 instructions per
+// element built on packed arithmetic (FADD2, F2FP.RELU.PACK, PRMT sign replication).
+enum : int {
+  EPI_GENERIC = 0,
+  EPI_BF16_FWD_BITS = 1,     // bf16 out = relu(acc + bias), + 1 bit per element ("> 0") for the dgrad through this ReLU
+  EPI_BF16_FWD = 2,          // bf16 out = relu(acc + bias)
+  EPI_BF16_MASKBITS = 3,     // bf16 out = acc where the producer's ReLU bit is set (dgrad into a hidden layer)
+  EPI_F32_FWD = 4,           // fp32 out = relu(acc + bias)
+  EPI_F32_PLAIN = 5,         // fp32 out (+)= acc (wgrad incl. bias-gradient row sums, dgrad into fp32 gradient buffers)
 };
 
 constexpr int T2_SMEM_BYTES = 1024 + T2_STAGES * (T2_A_BYTES + T2_B_BYTES) + T2_EPI_WARPS * T2_OUT_BUF_BYTES +
@@ -140,6 +157,132 @@ __device__ __forceinline__ void load_mask32(uint4 (&mk)[4], const uint16_t* mask
   }
 }
 
+// ---- packed arithmetic of the straight-line epilogue variants ------------------------------------------------------
+// (a0, a1) += (b0, b1): one FADD2
+__device__ __forceinline__ void add2(uint32_t& a0, uint32_t& a1, float b0, float b1) {
+  uint64_t x, y;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(x) : "r"(a0), "r"(a1));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(y) : "f"(b0), "f"(b1));
+  asm("add.rn.f32x2 %0, %0, %1;" : "+l"(x) : "l"(y));
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(a0), "=r"(a1) : "l"(x));
+}
+// {bf16(max(hi, 0)), bf16(max(lo, 0))}: one F2FP.RELU
+__device__ __forceinline__ uint32_t pack_relu_bf16x2(uint32_t lo, uint32_t hi) {
+  uint32_t r;
+  asm("cvt.rn.relu.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(__uint_as_float(hi)), "f"(__uint_as_float(lo)));
+  return r;
+}
+// One 32-column chunk of a ReLU forward layer (thread = row): p[i] = bf16x2 of relu(acc + bias) for columns (2i, 2i+1);
+// returns the chunk's ReLU bit word: bit i <-> column 2i, bit 16 + i <-> column 2i + 1 (see MmlrecGemmTcDesc).
+// A post-ReLU bf16 half h is in [0, 0x7FFF]: h + 0x7FFF carries into bit 15 exactly when h != 0 and never further.
+template <bool BITS>
+__device__ __forceinline__ uint32_t epi_bias_relu_pack(const uint32_t (&r)[32], uint32_t bias_addr, uint32_t (&p)[16]) {
+#pragma unroll
+  for (int g = 0; g < 8; ++g) {
+    const float4 b = ld_shared_f4(bias_addr + 16 * g);
+    uint32_t a0 = r[4 * g], a1 = r[4 * g + 1], a2 = r[4 * g + 2], a3 = r[4 * g + 3];
+    add2(a0, a1, b.x, b.y);
+    add2(a2, a3, b.z, b.w);
+    p[2 * g] = pack_relu_bf16x2(a0, a1);
+    p[2 * g + 1] = pack_relu_bf16x2(a2, a3);
+  }
+  uint32_t w = 0;
+  if (BITS) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w = (w >> 1) | ((p[i] + 0x7FFF7FFFu) & 0x80008000u);
+  }
+  return w;
+}
+// dgrad through a ReLU: p[i] = bf16x2(acc) of columns (2i, 2i+1), zeroed where the column's bit of w is clear.  The two
+// bits of a pair are moved to the sign positions of bytes 0 and 2; PRMT in sign-replication mode widens them to halfwords.
+__device__ __forceinline__ void epi_maskbits_pack(const uint32_t (&r)[32], uint32_t w, uint32_t (&p)[16]) {
+#pragma unroll
+  for (int i = 0; i < 16; ++i) {
+    const uint32_t s = i <= 7 ? (w << (7 - i)) : (w >> (i - 7));
+    uint32_t m;   // (__byte_perm drops the sign-replication bit of the selector digits: PTX directly)
+    asm("prmt.b32 %0, %1, 0, 0xAA88;" : "=r"(m) : "r"(s));
+    p[i] = pack_bf16x2(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])) & m;
+  }
+}
+// position of column j's bit inside a chunk's ReLU bit word
+__device__ __forceinline__ constexpr int relu_bit_pos(int j) { return (j >> 1) + ((j & 1) << 4); }
+// chunk c (0 / 1) of the warp's bf16 staging box: four conflict-free 16-byte stores per row
+__device__ __forceinline__ void stage_bf16_chunk(uint32_t buf, uint32_t row_off, uint32_t sw, int c, const uint32_t (&p)[16]) {
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    st_shared_v4(buf + row_off + (((uint32_t)(4 * c + i) ^ sw) << 4), p[4 * i], p[4 * i + 1], p[4 * i + 2], p[4 * i + 3]);
+}
+__device__ __forceinline__ void stage_f32_chunk(uint32_t buf, uint32_t row_off, uint32_t sw, const uint32_t (&r)[32]) {
+#pragma unroll
+  for (int c16 = 0; c16 < 8; ++c16)
+    st_shared_v4(buf + row_off + (((uint32_t)c16 ^ sw) << 4), r[4 * c16], r[4 * c16 + 1], r[4 * c16 + 2], r[4 * c16 + 3]);
+}
+
+// per-tile values of one epilogue warp that the straight-line variants need
+struct EpiTile {
+  const Tc2Record* R;
+  uint32_t buf, row_off, sw, bias_addr;      // staging box, this row's offset / swizzle phase in it, the warp's bias slot
+  uint32_t mb0, mb1;                         // ReLU bit words of this row (mask variants)
+  uint32_t* bits_word;                       // where this row's bit word of chunk 0 goes (chunk 1: + 32 words)
+  int m_base, n_first, lane, accumulate;
+  bool row_ok, c1_ok;
+};
+
+// The warp's 32 x 64 block, chunk by chunk: tcgen05.ld -> (stage handed back after the last load) -> packed math ->
+// staging box.  KIND is warp-uniform.  bf16 variants fill the warp's 64-column box (the caller issues its bulk store);
+// fp32 variants send one 32-column box per chunk themselves.
+template <int KIND>
+__device__ __forceinline__ void epi_tile_lean(const EpiTile& e, uint32_t taddr, uint32_t release_bar) {
+  constexpr bool BF16 = KIND == EPI_BF16_FWD_BITS || KIND == EPI_BF16_FWD || KIND == EPI_BF16_MASKBITS;
+#pragma unroll
+  for (int c = 0; c < 2; ++c) {
+    if (c == 1 && !e.c1_ok) break;
+    uint32_t r[32];
+    tc_ld32(taddr + 32 * c, r);
+    tc_wait_ld();
+    if (c == 1 || !e.c1_ok) {                  // this warp's last values sit in registers: the stage is free
+      tc_fence_before();
+      __syncwarp();
+      if (e.lane == 0) mbar_arrive_cluster(release_bar, 0);
+    }
+    if (BF16) {
+      uint32_t p[16];
+      if (KIND == EPI_BF16_MASKBITS) {
+        epi_maskbits_pack(r, c == 0 ? e.mb0 : e.mb1, p);
+      } else {
+        const uint32_t w = epi_bias_relu_pack<KIND == EPI_BF16_FWD_BITS>(r, e.bias_addr + 128u * c, p);
+        if (KIND == EPI_BF16_FWD_BITS && e.row_ok) e.bits_word[32 * c] = w;
+      }
+      if (c == 0) {
+        if (e.lane == 0) bulk_wait_read<0>();  // the previous tile's store has read the staging box
+        __syncwarp();
+      }
+      stage_bf16_chunk(e.buf, e.row_off, e.sw, c, p);
+    } else {
+      if (KIND == EPI_F32_FWD) {
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+          const float4 b = ld_shared_f4(e.bias_addr + 128u * c + 16 * g);
+          add2(r[4 * g], r[4 * g + 1], b.x, b.y);
+          add2(r[4 * g + 2], r[4 * g + 3], b.z, b.w);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) r[4 * g + k] = __float_as_uint(fmaxf(__uint_as_float(r[4 * g + k]), 0.f));
+        }
+      }
+      if (e.lane == 0) bulk_wait_read<0>();
+      __syncwarp();
+      stage_f32_chunk(e.buf, e.row_off, e.sw, r);
+      fence_async_smem();
+      __syncwarp();
+      if (e.lane == 0) {
+        if (e.accumulate) tma_reduce_add_2d(&e.R->tmC32, e.buf, e.n_first + 32 * c, e.m_base);
+        else tma_store_2d(&e.R->tmC32, e.buf, e.n_first + 32 * c, e.m_base);
+        bulk_commit();
+      }
+    }
+  }
+}
+
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(T2_THREADS, 1)
 gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __restrict__ prefix, int n_problems, int total_tiles,
                         const int32_t* __restrict__ tile_order, const int32_t* __restrict__ pair_start,
@@ -176,7 +319,7 @@ gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __res
     m.bias = R->bias; m.mask = R->mask; m.ldmask = R->ldmask; m.rowsum_a = R->rowsum_a;
     m.M = R->M; m.N = R->N; m.K = R->K; m.act = R->act; m.accumulate = R->accumulate;
     m.a_mn = R->a_mn; m.b_mn = R->b_mn; m.has_f32 = R->has_f32; m.has_bf16 = R->has_bf16;
-    m.bn = R->bn; m.rowsum_col = R->rowsum_col; m.pad_ = 0;
+    m.bn = R->bn; m.rowsum_col = R->rowsum_col; m.epi = R->epi;
     m.bits_out = R->bits_out; m.mask_bits = R->mask_bits;
     m.bits_out_chunks = R->bits_out_chunks; m.bits_out_chunk0 = R->bits_out_chunk0;
     m.mask_bits_chunks = R->mask_bits_chunks; m.mask_bits_chunk0 = R->mask_bits_chunk0;
@@ -384,6 +527,37 @@ gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __res
       uint32_t rs = 0;
       if (rowsum_out != nullptr) tc_ld1(t_row + rowsum_col, rs);
       const bool first_ok = rows_any && n_first < N;
+      const int kind = mt.epi;
+      if (kind != EPI_GENERIC && nchunks > 0) {
+        // straight-line variants (see EPI_*)
+        const bool c1_ok = rows_any && n_first + 32 < N;
+        if (rowsum_out != nullptr) {
+          tc_wait_ld();
+          if (row_ok) rowsum_out[my_m] = __uint_as_float(rs);
+        }
+        if (!first_ok) {                                         // nothing of this warp's block is inside the problem
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(tempty_bar + 8 * acc, 0);
+        } else {
+          EpiTile e;
+          e.R = R; e.buf = buf; e.row_off = row_off; e.sw = sw; e.bias_addr = bias_addr;
+          e.mb0 = mbits0; e.mb1 = mbits1;
+          e.bits_word = bits_out == nullptr ? nullptr
+              : bits_out + ((int64_t)(my_m >> 5) * mt.bits_out_chunks + mt.bits_out_chunk0 + (n_first >> 5)) * 32 + (my_m & 31);
+          e.m_base = m_base; e.n_first = n_first; e.lane = lane; e.accumulate = accumulate;
+          e.row_ok = row_ok; e.c1_ok = c1_ok;
+          const uint32_t taddr = t_row + col0, rel = tempty_bar + 8 * acc;
+          switch (kind) {
+            case EPI_BF16_FWD_BITS: epi_tile_lean<EPI_BF16_FWD_BITS>(e, taddr, rel); break;
+            case EPI_BF16_FWD:      epi_tile_lean<EPI_BF16_FWD>(e, taddr, rel); break;
+            case EPI_BF16_MASKBITS: epi_tile_lean<EPI_BF16_MASKBITS>(e, taddr, rel); break;
+            case EPI_F32_FWD:       epi_tile_lean<EPI_F32_FWD>(e, taddr, rel); break;
+            default:                epi_tile_lean<EPI_F32_PLAIN>(e, taddr, rel); break;
+          }
+        }
+        if (estamp && it < 64) dbg[it * 16 + 12] = clock64();
+      } else
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         if (c >= nchunks) break;
@@ -403,7 +577,7 @@ gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __res
         if (!c_ok) continue;
         if (mask_bits != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) r[j] = (mb[c] >> j) & 1u ? r[j] : 0u;
+          for (int j = 0; j < 32; ++j) r[j] = (mb[c] >> relu_bit_pos(j)) & 1u ? r[j] : 0u;
         } else if (mask != nullptr) {   // bf16 mask (no bit array for this activation): loaded at use
           uint4 mk[4];
           load_mask32(mk, mask, ldmask, my_m, row_ok, nc, N);
@@ -417,7 +591,7 @@ gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __res
           // "output > 0" of this row's 32 columns as one word (a float is > 0 iff its bits, read as int32, are > 0)
           uint32_t w = 0;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) w |= ((int32_t)r[j] > 0 ? 1u : 0u) << j;
+          for (int j = 0; j < 32; ++j) w |= ((int32_t)r[j] > 0 ? 1u : 0u) << relu_bit_pos(j);
           bits_out[((int64_t)(my_m >> 5) * mt.bits_out_chunks + mt.bits_out_chunk0 + (nc >> 5)) * 32 + (my_m & 31)] = w;
         }
         if (has_f32) {
@@ -531,6 +705,23 @@ extern "C" int mmlrec_tc2_encode_problem(const MmlrecGemmTcDesc* d, void* record
   rec.M = d->M; rec.N = d->N; rec.K = d->K; rec.act = d->act; rec.accumulate = d->accumulate;
   rec.a_mn = d->a_mn_major; rec.b_mn = d->b_mn_major; rec.bn = bn; rec.tiles_n = cdiv(d->N, bn);
   rec.rowsum_col = bn == 128 ? 128 : 240;
+  {
+    const bool any_mask = d->mask != nullptr || d->mask_bits != nullptr;
+    const char* force = getenv("MMLREC_TC2_EPILOGUE");                 // "generic": A/B switch for the profiles
+    int epi = EPI_GENERIC;
+    if (force != nullptr && strcmp(force, "generic") == 0) {
+    } else if (d->C_bf16 != nullptr) {
+      if (!any_mask && d->act == MMLREC_ACT_RELU && d->colsum == nullptr)
+        epi = d->relu_bits_out != nullptr ? EPI_BF16_FWD_BITS : EPI_BF16_FWD;
+      else if (d->mask_bits != nullptr && d->bias == nullptr && d->act == MMLREC_ACT_NONE && d->relu_bits_out == nullptr &&
+               d->colsum == nullptr)
+        epi = EPI_BF16_MASKBITS;
+    } else if (!any_mask && d->relu_bits_out == nullptr) {
+      if (d->act == MMLREC_ACT_RELU && d->colsum == nullptr && !d->accumulate) epi = EPI_F32_FWD;
+      else if (d->act == MMLREC_ACT_NONE && d->bias == nullptr) epi = EPI_F32_PLAIN;
+    }
+    rec.epi = epi;
+  }
   rec.bits_out = d->relu_bits_out; rec.bits_out_chunks = d->bits_out_chunks; rec.bits_out_chunk0 = d->bits_out_chunk0;
   rec.mask_bits = d->mask_bits; rec.mask_bits_chunks = d->mask_bits_chunks; rec.mask_bits_chunk0 = d->mask_bits_chunk0;
   MMLREC_CHECK_ARG(d->relu_bits_out == nullptr || d->bits_out_chunks > 0, "bits_out_chunks");

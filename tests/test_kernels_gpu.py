@@ -341,8 +341,9 @@ def test_gemm_tc_pair_relu_bitmask_roundtrip(M, N, col0):
     got = torch.zeros(M, N, dtype=torch.bool)
     for c in range(N):
         word = b3[rows // 32, (col0 + c) // 32, rows % 32]
-        got[:, c] = ((word >> ((col0 + c) % 32)) & 1).bool()
-    # the bit is taken from the fp32 value before the bf16 rounding: > 0 exactly where the fp32 result is > 0
+        j = (col0 + c) % 32                      # bit position inside the chunk word: even columns low half, odd high
+        got[:, c] = ((word >> ((j >> 1) + 16 * (j & 1))) & 1).bool()
+    # the bit says "the stored bf16 value is > 0" (= the fp32 result is > 0, up to values that round to bf16 zero)
     near = want.cpu().abs() < 1e-3
     assert torch.equal(got | near, (want.cpu() > 0) | near)
     # dgrad through the ReLU: mask by bits == mask by the bf16 activation (wherever the bf16 value did not round to 0)
@@ -357,6 +358,16 @@ def test_gemm_tc_pair_relu_bitmask_roundtrip(M, N, col0):
     base = dz.float() @ W2.float().T
     assert rel_err(out_mask[:, :N], base * (y16[:, :N].float() > 0)) < 1e-5
     assert rel_err(out_bits[:, :N], base * got.to(dev)) < 1e-5
+    # the straight-line epilogue variants with bf16 outputs: ReLU forward without the bit array, dgrad masked by bits
+    assert rel_err(y16[:, :N].float(), want) < 5e-3
+    y16b = torch.zeros_like(y16)
+    out16 = torch.zeros(M, (N + 7) // 8 * 8, dtype=torch.bfloat16, device=dev)
+    d3 = ops.tc_desc(A, W, M, N, K, C_bf16=y16b, bias=bias, act="relu")
+    d4 = ops.tc_desc(dz, W2, M, N, 72, C_bf16=out16, mask_bits=bits, bits_chunks=chunks, bits_chunk0=col0 // 32)
+    ops.TcProblemTable([d3, d4], dev, kernel=2).launch()
+    torch.cuda.synchronize()
+    assert torch.equal(y16b[:, :N], y16[:, :N])
+    assert torch.equal(out16[:, :N], out_bits[:, :N].to(torch.bfloat16)), "same fp32 values, rounded once"
 
 
 # ------------------------------------------------------------------------------------------------ dense optimizer
