@@ -3,6 +3,8 @@
 // element-wise utilities.  All of these are HBM/L2-bound streaming kernels; cross-CTA reductions
 // use per-CTA partials + a "last CTA reduces in fixed order" epilogue (deterministic, no float
 // atomics).
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace mmlrec {
@@ -433,6 +435,173 @@ heads_reduce_kernel(const MmlrecHead* heads, int T, float* loss, int esmm, const
 }
 
 // ------------------------------------------------------------------------------------------------
+// heads + loss, one launch (the training path for T <= TM tasks of width <= 32 * KM).  A warp owns R samples and
+// fetches ALL their tower rows first (R * T * KM independent loads per lane in flight -- the two-kernel version above
+// walks samples and tasks one dependent L2 round trip at a time), keeps them in registers for the logits, d_h and the
+// dw partial, and lane r * TM + t evaluates sigmoid / BCE / dz of (sample r, task t).  CTA partials go to scratch; the
+// LAST CTA to finish (atomic ticket) adds them up in index order, so the result does not depend on which CTA that is.
+// ------------------------------------------------------------------------------------------------
+template <int TM, int KM, int R>
+__global__ void __launch_bounds__(256)
+heads_fast_kernel(const MmlrecHead* heads, int T, int B, const float* y, int64_t ldy, float* pred, int64_t ld_pred,
+                  float* loss, int esmm, float* scratch, int stride_cta, int32_t* counter, int grad_mode) {
+  static_assert(R * TM <= 32, "one lane per (sample, task)");
+  pdl_prologue();
+  constexpr int PW = 2 + KM * 32;                          // per warp and task: loss, dz, dw[KM * 32]
+  __shared__ MmlrecHead Hd[TM];
+  __shared__ float red_s[8][TM][PW];
+  __shared__ float tot_s[TM][2];
+  __shared__ int last_s;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  if (tid < T) Hd[tid] = heads[tid];
+  __syncthreads();
+  const int row0 = (blockIdx.x * 8 + w) * R;
+  float hv[R][TM][KM], wv[TM][KM];
+#pragma unroll
+  for (int t = 0; t < TM; ++t)
+#pragma unroll
+    for (int k = 0; k < KM; ++k) {
+      const int h = lane + 32 * k;
+      const bool ok = t < T && h < Hd[t].H;
+      wv[t][k] = ok ? __ldg(Hd[t].w + h) : 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+        hv[r][t][k] = (ok && row0 + r < B) ? Hd[t].h[(int64_t)(row0 + r) * Hd[t].ld_h + h] : 0.f;
+    }
+  // logits: after the butterfly every lane holds every sum; lane r * TM + t keeps z of (sample r, task t)
+  const int my_r = lane / TM, my_t = lane - my_r * TM;
+  const int my_b = row0 + my_r;
+  const bool mine = my_r < R && my_t < T && my_b < B;
+  float z = 0.f;
+#pragma unroll
+  for (int r = 0; r < R; ++r)
+#pragma unroll
+    for (int t = 0; t < TM; ++t) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < KM; ++k) s = fmaf(hv[r][t][k], wv[t][k], s);
+      s = warp_sum(s);
+      if (lane == r * TM + t) z = s;
+    }
+  if (mine) z += (Hd[my_t].bias ? *Hd[my_t].bias : 0.f) + (Hd[my_t].bias2 ? *Hd[my_t].bias2 : 0.f);
+  const float z0 = __shfl_sync(0xffffffffu, z, my_r * TM < 32 ? my_r * TM : 0);   // task 0 of the same sample (esmm)
+  float dz = 0.f, l = 0.f, cross = 0.f;
+  if (mine) {
+    if (Hd[my_t].kind == MMLREC_HEAD_SIGMOID_BCE) {
+      const float p = 1.f / (1.f + expf(-z));
+      float out = p, scale = 1.f;
+      if (esmm && my_t == 1) {                               // esmm.py:59  ctcvr = ctr * cvr
+        const float p0 = 1.f / (1.f + expf(-z0));
+        out = p0 * p;
+        scale = p0;
+      }
+      pred[(int64_t)my_b * ld_pred + my_t] = out;
+      const float yy = y[(int64_t)my_b * ldy + my_t];
+      float gout;
+      if (grad_mode) {
+        gout = yy;
+      } else {   // same formulas as heads_kernel (F.binary_cross_entropy forward / backward, sigmoid_backward)
+        l = (yy - 1.f) * fmaxf(log1pf(-out), -100.f) - yy * fmaxf(logf(out), -100.f);
+        gout = (out - yy) / fmaxf((1.f - out) * out, 1e-12f);
+      }
+      dz = gout * scale * (1.f - p) * p;
+      if (esmm && my_t == 1) cross = gout * p;
+    } else {
+      pred[(int64_t)my_b * ld_pred + my_t] = z;
+      if (grad_mode) { dz = y[(int64_t)my_b * ldy + my_t]; }
+      else { const float d = z - y[(int64_t)my_b * ldy + my_t]; l = d * d; dz = 2.f * d; }
+    }
+  }
+  if (esmm) {   // head 0 also receives gradient through out1 = p0 * p1
+    const float c1 = __shfl_sync(0xffffffffu, cross, (lane + 1) & 31);
+    if (mine && my_t == 0) {
+      const float p0 = 1.f / (1.f + expf(-z));
+      dz += c1 * (1.f - p0) * p0;
+    }
+  }
+  // d_h rows and this warp's partials
+#pragma unroll
+  for (int t = 0; t < TM; ++t) {
+    float dzr[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) dzr[r] = __shfl_sync(0xffffffffu, dz, r * TM + t);
+    if (t >= T) continue;   // warp-uniform
+    const MmlrecHead& hd = Hd[t];
+    float ls = 0.f, ds = 0.f;
+#pragma unroll
+    for (int r = 0; r < R; ++r) { ls += __shfl_sync(0xffffffffu, l, r * TM + t); ds += dzr[r]; }
+    if (lane == 0) { red_s[w][t][0] = ls; red_s[w][t][1] = ds; }
+#pragma unroll
+    for (int k = 0; k < KM; ++k) {
+      const int h = lane + 32 * k;
+      float dw = 0.f;
+#pragma unroll
+      for (int r = 0; r < R; ++r) dw = fmaf(dzr[r], hv[r][t][k], dw);
+      red_s[w][t][2 + h] = dw;
+      if (h >= hd.H) continue;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (row0 + r >= B) break;
+        float g = dzr[r] * wv[t][k];
+        if (hd.relu_mask && !(hv[r][t][k] > 0.f)) g = 0.f;
+        if (hd.d_h) hd.d_h[(int64_t)(row0 + r) * hd.ld_d_h + h] = g;
+        if (hd.d_h_bf16) hd.d_h_bf16[(int64_t)(row0 + r) * hd.ld_d_h_bf16 + h] = float_to_bf16_bits(g);
+      }
+    }
+  }
+  __syncthreads();
+  // CTA partial -> scratch [cta][T][2 + hmax] (warps summed in fixed order)
+  const int per_t = stride_cta / T, n_out = T * per_t;
+  float* cta_out = scratch + (int64_t)blockIdx.x * stride_cta;
+  for (int i = tid; i < n_out; i += 256) {
+    const int t = i / per_t, k = i - t * per_t;
+    float s = 0.f;
+    if (k < PW) {
+#pragma unroll
+      for (int ww = 0; ww < 8; ++ww) s += red_s[ww][t][k];
+    }
+    cta_out[i] = s;
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) last_s = atomicAdd(counter, 1) == (int)gridDim.x - 1 ? 1 : 0;
+  __syncthreads();
+  if (!last_s) return;
+  if (tid == 0) *counter = 0;                                // ready for the next launch / graph replay
+  __threadfence();
+  const int n_cta = (int)gridDim.x;
+  for (int i = tid; i < n_out; i += 256) {
+    float a[16];
+#pragma unroll
+    for (int q = 0; q < 16; ++q) a[q] = 0.f;
+    int c = 0;
+    for (; c + 16 <= n_cta; c += 16) {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) a[q] += __ldcg(scratch + (int64_t)(c + q) * stride_cta + i);
+    }
+    for (; c < n_cta; ++c) a[0] += __ldcg(scratch + (int64_t)c * stride_cta + i);
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) v += a[q];
+    const int t = i / per_t, k = i - t * per_t;
+    if (k < 2) tot_s[t][k] = v;
+    else if (k - 2 < Hd[t].H) Hd[t].dw[k - 2] = v;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float total = 0.f;
+    for (int q = 0; q < T; ++q) { loss[q] = tot_s[q][0]; total += tot_s[q][0]; }
+    loss[T] = total;
+    if (esmm) {
+      if (Hd[0].dbias) *Hd[0].dbias = tot_s[0][1] + tot_s[1][1];
+    } else {
+      for (int q = 0; q < T; ++q) if (Hd[q].dbias) *Hd[q].dbias = tot_s[q][1];
+    }
+    for (int q = 0; q < T; ++q) if (Hd[q].dbias2) *Hd[q].dbias2 = tot_s[q][1];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // flat dense optimizer + element-wise utilities
 // ------------------------------------------------------------------------------------------------
 __global__ void dense_optimizer_kernel(float* p, const float* g, float* s1, float* s2, int64_t n,
@@ -706,6 +875,20 @@ static int heads_launch(const MmlrecHead* heads, int32_t T, int32_t B, const flo
       cudaError_t e = cudaFuncSetAttribute(heads_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) { set_error("heads: smem opt-in failed"); return (int)e; }
       opted = smem;
+    }
+  }
+  if (training && y != nullptr && getenv("MMLREC_HEADS_TWO_KERNELS") == nullptr) {
+    // one-launch path: rows fetched up front, last CTA reduces (heads_fast_kernel)
+    const int hmax = stride_cta / T - 2;
+    if (T <= 4 && hmax <= 64) {
+      launch_pdl(heads_fast_kernel<4, 2, 4>, dim3(cdiv(B, 32)), dim3(256), 0, stream, heads, T, B, y, ldy, pred, ld_pred, loss,
+                 esmm, scratch, stride_cta, counters, grad_mode);
+      MMLREC_RETURN_LAUNCH(1);
+    }
+    if (T <= 8 && hmax <= 128) {
+      launch_pdl(heads_fast_kernel<8, 4, 2>, dim3(cdiv(B, 16)), dim3(256), 0, stream, heads, T, B, y, ldy, pred, ld_pred, loss,
+                 esmm, scratch, stride_cta, counters, grad_mode);
+      MMLREC_RETURN_LAUNCH(1);
     }
   }
   launch_pdl(heads_kernel, dim3(n_cta), dim3(256), smem, stream, heads, T, B, y, ldy, pred, ld_pred, loss, esmm, training, scratch,
