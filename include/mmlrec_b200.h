@@ -363,6 +363,9 @@ typedef struct MmlrecGateLevel {
   uint16_t* d_gate_in_bf16[MMLREC_LEVEL_MAX_GATES]; int64_t ld_d_gate_in_bf16[MMLREC_LEVEL_MAX_GATES];
   int32_t relu_mask_gate_in[MMLREC_LEVEL_MAX_GATES]; int32_t accumulate_d_gate_in[MMLREC_LEVEL_MAX_GATES];
   float* dWg[MMLREC_LEVEL_MAX_GATES];
+  /* bit g set: gate g mixes expert u as a CONSTANT (`x.detach()`, hmoe.py:130): its mixture and its softmax gradient
+   * use the expert's value, but no gradient flows from gate g into d_expert[u] (tiled backward only) */
+  uint32_t detach_mask[MMLREC_LEVEL_MAX_EXPERTS];
 } MmlrecGateLevel;
 int mmlrec_gate_level_forward(const MmlrecGateLevel* level, int32_t B, void* stream);
 int mmlrec_gate_level_backward(const MmlrecGateLevel* level, int32_t B, int32_t total_wg /* sum_g n_e[g]*Hg[g] */,

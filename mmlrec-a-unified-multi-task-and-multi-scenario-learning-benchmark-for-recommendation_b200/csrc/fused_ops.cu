@@ -281,6 +281,8 @@ heads_kernel(const MmlrecHead* heads, int T, int B, const float* y, int64_t ldy,
   if (tid < T) Hd[tid] = heads[tid];
   __syncthreads();
   const bool bwd = training && y != nullptr;
+  const bool cum_bias = (esmm & 2) != 0;   // MMLREC_HEADS_CUMULATIVE_BIAS
+  esmm &= 1;
   const int hmax = bwd ? (stride_cta / T) - 2 : 0;
   float* my_dw = dw_s + (size_t)w * T * hmax;
   if (bwd) for (int i = lane; i < T * hmax; i += 32) my_dw[i] = 0.f;
@@ -295,7 +297,10 @@ heads_kernel(const MmlrecHead* heads, int T, int B, const float* y, int64_t ldy,
       float s = 0.f;
       for (int h = lane; h < Hd[t].H; h += 32) s = fmaf(hrow[h], __ldg(Hd[t].w + h), s);
       s = warp_sum(s);
-      if (lane == t) z = s + (Hd[t].bias ? *Hd[t].bias : 0.f) + (Hd[t].bias2 ? *Hd[t].bias2 : 0.f);
+      if (lane == t) {
+        z = s + (Hd[t].bias ? *Hd[t].bias : 0.f) + (Hd[t].bias2 ? *Hd[t].bias2 : 0.f);
+        if (cum_bias) for (int q = 0; q < t; ++q) z += Hd[q].bias ? *Hd[q].bias : 0.f;
+      }
     }
     // probabilities, loss terms, dz (lanes < T)
     const float z0 = __shfl_sync(0xffffffffu, z, 0);
@@ -483,7 +488,12 @@ heads_fast_kernel(const MmlrecHead* heads, int T, int B, const float* y, int64_t
       s = warp_sum(s);
       if (lane == r * TM + t) z = s;
     }
-  if (mine) z += (Hd[my_t].bias ? *Hd[my_t].bias : 0.f) + (Hd[my_t].bias2 ? *Hd[my_t].bias2 : 0.f);
+  const bool cum_bias = (esmm & 2) != 0;   // MMLREC_HEADS_CUMULATIVE_BIAS
+  esmm &= 1;
+  if (mine) {
+    z += (Hd[my_t].bias ? *Hd[my_t].bias : 0.f) + (Hd[my_t].bias2 ? *Hd[my_t].bias2 : 0.f);
+    if (cum_bias) for (int q = 0; q < my_t; ++q) z += Hd[q].bias ? *Hd[q].bias : 0.f;
+  }
   const float z0 = __shfl_sync(0xffffffffu, z, my_r * TM < 32 ? my_r * TM : 0);   // task 0 of the same sample (esmm)
   float dz = 0.f, l = 0.f, cross = 0.f;
   if (mine) {
@@ -519,30 +529,38 @@ heads_fast_kernel(const MmlrecHead* heads, int T, int B, const float* y, int64_t
       dz += c1 * (1.f - p0) * p0;
     }
   }
-  // d_h rows and this warp's partials
+  // this warp's partials (loss, dz, dw) and the d_h rows.  Heads that read the SAME tower output (MLP: one shared
+  // stack, sharedbottom without towers) share its gradient buffer: the first head of such a group writes the sum.
+  float dza[R][TM];
+#pragma unroll
+  for (int t = 0; t < TM; ++t)
+#pragma unroll
+    for (int r = 0; r < R; ++r) dza[r][t] = __shfl_sync(0xffffffffu, dz, r * TM + t);
 #pragma unroll
   for (int t = 0; t < TM; ++t) {
-    float dzr[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) dzr[r] = __shfl_sync(0xffffffffu, dz, r * TM + t);
-    if (t >= T) continue;   // warp-uniform
-    const MmlrecHead& hd = Hd[t];
     float ls = 0.f, ds = 0.f;
 #pragma unroll
-    for (int r = 0; r < R; ++r) { ls += __shfl_sync(0xffffffffu, l, r * TM + t); ds += dzr[r]; }
+    for (int r = 0; r < R; ++r) { ls += __shfl_sync(0xffffffffu, l, r * TM + t); ds += dza[r][t]; }
+    if (t >= T) continue;   // warp-uniform
+    const MmlrecHead& hd = Hd[t];
     if (lane == 0) { red_s[w][t][0] = ls; red_s[w][t][1] = ds; }
+    bool first = true;
+#pragma unroll
+    for (int q = 0; q < TM; ++q) if (q < t && Hd[q].h == hd.h) first = false;
 #pragma unroll
     for (int k = 0; k < KM; ++k) {
       const int h = lane + 32 * k;
       float dw = 0.f;
 #pragma unroll
-      for (int r = 0; r < R; ++r) dw = fmaf(dzr[r], hv[r][t][k], dw);
+      for (int r = 0; r < R; ++r) dw = fmaf(dza[r][t], hv[r][t][k], dw);
       red_s[w][t][2 + h] = dw;
-      if (h >= hd.H) continue;
+      if (h >= hd.H || !first) continue;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         if (row0 + r >= B) break;
-        float g = dzr[r] * wv[t][k];
+        float g = dza[r][t] * wv[t][k];
+#pragma unroll
+        for (int q = 0; q < TM; ++q) if (q > t && q < T && Hd[q].h == hd.h) g = fmaf(dza[r][q], wv[q][k], g);
         if (hd.relu_mask && !(hv[r][t][k] > 0.f)) g = 0.f;
         if (hd.d_h) hd.d_h[(int64_t)(row0 + r) * hd.ld_d_h + h] = g;
         if (hd.d_h_bf16) hd.d_h_bf16[(int64_t)(row0 + r) * hd.ld_d_h_bf16 + h] = float_to_bf16_bits(g);
@@ -585,15 +603,33 @@ heads_fast_kernel(const MmlrecHead* heads, int T, int B, const float* y, int64_t
     for (int q = 0; q < 16; ++q) v += a[q];
     const int t = i / per_t, k = i - t * per_t;
     if (k < 2) tot_s[t][k] = v;
-    else if (k - 2 < Hd[t].H) Hd[t].dw[k - 2] = v;
+    else if (k < PW) red_s[0][t][k] = v;                     // (the per-warp partials are consumed: reuse as dw[t][k])
   }
   __syncthreads();
+  // heads that share one final layer (mlp.py:28: every task reads the same logit) share its gradient: the first head of
+  // such a group writes the sum over the group, in task order
+  for (int i = tid; i < T * KM * 32; i += 256) {
+    const int t = i / (KM * 32), h = i - t * (KM * 32);
+    if (h >= Hd[t].H) continue;
+    bool first = true;
+    for (int q = 0; q < t; ++q) first = first && Hd[q].dw != Hd[t].dw;
+    if (!first) continue;
+    float v = red_s[0][t][2 + h];
+    for (int q = t + 1; q < T; ++q) if (Hd[q].dw == Hd[t].dw) v += red_s[0][q][2 + h];
+    Hd[t].dw[h] = v;
+  }
   if (tid == 0) {
     float total = 0.f;
     for (int q = 0; q < T; ++q) { loss[q] = tot_s[q][0]; total += tot_s[q][0]; }
     loss[T] = total;
     if (esmm) {
       if (Hd[0].dbias) *Hd[0].dbias = tot_s[0][1] + tot_s[1][1];
+    } else if (cum_bias) {   // bias q enters the logits of tasks q, q+1, ...
+      for (int q = 0; q < T; ++q) {
+        float v = 0.f;
+        for (int t = q; t < T; ++t) v += tot_s[t][1];
+        if (Hd[q].dbias) *Hd[q].dbias = v;
+      }
     } else {
       for (int q = 0; q < T; ++q) if (Hd[q].dbias) *Hd[q].dbias = tot_s[q][1];
     }
@@ -860,7 +896,8 @@ static int heads_launch(const MmlrecHead* heads, int32_t T, int32_t B, const flo
                         float* pred, int64_t ld_pred, float* loss, int32_t esmm, int32_t training,
                         float* scratch, int64_t scratch_floats, int32_t* counters, int grad_mode, void* stream) {
   MMLREC_CHECK_ARG(T > 0 && T < MMLREC_MAX_TASKS && B > 0, "bad sizes");
-  MMLREC_CHECK_ARG(!esmm || T == 2, "esmm needs exactly two heads");
+  MMLREC_CHECK_ARG(!(esmm & 1) || T == 2, "esmm needs exactly two heads");
+  MMLREC_CHECK_ARG((esmm & ~3) == 0 && esmm != 3, "bad head flags");
   const int n_cta = cdiv(B, kHeadRows);
   int stride_cta = 0;
   size_t smem = 0;
@@ -891,6 +928,7 @@ static int heads_launch(const MmlrecHead* heads, int32_t T, int32_t B, const flo
       MMLREC_RETURN_LAUNCH(1);
     }
   }
+  MMLREC_CHECK_ARG(!((esmm & 2) && training && y != nullptr), "cumulative biases are handled by the one-launch kernel only");
   launch_pdl(heads_kernel, dim3(n_cta), dim3(256), smem, stream, heads, T, B, y, ldy, pred, ld_pred, loss, esmm, training, scratch,
              stride_cta, counters, grad_mode);
   if (!(training && y != nullptr)) { MMLREC_RETURN_LAUNCH(1); }

@@ -296,7 +296,8 @@ struct GtTables {
   GtPair pair[GT_MAXP];                 // live (gate, expert) pairs, grouped by gate
   uint16_t pair_eo[GT_MAXP];            // expert row offset (float4) of the pair inside one sample's expert block
   uint8_t pair_g[GT_MAXP], pair_e[GT_MAXP];
-  uint8_t ucnt[MMLREC_LEVEL_MAX_EXPERTS], ug[MMLREC_LEVEL_MAX_EXPERTS][GL_MAXG];
+  uint8_t ucnt[MMLREC_LEVEL_MAX_EXPERTS], ug[MMLREC_LEVEL_MAX_EXPERTS][GL_MAXG];   // gates whose gradient reaches expert u
+  uint8_t used[MMLREC_LEVEL_MAX_EXPERTS];                                          // expert u is read by some live gate
   uint16_t ucol[MMLREC_LEVEL_MAX_EXPERTS][GL_MAXG];
   // rows to stage per sample
   const float* src[GT_MAXSRC];
@@ -364,11 +365,16 @@ __device__ __forceinline__ void gt_setup(const MmlrecGateLevel* lv, MmlrecGateLe
   }
   if (tid < E) {
     int n = 0;
+    bool used = false;
     for (int g = 0; g < G; ++g) {
       const int sl = L.slot[tid][g];
-      if (T.live[g] && sl >= 0) { T.ug[tid][n] = (uint8_t)g; T.ucol[tid][n] = (uint16_t)(T.ne_off[g] + sl); ++n; }
+      if (!T.live[g] || sl < 0) continue;
+      used = true;
+      if (backward && ((L.detach_mask[tid] >> g) & 1u)) continue;   // gate g treats this expert as a constant
+      T.ug[tid][n] = (uint8_t)g; T.ucol[tid][n] = (uint16_t)(T.ne_off[g] + sl); ++n;
     }
     T.ucnt[tid] = (uint8_t)n;
+    T.used[tid] = used ? 1 : 0;
   }
   __syncthreads();
 }
@@ -431,7 +437,7 @@ gate_level_forward_tiled_kernel(const MmlrecGateLevel* lv, int B) {
     const int v = tid;
     const float* src = nullptr; int64_t ld = 0; int off = 0, stride = 0, n4 = 0;
     if (v < E) {
-      if (T.ucnt[v]) { src = L.expert[v]; ld = L.ld_expert; off = (int)(eo_s - dyn_s) + v * H; stride = E * H; n4 = H4; }
+      if (T.used[v]) { src = L.expert[v]; ld = L.ld_expert; off = (int)(eo_s - dyn_s) + v * H; stride = E * H; n4 = H4; }
     } else {
       const int g = v - E;
       src = L.gate_in[g]; ld = L.ld_gate_in[g]; off = (int)(gin_s - dyn_s) + T.hg_off[g]; stride = total_hg; n4 = L.Hg[g] >> 2;
@@ -541,7 +547,7 @@ gate_level_backward_tiled_kernel(const MmlrecGateLevel* lv, int B, float* scratc
       if (T.live[v]) { src = L.d_mix[v]; ld = L.ld_d_mix[v]; off = (int)(dm_s - dyn_s) + v * H; stride = G * H; n4 = H4; }
     } else if (v < G + E) {
       const int u = v - G;
-      if (T.ucnt[u]) { src = L.expert[u]; ld = L.ld_expert; off = (int)(eo_s - dyn_s) + u * H; stride = E * H; n4 = H4; }
+      if (T.used[u]) { src = L.expert[u]; ld = L.ld_expert; off = (int)(eo_s - dyn_s) + u * H; stride = E * H; n4 = H4; }
     } else {
       const int g = v - G - E;
       if (T.live[g]) { src = L.gate_in[g]; ld = L.ld_gate_in[g]; off = (int)(gin_s - dyn_s) + T.hg_off[g]; stride = total_hg; n4 = L.Hg[g] >> 2; }

@@ -50,6 +50,13 @@ class ActGroup:
             at += w
         self.total = at
 
+    def span(self) -> "Act":
+        """All columns of the group as ONE activation (torch.cat of its members, cross_stitch.py:17: free here,
+        the members are adjacent columns of one buffer)."""
+        a = Act(self, 0, self.total, f"{self.name}[*]")
+        a.members = list(self.acts)
+        return a
+
     def materialize(self, b: "Builder") -> None:
         if not (self.need_f32 or self.need_bf16):  # produced but never consumed: keep one copy
             self.need_f32, self.need_bf16 = (not b.tc), b.tc
@@ -72,8 +79,23 @@ class Act:
 
     def __init__(self, group: ActGroup, col: int, width: int, name: str):
         self.group, self.col, self.width, self.name = group, col, width, name
-        self.grad_written = False
+        self._grad_written = False
         self.need_f32 = self.need_bf16 = False   # which copies THIS activation's consumers read
+        self.parent: Optional["Act"] = None      # set by sub(): this activation is a column range of `parent`
+        self.children: List["Act"] = []          # column ranges handed out by sub()
+        self.members: List["Act"] = []           # set by ActGroup.span(): this activation covers these whole ones
+
+    # "some writer has produced (part of) this gradient": a range written through its sub-ranges counts, and writing
+    # a span marks every activation it covers
+    @property
+    def grad_written(self) -> bool:
+        return self._grad_written or any(c.grad_written for c in self.children)
+
+    @grad_written.setter
+    def grad_written(self, v: bool) -> None:
+        self._grad_written = v
+        for m in self.members:
+            m.grad_written = v
 
     relu = property(lambda self: self.group.relu)
     # derivative folded into gradient writes: 0 none, 1 ReLU, 2 "2*sigmoid" (GateNN output)
@@ -82,6 +104,8 @@ class Act:
     def sub(self, col: int, width: int) -> "Act":
         """A column sub-range of this activation (e.g. one field's embedding inside dnn_input)."""
         a = Act(self.group, self.col + col, width, f"{self.name}[{col}:{col + width}]")
+        a.parent = self
+        self.children.append(a)
         return a
     # fp32 view
     ld = property(lambda self: self.group.buf.stride(0))
@@ -112,17 +136,24 @@ class Act:
         self.need_bf16 |= bf16
         self.group.need_f32 |= f32
         self.group.need_bf16 |= bf16
+        if self.parent is not None:
+            self.parent.want(f32, bf16)
+        for m in self.members:
+            m.want(f32, bf16)
         return self
 
 
 class LinearSpec:
     """One nn.Linear (+ optional BatchNorm1d) as the program sees it."""
 
-    def __init__(self, x: Act, linear: nn.Module, bn: Optional[nn.Module] = None):
+    def __init__(self, x: Act, linear: nn.Module, bn: Optional[nn.Module] = None, transposed: bool = False):
         self.x, self.linear, self.bn = x, linear, bn
         self.W: nn.Parameter = linear.weight
         self.b: Optional[nn.Parameter] = getattr(linear, "bias", None)
-        self.N, self.K = self.W.shape
+        # transposed: the parameter is stored [K, N] and applied as x @ W (cross_stitch.py:18) instead of x @ W^T
+        self.transposed = transposed
+        self.N, self.K = (self.W.shape[1], self.W.shape[0]) if transposed else self.W.shape
+        assert not (transposed and (self.b is not None or bn is not None)), "transposed weights: plain x @ W only"
 
 
 class Builder:
@@ -244,7 +275,9 @@ class Builder:
         return g.acts
 
     def note_params(self, params: Sequence[Optional[nn.Parameter]]) -> None:
-        self.param_order.extend(p for p in params if isinstance(p, nn.Parameter))
+        for p in params:   # a parameter shared by several consumers (MLP's one final layer) is laid out once
+            if isinstance(p, nn.Parameter) and not any(p is q for q in self.param_order):
+                self.param_order.append(p)
 
     def note_buffers(self, bufs: Sequence[Optional[torch.Tensor]]) -> None:
         self.buffer_order.extend(t for t in bufs if t is not None)
@@ -454,6 +487,8 @@ class _Group:
         self.K = members[0].K
         self.N = sum(m.N for m in members)
         self.W, self.b = members[0].W, members[0].b
+        self.transposed = members[0].transposed
+        assert not self.transposed or len(members) == 1
 
 
 def _tile_prefix_f32(problems: Sequence[L.GemmF32]) -> Tuple[List[int], int]:
@@ -506,7 +541,8 @@ class LinearStage(Stage):
                 self.groups.append(_Group(list(cur), [self.outs[specs.index(m)] for m in cur]))
 
         for s in specs:
-            ok = bool(cur) and s.x.same_as(cur[-1].x) and s.K == cur[-1].K and st.contiguous_after(cur[-1].W, s.W) \
+            ok = bool(cur) and not s.transposed and not cur[-1].transposed \
+                and s.x.same_as(cur[-1].x) and s.K == cur[-1].K and st.contiguous_after(cur[-1].W, s.W) \
                 and ((s.b is None) == (cur[-1].b is None)) and (s.b is None or st.contiguous_after(cur[-1].b, s.b))
             if ok and self.use_bn:
                 p, q = cur[-1].bn, s.bn
@@ -527,7 +563,7 @@ class LinearStage(Stage):
             for g in self.groups:
                 p = L.GemmF32()
                 p.A, p.a_rs, p.a_cs = g.x.ptr, g.x.ld, 1
-                p.B, p.b_rs, p.b_cs = g.W.data_ptr(), g.W._mm_ld, 1
+                p.B, p.b_rs, p.b_cs = (g.W.data_ptr(), 1, g.W._mm_ld) if g.transposed else (g.W.data_ptr(), g.W._mm_ld, 1)
                 p.C, p.ldc = tgt.buf.data_ptr() + 4 * g.y_col, tgt.buf.stride(0)
                 p.bias = g.b.data_ptr() if g.b is not None else None
                 p.M, p.N, p.K, p.act = b.B, g.N, g.K, act_code
@@ -556,7 +592,10 @@ class LinearStage(Stage):
                 for (f32, bf16), off, n in runs:
                     d = L.GemmTcDesc()
                     d.A, d.lda, d.a_mn_major = g.x.ptr16, g.x.ld16, 0
-                    d.B, d.ldb, d.b_mn_major = st.bf16_ptr(g.W) + 2 * off * g.W._mm_ld, g.W._mm_ld, 0
+                    if g.transposed:   # the array is [K, N]: read MN-major
+                        d.B, d.ldb, d.b_mn_major = st.bf16_ptr(g.W), g.W._mm_ld, 1
+                    else:
+                        d.B, d.ldb, d.b_mn_major = st.bf16_ptr(g.W) + 2 * off * g.W._mm_ld, g.W._mm_ld, 0
                     d.M, d.N, d.K = b.B, n, g.K
                     col = g.y_col + off
                     if f32:
@@ -635,8 +674,9 @@ class LinearStage(Stage):
             if not any(o.grad_written for o in g.outs):
                 continue  # nothing flows into this group: its parameters keep a zero gradient
             for o in g.outs:
-                if not o.grad_written:
-                    o.grad_tensor().zero_()  # stays zero: the buffer is never written afterwards
+                for part in ([o] if not o.children else o.children):
+                    if not part.grad_written:
+                        part.grad_tensor().zero_()  # stays zero: the buffer is never written afterwards
             self.live_groups.append(g)
             x = g.x
             want_dx = x.group.need_grad
@@ -647,16 +687,21 @@ class LinearStage(Stage):
             if not b.tc:
                 dz_ptr, dz_ld = dzg.gbuf.data_ptr() + 4 * g.y_col, dzg.gbuf.stride(0)
                 p = L.GemmF32()   # wgrad: dW[n,k] = sum_b dZ[b,n] X[b,k]; rowsum_a = bias gradient
-                p.A, p.a_rs, p.a_cs = dz_ptr, 1, dz_ld
-                p.B, p.b_rs, p.b_cs = x.ptr, 1, x.ld
+                if g.transposed:  # the parameter is [K, N]: dW[k,n] = sum_b X[b,k] dZ[b,n]
+                    p.A, p.a_rs, p.a_cs = x.ptr, 1, x.ld
+                    p.B, p.b_rs, p.b_cs = dz_ptr, 1, dz_ld
+                    p.M, p.N, p.K = g.K, g.N, b.B
+                else:
+                    p.A, p.a_rs, p.a_cs = dz_ptr, 1, dz_ld
+                    p.B, p.b_rs, p.b_cs = x.ptr, 1, x.ld
+                    p.rowsum_a = st.grad_ptr(g.b) if g.b is not None else None
+                    p.M, p.N, p.K = g.N, g.K, b.B
                 p.C, p.ldc = st.grad_ptr(g.W), g.W._mm_ld
-                p.rowsum_a = st.grad_ptr(g.b) if g.b is not None else None
-                p.M, p.N, p.K = g.N, g.K, b.B
                 waves[0].append(p)
                 if want_dx:
                     q = L.GemmF32()   # dgrad: dX[b,k] = sum_n dZ[b,n] W[n,k], masked by the producer's ReLU
                     q.A, q.a_rs, q.a_cs = dz_ptr, dz_ld, 1
-                    q.B, q.b_rs, q.b_cs = g.W.data_ptr(), 1, g.W._mm_ld
+                    q.B, q.b_rs, q.b_cs = (g.W.data_ptr(), g.W._mm_ld, 1) if g.transposed else (g.W.data_ptr(), 1, g.W._mm_ld)
                     q.C, q.ldc = x.gptr, x.gld
                     q.M, q.N, q.K = b.B, g.K, g.N
                     assert x.dkind in (0, 1), "a GEMM cannot back-propagate into a sigmoid output directly"
@@ -671,16 +716,21 @@ class LinearStage(Stage):
                 for k in range(S):
                     rows = b.B // S
                     d = L.GemmTcDesc()
-                    d.A, d.lda, d.a_mn_major = dz16 + 2 * k * rows * dz_ld, dz_ld, 1
-                    d.B, d.ldb, d.b_mn_major = x.ptr16 + 2 * k * rows * x.ld16, x.ld16, 1
-                    d.M, d.N, d.K = g.N, g.K, rows
+                    if g.transposed:   # dW[k,n] for a [K, N] parameter: the operands swap roles
+                        d.A, d.lda, d.a_mn_major = x.ptr16 + 2 * k * rows * x.ld16, x.ld16, 1
+                        d.B, d.ldb, d.b_mn_major = dz16 + 2 * k * rows * dz_ld, dz_ld, 1
+                        d.M, d.N, d.K = g.K, g.N, rows
+                    else:
+                        d.A, d.lda, d.a_mn_major = dz16 + 2 * k * rows * dz_ld, dz_ld, 1
+                        d.B, d.ldb, d.b_mn_major = x.ptr16 + 2 * k * rows * x.ld16, x.ld16, 1
+                        d.M, d.N, d.K = g.N, g.K, rows
+                        d.colsum = (st.grad_ptr(g.b) + 4 * k * st.slice_stride) if g.b is not None else None
                     d.C_f32, d.ldc_f32 = st.grad_ptr(g.W) + 4 * k * st.slice_stride, g.W._mm_ld
-                    d.colsum = (st.grad_ptr(g.b) + 4 * k * st.slice_stride) if g.b is not None else None
                     waves[0].append(d)
                 if want_dx:
                     e = L.GemmTcDesc()   # dgrad: A = dZ (K-major), B = W read MN-major
                     e.A, e.lda, e.a_mn_major = dz16, dz_ld, 0
-                    e.B, e.ldb, e.b_mn_major = st.bf16_ptr(g.W), g.W._mm_ld, 1
+                    e.B, e.ldb, e.b_mn_major = st.bf16_ptr(g.W), g.W._mm_ld, 0 if g.transposed else 1
                     e.M, e.N, e.K = b.B, g.K, g.N
                     if x.grad_is_f32:
                         e.C_f32, e.ldc_f32 = x.gptr, x.gld
@@ -693,7 +743,7 @@ class LinearStage(Stage):
                         xg = x.group
                         if xg.bits is not None and xg.bits_written and x.col % 32 == 0:
                             e.mask_bits, e.mask_bits_chunks, e.mask_bits_chunk0 = xg.bits.data_ptr(), xg.bits_chunks, x.col // 32
-                    if (b.tc_kernel == 2 and g.N >= 2048 and x.grad_is_f32 and not accumulate
+                    if (b.tc_kernel == 2 and g.N >= 2048 and x.grad_is_f32 and not accumulate and not g.transposed
                             and x.width == x.group.total):
                         # a very long contraction (K = the merged layer width) on a few tiles: two K halves as two
                         # problems that ADD into the zeroed gradient buffer (0 + a + b is order-independent: deterministic)
@@ -919,8 +969,12 @@ class _DryTensor:
 # gate head + softmax + mixture
 # ----------------------------------------------------------------------------------------------
 class GateSpec:
-    def __init__(self, gate_in: Act, head: nn.Module, experts: List[Act]):
+    """``detach[e]``: the gate mixes expert e as a constant (``x.detach()``, hmoe.py:130): value used, no gradient into it."""
+
+    def __init__(self, gate_in: Act, head: nn.Module, experts: List[Act], detach: Optional[List[bool]] = None):
         self.gate_in, self.head, self.experts = gate_in, head, experts
+        self.detach = list(detach) if detach is not None else [False] * len(experts)
+        assert len(self.detach) == len(experts)
 
 
 class GateMixStage(Stage):
@@ -934,6 +988,7 @@ class GateMixStage(Stage):
         H = gates[0].experts[0].width
         assert all(e.width == H for g in gates for e in g.experts)
         self.H = H
+        self.any_detach = any(any(g.detach) for g in gates)
         self.outs = b.new_group([H] * len(gates), relu=False, name=f"{label}.mix", grad_dtype="f32")
         self.outs[0].want(f32=True)
         for g in gates:
@@ -994,6 +1049,8 @@ class GateMixStage(Stage):
             for e, a in enumerate(g.experts):
                 u = next(k for k, x in enumerate(self.uniq) if x.same_as(a))
                 r.slot[u][i] = e
+                if g.detach[e]:
+                    r.detach_mask[u] |= 1 << i
             if live[i]:
                 r.d_mix[i], r.ld_d_mix[i] = o.gptr, o.gld
                 if gi.group.need_grad:
@@ -1008,8 +1065,9 @@ class GateMixStage(Stage):
                 r.dWg[i] = st.grad_ptr(g.head.weight)
         if backward:
             for u, a in enumerate(self.uniq):
-                if not any(live[i] and any(a.same_as(x) for x in g.experts) for i, g in enumerate(self.gates)):
-                    continue
+                if not any(live[i] and any(a.same_as(x) and not g.detach[e] for e, x in enumerate(g.experts))
+                           for i, g in enumerate(self.gates)):
+                    continue   # no live gate sends a gradient into this expert
                 assert not a.grad_written, "an expert output consumed elsewhere must be accumulated"
                 if a.grad_is_f32:
                     r.d_expert[u], r.ld_d_expert = a.gptr, a.gld
@@ -1081,6 +1139,8 @@ class GateMixStage(Stage):
                               for i in range(G))
                           and b.lib.mmlrec_gate_level_backward_tiled_smem(G, E, self.H, self.total_wg, self.total_ne,
                                                                           self.total_hg) <= 110 * 1024)
+            if self.any_detach and not self.tiled:
+                raise NotImplementedError("detached experts (HMoE task weights) need the tiled gate backward")
             if self.tiled:
                 n = b.lib.mmlrec_gate_level_backward_tiled_scratch(self.total_wg, b.B)
             else:
@@ -1088,6 +1148,8 @@ class GateMixStage(Stage):
             self.scratch = b.zeros(int(n))
             self.counters = b.zeros(1, dtype=torch.int32)
             return
+        if self.any_detach:
+            raise NotImplementedError("detached experts (HMoE task weights) need the level-fused gate kernels")
         # gates that share an input (no gate DNN: every head reads the level input) must not race on
         # d(gate_in): the kernel then walks the gates in order inside each CTA
         seen, self.serialize = [], 0
@@ -1166,14 +1228,21 @@ class HeadStage(Stage):
     (model/mmoe.py:97-100, model/utils.py:242-248, model/basemodel.py:294-296)."""
     name = "heads"
 
-    def __init__(self, b: Builder, heads: List[HeadSpec], esmm: bool = False):
+    def __init__(self, b: Builder, heads: List[HeadSpec], esmm: bool = False, cumulative_bias: bool = False):
+        # cumulative_bias: task t's logit carries the biases of tasks 0..t (mlp.py:47 hands ONE logit tensor to every
+        # PredictionLayer, whose ``output += self.bias`` works in place, model/utils.py:243-245)
         self.b, self.heads, self.esmm = b, heads, esmm
+        self.flags = (1 if esmm else 0) | (2 if cumulative_bias else 0)
         b.note_params([h.final.weight for h in heads])
         b.note_params([h.bias for h in heads])
         b.note_params([h.bias2 for h in heads])
         self.T = len(heads)
         for h in heads:
             h.h.want(f32=True)
+        # heads sharing one final layer (MLP): only the one-launch head kernel sums their weight gradients
+        shared = len({id(h.final.weight) for h in heads}) < len(heads)
+        if shared and not (self.T <= 8 and max(h.h.width for h in heads) <= 128):
+            raise NotImplementedError("a final layer shared by several heads needs T <= 8 tasks of width <= 128")
 
     def finalize(self):
         b, st = self.b, self.b.store
@@ -1189,7 +1258,10 @@ class HeadStage(Stage):
             r.w = h.final.weight.data_ptr()
             r.bias = h.bias.data_ptr() if h.bias is not None else None
             if h.h.group.need_grad:
-                assert not h.h.grad_written
+                # an activation read by several heads of this stage: the head kernel sums their contributions
+                again = any(o.h.same_as(h.h) for o in self.heads[:self.heads.index(h)])
+                assert again or not h.h.grad_written
+                assert not again or (self.T <= 8 and h.h.width <= 128), "heads sharing an input need the one-launch kernel"
                 if h.h.grad_is_f32:
                     r.d_h, r.ld_d_h = h.h.gptr, h.h.gld
                 else:
@@ -1210,7 +1282,7 @@ class HeadStage(Stage):
         b = self.b
         L.check(b.lib.mmlrec_heads_forward_backward(
             self.table.data_ptr(), self.T, b.B, self.y.data_ptr() if training else None, self.T, self.pred.data_ptr(),
-            self.T, self.loss.data_ptr(), 1 if self.esmm else 0, 1 if training else 0, self.scratch.data_ptr(),
+            self.T, self.loss.data_ptr(), self.flags, 1 if training else 0, self.scratch.data_ptr(),
             self.scratch.numel(), self.counter.data_ptr(), stream), "heads")
 
     def backward_external(self, stream, d_pred: torch.Tensor):
@@ -1219,7 +1291,7 @@ class HeadStage(Stage):
         self.d_pred.copy_(d_pred)
         L.check(b.lib.mmlrec_heads_backward_external(
             self.table.data_ptr(), self.T, b.B, self.d_pred.data_ptr(), self.T, self.pred.data_ptr(), self.T,
-            self.loss.data_ptr(), 1 if self.esmm else 0, self.scratch.data_ptr(), self.scratch.numel(),
+            self.loss.data_ptr(), self.flags, self.scratch.data_ptr(), self.scratch.numel(),
             self.counter.data_ptr(), stream), "heads (external gradient)")
 
 

@@ -91,7 +91,7 @@ class GateLevel(C.Structure):
                 ("mix_bf16", vp * _G), ("ld_mix_bf16", i64 * _G), ("d_mix", vp * _G), ("ld_d_mix", i64 * _G),
                 ("d_gate_in", vp * _G), ("ld_d_gate_in", i64 * _G), ("d_gate_in_bf16", vp * _G),
                 ("ld_d_gate_in_bf16", i64 * _G), ("relu_mask_gate_in", i32 * _G), ("accumulate_d_gate_in", i32 * _G),
-                ("dWg", vp * _G)]
+                ("dWg", vp * _G), ("detach_mask", C.c_uint32 * _E)]
 
 
 class Head(C.Structure):

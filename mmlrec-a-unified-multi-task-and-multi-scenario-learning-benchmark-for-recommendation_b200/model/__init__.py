@@ -1,21 +1,17 @@
 """Model zoo on the fused step program.  ``get_model`` mirrors ``main.py:37-68`` of the reference
-(case-insensitive names); families not yet ported raise ``NotImplementedError`` by name."""
+(case-insensitive names); the families outside the fused step (snr_trans, mssm, pcg, apg, aitm, escm) raise ``NotImplementedError`` by name."""
+from .cross_stitch import CrossStitch
 from .esmm import ESMM
+from .hmoe import HMOE
+from .mlp import MLP
 from .mmoe import MMOE
+from .pepnet import PepNet
 from .ple import PLE
 from .sharedbottom import SharedBottom
+from .star import STAR
 
-_REGISTRY = {"mmoe": MMOE, "ple": PLE, "sharedbottom": SharedBottom, "esmm": ESMM}
-try:  # families added after the first milestone
-    from .star import STAR
-    _REGISTRY["star"] = STAR
-except ImportError:
-    pass
-try:
-    from .pepnet import PepNet
-    _REGISTRY["pepnet"] = PepNet
-except ImportError:
-    pass
+_REGISTRY = {"mmoe": MMOE, "ple": PLE, "sharedbottom": SharedBottom, "esmm": ESMM, "star": STAR, "pepnet": PepNet,
+             "mlp": MLP, "cross_stitch": CrossStitch, "hmoe": HMOE}
 
 REFERENCE_NAMES = ("mmoe", "esmm", "sharedbottom", "ple", "snr_trans", "mssm", "star", "pcg", "apg", "mlp",
                    "cross_stitch", "aitm", "escm", "hmoe", "pepnet")

@@ -579,6 +579,58 @@ class BaseModel(nn.Module):
         clone.train(self.training)
         return clone
 
+    _CKPT_BUFFERS = ("dense", "emb", "stats", "counts", "dense_s1", "dense_s2", "emb_s1", "emb_s2", "row_touch")
+
+    def save_checkpoint(self, path: str) -> str:
+        """Everything a resumed run needs to continue bit for bit: the flat parameter / BatchNorm buffers, the optimizer
+        state of the dense parameters and of the tables (incl. the lazy dense-Adam row stamps and history ring) and the
+        device-side optimizer clock.  The reference keeps no checkpoint of its own (``deepcopy`` of the best
+        epoch only); the tensors are stored under their flat-store names, ``state_dict()`` rides along for interchange
+        with a reference model.  Row-sharded tables: every rank calls this and writes ITS shard to ``<path>.rank<r>``."""
+        self._require_cuda()
+        if self.hyper_dev is None:
+            raise RuntimeError("call compile() before save_checkpoint()")
+        torch.cuda.synchronize(self.device_obj)
+        st = self.store
+        blob = {"format": 1, "model": type(self).__name__, "optimizer": self.optimizer_name,
+                "precision": self.precision, "hyper": self.hyper_dev.cpu(),
+                "steps_since_flush": self._steps_since_flush,
+                "adam_hist": None if self.adam_hist is None else self.adam_hist.cpu(),
+                "store": {k: getattr(st, k).cpu() for k in self._CKPT_BUFFERS if getattr(st, k, None) is not None},
+                "shard": None if self.shard is None else (self.shard.rank, self.shard.world),
+                "state_dict": {k: v.cpu() for k, v in super().state_dict().items()}}
+        if self.shard is not None:
+            path = f"{path}.rank{self.shard.rank}"
+        torch.save(blob, path)
+        return path
+
+    def load_checkpoint(self, path: str) -> None:
+        """Restore ``save_checkpoint``'s state into a model built with the same columns / config and compiled with the
+        same optimizer; training then continues exactly where the saved run stopped."""
+        self._require_cuda()
+        if self.shard is not None:
+            path = f"{path}.rank{self.shard.rank}"
+        blob = torch.load(path, map_location="cpu", weights_only=False)
+        if blob.get("format") != 1 or blob["model"] != type(self).__name__:
+            raise ValueError(f"{path}: not a checkpoint of a {type(self).__name__}")
+        if self.hyper_dev is None or blob["optimizer"] != self.optimizer_name:
+            raise RuntimeError(f"compile() the model with optimizer {blob['optimizer']!r} before load_checkpoint()")
+        shard = None if self.shard is None else (self.shard.rank, self.shard.world)
+        if blob["shard"] != shard:
+            raise ValueError(f"{path}: saved with table shard {blob['shard']}, this model has {shard}")
+        st = self.store
+        for k, v in blob["store"].items():
+            dst = getattr(st, k, None)
+            if dst is None or dst.shape != v.shape:
+                raise ValueError(f"{path}: buffer {k!r} does not match this model")
+            dst.copy_(v)
+        self.hyper_dev.copy_(blob["hyper"])
+        if self.adam_hist is not None and blob["adam_hist"] is not None:
+            self.adam_hist.copy_(blob["adam_hist"])
+        self._steps_since_flush = int(blob["steps_since_flush"])
+        st.refresh_bf16()
+        torch.cuda.synchronize(self.device_obj)
+
     def load_state_dict(self, state_dict, strict=True, assign=False):
         out = super().load_state_dict(state_dict, strict=strict, assign=False)
         if self.store is not None:

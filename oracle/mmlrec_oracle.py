@@ -6,7 +6,7 @@ library is missing instead of falling back to anything here).
 
 What it is: a *functional* restatement, in plain fp32 PyTorch on the CPU, of the reference's
 step body (``/root/reference/model/basemodel.py:262-313``): multi-field gather + concat, the
-expert / gate / tower networks of six model families, sigmoid + BCE(sum), backward and the
+expert / gate / tower networks of nine model families, sigmoid + BCE(sum), backward and the
 ``torch.optim`` step.  All arithmetic of the reference lives in the third-party module ``torch``
 (reference prose pins "PyTorch 1.11.0", ``README.md:52``; no lock file; operative version in
 this image: torch 2.11.0+cu128), so the restatement calls the same ATen ops in the same order.
@@ -183,6 +183,7 @@ class Spec:
         self.tower_units = mc.get("tower_dnn_hidden_units", [64])
         self.dnn_units = mc.get("dnn_hidden_units", [256, 128])
         self.use_shared = mc.get("use_shared", True)
+        self.task_weight_units = mc.get("task_weight_hidden_units", [64])
         self.scene_feature = dc.get("scene_feature", "")
         self.user_sf = dc.get("user_sf", "")
         self.item_sf = dc.get("item_sf", "")
@@ -318,9 +319,66 @@ def forward_pepnet(p: Params, b: Params, s: Spec, X: Tensor, training: bool) -> 
     return torch.cat(outs, -1)
 
 
+def forward_mlp(p: Params, b: Params, s: Spec, X: Tensor, training: bool) -> Tensor:
+    """model/mlp.py:36-52: a stack of single-layer DNN blocks (no BatchNorm: the blocks are built with the DNN
+    defaults), ONE bias-free final layer; every task's PredictionLayer is applied to the same logit."""
+    h = gather_concat(X, p, s.columns)
+    for i in range(len(s.dnn_units)):
+        h = mlp(p, b, f"mlp_layers.{i}", h, False, training, "relu")
+    z = F.linear(h, p["final_layer.weight"])
+    outs = []
+    for t in range(s.num_tasks):  # PredictionLayer.forward does ``output += self.bias`` IN PLACE (utils.py:243-245) on the
+        z = z + p[f"out.{t}.bias"]   # one logit tensor all tasks share: task t sees biases 0..t
+        outs.append(torch.sigmoid(z) if s.task_types[t] == "binary" else z)
+    return torch.cat(outs, -1)
+
+
+def forward_cross_stitch(p: Params, b: Params, s: Spec, X: Tensor, training: bool) -> Tensor:
+    """model/cross_stitch.py:82-112: shared layer, then per level the T task layers and the cross-stitch unit
+    ``cat(outputs) @ W`` (:17-18; W is used as stored, [in, out]), split back per task."""
+    x = gather_concat(X, p, s.columns)
+    shared = mlp(p, b, "shared_layer", x, s.use_bn, training, s.act)
+    cur = [shared] * s.num_tasks
+    for i in range(len(s.dnn_units)):
+        cur = [mlp(p, b, f"cross_stitch.task_layer_{i}.{t}", cur[t], s.use_bn, training, s.act)
+               for t in range(s.num_tasks)]
+        stitched = torch.matmul(torch.cat(cur, -1), p[f"cross_stitch.gate_{i}.cross_stitch_weight"])
+        d = s.dnn_units[i]
+        cur = [stitched[:, t * d:(t + 1) * d] for t in range(s.num_tasks)]
+    return _towers(p, b, s, cur, training)
+
+
+def forward_hmoe(p: Params, b: Params, s: Spec, X: Tensor, training: bool) -> Tensor:
+    """model/hmoe.py:82-139: MMoE up to the towers; task i's head reads sum_j softmax(task_weight_i)[j] * tower_j
+    with tower_j detached for j != i (:126-131)."""
+    x = gather_concat(X, p, s.columns)
+    T = s.num_tasks
+    experts = [mlp(p, b, f"expert_dnn.{e}", x, s.use_bn, training, s.act) for e in range(s.num_experts)]
+    mixed, weights, towers = [], [], []
+    for t in range(T):
+        g = mlp(p, b, f"gate_dnn.{t}", x, s.use_bn, training, s.act) if len(s.gate_units) > 0 else x
+        mixed.append(_gate_mix(F.linear(g, p[f"gate_dnn_final_layer.{t}.weight"]), experts))
+    for t in range(T):
+        w = mlp(p, b, f"task_weight.{t}", x, s.use_bn, training, s.act) if len(s.task_weight_units) > 0 else x
+        weights.append(F.linear(w, p[f"task_weight_final_layer.{t}.weight"]).softmax(1))
+    for t in range(T):
+        towers.append(mlp(p, b, f"tower_dnn.{t}", mixed[t], s.use_bn, training, s.act) if len(s.tower_units) > 0
+                      else mixed[t])
+    outs = []
+    for i in range(T):
+        h = weights[i][:, i].view(-1, 1) * towers[i]
+        for j in range(T):
+            if j != i:
+                h = h + weights[i][:, j].view(-1, 1) * towers[j].detach()
+        logit = F.linear(h, p[f"tower_dnn_final_layer.{i}.weight"])
+        outs.append(predict_head(logit, p[f"out.{i}.bias"], s.task_types[i]))
+    return torch.cat(outs, -1)
+
+
 FORWARDS = {
     "mmoe": forward_mmoe, "pcg": forward_mmoe, "ple": forward_ple, "sharedbottom": forward_sharedbottom,
-    "esmm": forward_esmm, "star": forward_star, "pepnet": forward_pepnet,
+    "esmm": forward_esmm, "star": forward_star, "pepnet": forward_pepnet, "mlp": forward_mlp,
+    "cross_stitch": forward_cross_stitch, "hmoe": forward_hmoe,
 }
 
 

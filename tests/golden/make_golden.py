@@ -68,7 +68,16 @@ CASES = {
     # negative sample (log clamp at -100) and a ZERO gradient, unlike bce_with_logits
     "sharedbottom_kuairec_saturated_sgd": ("kuairec_sharedbottom", dict(max_vocab=200), SMALL,
                                            dict(optimizer="sgd", lr=1e-2)),
+    # model zoo on the same stages: one shared final layer (MLP), identity-initialised cross-stitch
+    # units applied as x @ W (CrossStitch), detached cross-task tower mixing (HMoE)
+    "mlp_kuairec_adam": ("kuairec_sharedbottom", dict(max_vocab=200), dict(SMALL, model_name="mlp"), {}),
+    "cross_stitch_kuairec_adam": ("kuairec_sharedbottom", dict(max_vocab=200),
+                                  dict(SMALL, model_name="cross_stitch", shared_hidden_unit=16), {}),
+    "hmoe_kuairec_adam": ("kuairec_sharedbottom", dict(max_vocab=200),
+                          dict(SMALL, model_name="hmoe", task_weight_hidden_units=[8]), {}),
 }
+# cases whose identity / 1e-4 initial state would leave parts of the model untested: perturbed after construction
+INIT_STD.update({"cross_stitch_kuairec_adam": 0.05, "hmoe_kuairec_adam": 0.05, "mlp_kuairec_adam": 0.05})
 
 
 def post_build(case, model):
@@ -77,6 +86,14 @@ def post_build(case, model):
         with torch.no_grad():
             model.out[0].bias.fill_(30.0)
         return ["out.0.bias"]
+    if case == "cross_stitch_kuairec_adam":   # identity units exercise no off-diagonal weight: add seeded noise
+        touched = []
+        with torch.no_grad():
+            for name, prm in model.named_parameters():
+                if name.endswith("cross_stitch_weight"):
+                    prm.add_(0.1 * torch.randn(prm.shape, generator=torch.Generator().manual_seed(7)))
+                    touched.append(name)
+        return touched
     return []
 
 
@@ -95,11 +112,14 @@ def build_reference(cfg, fields, init_std=0.0001):
     from model.esmm import ESMM
     from model.star import STAR
     from model.pepnet import PepNet
+    from model.mlp import MLP
+    from model.cross_stitch import CrossStitch
+    from model.hmoe import HMOE
     emb = cfg["model_config"]["emb"]
     cols = [SparseFeat(n, vocabulary_size=v, embedding_dim=emb) if k == "sparse" else DenseFeat(n, 1)
             for n, k, v in fields]
     cls = {"mmoe": MMOE, "ple": PLE, "sharedbottom": SharedBottom, "esmm": ESMM, "star": STAR,
-           "pepnet": PepNet}[cfg["model_config"]["model_name"].lower()]
+           "pepnet": PepNet, "mlp": MLP, "cross_stitch": CrossStitch, "hmoe": HMOE}[cfg["model_config"]["model_name"].lower()]
     with contextlib.redirect_stdout(io.StringIO()):
         model = cls(cols, init_std=init_std, device="cpu", config=cfg)
         model.compile(optimizer=cfg["optim_config"]["optimizer"], loss=cfg["optim_config"]["loss"],
