@@ -565,7 +565,11 @@ def run_ours(args, rank, world):
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
-        dist.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        # no teardown: destroying the process group while captured graphs still hold its collectives on two streams can
+        # block at interpreter exit; every rank has passed the barrier, the measurement is printed -> leave
+        os._exit(0)
 
 
 def main():

@@ -59,6 +59,14 @@ int mmlrec_hyper_advance(MmlrecHyper* hyper, void* stream);
 /* same, and records {step_size, bc2_sqrt} of the new step t in hist[(t mod cap)] (float pairs, cap a power of two):
  * the history the lazy dense-Adam catch-up replays */
 int mmlrec_hyper_advance_hist(MmlrecHyper* hyper, float* hist, int32_t cap, void* stream);
+/* The same catch-up on the owner of ROW-SHARDED tables: the rows are named by the request keys of the forward exchange
+ * (rq_keys[2][F_s][B_all], key = local_row << 32 | pos, ~0 = not this owner's; parity = (step + step_offset) & 1); runs
+ * between the ids barrier and mmlrec_emb_serve_rows.  No reference counterpart (torch.optim.Adam is dense,
+ * model/basemodel.py:569-584); see mmlrec_emb_adam_catch_up. */
+int mmlrec_emb_adam_catch_up_keys(const uint64_t* rq_keys, int32_t B_all, const int64_t* field_meta, int32_t F_s,
+                                  int32_t D, float* emb, float* exp_avg, float* exp_avg_sq, int32_t* row_touch,
+                                  const MmlrecHyper* hyper, int32_t step_offset, const float* hist, int32_t cap,
+                                  void* stream);
 /* Exact LAZY dense Adam on the embedding tables (the reference's nn.Embedding(sparse=False) + torch.optim.Adam moves
  * EVERY row every step, model/utils.py:475-479; a row the batch does not touch still takes a zero-gradient
  * step).  Instead of sweeping the whole table every step, a row remembers the step it is current for (row_touch) and

@@ -81,6 +81,31 @@ __global__ void emb_adam_catch_up_kernel(const float* __restrict__ X, int64_t ld
   }
 }
 
+// The same catch-up on the OWNER of row-sharded tables (csrc/peer.cu): the rows to bring up to date are named by the
+// request keys the forward exchange delivered -- key = local_row << 32 | pos in rq_keys[parity][F_s][B_all], ~0 where
+// the slot belongs to another owner -- and the kernel runs between the ids barrier and emb_serve_rows.
+__global__ void emb_adam_catch_up_keys_kernel(const uint64_t* __restrict__ rq_keys, int B_all,
+                                              const int64_t* __restrict__ field_meta, int F_s, int D, float* emb, float* m,
+                                              float* v, int32_t* row_touch, const MmlrecHyper* hyper, int step_offset,
+                                              const float2* hist, int cap) {
+  pdl_prologue();
+  const MmlrecHyper hp = *hyper;
+  const int target = hp.step - 1;
+  const int64_t n = (int64_t)F_s * B_all;
+  const uint64_t* keys = rq_keys + (int64_t)((hp.step + step_offset) & 1) * n;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const uint64_t key = keys[i];
+    if (key == ~0ull) continue;
+    const int f = (int)(i / B_all);
+    const int64_t off = field_meta[f * 4 + 0] + (int64_t)(key >> 32) * D;
+    const int64_t row = off / D;
+    const int last = row_touch[row];
+    if (last < 0 || last >= target) continue;
+    if (atomicCAS(row_touch + row, last, target) != last) continue;
+    adam_replay_row(emb, m, v, off, D, last, target, hist, cap, hp);
+  }
+}
+
 // part 2 (before anything reads the tables outside a training step -- predict, state_dict, a checkpoint -- and before
 // the history ring wraps): every row is brought up to the current step.
 __global__ void emb_adam_flush_kernel(float* emb, float* m, float* v, int32_t* row_touch, int64_t total_rows, int D,
@@ -464,6 +489,21 @@ extern "C" int mmlrec_emb_adam_catch_up(const float* X, int64_t ldx, int32_t B, 
   if (grid > 8 * emb_sm_count()) grid = 8 * emb_sm_count();
   launch_pdl(emb_adam_catch_up_kernel, dim3(grid), dim3(256), 0, stream, X, ldx, B, field_meta, F_s, D, emb, exp_avg, exp_avg_sq,
              row_touch, hyper, reinterpret_cast<const float2*>(hist), cap);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_emb_adam_catch_up_keys(const uint64_t* rq_keys, int32_t B_all, const int64_t* field_meta, int32_t F_s,
+                                             int32_t D, float* emb, float* exp_avg, float* exp_avg_sq, int32_t* row_touch,
+                                             const MmlrecHyper* hyper, int32_t step_offset, const float* hist, int32_t cap,
+                                             void* stream) {
+  using namespace mmlrec;
+  MMLREC_CHECK_ARG(rq_keys && field_meta && emb && exp_avg && exp_avg_sq && row_touch && hyper && hist, "null argument");
+  MMLREC_CHECK_ARG(B_all > 0 && F_s > 0 && D > 0 && (D & 3) == 0 && cap > 1 && (cap & (cap - 1)) == 0, "bad sizes");
+  const int64_t n = (int64_t)B_all * F_s;
+  int grid = (int)((n + 255) / 256);
+  if (grid > 8 * emb_sm_count()) grid = 8 * emb_sm_count();
+  launch_pdl(emb_adam_catch_up_keys_kernel, dim3(grid), dim3(256), 0, stream, rq_keys, B_all, field_meta, F_s, D, emb, exp_avg,
+             exp_avg_sq, row_touch, hyper, step_offset, reinterpret_cast<const float2*>(hist), cap);
   MMLREC_RETURN_LAUNCH(1);
 }
 

@@ -804,7 +804,14 @@ __global__ void star_fold_kernel(const float* d_w_eff, int64_t ld_w, const float
 
 static inline int grid_for(int64_t n) {
   int64_t g = (n + 255) / 256;
-  return (int)(g < 148 * 8 ? (g < 1 ? 1 : g) : 148 * 8);
+  static int cap = 0;   // 8 resident CTAs of 256 threads per SM
+  if (!cap) {
+    int dev = 0, n_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+    cap = 8 * (n_sm > 0 ? n_sm : 1);
+  }
+  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
 }  // namespace mmlrec

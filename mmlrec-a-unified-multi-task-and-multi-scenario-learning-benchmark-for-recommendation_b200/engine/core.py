@@ -169,6 +169,7 @@ class Builder:
         self.stages: List["Stage"] = []
         self.groups: List[ActGroup] = []
         self.param_order: List[nn.Parameter] = []
+        self._noted = 0
         self.buffer_order: List[torch.Tensor] = []
         self.keep: List[object] = []       # tensors whose addresses are baked into tables
         self.aux_floats = 0                # dry run: size of the derived-weight region
@@ -283,6 +284,9 @@ class Builder:
         self.buffer_order.extend(t for t in bufs if t is not None)
 
     def add(self, stage: "Stage") -> "Stage":
+        # the parameters a stage noted in its constructor (= a contiguous range of the flat store, in stage order)
+        stage._params = self.param_order[self._noted:]
+        self._noted = len(self.param_order)
         self.stages.append(stage)
         return stage
 
@@ -377,6 +381,12 @@ class GatherStage(Stage):
                                               sh.rank, sh.world, self.B_all, self.rq_keys.peer_table.data_ptr(),
                                               hy.data_ptr(), 0, self.oob.data_ptr(), stream), "emb_push_ids")
             sh.flag_barrier(stream)
+            if training and self.model.lazy_adam:   # lazy dense-Adam: the rows about to be served catch up first
+                m = self.model
+                L.check(b.lib.mmlrec_emb_adam_catch_up_keys(
+                    self.rq_keys.ptr, self.B_all, self.meta.data_ptr(), self.F_s, self.D, st.emb.data_ptr(),
+                    st.emb_s1.data_ptr(), st.emb_s2.data_ptr(), st.row_touch.data_ptr(), hy.data_ptr(), 0,
+                    m.adam_hist.data_ptr(), m.adam_hist_cap, stream), "emb_adam_catch_up_keys")
             if self.peer_read:   # K1 reads the rows straight from the owners' shards
                 L.check(b.lib.mmlrec_gather_concat_sharded(
                     self.X.data_ptr(), self.X.stride(0), b.B, sh.emb.peer_table.data_ptr(), sh.world,
@@ -432,8 +442,8 @@ class GatherStage(Stage):
 
     def catch_up(self, stream):
         """Lazy dense-Adam: the rows this step reads are brought up to the previous optimizer step (start of the step)."""
-        if not self.F_s or not self.model.lazy_adam:
-            return
+        if not self.F_s or not self.model.lazy_adam or self.sh is not None:
+            return   # (row-sharded tables: the owner catches up on the request keys, see forward)
         b, st, m = self.b, self.b.store, self.model
         L.check(b.lib.mmlrec_emb_adam_catch_up(self.X_all.data_ptr(), self.X_all.stride(0), self.B_all, self.meta.data_ptr(),
                                                self.F_s, self.D, st.emb.data_ptr(), st.emb_s1.data_ptr(), st.emb_s2.data_ptr(),
@@ -1314,10 +1324,59 @@ class StepPlan:
         # gradient slices this program writes (split-K wgrad, see LinearStage.plan_backward)
         self.grad_slices = max([getattr(s, "split_k", 1) for s in self.stages] + [1])
         self.fold_seg = self.b.ints([0, 0, model.store.slice_stride], dtype=torch.int64)
+        self._plan_buckets()
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.side = torch.cuda.Stream(device=model.device_obj)
         self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
         self.ev_bwd, self.ev_join2 = torch.cuda.Event(), torch.cuda.Event()
+
+    # ---- data parallel: gradient buckets
+    def _plan_buckets(self) -> None:
+        """Cut the flat dense-gradient store into buckets along stage boundaries.  The store is laid out in stage order
+        and backward runs the stages in reverse, so once stage k's backward has been issued the range [first parameter
+        of stage k, end) is final: its slices are folded and all-reduced on a communication stream while the earlier
+        stages' backward is still running; only the last bucket (the first stages' parameters) is reduced on the main
+        stream, after the last backward kernel.  ``b200_config["grad_bucket_floats"]`` = minimum bucket size (0: one
+        bucket = the old behaviour)."""
+        m, st = self.model, self.model.store
+        self.buckets, self.bucket_after, self.first_bucket_hi = [], {}, st.slice_stride
+        import os
+        min_floats = int(os.environ.get("MMLREC_GRAD_BUCKET_FLOATS", m.b200_config.get("grad_bucket_floats", 1 << 18)))
+        if getattr(m, "dp", None) is None or min_floats <= 0 or st.aux_floats > 64:
+            return   # (derived weights -- STAR -- are folded by a stage that runs last: one bucket)
+        firsts = []
+        for s in self.stages:
+            offs = [p._mm_off for p in getattr(s, "_params", []) if getattr(p, "_mm_kind", "") == "dense"]
+            if offs:
+                firsts.append((s, min(offs)))
+        if len(firsts) < 2 or any(a[1] >= b[1] for a, b in zip(firsts, firsts[1:])) or firsts[0][1] != 0:
+            return
+        hi = st.slice_stride
+        for s, lo in reversed(firsts[1:]):
+            if hi - lo >= min_floats and lo >= min_floats:
+                seg = self.b.ints([lo, lo, hi - lo], dtype=torch.int64)
+                self.bucket_after[id(s)] = len(self.buckets)
+                self.buckets.append((lo, hi, seg))
+                hi = lo
+        self.first_bucket_hi = hi
+        if self.buckets:
+            self.comm = torch.cuda.Stream(device=m.device_obj)
+            self.ev_bucket = [torch.cuda.Event() for _ in self.buckets]
+            self.ev_comm = torch.cuda.Event()
+            self.fold_seg = self.b.ints([0, 0, hi], dtype=torch.int64)
+
+    def _reduce_bucket(self, i: int, main) -> None:
+        """Fold + all-reduce bucket i on the communication stream, behind everything issued on `main` so far."""
+        lo, hi, seg = self.buckets[i]
+        st, lib = self.model.store, self.b.lib
+        self.ev_bucket[i].record(main)
+        self.comm.wait_event(self.ev_bucket[i])
+        with torch.cuda.stream(self.comm):
+            if self.grad_slices > 1:
+                L.check(lib.mmlrec_sum_slices(seg.data_ptr(), 1, hi - lo, st.dense_grad.data_ptr(), st.grad_slices.data_ptr(),
+                                              self.grad_slices, st.slice_stride, self.comm.cuda_stream), "fold bucket")
+            self.model.dp.sum_gradients(st.dense_grad[lo:hi])
+            self.ev_comm.record(self.comm)
 
     # ---- static inputs / outputs
     X = property(lambda self: self.gather.X)
@@ -1391,6 +1450,8 @@ class StepPlan:
         for s in reversed(self.stages):
             if s is not self.gather:
                 s.backward(stream)
+                if dp is not None and id(s) in self.bucket_after:
+                    self._reduce_bucket(self.bucket_after[id(s)], main)
         st = m.store
         p = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
 
@@ -1402,16 +1463,23 @@ class StepPlan:
         def fold_slices():
             """data parallel: the all-reduce wants ONE gradient buffer -> slice 0 += slices 1..S-1 (fixed order)"""
             if self.grad_slices > 1:
-                L.check(lib.mmlrec_sum_slices(self.fold_seg.data_ptr(), 1, st.slice_stride, st.dense_grad.data_ptr(),
+                L.check(lib.mmlrec_sum_slices(self.fold_seg.data_ptr(), 1, self.first_bucket_hi, st.dense_grad.data_ptr(),
                                               st.grad_slices.data_ptr(), self.grad_slices, st.slice_stride, stream),
                         "fold gradient slices")
+
+        def reduce_rest():
+            """the bucket that is final only now (the first stages' parameters), on the main stream; then join the
+            buckets that went out on the communication stream during the backward pass"""
+            dp.sum_gradients(st.dense_grad if not self.buckets else st.dense_grad[:self.first_bucket_hi])
+            if self.buckets:
+                main.wait_event(self.ev_comm)
 
         if dp is not None and sh is None:
             # replicated tables: collectives stay on the main stream in program order
             main.wait_event(self.ev_join)
             self.gather.backward(stream)
             fold_slices()
-            dp.sum_gradients(st.dense_grad)
+            reduce_rest()
             dense_step(1)
             return
         # the table update (K2) and the dense optimizer touch disjoint buffers: K2 runs on the side stream, behind the
@@ -1419,7 +1487,7 @@ class StepPlan:
         if sh is not None:
             self.gather.backward(stream)        # push gradient rows to their owners
             fold_slices()
-            dp.sum_gradients(st.dense_grad)     # also the barrier between the pushes and the owners' K2
+            reduce_rest()                       # also the barrier between the pushes and the owners' K2
         self.ev_bwd.record(main)
         self.side.wait_event(self.ev_bwd)
         if sh is not None:

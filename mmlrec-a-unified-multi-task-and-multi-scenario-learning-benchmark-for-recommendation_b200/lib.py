@@ -108,6 +108,7 @@ _SIGNATURES = {
     "mmlrec_hyper_advance": (C.c_int, [vp, vp]),
     "mmlrec_hyper_advance_hist": (C.c_int, [vp, vp, i32, vp]),
     "mmlrec_emb_adam_catch_up": (C.c_int, [vp, i64, i32, vp, i32, i32, vp, vp, vp, vp, vp, vp, i32, vp]),
+    "mmlrec_emb_adam_catch_up_keys": (C.c_int, [vp, i32, vp, i32, i32, vp, vp, vp, vp, vp, i32, vp, i32, vp]),
     "mmlrec_emb_adam_flush": (C.c_int, [vp, vp, vp, vp, i64, i32, vp, vp, i32, vp]),
     "mmlrec_gather_concat": (C.c_int, [vp, i64, i32, vp, vp, i32, i32, vp, i32, i32, vp, i64, vp, i64, vp, vp]),
     "mmlrec_sort_field_ids": (C.c_int, [vp, i64, i32, vp, i32, vp, vp, vp, vp]),

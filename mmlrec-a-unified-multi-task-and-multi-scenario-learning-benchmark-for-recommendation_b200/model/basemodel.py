@@ -260,10 +260,11 @@ class BaseModel(nn.Module):
             self.hyper_dev = torch.frombuffer(bytearray(bytes(h)), dtype=torch.uint8).to(self.device_obj)
             self._plans.clear()
             # exact lazy dense-Adam on the tables (csrc/emb_update.cu): rows catch up on the zero-gradient steps they
-            # missed when they are next read, instead of a sweep over every table every step.  Row-sharded tables keep
-            # the per-shard sweep (their rows are read on behalf of other ranks).
-            self.lazy_adam = (optimizer == "adam" and self.shard is None and bool(self.b200_config.get("lazy_adam", True))
-                              and self.store.n_emb > 0)
+            # missed when they are next read, instead of a sweep over every table every step.  Row-sharded tables: the
+            # owner catches up the rows named by the request keys before it serves them (the peer-read forward, where
+            # peers read the shard directly, keeps the per-shard sweep).
+            self.lazy_adam = (optimizer == "adam" and bool(self.b200_config.get("lazy_adam", True)) and self.store.n_emb > 0
+                              and (self.shard is None or self.shard.gather_mode == "owner_serve"))
             self.adam_hist_cap = 1 << 14
             self.adam_hist = (torch.zeros(2 * self.adam_hist_cap, dtype=torch.float32, device=self.device_obj)
                               if self.lazy_adam else None)
