@@ -588,7 +588,7 @@ heads_fast_kernel(const MmlrecHead* heads, int T, int B, const float* y, int64_t
   if (tid == 0) *counter = 0;                                // ready for the next launch / graph replay
   __threadfence();
   const int n_cta = (int)gridDim.x;
-  for (int i = tid; i < n_out; i += 256) {
+  for (int i = tid; i < n_out; i += 256) {   // (a 4-way split of the CTA range with 32 loads in flight measured slower)
     float a[16];
 #pragma unroll
     for (int q = 0; q < 16; ++q) a[q] = 0.f;

@@ -707,25 +707,35 @@ gate_level_backward_tiled_kernel(const MmlrecGateLevel* lv, int B, float* scratc
   }
 }
 
-// deterministic reduction of the CTA partials: 32 outputs x 8 partial-groups per CTA; each thread sums every
-// 8th partial of its output (coalesced across outputs), the 8 group sums are added in a fixed order
-__global__ void __launch_bounds__(256)
+// deterministic reduction of the CTA partials: 32 outputs x 32 partial-groups per CTA (1024 threads).  A thread sums
+// every 32nd partial of its output with all its loads in flight at once (the loop is pure L2 latency: 8 groups x 64
+// dependent rounds took 12 us for 512 partials), the 32 group sums are added in a fixed order.
+constexpr int GR_GROUPS = 32;
+__global__ void __launch_bounds__(32 * GR_GROUPS)
 gate_level_dwg_reduce_kernel(const MmlrecGateLevel* lv, const float* scratch, int n_cta, int total_wg) {
   pdl_prologue();
-  __shared__ float red[8][33];
+  __shared__ float red[GR_GROUPS][33];
   const int ix = threadIdx.x & 31, iy = threadIdx.x >> 5;
   const int i = blockIdx.x * 32 + ix;
   float s = 0.f;
   if (i < total_wg) {
-#pragma unroll 4
-    for (int c = iy; c < n_cta; c += 8) s += scratch[(int64_t)c * total_wg + i];
+    float a[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) a[q] = 0.f;
+    int c = iy;
+    for (; c + 7 * GR_GROUPS < n_cta; c += 8 * GR_GROUPS) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) a[q] += scratch[(int64_t)(c + q * GR_GROUPS) * total_wg + i];
+    }
+    for (; c < n_cta; c += GR_GROUPS) a[0] += scratch[(int64_t)c * total_wg + i];
+    s = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
   }
   red[iy][ix] = s;
   __syncthreads();
   if (iy != 0 || i >= total_wg) return;
   float t = 0.f;
 #pragma unroll
-  for (int k = 0; k < 8; ++k) t += red[k][ix];
+  for (int k = 0; k < GR_GROUPS; ++k) t += red[k][ix];
   int g = 0, off = 0;
   while (g + 1 < lv->n_gates && off + lv->n_e[g] * lv->Hg[g] <= i) { off += lv->n_e[g] * lv->Hg[g]; ++g; }
   if (lv->d_mix[g] != nullptr) {
@@ -763,7 +773,7 @@ extern "C" int mmlrec_gate_level_backward(const MmlrecGateLevel* level, int32_t 
   const int n_cta = cdiv(B, GL_BWD_ROWS);
   gate_level_backward_kernel<<<n_cta, GL_BWD_WARPS * 32, smem, (cudaStream_t)stream>>>(level, B, scratch);
   MMLREC_CHECK_LAUNCH(1);
-  launch_pdl(gate_level_dwg_reduce_kernel, dim3(cdiv(total_wg, 32)), dim3(256), 0, stream, level, (const float*)scratch, n_cta, total_wg);
+  launch_pdl(gate_level_dwg_reduce_kernel, dim3(cdiv(total_wg, 32)), dim3(32 * GR_GROUPS), 0, stream, level, (const float*)scratch, n_cta, total_wg);
   MMLREC_RETURN_LAUNCH(1);
 }
 
@@ -795,7 +805,7 @@ extern "C" int mmlrec_gate_level_backward_tiled(const MmlrecGateLevel* level, in
   const int n_cta = cdiv(B, GT_ROWS);
   launch_pdl(gate_level_backward_tiled_kernel, dim3(n_cta), dim3(GT_THREADS), (size_t)smem, stream, level, B, scratch);
   MMLREC_CHECK_LAUNCH(1);
-  launch_pdl(gate_level_dwg_reduce_kernel, dim3(cdiv(total_wg, 32)), dim3(256), 0, stream, level, (const float*)scratch, n_cta, total_wg);
+  launch_pdl(gate_level_dwg_reduce_kernel, dim3(cdiv(total_wg, 32)), dim3(32 * GR_GROUPS), 0, stream, level, (const float*)scratch, n_cta, total_wg);
   MMLREC_RETURN_LAUNCH(1);
 }
 

@@ -480,16 +480,20 @@ gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __res
       const int t_ = tile_order ? __ldg(tile_order + ti_) : ti_;
       tc = locate_tile(t_, s_prefix, s_tiles_n, n_problems);
       const Tc2Meta& m_ = s_meta[tc.pi];
-      const int nf = tc.tn * m_.bn + cq * 64;
-      const bool active_ = cq * 64 < m_.bn;
+      // fp32 output of a 128-wide tile: every epilogue warp takes ONE 32-column chunk (its own store box), so the 16
+      // warps work side by side; otherwise a warp owns 64 columns (one bf16 store box) and, with BN = 128, the warps
+      // of column quarters 2 and 3 have none
+      const bool narrow_ = m_.bn == 128 && m_.has_f32 != 0;
+      const int nf = tc.tn * m_.bn + (narrow_ ? cq * 32 : cq * 64);
+      const bool active_ = narrow_ || cq * 64 < m_.bn;
       bv0 = (active_ && m_.bias != nullptr && nf + lane < m_.N) ? __ldg(m_.bias + nf + lane) : 0.f;
-      bv1 = (active_ && m_.bias != nullptr && nf + 32 + lane < m_.N) ? __ldg(m_.bias + nf + 32 + lane) : 0.f;
+      bv1 = (active_ && !narrow_ && m_.bias != nullptr && nf + 32 + lane < m_.N) ? __ldg(m_.bias + nf + 32 + lane) : 0.f;
       const int mm = tc.tm * 256 + (int)rank * T2_BM + q * 32 + lane;
       if (active_ && m_.mask_bits != nullptr) {
         // one coalesced 128-byte read per chunk: the words of the warp's 32 rows are adjacent
         const int64_t w0 = ((int64_t)(mm >> 5) * m_.mask_bits_chunks + m_.mask_bits_chunk0 + (nf >> 5)) * 32 + (mm & 31);
         mbits0 = (mm < m_.M && nf < m_.N) ? __ldg(m_.mask_bits + w0) : 0u;
-        mbits1 = (mm < m_.M && nf + 32 < m_.N) ? __ldg(m_.mask_bits + w0 + 32) : 0u;
+        mbits1 = (!narrow_ && mm < m_.M && nf + 32 < m_.N) ? __ldg(m_.mask_bits + w0 + 32) : 0u;
       }
     };
     if (sched_begin < sched_end) prefetch_tile(sched_begin);
@@ -499,10 +503,10 @@ gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __res
       const Tc2Record* R = recs + tc.pi;
       const Tc2Meta& mt = s_meta[tc.pi];
       const int M = mt.M, N = mt.N, bn = mt.bn;
-      // a warp owns 64 columns (one bf16 store box); with BN = 128 the warps of column quarters 2 and 3 have none
-      const int nchunks = (cq * 64 < bn) ? 2 : 0;
+      const bool narrow = bn == 128 && mt.has_f32 != 0;         // see prefetch_tile: one chunk per warp
+      const int nchunks = narrow ? 1 : (cq * 64 < bn) ? 2 : 0;
       const int m_base = tc.tm * 256 + (int)rank * T2_BM + q * 32;
-      const int col0 = cq * 64;                                 // first accumulator column of this warp
+      const int col0 = narrow ? cq * 32 : cq * 64;              // first accumulator column of this warp
       const int n_first = tc.tn * bn + col0;
       const bool has_f32 = mt.has_f32 != 0, has_bf16 = mt.has_bf16 != 0;
       const uint32_t* const mask_bits = mt.mask_bits;
@@ -530,7 +534,7 @@ gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __res
       const int kind = mt.epi;
       if (kind != EPI_GENERIC && nchunks > 0) {
         // straight-line variants (see EPI_*)
-        const bool c1_ok = rows_any && n_first + 32 < N;
+        const bool c1_ok = nchunks == 2 && rows_any && n_first + 32 < N;
         if (rowsum_out != nullptr) {
           tc_wait_ld();
           if (row_ok) rowsum_out[my_m] = __uint_as_float(rs);
@@ -566,7 +570,7 @@ gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __res
         uint32_t r[32];
         if (c_ok) tc_ld32(t_row + col0 + c * 32, r);
         tc_wait_ld();
-        if (c == 1) {
+        if (c == nchunks - 1) {
           // the accumulator stage is free once this warp's last values sit in registers: tell the leader
           tc_fence_before();
           __syncwarp();

@@ -238,8 +238,12 @@ class Builder:
         for i, d in enumerate(descs):
             kb = (d.K + 63) // 64
             if pairs:
+                # bytes one CTA of the pair moves for the tile (operand k-blocks in, its 128 x BN block out) at the
+                # ~30 B/cycle/SM the L2 sustains with every SM pulling and pushing (profiles/tc_timeline_r02.txt:
+                # forward K = 256 tiles 5.7-6.5 k cycles, K = 128 dgrad 4 k, 16-k-block wgrad 18-20 k)
                 bn = 128 if (d.N <= 128 or (d.colsum and d.N > 240)) else 256
-                cost = kb * (900 if bn == 256 else 700) + 650 * (bn // 32)
+                out_b = 128 * min(bn, d.N) * (4 if d.C_f32 else 2)
+                cost = (kb * (16384 + bn * 64) + out_b) // 30 + 600
             else:
                 cost = 900 * kb + 2600
             tiles.extend((cost, t) for t in range(pre[i], pre[i + 1]))
