@@ -157,6 +157,12 @@ int mmlrec_peer_export(void* ptr, unsigned char* handle64);       /* 64-byte cud
 int mmlrec_peer_import(const unsigned char* handle64, void** ptr);
 int mmlrec_peer_close(void* ptr);
 int mmlrec_peer_fill_u64(uint64_t* p, int64_t n, uint64_t v /* 0 or ~0 */, void* stream);
+/* SUM all-reduce of `n` floats (n % 4 == 0) over peer memory: rank r reduces slice r of every rank's `peer_in[p]` in rank
+ * order (bit-identical result on every rank) and stores it into slice r of every `peer_out[p]`.  Bracket with
+ * mmlrec_peer_barrier on both sides.  The data-parallel towers' dense-gradient collective (no reference counterpart: the
+ * reference is single-process; the gradient is what loss.backward() leaves in .grad, model/basemodel.py:309-311). */
+int mmlrec_peer_allreduce_f32(const float* const* peer_in, float* const* peer_out, int64_t n, int32_t rank, int32_t R,
+                              void* stream);
 int mmlrec_peer_barrier(int32_t* const* peer_flags /* [R] -> int32 [R] */, int32_t* local_epoch, int32_t rank,
                         int32_t R, int32_t* err_flag, void* stream);
 int mmlrec_emb_push_ids(const float* X, int64_t ldx, int32_t b, const int64_t* field_meta, int32_t F_s,

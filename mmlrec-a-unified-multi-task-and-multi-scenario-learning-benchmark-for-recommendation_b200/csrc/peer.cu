@@ -121,9 +121,53 @@ __global__ void peer_barrier_kernel(int32_t* const* peer_flags, int32_t* local_e
   __threadfence_system();
 }
 
+// Dense-gradient all-reduce (SUM) over peer memory, the data-parallel towers' one collective: rank r adds up slice r
+// of every rank's gradient buffer (peer loads, fixed rank order 0..R-1 -> every rank ends up with bit-identical sums)
+// and stores the result into slice r of EVERY rank's output buffer (peer stores): a reduce-scatter and an all-gather in
+// one pass, 2 x (R-1)/R x n x 4 bytes over NVLink per GPU in each direction.  The caller brackets it with two flag
+// barriers (inputs complete everywhere / outputs landed everywhere).  Replaces ncclAllReduce on this path: 56 us for
+// 4.3 MB on 8 GPUs there, latency-dominated (profiles/sharded_timeline_8gpu_r02.txt).
+__global__ void __launch_bounds__(256) peer_allreduce_kernel(const float* const* __restrict__ in, float* const* __restrict__ out,
+                                                             int64_t n4, int rank, int R) {
+  __shared__ const float4* s_src[32];
+  __shared__ float4* s_dst[32];
+  if ((int)threadIdx.x < R) {
+    s_src[threadIdx.x] = reinterpret_cast<const float4*>(in[threadIdx.x]);
+    s_dst[threadIdx.x] = reinterpret_cast<float4*>(out[threadIdx.x]);
+  }
+  __syncthreads();
+  const int64_t per = (n4 + R - 1) / R;
+  const int64_t lo = (int64_t)rank * per, hi = lo + per < n4 ? lo + per : n4;
+  for (int64_t i = lo + blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < hi; i += (int64_t)gridDim.x * blockDim.x) {
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int p0 = 0; p0 < R; p0 += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) if (p0 + q < R) v[q] = __ldcg(s_src[p0 + q] + i);   // up to 8 peer loads in flight, L1 bypassed
+#pragma unroll
+      for (int q = 0; q < 8; ++q) if (p0 + q < R) { s.x += v[q].x; s.y += v[q].y; s.z += v[q].z; s.w += v[q].w; }
+    }
+    for (int p = 0; p < R; ++p) s_dst[p][i] = s;
+  }
+}
+
 }  // namespace mmlrec
 
 using namespace mmlrec;
+
+extern "C" int mmlrec_peer_allreduce_f32(const float* const* peer_in, float* const* peer_out, int64_t n, int32_t rank,
+                                         int32_t R, void* stream) {
+  MMLREC_CHECK_ARG(peer_in && peer_out && n > 0 && (n & 3) == 0, "buffers of a multiple of 4 floats");
+  MMLREC_CHECK_ARG(R > 0 && R <= 32 && rank >= 0 && rank < R, "bad rank / world");
+  const int64_t per = ((n >> 2) + R - 1) / R;
+  int grid = (int)((per + 255) / 256);
+  static int n_sm = 0;
+  if (!n_sm) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev); if (n_sm <= 0) n_sm = 1; }
+  if (grid > 4 * n_sm) grid = 4 * n_sm;
+  if (grid < 1) grid = 1;
+  peer_allreduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(peer_in, peer_out, n >> 2, rank, R);
+  MMLREC_RETURN_LAUNCH(1);
+}
 
 extern "C" int mmlrec_peer_alloc(void** ptr, int64_t bytes) {
   MMLREC_CHECK_ARG(ptr && bytes > 0, "bad args");

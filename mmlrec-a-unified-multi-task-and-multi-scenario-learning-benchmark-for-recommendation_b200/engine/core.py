@@ -1346,6 +1346,10 @@ class StepPlan:
         self.buckets, self.bucket_after, self.first_bucket_hi = [], {}, st.slice_stride
         import os
         min_floats = int(os.environ.get("MMLREC_GRAD_BUCKET_FLOATS", m.b200_config.get("grad_bucket_floats", 1 << 18)))
+        self.fold_all = self.b.ints([0, 0, st.slice_stride], dtype=torch.int64)
+        sh = getattr(m, "shard", None)
+        if sh is not None and sh.grad_in is not None:
+            return   # the peer-memory all-reduce takes the whole store after the last backward kernel
         if getattr(m, "dp", None) is None or min_floats <= 0 or st.aux_floats > 64:
             return   # (derived weights -- STAR -- are folded by a stage that runs last: one bucket)
         firsts = []
@@ -1459,9 +1463,9 @@ class StepPlan:
         st = m.store
         p = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
 
-        def dense_step(n_slices):
+        def dense_step(n_slices, grad_ptr=None):
             L.check(lib.mmlrec_dense_optimizer_step_sliced(
-                st.dense.data_ptr(), st.dense_grad.data_ptr(), p(st.dense_s1), p(st.dense_s2), st.n_dense,
+                st.dense.data_ptr(), grad_ptr or st.dense_grad.data_ptr(), p(st.dense_s1), p(st.dense_s2), st.n_dense,
                 m.hyper_dev.data_ptr(), p(st.dense_bf16), n_slices, st.slice_stride, stream), "dense_optimizer_step")
 
         def fold_slices():
@@ -1488,7 +1492,17 @@ class StepPlan:
             return
         # the table update (K2) and the dense optimizer touch disjoint buffers: K2 runs on the side stream, behind the
         # sort / sweep it depends on, while the main stream runs the dense optimizer
-        if sh is not None:
+        peer_ar = sh is not None and sh.grad_in is not None
+        if peer_ar:
+            # dense-gradient all-reduce over peer memory: the slices are folded straight into the exchange buffer, the
+            # reduced gradient lands in grad_out on every rank (bit-identical), which the optimizer then reads; its
+            # first flag barrier is also the barrier between the gradient-row pushes and the owners' K2
+            self.gather.backward(stream)
+            L.check(lib.mmlrec_sum_slices(self.fold_all.data_ptr(), 1, st.slice_stride, sh.grad_in.ptr,
+                                          st.grad_slices.data_ptr(), self.grad_slices, st.slice_stride, stream),
+                    "fold gradient slices -> exchange buffer")
+            sh.allreduce_gradients(stream)
+        elif sh is not None:
             self.gather.backward(stream)        # push gradient rows to their owners
             fold_slices()
             reduce_rest()                       # also the barrier between the pushes and the owners' K2
@@ -1499,7 +1513,10 @@ class StepPlan:
         else:
             self.gather.backward(self.side.cuda_stream)
         self.ev_join2.record(self.side)
-        dense_step(1 if sh is not None else self.grad_slices)
+        if peer_ar:
+            dense_step(1, sh.grad_out.ptr)
+        else:
+            dense_step(1 if sh is not None else self.grad_slices)
         main.wait_event(self.ev_join2)
 
     def capture(self) -> None:

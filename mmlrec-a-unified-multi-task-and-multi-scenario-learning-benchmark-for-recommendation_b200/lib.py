@@ -143,6 +143,7 @@ _SIGNATURES = {
     "mmlrec_peer_fill_u64": (C.c_int, [vp, i64, C.c_uint64, vp]),
     "mmlrec_gather_concat_sharded": (C.c_int, [vp, i64, i32, vp, i32, vp, i32, i32, vp, i32, i32, vp, i64, vp, i64, vp, vp]),
     "mmlrec_peer_barrier": (C.c_int, [vp, vp, i32, i32, vp, vp]),
+    "mmlrec_peer_allreduce_f32": (C.c_int, [vp, vp, i64, i32, i32, vp]),
     "mmlrec_emb_push_ids": (C.c_int, [vp, i64, i32, vp, i32, i32, i32, i32, vp, vp, i32, vp, vp]),
     "mmlrec_emb_serve_rows": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, vp, vp, i32, vp]),
     "mmlrec_gather_concat_staged": (C.c_int, [vp, i64, i32, vp, vp, i32, i32, vp, i32, i32, vp, i64, vp, i64, vp]),

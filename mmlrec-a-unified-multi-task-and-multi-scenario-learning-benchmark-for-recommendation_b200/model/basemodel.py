@@ -128,9 +128,12 @@ class BaseModel(nn.Module):
         if sh:
             from ..parallel import ShardContext
             self.shard = ShardContext(int(sh["rank"]), int(sh["world"]))
-            self.shard.gather_mode = sh.get("gather", "owner_serve")
-            if self.shard.gather_mode not in ("owner_serve", "peer_read"):
-                raise ValueError('shard_tables["gather"] must be "owner_serve" or "peer_read"')
+            # "auto": shards small enough for the peer TLB reach are read in place by the requesters (no id / row
+            # round trip through the owner at the head of the step), big ones are served by their owner
+            import os
+            self.shard.gather_mode = sh.get("gather", os.environ.get("MMLREC_SHARD_GATHER", "auto"))
+            if self.shard.gather_mode not in ("auto", "owner_serve", "peer_read"):
+                raise ValueError('shard_tables["gather"] must be "auto", "owner_serve" or "peer_read"')
         self.embedding_dict = create_embedding_matrix(dnn_feature_columns, init_std, sparse=False, device="cpu",
                                                       shard_world=self.shard.world if self.shard else 1)
         self.out = PredictionLayer(self.model_config.get("task", "binary"))
@@ -206,6 +209,9 @@ class BaseModel(nn.Module):
                                ordered_buffers=dry.buffer_order, aux_floats=dry.aux_floats + 64,
                                emb_alloc=self.shard.alloc_emb if self.shard else None)
         self._index_features()  # re-read the re-pointed table parameters
+        if self.shard is not None and self.shard.gather_mode == "auto":
+            limit = int(self.b200_config.get("peer_read_max_shard_bytes", 64 << 20))
+            self.shard.gather_mode = "peer_read" if 4 * self.store.n_emb <= limit else "owner_serve"
 
     def hyper_host_step(self) -> int:
         """Optimizer step count read back from the device clock (synchronises; evaluation paths only)."""

@@ -136,6 +136,8 @@ class ShardContext:
         self.flags: Optional[PeerBuffer] = None      # int32 [world]: barrier epochs written by the peers
         self.epoch: Optional[torch.Tensor] = None
         self.err: Optional[torch.Tensor] = None
+        self.grad_in: Optional[PeerBuffer] = None    # dense-gradient all-reduce over peer memory (csrc/peer.cu)
+        self.grad_out: Optional[PeerBuffer] = None
 
     def local_rows(self, vocabulary: int) -> int:
         return (vocabulary + self.world - 1) // self.world
@@ -172,6 +174,21 @@ class ShardContext:
                                                            self.rank, self.world, self.err.data_ptr(), stream),
                           "peer_barrier")
 
+    def connect_gradients(self, n_floats: int, device: torch.device) -> None:
+        """Exchange buffers of the peer-memory dense-gradient all-reduce (collective; called by attach_sharded)."""
+        if self.grad_in is None:
+            self.grad_in = self.alloc_exchanged(4 * n_floats, device)
+            self.grad_out = self.alloc_exchanged(4 * n_floats, device)
+            self.grad_floats = n_floats
+
+    def allreduce_gradients(self, stream: int) -> None:
+        """grad_out (every rank) = sum over ranks of grad_in, in rank order; flag barriers on both sides."""
+        self.flag_barrier(stream)
+        self.emb._L.check(self.emb.lib.mmlrec_peer_allreduce_f32(self.grad_in.peer_table.data_ptr(),
+                                                                 self.grad_out.peer_table.data_ptr(), self.grad_floats,
+                                                                 self.rank, self.world, stream), "peer_allreduce")
+        self.flag_barrier(stream)
+
     def check(self) -> None:
         """Raise if a barrier gave up waiting for a peer (host-side, outside the captured step)."""
         if int(self.err.item()) != 0:
@@ -187,6 +204,10 @@ def attach_sharded(model, group: Optional[dist.ProcessGroup] = None) -> ShardCon
     sh.group = group
     model.dp = DataParallelContext(sh.rank, sh.world, group)
     sh.connect()
+    import os
+    if model.store is not None and os.environ.get("MMLREC_NCCL_ALLREDUCE") is None \
+            and model.b200_config.get("peer_allreduce", True):
+        sh.connect_gradients(model.store.slice_stride, model.device_obj)
     model._plans.clear()
     return sh
 

@@ -139,7 +139,7 @@ def test_static_tile_schedule_is_a_balanced_partition(kernel):
     b.tc_kernel = kernel
     units = 148 if kernel == 1 else 74
     # a backward launch: 28 long wgrad tiles (K = 4096) + 896 short dgrad tiles (K = 128) + one odd problem
-    mk = lambda K, N, cs: types.SimpleNamespace(K=K, N=N, colsum=cs)  # noqa: E731
+    mk = lambda K, N, cs: types.SimpleNamespace(K=K, N=N, colsum=cs, C_f32=cs)  # noqa: E731  (wgrad: fp32 output)
     descs = [mk(4096, 256, 1)] * 14 + [mk(128, 256, None)] * 14 + [mk(199, 3904, None)]
     tiles_per = [2] * 14 + [64] * 14 + [7]
     pre = [0]
@@ -154,7 +154,7 @@ def test_static_tile_schedule_is_a_balanced_partition(kernel):
         kb = (d.K + 63) // 64
         if kernel == 2:
             bn = 128 if (d.N <= 128 or (d.colsum and d.N > 240)) else 256
-            c = kb * (900 if bn == 256 else 700) + 650 * (bn // 32)
+            c = (kb * (16384 + bn * 64) + 128 * min(bn, d.N) * (4 if d.C_f32 else 2)) // 30 + 600
         else:
             c = 900 * kb + 2600
         for t in range(pre[i], pre[i + 1]):
