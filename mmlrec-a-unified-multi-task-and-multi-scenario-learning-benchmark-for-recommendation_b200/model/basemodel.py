@@ -128,10 +128,11 @@ class BaseModel(nn.Module):
         if sh:
             from ..parallel import ShardContext
             self.shard = ShardContext(int(sh["rank"]), int(sh["world"]))
-            # "auto": shards small enough for the peer TLB reach are read in place by the requesters (no id / row
-            # round trip through the owner at the head of the step), big ones are served by their owner
+            # "owner_serve" (default): ids -> owner -> rows; works with the lazy dense-Adam.  "peer_read": requesters read
+            # the shard in place (no row round trip, but the owner must sweep its shard every step).  "auto": peer_read
+            # for shards within the peer TLB reach (measured slower than owner_serve + lazy Adam at 2 GPUs on PLE-AE)
             import os
-            self.shard.gather_mode = sh.get("gather", os.environ.get("MMLREC_SHARD_GATHER", "auto"))
+            self.shard.gather_mode = sh.get("gather", os.environ.get("MMLREC_SHARD_GATHER", "owner_serve"))
             if self.shard.gather_mode not in ("auto", "owner_serve", "peer_read"):
                 raise ValueError('shard_tables["gather"] must be "auto", "owner_serve" or "peer_read"')
         self.embedding_dict = create_embedding_matrix(dnn_feature_columns, init_std, sparse=False, device="cpu",
