@@ -363,6 +363,8 @@ class BaseModel(nn.Module):
             self._autograd_step(p)
             return
         n = self._steps_on_plan[p.B]
+        if p.B == 1 and self.model_config.get("dnn_use_bn", False):
+            raise ValueError("Expected more than 1 value per channel when training")   # what nn.BatchNorm1d raises
         if self.lazy_adam:
             if self._steps_since_flush >= self.adam_hist_cap - 2:   # the history ring is about to wrap
                 self.flush_tables()
