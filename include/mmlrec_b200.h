@@ -254,6 +254,13 @@ typedef struct MmlrecGemmTcDesc {           /* host-side description of one prob
    * chunk of this problem's column 0 (its first column must be a multiple of 32). */
   uint32_t* relu_bits_out; int32_t bits_out_chunks, bits_out_chunk0;
   const uint32_t* mask_bits; int32_t mask_bits_chunks, mask_bits_chunk0;
+  /* CTA-pair kernel only: store the fp32 result TRANSPOSED, C_f32[n * ldc_f32 + m] = D[m][n] (no bias / mask / activation /
+   * accumulate / colsum).  Lets a weight gradient dW[N_out, K_in] with N_out <= 128 be computed as the product
+   * X^T dZ (M = K_in: full 256-row pair tiles) instead of dZ^T X (M = N_out: half of every pair tile empty). */
+  int32_t c_transposed, pad1;
+  /* with c_transposed (N <= 128): also out[n] = sum_k B[n][k] -- the bias gradient when B = dZ -- from one extra MMA per
+   * k-step against an all-ones A tile, accumulated in the spare TMEM columns of the stage */
+  float* colsum_b;
 } MmlrecGemmTcDesc;
 /* size in bytes of one device problem record; the table is `n * mmlrec_tc_record_bytes()` */
 int64_t mmlrec_tc_record_bytes(void);

@@ -369,6 +369,7 @@ extern "C" int32_t mmlrec_tc_num_tiles(int32_t M, int32_t N) { return cdiv(M, TC
 
 extern "C" int mmlrec_tc_encode_problem(const MmlrecGemmTcDesc* d, void* record_host) {
   MMLREC_CHECK_ARG(d && record_host, "null argument");
+  MMLREC_CHECK_ARG(!d->c_transposed, "transposed stores are a CTA-pair kernel feature");
   MMLREC_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0, "bad sizes");
   MMLREC_CHECK_ARG(((uintptr_t)d->A & 15) == 0 && ((uintptr_t)d->B & 15) == 0, "operands must be 16-byte aligned");
   MMLREC_CHECK_ARG((d->lda & 7) == 0 && (d->ldb & 7) == 0, "operand row strides must be multiples of 8 elements");

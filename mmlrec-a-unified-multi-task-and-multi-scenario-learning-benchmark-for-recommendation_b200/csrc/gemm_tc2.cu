@@ -52,6 +52,8 @@ struct alignas(128) Tc2Record {
   uint32_t* bits_out; const uint32_t* mask_bits; // ReLU bit masks (see MmlrecGemmTcDesc)
   int32_t bits_out_chunks, bits_out_chunk0, mask_bits_chunks, mask_bits_chunk0;
   int32_t epi;                                  // epilogue variant (EPI_*), chosen at encode time
+  float* c_t; int64_t ldc_t;                    // EPI_F32_TRANSPOSED: C[n * ldc_t + m] = D[m][n]
+  float* colsum_b;                              // with it: column sums of B over K (ones-tile MMA into TMEM columns 128..)
 };
 
 // the scalar part of a record, cached in shared memory once per CTA (every role reads it at every tile)
@@ -67,6 +69,8 @@ struct Tc2Meta {
   int32_t bits_out_chunks, bits_out_chunk0, mask_bits_chunks, mask_bits_chunk0;
   int32_t epi;
   uint32_t* bits_out; const uint32_t* mask_bits;
+  float* c_t; int64_t ldc_t;
+  float* colsum_b;
 };
 
 // Epilogue variants.  The generic one handles every combination of mask / bias / activation / output precision at
@@ -80,6 +84,8 @@ enum : int {
   EPI_BF16_MASKBITS = 3,     // bf16 out = acc where the producer's ReLU bit is set (dgrad into a hidden layer)
   EPI_F32_FWD = 4,           // fp32 out = relu(acc + bias)
   EPI_F32_PLAIN = 5,         // fp32 out (+)= acc (wgrad incl. bias-gradient row sums, dgrad into fp32 gradient buffers)
+  EPI_F32_TRANSPOSED = 6,    // fp32 C[n][m] = acc[m][n], straight from registers (thread = row m: a warp's 32 stores of
+                             // one column are 128 contiguous bytes) -- weight gradients computed as X^T dZ
 };
 
 constexpr int T2_SMEM_BYTES = 1024 + T2_STAGES * (T2_A_BYTES + T2_B_BYTES) + T2_EPI_WARPS * T2_OUT_BUF_BYTES +
@@ -226,6 +232,7 @@ struct EpiTile {
   uint32_t* bits_word;                       // where this row's bit word of chunk 0 goes (chunk 1: + 32 words)
   int m_base, n_first, lane, accumulate;
   bool row_ok, c1_ok;
+  float* c_t; int64_t ldc_t; int N;          // EPI_F32_TRANSPOSED
 };
 
 // The warp's 32 x 64 block, chunk by chunk: tcgen05.ld -> (stage handed back after the last load) -> packed math ->
@@ -258,6 +265,13 @@ __device__ __forceinline__ void epi_tile_lean(const EpiTile& e, uint32_t taddr, 
         __syncwarp();
       }
       stage_bf16_chunk(e.buf, e.row_off, e.sw, c, p);
+    } else if (KIND == EPI_F32_TRANSPOSED) {
+      if (e.row_ok) {
+        float* col = e.c_t + (int64_t)(e.n_first + 32 * c) * e.ldc_t + (e.m_base + e.lane);
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (e.n_first + 32 * c + j < e.N) col[(int64_t)j * e.ldc_t] = __uint_as_float(r[j]);
+      }
     } else {
       if (KIND == EPI_F32_FWD) {
 #pragma unroll
@@ -319,7 +333,7 @@ gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __res
     m.bias = R->bias; m.mask = R->mask; m.ldmask = R->ldmask; m.rowsum_a = R->rowsum_a;
     m.M = R->M; m.N = R->N; m.K = R->K; m.act = R->act; m.accumulate = R->accumulate;
     m.a_mn = R->a_mn; m.b_mn = R->b_mn; m.has_f32 = R->has_f32; m.has_bf16 = R->has_bf16;
-    m.bn = R->bn; m.rowsum_col = R->rowsum_col; m.epi = R->epi;
+    m.bn = R->bn; m.rowsum_col = R->rowsum_col; m.epi = R->epi; m.c_t = R->c_t; m.ldc_t = R->ldc_t; m.colsum_b = R->colsum_b;
     m.bits_out = R->bits_out; m.mask_bits = R->mask_bits;
     m.bits_out_chunks = R->bits_out_chunks; m.bits_out_chunk0 = R->bits_out_chunk0;
     m.mask_bits_chunks = R->mask_bits_chunks; m.mask_bits_chunk0 = R->mask_bits_chunk0;
@@ -408,6 +422,9 @@ gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __res
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       const uint64_t ones_desc = make_smem_desc(smem_u32(sOnes), false);
+      // the same all-ones bytes as an A operand of 128 rows per CTA: a zero stride between the 8-row groups makes all of
+      // them alias the first 1 KB (every element is 1.0, so the swizzle pattern is irrelevant)
+      const uint64_t ones_a_desc = ones_desc & ~((uint64_t)0x3FFF << 32);
       int mit = -1;
       for (int ti = sched_begin; ti < sched_end; ti += sched_step) {
         ++mit;
@@ -421,6 +438,10 @@ gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __res
         const bool rowsum_shared = rowsum_col < bn;      // the row sums live in unused columns of the main accumulator
         const uint32_t idesc = make_idesc(256, bn, a_mn, b_mn);
         const uint32_t idesc_ones = make_idesc(256, 16, a_mn, false);
+        // column sums of B (bias gradient of a transposed-product wgrad): D2[256 x bn] += ones[256 x 16] B^T into the
+        // spare columns 128.. of the stage; every row of D2 is the column-sum vector
+        const bool colsum_b = mt.colsum_b != nullptr && tc.tm == 0;
+        const uint32_t idesc_csb = make_idesc(256, bn, false, b_mn);
         const int num_kb = (K + T2_BK - 1) / T2_BK;
         T2_STAMP(mit, 4);
         mbar_wait(tempty_bar + 8 * acc, acc_phase ^ 1);
@@ -443,6 +464,7 @@ gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __res
               // (shared columns were just zeroed / kept by the main MMA: B rows >= N are TMA zero fill)
               if (rowsum) tc2_mma(d_tmem + rowsum_col, a_desc + a_step * k, ones_desc + 2 * k, idesc_ones,
                                   rowsum_shared ? 1u : accumulate);
+              if (colsum_b) tc2_mma(d_tmem + 128, ones_a_desc + 2 * k, b_desc + b_step * k, idesc_csb, accumulate);
             }
           }
           tc2_commit(empty_bar + 8 * stage);             // frees the stage in both CTAs
@@ -530,6 +552,10 @@ gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __res
       const uint32_t t_row = tmem_base + acc * T2_ACC_COLS + ((uint32_t)(q * 32) << 16);
       uint32_t rs = 0;
       if (rowsum_out != nullptr) tc_ld1(t_row + rowsum_col, rs);
+      // column sums of B: every row of the second accumulator holds them; the leader's row-0 warps read one chunk each
+      float* const csb = (mt.colsum_b != nullptr && tc.tm == 0 && rank == 0 && q == 0 && narrow) ? mt.colsum_b : nullptr;
+      uint32_t rc[32];
+      if (csb != nullptr) tc_ld32(t_row + 128 + cq * 32, rc);
       const bool first_ok = rows_any && n_first < N;
       const int kind = mt.epi;
       if (kind != EPI_GENERIC && nchunks > 0) {
@@ -538,6 +564,14 @@ gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __res
         if (rowsum_out != nullptr) {
           tc_wait_ld();
           if (row_ok) rowsum_out[my_m] = __uint_as_float(rs);
+        }
+        if (csb != nullptr) {
+          tc_wait_ld();
+          if (lane == 0) {
+            const int n0 = tc.tn * bn + cq * 32;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if (n0 + j < N) csb[n0 + j] = __uint_as_float(rc[j]);
+          }
         }
         if (!first_ok) {                                         // nothing of this warp's block is inside the problem
           tc_fence_before();
@@ -551,12 +585,14 @@ gemm_grouped_tc2_kernel(const Tc2Record* __restrict__ recs, const int32_t* __res
               : bits_out + ((int64_t)(my_m >> 5) * mt.bits_out_chunks + mt.bits_out_chunk0 + (n_first >> 5)) * 32 + (my_m & 31);
           e.m_base = m_base; e.n_first = n_first; e.lane = lane; e.accumulate = accumulate;
           e.row_ok = row_ok; e.c1_ok = c1_ok;
+          e.c_t = mt.c_t; e.ldc_t = mt.ldc_t; e.N = N;
           const uint32_t taddr = t_row + col0, rel = tempty_bar + 8 * acc;
           switch (kind) {
             case EPI_BF16_FWD_BITS: epi_tile_lean<EPI_BF16_FWD_BITS>(e, taddr, rel); break;
             case EPI_BF16_FWD:      epi_tile_lean<EPI_BF16_FWD>(e, taddr, rel); break;
             case EPI_BF16_MASKBITS: epi_tile_lean<EPI_BF16_MASKBITS>(e, taddr, rel); break;
             case EPI_F32_FWD:       epi_tile_lean<EPI_F32_FWD>(e, taddr, rel); break;
+            case EPI_F32_TRANSPOSED: epi_tile_lean<EPI_F32_TRANSPOSED>(e, taddr, rel); break;
             default:                epi_tile_lean<EPI_F32_PLAIN>(e, taddr, rel); break;
           }
         }
@@ -680,9 +716,15 @@ extern "C" int mmlrec_tc2_encode_problem(const MmlrecGemmTcDesc* d, void* record
   MMLREC_CHECK_ARG(d->M > 0 && d->N > 0 && d->K > 0, "bad sizes");
   MMLREC_CHECK_ARG(((uintptr_t)d->A & 15) == 0 && ((uintptr_t)d->B & 15) == 0, "operands must be 16-byte aligned");
   MMLREC_CHECK_ARG((d->lda & 7) == 0 && (d->ldb & 7) == 0, "operand row strides must be multiples of 8 elements");
-  MMLREC_CHECK_ARG(d->C_f32 == nullptr || ((d->ldc_f32 & 3) == 0 && ((uintptr_t)d->C_f32 & 15) == 0), "C_f32 alignment");
+  MMLREC_CHECK_ARG(d->C_f32 == nullptr || d->c_transposed || ((d->ldc_f32 & 3) == 0 && ((uintptr_t)d->C_f32 & 15) == 0), "C_f32 alignment");
   MMLREC_CHECK_ARG(d->C_bf16 == nullptr || ((d->ldc_bf16 & 7) == 0 && ((uintptr_t)d->C_bf16 & 15) == 0), "C_bf16 alignment");
   MMLREC_CHECK_ARG(d->mask == nullptr || ((d->ldmask & 7) == 0 && ((uintptr_t)d->mask & 15) == 0), "mask alignment");
+  MMLREC_CHECK_ARG(!d->c_transposed || (d->C_f32 != nullptr && d->C_bf16 == nullptr && d->bias == nullptr && d->mask == nullptr &&
+                                        d->mask_bits == nullptr && d->relu_bits_out == nullptr && d->colsum == nullptr &&
+                                        (d->colsum_b == nullptr || d->N <= 128) &&
+                                        d->act == MMLREC_ACT_NONE && !d->accumulate),
+                   "a transposed store takes the plain fp32 product only");
+  MMLREC_CHECK_ARG(d->colsum_b == nullptr || d->c_transposed, "colsum_b comes with c_transposed");
   MMLREC_CHECK_ARG((d->C_f32 != nullptr) != (d->C_bf16 != nullptr),
                    "the CTA-pair kernel writes one output precision per problem (list the problem twice for both)");
   Tc2Record rec;
@@ -696,7 +738,7 @@ extern "C" int mmlrec_tc2_encode_problem(const MmlrecGemmTcDesc* d, void* record
   if (!d->b_mn_major) rc = tc_encode_map(&rec.tmB, BF, 2, d->B, d->ldb, d->K, d->N, T2_BK, bn / 2);
   else                rc = tc_encode_map(&rec.tmB, BF, 2, d->B, d->ldb, d->N, d->K, 64, T2_BK);
   if (rc) return rc;
-  if (d->C_f32) {
+  if (d->C_f32 && !d->c_transposed) {
     rc = tc_encode_map(&rec.tmC32, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, d->C_f32, d->ldc_f32, d->N, d->M, 32, 32);
     if (rc) return rc;
   }
@@ -724,6 +766,7 @@ extern "C" int mmlrec_tc2_encode_problem(const MmlrecGemmTcDesc* d, void* record
       if (d->act == MMLREC_ACT_RELU && d->colsum == nullptr && !d->accumulate) epi = EPI_F32_FWD;
       else if (d->act == MMLREC_ACT_NONE && d->bias == nullptr) epi = EPI_F32_PLAIN;
     }
+    if (d->c_transposed) { epi = EPI_F32_TRANSPOSED; rec.c_t = d->C_f32; rec.ldc_t = d->ldc_f32; rec.colsum_b = d->colsum_b; }
     rec.epi = epi;
   }
   rec.bits_out = d->relu_bits_out; rec.bits_out_chunks = d->bits_out_chunks; rec.bits_out_chunk0 = d->bits_out_chunk0;

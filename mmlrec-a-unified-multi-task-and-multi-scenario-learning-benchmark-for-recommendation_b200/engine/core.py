@@ -21,6 +21,7 @@ writer of a gradient assigns, later writers accumulate (``Act.grad_written``).
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import List, Optional, Sequence, Tuple
 
 import torch
@@ -727,9 +728,23 @@ class LinearStage(Stage):
                 dz16, dz_ld = dzg.gbuf16.data_ptr() + 2 * g.y_col, dzg.gbuf16.stride(0)
                 # wgrad: both operands MN-major (no transposed copies); batch slice k -> gradient slice k
                 S = self.split_k
+                # a layer with few outputs: dW^T = X^T dZ (M = K_in fills the 256-row pair tiles; with M = N_out <= 128
+                # half of every tile is empty and the peer CTA's operand path idles), stored transposed from registers;
+                # the bias gradient = column sums of dZ from an all-ones A tile (MmlrecGemmTcDesc.colsum_b)
+                swapped = b.tc_kernel == 2 and not g.transposed and g.N <= 128 and g.K >= g.N \
+                    and os.environ.get("MMLREC_NO_WGRAD_SWAP") is None
                 for k in range(S):
                     rows = b.B // S
                     d = L.GemmTcDesc()
+                    if swapped:
+                        d.A, d.lda, d.a_mn_major = x.ptr16 + 2 * k * rows * x.ld16, x.ld16, 1
+                        d.B, d.ldb, d.b_mn_major = dz16 + 2 * k * rows * dz_ld, dz_ld, 1
+                        d.M, d.N, d.K = g.K, g.N, rows
+                        d.C_f32, d.ldc_f32 = st.grad_ptr(g.W) + 4 * k * st.slice_stride, g.W._mm_ld
+                        d.c_transposed = 1
+                        d.colsum_b = (st.grad_ptr(g.b) + 4 * k * st.slice_stride) if g.b is not None else None
+                        waves[0].append(d)
+                        continue
                     if g.transposed:   # dW[k,n] for a [K, N] parameter: the operands swap roles
                         d.A, d.lda, d.a_mn_major = x.ptr16 + 2 * k * rows * x.ld16, x.ld16, 1
                         d.B, d.ldb, d.b_mn_major = dz16 + 2 * k * rows * dz_ld, dz_ld, 1

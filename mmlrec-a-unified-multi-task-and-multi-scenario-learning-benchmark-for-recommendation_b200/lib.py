@@ -43,7 +43,8 @@ class GemmTcDesc(C.Structure):
                 ("ldc_bf16", i64), ("bias", vp), ("mask", vp), ("ldmask", i64), ("colsum", vp),
                 ("act", i32), ("accumulate", i32),
                 ("relu_bits_out", vp), ("bits_out_chunks", i32), ("bits_out_chunk0", i32),
-                ("mask_bits", vp), ("mask_bits_chunks", i32), ("mask_bits_chunk0", i32)]
+                ("mask_bits", vp), ("mask_bits_chunks", i32), ("mask_bits_chunk0", i32),
+                ("c_transposed", i32), ("pad1", i32), ("colsum_b", vp)]
 
 
 def split_two_output_problems(descs):

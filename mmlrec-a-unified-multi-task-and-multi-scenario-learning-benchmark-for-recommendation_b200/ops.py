@@ -193,7 +193,8 @@ def tc_desc(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, a_mn: bool
             bias: Optional[torch.Tensor] = None, mask: Optional[torch.Tensor] = None,
             rowsum_a: Optional[torch.Tensor] = None, act: Optional[str] = None, accumulate: bool = False,
             relu_bits_out: Optional[torch.Tensor] = None, mask_bits: Optional[torch.Tensor] = None,
-            bits_chunks: int = 0, bits_chunk0: int = 0) -> L.GemmTcDesc:
+            bits_chunks: int = 0, bits_chunk0: int = 0, c_transposed: bool = False,
+            colsum_b: Optional[torch.Tensor] = None) -> L.GemmTcDesc:
     """D[M,N] = act(A B^T + bias).  ``A`` is a bf16 array [M,K] (or [K,M] when ``a_mn``); ``B`` is [N,K]
     (or [K,N] when ``b_mn``); both row-major with stride(1) == 1."""
     _need_cuda(A, B)
@@ -213,6 +214,9 @@ def tc_desc(A: torch.Tensor, B: torch.Tensor, M: int, N: int, K: int, a_mn: bool
     if rowsum_a is not None:
         d.colsum = rowsum_a.data_ptr()
     d.act, d.accumulate = L.ACT_CODES[act], int(accumulate)
+    d.c_transposed = int(c_transposed)   # C_f32 is then [N, M]: C[n, m] = D[m, n] (pair kernel)
+    if colsum_b is not None:             # [N] fp32: sums of B over K (N <= 128, with c_transposed)
+        d.colsum_b = colsum_b.data_ptr()
     if relu_bits_out is not None:   # int32 [ceil(M/32), bits_chunks, 32] (pair kernel only)
         d.relu_bits_out, d.bits_out_chunks, d.bits_out_chunk0 = relu_bits_out.data_ptr(), bits_chunks, bits_chunk0
     if mask_bits is not None:

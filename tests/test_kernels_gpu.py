@@ -370,6 +370,28 @@ def test_gemm_tc_pair_relu_bitmask_roundtrip(M, N, col0):
     assert torch.equal(out16[:, :N], out_bits[:, :N].to(torch.bfloat16)), "same fp32 values, rounded once"
 
 
+@pytest.mark.parametrize("M,N,K", [(256, 128, 1024), (199, 64, 520), (300, 100, 136), (128, 8, 4096), (264, 1792, 512)])
+def test_gemm_tc_pair_transposed_store_and_colsum(M, N, K):
+    """Weight gradient of a layer with few outputs as the transposed product: D[m, n] = sum_k X[k, m] dZ[k, n] with both
+    operands read MN-major, stored as C[n, m] straight from registers; for N <= 128 the bias gradient (column sums of
+    dZ) comes out of the same problem through the all-ones A tile."""
+    from mmlrec_b200 import ops
+    dev = _cuda()
+    g = torch.Generator().manual_seed(M + 3 * N + K)
+    X = _bf16(torch.randn(K, (M + 7) // 8 * 8, generator=g)).to(dev)
+    dZ = _bf16(torch.randn(K, (N + 7) // 8 * 8, generator=g)).to(dev)
+    C = torch.full((N, (M + 3) // 4 * 4 + 4), float("nan"), device=dev)
+    cs = torch.full((N,), float("nan"), device=dev) if N <= 128 else None
+    d = ops.tc_desc(X[:, :M], dZ[:, :N], M, N, K, a_mn=True, b_mn=True, C_f32=C, c_transposed=True, colsum_b=cs)
+    ops.TcProblemTable([d], dev, kernel=2).launch()
+    torch.cuda.synchronize()
+    want = dZ[:, :N].float().T @ X[:, :M].float()
+    assert rel_err(C[:, :M], want) < 1e-5
+    assert torch.isnan(C[:, M:]).all(), "nothing is written beyond column M"
+    if cs is not None:
+        assert rel_err(cs, dZ[:, :N].float().sum(0)) < 1e-5
+
+
 # ------------------------------------------------------------------------------------------------ dense optimizer
 @pytest.mark.parametrize("opt", ["adam", "adagrad", "sgd", "rmsprop"])
 def test_dense_optimizer_matches_torch(opt):
