@@ -1,5 +1,5 @@
 """Model zoo on the fused step program.  ``get_model`` mirrors ``main.py:37-68`` of the reference
-(case-insensitive names); the families outside the fused step (snr_trans, mssm, pcg, apg, aitm, escm) raise ``NotImplementedError`` by name."""
+(case-insensitive names); the families outside the fused step (snr_trans, mssm, apg, aitm, escm) raise ``NotImplementedError`` by name."""
 from .cross_stitch import CrossStitch
 from .esmm import ESMM
 from .hmoe import HMOE
@@ -11,7 +11,11 @@ from .sharedbottom import SharedBottom
 from .star import STAR
 
 _REGISTRY = {"mmoe": MMOE, "ple": PLE, "sharedbottom": SharedBottom, "esmm": ESMM, "star": STAR, "pepnet": PepNet,
-             "mlp": MLP, "cross_stitch": CrossStitch, "hmoe": HMOE}
+             "mlp": MLP, "cross_stitch": CrossStitch, "hmoe": HMOE,
+             # main.py:53-54 builds an MMOE for 'pcg' and wraps its optimizer in PCGrad (basemodel.py:564-565).  The loop
+             # hands pc_backward ONE objective -- the summed loss (basemodel.py:309-310) -- so the projection is the
+             # identity and the step is MMoE's (pinned by the golden case pcg_kuairec_adam)
+             "pcg": MMOE}
 
 REFERENCE_NAMES = ("mmoe", "esmm", "sharedbottom", "ple", "snr_trans", "mssm", "star", "pcg", "apg", "mlp",
                    "cross_stitch", "aitm", "escm", "hmoe", "pepnet")

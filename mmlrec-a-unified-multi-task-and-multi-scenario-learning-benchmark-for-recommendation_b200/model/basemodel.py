@@ -249,8 +249,6 @@ class BaseModel(nn.Module):
             raise NotImplementedError("optimizer must be a name or a torch.optim.Optimizer over model.parameters()")
         if optimizer not in ("sgd", "adam", "adagrad", "rmsprop"):
             raise NotImplementedError
-        if self.model_config["model_name"] == "pcg":
-            raise NotImplementedError("PCGrad (model_name='pcg') is outside the fused hot path")
         losses = [loss] * self.num_tasks if isinstance(loss, str) else list(loss or [])
         for t, (lname, ttype) in enumerate(zip(losses, self.task_types)):
             ok = (lname == "binary_crossentropy" and ttype == "binary") or (lname == "mse" and ttype == "regression")

@@ -75,9 +75,13 @@ CASES = {
                                   dict(SMALL, model_name="cross_stitch", shared_hidden_unit=16), {}),
     "hmoe_kuairec_adam": ("kuairec_sharedbottom", dict(max_vocab=200),
                           dict(SMALL, model_name="hmoe", task_weight_hidden_units=[8]), {}),
+    # 'pcg' = MMOE whose optimizer is wrapped in PCGrad (main.py:53-54, basemodel.py:564-565); the step goes through
+    # optim.pc_backward(total_loss) (basemodel.py:309-310) -- one objective, so no projection ever happens
+    "pcg_kuairec_adam": ("kuairec_sharedbottom", dict(max_vocab=200), dict(SMALL, model_name="pcg"), {}),
 }
 # cases whose identity / 1e-4 initial state would leave parts of the model untested: perturbed after construction
-INIT_STD.update({"cross_stitch_kuairec_adam": 0.05, "hmoe_kuairec_adam": 0.05, "mlp_kuairec_adam": 0.05})
+INIT_STD.update({"cross_stitch_kuairec_adam": 0.05, "hmoe_kuairec_adam": 0.05, "mlp_kuairec_adam": 0.05,
+                 "pcg_kuairec_adam": 0.05})
 
 
 def post_build(case, model):
@@ -119,7 +123,7 @@ def build_reference(cfg, fields, init_std=0.0001):
     cols = [SparseFeat(n, vocabulary_size=v, embedding_dim=emb) if k == "sparse" else DenseFeat(n, 1)
             for n, k, v in fields]
     cls = {"mmoe": MMOE, "ple": PLE, "sharedbottom": SharedBottom, "esmm": ESMM, "star": STAR,
-           "pepnet": PepNet, "mlp": MLP, "cross_stitch": CrossStitch, "hmoe": HMOE}[cfg["model_config"]["model_name"].lower()]
+           "pepnet": PepNet, "mlp": MLP, "cross_stitch": CrossStitch, "hmoe": HMOE, "pcg": MMOE}[cfg["model_config"]["model_name"].lower()]
     with contextlib.redirect_stdout(io.StringIO()):
         model = cls(cols, init_std=init_std, device="cpu", config=cfg)
         model.compile(optimizer=cfg["optim_config"]["optimizer"], loss=cfg["optim_config"]["loss"],
@@ -151,7 +155,10 @@ def reference_step(model, X, y):
     # model.loss_func is the list compile() built through _get_loss_func_single (basemodel.py:595-604)
     loss = sum(model.loss_func[i](y_pred[:, i], y[:, i], reduction="sum") for i in range(model.num_tasks))
     total = loss + model.get_regularization_loss() + model.aux_loss + torch.zeros((1,))
-    total.backward()
+    if model.model_config["model_name"] == "pcg":
+        model.optim.pc_backward(total)
+    else:
+        total.backward()
     grads = {n: (None if p.grad is None else p.grad.detach().clone()) for n, p in model.named_parameters()}
     model.optim.step()
     return y_pred.detach(), loss.detach(), grads

@@ -67,3 +67,29 @@ def test_world1_sharded_step_is_bit_identical_to_plain_step(case, precision, gat
     for k, v in sa.items():
         assert torch.equal(v, sb[k]), k
     assert int(sharded.plan(160).gather.oob.item()) == 0
+
+
+@pytest.mark.parametrize("R,n", [(1, 1000), (2, 4096), (8, 2397 * 4), (3, 44)])
+def test_peer_allreduce_kernel_simulated_ranks(R, n):
+    """mmlrec_peer_allreduce_f32 with all R "ranks" living on one GPU: rank r reduces slice r of every input buffer in
+    rank order and stores it into slice r of every output buffer, so after the R launches every output equals the
+    rank-ordered sum -- identical on all ranks, bit for bit."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from mmlrec_b200 import lib as L
+    lib = L.load()
+    n = (n + 3) // 4 * 4
+    g = torch.Generator().manual_seed(R * 1000 + n)
+    ins = [torch.randn(n, generator=g).cuda() for _ in range(R)]
+    outs = [torch.full((n,), float("nan"), device="cuda") for _ in range(R)]
+    tin = torch.tensor([t.data_ptr() for t in ins], dtype=torch.int64, device="cuda")
+    tout = torch.tensor([t.data_ptr() for t in outs], dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    for r in range(R):
+        L.check(lib.mmlrec_peer_allreduce_f32(tin.data_ptr(), tout.data_ptr(), n, r, R, st), "peer_allreduce")
+    torch.cuda.synchronize()
+    want = ins[0].clone()
+    for t in ins[1:]:
+        want = want + t          # the kernel's order: ((in0 + in1) + in2) + ...
+    for o in outs:
+        assert torch.equal(o, want)
