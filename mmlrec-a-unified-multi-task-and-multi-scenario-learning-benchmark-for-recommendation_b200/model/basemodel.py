@@ -302,10 +302,39 @@ class BaseModel(nn.Module):
         X = torch.as_tensor(X)
         y = torch.as_tensor(y)
         p = self.plan(X.shape[0])
-        p.X.copy_(X, non_blocking=True)
-        p.y.copy_(y.reshape(X.shape[0], -1), non_blocking=True)
+        if X.device.type == "cpu" and X.is_pinned() and y.device.type == "cpu" and y.is_pinned() \
+                and X.dtype == torch.float32 and y.dtype == torch.float32:
+            self._stage_pinned(p, X, y.reshape(X.shape[0], -1))
+        else:
+            p.X.copy_(X, non_blocking=True)
+            p.y.copy_(y.reshape(X.shape[0], -1), non_blocking=True)
         self._run_train(p)
         return p.loss
+
+    def _stage_pinned(self, p: StepPlan, X: torch.Tensor, y: torch.Tensor) -> None:
+        """Pinned host batch -> the step program's inputs through a two-deep device staging ring: the host-to-device
+        copy runs on a copy stream, i.e. beside the PREVIOUS step when the caller does not synchronise in between
+        (same scheme as fit()'s host-resident path); the main stream only does a device-to-device copy."""
+        ring = getattr(p, "_pin_ring", None)
+        if ring is None:
+            dev = self.device_obj
+            ring = p._pin_ring = {"k": 0, "stream": torch.cuda.Stream(device=dev),
+                                  "buf": [(torch.empty_like(p.X), torch.empty_like(p.y)) for _ in range(2)],
+                                  "copied": [torch.cuda.Event(), torch.cuda.Event()],
+                                  "consumed": [torch.cuda.Event(), torch.cuda.Event()]}
+        k = ring["k"] & 1
+        ring["k"] += 1
+        dx, dy = ring["buf"][k]
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(ring["stream"]):
+            ring["stream"].wait_event(ring["consumed"][k])   # the step that last read this pair has moved it on
+            dx.copy_(X, non_blocking=True)
+            dy.copy_(y, non_blocking=True)
+            ring["copied"][k].record()
+        main.wait_event(ring["copied"][k])
+        p.X.copy_(dx, non_blocking=True)
+        p.y.copy_(dy, non_blocking=True)
+        ring["consumed"][k].record(main)
 
     def check_ids(self) -> None:
         """Raise IndexError if any batch so far carried an id outside its table (the reference's nn.Embedding raises at
