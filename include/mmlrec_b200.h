@@ -316,6 +316,24 @@ int mmlrec_bn_backward(const float* dY, int64_t lddy, const float* Z, int64_t ld
                        const float* gamma, const float* save_mean, const float* save_invstd,
                        float* dZ, int64_t lddz, uint16_t* dZ_bf16, int64_t lddz_bf16,
                        float* dgamma, float* dbeta, void* stream);
+/* Synchronised BatchNorm for the data-parallel step (R ranks of M rows each: the statistics of the GLOBAL batch, which is
+ * what the single-process reference normalises over, model/utils.py:129-134).
+ *   forward : mmlrec_bn_stats (stats[0:N] = mean_r, stats[N:2N] = sum (z - mean_r)^2) -> all-gather to [R][2N] ->
+ *             mmlrec_bn_combine (global mean / invstd into save_*, running statistics, counters) ->
+ *             mmlrec_bn_forward(..., training = 2) (normalise with the given save_mean / save_invstd)
+ *   backward: mmlrec_bn_backward_sums (sums[0:N] = sum dy, sums[N:2N] = sum dy * xhat of this rank; also this rank's
+ *             dgamma / dbeta, which the dense-gradient all-reduce adds up) -> SUM all-reduce of sums ->
+ *             mmlrec_bn_backward_synced (dZ from the global sums, M_total = R * M) */
+int mmlrec_bn_stats(const float* Z, int64_t ldz, int32_t M, int32_t N, float* stats, void* stream);
+int mmlrec_bn_combine(const float* all_stats, int32_t R, int32_t M, int32_t N, float* running_mean, float* running_var,
+                      int64_t* num_batches_tracked, int32_t n_tracked, float* save_mean, float* save_invstd, void* stream);
+int mmlrec_bn_backward_sums(const float* dY, int64_t lddy, const float* Z, int64_t ldz, int32_t M, int32_t N,
+                            const float* save_mean, const float* save_invstd, float* sums, float* dgamma, float* dbeta,
+                            void* stream);
+int mmlrec_bn_backward_synced(const float* dY, int64_t lddy, const float* Z, int64_t ldz, int32_t M, int32_t N,
+                              const float* gamma, const float* save_mean, const float* save_invstd,
+                              float* dZ, int64_t lddz, uint16_t* dZ_bf16, int64_t lddz_bf16,
+                              const float* global_sums, int32_t M_total, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Gate head + softmax + expert mixture (model/mmoe.py:80-88, model/ple.py:127-152):

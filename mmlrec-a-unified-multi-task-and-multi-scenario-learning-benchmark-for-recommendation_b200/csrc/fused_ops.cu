@@ -53,7 +53,10 @@ bn_forward_kernel(const float* Z, int64_t ldz, int M, int N, const float* gamma,
   const bool cv = col < N;
   const float momentum = 0.1f, eps = 1e-5f;
   float mean, invstd;
-  if (training) {
+  if (training == 2) {   // synchronised statistics (bn_combine_kernel wrote them): only normalise
+    mean = cv ? save_mean[col] : 0.f;
+    invstd = cv ? save_invstd[col] : 0.f;
+  } else if (training) {
     float s = 0.f;
     if (cv) for (int r = w; r < M; r += 8) s += Z[r * ldz + col];
     s = bn_block_colsum(s, red);
@@ -86,7 +89,80 @@ bn_forward_kernel(const float* Z, int64_t ldz, int M, int N, const float* gamma,
 __global__ void __launch_bounds__(kBnThreads)
 bn_backward_kernel(const float* dY, int64_t lddy, const float* Z, int64_t ldz, int M, int N, const float* gamma,
                    const float* save_mean, const float* save_invstd, float* dZ, int64_t lddz,
-                   uint16_t* dZb, int64_t lddzb, float* dgamma, float* dbeta) {
+                   uint16_t* dZb, int64_t lddzb, float* dgamma, float* dbeta, const float* ext_sums, int M_total) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  const bool cv = col < N;
+  const float mean = cv ? save_mean[col] : 0.f, invstd = cv ? save_invstd[col] : 0.f;
+  float s1 = 0.f, s2 = 0.f;
+  if (ext_sums != nullptr) {   // synchronised: sums over the GLOBAL batch (all-reduced bn_backward_sums_kernel output)
+    s1 = cv ? ext_sums[col] : 0.f;
+    s2 = cv ? ext_sums[N + col] : 0.f;
+  } else {
+    if (cv) for (int r = w; r < M; r += 8) {
+      float dy = dY[r * lddy + col];
+      s1 += dy;
+      s2 += dy * (Z[r * ldz + col] - mean) * invstd;
+    }
+    s1 = bn_block_colsum(s1, red);
+    s2 = bn_block_colsum(s2, red);
+  }
+  if (!cv) return;
+  if (w == 0 && ext_sums == nullptr) { dgamma[col] = s2; dbeta[col] = s1; }
+  const float g = gamma[col], inv_m = 1.f / (float)M_total;
+  for (int r = w; r < M; r += 8) {
+    float xh = (Z[r * ldz + col] - mean) * invstd;
+    float dz = g * invstd * (dY[r * lddy + col] - s1 * inv_m - xh * s2 * inv_m);
+    if (dZ) dZ[r * lddz + col] = dz;
+    if (dZb) dZb[r * lddzb + col] = float_to_bf16_bits(dz);
+  }
+}
+
+// Synchronised BatchNorm under data parallelism (the global batch is what the single-process reference normalises over).
+// forward : bn_stats_kernel (per rank: mean_r, sum (x - mean_r)^2) -> all-gather -> bn_combine_kernel (Chan's pairwise
+//           formula over equal-sized ranks, running statistics with the global count) -> bn_forward_kernel(training = 2)
+// backward: bn_backward_sums_kernel (per rank: sum dy, sum dy * xhat; also THIS rank's dgamma / dbeta partials, which the
+//           dense-gradient all-reduce adds up) -> all-reduce -> bn_backward_kernel(ext_sums, M_total)
+__global__ void __launch_bounds__(kBnThreads) bn_stats_kernel(const float* Z, int64_t ldz, int M, int N, float* stats) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  const bool cv = col < N;
+  float s = 0.f;
+  if (cv) for (int r = w; r < M; r += 8) s += Z[r * ldz + col];
+  s = bn_block_colsum(s, red);
+  const float mean = s / (float)M;
+  float q = 0.f;
+  if (cv) for (int r = w; r < M; r += 8) { float d = Z[r * ldz + col] - mean; q += d * d; }
+  q = bn_block_colsum(q, red);
+  if (cv && w == 0) { stats[col] = mean; stats[N + col] = q; }
+}
+
+__global__ void bn_combine_kernel(const float* all_stats, int R, int M, int N, float* running_mean, float* running_var,
+                                  int64_t* nbt, int n_tracked, float* save_mean, float* save_invstd) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  const float momentum = 0.1f, eps = 1e-5f;
+  if (blockIdx.x == 0 && nbt && (int)threadIdx.x < n_tracked) nbt[threadIdx.x] += 1;
+  if (col >= N) return;
+  float mean = 0.f;
+  for (int r = 0; r < R; ++r) mean += all_stats[(int64_t)r * 2 * N + col];
+  mean /= (float)R;
+  float m2 = 0.f;
+  for (int r = 0; r < R; ++r) {
+    const float d = all_stats[(int64_t)r * 2 * N + col] - mean;
+    m2 += all_stats[(int64_t)r * 2 * N + N + col] + (float)M * d * d;
+  }
+  const float total = (float)M * (float)R;
+  save_mean[col] = mean;
+  save_invstd[col] = 1.f / sqrtf(m2 / total + eps);
+  running_mean[col] = (1.f - momentum) * running_mean[col] + momentum * mean;
+  running_var[col] = (1.f - momentum) * running_var[col] + momentum * (total > 1.f ? m2 / (total - 1.f) : m2);
+}
+
+__global__ void __launch_bounds__(kBnThreads)
+bn_backward_sums_kernel(const float* dY, int64_t lddy, const float* Z, int64_t ldz, int M, int N, const float* save_mean,
+                        const float* save_invstd, float* sums, float* dgamma, float* dbeta) {
   __shared__ float red[8][33];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
   const int col = blockIdx.x * 32 + lane;
@@ -100,15 +176,7 @@ bn_backward_kernel(const float* dY, int64_t lddy, const float* Z, int64_t ldz, i
   }
   s1 = bn_block_colsum(s1, red);
   s2 = bn_block_colsum(s2, red);
-  if (!cv) return;
-  if (w == 0) { dgamma[col] = s2; dbeta[col] = s1; }
-  const float g = gamma[col], inv_m = 1.f / (float)M;
-  for (int r = w; r < M; r += 8) {
-    float xh = (Z[r * ldz + col] - mean) * invstd;
-    float dz = g * invstd * (dY[r * lddy + col] - s1 * inv_m - xh * s2 * inv_m);
-    if (dZ) dZ[r * lddz + col] = dz;
-    if (dZb) dZb[r * lddzb + col] = float_to_bf16_bits(dz);
-  }
+  if (cv && w == 0) { sums[col] = s1; sums[N + col] = s2; dgamma[col] = s2; dbeta[col] = s1; }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -838,7 +906,42 @@ extern "C" int mmlrec_bn_backward(const float* dY, int64_t lddy, const float* Z,
                                   void* stream) {
   MMLREC_CHECK_ARG(M > 0 && N > 0, "bad sizes");
   bn_backward_kernel<<<cdiv(N, 32), kBnThreads, 0, (cudaStream_t)stream>>>(
-      dY, lddy, Z, ldz, M, N, gamma, save_mean, save_invstd, dZ, lddz, dZ_bf16, lddz_bf16, dgamma, dbeta);
+      dY, lddy, Z, ldz, M, N, gamma, save_mean, save_invstd, dZ, lddz, dZ_bf16, lddz_bf16, dgamma, dbeta, nullptr, M);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_bn_stats(const float* Z, int64_t ldz, int32_t M, int32_t N, float* stats, void* stream) {
+  MMLREC_CHECK_ARG(Z && stats && M > 0 && N > 0, "bad args");
+  bn_stats_kernel<<<cdiv(N, 32), kBnThreads, 0, (cudaStream_t)stream>>>(Z, ldz, M, N, stats);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_bn_combine(const float* all_stats, int32_t R, int32_t M, int32_t N, float* running_mean,
+                                 float* running_var, int64_t* num_batches_tracked, int32_t n_tracked, float* save_mean,
+                                 float* save_invstd, void* stream) {
+  MMLREC_CHECK_ARG(all_stats && R > 0 && M > 0 && N > 0 && running_mean && running_var && save_mean && save_invstd, "bad args");
+  MMLREC_CHECK_ARG(n_tracked <= 256, "too many tracked counters");
+  bn_combine_kernel<<<cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(all_stats, R, M, N, running_mean, running_var,
+                                                                   num_batches_tracked, n_tracked, save_mean, save_invstd);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_bn_backward_sums(const float* dY, int64_t lddy, const float* Z, int64_t ldz, int32_t M, int32_t N,
+                                       const float* save_mean, const float* save_invstd, float* sums, float* dgamma,
+                                       float* dbeta, void* stream) {
+  MMLREC_CHECK_ARG(dY && Z && sums && dgamma && dbeta && M > 0 && N > 0, "bad args");
+  bn_backward_sums_kernel<<<cdiv(N, 32), kBnThreads, 0, (cudaStream_t)stream>>>(dY, lddy, Z, ldz, M, N, save_mean, save_invstd,
+                                                                              sums, dgamma, dbeta);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_bn_backward_synced(const float* dY, int64_t lddy, const float* Z, int64_t ldz, int32_t M, int32_t N,
+                                         const float* gamma, const float* save_mean, const float* save_invstd, float* dZ,
+                                         int64_t lddz, uint16_t* dZ_bf16, int64_t lddz_bf16, const float* global_sums,
+                                         int32_t M_total, void* stream) {
+  MMLREC_CHECK_ARG(M > 0 && N > 0 && global_sums && M_total >= M, "bad args");
+  bn_backward_kernel<<<cdiv(N, 32), kBnThreads, 0, (cudaStream_t)stream>>>(
+      dY, lddy, Z, ldz, M, N, gamma, save_mean, save_invstd, dZ, lddz, dZ_bf16, lddz_bf16, nullptr, nullptr, global_sums, M_total);
   MMLREC_RETURN_LAUNCH(1);
 }
 

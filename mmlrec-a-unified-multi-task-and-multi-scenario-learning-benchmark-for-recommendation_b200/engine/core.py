@@ -627,6 +627,13 @@ class LinearStage(Stage):
         if self.use_bn:
             n_total = _align(yg.total, 4)
             self.save_mean, self.save_invstd = b.zeros(n_total), b.zeros(n_total)
+            # data parallel: BatchNorm statistics of the GLOBAL batch (what the single-process reference normalises over)
+            self.dp = getattr(b, "dp", None)
+            if self.dp is not None and self.dp.world > 1:
+                self.bn_stats = [(b.zeros(1, 2 * g.N), b.zeros(self.dp.world, 2 * g.N)) for g in self.groups]
+                self.bn_sums = [b.zeros(2 * g.N) for g in self.groups]
+            else:
+                self.dp = None
 
     MAX_TC_PROBLEMS = 96  # the tensor-core kernel caches its tile table in shared memory
 
@@ -647,8 +654,19 @@ class LinearStage(Stage):
             self._launch(tbl, stream, "linear fwd")
         if self.use_bn:
             zg, yg = self.zs[0].group, self.outs[0].group
-            for g in self.groups:
+            for gi, g in enumerate(self.groups):
                 bn0, c = g.members[0].bn, g.y_col
+                mode = 1 if training else 0
+                if training and self.dp is not None:
+                    local, every = self.bn_stats[gi]
+                    L.check(b.lib.mmlrec_bn_stats(zg.buf.data_ptr() + 4 * c, zg.buf.stride(0), b.B, g.N, local.data_ptr(),
+                                                  stream), f"bn stats {self.label}")
+                    self.dp.gather_rows(local, every)
+                    L.check(b.lib.mmlrec_bn_combine(every.data_ptr(), self.dp.world, b.B, g.N, bn0.running_mean.data_ptr(),
+                                                    bn0.running_var.data_ptr(), bn0.num_batches_tracked.data_ptr(),
+                                                    len(g.members), self.save_mean.data_ptr() + 4 * c,
+                                                    self.save_invstd.data_ptr() + 4 * c, stream), f"bn combine {self.label}")
+                    mode = 2
                 L.check(b.lib.mmlrec_bn_forward(
                     zg.buf.data_ptr() + 4 * c, zg.buf.stride(0), b.B, g.N, bn0.weight.data_ptr(), bn0.bias.data_ptr(),
                     bn0.running_mean.data_ptr(), bn0.running_var.data_ptr(), bn0.num_batches_tracked.data_ptr(),
@@ -657,7 +675,7 @@ class LinearStage(Stage):
                     yg.buf.stride(0) if yg.buf is not None else 0,
                     (yg.buf16.data_ptr() + 2 * c) if yg.buf16 is not None else None,
                     yg.buf16.stride(0) if yg.buf16 is not None else 0,
-                    L.ACT_CODES[self.act], 1 if training else 0, stream), f"bn fwd {self.label}")
+                    L.ACT_CODES[self.act], mode, stream), f"bn fwd {self.label}")
 
     # ---- backward
     def plan_backward(self):
@@ -807,6 +825,23 @@ class LinearStage(Stage):
             zg, yg = self.zs[0].group, self.outs[0].group
             for g in self.live_groups:
                 bn0, c = g.members[0].bn, g.y_col
+                if self.dp is not None:
+                    sums = self.bn_sums[self.groups.index(g)]
+                    dz32 = ((zg.gbuf.data_ptr() + 4 * c) if zg.gbuf is not None else None,
+                            zg.gbuf.stride(0) if zg.gbuf is not None else 0)
+                    dz16 = ((zg.gbuf16.data_ptr() + 2 * c) if zg.gbuf16 is not None else None,
+                            zg.gbuf16.stride(0) if zg.gbuf16 is not None else 0)
+                    L.check(b.lib.mmlrec_bn_backward_sums(
+                        yg.gbuf.data_ptr() + 4 * c, yg.gbuf.stride(0), zg.buf.data_ptr() + 4 * c, zg.buf.stride(0), b.B, g.N,
+                        self.save_mean.data_ptr() + 4 * c, self.save_invstd.data_ptr() + 4 * c, sums.data_ptr(),
+                        b.store.grad_ptr(bn0.weight), b.store.grad_ptr(bn0.bias), stream), f"bn bwd sums {self.label}")
+                    self.dp.sum_gradients(sums)
+                    L.check(b.lib.mmlrec_bn_backward_synced(
+                        yg.gbuf.data_ptr() + 4 * c, yg.gbuf.stride(0), zg.buf.data_ptr() + 4 * c, zg.buf.stride(0), b.B, g.N,
+                        bn0.weight.data_ptr(), self.save_mean.data_ptr() + 4 * c, self.save_invstd.data_ptr() + 4 * c,
+                        dz32[0], dz32[1], dz16[0], dz16[1], sums.data_ptr(), b.B * self.dp.world, stream),
+                        f"bn bwd {self.label}")
+                    continue
                 L.check(b.lib.mmlrec_bn_backward(
                     yg.gbuf.data_ptr() + 4 * c, yg.gbuf.stride(0), zg.buf.data_ptr() + 4 * c, zg.buf.stride(0), b.B, g.N,
                     bn0.weight.data_ptr(), self.save_mean.data_ptr() + 4 * c, self.save_invstd.data_ptr() + 4 * c,
@@ -1333,6 +1368,7 @@ class StepPlan:
     def __init__(self, model, B: int):
         self.model, self.B = model, B
         self.b = Builder(B, model.device_obj, model.store, dry=False, precision=model.precision)
+        self.b.dp = getattr(model, "dp", None)
         model.build_graph(self.b)
         self.b.materialize()
         self.stages = self.b.stages

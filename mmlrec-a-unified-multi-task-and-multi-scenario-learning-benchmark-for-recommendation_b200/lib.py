@@ -130,6 +130,10 @@ _SIGNATURES = {
     "mmlrec_tc_num_tiles": (i32, [i32, i32]),
     "mmlrec_bn_forward": (C.c_int, [vp, i64, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, i64, vp, i64, i32, i32, vp]),
     "mmlrec_bn_backward": (C.c_int, [vp, i64, vp, i64, i32, i32, vp, vp, vp, vp, i64, vp, i64, vp, vp, vp]),
+    "mmlrec_bn_stats": (C.c_int, [vp, i64, i32, i32, vp, vp]),
+    "mmlrec_bn_combine": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp]),
+    "mmlrec_bn_backward_sums": (C.c_int, [vp, i64, vp, i64, i32, i32, vp, vp, vp, vp, vp, vp]),
+    "mmlrec_bn_backward_synced": (C.c_int, [vp, i64, vp, i64, i32, i32, vp, vp, vp, vp, i64, vp, i64, vp, i32, vp]),
     "mmlrec_gate_mix_forward": (C.c_int, [vp, i32, i32, vp]),
     "mmlrec_gate_mix_backward": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, vp, vp, vp]),
     "mmlrec_gate_mix_backward_scratch": (i64, [i32, i32, i32, i32]),

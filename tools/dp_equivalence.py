@@ -12,7 +12,11 @@ rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
 ok = True
-CASES = (("mmoe_synth26_adagrad", False), ("ple_ae_t4_adam", True), ("esmm_kuairec_adam", True))
+# the census case has BatchNorm: the ranks must normalise over the GLOBAL batch (synchronised statistics) to match
+CASES = (("mmoe_synth26_adagrad", False), ("ple_ae_t4_adam", True), ("esmm_kuairec_adam", True),
+         ("mmoe_census_bn_adam", True), ("mmoe_census_bn_adagrad", False))
+if os.environ.get("DP_CASES"):
+    CASES = tuple(c for c in CASES if c[0] in os.environ["DP_CASES"].split(","))
 STEPS = int(os.environ.get("DP_STEPS", 1))
 # one step is a rounding-level check; over several steps Adagrad / Adam amplify 1-ulp gradient differences on
 # near-zero gradients (measured drift after 3 steps: 1e-4 .. 3e-3)
@@ -42,8 +46,14 @@ for case, graph in CASES:
     if rank == 0:
         worst, rows = 0.0, []
         sd_dp, sd_1 = model.state_dict(), single.state_dict()
+        use_bn = cfg["model_config"].get("dnn_use_bn", False)
         for k, v in sd_1.items():
             if v.dtype != torch.float32:
+                continue
+            if use_bn and ((".linears." in k and k.endswith(".bias")) or k.endswith("running_mean")):
+                # a Linear bias feeding BatchNorm has an exactly-zero true gradient: what reaches the optimizer is rounding
+                # noise, which Adam / Adagrad normalise to +-lr steps (tests/test_step_gpu.py treats these the same way);
+                # running_mean tracks that bias.  The gradient vector itself is compared below.
                 continue
             ref_scale = float(v.abs().max()) + 1e-12
             d = float((sd_dp[k] - v).abs().max()) / ref_scale
@@ -52,9 +62,11 @@ for case, graph in CASES:
         for d, k in sorted(rows, reverse=True)[:4]:
             print(f"      {k:50s} {d:.3e}", flush=True)
         g_dp, g_1 = model.store.dense_grad, single.store.dense_grad
-        print(f"      last-step dense grad rel diff {float((g_dp - g_1).norm() / g_1.norm()):.3e}", flush=True)
+        gdiff = float((g_dp - g_1).norm() / g_1.norm())
+        print(f"      last-step dense grad rel diff {gdiff:.3e}", flush=True)
+        ok &= gdiff < 1e-5
         print(f"{case} graph={graph}: max rel param diff DP({world}x{b}) vs single({world * b}) = {worst:.3e}", flush=True)
-        ok &= worst < TOL
+        ok &= worst < (TOL if "_bn_" not in case else 50 * TOL)   # (BatchNorm: the batch variance is combined from per-rank parts)
     # replicas must stay bit-identical
     chk = model.store.emb.double().sum() + model.store.dense.double().sum()
     allc = [torch.zeros_like(chk) for _ in range(world)]
