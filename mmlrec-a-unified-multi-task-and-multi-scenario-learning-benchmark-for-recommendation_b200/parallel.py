@@ -3,12 +3,14 @@
 The reference has no functional multi-GPU path, so the contract is: R ranks with per-rank batch
 b produce exactly the single-process step at the global batch R*b drawn in rank-major order.
 
-  * dense parameters: local forward/backward, then ONE ``all_reduce(SUM)`` over the flat ``dense_grad`` bucket
-    (SUM, not mean: the loss is ``reduction='sum'``, basemodel.py:294-296);
+  * dense parameters: local forward/backward, then a SUM all-reduce of the flat dense gradient (SUM, not mean: the loss
+    is ``reduction='sum'``, basemodel.py:294-296) -- with row-sharded tables a reduce-scatter + all-gather kernel over
+    NVLink peer memory (csrc/peer.cu), otherwise NCCL on stage-boundary buckets overlapped with the backward pass;
   * embedding tables (replicated): the id columns are all-gathered at the start of the step so every rank
     sorts the GLOBAL batch; after the local backward the ``d(dnn_input)`` rows are all-gathered and every rank
     runs the same K2 segmented reduce + fused row update (+ dense-Adam sweep) -> tables stay bit-identical;
-  * BatchNorm statistics are per rank (no Sync-BN yet; only the census shape uses BatchNorm).
+  * BatchNorm normalises over the GLOBAL batch (synchronised statistics: per-rank moments are all-gathered and
+    combined, the backward sums all-reduced; engine/core.py LinearStage, csrc/fused_ops.cu bn_stats / bn_combine).
 
 All collectives are issued on the step's stream through ``torch.distributed`` so they are captured in the
 step's CUDA graph.
