@@ -500,6 +500,13 @@ int mmlrec_star_fold(const float* d_w_eff, int64_t ld_w, const float* d_b_eff, c
                      float* d_shared_b, float* d_spec_last, float* d_spec_b_last, void* stream);
 
 /* small utilities */
+/* L2 regularisation of the dense parameters (model/basemodel.py:524-540 get_regularization_loss, added to the loss at
+ * :303): grad[i] += 2 * l2_coef[i] * param[i]; *reg_out = sum l2_coef[i] * param[i]^2 (deterministic).  l2_coef is 0
+ * wherever a parameter is not registered; a NEGATIVE coefficient means "no kernel writes this gradient entry": the
+ * entry is assigned 2 * |coef| * param instead of accumulated.  scratch: mmlrec_l2_scratch() floats. */
+int mmlrec_l2_regularize(const float* param, float* grad, const float* l2_coef, int64_t n, float* reg_out, float* scratch,
+                         void* stream);
+int64_t mmlrec_l2_scratch(void);
 /* Deterministic split-K for the batch-contraction wgrad GEMMs: the S partial problems write their tiles into S
  * scratch slices; this sums the slices in a fixed order into the gradient buffer.
  * segments: int64 [n_segments][3] = {dst element offset, src element offset inside a slice, element count}. */

@@ -1093,6 +1093,55 @@ extern "C" int mmlrec_sum_slices(const int64_t* segments, int32_t n_segments, in
   MMLREC_RETURN_LAUNCH(1);
 }
 
+namespace mmlrec {
+// L2 regularisation of the dense parameters (model/basemodel.py:524-540: reg = sum l2 * w^2 over the registered weights,
+// added to the loss before backward): grad += 2 * coef * p, and the value of the term.  coef holds the per-element l2
+// (0 for biases / BatchNorm / anything not registered; NEGATIVE where the gradient entry is written by nobody else and
+// must be assigned instead of accumulated); CTA partials of the value are added by the finish kernel in
+// block order (deterministic).
+__global__ void __launch_bounds__(256) l2_grad_kernel(const float* __restrict__ p, float* g, const float* __restrict__ coef,
+                                                      int64_t n, float* partial) {
+  __shared__ float red[8];
+  float acc = 0.f;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float c = coef[i];
+    if (c != 0.f) {   // c < 0: no backward kernel ever writes this entry (an unused expert): ASSIGN, the buffer holds stale data
+      const float w = p[i], a = fabsf(c);
+      g[i] = (c > 0.f ? g[i] : 0.f) + 2.f * a * w;
+      acc = fmaf(a * w, w, acc);
+    }
+  }
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += red[k];
+    partial[blockIdx.x] = t;
+  }
+}
+__global__ void l2_finish_kernel(const float* partial, int n_part, float* reg_out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float t = 0.f;
+  for (int k = 0; k < n_part; ++k) t += partial[k];
+  *reg_out = t;
+}
+}  // namespace mmlrec
+
+extern "C" int64_t mmlrec_l2_scratch(void) { return 1024; }
+
+extern "C" int mmlrec_l2_regularize(const float* param, float* grad, const float* l2_coef, int64_t n, float* reg_out,
+                                    float* scratch, void* stream) {
+  MMLREC_CHECK_ARG(param && grad && l2_coef && reg_out && scratch && n > 0, "bad args");
+  int grid = grid_for(n);
+  if (grid > 1024) grid = 1024;
+  mmlrec::l2_grad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(param, grad, l2_coef, n, scratch);
+  MMLREC_CHECK_LAUNCH(1);
+  mmlrec::l2_finish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(scratch, grid, reg_out);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
 extern "C" int mmlrec_fill_f32(float* p, int64_t n, float v, void* stream) {
   if (n <= 0) return 0;
   launch_pdl(fill_kernel, dim3(grid_for(n)), dim3(256), 0, stream, p, n, v);

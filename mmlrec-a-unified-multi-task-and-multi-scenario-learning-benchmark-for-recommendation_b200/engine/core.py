@@ -1380,6 +1380,8 @@ class StepPlan:
         self.grad_slices = max([getattr(s, "split_k", 1) for s in self.stages] + [1])
         self.fold_seg = self.b.ints([0, 0, model.store.slice_stride], dtype=torch.int64)
         self._plan_buckets()
+        self.reg_loss = self.b.zeros(1)     # value of the L2 term of the last step (0 without regularisation)
+        self.l2_scratch = self.b.zeros(int(self.b.lib.mmlrec_l2_scratch())) if model.store.l2_coef is not None else None
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.side = torch.cuda.Stream(device=model.device_obj)
         self.ev_fork, self.ev_join = torch.cuda.Event(), torch.cuda.Event()
@@ -1498,6 +1500,11 @@ class StepPlan:
             self.side.wait_event(self.ev_fork)
             self.gather.sort(self.side.cuda_stream)
             self.ev_join.record(self.side)
+        probe_l2 = m.store.l2_coef is not None and not m.store.l2_probed and not torch.cuda.is_current_stream_capturing()
+        if probe_l2:
+            # first (eager) step with L2 regularisation: find the gradient entries that NO backward kernel writes (PLE's
+            # allocated-but-unused shared experts, a dead gate): the reg kernel must assign those, not accumulate
+            m.store.dense_grad[:m.store.n_dense].fill_(float("nan"))
         for s in self.stages:
             s.forward(stream, True)
             if s is self.gather and sh is not None and self.gather.F_s:
@@ -1513,8 +1520,18 @@ class StepPlan:
                     self._reduce_bucket(self.bucket_after[id(s)], main)
         st = m.store
         p = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
+        if probe_l2:
+            g = st.dense_grad[:st.n_dense]
+            unwritten = torch.isnan(g)
+            g[unwritten] = 0.0
+            st.l2_coef[unwritten] = -st.l2_coef[unwritten].abs()
+            st.l2_probed = True
 
         def dense_step(n_slices, grad_ptr=None):
+            if st.l2_coef is not None:   # reg gradient into the buffer the optimizer reads (slice 0), reg value beside the loss
+                L.check(lib.mmlrec_l2_regularize(st.dense.data_ptr(), grad_ptr or st.dense_grad.data_ptr(),
+                                                 st.l2_coef.data_ptr(), st.n_dense, self.reg_loss.data_ptr(),
+                                                 self.l2_scratch.data_ptr(), stream), "l2 regularisation")
             L.check(lib.mmlrec_dense_optimizer_step_sliced(
                 st.dense.data_ptr(), grad_ptr or st.dense_grad.data_ptr(), p(st.dense_s1), p(st.dense_s2), st.n_dense,
                 m.hyper_dev.data_ptr(), p(st.dense_bf16), n_slices, st.slice_stride, stream), "dense_optimizer_step")

@@ -70,6 +70,8 @@ class FlatStore:
         self.grad_slices = torch.zeros(self.max_grad_slices, self.slice_stride, dtype=torch.float32, device=device)
         self.dense_grad = self.grad_slices[0]
         self.live_slices = 1          # slices the last executed step program wrote (engine/core.py StepPlan)
+        self.l2_coef = None           # per-element l2 of the registered weights (set_l2), None while nothing is regularised
+        self.l2_probed = False        # the sign of l2_coef marks entries no backward kernel writes (StepPlan.train_step)
         self.dense_s1: Optional[torch.Tensor] = None
         self.dense_s2: Optional[torch.Tensor] = None
         self.dense_bf16 = (torch.zeros(self.n_dense + self.aux_floats, dtype=torch.bfloat16, device=device)
@@ -200,6 +202,13 @@ class FlatStore:
         """True when ``b`` starts exactly where ``a`` ends (so [a;b] is one matrix)."""
         return (a._mm_kind == b._mm_kind == "dense" and a._mm_off + a._mm_span == b._mm_off
                 and a._mm_ld == b._mm_ld)
+
+    def set_l2(self, p: nn.Parameter, l2: float) -> None:
+        """Register dense parameter `p` for L2 regularisation (coefficients add up when it is registered twice, as the
+        reference's list of weight lists would count it twice)."""
+        if self.l2_coef is None:
+            self.l2_coef = torch.zeros(self.n_dense, dtype=torch.float32, device=self.device)
+        self.l2_coef[p._mm_off:p._mm_off + p._mm_span] += float(l2)
 
     def refresh_bf16(self) -> None:
         if self.dense_bf16 is not None:

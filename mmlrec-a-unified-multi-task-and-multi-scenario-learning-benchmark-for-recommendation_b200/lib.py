@@ -130,6 +130,8 @@ _SIGNATURES = {
     "mmlrec_tc_num_tiles": (i32, [i32, i32]),
     "mmlrec_bn_forward": (C.c_int, [vp, i64, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, i64, vp, i64, i32, i32, vp]),
     "mmlrec_bn_backward": (C.c_int, [vp, i64, vp, i64, i32, i32, vp, vp, vp, vp, i64, vp, i64, vp, vp, vp]),
+    "mmlrec_l2_regularize": (C.c_int, [vp, vp, vp, i64, vp, vp, vp]),
+    "mmlrec_l2_scratch": (i64, []),
     "mmlrec_bn_stats": (C.c_int, [vp, i64, i32, i32, vp, vp]),
     "mmlrec_bn_combine": (C.c_int, [vp, i32, i32, i32, vp, vp, vp, i32, vp, vp, vp]),
     "mmlrec_bn_backward_sums": (C.c_int, [vp, i64, vp, i64, i32, i32, vp, vp, vp, vp, vp, vp]),

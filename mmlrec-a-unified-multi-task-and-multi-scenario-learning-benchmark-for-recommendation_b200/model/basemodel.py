@@ -115,11 +115,15 @@ class BaseModel(nn.Module):
         for task_type in self.task_types:
             if task_type not in ["binary", "regression"]:
                 raise ValueError("task must be binary or regression, {} is illegal".format(task_type))
-        for key in ("l2_reg_linear", "l2_reg_embedding", "l2_reg_dnn"):
-            # the reference defaults l2_reg_linear/embedding to 1e-5 when the key is absent; every
-            # shipped config sets all three to 0 and the fused step implements only that case
-            if self.model_config.get(key, 0) not in (0, 0.0):
-                raise NotImplementedError(f"{key} > 0 is not implemented in the fused step")
+        # L2 regularisation (basemodel.py:115-130, :514-540).  l2_reg_dnn is fused into the step (the model classes
+        # register the same weight lists as the reference's); l2_reg_linear has nothing to act on (no linear columns);
+        # l2_reg_embedding > 0 would put a dense gradient on every table row every step and is not implemented.  An
+        # absent key counts as 0 here (the reference defaults the linear / embedding terms to 1e-5; every shipped
+        # config sets all three to 0).
+        if self.model_config.get("l2_reg_embedding", 0) not in (0, 0.0):
+            raise NotImplementedError("l2_reg_embedding > 0 is not implemented in the fused step")
+        self.regularization_weight = []
+        self._regularized_modules = []
 
         self.feature_index = build_input_features(list(linear_feature_columns) + list(dnn_feature_columns))
         # row-sharded tables (BASELINE config 5): this process holds rows rank::world of every table
@@ -193,6 +197,38 @@ class BaseModel(nn.Module):
         self.input_dim_total = len(sparse) * self.emb_dim + len(self.dense_x_cols)
         self.num_x_cols = max(e for _, e in self.feature_index.values())
 
+    # ------------------------------------------------------------------ regularisation
+    def add_regularization_weight(self, weight_list, l1=0.0, l2=0.0):
+        """basemodel.py:514-523: a parameter, or an iterable of parameters / (name, parameter) pairs."""
+        weight_list = [weight_list] if isinstance(weight_list, nn.Parameter) else list(weight_list)
+        if l1:
+            raise NotImplementedError("l1 regularisation is not fused (the reference never passes l1 > 0)")
+        self.regularization_weight.append((weight_list, l1, l2))
+
+    def regularize(self, modules, l2) -> None:
+        """The reference's idiom (e.g. mmoe.py:60-63): every '*weight*' that is not a BatchNorm weight of each module.
+        The MODULES are remembered, not the tensors: _finalize re-creates the parameters as views of the flat store."""
+        self._regularized_modules.extend((m, l2) for m in modules)
+
+    def _regularized(self):
+        """(parameter, l2) pairs in registration order (a parameter registered twice appears twice)."""
+        for m, l2 in self._regularized_modules:
+            for name, prm in m.named_parameters():
+                if "weight" in name and "bn" not in name:
+                    yield prm, l2
+        for weight_list, _, l2 in self.regularization_weight:
+            for w in weight_list:
+                yield (w[1] if isinstance(w, tuple) else w), l2
+
+    def get_regularization_loss(self) -> torch.Tensor:
+        """basemodel.py:524-540, as torch ops on the parameters (the differentiable-forward / external-optimizer path;
+        the fused step computes the same value and its gradient in mmlrec_l2_regularize)."""
+        total = torch.zeros((1,), device=self.device_obj)
+        for prm, l2 in self._regularized():
+            if l2 > 0:
+                total = total + torch.sum(l2 * torch.square(prm))
+        return total
+
     # ------------------------------------------------------------------ program construction
     def build_graph(self, b: Builder) -> None:  # pragma: no cover - abstract
         raise NotImplementedError
@@ -210,6 +246,11 @@ class BaseModel(nn.Module):
                                ordered_buffers=dry.buffer_order, aux_floats=dry.aux_floats + 64,
                                emb_alloc=self.shard.alloc_emb if self.shard else None)
         self._index_features()  # re-read the re-pointed table parameters
+        for prm, l2 in self._regularized():
+            if l2:
+                if getattr(prm, "_mm_kind", "") != "dense":
+                    raise NotImplementedError("L2 regularisation of an embedding table is not implemented in the fused step")
+                self.store.set_l2(prm, l2)
         if self.shard is not None and self.shard.gather_mode == "auto":
             limit = int(self.b200_config.get("peer_read_max_shard_bytes", 64 << 20))
             self.shard.gather_mode = "peer_read" if 4 * self.store.n_emb <= limit else "owner_serve"
@@ -509,7 +550,8 @@ class BaseModel(nn.Module):
                 self._run_train(p)
                 preds.append(p.pred.clone())
                 ys.append(p.y.clone())
-                losses.append(p.loss[self.num_tasks].clone())
+                # (the epoch log is the TOTAL loss: task losses + the L2 term, basemodel.py:303-308, :333)
+                losses.append(p.loss[self.num_tasks] + p.reg_loss[0])
                 idxs.append(idx)
             total = float(torch.stack(losses).sum().item())
             self.check_ids()

@@ -51,6 +51,8 @@ class CrossStitch(BaseModel):
             tower_in = self.tower_dnn_hidden_units[-1]
         self.tower_dnn_final_layer = nn.ModuleList(nn.Linear(tower_in, 1, bias=False) for _ in range(T))
         self.out = nn.ModuleList(PredictionLayer(task) for task in self.task_types)
+        if len(self.tower_dnn_hidden_units) > 0:
+            self.regularize([self.tower_dnn], mc.get("l2_reg_dnn", 0))   # cross_stitch.py:70-72 (only the towers are registered)
         self._finalize()
 
     def build_graph(self, b: Builder) -> None:

@@ -26,6 +26,9 @@ class ESMM(BaseModel):
         self.cvr_dnn = DNN(self.input_dim, self.expert_dnn_hidden_units, **kw)
         self.ctr_dnn_final_layer = nn.Linear(self.expert_dnn_hidden_units[-1], 1, bias=False)
         self.cvr_dnn_final_layer = nn.Linear(self.expert_dnn_hidden_units[-1], 1, bias=False)
+        # esmm.py:38-43
+        self.regularize([self.ctr_dnn, self.cvr_dnn, self.ctr_dnn_final_layer, self.cvr_dnn_final_layer],
+                        mc.get("l2_reg_dnn", 0))
         self._finalize()
 
     def build_graph(self, b: Builder) -> None:

@@ -43,6 +43,12 @@ class HMOE(BaseModel):
         self.task_weight_final_layer = nn.ModuleList(nn.Linear(tw_in, T, bias=False) for _ in range(T))
         self.tower_dnn_final_layer = nn.ModuleList(nn.Linear(tower_in, 1, bias=False) for _ in range(T))
         self.out = nn.ModuleList(PredictionLayer(task) for task in self.task_types)
+        # hmoe.py:39-41, :51-53, :61-63, :75-80
+        self.regularize(([self.gate_dnn] if len(self.gate_dnn_hidden_units) > 0 else [])
+                        + ([self.tower_dnn] if len(self.tower_dnn_hidden_units) > 0 else [])
+                        + ([self.task_weight] if len(self.task_weight_hidden_units) > 0 else [])
+                        + [self.expert_dnn, self.gate_dnn_final_layer, self.task_weight_final_layer,
+                           self.tower_dnn_final_layer], mc.get("l2_reg_dnn", 0))
         self._finalize()
 
     def build_graph(self, b: Builder) -> None:

@@ -26,6 +26,7 @@ class MLP(BaseModel):
             # the in-place bias add of the PredictionLayers aliases ONE logit tensor (see HeadStage.cumulative_bias); with
             # a regression task the reference's own outputs alias each other -- not reproduced
             raise NotImplementedError("MLP supports binary tasks only")
+        self.regularize([self.mlp_layers], mc.get("l2_reg_dnn", 0))   # mlp.py:31-33
         self._finalize()
 
     def build_graph(self, b: Builder) -> None:

@@ -37,6 +37,10 @@ class MMOE(BaseModel):
             tower_in = self.tower_dnn_hidden_units[-1]
         self.tower_dnn_final_layer = nn.ModuleList(nn.Linear(tower_in, 1, bias=False) for _ in range(T))
         self.out = nn.ModuleList(PredictionLayer(task) for task in self.task_types)
+        # mmoe.py:36-38, :49-51, :60-63
+        self.regularize(([self.gate_dnn] if len(self.gate_dnn_hidden_units) > 0 else [])
+                        + ([self.tower_dnn] if len(self.tower_dnn_hidden_units) > 0 else [])
+                        + [self.expert_dnn, self.gate_dnn_final_layer, self.tower_dnn_final_layer], mc.get("l2_reg_dnn", 0))
         self._finalize()
 
     def build_graph(self, b: Builder) -> None:

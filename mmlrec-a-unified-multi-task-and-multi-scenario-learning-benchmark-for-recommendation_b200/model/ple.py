@@ -64,6 +64,11 @@ class PLE(BaseModel):
             tower_in = self.tower_dnn_hidden_units[-1]
         self.tower_dnn_final_layer = nn.ModuleList(nn.Linear(tower_in, 1, bias=False) for _ in range(T))
         self.out = nn.ModuleList(PredictionLayer(task) for task in self.task_types)
+        # ple.py:57-59, :74-76, :89-91, :99-103 (the unused shared experts are registered too: under L2 they do move)
+        self.regularize(([self.specific_gate_dnn, self.shared_gate_dnn] if has_gate_dnn else [])
+                        + ([self.tower_dnn] if len(self.tower_dnn_hidden_units) > 0 else [])
+                        + [self.specific_experts, self.shared_experts, self.specific_gate_dnn_final_layer,
+                           self.shared_gate_dnn_final_layer, self.tower_dnn_final_layer], mc.get("l2_reg_dnn", 0))
         self._finalize()
 
     def build_graph(self, b: Builder) -> None:

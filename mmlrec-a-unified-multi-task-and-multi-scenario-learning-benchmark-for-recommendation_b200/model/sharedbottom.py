@@ -27,6 +27,9 @@ class SharedBottom(BaseModel):
             tower_in = self.tower_dnn_hidden_units[-1]
         self.tower_dnn_final_layer = nn.ModuleList(nn.Linear(tower_in, 1, bias=False) for _ in range(T))
         self.out = nn.ModuleList(PredictionLayer(task) for task in self.task_types)
+        # sharedbottom.py:36-38, :45-49
+        self.regularize(([self.tower_dnn] if len(self.tower_dnn_hidden_units) > 0 else [])
+                        + [self.bottom_dnn, self.tower_dnn_final_layer], mc.get("l2_reg_dnn", 0))
         self._finalize()
 
     def build_graph(self, b: Builder) -> None:

@@ -383,6 +383,40 @@ FORWARDS = {
 
 
 # --------------------------------------------------------------------------------------
+# L2 regularisation (basemodel.py:514-540; the per-model registrations, e.g. mmoe.py:36-38, :49-51, :60-63)
+# --------------------------------------------------------------------------------------
+# module prefixes each model registers with l2_reg_dnn, in registration order (a module listed twice counts twice)
+REG_MODULES = {
+    "mmoe": ["gate_dnn", "tower_dnn", "expert_dnn", "gate_dnn_final_layer", "tower_dnn_final_layer"],
+    "ple": ["specific_gate_dnn", "shared_gate_dnn", "tower_dnn", "specific_experts", "shared_experts",
+            "specific_gate_dnn_final_layer", "shared_gate_dnn_final_layer", "tower_dnn_final_layer"],
+    "sharedbottom": ["tower_dnn", "bottom_dnn", "tower_dnn_final_layer"],
+    "esmm": ["ctr_dnn", "cvr_dnn", "ctr_dnn_final_layer", "cvr_dnn_final_layer"],
+    "hmoe": ["gate_dnn", "tower_dnn", "task_weight", "expert_dnn", "gate_dnn_final_layer", "task_weight_final_layer",
+             "tower_dnn_final_layer"],
+    "mlp": ["mlp_layers"],
+    "cross_stitch": ["tower_dnn"],
+    "star": [], "pepnet": [],
+}
+REG_MODULES["pcg"] = REG_MODULES["mmoe"]
+
+
+def regularization_loss(params: Params, model: str, l2: float) -> Tensor:
+    """sum over the registered modules of l2 * sum(w^2) for every parameter whose name inside the module contains
+    'weight' and not 'bn' (the reference's filter)."""
+    total = torch.zeros((1,))
+    if not l2:
+        return total
+    for mod in REG_MODULES[model]:
+        for k, v in params.items():
+            if k.startswith(mod + "."):
+                local = k[len(mod) + 1:]
+                if "weight" in local and "bn" not in local:
+                    total = total + torch.sum(l2 * torch.square(v))
+    return total
+
+
+# --------------------------------------------------------------------------------------
 # the step body (basemodel.py:262-313)
 # --------------------------------------------------------------------------------------
 class OracleTrainer:
@@ -401,6 +435,8 @@ class OracleTrainer:
         self.trainable = keys
         self.buffers = {k: v.detach().clone() for k, v in (buffers or {}).items()}
         oc = config["optim_config"]
+        self.l2_dnn = config["model_config"].get("l2_reg_dnn", 0)
+        self.last_reg = 0.0
         lr, name = oc.get("lr", 1e-3), oc.get("optimizer", "adagrad")
         loss = oc.get("loss", "binary_crossentropy")
         self.loss_names = [loss] * self.spec.num_tasks if isinstance(loss, str) else list(loss)
@@ -423,7 +459,9 @@ class OracleTrainer:
         pred = self.forward(X, training=True)
         self.optim.zero_grad()
         loss = loss_sum(pred, y.float(), self.loss_names)
-        loss.backward()
+        reg = regularization_loss(self.params, self.spec.model, self.l2_dnn).to(loss.device)
+        self.last_reg = float(reg.detach())
+        (loss + reg).backward()   # basemodel.py:303 total_loss = loss + reg_loss (+ aux / cka terms that are zero)
         grads = {k: (None if self.params[k].grad is None else self.params[k].grad.detach().clone())
                  for k in self.trainable}
         return pred.detach(), loss.detach(), grads

@@ -78,10 +78,17 @@ CASES = {
     # 'pcg' = MMOE whose optimizer is wrapped in PCGrad (main.py:53-54, basemodel.py:564-565); the step goes through
     # optim.pc_backward(total_loss) (basemodel.py:309-310) -- one objective, so no projection ever happens
     "pcg_kuairec_adam": ("kuairec_sharedbottom", dict(max_vocab=200), dict(SMALL, model_name="pcg"), {}),
+    # l2_reg_dnn > 0 (basemodel.py:514-540): reg gradient 2*l2*w on the weights each model registers, also on PLE's
+    # allocated-but-unused shared experts
+    "mmoe_kuairec_l2_adam": ("kuairec_sharedbottom", dict(max_vocab=200), dict(SMALL, model_name="mmoe", l2_reg_dnn=1e-2), {}),
+    "ple_ae_t2_l2_sgd": ("ae_ple_t2", dict(max_vocab=300), dict(SMALL, l2_reg_dnn=1e-2), dict(optimizer="sgd", lr=1e-2)),
+    "esmm_kuairec_l2_adagrad": ("kuairec_esmm", dict(max_vocab=200), dict(SMALL, l2_reg_dnn=1e-2),
+                                dict(optimizer="adagrad", lr=1e-2)),
 }
 # cases whose identity / 1e-4 initial state would leave parts of the model untested: perturbed after construction
 INIT_STD.update({"cross_stitch_kuairec_adam": 0.05, "hmoe_kuairec_adam": 0.05, "mlp_kuairec_adam": 0.05,
-                 "pcg_kuairec_adam": 0.05})
+                 "pcg_kuairec_adam": 0.05, "mmoe_kuairec_l2_adam": 0.05, "ple_ae_t2_l2_sgd": 0.05,
+                 "esmm_kuairec_l2_adagrad": 0.05})
 
 
 def post_build(case, model):
