@@ -1,6 +1,7 @@
 // PTX wrappers shared by the tcgen05 grouped-GEMM kernels (gemm_tc.cu: one CTA per tile; gemm_tc2.cu: CTA pairs).
 #pragma once
 #include <cuda.h>
+#include <cstdlib>
 
 #include "common.cuh"
 
@@ -187,9 +188,16 @@ static inline int tc_encode_map(CUtensorMap* tm, CUtensorMapDataType dt, int ele
   cuuint64_t strides[1] = {(cuuint64_t)ld * (cuuint64_t)elem_bytes};
   cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_outer};
   cuuint32_t estr[2] = {1, 1};
+  static int promo = -1;   // MMLREC_TMA_L2_PROMOTION = 0 (none) / 64 / 128 / 256 (default): A/B switch for the profiles
+  if (promo < 0) {
+    const char* e = getenv("MMLREC_TMA_L2_PROMOTION");
+    promo = e ? atoi(e) : 256;
+  }
+  const CUtensorMapL2promotion l2p = promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                     : promo == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                     : promo == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   CUresult r = fn(tm, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, l2p, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r); return -3; }
   return 0;
 }
