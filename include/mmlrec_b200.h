@@ -437,7 +437,8 @@ int64_t mmlrec_gate_level_backward_tiled_smem(int32_t n_gates, int32_t n_experts
 typedef struct MmlrecHead {
   const float* h; int64_t ld_h; int32_t H; int32_t kind;     /* tower output [B,H]; MMLREC_HEAD_* */
   const float* w; const float* bias;                          /* [H], [1] */
-  float* d_h; int64_t ld_d_h; int32_t relu_mask; int32_t pad0; /* d(tower output), nullable */
+  float* d_h; int64_t ld_d_h; int32_t relu_mask;              /* d(tower output), nullable */
+  int32_t mask_col;                                           /* column of the scenario mask this head is multiplied by */
   float* dw; float* dbias;                                    /* [H], [1] */
   uint16_t* d_h_bf16; int64_t ld_d_h_bf16;                    /* nullable bf16 copy of d_h */
   const float* bias2; float* dbias2;                          /* optional second scalar bias (PEPNet: the final
@@ -448,6 +449,14 @@ int mmlrec_heads_forward_backward(const MmlrecHead* heads, int32_t T, int32_t B,
                                   float* pred, int64_t ld_pred, float* loss /*[T+1]: per task, total*/,
                                   int32_t esmm, int32_t training,
                                   float* scratch, int64_t scratch_floats, int32_t* counters, void* stream);
+/* The same with the scenario mask the reference's model classes and loop are written for but never receive (SURVEY Q4:
+ * the loop sets domain_mask = None unconditionally, basemodel.py:265-266): pred[b][t] = head output * mask[b][mask_col_t]
+ * (model/mmoe.py:101-106) and loss_t = BCE(pred_t, y_t, weight = mask column, reduction = 'sum')
+ * (model/basemodel.py:273-282).  mask: fp32 [B, ld_mask] of 0 / 1.  Binary heads only. */
+int mmlrec_heads_forward_backward_masked(const MmlrecHead* heads, int32_t T, int32_t B, const float* y, int64_t ldy,
+                                         const float* mask, int64_t ld_mask, float* pred, int64_t ld_pred, float* loss,
+                                         int32_t flags, int32_t training, float* scratch, int64_t scratch_floats,
+                                         int32_t* counters, void* stream);
 /* Backward of the heads for an upstream gradient d_pred = dL/d(pred) [B, ld_d_pred] supplied by the caller instead of
  * the fused BCE / MSE (the differentiable forward() of the model classes, model/mmoe.py:65: any loss built by autograd
  * on the returned probabilities).  Recomputes the logits, writes d(tower output), dw, dbias; `loss` receives zeros. */

@@ -340,7 +340,8 @@ constexpr int kHeadMaxK = 8;  // H <= 256
 
 __global__ void __launch_bounds__(256)
 heads_kernel(const MmlrecHead* heads, int T, int B, const float* y, int64_t ldy, float* pred, int64_t ld_pred,
-             float* loss, int esmm, int training, float* scratch, int stride_cta, int32_t* counter, int grad_mode) {
+             float* loss, int esmm, int training, float* scratch, int stride_cta, int32_t* counter, int grad_mode,
+             const float* mask, int64_t ldm) {
   pdl_prologue();
   extern __shared__ __align__(16) float dw_s[];            // [8 warps][T][hmax]
   __shared__ MmlrecHead Hd[MMLREC_MAX_TASKS];
@@ -383,6 +384,11 @@ heads_kernel(const MmlrecHead* heads, int T, int B, const float* y, int64_t ldy,
           out = p0 * p;
           scale = p0;
         }
+        // scenario mask (mmoe.py:101-106): the prediction is multiplied by the sample's domain-mask entry of this head,
+        // the loss is BCE(masked prediction, y, weight = mask) (basemodel.py:273-282)
+        const float mk = mask ? mask[(int64_t)b * ldm + Hd[t].mask_col] : 1.f;
+        out *= mk;
+        scale *= mk;
         pred[(int64_t)b * ld_pred + t] = out;
         if (y) {
           const float yy = y[(int64_t)b * ldy + t];
@@ -391,9 +397,9 @@ heads_kernel(const MmlrecHead* heads, int T, int B, const float* y, int64_t ldy,
             gout = yy;
           } else {
             // F.binary_cross_entropy: (y-1)*max(log1p(-x),-100) - y*max(log(x),-100)
-            l = (yy - 1.f) * fmaxf(log1pf(-out), -100.f) - yy * fmaxf(logf(out), -100.f);
+            l = mk * ((yy - 1.f) * fmaxf(log1pf(-out), -100.f) - yy * fmaxf(logf(out), -100.f));
             // binary_cross_entropy_backward: (x-y)/max((1-x)*x, 1e-12); sigmoid_backward: g*(1-p)*p
-            gout = (out - yy) / fmaxf((1.f - out) * out, 1e-12f);
+            gout = mk * (out - yy) / fmaxf((1.f - out) * out, 1e-12f);
           }
           dz = gout * scale * (1.f - p) * p;
           if (esmm && t == 1) cross = gout * p;  // d loss_1 / d p0
@@ -517,7 +523,8 @@ heads_reduce_kernel(const MmlrecHead* heads, int T, float* loss, int esmm, const
 template <int TM, int KM, int R>
 __global__ void __launch_bounds__(256)
 heads_fast_kernel(const MmlrecHead* heads, int T, int B, const float* y, int64_t ldy, float* pred, int64_t ld_pred,
-                  float* loss, int esmm, float* scratch, int stride_cta, int32_t* counter, int grad_mode) {
+                  float* loss, int esmm, float* scratch, int stride_cta, int32_t* counter, int grad_mode,
+                  const float* mask, int64_t ldm) {
   static_assert(R * TM <= 32, "one lane per (sample, task)");
   pdl_prologue();
   constexpr int PW = 2 + KM * 32;                          // per warp and task: loss, dz, dw[KM * 32]
@@ -573,14 +580,17 @@ heads_fast_kernel(const MmlrecHead* heads, int T, int B, const float* y, int64_t
         out = p0 * p;
         scale = p0;
       }
+      const float mk = mask ? mask[(int64_t)my_b * ldm + Hd[my_t].mask_col] : 1.f;   // scenario mask, see heads_kernel
+      out *= mk;
+      scale *= mk;
       pred[(int64_t)my_b * ld_pred + my_t] = out;
       const float yy = y[(int64_t)my_b * ldy + my_t];
       float gout;
       if (grad_mode) {
         gout = yy;
       } else {   // same formulas as heads_kernel (F.binary_cross_entropy forward / backward, sigmoid_backward)
-        l = (yy - 1.f) * fmaxf(log1pf(-out), -100.f) - yy * fmaxf(logf(out), -100.f);
-        gout = (out - yy) / fmaxf((1.f - out) * out, 1e-12f);
+        l = mk * ((yy - 1.f) * fmaxf(log1pf(-out), -100.f) - yy * fmaxf(logf(out), -100.f));
+        gout = mk * (out - yy) / fmaxf((1.f - out) * out, 1e-12f);
       }
       dz = gout * scale * (1.f - p) * p;
       if (esmm && my_t == 1) cross = gout * p;
@@ -987,7 +997,8 @@ extern "C" int64_t mmlrec_heads_scratch(int32_t T, int32_t max_h, int32_t B) {
 
 static int heads_launch(const MmlrecHead* heads, int32_t T, int32_t B, const float* y, int64_t ldy,
                         float* pred, int64_t ld_pred, float* loss, int32_t esmm, int32_t training,
-                        float* scratch, int64_t scratch_floats, int32_t* counters, int grad_mode, void* stream);
+                        float* scratch, int64_t scratch_floats, int32_t* counters, int grad_mode, void* stream,
+                        const float* mask = nullptr, int64_t ldm = 0);
 
 extern "C" int mmlrec_heads_forward_backward(const MmlrecHead* heads, int32_t T, int32_t B, const float* y, int64_t ldy,
                                              float* pred, int64_t ld_pred, float* loss, int32_t esmm, int32_t training,
@@ -1002,9 +1013,20 @@ extern "C" int mmlrec_heads_backward_external(const MmlrecHead* heads, int32_t T
   return heads_launch(heads, T, B, d_pred, ld_d_pred, pred, ld_pred, loss, esmm, 1, scratch, scratch_floats, counters, 1, stream);
 }
 
+extern "C" int mmlrec_heads_forward_backward_masked(const MmlrecHead* heads, int32_t T, int32_t B, const float* y,
+                                                    int64_t ldy, const float* mask, int64_t ld_mask, float* pred,
+                                                    int64_t ld_pred, float* loss, int32_t flags, int32_t training,
+                                                    float* scratch, int64_t scratch_floats, int32_t* counters,
+                                                    void* stream) {
+  MMLREC_CHECK_ARG(mask != nullptr && (flags & 1) == 0, "a scenario mask (not with the ESMM product head)");
+  return heads_launch(heads, T, B, y, ldy, pred, ld_pred, loss, flags, training, scratch, scratch_floats, counters, 0, stream,
+                      mask, ld_mask);
+}
+
 static int heads_launch(const MmlrecHead* heads, int32_t T, int32_t B, const float* y, int64_t ldy,
                         float* pred, int64_t ld_pred, float* loss, int32_t esmm, int32_t training,
-                        float* scratch, int64_t scratch_floats, int32_t* counters, int grad_mode, void* stream) {
+                        float* scratch, int64_t scratch_floats, int32_t* counters, int grad_mode, void* stream,
+                        const float* mask, int64_t ldm) {
   MMLREC_CHECK_ARG(T > 0 && T < MMLREC_MAX_TASKS && B > 0, "bad sizes");
   MMLREC_CHECK_ARG(!(esmm & 1) || T == 2, "esmm needs exactly two heads");
   MMLREC_CHECK_ARG((esmm & ~3) == 0 && esmm != 3, "bad head flags");
@@ -1029,18 +1051,18 @@ static int heads_launch(const MmlrecHead* heads, int32_t T, int32_t B, const flo
     const int hmax = stride_cta / T - 2;
     if (T <= 4 && hmax <= 64) {
       launch_pdl(heads_fast_kernel<4, 2, 4>, dim3(cdiv(B, 32)), dim3(256), 0, stream, heads, T, B, y, ldy, pred, ld_pred, loss,
-                 esmm, scratch, stride_cta, counters, grad_mode);
+                 esmm, scratch, stride_cta, counters, grad_mode, mask, ldm);
       MMLREC_RETURN_LAUNCH(1);
     }
     if (T <= 8 && hmax <= 128) {
       launch_pdl(heads_fast_kernel<8, 4, 2>, dim3(cdiv(B, 16)), dim3(256), 0, stream, heads, T, B, y, ldy, pred, ld_pred, loss,
-                 esmm, scratch, stride_cta, counters, grad_mode);
+                 esmm, scratch, stride_cta, counters, grad_mode, mask, ldm);
       MMLREC_RETURN_LAUNCH(1);
     }
   }
   MMLREC_CHECK_ARG(!((esmm & 2) && training && y != nullptr), "cumulative biases are handled by the one-launch kernel only");
   launch_pdl(heads_kernel, dim3(n_cta), dim3(256), smem, stream, heads, T, B, y, ldy, pred, ld_pred, loss, esmm, training, scratch,
-             stride_cta, counters, grad_mode);
+             stride_cta, counters, grad_mode, mask, ldm);
   if (!(training && y != nullptr)) { MMLREC_RETURN_LAUNCH(1); }
   MMLREC_CHECK_LAUNCH(1);
   launch_pdl(heads_reduce_kernel, dim3(cdiv(stride_cta, 32)), dim3(256), 0, stream, heads, T, loss, esmm, scratch, stride_cta, n_cta);

@@ -1311,6 +1311,14 @@ class HeadStage(Stage):
     def finalize(self):
         b, st = self.b, self.b.store
         self.y = b.zeros(b.B, self.T)
+        # scenario mask (b200_config["domain_mask"]): [B, num_domains] of 0 / 1, head t reads column t (msl) or
+        # t % num_domains (mtmsl) -- mmoe.py:101-106
+        self.mask = None
+        D = getattr(self.b, "mask_domains", 0)
+        if D:
+            assert not self.esmm and all(h.task == "binary" for h in self.heads), "scenario masks: binary heads only"
+            self.mask = b.zeros(b.B, D)
+            self.mask.fill_(1.0)
         self.d_pred = b.zeros(b.B, self.T)
         self.pred = b.zeros(b.B, self.T)
         self.loss = b.zeros(self.T + 1)
@@ -1336,6 +1344,7 @@ class HeadStage(Stage):
             r.dbias = st.grad_ptr(h.bias) if h.bias is not None else None
             if h.bias2 is not None:
                 r.bias2, r.dbias2 = h.bias2.data_ptr(), st.grad_ptr(h.bias2)
+            r.mask_col = (len(recs) % D) if D else 0
             recs.append(r)
         self.table = b.table(recs)
         max_h = max(h.h.width for h in self.heads)
@@ -1344,6 +1353,12 @@ class HeadStage(Stage):
 
     def forward(self, stream, training):
         b = self.b
+        if self.mask is not None:
+            L.check(b.lib.mmlrec_heads_forward_backward_masked(
+                self.table.data_ptr(), self.T, b.B, self.y.data_ptr() if training else None, self.T, self.mask.data_ptr(),
+                self.mask.stride(0), self.pred.data_ptr(), self.T, self.loss.data_ptr(), self.flags, 1 if training else 0,
+                self.scratch.data_ptr(), self.scratch.numel(), self.counter.data_ptr(), stream), "heads (masked)")
+            return
         L.check(b.lib.mmlrec_heads_forward_backward(
             self.table.data_ptr(), self.T, b.B, self.y.data_ptr() if training else None, self.T, self.pred.data_ptr(),
             self.T, self.loss.data_ptr(), self.flags, 1 if training else 0, self.scratch.data_ptr(),
@@ -1369,6 +1384,7 @@ class StepPlan:
         self.model, self.B = model, B
         self.b = Builder(B, model.device_obj, model.store, dry=False, precision=model.precision)
         self.b.dp = getattr(model, "dp", None)
+        self.b.mask_domains = model.num_domains if getattr(model, "use_domain_mask", False) else 0
         model.build_graph(self.b)
         self.b.materialize()
         self.stages = self.b.stages

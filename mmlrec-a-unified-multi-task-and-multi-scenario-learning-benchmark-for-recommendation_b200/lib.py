@@ -97,7 +97,7 @@ class GateLevel(C.Structure):
 
 class Head(C.Structure):
     _fields_ = [("h", vp), ("ld_h", i64), ("H", i32), ("kind", i32), ("w", vp), ("bias", vp),
-                ("d_h", vp), ("ld_d_h", i64), ("relu_mask", i32), ("pad0", i32), ("dw", vp), ("dbias", vp),
+                ("d_h", vp), ("ld_d_h", i64), ("relu_mask", i32), ("mask_col", i32), ("dw", vp), ("dbias", vp),
                 ("d_h_bf16", vp), ("ld_d_h_bf16", i64), ("bias2", vp), ("dbias2", vp)]
 
 
@@ -164,6 +164,7 @@ _SIGNATURES = {
     "mmlrec_gate_level_forward_tiled_smem": (i64, [i32, i32, i32, i32, i32]),
     "mmlrec_gate_level_backward_tiled_smem": (i64, [i32, i32, i32, i32, i32, i32]),
     "mmlrec_heads_forward_backward": (C.c_int, [vp, i32, i32, vp, i64, vp, i64, vp, i32, i32, vp, i64, vp, vp]),
+    "mmlrec_heads_forward_backward_masked": (C.c_int, [vp, i32, i32, vp, i64, vp, i64, vp, i64, vp, i32, i32, vp, i64, vp, vp]),
     "mmlrec_heads_backward_external": (C.c_int, [vp, i32, i32, vp, i64, vp, i64, vp, i32, vp, i64, vp, vp]),
     "mmlrec_heads_scratch": (i64, [i32, i32, i32]),
     "mmlrec_dense_optimizer_step": (C.c_int, [vp, vp, vp, vp, i64, vp, vp, vp]),

@@ -149,6 +149,15 @@ class BaseModel(nn.Module):
         self.use_cuda_graph = bool(self.b200_config.get("cuda_graph", True))
         self.precision = self.b200_config.get("precision", "fp32")
         self.dp = None  # set by mmlrec_b200.parallel.attach()
+        # The scenario mask the reference's classes and loop are written for but never receive (its loop sets
+        # domain_mask = None unconditionally, basemodel.py:265-266).  Opt-in: predictions are multiplied by the
+        # sample's domain-mask entry (mmoe.py:101-106) and the per-task BCE is weighted by it (basemodel.py:273-282).
+        self.use_domain_mask = bool(self.b200_config.get("domain_mask", False))
+        if self.use_domain_mask:
+            if self.task_name not in ("msl", "mtmsl"):
+                raise ValueError('b200_config["domain_mask"] needs task_name "msl" or "mtmsl"')
+            if self.model_config.get("model_name", "").lower() == "star":
+                raise NotImplementedError("STAR with a domain mask goes through DomainBatchNorm (not built)")
         self.optimizer_name: Optional[str] = None
         self.lazy_adam, self.adam_hist, self._steps_since_flush = False, None, 0
         self._user_optimizer = None
@@ -335,14 +344,19 @@ class BaseModel(nn.Module):
         return table
 
     # ------------------------------------------------------------------ one step
-    def train_on_batch(self, X, y) -> torch.Tensor:
+    def train_on_batch(self, X, y, domain_mask=None) -> torch.Tensor:
         """One optimizer step on a batch (host or device tensors / arrays).  Returns the device
-        tensor ``[T+1]`` of per-task BCE sums and their total (no host synchronisation)."""
+        tensor ``[T+1]`` of per-task BCE sums and their total (no host synchronisation).  ``domain_mask``
+        ``[B, num_domains]`` of 0 / 1 is required (and only used) with ``b200_config["domain_mask"]``."""
         if self.hyper_dev is None:
             raise RuntimeError("call compile() before training")
         X = torch.as_tensor(X)
         y = torch.as_tensor(y)
         p = self.plan(X.shape[0])
+        if self.use_domain_mask:
+            if domain_mask is None:
+                raise ValueError('this model was built with b200_config["domain_mask"]: pass domain_mask')
+            p.heads.mask.copy_(torch.as_tensor(domain_mask).reshape(X.shape[0], -1), non_blocking=True)
         if X.device.type == "cpu" and X.is_pinned() and y.device.type == "cpu" and y.is_pinned() \
                 and X.dtype == torch.float32 and y.dtype == torch.float32:
             self._stage_pinned(p, X, y.reshape(X.shape[0], -1))
@@ -458,6 +472,8 @@ class BaseModel(nn.Module):
         X = torch.as_tensor(X)
         self.flush_tables()
         p = self.plan(X.shape[0])
+        if p.heads.mask is not None:
+            p.heads.mask.fill_(1.0)   # the mask is applied to the returned tensor below
         if torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters()):
             out = _FusedForward.apply(self, p, X.to(self.device_obj), *[q for q in self.parameters()])
         else:
@@ -487,6 +503,14 @@ class BaseModel(nn.Module):
             validation_data=None, shuffle=True):
         self._require_cuda()
         from torch.utils.data import DataLoader, TensorDataset
+        dm, dm_val = None, None
+        if self.use_domain_mask:
+            col, vals = self.data_config.get("mask_column", ""), self.data_config.get("mask_values", [])
+            if col == "" or not isinstance(x, dict):
+                raise ValueError('b200_config["domain_mask"]: fit() needs dict inputs and data_config["mask_column"]')
+            dm = get_mask(list(np.asarray(x[col])), vals, self.num_domains).float()
+            if validation_data:
+                dm_val = get_mask(list(np.asarray(validation_data[0][col])), vals, self.num_domains).float()
         X = self._stack_inputs(x)
         y = np.asarray(y, dtype=np.float32).reshape(len(X), self.num_tasks)
         val = None
@@ -498,6 +522,8 @@ class BaseModel(nn.Module):
         elif validation_split and 0. < validation_split < 1.:
             cut = int(len(X) * (1. - validation_split))
             X, y, val = X[:cut], y[:cut], (X[cut:], y[cut:])
+            if dm is not None:
+                dm, dm_val = dm[:cut], dm[cut:]
         batch_size = 256 if batch_size is None else batch_size
         dev = self.device_obj
         # input pipeline.  A dataset that fits is kept in HBM and batches are index_select'ed on the
@@ -514,6 +540,8 @@ class BaseModel(nn.Module):
                       for _ in range(2)]
             copy_stream = torch.cuda.Stream(device=dev)
             copied, consumed = [torch.cuda.Event(), torch.cuda.Event()], [torch.cuda.Event(), torch.cuda.Event()]
+        if dm is not None:
+            dm = dm.to(dev)
         n = len(X)
         steps = (n - 1) // batch_size + 1
         # the reference's DataLoader(shuffle=True) consumes the global torch RNG; iterating a DataLoader
@@ -547,6 +575,8 @@ class BaseModel(nn.Module):
                     p.X.copy_(dx[:nb], non_blocking=True)         # device -> device into the step program's input
                     p.y.copy_(dy[:nb], non_blocking=True)
                     consumed[k & 1].record(main)
+                if dm is not None:
+                    torch.index_select(dm, 0, idx.to(dev, non_blocking=True), out=p.heads.mask)
                 self._run_train(p)
                 preds.append(p.pred.clone())
                 ys.append(p.y.clone())
@@ -567,7 +597,7 @@ class BaseModel(nn.Module):
                 for k, v in sums.items():
                     logs[k] = v / steps
             if val is not None:
-                res = self.evaluate(val[0], val[1], batch_size)
+                res = self.evaluate(val[0], val[1], batch_size, dm_val)
                 print(res)
                 if res.get("auc", 0) > best_auc:
                     best_auc, best_model, stall = res["auc"], copy.deepcopy(self), 0
@@ -618,6 +648,8 @@ class BaseModel(nn.Module):
         for a in range(0, len(X), batch_size):
             xb = X[a:a + batch_size]
             p = self.plan(len(xb))
+            if p.heads.mask is not None:
+                p.heads.mask.fill_(1.0)
             p.X.copy_(xb)
             p.forward(training=False)
             out.append(p.pred.clone())

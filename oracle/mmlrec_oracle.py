@@ -452,13 +452,28 @@ class OracleTrainer:
         else:
             raise NotImplementedError(name)
 
-    def forward(self, X: Tensor, training: bool = False) -> Tensor:
-        return self.fwd(self.params, self.buffers, self.spec, X.float(), training)
+    def _mask_columns(self, domain_mask: Tensor) -> Tensor:
+        """[B, T]: the mask entry head t is multiplied by -- column t for 'msl', t % num_domains for 'mtmsl'
+        (mmoe.py:101-106)."""
+        D = domain_mask.shape[1]
+        return domain_mask.float()[:, [t % D for t in range(self.spec.num_tasks)]]
 
-    def loss_and_grads(self, X: Tensor, y: Tensor) -> Tuple[Tensor, Tensor, Dict[str, Optional[Tensor]]]:
-        pred = self.forward(X, training=True)
+    def forward(self, X: Tensor, training: bool = False, domain_mask: Optional[Tensor] = None) -> Tensor:
+        pred = self.fwd(self.params, self.buffers, self.spec, X.float(), training)
+        if domain_mask is not None:   # every model multiplies its task outputs by the mask at the very end of forward
+            pred = pred * self._mask_columns(domain_mask).to(pred.device)
+        return pred
+
+    def loss_and_grads(self, X: Tensor, y: Tensor, domain_mask: Optional[Tensor] = None
+                       ) -> Tuple[Tensor, Tensor, Dict[str, Optional[Tensor]]]:
+        pred = self.forward(X, training=True, domain_mask=domain_mask)
         self.optim.zero_grad()
-        loss = loss_sum(pred, y.float(), self.loss_names)
+        if domain_mask is not None:   # basemodel.py:273-282: BCE weighted by the task's mask column
+            w = self._mask_columns(domain_mask).to(pred.device)
+            loss = sum(F.binary_cross_entropy(pred[:, t], y.float()[:, t], weight=w[:, t], reduction="sum")
+                       for t in range(pred.shape[1]))
+        else:
+            loss = loss_sum(pred, y.float(), self.loss_names)
         reg = regularization_loss(self.params, self.spec.model, self.l2_dnn).to(loss.device)
         self.last_reg = float(reg.detach())
         (loss + reg).backward()   # basemodel.py:303 total_loss = loss + reg_loss (+ aux / cka terms that are zero)
@@ -466,8 +481,8 @@ class OracleTrainer:
                  for k in self.trainable}
         return pred.detach(), loss.detach(), grads
 
-    def step(self, X: Tensor, y: Tensor) -> Tuple[Tensor, Tensor]:
-        pred, loss, _ = self.loss_and_grads(X, y)
+    def step(self, X: Tensor, y: Tensor, domain_mask: Optional[Tensor] = None) -> Tuple[Tensor, Tensor]:
+        pred, loss, _ = self.loss_and_grads(X, y, domain_mask)
         self.optim.step()
         return pred, loss
 

@@ -84,11 +84,18 @@ CASES = {
     "ple_ae_t2_l2_sgd": ("ae_ple_t2", dict(max_vocab=300), dict(SMALL, l2_reg_dnn=1e-2), dict(optimizer="sgd", lr=1e-2)),
     "esmm_kuairec_l2_adagrad": ("kuairec_esmm", dict(max_vocab=200), dict(SMALL, l2_reg_dnn=1e-2),
                                 dict(optimizer="adagrad", lr=1e-2)),
+    # the scenario mask the reference is written for but never passes (basemodel.py:265-266 sets it to None): here the
+    # reference's own modules are called WITH the mask (model(x, domain_mask), mmoe.py:101-106) and the loss is the
+    # masked branch of its loop (basemodel.py:273-282), computed by this script
+    "ple_ae_t4_masked_adam": ("ae_ple_t4", dict(max_vocab=300), SMALL, {}),
+    "mmoe_movielens_masked_adam": ("movielens_star", dict(vocab_scale=0.02),
+                                   dict(model_name="mmoe", expert_dnn_hidden_units=[16, 16]), {}),
 }
+MASKED = {"ple_ae_t4_masked_adam", "mmoe_movielens_masked_adam"}
 # cases whose identity / 1e-4 initial state would leave parts of the model untested: perturbed after construction
 INIT_STD.update({"cross_stitch_kuairec_adam": 0.05, "hmoe_kuairec_adam": 0.05, "mlp_kuairec_adam": 0.05,
                  "pcg_kuairec_adam": 0.05, "mmoe_kuairec_l2_adam": 0.05, "ple_ae_t2_l2_sgd": 0.05,
-                 "esmm_kuairec_l2_adagrad": 0.05})
+                 "esmm_kuairec_l2_adagrad": 0.05, "ple_ae_t4_masked_adam": 0.05, "mmoe_movielens_masked_adam": 0.05})
 
 
 def post_build(case, model):
@@ -153,14 +160,28 @@ def unregistered_star_tensors(model):
     return extra
 
 
-def reference_step(model, X, y):
-    """model/basemodel.py:262-313 verbatim in effect (domain_mask is always None, :265-266)."""
+def domain_mask_of(cfg, fields, X):
+    """basemodel.py:152-161: get_mask(values of data_config['mask_column'], mask_values, num_domains)."""
+    from model.utils import get_mask
+    dc = cfg["data_config"]
+    col = [n for n, _, _ in fields].index(dc["mask_column"])
+    return get_mask(list(X[:, col]), dc["mask_values"], dc["num_domains"]).float()
+
+
+def reference_step(model, X, y, domain_mask=None):
+    """model/basemodel.py:262-313 verbatim in effect (domain_mask is always None, :265-266); with a mask: the branch of
+    the same loop that the unconditional None makes unreachable (:273-282)."""
     x = X.float()
     y = y.float()
-    y_pred = model(x, None).squeeze()
+    y_pred = model(x, domain_mask).squeeze()
     model.optim.zero_grad()
     # model.loss_func is the list compile() built through _get_loss_func_single (basemodel.py:595-604)
-    loss = sum(model.loss_func[i](y_pred[:, i], y[:, i], reduction="sum") for i in range(model.num_tasks))
+    if domain_mask is not None:
+        D = model.num_domains
+        loss = sum(model.loss_func[i](y_pred[:, i], y[:, i], weight=domain_mask[:, i % D], reduction="sum")
+                   for i in range(model.num_tasks))
+    else:
+        loss = sum(model.loss_func[i](y_pred[:, i], y[:, i], reduction="sum") for i in range(model.num_tasks))
     total = loss + model.get_regularization_loss() + model.aux_loss + torch.zeros((1,))
     if model.model_config["model_name"] == "pcg":
         model.optim.pc_backward(total)
@@ -195,7 +216,10 @@ def main():
             X, y = synthetic.make_batch(cfg, fields, BATCH, seed=100 + s)
             y = make_labels(case, y, s)
             blob[f"step{s}/X"], blob[f"step{s}/y"] = X, y
-            pred, loss, grads = reference_step(model, torch.from_numpy(X), torch.from_numpy(y))
+            dm = domain_mask_of(cfg, fields, X) if case in MASKED else None
+            if dm is not None:
+                blob[f"step{s}/mask"] = dm.numpy()
+            pred, loss, grads = reference_step(model, torch.from_numpy(X), torch.from_numpy(y), dm)
             blob[f"step{s}/pred"] = pred.numpy()
             blob[f"step{s}/loss"] = loss.numpy()
             if s == 0:
@@ -207,7 +231,10 @@ def main():
         with torch.no_grad():
             Xe, _ = synthetic.make_batch(cfg, fields, BATCH, seed=999)
             blob["eval/X"] = Xe
-            blob["eval/pred"] = model(torch.from_numpy(Xe).float(), None).numpy()
+            dme = domain_mask_of(cfg, fields, Xe) if case in MASKED else None
+            if dme is not None:
+                blob["eval/mask"] = dme.numpy()
+            blob["eval/pred"] = model(torch.from_numpy(Xe).float(), dme).numpy()
         for k, v in model.state_dict().items():
             blob["final/" + k] = v.detach().numpy().copy()
         import json

@@ -109,3 +109,46 @@ def test_main_py_runs_end_to_end_on_a_csv(tmp_path):
     res = pd.read_csv(tmp_path / "res.csv")
     assert {"auc_0", "auc_1", "log_loss_0", "log_loss_1"} <= set(res.columns) and len(res) == 1
     assert 0.5 < float(res["auc_0"][0]) <= 1.0
+
+
+def test_fit_with_domain_mask_follows_the_masked_oracle():
+    """``b200_config["domain_mask"]``: fit() builds the mask from ``data_config["mask_column"]`` like the reference's fit()
+    (basemodel.py:152-161) and -- unlike the reference, whose loop then drops it (:265-266) -- applies it.  One epoch
+    without shuffling must give the epoch loss of the oracle stepping the same batches with the same masks, and
+    predict(domain_mask) must zero the other scenarios' heads."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import copy
+    from helpers import oracle_columns
+    from mmlrec_b200 import synthetic
+    from mmlrec_b200.model import get_model_class
+    from mmlrec_b200.model.utils import DenseFeat, SparseFeat, get_mask
+    from oracle.mmlrec_oracle import OracleTrainer
+    cfg, fields = synthetic.workload("ae_ple_t4", max_vocab=200)
+    cfg["model_config"].update(expert_dnn_hidden_units=[16, 8], gate_dnn_hidden_units=[8], tower_dnn_hidden_units=[8])
+    cfg["b200_config"] = {"precision": "fp32", "domain_mask": True}
+    emb = cfg["model_config"]["emb"]
+    cols = [SparseFeat(n, v, emb) if k == "sparse" else DenseFeat(n, 1) for n, k, v in fields]
+    torch.manual_seed(3)
+    model = get_model_class("ple")(cols, init_std=0.05, device="cuda:0", config=copy.deepcopy(cfg))
+    model.compile(cfg["optim_config"]["optimizer"], cfg["optim_config"]["loss"], ["auc"])
+    sd = {k: v.detach().cpu().clone() for k, v in model.state_dict().items()}
+    names = [n for n, _ in model.named_parameters()]
+    oracle = OracleTrainer(cfg, oracle_columns(cfg, fields), {k: v for k, v in sd.items() if k in names},
+                           {k: v for k, v in sd.items() if k not in names}, names)
+    N, B = 512, 128
+    X, y = synthetic.make_batch(cfg, fields, N, seed=77)
+    cols_names = [f[0] for f in fields]
+    dc = cfg["data_config"]
+    dm = get_mask(list(X[:, cols_names.index(dc["mask_column"])]), dc["mask_values"], dc["num_domains"]).float()
+    total = 0.0
+    for a in range(0, N, B):
+        _, loss = oracle.step(torch.from_numpy(X[a:a + B]), torch.from_numpy(y[a:a + B]), dm[a:a + B])
+        total += float(loss)
+    buf = io.StringIO()
+    with contextlib.redirect_stdout(buf):
+        model.fit({n: X[:, i] for i, n in enumerate(cols_names)}, y, batch_size=B, epochs=1, shuffle=False)
+    epochs, _ = _parse(buf.getvalue())
+    assert abs(epochs[0]["loss"] - total / N) <= 1e-4 * abs(total / N), (epochs, total / N)
+    pred = model.predict([X[:, i] for i in range(X.shape[1])], B, domain_mask=dm.numpy())
+    assert np.all(pred[dm.numpy() == 0] == 0) and np.all(pred[dm.numpy() == 1] > 0)

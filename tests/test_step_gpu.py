@@ -15,12 +15,12 @@ def _implemented():
 
 
 
-def build_model(cfg, fields, device="cuda:0", precision="fp32", cuda_graph=True):
+def build_model(cfg, fields, device="cuda:0", precision="fp32", cuda_graph=True, domain_mask=False):
     import copy
     from mmlrec_b200.model import get_model_class
     from mmlrec_b200.model.utils import DenseFeat, SparseFeat
     cfg = copy.deepcopy(cfg)
-    cfg["b200_config"] = {"precision": precision, "cuda_graph": cuda_graph}
+    cfg["b200_config"] = {"precision": precision, "cuda_graph": cuda_graph, "domain_mask": domain_mask}
     emb = cfg["model_config"]["emb"]
     cols = [SparseFeat(n, v, emb) if k == "sparse" else DenseFeat(n, 1) for n, k, v in fields]
     model = get_model_class(cfg["model_config"]["model_name"])(cols, device=device, config=cfg)
@@ -52,7 +52,8 @@ def test_fp32_step_matches_reference_golden(case, graph):
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
     z, cfg, fields = load_golden(case)
-    model, cfg = build_model(cfg, fields, cuda_graph=graph)
+    masked = "step0/mask" in z.files   # scenario-mask cases: the reference's modules were called WITH the domain mask
+    model, cfg = build_model(cfg, fields, cuda_graph=graph, domain_mask=masked)
     load_init(model, z)
     model.compile(cfg["optim_config"]["optimizer"], cfg["optim_config"]["loss"], ["auc"])
     model.train()
@@ -67,7 +68,7 @@ def test_fp32_step_matches_reference_golden(case, graph):
     gtol = 0.2 if loose else 1e-5
     for s in range(steps):
         X, y = torch.from_numpy(z[f"step{s}/X"]), torch.from_numpy(z[f"step{s}/y"])
-        loss = model.train_on_batch(X, y)
+        loss = model.train_on_batch(X, y, torch.from_numpy(z[f"step{s}/mask"]) if masked else None)
         torch.cuda.synchronize()
         p = model.plan(X.shape[0])
         assert rel_err(p.pred.cpu(), z[f"step{s}/pred"]) < (1e-2 if (loose and s > 0) else 1e-5), f"step {s} predictions"
@@ -128,7 +129,7 @@ def test_fp32_step_matches_reference_golden(case, graph):
         assert float((got - want).abs().max()) <= max(tol, 2e-3 * float(moved_ref)), \
             f"final {name}: {float((got - want).abs().max()):.3e} moved {float(moved_ref):.3e}"
     model.eval()
-    pe = model(torch.from_numpy(z["eval/X"]).cuda())
+    pe = model(torch.from_numpy(z["eval/X"]).cuda(), torch.from_numpy(z["eval/mask"]).cuda() if masked else None)
     # with BatchNorm the eval output depends on (bias - running_mean), both noise-driven (see above)
     eval_tol = 5e-2 if cfg["model_config"].get("dnn_use_bn", False) else 2e-4
     assert rel_err(pe.cpu(), z["eval/pred"]) < eval_tol, "eval-mode forward after training"
@@ -194,7 +195,8 @@ def test_bf16_tensor_core_step_close_to_reference_golden(case):
     if not torch.cuda.is_available():
         pytest.skip("needs a CUDA device")
     z, cfg, fields = load_golden(case)
-    model, cfg = build_model(cfg, fields, precision="bf16")
+    masked = "step0/mask" in z.files
+    model, cfg = build_model(cfg, fields, precision="bf16", domain_mask=masked)
     load_init(model, z)
     model.compile(cfg["optim_config"]["optimizer"], cfg["optim_config"]["loss"], [])
     model.train()
@@ -202,7 +204,7 @@ def test_bf16_tensor_core_step_close_to_reference_golden(case):
     use_bn = cfg["model_config"].get("dnn_use_bn", False)
     for s in range(steps):
         X, y = torch.from_numpy(z[f"step{s}/X"]), torch.from_numpy(z[f"step{s}/y"])
-        loss = model.train_on_batch(X, y)
+        loss = model.train_on_batch(X, y, torch.from_numpy(z[f"step{s}/mask"]) if masked else None)
         torch.cuda.synchronize()
         p = model.plan(X.shape[0])
         ptol = 5e-2 if use_bn else 2e-2  # BatchNorm centring amplifies bf16 rounding of z
