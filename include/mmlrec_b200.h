@@ -432,7 +432,9 @@ int64_t mmlrec_gate_level_backward_tiled_smem(int32_t n_gates, int32_t n_experts
  * Replaces tower_dnn_final_layer (Linear(H,1,bias=False), mmoe.py:52-55), PredictionLayer
  * (utils.py:242-248), F.binary_cross_entropy(.., reduction='sum') summed over tasks
  * (basemodel.py:294-296; log terms clamped at -100) and their autograd.
- *   esmm != 0: two heads share ONE bias and pred = [p0, p0*p1] (esmm.py:57-62).
+ *   esmm = flags: bit 0: two heads share ONE bias and pred = [p0, p0*p1] (esmm.py:57-62); bit 1: task t's logit carries
+ *   the biases of tasks 0..t (mlp.py:45-52); bit 2: every head adds the SAME bias parameter (heads[0].bias): its gradient
+ *   is the sum over the heads (escm.py:86-87 without the product head).
  * ------------------------------------------------------------------------------------------- */
 typedef struct MmlrecHead {
   const float* h; int64_t ld_h; int32_t H; int32_t kind;     /* tower output [B,H]; MMLREC_HEAD_* */

@@ -564,6 +564,7 @@ heads_fast_kernel(const MmlrecHead* heads, int T, int B, const float* y, int64_t
       if (lane == r * TM + t) z = s;
     }
   const bool cum_bias = (esmm & 2) != 0;   // MMLREC_HEADS_CUMULATIVE_BIAS
+  const bool shared_bias = (esmm & 4) != 0;   // one bias parameter behind every head: its gradient is the sum
   esmm &= 1;
   if (mine) {
     z += (Hd[my_t].bias ? *Hd[my_t].bias : 0.f) + (Hd[my_t].bias2 ? *Hd[my_t].bias2 : 0.f);
@@ -700,8 +701,10 @@ heads_fast_kernel(const MmlrecHead* heads, int T, int B, const float* y, int64_t
     float total = 0.f;
     for (int q = 0; q < T; ++q) { loss[q] = tot_s[q][0]; total += tot_s[q][0]; }
     loss[T] = total;
-    if (esmm) {
-      if (Hd[0].dbias) *Hd[0].dbias = tot_s[0][1] + tot_s[1][1];
+    if (esmm || shared_bias) {
+      float v = 0.f;
+      for (int q = 0; q < T; ++q) v += tot_s[q][1];
+      if (Hd[0].dbias) *Hd[0].dbias = v;
     } else if (cum_bias) {   // bias q enters the logits of tasks q, q+1, ...
       for (int q = 0; q < T; ++q) {
         float v = 0.f;
@@ -1029,7 +1032,8 @@ static int heads_launch(const MmlrecHead* heads, int32_t T, int32_t B, const flo
                         const float* mask, int64_t ldm) {
   MMLREC_CHECK_ARG(T > 0 && T < MMLREC_MAX_TASKS && B > 0, "bad sizes");
   MMLREC_CHECK_ARG(!(esmm & 1) || T == 2, "esmm needs exactly two heads");
-  MMLREC_CHECK_ARG((esmm & ~3) == 0 && esmm != 3, "bad head flags");
+  MMLREC_CHECK_ARG((esmm & ~7) == 0 && (esmm & 3) != 3, "bad head flags");
+  MMLREC_CHECK_ARG(!((esmm & 4) && training && y != nullptr && !(T <= 8)), "shared bias: one-launch kernel only");
   const int n_cta = cdiv(B, kHeadRows);
   int stride_cta = 0;
   size_t smem = 0;
@@ -1060,7 +1064,7 @@ static int heads_launch(const MmlrecHead* heads, int32_t T, int32_t B, const flo
       MMLREC_RETURN_LAUNCH(1);
     }
   }
-  MMLREC_CHECK_ARG(!((esmm & 2) && training && y != nullptr), "cumulative biases are handled by the one-launch kernel only");
+  MMLREC_CHECK_ARG(!((esmm & 6) && training && y != nullptr), "cumulative / shared biases are handled by the one-launch kernel only");
   launch_pdl(heads_kernel, dim3(n_cta), dim3(256), smem, stream, heads, T, B, y, ldy, pred, ld_pred, loss, esmm, training, scratch,
              stride_cta, counters, grad_mode, mask, ldm);
   if (!(training && y != nullptr)) { MMLREC_RETURN_LAUNCH(1); }

@@ -1292,11 +1292,19 @@ class HeadStage(Stage):
     (model/mmoe.py:97-100, model/utils.py:242-248, model/basemodel.py:294-296)."""
     name = "heads"
 
-    def __init__(self, b: Builder, heads: List[HeadSpec], esmm: bool = False, cumulative_bias: bool = False):
+    def __init__(self, b: Builder, heads: List[HeadSpec], esmm: bool = False, cumulative_bias: bool = False,
+                 escm: Optional[Tuple[float, float]] = None):
         # cumulative_bias: task t's logit carries the biases of tasks 0..t (mlp.py:47 hands ONE logit tensor to every
         # PredictionLayer, whose ``output += self.bias`` works in place, model/utils.py:243-245)
         self.b, self.heads, self.esmm = b, heads, esmm
         self.flags = (1 if esmm else 0) | (2 if cumulative_bias else 0)
+        # ESCM (escm.py:74-96 + the loss of basemodel.py:284-292): the kernel gives the two probabilities (shared bias),
+        # the three-column prediction, the IPW-weighted loss and its gradient with respect to the probabilities are a
+        # dozen element-wise torch ops on [B]-sized tensors, then the kernel's external-gradient backward takes over
+        self.escm = escm   # (counterfactual_w, global_w) or None
+        if escm is not None:
+            assert len(heads) == 2 and not esmm
+            self.flags = 4
         b.note_params([h.final.weight for h in heads])
         b.note_params([h.bias for h in heads])
         b.note_params([h.bias2 for h in heads])
@@ -1321,6 +1329,8 @@ class HeadStage(Stage):
             self.mask.fill_(1.0)
         self.d_pred = b.zeros(b.B, self.T)
         self.pred = b.zeros(b.B, self.T)
+        if self.escm is not None:
+            self.pred2, self.pred = self.pred, b.zeros(b.B, 3)   # kernel output [p_ctr, p_cvr]; model output adds ctcvr
         self.loss = b.zeros(self.T + 1)
         recs = []
         for h in self.heads:
@@ -1353,6 +1363,8 @@ class HeadStage(Stage):
 
     def forward(self, stream, training):
         b = self.b
+        if self.escm is not None:
+            return self._escm_forward(stream, training)
         if self.mask is not None:
             L.check(b.lib.mmlrec_heads_forward_backward_masked(
                 self.table.data_ptr(), self.T, b.B, self.y.data_ptr() if training else None, self.T, self.mask.data_ptr(),
@@ -1364,12 +1376,46 @@ class HeadStage(Stage):
             self.T, self.loss.data_ptr(), self.flags, 1 if training else 0, self.scratch.data_ptr(),
             self.scratch.numel(), self.counter.data_ptr(), stream), "heads")
 
+    def _escm_forward(self, stream, training):
+        b, B = self.b, self.b.B
+        L.check(b.lib.mmlrec_heads_forward_backward(
+            self.table.data_ptr(), self.T, B, None, self.T, self.pred2.data_ptr(), self.T, self.loss.data_ptr(), self.flags,
+            0, self.scratch.data_ptr(), self.scratch.numel(), self.counter.data_ptr(), stream), "heads (escm forward)")
+        p0, p1 = self.pred2[:, 0], self.pred2[:, 1]
+        p2 = p0 * p1                                             # escm.py:88  ctcvr = ctr * cvr
+        torch.stack([p0, p1, p2], dim=1, out=self.pred)
+        if not training:
+            return
+        w_cf, w_g = self.escm
+        y0, y1 = self.y[:, 0], self.y[:, 1]
+
+        def bce(p, y):        # F.binary_cross_entropy per element (log terms clamped at -100) and its derivative in p
+            val = (y - 1.0) * torch.log1p(-p).clamp_min(-100.0) - y * torch.log(p).clamp_min(-100.0)
+            return val, (p - y) / ((1.0 - p) * p).clamp_min(1e-12)
+
+        (l0, g_l0), (l1, g_l1), (l2, g_l2) = bce(p0, y0), bce(p1, y1), bce(p2, y1)
+        L0, L1, L2 = l0.sum(), l1.sum(), l2.sum()
+        # counterfact_ipw (escm.py:98-111; `ips.stop_gradient = True` is a no-op in torch: the gradient flows through ips)
+        n = y0.sum()
+        ps_raw = p0 * n
+        ps = ps_raw.clamp_min(1e-6)
+        inv = 1.0 / ps
+        ips = inv.clamp(-15.0, 15.0) * float(B)
+        s = (ips * y0).mean()
+        total = L0 + w_cf * (L1 * s) + w_g * L2                  # basemodel.py:284-292
+        d_ips = torch.where((inv >= -15.0) & (inv <= 15.0) & (ps_raw > 1e-6), -n / (ps * ps), torch.zeros_like(ps)) * float(B)
+        g0 = g_l0 + w_cf * L1 * (y0 * d_ips) / float(B) + w_g * g_l2 * p1
+        g1 = w_cf * s * g_l1 + w_g * g_l2 * p0
+        self.backward_external(stream, torch.stack([g0, g1], dim=1))
+        self.loss.copy_(torch.stack([L0, total - L0, total]))
+
     def backward_external(self, stream, d_pred: torch.Tensor):
         """Backward for an upstream gradient dL/d(pred) [B, T] handed in by autograd (differentiable forward())."""
         b = self.b
         self.d_pred.copy_(d_pred)
+        pred = self.pred2 if self.escm is not None else self.pred   # (the kernel's own [B, T] output buffer)
         L.check(b.lib.mmlrec_heads_backward_external(
-            self.table.data_ptr(), self.T, b.B, self.d_pred.data_ptr(), self.T, self.pred.data_ptr(), self.T,
+            self.table.data_ptr(), self.T, b.B, self.d_pred.data_ptr(), self.T, pred.data_ptr(), self.T,
             self.loss.data_ptr(), self.flags, self.scratch.data_ptr(), self.scratch.numel(),
             self.counter.data_ptr(), stream), "heads (external gradient)")
 

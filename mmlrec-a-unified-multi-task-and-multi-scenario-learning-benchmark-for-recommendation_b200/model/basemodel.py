@@ -474,7 +474,7 @@ class BaseModel(nn.Module):
         p = self.plan(X.shape[0])
         if p.heads.mask is not None:
             p.heads.mask.fill_(1.0)   # the mask is applied to the returned tensor below
-        if torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters()):
+        if torch.is_grad_enabled() and any(q.requires_grad for q in self.parameters()) and p.heads.escm is None:
             out = _FusedForward.apply(self, p, X.to(self.device_obj), *[q for q in self.parameters()])
         else:
             p.X.copy_(X, non_blocking=True)
@@ -620,6 +620,8 @@ class BaseModel(nn.Module):
 
     def _train_metric(self, fn, y_true, y_pred):
         """The reference's metric inputs per task type (basemodel.py:316-331, :383-392); tensors on the device."""
+        if y_pred.shape[1] == 3 and self.model_config.get("model_name", "").lower() == "escm":
+            y_pred = y_pred[:, [0, 2]]   # ctr and ctcvr (basemodel.py:328-329, :438-441)
         if self.task_name == "msl":
             return fn(y_true[:, 0], y_pred.sum(dim=-1))
         if self.task_name == "mtmsl":
@@ -655,6 +657,8 @@ class BaseModel(nn.Module):
             out.append(p.pred.clone())
         self.train(was_training)
         res = torch.cat(out)
+        if res.shape[1] == 3 and self.model_config.get("model_name", "").lower() == "escm":
+            res = res[:, [0, 2]].contiguous()   # basemodel.py:438-441: predict() returns ctr and ctcvr
         if domain_mask is not None:
             dm = torch.as_tensor(domain_mask).to(res)
             if self.task_name == "msl":

@@ -6,7 +6,7 @@ library is missing instead of falling back to anything here).
 
 What it is: a *functional* restatement, in plain fp32 PyTorch on the CPU, of the reference's
 step body (``/root/reference/model/basemodel.py:262-313``): multi-field gather + concat, the
-expert / gate / tower networks of nine model families, sigmoid + BCE(sum), backward and the
+expert / gate / tower networks of ten model families, sigmoid + BCE(sum), backward and the
 ``torch.optim`` step.  All arithmetic of the reference lives in the third-party module ``torch``
 (reference prose pins "PyTorch 1.11.0", ``README.md:52``; no lock file; operative version in
 this image: torch 2.11.0+cu128), so the restatement calls the same ATen ops in the same order.
@@ -255,6 +255,29 @@ def forward_esmm(p: Params, b: Params, s: Spec, X: Tensor, training: bool) -> Te
     return torch.cat([p_ctr, p_ctr * p_cvr], -1)
 
 
+def forward_escm(p: Params, b: Params, s: Spec, X: Tensor, training: bool) -> Tensor:
+    """model/escm.py:74-96 (the 'escm' variant): ESMM's towers, output [p_ctr, p_cvr, p_ctr * p_cvr]."""
+    x = gather_concat(X, p, s.columns)
+    ctr = F.linear(mlp(p, b, "ctr_dnn", x, s.use_bn, training, s.act), p["ctr_dnn_final_layer.weight"])
+    cvr = F.linear(mlp(p, b, "cvr_dnn", x, s.use_bn, training, s.act), p["cvr_dnn_final_layer.weight"])
+    p_ctr = predict_head(ctr, p["out.bias"], s.task)
+    p_cvr = predict_head(cvr, p["out.bias"], s.task)
+    return torch.cat([p_ctr, p_cvr, p_ctr * p_cvr], -1)
+
+
+def escm_loss(pred: Tensor, y: Tensor, counterfactual_w: float = 0.1, global_w: float = 1.0) -> Tensor:
+    """model/basemodel.py:284-292 with model/escm.py:98-111 (counterfact_ipw; `ips.stop_gradient = True` is a no-op
+    attribute assignment in torch, so the gradient flows through the weights)."""
+    loss_0 = F.binary_cross_entropy(pred[:, 0], y[:, 0], reduction="sum")
+    loss_1 = F.binary_cross_entropy(pred[:, 1], y[:, 1], reduction="sum")
+    loss_2 = F.binary_cross_entropy(pred[:, 2], y[:, 1], reduction="sum")
+    ctr_num, o = torch.sum(y[:, 0]), y[:, 0].float()
+    ps = torch.maximum(pred[:, 0] * ctr_num.float(), torch.full_like(pred[:, 0], 0.000001))
+    ips = torch.clip(torch.reciprocal(ps), min=-15, max=15) * torch.sum(torch.full_like(o, 1).float(), 0)
+    loss_1 = torch.mean(loss_1 * ips * o)
+    return loss_0 + loss_1 * counterfactual_w + loss_2 * global_w
+
+
 def star_weight(p: Params, prefix: str, i: int, last: int, which: str) -> Tensor:
     """SharedSpecificLinear keeps per-domain tensors in plain lists (model/utils.py:181-191); only
     the last one is a registered parameter (``<prefix>.specific_<which>``).  The oracle stores the
@@ -378,7 +401,7 @@ def forward_hmoe(p: Params, b: Params, s: Spec, X: Tensor, training: bool) -> Te
 FORWARDS = {
     "mmoe": forward_mmoe, "pcg": forward_mmoe, "ple": forward_ple, "sharedbottom": forward_sharedbottom,
     "esmm": forward_esmm, "star": forward_star, "pepnet": forward_pepnet, "mlp": forward_mlp,
-    "cross_stitch": forward_cross_stitch, "hmoe": forward_hmoe,
+    "cross_stitch": forward_cross_stitch, "hmoe": forward_hmoe, "escm": forward_escm,
 }
 
 
@@ -397,6 +420,7 @@ REG_MODULES = {
     "mlp": ["mlp_layers"],
     "cross_stitch": ["tower_dnn"],
     "star": [], "pepnet": [],
+    "escm": ["ctr_dnn", "cvr_dnn", "ctr_dnn_final_layer", "cvr_dnn_final_layer"],
 }
 REG_MODULES["pcg"] = REG_MODULES["mmoe"]
 
@@ -472,6 +496,8 @@ class OracleTrainer:
             w = self._mask_columns(domain_mask).to(pred.device)
             loss = sum(F.binary_cross_entropy(pred[:, t], y.float()[:, t], weight=w[:, t], reduction="sum")
                        for t in range(pred.shape[1]))
+        elif self.spec.model == "escm":
+            loss = escm_loss(pred, y.float())
         else:
             loss = loss_sum(pred, y.float(), self.loss_names)
         reg = regularization_loss(self.params, self.spec.model, self.l2_dnn).to(loss.device)

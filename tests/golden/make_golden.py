@@ -92,6 +92,10 @@ CASES = {
                                    dict(model_name="mmoe", expert_dnn_hidden_units=[16, 16]), {}),
 }
 MASKED = {"ple_ae_t4_masked_adam", "mmoe_movielens_masked_adam"}
+# ESCM-IPW: three-column output, the loop's special loss (basemodel.py:284-292)
+CASES["escm_kuairec_adam"] = ("kuairec_esmm", dict(max_vocab=200), dict(SMALL, model_name="escm"), {})
+CASES["escm_kuairec_sgd"] = ("kuairec_esmm", dict(max_vocab=200), dict(SMALL, model_name="escm"), dict(optimizer="sgd", lr=1e-3))
+INIT_STD.update({"escm_kuairec_adam": 0.05, "escm_kuairec_sgd": 0.05})
 # cases whose identity / 1e-4 initial state would leave parts of the model untested: perturbed after construction
 INIT_STD.update({"cross_stitch_kuairec_adam": 0.05, "hmoe_kuairec_adam": 0.05, "mlp_kuairec_adam": 0.05,
                  "pcg_kuairec_adam": 0.05, "mmoe_kuairec_l2_adam": 0.05, "ple_ae_t2_l2_sgd": 0.05,
@@ -133,11 +137,12 @@ def build_reference(cfg, fields, init_std=0.0001):
     from model.mlp import MLP
     from model.cross_stitch import CrossStitch
     from model.hmoe import HMOE
+    from model.escm import ESCM
     emb = cfg["model_config"]["emb"]
     cols = [SparseFeat(n, vocabulary_size=v, embedding_dim=emb) if k == "sparse" else DenseFeat(n, 1)
             for n, k, v in fields]
     cls = {"mmoe": MMOE, "ple": PLE, "sharedbottom": SharedBottom, "esmm": ESMM, "star": STAR,
-           "pepnet": PepNet, "mlp": MLP, "cross_stitch": CrossStitch, "hmoe": HMOE, "pcg": MMOE}[cfg["model_config"]["model_name"].lower()]
+           "pepnet": PepNet, "mlp": MLP, "cross_stitch": CrossStitch, "hmoe": HMOE, "pcg": MMOE, "escm": ESCM}[cfg["model_config"]["model_name"].lower()]
     with contextlib.redirect_stdout(io.StringIO()):
         model = cls(cols, init_std=init_std, device="cpu", config=cfg)
         model.compile(optimizer=cfg["optim_config"]["optimizer"], loss=cfg["optim_config"]["loss"],
@@ -180,6 +185,15 @@ def reference_step(model, X, y, domain_mask=None):
         D = model.num_domains
         loss = sum(model.loss_func[i](y_pred[:, i], y[:, i], weight=domain_mask[:, i % D], reduction="sum")
                    for i in range(model.num_tasks))
+    elif model.model_config["model_name"] == "escm":   # basemodel.py:284-292, line for line
+        loss_func = model.loss_func
+        loss_0 = loss_func[0](y_pred[:, 0], y[:, 0], reduction="sum")
+        loss_1 = loss_func[1](y_pred[:, 1], y[:, 1], reduction="sum")
+        loss_2 = loss_func[1](y_pred[:, 2], y[:, 1], reduction="sum")
+        ctr_num = torch.sum(y[:, 0])
+        o = y[:, 0].float()
+        loss_1 = model.counterfact_ipw(loss_1, ctr_num, o, y_pred[:, 0])
+        loss = loss_0 + loss_1 * model.counterfactual_w + loss_2 * model.global_w
     else:
         loss = sum(model.loss_func[i](y_pred[:, i], y[:, i], reduction="sum") for i in range(model.num_tasks))
     total = loss + model.get_regularization_loss() + model.aux_loss + torch.zeros((1,))
