@@ -301,7 +301,8 @@ def gemm_roofline(model, plan, tf_burst, which):
     return {"kernel": kname, "bound": "tensor", "achieved": ach, "peak": tf_burst, "unit": "TFLOP/s", "frac": ach / tf_burst,
             "traffic": traffic, "traffic_unit": "bytes/launch", "traffic_source": traffic_src,
             "peak_source": which + " (bf16 cuBLAS burst)", "launches_per_step": len(per), "flops_per_step": total_flops,
-            "ms_per_step_in_gemm": total_ms, "timing": "CUDA events around a graph of 20 replays of each launch, best of 5",
+            "ms_per_step_in_gemm": total_ms, "timing": "CUDA events around a graph of 20 back-to-back replays of each launch on the same operands (L2-warm; "
+                                                        "consecutive launches overlap through programmatic dependent launch), best of 5",
             "per_launch": per}
 
 
