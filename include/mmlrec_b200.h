@@ -497,6 +497,16 @@ int mmlrec_mul_backward(const float* d_out, int64_t ld_dout, const float* a, int
                         float* da_f32, uint16_t* da_bf16, int64_t ld_da, int32_t dkind_a, int32_t acc_a,
                         float* db_f32, uint16_t* db_bf16, int64_t ld_db, int32_t dkind_b, int32_t acc_b,
                         int32_t rows, int32_t cols, void* stream);
+/* AITM information transfer between two consecutive tasks (reference model/aitm.py:82-91: cat([p, q], 1) -> h1/h2/h3 ->
+ * softmax(sum(K*Q, 2) / sqrt(H), dim=1) * V summed over the two tokens).  vkq: [rows, 6H] = V_p K_p Q_p V_q K_q Q_q (the
+ * three projections of token p, then of token q); out[r, :] = a_p V_p + a_q V_q (fp32 and / or bf16); attn [rows, 2]
+ * receives (a_p, a_q) for the backward pass (may be NULL for inference). */
+int mmlrec_aitm_attention_forward(const float* vkq, int64_t ld, int32_t rows, int32_t H, float* out_f32, int64_t ld_f32,
+                                  uint16_t* out_bf16, int64_t ld_bf16, float* attn, void* stream);
+/* d_vkq (same 6H layout, fp32 or bf16, assigned) from d_out [rows, H] (fp32) and the saved attn */
+int mmlrec_aitm_attention_backward(const float* d_out, int64_t ld_dout, const float* vkq, int64_t ld, const float* attn,
+                                   int32_t rows, int32_t H, float* d_vkq_f32, uint16_t* d_vkq_bf16, int64_t ld_d,
+                                   void* stream);
 /* STAR: effective weights of all T domains in nn.Linear layout:
  *   w_eff[t*N + n, k] = spec[t][k, n] * shared[k, n];  b_eff[t*N + n] = spec_b[t][n] + shared_b[n]
  * spec / spec_b: T device pointers (int64 array on device); bf16 shadow optional. */

@@ -843,6 +843,66 @@ __global__ void mul_backward_kernel(const float* d_out, int64_t ld_dout, const f
   }
 }
 
+// AITM information transfer (aitm.py:82-91): two tokens (p = the previous task's transferred feature, q = this task's
+// own feature), each with value / key / query projections, one row of [V_p K_p Q_p V_q K_q Q_q] (6H floats):
+//   s_j = <K_j, Q_j> / sqrt(H),  a = softmax_j(s),  out = a_p V_p + a_q V_q
+// One warp per row; the row's two attention weights are kept for the backward pass.
+__global__ void aitm_attention_forward_kernel(const float* vkq, int64_t ld, int rows, int H, float denom, float* o32,
+                                              int64_t ld32, uint16_t* o16, int64_t ld16, float* attn) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    const float* x = vkq + (int64_t)r * ld;
+    float sp = 0.f, sq = 0.f;
+    for (int h = lane; h < H; h += 32) {
+      sp = fmaf(x[H + h], x[2 * H + h], sp);
+      sq = fmaf(x[4 * H + h], x[5 * H + h], sq);
+    }
+    sp = warp_sum(sp) / denom;
+    sq = warp_sum(sq) / denom;
+    const float m = fmaxf(sp, sq);
+    const float ep = expf(sp - m), eq = expf(sq - m);
+    const float ap = ep / (ep + eq), aq = eq / (ep + eq);
+    if (attn && lane == 0) { attn[2 * (int64_t)r] = ap; attn[2 * (int64_t)r + 1] = aq; }
+    for (int h = lane; h < H; h += 32) {
+      const float v = ap * x[h] + aq * x[3 * H + h];
+      if (o32) o32[(int64_t)r * ld32 + h] = v;
+      if (o16) o16[(int64_t)r * ld16 + h] = float_to_bf16_bits(v);
+    }
+  }
+}
+
+// d_vkq (fp32 or bf16, same 6H layout) from d_out: dV_j = a_j d_out; with g_j = <d_out, V_j>:
+// ds_j = a_j (g_j - sum_i a_i g_i); dK_j = ds_j Q_j / sqrt(H); dQ_j = ds_j K_j / sqrt(H)
+__global__ void aitm_attention_backward_kernel(const float* d_out, int64_t ld_dout, const float* vkq, int64_t ld,
+                                               const float* attn, int rows, int H, float denom, float* d32, uint16_t* d16,
+                                               int64_t ld_d) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < rows; r += gridDim.x * wpb) {
+    const float* x = vkq + (int64_t)r * ld;
+    const float* g = d_out + (int64_t)r * ld_dout;
+    const float ap = attn[2 * (int64_t)r], aq = attn[2 * (int64_t)r + 1];
+    float gp = 0.f, gq = 0.f;
+    for (int h = lane; h < H; h += 32) {
+      const float go = g[h];
+      gp = fmaf(go, x[h], gp);
+      gq = fmaf(go, x[3 * H + h], gq);
+    }
+    gp = warp_sum(gp);
+    gq = warp_sum(gq);
+    const float mean = ap * gp + aq * gq;
+    const float dsp = ap * (gp - mean) / denom, dsq = aq * (gq - mean) / denom;
+    for (int h = lane; h < H; h += 32) {
+      const float go = g[h];
+      const float v[6] = {ap * go, dsp * x[2 * H + h], dsp * x[H + h], aq * go, dsq * x[5 * H + h], dsq * x[4 * H + h]};
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        if (d32) d32[(int64_t)r * ld_d + j * H + h] = v[j];
+        if (d16) d16[(int64_t)r * ld_d + j * H + h] = float_to_bf16_bits(v[j]);
+      }
+    }
+  }
+}
+
 // i indexes (t, n, k) of w_eff [T*N, ld_w]; spec[t] and shared are [K, N] row-major
 __global__ void star_weights_kernel(const int64_t* spec_ptrs, const int64_t* spec_b_ptrs, const float* shared,
                                     const float* shared_b, int T, int K, int N, float* w_eff, int64_t ld_w,
@@ -1221,6 +1281,26 @@ extern "C" int mmlrec_mul_backward(const float* d_out, int64_t ld_dout, const fl
   mul_backward_kernel<<<grid_for((int64_t)rows * cols), 256, 0, (cudaStream_t)stream>>>(
       d_out, ld_dout, a, lda, b, ldb, da_f32, da_bf16, ld_da, dkind_a, acc_a, db_f32, db_bf16, ld_db, dkind_b, acc_b, rows,
       cols);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_aitm_attention_forward(const float* vkq, int64_t ld, int32_t rows, int32_t H, float* out_f32,
+                                             int64_t ld_f32, uint16_t* out_bf16, int64_t ld_bf16, float* attn,
+                                             void* stream) {
+  if (rows <= 0 || H <= 0) return 0;
+  MMLREC_CHECK_ARG(vkq && (out_f32 || out_bf16), "null buffer");
+  aitm_attention_forward_kernel<<<grid_for((int64_t)rows * 32), 256, 0, (cudaStream_t)stream>>>(
+      vkq, ld, rows, H, sqrtf((float)H), out_f32, ld_f32, out_bf16, ld_bf16, attn);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_aitm_attention_backward(const float* d_out, int64_t ld_dout, const float* vkq, int64_t ld,
+                                              const float* attn, int32_t rows, int32_t H, float* d_vkq_f32,
+                                              uint16_t* d_vkq_bf16, int64_t ld_d, void* stream) {
+  if (rows <= 0 || H <= 0) return 0;
+  MMLREC_CHECK_ARG(d_out && vkq && attn && (d_vkq_f32 || d_vkq_bf16), "null buffer");
+  aitm_attention_backward_kernel<<<grid_for((int64_t)rows * 32), 256, 0, (cudaStream_t)stream>>>(
+      d_out, ld_dout, vkq, ld, attn, rows, H, sqrtf((float)H), d_vkq_f32, d_vkq_bf16, ld_d);
   MMLREC_RETURN_LAUNCH(1);
 }
 

@@ -22,7 +22,7 @@ from __future__ import annotations
 
 import ctypes as C
 import os
-from typing import List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Sequence, Tuple
 
 import torch
 import torch.nn as nn
@@ -703,9 +703,31 @@ class LinearStage(Stage):
                         break
         self.zero_before_bwd = []   # gradient buffers a K-split dgrad accumulates into from zero
         dzg = self.zs[0].group if self.use_bn else self.outs[0].group   # where dZ lives
+        # one Linear applied to several inputs in this stage (AITM's h1/h2/h3 on both tokens, aitm.py:86-88): every
+        # application writes its weight / bias gradient into its OWN gradient slices (the optimizer adds slices up in
+        # slice order anyway), so the launch holds no two problems with the same destination
+        live = [g for g in self.groups if any(o.grad_written for o in g.outs)]
+        uses: Dict[int, int] = {}
+        for g in live:
+            uses[g.W.data_ptr()] = uses.get(g.W.data_ptr(), 0) + 1
+        dup = max(uses.values(), default=1)
+        if dup > 1:
+            assert dup <= st.max_grad_slices and not derived, "too many applications of one Linear in a stage"
+            self.split_k = max(min(self.split_k, st.max_grad_slices // dup), 1)
+        S = self.split_k
+        self.split_k = S * dup      # gradient slices this stage writes (StepPlan.grad_slices)
+        seen: Dict[int, int] = {}
+        # tensor-core mode, dZ kept in fp32 because several stages add into it (an activation with consumers in
+        # different stages): the GEMMs read a bf16 copy made at the start of this stage's backward
+        self.dz_stage = None
+        if b.tc and not self.use_bn and dzg.gbuf16 is None and live:
+            self.dz_stage = b.zeros(b.B, _align(dzg.total, 8), dtype=torch.bfloat16)
         for g in self.groups:
             if not any(o.grad_written for o in g.outs):
                 continue  # nothing flows into this group: its parameters keep a zero gradient
+            slice0 = seen.get(g.W.data_ptr(), 0) * S     # first gradient slice of this application
+            seen[g.W.data_ptr()] = seen.get(g.W.data_ptr(), 0) + 1
+            g_off = 4 * slice0 * st.slice_stride
             for o in g.outs:
                 for part in ([o] if not o.children else o.children):
                     if not part.grad_written:
@@ -727,9 +749,9 @@ class LinearStage(Stage):
                 else:
                     p.A, p.a_rs, p.a_cs = dz_ptr, 1, dz_ld
                     p.B, p.b_rs, p.b_cs = x.ptr, 1, x.ld
-                    p.rowsum_a = st.grad_ptr(g.b) if g.b is not None else None
+                    p.rowsum_a = (st.grad_ptr(g.b) + g_off) if g.b is not None else None
                     p.M, p.N, p.K = g.N, g.K, b.B
-                p.C, p.ldc = st.grad_ptr(g.W), g.W._mm_ld
+                p.C, p.ldc = st.grad_ptr(g.W) + g_off, g.W._mm_ld
                 waves[0].append(p)
                 if want_dx:
                     q = L.GemmF32()   # dgrad: dX[b,k] = sum_n dZ[b,n] W[n,k], masked by the producer's ReLU
@@ -743,9 +765,9 @@ class LinearStage(Stage):
                     q.accumulate = accumulate
                     waves[wave].append(q)
             else:
-                dz16, dz_ld = dzg.gbuf16.data_ptr() + 2 * g.y_col, dzg.gbuf16.stride(0)
-                # wgrad: both operands MN-major (no transposed copies); batch slice k -> gradient slice k
-                S = self.split_k
+                dz_buf = self.dz_stage if self.dz_stage is not None else dzg.gbuf16
+                dz16, dz_ld = dz_buf.data_ptr() + 2 * g.y_col, dz_buf.stride(0)
+                # wgrad: both operands MN-major (no transposed copies); batch slice k -> gradient slice slice0 + k
                 # a layer with few outputs: dW^T = X^T dZ (M = K_in fills the 256-row pair tiles; with M = N_out <= 128
                 # half of every tile is empty and the peer CTA's operand path idles), stored transposed from registers;
                 # the bias gradient = column sums of dZ from an all-ones A tile (MmlrecGemmTcDesc.colsum_b)
@@ -758,9 +780,9 @@ class LinearStage(Stage):
                         d.A, d.lda, d.a_mn_major = x.ptr16 + 2 * k * rows * x.ld16, x.ld16, 1
                         d.B, d.ldb, d.b_mn_major = dz16 + 2 * k * rows * dz_ld, dz_ld, 1
                         d.M, d.N, d.K = g.K, g.N, rows
-                        d.C_f32, d.ldc_f32 = st.grad_ptr(g.W) + 4 * k * st.slice_stride, g.W._mm_ld
+                        d.C_f32, d.ldc_f32 = st.grad_ptr(g.W) + g_off + 4 * k * st.slice_stride, g.W._mm_ld
                         d.c_transposed = 1
-                        d.colsum_b = (st.grad_ptr(g.b) + 4 * k * st.slice_stride) if g.b is not None else None
+                        d.colsum_b = (st.grad_ptr(g.b) + g_off + 4 * k * st.slice_stride) if g.b is not None else None
                         waves[0].append(d)
                         continue
                     if g.transposed:   # dW[k,n] for a [K, N] parameter: the operands swap roles
@@ -771,8 +793,8 @@ class LinearStage(Stage):
                         d.A, d.lda, d.a_mn_major = dz16 + 2 * k * rows * dz_ld, dz_ld, 1
                         d.B, d.ldb, d.b_mn_major = x.ptr16 + 2 * k * rows * x.ld16, x.ld16, 1
                         d.M, d.N, d.K = g.N, g.K, rows
-                        d.colsum = (st.grad_ptr(g.b) + 4 * k * st.slice_stride) if g.b is not None else None
-                    d.C_f32, d.ldc_f32 = st.grad_ptr(g.W) + 4 * k * st.slice_stride, g.W._mm_ld
+                        d.colsum = (st.grad_ptr(g.b) + g_off + 4 * k * st.slice_stride) if g.b is not None else None
+                    d.C_f32, d.ldc_f32 = st.grad_ptr(g.W) + g_off + 4 * k * st.slice_stride, g.W._mm_ld
                     waves[0].append(d)
                 if want_dx:
                     e = L.GemmTcDesc()   # dgrad: A = dZ (K-major), B = W read MN-major
@@ -850,6 +872,10 @@ class LinearStage(Stage):
                     (zg.gbuf16.data_ptr() + 2 * c) if zg.gbuf16 is not None else None,
                     zg.gbuf16.stride(0) if zg.gbuf16 is not None else 0,
                     b.store.grad_ptr(bn0.weight), b.store.grad_ptr(bn0.bias), stream), f"bn bwd {self.label}")
+        if self.dz_stage is not None:
+            dzg = self.outs[0].group
+            L.check(b.lib.mmlrec_copy_cols(dzg.gbuf.data_ptr(), dzg.gbuf.stride(0), None, 0, self.dz_stage.data_ptr(),
+                                           self.dz_stage.stride(0), b.B, dzg.total, stream), f"dZ -> bf16 {self.label}")
         for buf in self.zero_before_bwd:
             L.check(b.lib.mmlrec_fill_f32(buf.data_ptr(), buf.numel(), 0.0, stream), f"zero d(input) {self.label}")
         for tbl in self.bwd:
@@ -938,6 +964,49 @@ class MulStage(Stage):
             L.check(b.lib.mmlrec_mul_backward(o.gptr, o.gld, a.ptr, a.ld, c.ptr, c.ld, sa[0], sa[1], sa[2], sa[3], sa[4],
                                               sc[0], sc[1], sc[2], sc[3], sc[4], b.B, a.width, stream),
                     f"mul bwd {self.label}")
+
+
+class PairAttentionStage(Stage):
+    """AITM's information transfer between two consecutive tasks (aitm.py:82-91): the tokens p (transferred from the
+    previous task) and q (this task's own feature) each carry value / key / query projections; ``out = sum_j
+    softmax_j(<K_j, Q_j> / sqrt(H)) V_j``.  ``vkq`` = the six [B, H] projections V_p K_p Q_p V_q K_q Q_q as ADJACENT
+    columns of one buffer (the outputs of one LinearStage, in that order)."""
+    name = "aitm_attention"
+
+    def __init__(self, b: Builder, vkq: List[Act], label: str = ""):
+        self.b, self.vkq, self.label = b, vkq, label
+        H = vkq[0].width
+        assert len(vkq) == 6 and all(a.group is vkq[0].group and a.width == H and a.col == vkq[0].col + i * H
+                                     for i, a in enumerate(vkq)), "the six projections must be adjacent columns"
+        self.H = H
+        for a in vkq:
+            a.want(f32=True)
+        (self.out,) = b.new_group([H], relu=False, name=f"{label}.att", grad_dtype="f32")
+
+    def finalize(self):
+        self.attn = self.b.zeros(self.b.B, 2)
+
+    def forward(self, stream, training):
+        b, o, x = self.b, self.out, self.vkq[0]
+        L.check(b.lib.mmlrec_aitm_attention_forward(x.ptr, x.ld, b.B, self.H, o.ptr if o.has_f32 else None,
+                                                    o.ld if o.has_f32 else 0, o.ptr16 if o.has_bf16 else None,
+                                                    o.ld16 if o.has_bf16 else 0, self.attn.data_ptr(), stream),
+                f"attention fwd {self.label}")
+
+    def plan_backward(self):
+        self.live = self.out.grad_written and self.vkq[0].group.need_grad
+        if self.live:
+            for a in self.vkq:
+                a.grad_written = True
+
+    def backward(self, stream):
+        if not self.live:
+            return
+        b, o, x = self.b, self.out, self.vkq[0]
+        f32 = x.grad_is_f32
+        L.check(b.lib.mmlrec_aitm_attention_backward(o.gptr, o.gld, x.ptr, x.ld, self.attn.data_ptr(), b.B, self.H,
+                                                     x.gptr if f32 else None, None if f32 else x.gptr, x.gld, stream),
+                f"attention bwd {self.label}")
 
 
 class DerivedLinear:

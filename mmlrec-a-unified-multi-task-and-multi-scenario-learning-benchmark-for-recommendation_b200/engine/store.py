@@ -65,7 +65,8 @@ class FlatStore:
         self.dense = torch.zeros(self.n_dense + self.aux_floats, dtype=torch.float32, device=device)
         # gradient slices: slice 0 is THE gradient buffer; in tensor-core mode the split-K wgrad problems write the
         # partial tiles of batch slices 1..S-1 into the further slices (same offsets) and the optimizer adds them up
-        self.max_grad_slices = self.MAX_GRAD_SLICES if want_bf16 else 1
+        # (fp32 mode: no split-K; the second slice serves a Linear applied twice in one stage, LinearStage.plan_backward)
+        self.max_grad_slices = self.MAX_GRAD_SLICES if want_bf16 else 2
         self.slice_stride = self.n_dense + self.aux_floats
         self.grad_slices = torch.zeros(self.max_grad_slices, self.slice_stride, dtype=torch.float32, device=device)
         self.dense_grad = self.grad_slices[0]

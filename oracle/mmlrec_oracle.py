@@ -6,7 +6,7 @@ library is missing instead of falling back to anything here).
 
 What it is: a *functional* restatement, in plain fp32 PyTorch on the CPU, of the reference's
 step body (``/root/reference/model/basemodel.py:262-313``): multi-field gather + concat, the
-expert / gate / tower networks of ten model families, sigmoid + BCE(sum), backward and the
+expert / gate / tower networks of eleven model families, sigmoid + BCE(sum), backward and the
 ``torch.optim`` step.  All arithmetic of the reference lives in the third-party module ``torch``
 (reference prose pins "PyTorch 1.11.0", ``README.md:52``; no lock file; operative version in
 this image: torch 2.11.0+cu128), so the restatement calls the same ATen ops in the same order.
@@ -398,10 +398,27 @@ def forward_hmoe(p: Params, b: Params, s: Spec, X: Tensor, training: bool) -> Te
     return torch.cat(outs, -1)
 
 
+def forward_aitm(p: Params, b: Params, s: Spec, X: Tensor, training: bool) -> Tensor:
+    """model/aitm.py:77-108: per-task bottoms (built from ``expert_dnn_hidden_units``, aitm.py:20); task i >= 1 replaces
+    its feature by the attention over [g(feat_{i-1}), feat_i] with values / keys / queries from h1 / h2 / h3."""
+    x = gather_concat(X, p, s.columns)
+    feat = [mlp(p, b, f"bottom.{t}", x, s.use_bn, training, s.act) for t in range(s.num_tasks)]
+    H = feat[0].shape[1]
+    for i in range(1, s.num_tasks):
+        tok = torch.cat([F.linear(feat[i - 1], p[f"g.{i - 1}.weight"], p[f"g.{i - 1}.bias"]).unsqueeze(1),
+                         feat[i].unsqueeze(1)], dim=1)
+        V = F.linear(tok, p["h1.weight"], p["h1.bias"])
+        K = F.linear(tok, p["h2.weight"], p["h2.bias"])
+        Q = F.linear(tok, p["h3.weight"], p["h3.bias"])
+        a = torch.softmax(torch.sum(K * Q, 2, True) / math.sqrt(H), dim=1)
+        feat[i] = torch.sum(a * V, 1)
+    return _towers(p, b, s, feat, training)
+
+
 FORWARDS = {
     "mmoe": forward_mmoe, "pcg": forward_mmoe, "ple": forward_ple, "sharedbottom": forward_sharedbottom,
     "esmm": forward_esmm, "star": forward_star, "pepnet": forward_pepnet, "mlp": forward_mlp,
-    "cross_stitch": forward_cross_stitch, "hmoe": forward_hmoe, "escm": forward_escm,
+    "cross_stitch": forward_cross_stitch, "hmoe": forward_hmoe, "escm": forward_escm, "aitm": forward_aitm,
 }
 
 
@@ -421,6 +438,7 @@ REG_MODULES = {
     "cross_stitch": ["tower_dnn"],
     "star": [], "pepnet": [],
     "escm": ["ctr_dnn", "cvr_dnn", "ctr_dnn_final_layer", "cvr_dnn_final_layer"],
+    "aitm": ["tower_dnn", "bottom", "tower_dnn_final_layer"],
 }
 REG_MODULES["pcg"] = REG_MODULES["mmoe"]
 

@@ -96,6 +96,12 @@ MASKED = {"ple_ae_t4_masked_adam", "mmoe_movielens_masked_adam"}
 CASES["escm_kuairec_adam"] = ("kuairec_esmm", dict(max_vocab=200), dict(SMALL, model_name="escm"), {})
 CASES["escm_kuairec_sgd"] = ("kuairec_esmm", dict(max_vocab=200), dict(SMALL, model_name="escm"), dict(optimizer="sgd", lr=1e-3))
 INIT_STD.update({"escm_kuairec_adam": 0.05, "escm_kuairec_sgd": 0.05})
+# AITM (aitm.py): h1 / h2 / h3 applied to both tokens (shared weights), feat_0 read by g and by tower 0
+CASES["aitm_kuairec_adam"] = ("kuairec_sharedbottom", dict(max_vocab=200), dict(SMALL, model_name="aitm"), {})
+CASES["aitm_kuairec_notower_l2_sgd"] = ("kuairec_sharedbottom", dict(max_vocab=200),
+                                        dict(SMALL, model_name="aitm", expert_dnn_hidden_units=[32, 40],
+                                             tower_dnn_hidden_units=[], l2_reg_dnn=1e-2), dict(optimizer="sgd", lr=1e-2))
+INIT_STD.update({"aitm_kuairec_adam": 0.05, "aitm_kuairec_notower_l2_sgd": 0.05})
 # cases whose identity / 1e-4 initial state would leave parts of the model untested: perturbed after construction
 INIT_STD.update({"cross_stitch_kuairec_adam": 0.05, "hmoe_kuairec_adam": 0.05, "mlp_kuairec_adam": 0.05,
                  "pcg_kuairec_adam": 0.05, "mmoe_kuairec_l2_adam": 0.05, "ple_ae_t2_l2_sgd": 0.05,
@@ -138,11 +144,12 @@ def build_reference(cfg, fields, init_std=0.0001):
     from model.cross_stitch import CrossStitch
     from model.hmoe import HMOE
     from model.escm import ESCM
+    from model.aitm import AITM
     emb = cfg["model_config"]["emb"]
     cols = [SparseFeat(n, vocabulary_size=v, embedding_dim=emb) if k == "sparse" else DenseFeat(n, 1)
             for n, k, v in fields]
     cls = {"mmoe": MMOE, "ple": PLE, "sharedbottom": SharedBottom, "esmm": ESMM, "star": STAR,
-           "pepnet": PepNet, "mlp": MLP, "cross_stitch": CrossStitch, "hmoe": HMOE, "pcg": MMOE, "escm": ESCM}[cfg["model_config"]["model_name"].lower()]
+           "pepnet": PepNet, "mlp": MLP, "cross_stitch": CrossStitch, "hmoe": HMOE, "pcg": MMOE, "escm": ESCM, "aitm": AITM}[cfg["model_config"]["model_name"].lower()]
     with contextlib.redirect_stdout(io.StringIO()):
         model = cls(cols, init_std=init_std, device="cpu", config=cfg)
         model.compile(optimizer=cfg["optim_config"]["optimizer"], loss=cfg["optim_config"]["loss"],

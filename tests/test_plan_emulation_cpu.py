@@ -1,0 +1,110 @@
+"""CPU: the step PLANNER (engine/core.py) checked without a GPU -- the planned forward + backward program of a model
+is run from its own argument tables by numpy restatements of the kernels' documented semantics
+(tests/plan_emulator.py) and compared with what the REFERENCE produced (tests/golden/*.npz) and with the oracle at
+batches the fixtures do not hold.  Pins the host logic: buffer wiring, strides / operand majors, mask sources,
+assign-vs-accumulate, gradient slices (split-K and shared weights), parameter layout."""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import golden_init, load_golden, make_oracle, rel_err
+from plan_emulator import EmulatedPlan
+
+
+def _model(cfg, fields, precision):
+    from mmlrec_b200.model import get_model_class
+    from mmlrec_b200.model.utils import DenseFeat, SparseFeat
+    cfg = copy.deepcopy(cfg)
+    cfg["b200_config"] = {"precision": precision, "cuda_graph": False}
+    emb = cfg["model_config"]["emb"]
+    cols = [SparseFeat(n, v, emb) if k == "sparse" else DenseFeat(n, 1) for n, k, v in fields]
+    return get_model_class(cfg["model_config"]["model_name"])(cols, device="cpu", config=cfg)
+
+
+def _load(model, z):
+    params, bufs, _ = golden_init(z)
+    model.load_state_dict({**params, **bufs}, strict=True)
+
+
+def _table_grads(model, plan, X):
+    """dense [V, D] table gradients from d(dnn_input) (what K2 would scatter)"""
+    d_in = plan.input_grad()
+    out = {}
+    D = model.emb_dim
+    names = {id(p): n for n, p in model.named_parameters()}
+    for prm, vocab, xc, oc in model.embedding_layout:
+        g = torch.zeros(vocab, D)
+        g.index_add_(0, torch.as_tensor(X[:, xc]).long(), d_in[:, oc:oc + D])
+        out[names[id(prm)]] = g
+    return out
+
+
+CASES = ["sharedbottom_kuairec_adam", "aitm_kuairec_adam", "aitm_kuairec_notower_l2_sgd"]
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("case", CASES)
+def test_planned_step_reproduces_the_reference_golden(case, precision):
+    z, cfg, fields = load_golden(case)
+    cfg["model_config"]["l2_reg_dnn"] = 0    # the regulariser is a separate kernel (GPU tests); gradients below exclude it
+    model = _model(cfg, fields, precision)
+    plan = EmulatedPlan(model, int(z["step0/X"].shape[0]), precision)
+    _load(model, z)
+    plan.build()
+    X, y = z["step0/X"], z["step0/y"]
+    pred, loss = plan.forward_backward(X, y)
+    tol = 1e-5 if precision == "fp32" else 2e-2
+    assert rel_err(pred, z["step0/pred"]) < tol
+    assert abs(float(loss[-1]) - float(z["step0/loss"])) <= tol * abs(float(z["step0/loss"]))
+    # gradients of the data term: the golden's, minus the reference's l2 term 2 * l2 * w where the case has one
+    tr, _, gcfg, _ = make_oracle(case)
+    l2 = gcfg["model_config"].get("l2_reg_dnn", 0)
+    if l2:
+        tr.l2_dnn = 0
+        _, _, want = tr.loss_and_grads(torch.from_numpy(X), torch.from_numpy(y))
+    else:
+        want = {k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("grad0/")}
+    got_all, want_all = [], []
+    for name, prm in model.named_parameters():
+        if getattr(prm, "_mm_kind", "") != "dense" or want.get(name) is None:
+            continue
+        g, w = plan.grad(prm), want[name]
+        got_all.append(g.flatten())
+        want_all.append(w.flatten())
+        if precision == "fp32":
+            assert float((g - w).abs().max()) <= 1e-5 * float(w.abs().max()) + 1e-9, name
+    assert rel_err(torch.cat(got_all), torch.cat(want_all)) < tol
+    for name, g in _table_grads(model, plan, X).items():
+        w = want.get(name)
+        if w is not None and float(w.abs().max()) > 0:
+            # bf16: one field's rows sit behind every bf16-rounded layer of the backward chain (sanity bound only)
+            assert rel_err(g, w) < (1e-5 if precision == "fp32" else 0.1), name
+
+
+@pytest.mark.parametrize("precision,B", [("bf16", 2048), ("fp32", 1024)])
+def test_aitm_plan_at_a_split_k_batch_matches_the_oracle(precision, B):
+    """B = 2048 in bf16 mode: split-K wgrad (2 batch slices) TIMES the two applications of h1 / h2 / h3 = 4 gradient
+    slices; feat_0's gradient accumulated in fp32 and re-quantised for the bottom layer's GEMMs."""
+    from mmlrec_b200 import synthetic
+    tr, z, cfg, fields = make_oracle("aitm_kuairec_adam")
+    model = _model(cfg, fields, precision)
+    plan = EmulatedPlan(model, B, precision)
+    _load(model, z)
+    plan.build()
+    assert plan.grad_slices == (4 if precision == "bf16" else 2)
+    X, y = synthetic.make_batch(cfg, fields, B, seed=7)
+    pred, loss = plan.forward_backward(X, y)
+    want_pred, want_loss, want = tr.loss_and_grads(torch.from_numpy(X), torch.from_numpy(y))
+    tol = 1e-5 if precision == "fp32" else 2e-2
+    assert rel_err(pred, want_pred.detach()) < tol
+    assert abs(float(loss[-1]) - float(want_loss)) <= tol * abs(float(want_loss))
+    got_all, want_all = [], []
+    for name, prm in model.named_parameters():
+        if getattr(prm, "_mm_kind", "") != "dense" or want.get(name) is None:
+            continue
+        got_all.append(plan.grad(prm).flatten())
+        want_all.append(want[name].flatten())
+        assert rel_err(got_all[-1], want_all[-1]) < (1e-5 if precision == "fp32" else 0.1), name
+    assert rel_err(torch.cat(got_all), torch.cat(want_all)) < tol
