@@ -903,6 +903,76 @@ __global__ void aitm_attention_backward_kernel(const float* d_out, int64_t ld_do
   }
 }
 
+// SNR-trans gate (snr_trans.py:9-50): out_i = sum_j z_ij * (x_j @ M_ij) with a hard-concrete scalar per (output i,
+// input j): s = sigmoid(log u - log(1 - u) + log(alpha) / beta), z = clamp(s * (eps - gamma) + gamma, 0, 1).  The
+// trans matrices M_ij [U, U] are constants (the reference keeps them in a plain list: never registered, never
+// updated).  All outputs of the gate are ONE Linear over the concatenated inputs with the derived weight
+//   W_eff[i * U + v][j * U + u] = z_ij * M_ij[u][v]          (nn.Linear layout [n_out * U, n_in * U])
+__device__ __forceinline__ float snr_gate_s(float u, float alpha) {
+  const float logit = logf(u) - logf(1.f - u) + logf(alpha) / 0.9f;
+  return 1.f / (1.f + expf(-logit));
+}
+
+__global__ void snr_gate_weights_kernel(const float* u, const float* alpha, const float* M, int n_out, int n_in, int U,
+                                        float* w_eff, int64_t ld_w, uint16_t* w16) {
+  const int64_t n = (int64_t)n_out * U * n_in * U;
+  const float a = alpha[0];
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int col = (int)(i % (n_in * U));
+    const int row = (int)(i / (n_in * U));
+    const int oi = row / U, v = row - oi * U, ij = col / U, uu = col - ij * U;
+    const float s_ = snr_gate_s(u[oi * n_in + ij], a) * 1.2f - 0.1f;   // eps - gamma = 1.1 + 0.1, gamma = -0.1
+    const float z = fminf(fmaxf(s_, 0.f), 1.f);
+    const float w = z * M[(((int64_t)oi * n_in + ij) * U + uu) * U + v];
+    w_eff[row * ld_w + col] = w;
+    if (w16) w16[row * ld_w + col] = float_to_bf16_bits(w);
+  }
+}
+
+// dz_ij = sum_{u,v} dW_eff[i*U+v][j*U+u] * M_ij[u][v]: one CTA per (i, j)
+__global__ void snr_gate_fold_kernel(const float* d_w_eff, int64_t ld_w, const float* M, int n_in, int U, float* dz) {
+  const int oi = blockIdx.x / n_in, ij = blockIdx.x - oi * n_in;
+  const float* m = M + (int64_t)blockIdx.x * U * U;
+  float acc = 0.f;
+  for (int e = threadIdx.x; e < U * U; e += blockDim.x) {
+    const int v = e / U, uu = e - v * U;            // consecutive threads walk a row of dW_eff
+    acc = fmaf(d_w_eff[(int64_t)(oi * U + v) * ld_w + ij * U + uu], m[(int64_t)uu * U + v], acc);
+  }
+  __shared__ float part[32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) dz[blockIdx.x] = t;
+  }
+}
+
+// chain rule through the hard-concrete gate: the clamp passes a gradient where 0 < s' <= 1 (snr_trans.py:41-44)
+__global__ void snr_gate_chain_kernel(const float* dz, const float* u, const float* alpha, int n, float* d_u,
+                                      float* d_alpha) {
+  const float a = alpha[0];
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const float uu = u[i];
+    const float s = snr_gate_s(uu, a);
+    const float s_ = s * 1.2f - 0.1f;
+    const float dlogit = (s_ > 0.f && s_ <= 1.f) ? dz[i] * 1.2f * s * (1.f - s) : 0.f;
+    d_u[i] = dlogit * (1.f / uu + 1.f / (1.f - uu));
+    acc += dlogit;
+  }
+  __shared__ float part[32];
+  acc = warp_sum(acc);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? part[threadIdx.x] : 0.f;
+    t = warp_sum(t);
+    if (threadIdx.x == 0) d_alpha[0] = t / (a * 0.9f);
+  }
+}
+
 // i indexes (t, n, k) of w_eff [T*N, ld_w]; spec[t] and shared are [K, N] row-major
 __global__ void star_weights_kernel(const int64_t* spec_ptrs, const int64_t* spec_b_ptrs, const float* shared,
                                     const float* shared_b, int T, int K, int N, float* w_eff, int64_t ld_w,
@@ -1301,6 +1371,25 @@ extern "C" int mmlrec_aitm_attention_backward(const float* d_out, int64_t ld_dou
   MMLREC_CHECK_ARG(d_out && vkq && attn && (d_vkq_f32 || d_vkq_bf16), "null buffer");
   aitm_attention_backward_kernel<<<grid_for((int64_t)rows * 32), 256, 0, (cudaStream_t)stream>>>(
       d_out, ld_dout, vkq, ld, attn, rows, H, sqrtf((float)H), d_vkq_f32, d_vkq_bf16, ld_d);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_snr_gate_weights(const float* u, const float* alpha, const float* trans, int32_t n_out, int32_t n_in,
+                                       int32_t U, float* w_eff, int64_t ld_w, uint16_t* w_eff_bf16, void* stream) {
+  MMLREC_CHECK_ARG(u && alpha && trans && w_eff && n_out > 0 && n_in > 0 && U > 0, "bad argument");
+  snr_gate_weights_kernel<<<grid_for((int64_t)n_out * U * n_in * U), 256, 0, (cudaStream_t)stream>>>(
+      u, alpha, trans, n_out, n_in, U, w_eff, ld_w, w_eff_bf16);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_snr_gate_fold(const float* d_w_eff, int64_t ld_w, const float* trans, const float* u,
+                                    const float* alpha, int32_t n_out, int32_t n_in, int32_t U, float* dz_scratch,
+                                    float* d_u, float* d_alpha, void* stream) {
+  MMLREC_CHECK_ARG(d_w_eff && trans && u && alpha && dz_scratch && d_u && d_alpha && n_out > 0 && n_in > 0 && U > 0,
+                   "bad argument");
+  snr_gate_fold_kernel<<<n_out * n_in, 256, 0, (cudaStream_t)stream>>>(d_w_eff, ld_w, trans, n_in, U, dz_scratch);
+  MMLREC_CHECK_LAUNCH(1);
+  snr_gate_chain_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(dz_scratch, u, alpha, n_out * n_in, d_u, d_alpha);
   MMLREC_RETURN_LAUNCH(1);
 }
 

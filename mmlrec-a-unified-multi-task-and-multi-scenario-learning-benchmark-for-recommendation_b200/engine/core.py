@@ -1085,12 +1085,43 @@ class StarWeightStage(Stage):
                     f"star fold {self.label}")
 
 
+class SnrGateStage(Stage):
+    """SNR-trans gate (snr_trans.py:9-50) as a derived weight: ``out_i = sum_j z_ij (x_j @ M_ij)`` for all i is ONE Linear
+    over the concatenated inputs with ``W_eff[i*U+v, j*U+u] = z_ij M_ij[u, v]``, rebuilt every step from the trained
+    hard-concrete parameters (``u``, ``alpha``) and the constant trans matrices; an ordinary LinearStage applies it, and
+    this stage's backward folds d(W_eff) into d(u), d(alpha)."""
+    name = "snr_gate"
+
+    def __init__(self, b: Builder, gate: nn.Module, label: str = ""):
+        self.b, self.gate, self.label = b, gate, label
+        b.note_params([gate.alpha, gate.u])
+        self.n_out, self.n_in, self.U = gate.output_dim, gate.input_dim, gate.units
+        w = b.aux_matrix(self.n_out * self.U, self.n_in * self.U)
+        self.derived = _DryLinear(self.n_out * self.U, self.n_in * self.U, bias=False) if b.dry else DerivedLinear(w, None)
+
+    def finalize(self):
+        self.dz = self.b.zeros(self.n_out * self.n_in)
+
+    def forward(self, stream, training):
+        b, st, g, w = self.b, self.b.store, self.gate, self.derived.weight
+        L.check(b.lib.mmlrec_snr_gate_weights(g.u.data_ptr(), g.alpha.data_ptr(), g.trans_matrix.data_ptr(), self.n_out,
+                                              self.n_in, self.U, w.data_ptr(), w._mm_ld,
+                                              st.bf16_ptr(w) if st.dense_bf16 is not None else None, stream),
+                f"snr gate weights {self.label}")
+
+    def backward(self, stream):
+        b, st, g, w = self.b, self.b.store, self.gate, self.derived.weight
+        L.check(b.lib.mmlrec_snr_gate_fold(st.grad_ptr(w), w._mm_ld, g.trans_matrix.data_ptr(), g.u.data_ptr(),
+                                           g.alpha.data_ptr(), self.n_out, self.n_in, self.U, self.dz.data_ptr(),
+                                           st.grad_ptr(g.u), st.grad_ptr(g.alpha), stream), f"snr gate fold {self.label}")
+
+
 class _DryLinear:
     """Shape-only stand-in used while recording the parameter order."""
 
-    def __init__(self, n, k):
+    def __init__(self, n, k, bias=True):
         self.weight = _DryTensor((n, k))
-        self.bias = _DryTensor((n,))
+        self.bias = _DryTensor((n,)) if bias else None
 
 
 class _DryTensor:

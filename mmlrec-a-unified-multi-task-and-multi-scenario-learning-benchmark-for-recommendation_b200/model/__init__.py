@@ -1,5 +1,5 @@
 """Model zoo on the fused step program.  ``get_model`` mirrors ``main.py:37-68`` of the reference
-(case-insensitive names); the families outside the fused step (snr_trans, mssm, apg) raise ``NotImplementedError`` by name."""
+(case-insensitive names); the families outside the fused step (mssm, apg) raise ``NotImplementedError`` by name."""
 from .aitm import AITM
 from .cross_stitch import CrossStitch
 from .escm import ESCM
@@ -10,10 +10,11 @@ from .mmoe import MMOE
 from .pepnet import PepNet
 from .ple import PLE
 from .sharedbottom import SharedBottom
+from .snr_trans import SNR_trans
 from .star import STAR
 
 _REGISTRY = {"mmoe": MMOE, "ple": PLE, "sharedbottom": SharedBottom, "esmm": ESMM, "star": STAR, "pepnet": PepNet,
-             "mlp": MLP, "cross_stitch": CrossStitch, "hmoe": HMOE, "escm": ESCM, "aitm": AITM,
+             "mlp": MLP, "cross_stitch": CrossStitch, "hmoe": HMOE, "escm": ESCM, "aitm": AITM, "snr_trans": SNR_trans,
              # main.py:53-54 builds an MMOE for 'pcg' and wraps its optimizer in PCGrad (basemodel.py:564-565).  The loop
              # hands pc_backward ONE objective -- the summed loss (basemodel.py:309-310) -- so the projection is the
              # identity and the step is MMoE's (pinned by the golden case pcg_kuairec_adam)

@@ -6,7 +6,7 @@ library is missing instead of falling back to anything here).
 
 What it is: a *functional* restatement, in plain fp32 PyTorch on the CPU, of the reference's
 step body (``/root/reference/model/basemodel.py:262-313``): multi-field gather + concat, the
-expert / gate / tower networks of eleven model families, sigmoid + BCE(sum), backward and the
+expert / gate / tower networks of twelve model families, sigmoid + BCE(sum), backward and the
 ``torch.optim`` step.  All arithmetic of the reference lives in the third-party module ``torch``
 (reference prose pins "PyTorch 1.11.0", ``README.md:52``; no lock file; operative version in
 this image: torch 2.11.0+cu128), so the restatement calls the same ATen ops in the same order.
@@ -180,6 +180,7 @@ class Spec:
         self.specific_n = mc.get("specific_expert_num", 3)
         self.levels = mc.get("num_levels", 1)
         self.gate_units = mc.get("gate_dnn_hidden_units", [64])
+        self.expert_units = mc.get("expert_dnn_hidden_units", [256, 128])
         self.tower_units = mc.get("tower_dnn_hidden_units", [64])
         self.dnn_units = mc.get("dnn_hidden_units", [256, 128])
         self.use_shared = mc.get("use_shared", True)
@@ -415,10 +416,38 @@ def forward_aitm(p: Params, b: Params, s: Spec, X: Tensor, training: bool) -> Te
     return _towers(p, b, s, feat, training)
 
 
+def _snr_gate(p: Params, prefix: str, xs: List[Tensor], n_out: int) -> List[Tensor]:
+    """snr_trans.py:36-50: hard-concrete connection scalars z [n_out, n_in] from (u, alpha); out_i = sum_j z_ij * (x_j @ M_ij).
+    The transformation matrices ``<prefix>.trans_matrix.<i>.<j>`` are unregistered constants in the reference."""
+    u, alpha = p[f"{prefix}.u"], p[f"{prefix}.alpha"]
+    s = torch.sigmoid(torch.log(u) - torch.log(1 - u) + torch.log(alpha) / 0.9)
+    s_ = s * (1.1 - -0.1) + -0.1
+    z = (s_ > 0).float() * s_
+    z = (z > 1).float() + (z <= 1).float() * z
+    outs = []
+    for i in range(n_out):
+        o = torch.stack([torch.matmul(xs[j], p[f"{prefix}.trans_matrix.{i}.{j}"]) * z[i][j] for j in range(len(xs))], 1)
+        outs.append(o.sum(1))
+    return outs
+
+
+def forward_snr_trans(p: Params, b: Params, s: Spec, X: Tensor, training: bool) -> Tensor:
+    """model/snr_trans.py:120-156: per level E single-layer experts (level 0 on dnn_input, level l on mixed feature j),
+    then the gate; the last gate has one output per task."""
+    x = gather_concat(X, p, s.columns)
+    feats = [x] * s.num_experts
+    levels = len(s.expert_units)
+    for l in range(levels):
+        outs = [mlp(p, b, f"trans.trans{l + 1}.{j}", feats[j], s.use_bn, training, s.act) for j in range(s.num_experts)]
+        feats = _snr_gate(p, f"trans.gate{l + 1}", outs, s.num_tasks if l == levels - 1 else s.num_experts)
+    return _towers(p, b, s, feats, training)
+
+
 FORWARDS = {
     "mmoe": forward_mmoe, "pcg": forward_mmoe, "ple": forward_ple, "sharedbottom": forward_sharedbottom,
     "esmm": forward_esmm, "star": forward_star, "pepnet": forward_pepnet, "mlp": forward_mlp,
     "cross_stitch": forward_cross_stitch, "hmoe": forward_hmoe, "escm": forward_escm, "aitm": forward_aitm,
+    "snr_trans": forward_snr_trans,
 }
 
 
@@ -439,6 +468,7 @@ REG_MODULES = {
     "star": [], "pepnet": [],
     "escm": ["ctr_dnn", "cvr_dnn", "ctr_dnn_final_layer", "cvr_dnn_final_layer"],
     "aitm": ["tower_dnn", "bottom", "tower_dnn_final_layer"],
+    "snr_trans": ["tower_dnn"],
 }
 REG_MODULES["pcg"] = REG_MODULES["mmoe"]
 

@@ -102,6 +102,12 @@ CASES["aitm_kuairec_notower_l2_sgd"] = ("kuairec_sharedbottom", dict(max_vocab=2
                                         dict(SMALL, model_name="aitm", expert_dnn_hidden_units=[32, 40],
                                              tower_dnn_hidden_units=[], l2_reg_dnn=1e-2), dict(optimizer="sgd", lr=1e-2))
 INIT_STD.update({"aitm_kuairec_adam": 0.05, "aitm_kuairec_notower_l2_sgd": 0.05})
+# SNR-trans (snr_trans.py): hard-concrete gates over unregistered (constant) transformation matrices
+CASES["snr_trans_kuairec_adam"] = ("kuairec_sharedbottom", dict(max_vocab=200), dict(SMALL, model_name="snr_trans"), {})
+CASES["snr_trans_kuairec_1level_sgd"] = ("kuairec_sharedbottom", dict(max_vocab=200),
+                                         dict(SMALL, model_name="snr_trans", expert_dnn_hidden_units=[24], num_experts=3,
+                                              tower_dnn_hidden_units=[]), dict(optimizer="sgd", lr=1e-2))
+INIT_STD.update({"snr_trans_kuairec_adam": 0.05, "snr_trans_kuairec_1level_sgd": 0.05})
 # cases whose identity / 1e-4 initial state would leave parts of the model untested: perturbed after construction
 INIT_STD.update({"cross_stitch_kuairec_adam": 0.05, "hmoe_kuairec_adam": 0.05, "mlp_kuairec_adam": 0.05,
                  "pcg_kuairec_adam": 0.05, "mmoe_kuairec_l2_adam": 0.05, "ple_ae_t2_l2_sgd": 0.05,
@@ -145,11 +151,12 @@ def build_reference(cfg, fields, init_std=0.0001):
     from model.hmoe import HMOE
     from model.escm import ESCM
     from model.aitm import AITM
+    from model.snr_trans import SNR_trans
     emb = cfg["model_config"]["emb"]
     cols = [SparseFeat(n, vocabulary_size=v, embedding_dim=emb) if k == "sparse" else DenseFeat(n, 1)
             for n, k, v in fields]
     cls = {"mmoe": MMOE, "ple": PLE, "sharedbottom": SharedBottom, "esmm": ESMM, "star": STAR,
-           "pepnet": PepNet, "mlp": MLP, "cross_stitch": CrossStitch, "hmoe": HMOE, "pcg": MMOE, "escm": ESCM, "aitm": AITM}[cfg["model_config"]["model_name"].lower()]
+           "pepnet": PepNet, "mlp": MLP, "cross_stitch": CrossStitch, "hmoe": HMOE, "pcg": MMOE, "escm": ESCM, "aitm": AITM, "snr_trans": SNR_trans}[cfg["model_config"]["model_name"].lower()]
     with contextlib.redirect_stdout(io.StringIO()):
         model = cls(cols, init_std=init_std, device="cpu", config=cfg)
         model.compile(optimizer=cfg["optim_config"]["optimizer"], loss=cfg["optim_config"]["loss"],
@@ -161,6 +168,13 @@ def unregistered_star_tensors(model):
     """SharedSpecificLinear keeps all but the last per-domain weight outside ``named_parameters``
     (model/utils.py:181-191); export them so the oracle can treat them as constants."""
     extra = {}
+    if type(model).__name__ == "SNR_trans":   # gate.trans_matrix: a plain list of lists of Parameters (snr_trans.py:31-34)
+        for name, mod in model.trans.items():
+            if name.startswith("gate"):
+                for i, row in enumerate(mod.trans_matrix):
+                    for j, m in enumerate(row):
+                        extra[f"trans.{name}.trans_matrix.{i}.{j}"] = m.detach().clone()
+        return extra
     if type(model).__name__ != "STAR":
         return extra
     for prefix, mods in (("linears", model.linears), ("final_layers", model.final_layers)):

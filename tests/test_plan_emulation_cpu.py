@@ -25,7 +25,12 @@ def _model(cfg, fields, precision):
 
 def _load(model, z):
     params, bufs, _ = golden_init(z)
-    model.load_state_dict({**params, **bufs}, strict=True)
+    sd = {**params, **bufs}
+    own = model.state_dict()
+    model.load_state_dict({k: v for k, v in sd.items() if k in own}, strict=True)
+    extra = {k: v for k, v in sd.items() if k not in own}   # the reference's unregistered tensors (SNR-trans matrices)
+    if extra:
+        model.load_unregistered(extra)
 
 
 def _table_grads(model, plan, X):
@@ -41,7 +46,8 @@ def _table_grads(model, plan, X):
     return out
 
 
-CASES = ["sharedbottom_kuairec_adam", "aitm_kuairec_adam", "aitm_kuairec_notower_l2_sgd"]
+CASES = ["sharedbottom_kuairec_adam", "aitm_kuairec_adam", "aitm_kuairec_notower_l2_sgd", "snr_trans_kuairec_adam",
+         "snr_trans_kuairec_1level_sgd"]
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
