@@ -507,16 +507,19 @@ int mmlrec_aitm_attention_forward(const float* vkq, int64_t ld, int32_t rows, in
 int mmlrec_aitm_attention_backward(const float* d_out, int64_t ld_dout, const float* vkq, int64_t ld, const float* attn,
                                    int32_t rows, int32_t H, float* d_vkq_f32, uint16_t* d_vkq_bf16, int64_t ld_d,
                                    void* stream);
-/* SNR-trans gate (reference model/snr_trans.py:9-50): out_i = sum_j z_ij * (x_j @ M_ij), z_ij the hard-concrete scalar of
- * (u_ij, alpha): s = sigmoid(log u - log(1-u) + log(alpha)/0.9), z = clamp(1.2 s - 0.1, 0, 1).  u [n_out, n_in], alpha [1],
- * trans [n_out, n_in, U, U] (constants).  Derived weight in nn.Linear layout over the concatenated inputs:
- *   w_eff[i*U + v, j*U + u] = z_ij * trans[i][j][u][v]        (fp32 + optional bf16 shadow, same ld) */
+/* SNR-trans / MSSM gate (reference model/snr_trans.py:9-50, model/mssm.py:9-60): out_i = sum_j z_ij * (x_j @ M_ij), z_ij the
+ * hard-concrete gate of (u_ij, alpha): s = sigmoid(log u - log(1-u) + log(alpha)/0.9), z = clamp(1.2 s - 0.1, 0, 1).
+ * zdim = 1 (SNR-trans): u [n_out, n_in], one scalar per connection; zdim = U (MSSM): u [n_out, n_in, U], one gate per
+ * output unit v of the connection.  alpha [1], trans [n_out, n_in, U, U] (constants).  Derived weight in nn.Linear layout
+ * over the concatenated inputs:
+ *   w_eff[i*U + v, j*U + u] = z_ij[v] * trans[i][j][u][v]        (fp32 + optional bf16 shadow, same ld) */
 int mmlrec_snr_gate_weights(const float* u, const float* alpha, const float* trans, int32_t n_out, int32_t n_in, int32_t U,
-                            float* w_eff, int64_t ld_w, uint16_t* w_eff_bf16, void* stream);
-/* d_u, d_alpha (assigned) from d(w_eff); dz_scratch: n_out * n_in floats */
+                            int32_t zdim, float* w_eff, int64_t ld_w, uint16_t* w_eff_bf16, void* stream);
+/* d_u (assigned; NULL where u is a constant: MSSM, mssm.py:27-29 keeps it in a plain list), d_alpha (assigned) from
+ * d(w_eff); dz_scratch: n_out * n_in * zdim floats */
 int mmlrec_snr_gate_fold(const float* d_w_eff, int64_t ld_w, const float* trans, const float* u, const float* alpha,
-                         int32_t n_out, int32_t n_in, int32_t U, float* dz_scratch, float* d_u, float* d_alpha,
-                         void* stream);
+                         int32_t n_out, int32_t n_in, int32_t U, int32_t zdim, float* dz_scratch, float* d_u,
+                         float* d_alpha, void* stream);
 /* STAR: effective weights of all T domains in nn.Linear layout:
  *   w_eff[t*N + n, k] = spec[t][k, n] * shared[k, n];  b_eff[t*N + n] = spec_b[t][n] + shared_b[n]
  * spec / spec_b: T device pointers (int64 array on device); bf16 shadow optional. */

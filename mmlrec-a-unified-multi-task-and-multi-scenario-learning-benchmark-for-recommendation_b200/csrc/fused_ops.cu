@@ -903,25 +903,27 @@ __global__ void aitm_attention_backward_kernel(const float* d_out, int64_t ld_do
   }
 }
 
-// SNR-trans gate (snr_trans.py:9-50): out_i = sum_j z_ij * (x_j @ M_ij) with a hard-concrete scalar per (output i,
-// input j): s = sigmoid(log u - log(1 - u) + log(alpha) / beta), z = clamp(s * (eps - gamma) + gamma, 0, 1).  The
-// trans matrices M_ij [U, U] are constants (the reference keeps them in a plain list: never registered, never
-// updated).  All outputs of the gate are ONE Linear over the concatenated inputs with the derived weight
-//   W_eff[i * U + v][j * U + u] = z_ij * M_ij[u][v]          (nn.Linear layout [n_out * U, n_in * U])
+// SNR-trans / MSSM gate (snr_trans.py:9-50, mssm.py:9-60): out_i = sum_j z_ij * (x_j @ M_ij) with a hard-concrete gate
+// per (output i, input j): s = sigmoid(log u - log(1 - u) + log(alpha) / beta), z = clamp(s * (eps - gamma) + gamma, 0, 1).
+// SNR-trans: u, z are scalars per connection (Z = 1, u trained); MSSM: vectors over the output unit v (Z = U, u a
+// constant: the reference keeps it in a plain list).  The trans matrices M_ij [U, U] are constants in both (never
+// registered, never updated).  All outputs of the gate are ONE Linear over the concatenated inputs with the derived weight
+//   W_eff[i * U + v][j * U + u] = z_ij[v] * M_ij[u][v]          (nn.Linear layout [n_out * U, n_in * U])
 __device__ __forceinline__ float snr_gate_s(float u, float alpha) {
   const float logit = logf(u) - logf(1.f - u) + logf(alpha) / 0.9f;
   return 1.f / (1.f + expf(-logit));
 }
 
 __global__ void snr_gate_weights_kernel(const float* u, const float* alpha, const float* M, int n_out, int n_in, int U,
-                                        float* w_eff, int64_t ld_w, uint16_t* w16) {
+                                        int Z, float* w_eff, int64_t ld_w, uint16_t* w16) {
   const int64_t n = (int64_t)n_out * U * n_in * U;
   const float a = alpha[0];
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const int col = (int)(i % (n_in * U));
     const int row = (int)(i / (n_in * U));
     const int oi = row / U, v = row - oi * U, ij = col / U, uu = col - ij * U;
-    const float s_ = snr_gate_s(u[oi * n_in + ij], a) * 1.2f - 0.1f;   // eps - gamma = 1.1 + 0.1, gamma = -0.1
+    const float ug = u[(int64_t)(oi * n_in + ij) * Z + (Z > 1 ? v : 0)];
+    const float s_ = snr_gate_s(ug, a) * 1.2f - 0.1f;   // eps - gamma = 1.1 + 0.1, gamma = -0.1
     const float z = fminf(fmaxf(s_, 0.f), 1.f);
     const float w = z * M[(((int64_t)oi * n_in + ij) * U + uu) * U + v];
     w_eff[row * ld_w + col] = w;
@@ -929,10 +931,22 @@ __global__ void snr_gate_weights_kernel(const float* u, const float* alpha, cons
   }
 }
 
-// dz_ij = sum_{u,v} dW_eff[i*U+v][j*U+u] * M_ij[u][v]: one CTA per (i, j)
-__global__ void snr_gate_fold_kernel(const float* d_w_eff, int64_t ld_w, const float* M, int n_in, int U, float* dz) {
+// Z = 1: dz_ij = sum_{u,v} dW_eff[i*U+v][j*U+u] * M_ij[u][v]; Z = U: dz_ij[v] = sum_u (same term).  One CTA per (i, j).
+__global__ void snr_gate_fold_kernel(const float* d_w_eff, int64_t ld_w, const float* M, int n_in, int U, int Z,
+                                     float* dz) {
   const int oi = blockIdx.x / n_in, ij = blockIdx.x - oi * n_in;
   const float* m = M + (int64_t)blockIdx.x * U * U;
+  if (Z > 1) {   // a warp per output unit v, lanes over u, fixed order
+    const int lane = threadIdx.x & 31;
+    for (int v = threadIdx.x >> 5; v < U; v += blockDim.x >> 5) {
+      float acc = 0.f;
+      for (int uu = lane; uu < U; uu += 32)
+        acc = fmaf(d_w_eff[(int64_t)(oi * U + v) * ld_w + ij * U + uu], m[(int64_t)uu * U + v], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) dz[(int64_t)blockIdx.x * U + v] = acc;
+    }
+    return;
+  }
   float acc = 0.f;
   for (int e = threadIdx.x; e < U * U; e += blockDim.x) {
     const int v = e / U, uu = e - v * U;            // consecutive threads walk a row of dW_eff
@@ -959,7 +973,7 @@ __global__ void snr_gate_chain_kernel(const float* dz, const float* u, const flo
     const float s = snr_gate_s(uu, a);
     const float s_ = s * 1.2f - 0.1f;
     const float dlogit = (s_ > 0.f && s_ <= 1.f) ? dz[i] * 1.2f * s * (1.f - s) : 0.f;
-    d_u[i] = dlogit * (1.f / uu + 1.f / (1.f - uu));
+    if (d_u) d_u[i] = dlogit * (1.f / uu + 1.f / (1.f - uu));   // MSSM's u is a constant: no d_u
     acc += dlogit;
   }
   __shared__ float part[32];
@@ -1375,21 +1389,24 @@ extern "C" int mmlrec_aitm_attention_backward(const float* d_out, int64_t ld_dou
 }
 
 extern "C" int mmlrec_snr_gate_weights(const float* u, const float* alpha, const float* trans, int32_t n_out, int32_t n_in,
-                                       int32_t U, float* w_eff, int64_t ld_w, uint16_t* w_eff_bf16, void* stream) {
+                                       int32_t U, int32_t zdim, float* w_eff, int64_t ld_w, uint16_t* w_eff_bf16,
+                                       void* stream) {
   MMLREC_CHECK_ARG(u && alpha && trans && w_eff && n_out > 0 && n_in > 0 && U > 0, "bad argument");
+  MMLREC_CHECK_ARG(zdim == 1 || zdim == U, "zdim must be 1 (SNR-trans) or U (MSSM)");
   snr_gate_weights_kernel<<<grid_for((int64_t)n_out * U * n_in * U), 256, 0, (cudaStream_t)stream>>>(
-      u, alpha, trans, n_out, n_in, U, w_eff, ld_w, w_eff_bf16);
+      u, alpha, trans, n_out, n_in, U, zdim, w_eff, ld_w, w_eff_bf16);
   MMLREC_RETURN_LAUNCH(1);
 }
 
 extern "C" int mmlrec_snr_gate_fold(const float* d_w_eff, int64_t ld_w, const float* trans, const float* u,
-                                    const float* alpha, int32_t n_out, int32_t n_in, int32_t U, float* dz_scratch,
-                                    float* d_u, float* d_alpha, void* stream) {
-  MMLREC_CHECK_ARG(d_w_eff && trans && u && alpha && dz_scratch && d_u && d_alpha && n_out > 0 && n_in > 0 && U > 0,
+                                    const float* alpha, int32_t n_out, int32_t n_in, int32_t U, int32_t zdim,
+                                    float* dz_scratch, float* d_u, float* d_alpha, void* stream) {
+  MMLREC_CHECK_ARG(d_w_eff && trans && u && alpha && dz_scratch && d_alpha && n_out > 0 && n_in > 0 && U > 0,
                    "bad argument");
-  snr_gate_fold_kernel<<<n_out * n_in, 256, 0, (cudaStream_t)stream>>>(d_w_eff, ld_w, trans, n_in, U, dz_scratch);
+  MMLREC_CHECK_ARG(zdim == 1 || zdim == U, "zdim must be 1 (SNR-trans) or U (MSSM)");
+  snr_gate_fold_kernel<<<n_out * n_in, 256, 0, (cudaStream_t)stream>>>(d_w_eff, ld_w, trans, n_in, U, zdim, dz_scratch);
   MMLREC_CHECK_LAUNCH(1);
-  snr_gate_chain_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(dz_scratch, u, alpha, n_out * n_in, d_u, d_alpha);
+  snr_gate_chain_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(dz_scratch, u, alpha, n_out * n_in * zdim, d_u, d_alpha);
   MMLREC_RETURN_LAUNCH(1);
 }
 

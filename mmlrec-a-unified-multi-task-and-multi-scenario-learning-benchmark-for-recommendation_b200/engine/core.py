@@ -1094,26 +1094,30 @@ class SnrGateStage(Stage):
 
     def __init__(self, b: Builder, gate: nn.Module, label: str = ""):
         self.b, self.gate, self.label = b, gate, label
-        b.note_params([gate.alpha, gate.u])
+        # SNR-trans trains u [n_out, n_in]; MSSM's u [n_out, n_in, U] is an unregistered constant (mssm.py:27-29)
+        self.u_trained = isinstance(gate.u, nn.Parameter)
+        b.note_params([gate.alpha, gate.u] if self.u_trained else [gate.alpha])
         self.n_out, self.n_in, self.U = gate.output_dim, gate.input_dim, gate.units
+        self.zdim = self.U if gate.u.dim() == 3 else 1
         w = b.aux_matrix(self.n_out * self.U, self.n_in * self.U)
         self.derived = _DryLinear(self.n_out * self.U, self.n_in * self.U, bias=False) if b.dry else DerivedLinear(w, None)
 
     def finalize(self):
-        self.dz = self.b.zeros(self.n_out * self.n_in)
+        self.dz = self.b.zeros(self.n_out * self.n_in * self.zdim)
 
     def forward(self, stream, training):
         b, st, g, w = self.b, self.b.store, self.gate, self.derived.weight
         L.check(b.lib.mmlrec_snr_gate_weights(g.u.data_ptr(), g.alpha.data_ptr(), g.trans_matrix.data_ptr(), self.n_out,
-                                              self.n_in, self.U, w.data_ptr(), w._mm_ld,
+                                              self.n_in, self.U, self.zdim, w.data_ptr(), w._mm_ld,
                                               st.bf16_ptr(w) if st.dense_bf16 is not None else None, stream),
                 f"snr gate weights {self.label}")
 
     def backward(self, stream):
         b, st, g, w = self.b, self.b.store, self.gate, self.derived.weight
         L.check(b.lib.mmlrec_snr_gate_fold(st.grad_ptr(w), w._mm_ld, g.trans_matrix.data_ptr(), g.u.data_ptr(),
-                                           g.alpha.data_ptr(), self.n_out, self.n_in, self.U, self.dz.data_ptr(),
-                                           st.grad_ptr(g.u), st.grad_ptr(g.alpha), stream), f"snr gate fold {self.label}")
+                                           g.alpha.data_ptr(), self.n_out, self.n_in, self.U, self.zdim,
+                                           self.dz.data_ptr(), st.grad_ptr(g.u) if self.u_trained else None,
+                                           st.grad_ptr(g.alpha), stream), f"snr gate fold {self.label}")
 
 
 class _DryLinear:

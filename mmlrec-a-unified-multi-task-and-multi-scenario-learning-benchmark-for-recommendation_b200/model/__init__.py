@@ -1,5 +1,5 @@
 """Model zoo on the fused step program.  ``get_model`` mirrors ``main.py:37-68`` of the reference
-(case-insensitive names); the families outside the fused step (mssm, apg) raise ``NotImplementedError`` by name."""
+(case-insensitive names); the family outside the fused step (apg) raises ``NotImplementedError`` by name."""
 from .aitm import AITM
 from .cross_stitch import CrossStitch
 from .escm import ESCM
@@ -7,6 +7,7 @@ from .esmm import ESMM
 from .hmoe import HMOE
 from .mlp import MLP
 from .mmoe import MMOE
+from .mssm import MSSM
 from .pepnet import PepNet
 from .ple import PLE
 from .sharedbottom import SharedBottom
@@ -15,6 +16,7 @@ from .star import STAR
 
 _REGISTRY = {"mmoe": MMOE, "ple": PLE, "sharedbottom": SharedBottom, "esmm": ESMM, "star": STAR, "pepnet": PepNet,
              "mlp": MLP, "cross_stitch": CrossStitch, "hmoe": HMOE, "escm": ESCM, "aitm": AITM, "snr_trans": SNR_trans,
+             "mssm": MSSM,
              # main.py:53-54 builds an MMOE for 'pcg' and wraps its optimizer in PCGrad (basemodel.py:564-565).  The loop
              # hands pc_backward ONE objective -- the summed loss (basemodel.py:309-310) -- so the projection is the
              # identity and the step is MMoE's (pinned by the golden case pcg_kuairec_adam)

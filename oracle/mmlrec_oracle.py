@@ -417,13 +417,22 @@ def forward_aitm(p: Params, b: Params, s: Spec, X: Tensor, training: bool) -> Te
 
 
 def _snr_gate(p: Params, prefix: str, xs: List[Tensor], n_out: int) -> List[Tensor]:
-    """snr_trans.py:36-50: hard-concrete connection scalars z [n_out, n_in] from (u, alpha); out_i = sum_j z_ij * (x_j @ M_ij).
+    """snr_trans.py:36-50 / mssm.py:38-60: hard-concrete gates z from (u, alpha) -- a scalar per connection [n_out, n_in]
+    (SNR-trans) or a vector over the output units [n_out, n_in, U] (MSSM); out_i = sum_j (x_j @ M_ij) * z_ij.
     The transformation matrices ``<prefix>.trans_matrix.<i>.<j>`` are unregistered constants in the reference."""
-    u, alpha = p[f"{prefix}.u"], p[f"{prefix}.alpha"]
-    s = torch.sigmoid(torch.log(u) - torch.log(1 - u) + torch.log(alpha) / 0.9)
-    s_ = s * (1.1 - -0.1) + -0.1
-    z = (s_ > 0).float() * s_
-    z = (z > 1).float() + (z <= 1).float() * z
+    alpha = p[f"{prefix}.alpha"]
+
+    def hard_concrete(u):
+        s = torch.sigmoid(torch.log(u) - torch.log(1 - u) + torch.log(alpha) / 0.9)
+        s_ = s * (1.1 - -0.1) + -0.1
+        z = (s_ > 0).float() * s_
+        return (z > 1).float() + (z <= 1).float() * z
+
+    if f"{prefix}.u" in p:
+        z = hard_concrete(p[f"{prefix}.u"])
+    else:   # mssm.py:26-29, :40-50: one [U] vector of gate logits per connection (unregistered constants like the
+        # matrices), each pushed through the gate separately -- d(alpha) accumulates connection by connection
+        z = [[hard_concrete(p[f"{prefix}.u.{i}.{j}"]) for j in range(len(xs))] for i in range(n_out)]
     outs = []
     for i in range(n_out):
         o = torch.stack([torch.matmul(xs[j], p[f"{prefix}.trans_matrix.{i}.{j}"]) * z[i][j] for j in range(len(xs))], 1)
@@ -443,11 +452,22 @@ def forward_snr_trans(p: Params, b: Params, s: Spec, X: Tensor, training: bool) 
     return _towers(p, b, s, feats, training)
 
 
+def forward_mssm(p: Params, b: Params, s: Spec, X: Tensor, training: bool) -> Tensor:
+    """model/mssm.py:140-179: SNR-trans's level structure under the names ``mssm.expert<l>.<j>`` / ``mssm.gate<l>``."""
+    x = gather_concat(X, p, s.columns)
+    feats = [x] * s.num_experts
+    levels = len(s.expert_units)
+    for l in range(levels):
+        outs = [mlp(p, b, f"mssm.expert{l + 1}.{j}", feats[j], s.use_bn, training, s.act) for j in range(s.num_experts)]
+        feats = _snr_gate(p, f"mssm.gate{l + 1}", outs, s.num_tasks if l == levels - 1 else s.num_experts)
+    return _towers(p, b, s, feats, training)
+
+
 FORWARDS = {
     "mmoe": forward_mmoe, "pcg": forward_mmoe, "ple": forward_ple, "sharedbottom": forward_sharedbottom,
     "esmm": forward_esmm, "star": forward_star, "pepnet": forward_pepnet, "mlp": forward_mlp,
     "cross_stitch": forward_cross_stitch, "hmoe": forward_hmoe, "escm": forward_escm, "aitm": forward_aitm,
-    "snr_trans": forward_snr_trans,
+    "snr_trans": forward_snr_trans, "mssm": forward_mssm,
 }
 
 
@@ -469,6 +489,7 @@ REG_MODULES = {
     "escm": ["ctr_dnn", "cvr_dnn", "ctr_dnn_final_layer", "cvr_dnn_final_layer"],
     "aitm": ["tower_dnn", "bottom", "tower_dnn_final_layer"],
     "snr_trans": ["tower_dnn"],
+    "mssm": ["tower_dnn"],
 }
 REG_MODULES["pcg"] = REG_MODULES["mmoe"]
 

@@ -108,6 +108,12 @@ CASES["snr_trans_kuairec_1level_sgd"] = ("kuairec_sharedbottom", dict(max_vocab=
                                          dict(SMALL, model_name="snr_trans", expert_dnn_hidden_units=[24], num_experts=3,
                                               tower_dnn_hidden_units=[]), dict(optimizer="sgd", lr=1e-2))
 INIT_STD.update({"snr_trans_kuairec_adam": 0.05, "snr_trans_kuairec_1level_sgd": 0.05})
+# MSSM (mssm.py): SNR-trans's structure with a hard-concrete gate per output unit; u AND the matrices are unregistered
+CASES["mssm_kuairec_adam"] = ("kuairec_sharedbottom", dict(max_vocab=200), dict(SMALL, model_name="mssm"), {})
+CASES["mssm_kuairec_1level_l2_sgd"] = ("kuairec_sharedbottom", dict(max_vocab=200),
+                                       dict(SMALL, model_name="mssm", expert_dnn_hidden_units=[24], num_experts=3,
+                                            tower_dnn_hidden_units=[16], l2_reg_dnn=1e-2), dict(optimizer="sgd", lr=1e-2))
+INIT_STD.update({"mssm_kuairec_adam": 0.05, "mssm_kuairec_1level_l2_sgd": 0.05})
 # cases whose identity / 1e-4 initial state would leave parts of the model untested: perturbed after construction
 INIT_STD.update({"cross_stitch_kuairec_adam": 0.05, "hmoe_kuairec_adam": 0.05, "mlp_kuairec_adam": 0.05,
                  "pcg_kuairec_adam": 0.05, "mmoe_kuairec_l2_adam": 0.05, "ple_ae_t2_l2_sgd": 0.05,
@@ -152,11 +158,13 @@ def build_reference(cfg, fields, init_std=0.0001):
     from model.escm import ESCM
     from model.aitm import AITM
     from model.snr_trans import SNR_trans
+    from model.mssm import MSSM
     emb = cfg["model_config"]["emb"]
     cols = [SparseFeat(n, vocabulary_size=v, embedding_dim=emb) if k == "sparse" else DenseFeat(n, 1)
             for n, k, v in fields]
     cls = {"mmoe": MMOE, "ple": PLE, "sharedbottom": SharedBottom, "esmm": ESMM, "star": STAR,
-           "pepnet": PepNet, "mlp": MLP, "cross_stitch": CrossStitch, "hmoe": HMOE, "pcg": MMOE, "escm": ESCM, "aitm": AITM, "snr_trans": SNR_trans}[cfg["model_config"]["model_name"].lower()]
+           "pepnet": PepNet, "mlp": MLP, "cross_stitch": CrossStitch, "hmoe": HMOE, "pcg": MMOE, "escm": ESCM, "aitm": AITM, "snr_trans": SNR_trans,
+           "mssm": MSSM}[cfg["model_config"]["model_name"].lower()]
     with contextlib.redirect_stdout(io.StringIO()):
         model = cls(cols, init_std=init_std, device="cpu", config=cfg)
         model.compile(optimizer=cfg["optim_config"]["optimizer"], loss=cfg["optim_config"]["loss"],
@@ -174,6 +182,14 @@ def unregistered_star_tensors(model):
                 for i, row in enumerate(mod.trans_matrix):
                     for j, m in enumerate(row):
                         extra[f"trans.{name}.trans_matrix.{i}.{j}"] = m.detach().clone()
+        return extra
+    if type(model).__name__ == "MSSM":   # gate.u AND gate.trans_matrix: plain lists of lists (mssm.py:26-36)
+        for name, mod in model.mssm.items():
+            if name.startswith("gate"):
+                for attr in ("trans_matrix", "u"):
+                    for i, row in enumerate(getattr(mod, attr)):
+                        for j, m in enumerate(row):
+                            extra[f"mssm.{name}.{attr}.{i}.{j}"] = m.detach().clone()
         return extra
     if type(model).__name__ != "STAR":
         return extra

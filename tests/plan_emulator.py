@@ -269,30 +269,33 @@ class FakeLib:
         logit = np.log(u) - np.log(1.0 - u) + np.log(alpha) / 0.9
         return 1.0 / (1.0 + np.exp(-logit))
 
-    def mmlrec_snr_gate_weights(self, u, alpha, trans, n_out, n_in, U, w_eff, ld_w, w16, stream):
+    def mmlrec_snr_gate_weights(self, u, alpha, trans, n_out, n_in, U, zdim, w_eff, ld_w, w16, stream):
         self.calls.append("snr_gate_weights")
-        uu = view(u, np.float32, n_out * n_in).reshape(n_out, n_in).astype(np.float64)
+        assert zdim in (1, U)
+        uu = view(u, np.float32, n_out * n_in * zdim).reshape(n_out, n_in, zdim).astype(np.float64)
         a = float(view(alpha, np.float32, 1)[0])
         M = view(trans, np.float32, n_out * n_in * U * U).reshape(n_out, n_in, U, U).astype(np.float64)
-        z = np.clip(self._snr_s(uu, a) * 1.2 - 0.1, 0.0, 1.0)
-        # w[i*U+v, j*U+u] = z_ij * M[i, j, u, v]
-        w = (z[:, :, None, None] * M).transpose(0, 3, 1, 2).reshape(n_out * U, n_in * U)
+        z = np.clip(self._snr_s(uu, a) * 1.2 - 0.1, 0.0, 1.0)            # [n_out, n_in, zdim] over the output unit v
+        # w[i*U+v, j*U+u] = z_ij[v] * M[i, j, u, v]
+        w = (z[:, :, None, :] * M).transpose(0, 3, 1, 2).reshape(n_out * U, n_in * U)
         view2(w_eff, np.float32, n_out * U, n_in * U, ld_w)[:] = w.astype(np.float32)
         if _ptr(w16):
             view2(w16, np.uint16, n_out * U, n_in * U, ld_w)[:] = f32_to_bf16(w).reshape(n_out * U, n_in * U)
         return 0
 
-    def mmlrec_snr_gate_fold(self, d_w_eff, ld_w, trans, u, alpha, n_out, n_in, U, dz_scratch, d_u, d_alpha, stream):
+    def mmlrec_snr_gate_fold(self, d_w_eff, ld_w, trans, u, alpha, n_out, n_in, U, zdim, dz_scratch, d_u, d_alpha, stream):
         self.calls.append("snr_gate_fold")
         dW = view2(d_w_eff, np.float32, n_out * U, n_in * U, ld_w).astype(np.float64)
-        uu = view(u, np.float32, n_out * n_in).reshape(n_out, n_in).astype(np.float64)
+        uu = view(u, np.float32, n_out * n_in * zdim).reshape(n_out, n_in, zdim).astype(np.float64)
         a = float(view(alpha, np.float32, 1)[0])
         M = view(trans, np.float32, n_out * n_in * U * U).reshape(n_out, n_in, U, U).astype(np.float64)
-        dz = (dW.reshape(n_out, U, n_in, U).transpose(0, 2, 3, 1) * M).sum((2, 3))
+        t = dW.reshape(n_out, U, n_in, U).transpose(0, 2, 3, 1) * M      # [i, j, u, v]
+        dz = t.sum((2, 3))[:, :, None] if zdim == 1 else t.sum(2)
         s = self._snr_s(uu, a)
         s_ = s * 1.2 - 0.1
         dlogit = np.where((s_ > 0) & (s_ <= 1), dz * 1.2 * s * (1 - s), 0.0)
-        view(d_u, np.float32, n_out * n_in)[:] = (dlogit * (1 / uu + 1 / (1 - uu))).reshape(-1).astype(np.float32)
+        if _ptr(d_u):
+            view(d_u, np.float32, n_out * n_in * zdim)[:] = (dlogit * (1 / uu + 1 / (1 - uu))).reshape(-1).astype(np.float32)
         view(d_alpha, np.float32, 1)[0] = np.float32(dlogit.sum() / (a * 0.9))
         return 0
 

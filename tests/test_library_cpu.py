@@ -73,7 +73,7 @@ def test_same_state_dict_keys_and_seeded_init_as_reference(case):
     model, z, _ = _build_cpu(case)
     sd = model.state_dict()
     ref = {k[5:]: z[k] for k in z.files if k.startswith("init/") and ".specific_weights." not in k
-           and ".specific_biases." not in k and ".trans_matrix." not in k}
+           and ".specific_biases." not in k and ".trans_matrix." not in k and ".u." not in k}
     assert set(sd) == set(ref)
     edited = set(str(s) for s in z["meta/init_overridden"]) if "meta/init_overridden" in z.files else set()
     for k, v in ref.items():
@@ -86,7 +86,7 @@ def test_same_state_dict_keys_and_seeded_init_as_reference(case):
             prefix, kind, idx = k[5:].rsplit(".", 2)
             name = ("frozen_weight_" if kind == "specific_weights" else "frozen_bias_") + idx
             assert np.array_equal(getattr(model.get_submodule(prefix), name).numpy(), z[k]), k
-        if k.startswith("init/") and ".trans_matrix." in k:  # SNR-trans: the unregistered transformation matrices
+        if k.startswith("init/") and (".trans_matrix." in k or ".u." in k):  # SNR-trans / MSSM: unregistered gate tensors
             prefix, i, j = k[5:].rsplit(".", 2)
             mod_name, attr = prefix.rsplit(".", 1)
             assert np.array_equal(getattr(model.get_submodule(mod_name), attr)[int(i), int(j)].numpy(), z[k]), k

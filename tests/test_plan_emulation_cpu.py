@@ -47,7 +47,7 @@ def _table_grads(model, plan, X):
 
 
 CASES = ["sharedbottom_kuairec_adam", "aitm_kuairec_adam", "aitm_kuairec_notower_l2_sgd", "snr_trans_kuairec_adam",
-         "snr_trans_kuairec_1level_sgd"]
+         "snr_trans_kuairec_1level_sgd", "mssm_kuairec_adam", "mssm_kuairec_1level_l2_sgd"]
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
