@@ -507,6 +507,21 @@ int mmlrec_aitm_attention_forward(const float* vkq, int64_t ld, int32_t rows, in
 int mmlrec_aitm_attention_backward(const float* d_out, int64_t ld_dout, const float* vkq, int64_t ld, const float* attn,
                                    int32_t rows, int32_t H, float* d_vkq_f32, uint16_t* d_vkq_bf16, int64_t ld_d,
                                    void* stream);
+/* APG layer (reference model/apg.py:76-78, :96-99: ``torch.matmul(output_nk.unsqueeze(1), specific_weight_kk.view(-1, k, k))
+ * .squeeze() + specific_bias_kk``): a per-sample [1, k] x [k, k] product.  nk [B, k]; wkk [B, k*k] (row b = the sample's
+ * matrix, row-major [i][j]) and bkk [B, k] are the outputs of the two scene-embedding Linear layers.
+ *   out[b, j] = sum_i nk[b, i] * wkk[b, i*k + j] + bkk[b, j]          (fp32 and/or bf16 copy) */
+int mmlrec_apg_mix_forward(const float* nk, int64_t ld_nk, const float* wkk, int64_t ld_w, const float* bkk, int64_t ld_b,
+                           int32_t B, int32_t k, float* out_f32, int64_t ld_f32, uint16_t* out_bf16, int64_t ld_bf16,
+                           void* stream);
+/* d(nk), d(wkk), d(bkk) (assigned; each fp32 or bf16) from d(out) [B, k] (fp32) */
+int mmlrec_apg_mix_backward(const float* d_kk, int64_t ld_dkk, const float* nk, int64_t ld_nk, const float* wkk, int64_t ld_w,
+                            int32_t B, int32_t k, float* d_nk_f32, uint16_t* d_nk_bf16, int64_t ld_dnk, float* d_wkk_f32,
+                            uint16_t* d_wkk_bf16, int64_t ld_dw, float* d_bkk_f32, uint16_t* d_bkk_bf16, int64_t ld_db,
+                            void* stream);
+/* out[n] = sum_b Z[b, n], Z [B, N] fp32 or bf16 (exactly one non-NULL), fixed summation order: the bias gradient of a
+ * Linear whose weight is stored [K, N] and applied as x @ W + b (apg.py:92, :99 ``torch.matmul(x, shared_weight) + bias``) */
+int mmlrec_colsum(const float* z_f32, const uint16_t* z_bf16, int64_t ld, int32_t B, int32_t N, float* out, void* stream);
 /* SNR-trans / MSSM gate (reference model/snr_trans.py:9-50, model/mssm.py:9-60): out_i = sum_j z_ij * (x_j @ M_ij), z_ij the
  * hard-concrete gate of (u_ij, alpha): s = sigmoid(log u - log(1-u) + log(alpha)/0.9), z = clamp(1.2 s - 0.1, 0, 1).
  * zdim = 1 (SNR-trans): u [n_out, n_in], one scalar per connection; zdim = U (MSSM): u [n_out, n_in, U], one gate per

@@ -903,6 +903,80 @@ __global__ void aitm_attention_backward_kernel(const float* d_out, int64_t ld_do
   }
 }
 
+// APG (apg.py:87-99, the shipped use_uv_shared / no-P variant): the per-sample k x k matrix of the layer,
+//   kk[b, j] = sum_i nk[b, i] * wkk[b, i * k + j] + bkk[b, j],
+// where wkk [B, k*k] and bkk [B, k] are generated from the (detached) scene embedding by two Linear layers.  Byte work:
+// every sample streams its own k*k matrix once (4 k^2 B per sample each way); one warp per sample, lanes over j so the
+// matrix rows are read coalesced.
+__global__ void apg_mix_forward_kernel(const float* nk, int64_t ld_nk, const float* wkk, int64_t ld_w, const float* bkk,
+                                       int64_t ld_b, int B, int k, float* o32, int64_t ld32, uint16_t* o16, int64_t ld16) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < B; r += gridDim.x * wpb) {
+    const float* x = nk + (int64_t)r * ld_nk;
+    const float* w = wkk + (int64_t)r * ld_w;
+    for (int j = lane; j < k; j += 32) {
+      float acc = 0.f;
+      for (int i = 0; i < k; ++i) acc = fmaf(x[i], w[i * k + j], acc);
+      acc += bkk[(int64_t)r * ld_b + j];
+      if (o32) o32[(int64_t)r * ld32 + j] = acc;
+      if (o16) o16[(int64_t)r * ld16 + j] = float_to_bf16_bits(acc);
+    }
+  }
+}
+
+// d(nk)[b, i] = sum_j d(kk)[b, j] wkk[b, i*k + j];  d(wkk)[b, i*k + j] = nk[b, i] d(kk)[b, j];  d(bkk) = d(kk).
+// All three are assigned (each input has this stage as its only consumer), in fp32 or bf16 as the producers' GEMMs read them.
+__global__ void apg_mix_backward_kernel(const float* d_kk, int64_t ld_dkk, const float* nk, int64_t ld_nk, const float* wkk,
+                                        int64_t ld_w, int B, int k, float* dnk32, uint16_t* dnk16, int64_t ld_dnk,
+                                        float* dw32, uint16_t* dw16, int64_t ld_dw, float* db32, uint16_t* db16,
+                                        int64_t ld_db) {
+  const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+  for (int r = blockIdx.x * wpb + (threadIdx.x >> 5); r < B; r += gridDim.x * wpb) {
+    const float* g = d_kk + (int64_t)r * ld_dkk;
+    const float* x = nk + (int64_t)r * ld_nk;
+    const float* w = wkk + (int64_t)r * ld_w;
+    for (int i = 0; i < k; ++i) {
+      float acc = 0.f;
+      for (int j = lane; j < k; j += 32) acc = fmaf(g[j], w[i * k + j], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        if (dnk32) dnk32[(int64_t)r * ld_dnk + i] = acc;
+        if (dnk16) dnk16[(int64_t)r * ld_dnk + i] = float_to_bf16_bits(acc);
+      }
+    }
+    for (int e = lane; e < k * k; e += 32) {
+      const int i = e / k, j = e - i * k;
+      const float v = x[i] * g[j];
+      if (dw32) dw32[(int64_t)r * ld_dw + e] = v;
+      if (dw16) dw16[(int64_t)r * ld_dw + e] = float_to_bf16_bits(v);
+    }
+    for (int j = lane; j < k; j += 32) {
+      if (db32) db32[(int64_t)r * ld_db + j] = g[j];
+      if (db16) db16[(int64_t)r * ld_db + j] = float_to_bf16_bits(g[j]);
+    }
+  }
+}
+
+// out[n] = sum_b Z[b, n] (fp32 or bf16 input): the bias gradient of a Linear whose weight is stored [K, N] (its wgrad
+// problem has dZ as the B operand, so the GEMM's row-sum path does not apply).  One CTA per 32 columns, 32 row groups,
+// partials added in row-group order: deterministic.
+__global__ void colsum_kernel(const float* z32, const uint16_t* z16, int64_t ld, int B, int N, float* out) {
+  __shared__ float part[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  if (n < N)
+    for (int r = ty; r < B; r += 32)
+      acc += z32 ? z32[(int64_t)r * ld + n] : bf16_bits_to_float(z16[(int64_t)r * ld + n]);
+  part[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && n < N) {
+    float t = 0.f;
+    for (int g = 0; g < 32; ++g) t += part[g][tx];
+    out[n] = t;
+  }
+}
+
 // SNR-trans / MSSM gate (snr_trans.py:9-50, mssm.py:9-60): out_i = sum_j z_ij * (x_j @ M_ij) with a hard-concrete gate
 // per (output i, input j): s = sigmoid(log u - log(1 - u) + log(alpha) / beta), z = clamp(s * (eps - gamma) + gamma, 0, 1).
 // SNR-trans: u, z are scalars per connection (Z = 1, u trained); MSSM: vectors over the output unit v (Z = U, u a
@@ -1385,6 +1459,37 @@ extern "C" int mmlrec_aitm_attention_backward(const float* d_out, int64_t ld_dou
   MMLREC_CHECK_ARG(d_out && vkq && attn && (d_vkq_f32 || d_vkq_bf16), "null buffer");
   aitm_attention_backward_kernel<<<grid_for((int64_t)rows * 32), 256, 0, (cudaStream_t)stream>>>(
       d_out, ld_dout, vkq, ld, attn, rows, H, sqrtf((float)H), d_vkq_f32, d_vkq_bf16, ld_d);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_apg_mix_forward(const float* nk, int64_t ld_nk, const float* wkk, int64_t ld_w, const float* bkk,
+                                      int64_t ld_b, int32_t B, int32_t k, float* out_f32, int64_t ld_f32,
+                                      uint16_t* out_bf16, int64_t ld_bf16, void* stream) {
+  if (B <= 0 || k <= 0) return 0;
+  MMLREC_CHECK_ARG(nk && wkk && bkk && (out_f32 || out_bf16), "null buffer");
+  apg_mix_forward_kernel<<<grid_for((int64_t)B * 32), 256, 0, (cudaStream_t)stream>>>(nk, ld_nk, wkk, ld_w, bkk, ld_b, B, k,
+                                                                                     out_f32, ld_f32, out_bf16, ld_bf16);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_apg_mix_backward(const float* d_kk, int64_t ld_dkk, const float* nk, int64_t ld_nk, const float* wkk,
+                                       int64_t ld_w, int32_t B, int32_t k, float* d_nk_f32, uint16_t* d_nk_bf16,
+                                       int64_t ld_dnk, float* d_wkk_f32, uint16_t* d_wkk_bf16, int64_t ld_dw,
+                                       float* d_bkk_f32, uint16_t* d_bkk_bf16, int64_t ld_db, void* stream) {
+  if (B <= 0 || k <= 0) return 0;
+  MMLREC_CHECK_ARG(d_kk && nk && wkk && (d_nk_f32 || d_nk_bf16) && (d_wkk_f32 || d_wkk_bf16) && (d_bkk_f32 || d_bkk_bf16),
+                   "null buffer");
+  apg_mix_backward_kernel<<<grid_for((int64_t)B * 32), 256, 0, (cudaStream_t)stream>>>(
+      d_kk, ld_dkk, nk, ld_nk, wkk, ld_w, B, k, d_nk_f32, d_nk_bf16, ld_dnk, d_wkk_f32, d_wkk_bf16, ld_dw, d_bkk_f32,
+      d_bkk_bf16, ld_db);
+  MMLREC_RETURN_LAUNCH(1);
+}
+
+extern "C" int mmlrec_colsum(const float* z_f32, const uint16_t* z_bf16, int64_t ld, int32_t B, int32_t N, float* out,
+                             void* stream) {
+  if (N <= 0) return 0;
+  MMLREC_CHECK_ARG((z_f32 || z_bf16) && out && B >= 0, "null buffer");
+  colsum_kernel<<<(N + 31) / 32, 1024, 0, (cudaStream_t)stream>>>(z_f32, z_bf16, ld, B, N, out);
   MMLREC_RETURN_LAUNCH(1);
 }
 

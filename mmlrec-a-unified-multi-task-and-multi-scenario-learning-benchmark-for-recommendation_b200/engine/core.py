@@ -35,7 +35,10 @@ class ActGroup:
     """One wide buffer family [B, sum(widths)]: forward values and gradients, each optionally in
     fp32 and/or bf16 (decided by the consumers before ``materialize``)."""
 
-    def __init__(self, widths: Sequence[int], relu: bool, name: str, grad_dtype: str, act: Optional[str] = None):
+    def __init__(self, widths: Sequence[int], relu: bool, name: str, grad_dtype: str, act: Optional[str] = None,
+                 align: int = 1):
+        # align: every member starts on a multiple of `align` columns (members whose widths are not multiples of 8 still
+        # start on the 16-byte boundaries the tensor-core kernel's tensor maps need; APG's k, k*k, k wide outputs)
         self.widths, self.relu, self.name, self.grad_dtype = list(widths), relu, name, grad_dtype
         self.act = act if act is not None else ("relu" if relu else None)   # activation that produced the values
         self.need_f32 = self.need_bf16 = False
@@ -48,7 +51,7 @@ class ActGroup:
         at = 0
         for i, w in enumerate(widths):
             self.acts.append(Act(self, at, w, f"{name}[{i}]"))
-            at += w
+            at += w if i == len(widths) - 1 else _align(w, align)
         self.total = at
 
     def span(self) -> "Act":
@@ -151,10 +154,11 @@ class LinearSpec:
         self.x, self.linear, self.bn = x, linear, bn
         self.W: nn.Parameter = linear.weight
         self.b: Optional[nn.Parameter] = getattr(linear, "bias", None)
-        # transposed: the parameter is stored [K, N] and applied as x @ W (cross_stitch.py:18) instead of x @ W^T
+        # transposed: the parameter is stored [K, N] and applied as x @ W (cross_stitch.py:18) or x @ W + b (apg.py:92, :99)
+        # instead of x @ W^T; its bias gradient comes from a column-sum kernel (the wgrad problem has dZ as the B operand)
         self.transposed = transposed
         self.N, self.K = (self.W.shape[1], self.W.shape[0]) if transposed else self.W.shape
-        assert not (transposed and (self.b is not None or bn is not None)), "transposed weights: plain x @ W only"
+        assert not (transposed and bn is not None), "transposed weights: x @ W [+ b] only"
 
 
 class Builder:
@@ -275,8 +279,8 @@ class Builder:
         return self.store.aux_vector(n)
 
     def new_group(self, widths: Sequence[int], relu: bool, name: str, grad_dtype: str = "f32",
-                  act: Optional[str] = None) -> List[Act]:
-        g = ActGroup(widths, relu, name, grad_dtype if self.tc else "f32", act)
+                  act: Optional[str] = None, align: int = 1) -> List[Act]:
+        g = ActGroup(widths, relu, name, grad_dtype if self.tc else "f32", act, align)
         self.groups.append(g)
         return g.acts
 
@@ -519,7 +523,7 @@ class LinearStage(Stage):
     (model/utils.py:146-161), and in backward by one launch holding every wgrad + dgrad problem."""
     name = "linear"
 
-    def __init__(self, b: Builder, specs: List[LinearSpec], act: Optional[str], label: str = ""):
+    def __init__(self, b: Builder, specs: List[LinearSpec], act: Optional[str], label: str = "", align_outs: int = 1):
         self.b, self.specs, self.act, self.label = b, specs, act, label
         self.use_bn = specs[0].bn is not None
         assert all((s.bn is not None) == self.use_bn for s in specs)
@@ -536,8 +540,8 @@ class LinearStage(Stage):
         # without BatchNorm the backward GEMMs read dZ = d(out) directly (bf16 in tensor-core mode);
         # with BatchNorm d(out) feeds the BN backward kernel (fp32) which emits dZ
         self.outs = b.new_group(widths, relu=(act == "relu"), name=f"{label}.y",
-                                grad_dtype="f32" if self.use_bn else "bf16", act=act)
-        self.zs = b.new_group(widths, relu=False, name=f"{label}.z", grad_dtype="bf16") if self.use_bn else None
+                                grad_dtype="f32" if self.use_bn else "bf16", act=act, align=align_outs)
+        self.zs = b.new_group(widths, relu=False, name=f"{label}.z", grad_dtype="bf16", align=align_outs) if self.use_bn else None
         if self.use_bn:
             self.zs[0].want(f32=True)
         for s in specs:
@@ -557,6 +561,7 @@ class LinearStage(Stage):
 
         for s in specs:
             ok = bool(cur) and not s.transposed and not cur[-1].transposed \
+                and self.outs[specs.index(s)].col == self.outs[specs.index(cur[-1])].col + cur[-1].N \
                 and s.x.same_as(cur[-1].x) and s.K == cur[-1].K and st.contiguous_after(cur[-1].W, s.W) \
                 and ((s.b is None) == (cur[-1].b is None)) and (s.b is None or st.contiguous_after(cur[-1].b, s.b))
             if ok and self.use_bn:
@@ -702,6 +707,7 @@ class LinearStage(Stage):
                         self.split_k = cand
                         break
         self.zero_before_bwd = []   # gradient buffers a K-split dgrad accumulates into from zero
+        self.colsums = []           # (dZ fp32 ptr, dZ bf16 ptr, ld, N, bias-gradient ptr) of [K, N]-stored layers with a bias
         dzg = self.zs[0].group if self.use_bn else self.outs[0].group   # where dZ lives
         # one Linear applied to several inputs in this stage (AITM's h1/h2/h3 on both tokens, aitm.py:86-88): every
         # application writes its weight / bias gradient into its OWN gradient slices (the optimizer adds slices up in
@@ -739,6 +745,13 @@ class LinearStage(Stage):
             while len(waves) <= wave:
                 waves.append([])
             accumulate = 1 if (want_dx and (x.grad_written or wave > 0)) else 0
+            if g.transposed and g.b is not None:
+                if b.tc:
+                    zb = self.dz_stage if self.dz_stage is not None else dzg.gbuf16
+                    self.colsums.append((None, zb.data_ptr() + 2 * g.y_col, zb.stride(0), g.N, st.grad_ptr(g.b) + g_off))
+                else:
+                    self.colsums.append((dzg.gbuf.data_ptr() + 4 * g.y_col, None, dzg.gbuf.stride(0), g.N,
+                                         st.grad_ptr(g.b) + g_off))
             if not b.tc:
                 dz_ptr, dz_ld = dzg.gbuf.data_ptr() + 4 * g.y_col, dzg.gbuf.stride(0)
                 p = L.GemmF32()   # wgrad: dW[n,k] = sum_b dZ[b,n] X[b,k]; rowsum_a = bias gradient
@@ -880,6 +893,8 @@ class LinearStage(Stage):
             L.check(b.lib.mmlrec_fill_f32(buf.data_ptr(), buf.numel(), 0.0, stream), f"zero d(input) {self.label}")
         for tbl in self.bwd:
             self._launch(tbl, stream, "linear bwd")
+        for z32, z16, ld, n, out in self.colsums:
+            L.check(b.lib.mmlrec_colsum(z32, z16, ld, b.B, n, out, stream), f"bias gradient {self.label}")
 
 
 def mlp_stages(b: Builder, items: Sequence[Tuple[Act, nn.Module]], label: str) -> List[Act]:
@@ -1007,6 +1022,48 @@ class PairAttentionStage(Stage):
         L.check(b.lib.mmlrec_aitm_attention_backward(o.gptr, o.gld, x.ptr, x.ld, self.attn.data_ptr(), b.B, self.H,
                                                      x.gptr if f32 else None, None if f32 else x.gptr, x.gld, stream),
                 f"attention bwd {self.label}")
+
+
+class ApgMixStage(Stage):
+    """APG's per-sample product (apg.py:96-99): ``kk[b] = nk[b] @ wkk[b].view(k, k) + bkk[b]`` with the sample's matrix
+    and bias generated from its scene embedding.  ``nk`` [B, k], ``wkk`` [B, k*k], ``bkk`` [B, k] are outputs of the
+    preceding LinearStage; this stage is their only consumer, so backward assigns all three gradients."""
+    name = "apg_mix"
+
+    def __init__(self, b: Builder, nk: Act, wkk: Act, bkk: Act, label: str = ""):
+        self.b, self.nk, self.wkk, self.bkk, self.label = b, nk, wkk, bkk, label
+        self.k = nk.width
+        assert wkk.width == self.k * self.k and bkk.width == self.k
+        for a in (nk, wkk, bkk):
+            assert a.dkind == 0, "the inputs of the APG product carry no activation"
+            a.want(f32=True)
+        (self.out,) = b.new_group([self.k], relu=False, name=f"{label}.kk", grad_dtype="f32")
+
+    def forward(self, stream, training):
+        b, o = self.b, self.out
+        L.check(b.lib.mmlrec_apg_mix_forward(self.nk.ptr, self.nk.ld, self.wkk.ptr, self.wkk.ld, self.bkk.ptr, self.bkk.ld,
+                                             b.B, self.k, o.ptr if o.has_f32 else None, o.ld if o.has_f32 else 0,
+                                             o.ptr16 if o.has_bf16 else None, o.ld16 if o.has_bf16 else 0, stream),
+                f"apg mix fwd {self.label}")
+
+    def plan_backward(self):
+        self.live = self.out.grad_written
+        if self.live:
+            for a in (self.nk, self.wkk, self.bkk):
+                assert a.group.need_grad and not a.grad_written, "the APG product is the only consumer of its inputs"
+                a.grad_written = True
+
+    def backward(self, stream):
+        if not self.live:
+            return
+        b, o = self.b, self.out
+
+        def dst(a):
+            return (a.gptr if a.grad_is_f32 else None, None if a.grad_is_f32 else a.gptr, a.gld)
+
+        L.check(b.lib.mmlrec_apg_mix_backward(o.gptr, o.gld, self.nk.ptr, self.nk.ld, self.wkk.ptr, self.wkk.ld, b.B, self.k,
+                                              *dst(self.nk), *dst(self.wkk), *dst(self.bkk), stream),
+                f"apg mix bwd {self.label}")
 
 
 class DerivedLinear:

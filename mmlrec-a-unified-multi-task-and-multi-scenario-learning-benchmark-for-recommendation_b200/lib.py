@@ -174,6 +174,9 @@ _SIGNATURES = {
     "mmlrec_mul_backward": (C.c_int, [vp, i64, vp, i64, vp, i64, vp, vp, i64, i32, i32, vp, vp, i64, i32, i32, i32, i32, vp]),
     "mmlrec_aitm_attention_forward": (C.c_int, [vp, i64, i32, i32, vp, i64, vp, i64, vp, vp]),
     "mmlrec_aitm_attention_backward": (C.c_int, [vp, i64, vp, i64, vp, i32, i32, vp, vp, i64, vp]),
+    "mmlrec_apg_mix_forward": (C.c_int, [vp, i64, vp, i64, vp, i64, i32, i32, vp, i64, vp, i64, vp]),
+    "mmlrec_apg_mix_backward": (C.c_int, [vp, i64, vp, i64, vp, i64, i32, i32, vp, vp, i64, vp, vp, i64, vp, vp, i64, vp]),
+    "mmlrec_colsum": (C.c_int, [vp, vp, i64, i32, i32, vp, vp]),
     "mmlrec_snr_gate_weights": (C.c_int, [vp, vp, vp, i32, i32, i32, i32, vp, i64, vp, vp]),
     "mmlrec_snr_gate_fold": (C.c_int, [vp, i64, vp, vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]),
     "mmlrec_star_weights": (C.c_int, [vp, vp, vp, vp, i32, i32, i32, vp, i64, vp, vp, vp]),

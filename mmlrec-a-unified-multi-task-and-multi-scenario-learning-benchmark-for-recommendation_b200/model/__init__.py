@@ -1,6 +1,7 @@
 """Model zoo on the fused step program.  ``get_model`` mirrors ``main.py:37-68`` of the reference
-(case-insensitive names); the family outside the fused step (apg) raises ``NotImplementedError`` by name."""
+(case-insensitive names): all fifteen names the reference's factory knows are on the fused step."""
 from .aitm import AITM
+from .apg import APG
 from .cross_stitch import CrossStitch
 from .escm import ESCM
 from .esmm import ESMM
@@ -16,7 +17,7 @@ from .star import STAR
 
 _REGISTRY = {"mmoe": MMOE, "ple": PLE, "sharedbottom": SharedBottom, "esmm": ESMM, "star": STAR, "pepnet": PepNet,
              "mlp": MLP, "cross_stitch": CrossStitch, "hmoe": HMOE, "escm": ESCM, "aitm": AITM, "snr_trans": SNR_trans,
-             "mssm": MSSM,
+             "mssm": MSSM, "apg": APG,
              # main.py:53-54 builds an MMOE for 'pcg' and wraps its optimizer in PCGrad (basemodel.py:564-565).  The loop
              # hands pc_backward ONE objective -- the summed loss (basemodel.py:309-310) -- so the projection is the
              # identity and the step is MMoE's (pinned by the golden case pcg_kuairec_adam)

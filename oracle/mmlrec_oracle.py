@@ -463,11 +463,34 @@ def forward_mssm(p: Params, b: Params, s: Spec, X: Tensor, training: bool) -> Te
     return _towers(p, b, s, feats, training)
 
 
+def forward_apg(p: Params, b: Params, s: Spec, X: Tensor, training: bool) -> Tensor:
+    """model/apg.py:152-176 with the layer of :76-125 in the variant the model builds (use_uv_shared, no P module, no inner /
+    generating activation): nk = x @ W_nk + b_nk; kk = nk @ W_kk(scene) + b_kk(scene) per sample; out = act(kk @ W_km + b_km).
+    The scene embedding is sparse_embedding_list[X column of the scene feature], detached (:158-159)."""
+    rows, dense = gather_fields(X, p, s.columns)
+    h = concat_fields(rows, dense)
+    scene_col = feature_layout(s.columns)[s.scene_feature][0]
+    scene = rows[scene_col].squeeze().detach()
+    for l in range(len(s.dnn_units)):
+        pre = f"apg_layers.{l}"
+        k = p[f"{pre}.shared_weight_nk"].shape[1]
+        w_kk = mlp(p, b, f"{pre}.specific_weight_kk", scene, False, training, None).view(-1, k, k)
+        b_kk = mlp(p, b, f"{pre}.specific_bias_kk", scene, False, training, None)
+        nk = torch.matmul(h, p[f"{pre}.shared_weight_nk"]) + p[f"{pre}.shared_bias_nk"]
+        kk = torch.matmul(nk.unsqueeze(1), w_kk).squeeze() + b_kk
+        h = torch.matmul(kk, p[f"{pre}.shared_weight_km"]) + p[f"{pre}.shared_bias_km"]
+        if s.act is not None:
+            h = torch.relu(h)
+    outs = [predict_head(F.linear(h, p[f"final_layer.{t}.weight"]), p[f"out.{t}.bias"], s.task_types[t])
+            for t in range(s.num_tasks)]
+    return torch.cat(outs, -1)
+
+
 FORWARDS = {
     "mmoe": forward_mmoe, "pcg": forward_mmoe, "ple": forward_ple, "sharedbottom": forward_sharedbottom,
     "esmm": forward_esmm, "star": forward_star, "pepnet": forward_pepnet, "mlp": forward_mlp,
     "cross_stitch": forward_cross_stitch, "hmoe": forward_hmoe, "escm": forward_escm, "aitm": forward_aitm,
-    "snr_trans": forward_snr_trans, "mssm": forward_mssm,
+    "snr_trans": forward_snr_trans, "mssm": forward_mssm, "apg": forward_apg,
 }
 
 
@@ -490,6 +513,7 @@ REG_MODULES = {
     "aitm": ["tower_dnn", "bottom", "tower_dnn_final_layer"],
     "snr_trans": ["tower_dnn"],
     "mssm": ["tower_dnn"],
+    "apg": [],
 }
 REG_MODULES["pcg"] = REG_MODULES["mmoe"]
 

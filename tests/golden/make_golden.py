@@ -114,6 +114,12 @@ CASES["mssm_kuairec_1level_l2_sgd"] = ("kuairec_sharedbottom", dict(max_vocab=20
                                        dict(SMALL, model_name="mssm", expert_dnn_hidden_units=[24], num_experts=3,
                                             tower_dnn_hidden_units=[16], l2_reg_dnn=1e-2), dict(optimizer="sgd", lr=1e-2))
 INIT_STD.update({"mssm_kuairec_adam": 0.05, "mssm_kuairec_1level_l2_sgd": 0.05})
+# APG (apg.py): per-sample k x k matrices generated from the detached scene embedding between two shared low-rank maps;
+# the generating DNNs are built with the DNN default init (1e-4), so the seeded state is perturbed after construction
+CASES["apg_movielens_adam"] = ("movielens_star", dict(vocab_scale=0.02), dict(model_name="apg", dnn_hidden_units=[16, 16]), {})
+CASES["apg_movielens_odd_sgd"] = ("movielens_star", dict(vocab_scale=0.02), dict(model_name="apg", dnn_hidden_units=[24, 10]),
+                                  dict(optimizer="sgd", lr=1e-2))
+INIT_STD.update({"apg_movielens_adam": 0.05, "apg_movielens_odd_sgd": 0.05})
 # cases whose identity / 1e-4 initial state would leave parts of the model untested: perturbed after construction
 INIT_STD.update({"cross_stitch_kuairec_adam": 0.05, "hmoe_kuairec_adam": 0.05, "mlp_kuairec_adam": 0.05,
                  "pcg_kuairec_adam": 0.05, "mmoe_kuairec_l2_adam": 0.05, "ple_ae_t2_l2_sgd": 0.05,
@@ -126,6 +132,17 @@ def post_build(case, model):
         with torch.no_grad():
             model.out[0].bias.fill_(30.0)
         return ["out.0.bias"]
+    if case.startswith("apg_"):   # generated matrices / biases that really depend on the scene embedding
+        touched = []
+        with torch.no_grad():
+            for name, prm in model.named_parameters():
+                if ".specific_" in name and name.endswith(".weight"):
+                    prm.add_(0.5 * torch.randn(prm.shape, generator=torch.Generator().manual_seed(11)))
+                    touched.append(name)
+                if name.endswith("shared_bias_nk") or name.endswith("shared_bias_km"):
+                    prm.add_(0.05 * torch.randn(prm.shape, generator=torch.Generator().manual_seed(12)))
+                    touched.append(name)
+        return touched
     if case == "cross_stitch_kuairec_adam":   # identity units exercise no off-diagonal weight: add seeded noise
         touched = []
         with torch.no_grad():
@@ -159,12 +176,13 @@ def build_reference(cfg, fields, init_std=0.0001):
     from model.aitm import AITM
     from model.snr_trans import SNR_trans
     from model.mssm import MSSM
+    from model.apg import APG
     emb = cfg["model_config"]["emb"]
     cols = [SparseFeat(n, vocabulary_size=v, embedding_dim=emb) if k == "sparse" else DenseFeat(n, 1)
             for n, k, v in fields]
     cls = {"mmoe": MMOE, "ple": PLE, "sharedbottom": SharedBottom, "esmm": ESMM, "star": STAR,
            "pepnet": PepNet, "mlp": MLP, "cross_stitch": CrossStitch, "hmoe": HMOE, "pcg": MMOE, "escm": ESCM, "aitm": AITM, "snr_trans": SNR_trans,
-           "mssm": MSSM}[cfg["model_config"]["model_name"].lower()]
+           "mssm": MSSM, "apg": APG}[cfg["model_config"]["model_name"].lower()]
     with contextlib.redirect_stdout(io.StringIO()):
         model = cls(cols, init_std=init_std, device="cpu", config=cfg)
         model.compile(optimizer=cfg["optim_config"]["optimizer"], loss=cfg["optim_config"]["loss"],

@@ -183,6 +183,7 @@ class FakeLib:
         total = 0.0
         lossv = view(loss, np.float32, T + 1)
         wrote = set()
+        dh_sum = {}   # heads that share an input: the kernel sums their contributions to d(h) (include/mmlrec_b200.h)
         for t, h in enumerate(heads):
             assert h.kind == L.HEAD_SIGMOID_BCE
             hv = view2(h.h, np.float32, B, h.H, h.ld_h).astype(np.float64)
@@ -207,6 +208,8 @@ class FakeLib:
             dh = dz[:, None] * w[None, :]
             if h.relu_mask:
                 dh = np.where(hv > 0, dh, 0.0)
+            key = (_ptr(h.d_h), _ptr(h.d_h_bf16))
+            dh = dh_sum[key] = dh_sum.get(key, 0.0) + dh
             if h.d_h:
                 view2(h.d_h, np.float32, B, h.H, h.ld_d_h)[:] = dh.astype(np.float32)
             if h.d_h_bf16:
@@ -262,6 +265,41 @@ class FakeLib:
             view2(d16, np.uint16, rows, 6 * H, ld_d)[:] = f32_to_bf16(d).reshape(rows, 6 * H)
         return 0
 
+
+    # apg.py:96-99 per-sample product and the column-sum bias gradient (include/mmlrec_b200.h mmlrec_apg_mix_*, mmlrec_colsum)
+    def mmlrec_apg_mix_forward(self, nk, ld_nk, wkk, ld_w, bkk, ld_b, B, k, o32, ld32, o16, ld16, stream):
+        self.calls.append("apg_mix_forward")
+        x = view2(nk, np.float32, B, k, ld_nk).astype(np.float64)
+        w = view2(wkk, np.float32, B, k * k, ld_w).astype(np.float64).reshape(B, k, k)
+        out = np.einsum("bi,bij->bj", x, w) + view2(bkk, np.float32, B, k, ld_b)
+        if _ptr(o32):
+            view2(o32, np.float32, B, k, ld32)[:] = out.astype(np.float32)
+        if _ptr(o16):
+            view2(o16, np.uint16, B, k, ld16)[:] = f32_to_bf16(out).reshape(B, k)
+        return 0
+
+    def mmlrec_apg_mix_backward(self, d_kk, ld_dkk, nk, ld_nk, wkk, ld_w, B, k, dnk32, dnk16, ld_dnk, dw32, dw16, ld_dw,
+                                db32, db16, ld_db, stream):
+        self.calls.append("apg_mix_backward")
+        g = view2(d_kk, np.float32, B, k, ld_dkk).astype(np.float64)
+        x = view2(nk, np.float32, B, k, ld_nk).astype(np.float64)
+        w = view2(wkk, np.float32, B, k * k, ld_w).astype(np.float64).reshape(B, k, k)
+        for val, p32, p16, ld, cols in ((np.einsum("bj,bij->bi", g, w), dnk32, dnk16, ld_dnk, k),
+                                        (np.einsum("bi,bj->bij", x, g).reshape(B, k * k), dw32, dw16, ld_dw, k * k),
+                                        (g, db32, db16, ld_db, k)):
+            assert bool(_ptr(p32)) != bool(_ptr(p16)), "exactly one destination precision"
+            if _ptr(p32):
+                view2(p32, np.float32, B, cols, ld)[:] = val.astype(np.float32)
+            else:
+                view2(p16, np.uint16, B, cols, ld)[:] = f32_to_bf16(val).reshape(B, cols)
+        return 0
+
+    def mmlrec_colsum(self, z32, z16, ld, B, N, out, stream):
+        self.calls.append("colsum")
+        assert bool(_ptr(z32)) != bool(_ptr(z16))
+        z = view2(z32, np.float32, B, N, ld) if _ptr(z32) else bf16_to_f32(view2(z16, np.uint16, B, N, ld))
+        view(out, np.float32, N)[:] = z.astype(np.float64).sum(0).astype(np.float32)
+        return 0
 
     # snr_trans.py:36-50 as a derived weight (include/mmlrec_b200.h mmlrec_snr_gate_weights / _fold)
     @staticmethod
@@ -355,7 +393,20 @@ class EmulatedPlan:
         return self.gather.out.grad_tensor().clone()
 
 
+def _check_tc_desc(d):
+    """The argument checks of mmlrec_tc2_encode_problem (csrc/gemm_tc2.cu): what the tensor maps need.  Host buffers of
+    the emulation are 64-byte aligned like the device allocations, so column offsets show up the same way."""
+    assert d.M > 0 and d.N > 0 and d.K > 0, "bad sizes"
+    assert _ptr(d.A) % 16 == 0 and _ptr(d.B) % 16 == 0, "operands must be 16-byte aligned"
+    assert d.lda % 8 == 0 and d.ldb % 8 == 0, "operand row strides must be multiples of 8 elements"
+    assert not d.C_f32 or d.c_transposed or (d.ldc_f32 % 4 == 0 and _ptr(d.C_f32) % 16 == 0), "C_f32 alignment"
+    assert not d.C_bf16 or (d.ldc_bf16 % 8 == 0 and _ptr(d.C_bf16) % 16 == 0), "C_bf16 alignment"
+    assert not d.mask or (d.ldmask % 8 == 0 and _ptr(d.mask) % 16 == 0), "mask alignment"
+    assert not d.colsum_b or d.c_transposed, "colsum_b comes with c_transposed"
+
+
 def _copy_desc(d):
+    _check_tc_desc(d)
     c = L.GemmTcDesc()
     C.memmove(C.byref(c), C.byref(d), C.sizeof(L.GemmTcDesc))
     return c

@@ -47,7 +47,8 @@ def _table_grads(model, plan, X):
 
 
 CASES = ["sharedbottom_kuairec_adam", "aitm_kuairec_adam", "aitm_kuairec_notower_l2_sgd", "snr_trans_kuairec_adam",
-         "snr_trans_kuairec_1level_sgd", "mssm_kuairec_adam", "mssm_kuairec_1level_l2_sgd"]
+         "snr_trans_kuairec_1level_sgd", "mssm_kuairec_adam", "mssm_kuairec_1level_l2_sgd", "apg_movielens_adam",
+         "apg_movielens_odd_sgd"]
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -111,6 +112,49 @@ def test_aitm_plan_at_a_split_k_batch_matches_the_oracle(precision, B):
         if getattr(prm, "_mm_kind", "") != "dense" or want.get(name) is None:
             continue
         got_all.append(plan.grad(prm).flatten())
+        want_all.append(want[name].flatten())
+        assert rel_err(got_all[-1], want_all[-1]) < (1e-5 if precision == "fp32" else 0.1), name
+    assert rel_err(torch.cat(got_all), torch.cat(want_all)) < tol
+
+
+@pytest.mark.parametrize("precision,B", [("bf16", 2048), ("fp32", 192)])
+def test_apg_plan_at_full_width_matches_the_oracle(precision, B):
+    """MovieLens shape at its full widths [128, 128]: k = 14 and 32, i.e. per-sample matrices of 196 and 1024 generated
+    values whose columns (14 | 196 | 14 wide) must start on the 16-byte boundaries the tensor maps need; B = 2048 in bf16
+    mode adds split-K wgrad (2 batch slices) next to the column-sum bias gradients, which write slice 0 only."""
+    from mmlrec_b200 import synthetic
+    from oracle.mmlrec_oracle import OracleTrainer
+    from helpers import oracle_columns
+    cfg, fields = synthetic.workload("movielens_star", vocab_scale=0.02)
+    cfg["model_config"]["model_name"] = "apg"
+    torch.manual_seed(5)
+    model = _model(cfg, fields, precision)
+    with torch.no_grad():   # the generating DNNs start at N(0, 1e-4): make the generated matrices depend on the scene
+        for name, prm in model.named_parameters():
+            if ".specific_" in name and name.endswith(".weight"):
+                prm.add_(0.5 * torch.randn(prm.shape))
+            if name.startswith("embedding_dict"):
+                prm.mul_(500.0)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    names = [n for n, _ in model.named_parameters()]
+    tr = OracleTrainer(cfg, oracle_columns(cfg, fields), {k: v for k, v in sd.items() if k in names},
+                       {k: v for k, v in sd.items() if k not in names}, names)
+    plan = EmulatedPlan(model, B, precision)
+    model.load_state_dict(sd, strict=True)
+    plan.build()
+    assert plan.grad_slices == (2 if precision == "bf16" else 1)
+    X, y = synthetic.make_batch(cfg, fields, B, seed=3)
+    pred, loss = plan.forward_backward(X, y)
+    want_pred, want_loss, want = tr.loss_and_grads(torch.from_numpy(X), torch.from_numpy(y))
+    tol = 1e-5 if precision == "fp32" else 2e-2
+    assert rel_err(pred, want_pred.detach()) < tol
+    assert abs(float(loss[-1]) - float(want_loss)) <= tol * abs(float(want_loss))
+    got_all, want_all = [], []
+    for name, prm in model.named_parameters():
+        if getattr(prm, "_mm_kind", "") != "dense" or want.get(name) is None:
+            continue
+        g = plan.grad(prm)   # (the sum of the gradient slices, like the optimizer's)
+        got_all.append(g.flatten())
         want_all.append(want[name].flatten())
         assert rel_err(got_all[-1], want_all[-1]) < (1e-5 if precision == "fp32" else 0.1), name
     assert rel_err(torch.cat(got_all), torch.cat(want_all)) < tol
