@@ -226,10 +226,13 @@ def test_bf16_tensor_core_step_close_to_reference_golden(case):
                 got_all.append(g.flatten())
                 want_all.append(want.flatten())
                 e = rel_err(g, want)
-                # a one-element gradient that is a signed sum over every connection of a gate (SNR-trans
-                # d(alpha) = sum_ij dz_ij ds_ij/d(alpha): 0.11 measured on B200) cancels like the BatchNorm terms
-                loose = use_bn or want.numel() == 1
-                if e > (0.25 if loose else 0.1) and float(want.norm()) > 1e-12:
+                # a one-element gradient that is a signed sum over every connection of a gate (SNR-trans / MSSM d(alpha) =
+                # sum_ij dz_ij ds_ij/d(alpha)) cancels: bf16 rounding of the GEMM operands alone moves it by 0.11 (SNR-trans)
+                # and 0.25 (MSSM) on these fixtures -- the same 4 digits on B200 and in the CPU plan emulation, which
+                # rounds the operands to bf16 and accumulates in fp64 (tests/test_plan_emulation_cpu.py), so this is the
+                # arithmetic mode, not the kernels; the fp32 mode pins these entries to 1e-5
+                limit = 0.5 if want.numel() == 1 else (0.25 if use_bn else 0.1)
+                if e > limit and float(want.norm()) > 1e-12:
                     bad.append(f"{name}: rel {e:.3e} norm {float(want.norm()):.3e}")
             assert not bad, "bf16 gradients off: " + "; ".join(bad)
             flat = rel_err(torch.cat(got_all), torch.cat(want_all))
@@ -405,3 +408,55 @@ def test_aitm_at_full_width_and_batch_4096_matches_oracle(precision):
     att = [st for st in plan.stages if isinstance(st, PairAttentionStage)]
     assert len(att) == 1 and att[0].H == model.bottom_dnn_hidden_units[-1] >= 128 and att[0].live
     assert plan.grad_slices == (4 if precision == "bf16" else 2)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_apg_at_full_width_and_batch_4096_matches_oracle(precision):
+    """APG (apg.py) at the MovieLens workload's full widths [128, 128] and B = 4096: k = 14 and 32, per-sample matrices of
+    196 and 1024 generated values (16 MB of them per step), output columns 14 | 196 | 14 wide on 16-byte boundaries, the
+    [K, N]-stored shared weights with their column-sum bias gradients next to split-K weight gradients (bf16)."""
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    from helpers import build_pair
+    from mmlrec_b200 import synthetic
+    from mmlrec_b200.engine.core import ApgMixStage
+    B = 4096
+    model, oracle, cfg, fields, sd0 = build_pair("movielens_star", {}, precision, 0.05, mc_over=dict(model_name="apg"))
+    gen = torch.Generator().manual_seed(21)
+    with torch.no_grad():   # the generating DNNs start at N(0, 1e-4): make the generated matrices depend on the scene
+        for name, prm in model.named_parameters():
+            if ".specific_" in name and name.endswith(".weight"):
+                noise = 0.5 * torch.randn(prm.shape, generator=gen)
+                prm.add_(noise.to(prm.device))
+                oracle.params[name].add_(noise)
+    if model.store.dense_bf16 is not None:
+        model.store.refresh_bf16()
+    tol = 1e-5 if precision == "fp32" else 2e-2
+    for s in range(2):   # eager, then capture + replay
+        X, y = synthetic.make_batch(cfg, fields, B, seed=80 + s)
+        pred_o, loss_o, grads_o = oracle.loss_and_grads(torch.from_numpy(X), torch.from_numpy(y))
+        oracle.optim.step()
+        loss = model.train_on_batch(X, y)
+        torch.cuda.synchronize()
+        assert torch.isfinite(loss).all()
+        if s > 0 and precision == "bf16":
+            continue
+        pred = model.plan(B).pred.cpu()
+        assert rel_err(pred, pred_o) < tol, f"step {s} predictions {rel_err(pred, pred_o):.3e}"
+        assert abs(float(loss[-1]) - float(loss_o)) <= 2 * tol * abs(float(loss_o)), f"step {s} loss"
+        if s == 0:
+            got_all, want_all, bad = [], [], []
+            for name, prm in model.named_parameters():
+                if getattr(prm, "_mm_kind", "") != "dense" or grads_o.get(name) is None:
+                    continue
+                g, want = model.store.grad_view(prm).cpu(), grads_o[name]
+                got_all.append(g.flatten())
+                want_all.append(want.flatten())
+                e = rel_err(g, want)
+                if e > (1e-3 if precision == "fp32" else 0.1):
+                    bad.append(f"{name}: rel {e:.3e}")
+            assert not bad, "gradients off: " + "; ".join(bad)
+            flat = rel_err(torch.cat(got_all), torch.cat(want_all))
+            assert flat < (1e-4 if precision == "fp32" else 2e-2), f"dense gradient vector rel err {flat:.3e}"
+    mixes = [st for st in model.plan(B).stages if isinstance(st, ApgMixStage)]
+    assert [m.k for m in mixes] == [14, 32] and all(m.live for m in mixes)
