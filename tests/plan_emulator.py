@@ -10,8 +10,9 @@ gradient is assigned / accumulated / sliced, parameter layout -- for both arithm
 descriptors are captured before they would be encoded into tensor maps).  What it cannot pin: the CUDA kernels
 themselves (the ``-m gpu`` tests do that).
 
-Only dense single-process plans without BatchNorm / gate stages are emulated (what the CPU tests need); anything else
-raises ``NotImplementedError`` from ``FakeLib.__getattr__``.
+Single-process plans of every model family are emulated (GEMMs, BatchNorm, gate levels, heads with all their flags,
+the element-wise and derived-weight stages); the table update (K2), the optimizer, the L2 kernel and the multi-GPU
+exchanges are not: anything else raises ``NotImplementedError`` from ``FakeLib.__getattr__``.
 """
 import ctypes as C
 
@@ -72,8 +73,9 @@ class FakeLib:
         self.calls = []
 
     def __getattr__(self, name):
-        if name in ("mmlrec_heads_scratch", "mmlrec_l2_scratch", "mmlrec_tc_sm_count", "mmlrec_last_error"):
-            return getattr(self._real, name)
+        if name in ("mmlrec_l2_scratch", "mmlrec_tc_sm_count", "mmlrec_last_error") or name.endswith("_scratch") \
+                or name.endswith("_smem"):
+            return getattr(self._real, name)   # host-side size queries: no device work
         raise NotImplementedError(f"plan emulator: {name} is not restated")
 
     # K1: include/mmlrec_b200.h mmlrec_gather_concat
@@ -171,51 +173,313 @@ class FakeLib:
                 view(d.colsum, np.float32, d.M)[:] += a_sum
         return 0
 
-    # K4: MmlrecHead, mmlrec_heads_forward_backward (flags 0: independent heads)
-    def mmlrec_heads_forward_backward(self, table, T, B, y, ldy, pred, ldp, loss, flags, training, scratch, n_scratch,
-                                      counter, stream):
+    # K4: MmlrecHead (include/mmlrec_b200.h): flags bit 0 esmm, bit 1 cumulative biases, bit 2 one shared bias
+    def _heads(self, table, T, B, y, ldy, mask, ldm, pred, ldp, loss, flags, training, external):
         self.calls.append("heads")
-        if flags:
-            raise NotImplementedError("plan emulator: plain heads only")
         raw = bytes(view(table, np.uint8, T * C.sizeof(L.Head)))
         heads = [L.Head.from_buffer_copy(raw, i * C.sizeof(L.Head)) for i in range(T)]
+        esmm, cum, shared = bool(flags & 1), bool(flags & 2), bool(flags & 4)
         P = view2(pred, np.float32, B, T, ldp)
-        total = 0.0
         lossv = view(loss, np.float32, T + 1)
-        wrote = set()
-        dh_sum = {}   # heads that share an input: the kernel sums their contributions to d(h) (include/mmlrec_b200.h)
+        scal = lambda p: float(view(p, np.float32, 1)[0]) if p else 0.0   # noqa: E731
+        sig32 = lambda v: (1.0 / (1.0 + np.exp(-v.astype(np.float32)))).astype(np.float32).astype(np.float64)   # noqa: E731
+        hv = [view2(h.h, np.float32, B, h.H, h.ld_h).astype(np.float64) for h in heads]
+        wv = [view(h.w, np.float32, h.H).astype(np.float64) for h in heads]
+        z = []
         for t, h in enumerate(heads):
-            assert h.kind == L.HEAD_SIGMOID_BCE
-            hv = view2(h.h, np.float32, B, h.H, h.ld_h).astype(np.float64)
-            w = view(h.w, np.float32, h.H).astype(np.float64)
-            z = hv @ w + (float(view(h.bias, np.float32, 1)[0]) if h.bias else 0.0)
-            p = 1.0 / (1.0 + np.exp(-z))
-            P[:, t] = p.astype(np.float32)
-            if not training:
-                continue
-            yt = view2(y, np.float32, B, T, ldy)[:, t].astype(np.float64)
-            p32 = P[:, t].astype(np.float64)
-            lt = -(yt * np.maximum(np.log(p32), -100.0) + (1 - yt) * np.maximum(np.log1p(-p32), -100.0)).sum()
-            lossv[t] = lt
-            total += lt
-            dz = p32 - yt
-            for dst in (h.dw, h.dbias):
-                assert not dst or _ptr(dst) not in wrote, "two heads assign the same gradient"
-                wrote.add(_ptr(dst))
-            view(h.dw, np.float32, h.H)[:] = (dz[:, None] * hv).sum(0).astype(np.float32)
-            if h.dbias:
-                view(h.dbias, np.float32, 1)[0] = np.float32(dz.sum())
-            dh = dz[:, None] * w[None, :]
-            if h.relu_mask:
-                dh = np.where(hv > 0, dh, 0.0)
+            zt = hv[t] @ wv[t] + scal(h.bias) + scal(h.bias2)
+            if cum:
+                zt = zt + sum(scal(heads[q].bias) for q in range(t))
+            z.append(zt)
+        Y = view2(y, np.float32, B, T, ldy).astype(np.float64) if (training or external) else None
+        M = view2(mask, np.float32, B, int(ldm), ldm).astype(np.float64) if mask else None
+        dz, lt = [None] * T, [0.0] * T
+        cross = None
+        for t, h in enumerate(heads):
+            if h.kind == L.HEAD_SIGMOID_BCE:
+                # the probability is an fp32 number in the kernel: a saturated logit gives exactly 1.0f, hence a zero
+                # (1 - p) p factor and the reference's zero gradient behind the -100 clamp
+                p = sig32(z[t])
+                out, scale = p, np.ones(B)
+                if esmm and t == 1:
+                    p0 = sig32(z[0])
+                    out, scale = p0 * p, p0
+                if M is not None:
+                    mk = M[:, h.mask_col]
+                    out, scale = out * mk, scale * mk
+                else:
+                    mk = 1.0
+                P[:, t] = out.astype(np.float32)
+                if Y is None:
+                    continue
+                o32 = P[:, t].astype(np.float64)
+                if external:
+                    gout = Y[:, t]
+                else:
+                    with np.errstate(divide="ignore"):
+                        lt[t] = float((mk * ((Y[:, t] - 1) * np.maximum(np.log1p(-o32), -100.0)
+                                             - Y[:, t] * np.maximum(np.log(o32), -100.0))).sum())
+                    gout = mk * (o32 - Y[:, t]) / np.maximum((1 - o32) * o32, 1e-12)
+                dz[t] = gout * scale * (1 - p) * p
+                if esmm and t == 1:
+                    cross = gout * p
+            else:
+                P[:, t] = z[t].astype(np.float32)
+                if Y is None:
+                    continue
+                if external:
+                    dz[t] = Y[:, t]
+                else:
+                    d = z[t] - Y[:, t]
+                    lt[t] = float((d * d).sum())
+                    dz[t] = 2 * d
+        if Y is None:
+            return 0
+        if esmm:
+            p0 = sig32(z[0])
+            dz[0] = dz[0] + cross * (1 - p0) * p0
+        for t in range(T):
+            lossv[t] = 0.0 if external else lt[t]
+        lossv[T] = 0.0 if external else sum(lt)
+        # dw: heads that share one final layer share its gradient (sum in task order); d(h): heads that read the same
+        # activation share its gradient buffer (the kernel writes the sum once)
+        dw_sum, dh_sum = {}, {}
+        for t, h in enumerate(heads):
+            dw_sum[_ptr(h.dw)] = dw_sum.get(_ptr(h.dw), 0.0) + (dz[t][:, None] * hv[t]).sum(0)
             key = (_ptr(h.d_h), _ptr(h.d_h_bf16))
-            dh = dh_sum[key] = dh_sum.get(key, 0.0) + dh
-            if h.d_h:
-                view2(h.d_h, np.float32, B, h.H, h.ld_d_h)[:] = dh.astype(np.float32)
-            if h.d_h_bf16:
-                view2(h.d_h_bf16, np.uint16, B, h.H, h.ld_d_h_bf16)[:] = f32_to_bf16(dh).reshape(B, h.H)
-        if training:
-            lossv[T] = total
+            if key != (0, 0):
+                dh_sum[key] = dh_sum.get(key, 0.0) + dz[t][:, None] * wv[t][None, :]
+        for t, h in enumerate(heads):
+            view(h.dw, np.float32, h.H)[:] = dw_sum[_ptr(h.dw)].astype(np.float32)
+            key = (_ptr(h.d_h), _ptr(h.d_h_bf16))
+            if key != (0, 0):
+                dh = np.where(hv[t] > 0, dh_sum[key], 0.0) if h.relu_mask else dh_sum[key]
+                if h.d_h:
+                    view2(h.d_h, np.float32, B, h.H, h.ld_d_h)[:] = dh.astype(np.float32)
+                if h.d_h_bf16:
+                    view2(h.d_h_bf16, np.uint16, B, h.H, h.ld_d_h_bf16)[:] = f32_to_bf16(dh).reshape(B, h.H)
+        tot = [float(d.sum()) for d in dz]
+        if esmm or shared:
+            if heads[0].dbias:
+                view(heads[0].dbias, np.float32, 1)[0] = np.float32(sum(tot))
+        elif cum:
+            for q, h in enumerate(heads):
+                if h.dbias:
+                    view(h.dbias, np.float32, 1)[0] = np.float32(sum(tot[q:]))
+        else:
+            for q, h in enumerate(heads):
+                if h.dbias:
+                    view(h.dbias, np.float32, 1)[0] = np.float32(tot[q])
+        for q, h in enumerate(heads):
+            if h.dbias2:
+                view(h.dbias2, np.float32, 1)[0] = np.float32(tot[q])
+        return 0
+
+    def mmlrec_heads_forward_backward(self, table, T, B, y, ldy, pred, ldp, loss, flags, training, scratch, n_scratch,
+                                      counter, stream):
+        return self._heads(table, T, B, y, ldy, None, 0, pred, ldp, loss, flags, training, False)
+
+    def mmlrec_heads_forward_backward_masked(self, table, T, B, y, ldy, mask, ldm, pred, ldp, loss, flags, training,
+                                             scratch, n_scratch, counter, stream):
+        return self._heads(table, T, B, y, ldy, mask, ldm, pred, ldp, loss, flags, training, False)
+
+    def mmlrec_heads_backward_external(self, table, T, B, d_pred, ld_d_pred, pred, ldp, loss, flags, scratch, n_scratch,
+                                       counter, stream):
+        return self._heads(table, T, B, d_pred, ld_d_pred, None, 0, pred, ldp, loss, flags, True, True)
+
+    # gate head + softmax + mixture of a level (MmlrecGateLevel; the tiled and the plain kernels share these semantics)
+    @staticmethod
+    def _level(level):
+        return L.GateLevel.from_buffer_copy(bytes(view(level, np.uint8, C.sizeof(L.GateLevel))))
+
+    def _gate_level_forward(self, level, B):
+        self.calls.append("gate_level_forward")
+        r = self._level(level)
+        ex = [view2(r.expert[u], np.float32, B, r.H, r.ld_expert).astype(np.float64) for u in range(r.n_experts)]
+        for g in range(r.n_gates):
+            gi = view2(r.gate_in[g], np.float32, B, r.Hg[g], r.ld_gate_in[g]).astype(np.float64)
+            Wg = view2(r.Wg[g], np.float32, r.n_e[g], r.Hg[g], r.ld_Wg[g]).astype(np.float64)
+            logit = gi @ Wg.T
+            e = np.exp(logit - logit.max(1, keepdims=True))
+            p = e / e.sum(1, keepdims=True)
+            view2(r.probs[g], np.float32, B, r.n_e[g], r.n_e[g])[:] = p.astype(np.float32)
+            mix = np.zeros((B, r.H))
+            for u in range(r.n_experts):
+                if r.slot[u][g] >= 0:
+                    mix += p[:, r.slot[u][g]][:, None] * ex[u]
+            view2(r.mix[g], np.float32, B, r.H, r.ld_mix[g])[:] = mix.astype(np.float32)
+            if r.mix_bf16[g]:
+                view2(r.mix_bf16[g], np.uint16, B, r.H, r.ld_mix_bf16[g])[:] = f32_to_bf16(mix).reshape(B, r.H)
+        return 0
+
+    def mmlrec_gate_level_forward(self, level, B, stream):
+        return self._gate_level_forward(level, B)
+
+    def mmlrec_gate_level_forward_tiled(self, level, B, n_experts, H, total_wg, total_ne, total_hg, stream):
+        return self._gate_level_forward(level, B)
+
+    def _gate_level_backward(self, level, B, tiled):
+        self.calls.append("gate_level_backward")
+        r = self._level(level)
+        ex = [view2(r.expert[u], np.float32, B, r.H, r.ld_expert).astype(np.float64) for u in range(r.n_experts)]
+        d_ex = [np.zeros((B, r.H)) for _ in range(r.n_experts)]
+        for g in range(r.n_gates):
+            if not r.d_mix[g]:
+                continue
+            dm = view2(r.d_mix[g], np.float32, B, r.H, r.ld_d_mix[g]).astype(np.float64)
+            p = view2(r.probs[g], np.float32, B, r.n_e[g], r.n_e[g]).astype(np.float64)
+            dp = np.zeros_like(p)
+            for u in range(r.n_experts):
+                s_ = r.slot[u][g]
+                if s_ < 0:
+                    continue
+                dp[:, s_] = (dm * ex[u]).sum(1)
+                detached = bool(r.detach_mask[u] >> g & 1)
+                assert tiled or not detached, "detached pairs need the tiled backward"
+                if not detached:
+                    d_ex[u] += p[:, s_][:, None] * dm
+            dlogit = p * (dp - (p * dp).sum(1, keepdims=True))
+            gi = view2(r.gate_in[g], np.float32, B, r.Hg[g], r.ld_gate_in[g]).astype(np.float64)
+            Wg = view2(r.Wg[g], np.float32, r.n_e[g], r.Hg[g], r.ld_Wg[g]).astype(np.float64)
+            view2(r.dWg[g], np.float32, r.n_e[g], r.Hg[g], r.ld_Wg[g])[:] = (dlogit.T @ gi).astype(np.float32)
+            dgi = dlogit @ Wg
+            if r.relu_mask_gate_in[g]:
+                dgi = np.where(gi > 0, dgi, 0.0)
+            if r.d_gate_in[g]:
+                dst = view2(r.d_gate_in[g], np.float32, B, r.Hg[g], r.ld_d_gate_in[g])
+                dst[:] = (dst + dgi).astype(np.float32) if r.accumulate_d_gate_in[g] else dgi.astype(np.float32)
+            if r.d_gate_in_bf16[g]:
+                view2(r.d_gate_in_bf16[g], np.uint16, B, r.Hg[g], r.ld_d_gate_in_bf16[g])[:] = \
+                    f32_to_bf16(dgi).reshape(B, r.Hg[g])
+        for u in range(r.n_experts):
+            if not (r.d_expert[u] or r.d_expert_bf16[u]):
+                continue
+            v = np.where(ex[u] > 0, d_ex[u], 0.0) if r.expert_relu else d_ex[u]
+            if r.d_expert[u]:
+                view2(r.d_expert[u], np.float32, B, r.H, r.ld_d_expert)[:] = v.astype(np.float32)
+            if r.d_expert_bf16[u]:
+                view2(r.d_expert_bf16[u], np.uint16, B, r.H, r.ld_d_expert_bf16)[:] = f32_to_bf16(v).reshape(B, r.H)
+        return 0
+
+    def mmlrec_gate_level_backward(self, level, B, total_wg, total_ne, total_hg, scratch, counter, stream):
+        return self._gate_level_backward(level, B, False)
+
+    def mmlrec_gate_level_backward_tiled(self, level, B, n_gates, n_experts, H, total_wg, total_ne, total_hg, scratch,
+                                         stream):
+        return self._gate_level_backward(level, B, True)
+
+    # BatchNorm1d + activation (training statistics over the batch, momentum 0.1, eps 1e-5, unbiased running variance)
+    def mmlrec_bn_forward(self, Z, ldz, M, N, gamma, beta, rmean, rvar, nbt, n_tracked, smean, sinv, Y, ldy, Y16, ldy16,
+                          act, training, stream):
+        self.calls.append("bn_forward")
+        z = view2(Z, np.float32, M, N, ldz).astype(np.float64)
+        g, b_ = view(gamma, np.float32, N).astype(np.float64), view(beta, np.float32, N).astype(np.float64)
+        rm, rv = view(rmean, np.float32, N), view(rvar, np.float32, N)
+        if training == 1:
+            if M <= 1:
+                return -1
+            mean, var = z.mean(0), z.var(0)
+            inv = 1.0 / np.sqrt(var + 1e-5)
+            view(smean, np.float32, N)[:] = mean
+            view(sinv, np.float32, N)[:] = inv
+            rm[:] = (0.9 * rm + 0.1 * mean).astype(np.float32)
+            rv[:] = (0.9 * rv + 0.1 * var * M / (M - 1)).astype(np.float32)
+            view(nbt, np.int64, n_tracked)[:] += 1
+        elif training == 2:
+            mean, inv = view(smean, np.float32, N).astype(np.float64), view(sinv, np.float32, N).astype(np.float64)
+        else:
+            mean, inv = rm.astype(np.float64), 1.0 / np.sqrt(rv.astype(np.float64) + 1e-5)
+        out = _act((z - mean) * inv * g + b_, act)
+        if _ptr(Y):
+            view2(Y, np.float32, M, N, ldy)[:] = out.astype(np.float32)
+        if _ptr(Y16):
+            view2(Y16, np.uint16, M, N, ldy16)[:] = f32_to_bf16(out).reshape(M, N)
+        return 0
+
+    def mmlrec_bn_backward(self, dY, lddy, Z, ldz, M, N, gamma, smean, sinv, dZ, lddz, dZ16, lddz16, dgamma, dbeta, stream):
+        self.calls.append("bn_backward")
+        dy = view2(dY, np.float32, M, N, lddy).astype(np.float64)
+        z = view2(Z, np.float32, M, N, ldz).astype(np.float64)
+        g = view(gamma, np.float32, N).astype(np.float64)
+        mean, inv = view(smean, np.float32, N).astype(np.float64), view(sinv, np.float32, N).astype(np.float64)
+        xhat = (z - mean) * inv
+        dg, db = (dy * xhat).sum(0), dy.sum(0)
+        view(dgamma, np.float32, N)[:] = dg
+        view(dbeta, np.float32, N)[:] = db
+        dz = g * inv * (dy - db / M - xhat * dg / M)
+        if _ptr(dZ):
+            view2(dZ, np.float32, M, N, lddz)[:] = dz.astype(np.float32)
+        if _ptr(dZ16):
+            view2(dZ16, np.uint16, M, N, lddz16)[:] = f32_to_bf16(dz).reshape(M, N)
+        return 0
+
+    # PEPNet: element-wise product with the producers' activation derivatives folded into the gradient writes
+    def mmlrec_mul_forward(self, a, lda, b, ldb, o32, ld32, o16, ld16, rows, cols, stream):
+        self.calls.append("mul_forward")
+        v = view2(a, np.float32, rows, cols, lda).astype(np.float64) * view2(b, np.float32, rows, cols, ldb)
+        if _ptr(o32):
+            view2(o32, np.float32, rows, cols, ld32)[:] = v.astype(np.float32)
+        if _ptr(o16):
+            view2(o16, np.uint16, rows, cols, ld16)[:] = f32_to_bf16(v).reshape(rows, cols)
+        return 0
+
+    def mmlrec_mul_backward(self, d_out, ld_dout, a, lda, b, ldb, da32, da16, ld_da, dkind_a, acc_a, db32, db16, ld_db,
+                            dkind_b, acc_b, rows, cols, stream):
+        self.calls.append("mul_backward")
+        g = view2(d_out, np.float32, rows, cols, ld_dout).astype(np.float64)
+        av = view2(a, np.float32, rows, cols, lda).astype(np.float64)
+        bv = view2(b, np.float32, rows, cols, ldb).astype(np.float64)
+
+        def fold(v, own, dkind):
+            if dkind == 1:
+                return np.where(own > 0, v, 0.0)
+            if dkind == 2:
+                return v * own * (1 - own / 2)
+            return v
+        for val, p32, p16, ld, acc in ((fold(g * bv, av, dkind_a), da32, da16, ld_da, acc_a),
+                                       (fold(g * av, bv, dkind_b), db32, db16, ld_db, acc_b)):
+            if _ptr(p32):
+                dst = view2(p32, np.float32, rows, cols, ld)
+                dst[:] = (dst + val).astype(np.float32) if acc else val.astype(np.float32)
+            if _ptr(p16):
+                assert not acc
+                view2(p16, np.uint16, rows, cols, ld)[:] = f32_to_bf16(val).reshape(rows, cols)
+        return 0
+
+    # STAR: effective per-domain weights shared * specific and the fold of their gradients
+    def mmlrec_star_weights(self, spec_ptrs, spec_b_ptrs, shared, shared_b, T, K, N, w_eff, ld_w, w16, b_eff, stream):
+        self.calls.append("star_weights")
+        sp, sb = view(spec_ptrs, np.int64, T), view(spec_b_ptrs, np.int64, T)
+        sh = view(shared, np.float32, K * N).reshape(K, N).astype(np.float64)
+        shb = view(shared_b, np.float32, N).astype(np.float64)
+        for t in range(T):
+            w = (view(int(sp[t]), np.float32, K * N).reshape(K, N) * sh).T      # [N, K]
+            view2(_ptr(w_eff) + 4 * t * N * ld_w, np.float32, N, K, ld_w)[:] = w.astype(np.float32)
+            if _ptr(w16):
+                view2(_ptr(w16) + 2 * t * N * ld_w, np.uint16, N, K, ld_w)[:] = f32_to_bf16(w).reshape(N, K)
+            view(_ptr(b_eff) + 4 * t * N, np.float32, N)[:] = (view(int(sb[t]), np.float32, N) + shb).astype(np.float32)
+        return 0
+
+    def mmlrec_star_fold(self, d_w_eff, ld_w, d_b_eff, spec_ptrs, shared, live, T, K, N, d_shared, d_shared_b, d_spec_last,
+                         d_spec_b_last, stream):
+        self.calls.append("star_fold")
+        sp, lv = view(spec_ptrs, np.int64, T), view(live, np.int32, T)
+        sh = view(shared, np.float32, K * N).reshape(K, N).astype(np.float64)
+        acc, bacc = np.zeros((K, N)), np.zeros(N)
+        for t in range(T):
+            if not lv[t]:
+                continue
+            g = view2(_ptr(d_w_eff) + 4 * t * N * ld_w, np.float32, N, K, ld_w).astype(np.float64).T   # [K, N]
+            acc += g * view(int(sp[t]), np.float32, K * N).reshape(K, N)
+            gb = view(_ptr(d_b_eff) + 4 * t * N, np.float32, N).astype(np.float64)
+            bacc += gb
+            if t == T - 1:
+                if _ptr(d_spec_last):
+                    view(d_spec_last, np.float32, K * N)[:] = (g * sh).reshape(-1).astype(np.float32)
+                if _ptr(d_spec_b_last):
+                    view(d_spec_b_last, np.float32, N)[:] = gb.astype(np.float32)
+        view(d_shared, np.float32, K * N)[:] = acc.reshape(-1).astype(np.float32)
+        view(d_shared_b, np.float32, N)[:] = bacc.astype(np.float32)
         return 0
 
     def mmlrec_copy_cols(self, src, ld_src, d32, ld32, d16, ld16, rows, cols, stream):
@@ -363,7 +627,8 @@ class EmulatedPlan:
         launches = []
         b.tc_table = lambda descs: ("captured", launches.append([_copy_desc(d) for d in descs]) or len(launches) - 1)
         b.tc_launch = lambda tbl, stream, stamps=None: fake.run_tc(launches[tbl[1]])
-        b.dp, b.mask_domains = None, 0
+        b.dp = None
+        b.mask_domains = model.num_domains if getattr(model, "use_domain_mask", False) else 0
         model.build_graph(b)
         b.materialize()
         self.b, self.fake, self.stages = b, fake, b.stages
@@ -374,9 +639,11 @@ class EmulatedPlan:
         self.grad_slices = max([getattr(s, "split_k", 1) for s in b.stages] + [1])
         return self
 
-    def forward_backward(self, X, y):
+    def forward_backward(self, X, y, mask=None):
         self.gather.X.copy_(torch.as_tensor(X, dtype=torch.float32))
         self.heads.y.copy_(torch.as_tensor(y, dtype=torch.float32))
+        if mask is not None:
+            self.heads.mask.copy_(torch.as_tensor(mask, dtype=torch.float32))
         self.model.store.grad_slices.zero_()
         for s in self.stages:
             s.forward(0, True)

@@ -13,11 +13,11 @@ from helpers import golden_init, load_golden, make_oracle, rel_err
 from plan_emulator import EmulatedPlan
 
 
-def _model(cfg, fields, precision):
+def _model(cfg, fields, precision, domain_mask=False):
     from mmlrec_b200.model import get_model_class
     from mmlrec_b200.model.utils import DenseFeat, SparseFeat
     cfg = copy.deepcopy(cfg)
-    cfg["b200_config"] = {"precision": precision, "cuda_graph": False}
+    cfg["b200_config"] = {"precision": precision, "cuda_graph": False, "domain_mask": domain_mask}
     emb = cfg["model_config"]["emb"]
     cols = [SparseFeat(n, v, emb) if k == "sparse" else DenseFeat(n, 1) for n, k, v in fields]
     return get_model_class(cfg["model_config"]["model_name"])(cols, device="cpu", config=cfg)
@@ -46,23 +46,28 @@ def _table_grads(model, plan, X):
     return out
 
 
-CASES = ["sharedbottom_kuairec_adam", "aitm_kuairec_adam", "aitm_kuairec_notower_l2_sgd", "snr_trans_kuairec_adam",
-         "snr_trans_kuairec_1level_sgd", "mssm_kuairec_adam", "mssm_kuairec_1level_l2_sgd", "apg_movielens_adam",
-         "apg_movielens_odd_sgd"]
+def _cases():
+    from helpers import GOLDEN_CASES
+    return GOLDEN_CASES
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-@pytest.mark.parametrize("case", CASES)
+@pytest.mark.parametrize("case", _cases())
 def test_planned_step_reproduces_the_reference_golden(case, precision):
+    """Every golden case (all model families): predictions, loss, every dense gradient and the table gradients of the
+    first step, from the planned program run on the CPU."""
     z, cfg, fields = load_golden(case)
     cfg["model_config"]["l2_reg_dnn"] = 0    # the regulariser is a separate kernel (GPU tests); gradients below exclude it
-    model = _model(cfg, fields, precision)
+    masked = "step0/mask" in z.files
+    use_bn = cfg["model_config"].get("dnn_use_bn", False)
+    loose = "default_init" in case           # BatchNorm at init_std = 1e-4: gradients are rounding noise (DESIGN section 2)
+    model = _model(cfg, fields, precision, domain_mask=masked)
     plan = EmulatedPlan(model, int(z["step0/X"].shape[0]), precision)
     _load(model, z)
     plan.build()
     X, y = z["step0/X"], z["step0/y"]
-    pred, loss = plan.forward_backward(X, y)
-    tol = 1e-5 if precision == "fp32" else 2e-2
+    pred, loss = plan.forward_backward(X, y, z["step0/mask"] if masked else None)
+    tol = 1e-5 if precision == "fp32" else (5e-2 if use_bn else 2e-2)
     assert rel_err(pred, z["step0/pred"]) < tol
     assert abs(float(loss[-1]) - float(z["step0/loss"])) <= tol * abs(float(z["step0/loss"]))
     # gradients of the data term: the golden's, minus the reference's l2 term 2 * l2 * w where the case has one
@@ -73,21 +78,31 @@ def test_planned_step_reproduces_the_reference_golden(case, precision):
         _, _, want = tr.loss_and_grads(torch.from_numpy(X), torch.from_numpy(y))
     else:
         want = {k[6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("grad0/")}
+    gradless = set(str(n) for n in z["meta/gradless"])
     got_all, want_all = [], []
     for name, prm in model.named_parameters():
-        if getattr(prm, "_mm_kind", "") != "dense" or want.get(name) is None:
+        if getattr(prm, "_mm_kind", "") != "dense":
             continue
-        g, w = plan.grad(prm), want[name]
+        g = plan.grad(prm)
+        if name in gradless or want.get(name) is None:
+            assert float(g.abs().max()) == 0.0, f"{name} must not receive a gradient"
+            continue
+        if use_bn and ".linears." in name and name.endswith(".bias"):
+            continue   # exactly-zero true gradient: rounding noise in any implementation (profiles/bn_conditioning_r01.txt)
+        w = want[name]
         got_all.append(g.flatten())
         want_all.append(w.flatten())
-        if precision == "fp32":
+        if precision == "fp32" and not loose:
             assert float((g - w).abs().max()) <= 1e-5 * float(w.abs().max()) + 1e-9, name
-    assert rel_err(torch.cat(got_all), torch.cat(want_all)) < tol
+    flat_tol = 0.2 if loose else (tol if precision == "fp32" else (0.12 if use_bn else 2e-2))
+    assert rel_err(torch.cat(got_all), torch.cat(want_all)) < flat_tol
+    if loose:
+        return
     for name, g in _table_grads(model, plan, X).items():
         w = want.get(name)
         if w is not None and float(w.abs().max()) > 0:
             # bf16: one field's rows sit behind every bf16-rounded layer of the backward chain (sanity bound only)
-            assert rel_err(g, w) < (1e-5 if precision == "fp32" else 0.1), name
+            assert rel_err(g, w) < (1e-5 if precision == "fp32" else (0.25 if use_bn else 0.1)), name
 
 
 @pytest.mark.parametrize("precision,B", [("bf16", 2048), ("fp32", 1024)])
@@ -158,3 +173,44 @@ def test_apg_plan_at_full_width_matches_the_oracle(precision, B):
         want_all.append(want[name].flatten())
         assert rel_err(got_all[-1], want_all[-1]) < (1e-5 if precision == "fp32" else 0.1), name
     assert rel_err(torch.cat(got_all), torch.cat(want_all)) < tol
+
+
+@pytest.mark.parametrize("workload,kw,B", [("ae_ple_t4", dict(max_vocab=2000), 4096), ("synth26_mmoe", dict(vocab=5000), 2048)])
+def test_benchmarked_plans_at_full_width_match_the_oracle(workload, kw, B):
+    """The benchmarked programs themselves (BASELINE configs 2 and 5 at their unshrunk widths, bf16 mode, a split-K batch):
+    PLE-AE T=4 with experts [256, 128], gates [64], towers [64] -- a 3904-wide level-0 problem, 14-expert shared gate, four
+    gradient slices -- and the 26-field MMoE [512, 256]; vocabularies shrunk (they do not change the program)."""
+    from mmlrec_b200 import synthetic
+    from oracle.mmlrec_oracle import OracleTrainer
+    from helpers import oracle_columns
+    cfg, fields = synthetic.workload(workload, **kw)
+    torch.manual_seed(11)
+    model = _model(cfg, fields, "bf16")
+    with torch.no_grad():   # init_std = 1e-4 leaves activations at 1e-6: scale the seeded state up to O(0.1) signals
+        for name, prm in model.named_parameters():
+            if name.endswith(".weight") and (".linears." in name or name.startswith("embedding_dict")):
+                prm.mul_(300.0)
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    names = [n for n, _ in model.named_parameters()]
+    tr = OracleTrainer(cfg, oracle_columns(cfg, fields), {k: v for k, v in sd.items() if k in names},
+                       {k: v for k, v in sd.items() if k not in names}, names)
+    plan = EmulatedPlan(model, B, "bf16")
+    model.load_state_dict(sd, strict=True)
+    plan.build()
+    assert plan.grad_slices == min(B // 1024, 4)
+    X, y = synthetic.make_batch(cfg, fields, B, seed=5)
+    pred, loss = plan.forward_backward(X, y)
+    want_pred, want_loss, want = tr.loss_and_grads(torch.from_numpy(X), torch.from_numpy(y))
+    assert rel_err(pred, want_pred.detach()) < 2e-2
+    assert abs(float(loss[-1]) - float(want_loss)) <= 2e-2 * abs(float(want_loss))
+    got_all, want_all = [], []
+    for name, prm in model.named_parameters():
+        if getattr(prm, "_mm_kind", "") != "dense":
+            continue
+        g = plan.grad(prm)
+        if want.get(name) is None:   # PLE's allocated-but-unused shared experts / dead last-level shared gate (Q10)
+            assert float(g.abs().max()) == 0.0, name
+            continue
+        got_all.append(g.flatten())
+        want_all.append(want[name].flatten())
+    assert rel_err(torch.cat(got_all), torch.cat(want_all)) < 2e-2
