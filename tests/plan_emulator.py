@@ -413,6 +413,55 @@ class FakeLib:
             view2(dZ16, np.uint16, M, N, lddz16)[:] = f32_to_bf16(dz).reshape(M, N)
         return 0
 
+    # Synchronised BatchNorm (data parallel): per-rank moments -> all-gather -> combination; backward sums -> all-reduce
+    def mmlrec_bn_stats(self, Z, ldz, M, N, stats, stream):
+        self.calls.append("bn_stats")
+        z = view2(Z, np.float32, M, N, ldz).astype(np.float64)
+        st = view(stats, np.float32, 2 * N)
+        st[:N] = z.mean(0)
+        st[N:] = ((z - z.mean(0)) ** 2).sum(0)
+        return 0
+
+    def mmlrec_bn_combine(self, all_stats, R, M, N, rmean, rvar, nbt, n_tracked, smean, sinv, stream):
+        self.calls.append("bn_combine")
+        a = view(all_stats, np.float32, R * 2 * N).reshape(R, 2 * N).astype(np.float64)
+        mean = a[:, :N].mean(0)
+        m2 = (a[:, N:] + M * (a[:, :N] - mean) ** 2).sum(0)     # Chan's combination over equal-sized ranks
+        total = float(M * R)
+        view(smean, np.float32, N)[:] = mean
+        view(sinv, np.float32, N)[:] = 1.0 / np.sqrt(m2 / total + 1e-5)
+        rm, rv = view(rmean, np.float32, N), view(rvar, np.float32, N)
+        rm[:] = (0.9 * rm + 0.1 * mean).astype(np.float32)
+        rv[:] = (0.9 * rv + 0.1 * m2 / (total - 1)).astype(np.float32)
+        view(nbt, np.int64, n_tracked)[:] += 1
+        return 0
+
+    def mmlrec_bn_backward_sums(self, dY, lddy, Z, ldz, M, N, smean, sinv, sums, dgamma, dbeta, stream):
+        self.calls.append("bn_backward_sums")
+        dy = view2(dY, np.float32, M, N, lddy).astype(np.float64)
+        z = view2(Z, np.float32, M, N, ldz).astype(np.float64)
+        xhat = (z - view(smean, np.float32, N)) * view(sinv, np.float32, N)
+        s = view(sums, np.float32, 2 * N)
+        s[:N], s[N:] = dy.sum(0), (dy * xhat).sum(0)
+        view(dgamma, np.float32, N)[:] = s[N:]
+        view(dbeta, np.float32, N)[:] = s[:N]
+        return 0
+
+    def mmlrec_bn_backward_synced(self, dY, lddy, Z, ldz, M, N, gamma, smean, sinv, dZ, lddz, dZ16, lddz16, gsums, M_total,
+                                  stream):
+        self.calls.append("bn_backward_synced")
+        dy = view2(dY, np.float32, M, N, lddy).astype(np.float64)
+        z = view2(Z, np.float32, M, N, ldz).astype(np.float64)
+        inv = view(sinv, np.float32, N).astype(np.float64)
+        xhat = (z - view(smean, np.float32, N)) * inv
+        gs = view(gsums, np.float32, 2 * N).astype(np.float64)
+        dz = view(gamma, np.float32, N) * inv * (dy - gs[:N] / M_total - xhat * gs[N:] / M_total)
+        if _ptr(dZ):
+            view2(dZ, np.float32, M, N, lddz)[:] = dz.astype(np.float32)
+        if _ptr(dZ16):
+            view2(dZ16, np.uint16, M, N, lddz16)[:] = f32_to_bf16(dz).reshape(M, N)
+        return 0
+
     # PEPNet: element-wise product with the producers' activation derivatives folded into the gradient writes
     def mmlrec_mul_forward(self, a, lda, b, ldb, o32, ld32, o16, ld16, rows, cols, stream):
         self.calls.append("mul_forward")
@@ -605,9 +654,9 @@ class FakeLib:
 class EmulatedPlan:
     """The planned step of `model` (constructed on the CPU) at batch B, every buffer in host memory."""
 
-    def __init__(self, model, B, precision):
+    def __init__(self, model, B, precision, dp=None):
         cpu = torch.device("cpu")
-        self.model = model
+        self.model, self.dp = model, dp   # dp: a parallel.DataParallelContext (gloo): Sync-BatchNorm + gradient all-reduce
         dry = core.Builder(2, cpu, None, dry=True, precision=precision)
         model.build_graph(dry)
         model.store = FlatStore(model, dry.param_order, [t[0] for t in model.embedding_layout], cpu,
@@ -627,7 +676,7 @@ class EmulatedPlan:
         launches = []
         b.tc_table = lambda descs: ("captured", launches.append([_copy_desc(d) for d in descs]) or len(launches) - 1)
         b.tc_launch = lambda tbl, stream, stamps=None: fake.run_tc(launches[tbl[1]])
-        b.dp = None
+        b.dp = self.dp
         b.mask_domains = model.num_domains if getattr(model, "use_domain_mask", False) else 0
         model.build_graph(b)
         b.materialize()
@@ -651,6 +700,12 @@ class EmulatedPlan:
             if s is not self.gather:
                 s.backward(0)
         self.model.store.live_slices = self.grad_slices
+        if self.dp is not None:   # what StepPlan.train_step does for replicated tables: fold the slices, SUM all-reduce
+            st = self.model.store
+            for k in range(1, self.grad_slices):
+                st.dense_grad.add_(st.grad_slices[k])
+            st.live_slices = 1
+            self.dp.sum_gradients(st.dense_grad)
         return self.heads.pred.clone(), self.heads.loss.clone()
 
     def grad(self, prm):
