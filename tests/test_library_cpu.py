@@ -169,3 +169,18 @@ def test_static_tile_schedule_is_a_balanced_partition(kernel):
     # fewer tiles than SMs: one CTA per tile
     order, starts, n_ctas = b._tc_schedule(descs[:2], [0, 2, 4])
     assert n_ctas == 4 and sorted(order) == [0, 1, 2, 3]
+
+
+def test_header_is_plain_c():
+    """include/mmlrec_b200.h is the drop-in boundary: it must compile as C99 (no C++ / torch types in the signatures)."""
+    import shutil
+    import subprocess
+    import tempfile
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    with tempfile.NamedTemporaryFile("w", suffix=".c", delete=False) as f:
+        f.write('#include "mmlrec_b200.h"\nint (*probe)(void) = mmlrec_abi_version;\n')
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), f.name],
+                       capture_output=True, text=True)
+    os.unlink(f.name)
+    assert r.returncode == 0, r.stderr
