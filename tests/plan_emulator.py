@@ -673,7 +673,7 @@ class EmulatedPlan:
         b = core.Builder(self.B, cpu, model.store, dry=False, precision=self.precision)
         fake = FakeLib(b.lib)
         b.lib = fake
-        launches = []
+        launches = self.launch_tables = []   # descriptor lists of the tensor-core launches, in planning order
         b.tc_table = lambda descs: ("captured", launches.append([_copy_desc(d) for d in descs]) or len(launches) - 1)
         b.tc_launch = lambda tbl, stream, stamps=None: fake.run_tc(launches[tbl[1]])
         b.dp = self.dp
