@@ -184,3 +184,16 @@ def test_header_is_plain_c():
                        capture_output=True, text=True)
     os.unlink(f.name)
     assert r.returncode == 0, r.stderr
+
+
+def test_factory_knows_every_model_name_of_the_reference():
+    """main.py:37-68 of the reference dispatches on 15 names; every one resolves to a class of the fused step, each with a
+    golden case generated from the reference (so none is a stub)."""
+    from mmlrec_b200.model import REFERENCE_NAMES, _REGISTRY, get_model_class
+    assert len(REFERENCE_NAMES) == 15 and set(REFERENCE_NAMES) == set(_REGISTRY)
+    covered = {load_golden(c)[1]["model_config"]["model_name"].lower() for c in GOLDEN_CASES}
+    for name in REFERENCE_NAMES:
+        assert get_model_class(name.upper()) is _REGISTRY[name]   # case-insensitive like the reference's .lower()
+        assert name in covered, f"{name}: no reference-generated golden case"
+    with pytest.raises(ValueError):
+        get_model_class("no_such_model")
