@@ -142,8 +142,20 @@ WORKLOADS = {
 }
 
 
+_DATASETS = {"census": census, "ae_t4": lambda m, **k: aliexpress(m, 4, **k), "ae_t2": lambda m, **k: aliexpress(m, 2, **k),
+             "kuairec": kuairec, "movielens": movielens, "synth26": synth26}
+
+
 def workload(name: str, **kw) -> Tuple[dict, List[FieldSpec]]:
-    cfg, fields = WORKLOADS[name](**kw)
+    """A named BASELINE workload, or ``"<dataset>:<model>"`` -- any model of the zoo on a dataset shape, e.g.
+    ``"movielens:apg"``, ``"kuairec:aitm"``, ``"kuairec:mssm"`` (datasets: census, ae_t4, ae_t2, kuairec, movielens, synth26)."""
+    if name not in WORKLOADS and ":" in name:
+        dataset, model_name = name.split(":", 1)
+        if dataset not in _DATASETS:
+            raise KeyError(f"unknown dataset shape {dataset!r} (have {sorted(_DATASETS)})")
+        cfg, fields = _DATASETS[dataset](model_name, **kw)
+    else:
+        cfg, fields = WORKLOADS[name](**kw)
     return copy.deepcopy(cfg), list(fields)
 
 

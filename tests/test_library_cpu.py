@@ -197,3 +197,20 @@ def test_factory_knows_every_model_name_of_the_reference():
         assert name in covered, f"{name}: no reference-generated golden case"
     with pytest.raises(ValueError):
         get_model_class("no_such_model")
+
+
+def test_any_model_of_the_zoo_builds_on_any_dataset_shape():
+    """``synthetic.workload("<dataset>:<model>")``: the constructors accept the dataset shapes their reference classes accept."""
+    from mmlrec_b200 import synthetic
+    from mmlrec_b200.model import get_model_class
+    from mmlrec_b200.model.utils import DenseFeat, SparseFeat
+    for name, kw in (("kuairec:aitm", dict(max_vocab=50)), ("kuairec:mssm", dict(max_vocab=50)),
+                     ("kuairec:snr_trans", dict(max_vocab=50)), ("movielens:apg", dict(vocab_scale=0.01)),
+                     ("ae_t4:apg", dict(max_vocab=50)), ("census:hmoe", dict(vocab_scale=0.1))):
+        cfg, fields = synthetic.workload(name, **kw)
+        emb = cfg["model_config"]["emb"]
+        cols = [SparseFeat(n, v, emb) if k == "sparse" else DenseFeat(n, 1) for n, k, v in fields]
+        model = get_model_class(cfg["model_config"]["model_name"])(cols, device="cpu", config=cfg)
+        assert sum(p.numel() for p in model.parameters()) > 0, name
+    with pytest.raises(KeyError):
+        synthetic.workload("nowhere:mmoe")

@@ -35,7 +35,7 @@ def main():
     args = ap.parse_args()
     kw = {"max_vocab": args.max_vocab} if args.workload.startswith(("ae_", "kuairec")) else (
         {"vocab": args.max_vocab} if args.workload.startswith("synth26") else {"vocab_scale": 0.05}
-        if args.workload.startswith("movielens") else {})
+        if args.workload.startswith("movielens") else {})   # ("<dataset>:<model>" names start with the dataset too)
     cfg, fields = synthetic.workload(args.workload, **kw)
     if args.model_name:
         cfg["model_config"]["model_name"] = args.model_name
