@@ -35,8 +35,6 @@ class CrossStitch(BaseModel):
         self.tower_dnn_hidden_units = mc.get("tower_dnn_hidden_units", [64])
         kw = dict(activation=mc.get("dnn_activation", "relu"), l2_reg=mc.get("l2_reg_dnn", 0),
                   dropout_rate=mc.get("dnn_dropout", 0), use_bn=mc.get("dnn_use_bn", False), init_std=init_std)
-        if kw["use_bn"]:
-            raise NotImplementedError("CrossStitch with BatchNorm is not wired into the fused step")
         T, units = self.num_tasks, self.dnn_hidden_units
         self.input_dim = self.compute_input_dim(dnn_feature_columns)
         self.shared_layer = DNN(self.input_dim, [self.shared_hidden_unit], **kw)

@@ -33,6 +33,7 @@ class PLE(BaseModel):
         self.tower_dnn_hidden_units = mc.get("tower_dnn_hidden_units", [64])
         kw = dict(activation=mc.get("dnn_activation", "relu"), l2_reg=mc.get("l2_reg_dnn", 0),
                   dropout_rate=mc.get("dnn_dropout", 0), use_bn=mc.get("dnn_use_bn", False), init_std=init_std)
+        self.dnn_use_bn = kw["use_bn"]
         T, S, Sh, Lv = self.num_tasks, self.specific_expert_num, self.shared_expert_num, self.num_levels
         H = self.expert_dnn_hidden_units[-1]
 
@@ -90,7 +91,10 @@ class PLE(BaseModel):
             for k in range(Sh):
                 where[("shared", k)] = len(blocks)
                 blocks.append((inputs[T], self.shared_experts[lv][0][k]))
-            if has_gate_dnn and not last:
+            # the last level's shared gate feeds nothing (Q10) and is skipped -- unless its DNN carries BatchNorm: the
+            # reference still runs it (ple.py:141-148), so its running statistics move every training step; here it then
+            # rides along in the level's wide GEMM, forward only (no gradient reaches it: its parameters stay put)
+            if has_gate_dnn and (not last or self.dnn_use_bn):
                 where[("sgate",)] = len(blocks)
                 blocks.append((inputs[T], self.shared_gate_dnn[lv]))
             outs = mlp_stages(b, blocks, f"cgc{lv}")

@@ -120,6 +120,16 @@ CASES["apg_movielens_adam"] = ("movielens_star", dict(vocab_scale=0.02), dict(mo
 CASES["apg_movielens_odd_sgd"] = ("movielens_star", dict(vocab_scale=0.02), dict(model_name="apg", dnn_hidden_units=[24, 10]),
                                   dict(optimizer="sgd", lr=1e-2))
 INIT_STD.update({"apg_movielens_adam": 0.05, "apg_movielens_odd_sgd": 0.05})
+# BatchNorm variants added after the round's GPU budget was spent: checked on the CPU only (oracle + plan emulation), kept in
+# tests/golden/cpu_only/ so that the -m gpu step tests do not enumerate them.  PLE with BatchNorm: the reference keeps running
+# the dead last-level shared-gate DNN, whose running statistics therefore move; CrossStitch with BatchNorm (census shape).
+CASES["ple_census_bn_adam"] = ("census_mmoe", {}, dict(model_name="ple", expert_dnn_hidden_units=[16, 8],
+                                                       gate_dnn_hidden_units=[8], tower_dnn_hidden_units=[8],
+                                                       shared_expert_num=2, specific_expert_num=2, num_levels=2), {})
+CASES["cross_stitch_census_bn_adam"] = ("census_mmoe", {}, dict(model_name="cross_stitch", shared_hidden_unit=16,
+                                                                dnn_hidden_units=[16, 8], tower_dnn_hidden_units=[8]), {})
+CPU_ONLY = {"ple_census_bn_adam", "cross_stitch_census_bn_adam"}
+INIT_STD.update({"ple_census_bn_adam": 0.05, "cross_stitch_census_bn_adam": 0.05})
 # cases whose identity / 1e-4 initial state would leave parts of the model untested: perturbed after construction
 INIT_STD.update({"cross_stitch_kuairec_adam": 0.05, "hmoe_kuairec_adam": 0.05, "mlp_kuairec_adam": 0.05,
                  "pcg_kuairec_adam": 0.05, "mmoe_kuairec_l2_adam": 0.05, "ple_ae_t2_l2_sgd": 0.05,
@@ -143,7 +153,7 @@ def post_build(case, model):
                     prm.add_(0.05 * torch.randn(prm.shape, generator=torch.Generator().manual_seed(12)))
                     touched.append(name)
         return touched
-    if case == "cross_stitch_kuairec_adam":   # identity units exercise no off-diagonal weight: add seeded noise
+    if case in ("cross_stitch_kuairec_adam", "cross_stitch_census_bn_adam"):   # identity units exercise no off-diagonal weight: add seeded noise
         touched = []
         with torch.no_grad():
             for name, prm in model.named_parameters():
@@ -310,7 +320,8 @@ def main():
         blob["meta/init_std"] = np.array(INIT_STD.get(case, 0.0001))
         blob["meta/config"] = np.array(json.dumps(cfg))
         blob["meta/fields"] = np.array(json.dumps(fields))
-        path = os.path.join(HERE, case + ".npz")
+        path = os.path.join(HERE, "cpu_only", case + ".npz") if case in CPU_ONLY else os.path.join(HERE, case + ".npz")
+        os.makedirs(os.path.dirname(path), exist_ok=True)
         np.savez_compressed(path, **blob)
         print(f"{case:32s} {os.path.getsize(path) / 1024:8.1f} KiB  loss0={float(blob['step0/loss']):.6f}")
 

@@ -8,10 +8,16 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 GOLDEN_CASES = sorted(f[:-4] for f in os.listdir(GOLDEN) if f.endswith(".npz") and not f.startswith("fit_"))
+# cases verified on the CPU only (oracle + plan emulation): the -m gpu step tests enumerate GOLDEN_CASES, not these
+GOLDEN_CPU_ONLY = sorted(f[:-4] for f in os.listdir(os.path.join(GOLDEN, "cpu_only")) if f.endswith(".npz")) \
+    if os.path.isdir(os.path.join(GOLDEN, "cpu_only")) else []
 
 
 def load_golden(case):
-    z = np.load(os.path.join(GOLDEN, case + ".npz"), allow_pickle=False)
+    path = os.path.join(GOLDEN, case + ".npz")
+    if not os.path.exists(path):
+        path = os.path.join(GOLDEN, "cpu_only", case + ".npz")
+    z = np.load(path, allow_pickle=False)
     cfg = json.loads(str(z["meta/config"]))
     fields = [tuple(f) for f in json.loads(str(z["meta/fields"]))]
     return z, cfg, fields

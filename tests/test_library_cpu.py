@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 import torch
 
-from helpers import ROOT, GOLDEN_CASES, load_golden
+from helpers import ROOT, GOLDEN_CASES, GOLDEN_CPU_ONLY, load_golden
 
 HEADER = os.path.join(ROOT, "include", "mmlrec_b200.h")
 
@@ -63,7 +63,7 @@ def _build_cpu(case):
 
 def _implemented_cases():
     from mmlrec_b200.model import _REGISTRY
-    return [c for c in GOLDEN_CASES if load_golden(c)[1]["model_config"]["model_name"].lower() in _REGISTRY]
+    return [c for c in GOLDEN_CASES + GOLDEN_CPU_ONLY if load_golden(c)[1]["model_config"]["model_name"].lower() in _REGISTRY]
 
 
 @pytest.mark.parametrize("case", _implemented_cases())

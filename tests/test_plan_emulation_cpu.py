@@ -47,8 +47,8 @@ def _table_grads(model, plan, X):
 
 
 def _cases():
-    from helpers import GOLDEN_CASES
-    return GOLDEN_CASES
+    from helpers import GOLDEN_CASES, GOLDEN_CPU_ONLY
+    return GOLDEN_CASES + GOLDEN_CPU_ONLY
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
@@ -94,15 +94,27 @@ def test_planned_step_reproduces_the_reference_golden(case, precision):
         want_all.append(w.flatten())
         if precision == "fp32" and not loose:
             assert float((g - w).abs().max()) <= 1e-5 * float(w.abs().max()) + 1e-9, name
-    flat_tol = 0.2 if loose else (tol if precision == "fp32" else (0.12 if use_bn else 2e-2))
+    # (three BatchNorm layers deep on 48 rows -- the cpu_only cases -- the bf16 rounding is amplified further: 0.18 measured)
+    deep_bn = use_bn and cfg["model_config"]["model_name"] in ("ple", "cross_stitch")
+    flat_tol = 0.2 if loose else (tol if precision == "fp32" else (0.3 if deep_bn else 0.12 if use_bn else 2e-2))
     assert rel_err(torch.cat(got_all), torch.cat(want_all)) < flat_tol
+    if use_bn and precision == "fp32":
+        # BatchNorm running statistics after the step == the oracle's after its first step (incl. those of PLE's dead
+        # last-level shared-gate DNN, which the reference keeps running: ple.py:141-148)
+        tr.step(torch.from_numpy(X), torch.from_numpy(y), torch.from_numpy(z["step0/mask"]) if masked else None)
+        for name, buf in model.named_buffers():
+            want_buf = tr.buffers[name]
+            if buf.dtype == torch.int64:
+                assert int(buf) == int(want_buf) == 1, name
+            else:
+                assert float((buf - want_buf).abs().max()) <= 1e-5 * float(want_buf.abs().max()) + 1e-8, name
     if loose:
         return
     for name, g in _table_grads(model, plan, X).items():
         w = want.get(name)
         if w is not None and float(w.abs().max()) > 0:
             # bf16: one field's rows sit behind every bf16-rounded layer of the backward chain (sanity bound only)
-            assert rel_err(g, w) < (1e-5 if precision == "fp32" else (0.25 if use_bn else 0.1)), name
+            assert rel_err(g, w) < (1e-5 if precision == "fp32" else (0.5 if deep_bn else 0.25 if use_bn else 0.1)), name
 
 
 @pytest.mark.parametrize("precision,B", [("bf16", 2048), ("fp32", 1024)])
