@@ -57,6 +57,10 @@ class ActGroup:
     def span(self) -> "Act":
         """All columns of the group as ONE activation (torch.cat of its members, cross_stitch.py:17: free here,
         the members are adjacent columns of one buffer)."""
+        if any(x.col != sum(self.widths[:i]) for i, x in enumerate(self.acts)):
+            raise NotImplementedError(f"{self.name}: members of widths {self.widths} are padded to 16-byte boundaries in "
+                                      "bf16 mode; their concatenation is not contiguous (use widths that are multiples of 8 "
+                                      "or the fp32 mode)")
         a = Act(self, 0, self.total, f"{self.name}[*]")
         a.members = list(self.acts)
         return a
@@ -280,7 +284,10 @@ class Builder:
 
     def new_group(self, widths: Sequence[int], relu: bool, name: str, grad_dtype: str = "f32",
                   act: Optional[str] = None, align: int = 1) -> List[Act]:
-        g = ActGroup(widths, relu, name, grad_dtype if self.tc else "f32", act, align)
+        # tensor-core mode: every member starts on a 16-byte boundary (8 bf16 / 8 fp32 columns) -- what the tensor maps of
+        # the GEMMs reading or writing it need.  A no-op for widths that are multiples of 8 (every BASELINE shape); odd
+        # widths (PEPNet on the 199-wide AliExpress input, APG's k-wide outputs) get pad columns nobody reads
+        g = ActGroup(widths, relu, name, grad_dtype if self.tc else "f32", act, max(align, 8) if self.tc else align)
         self.groups.append(g)
         return g.acts
 

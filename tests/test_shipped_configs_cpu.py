@@ -1,0 +1,131 @@
+"""CPU: every model of the zoo on the shape of every JSON config the reference ships (12 configs x 15 factory names).  Where
+the reference's constructor accepts the pair, the planned fp32 program -- built by the product planner at the config's full
+layer widths and run on the CPU by tests/plan_emulator.py -- must reproduce the oracle's predictions, loss and dense
+gradients of one step to 1e-5; the bf16 program must plan (tensor-map alignment of every GEMM operand / output, odd widths
+like the 199-wide AliExpress input included) and stay within 2e-2 on the predictions."""
+import copy
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import GOLDEN, oracle_columns, rel_err
+from plan_emulator import EmulatedPlan
+
+SHAPES = json.load(open(os.path.join(GOLDEN, "shipped_configs.json")))
+V = 50
+
+
+def _rows(shape):
+    """16 rows; 64 where the config has BatchNorm (a batch of 16 leaves near-constant columns whose normalisation amplifies the
+    fp32-vs-fp64 rounding difference between the oracle and the emulation to 1e-3)"""
+    return 64 if shape["model_config"].get("dnn_use_bn", False) else 16
+
+
+def _build(shape, name, precision):
+    from mmlrec_b200.model import get_model_class
+    from mmlrec_b200.model.utils import DenseFeat, SparseFeat
+    sparse = [f"s{j}" for j in range(shape["n_sparse"])]
+    dense = [f"d{j}" for j in range(shape["n_dense"])]
+    at = lambda p: sparse[p] if p >= 0 else ""   # noqa: E731
+    cfg = {"data_config": {"label_columns": ["y"] * shape["n_labels"], "num_domains": shape["num_domains"],
+                           "mask_values": shape["mask_values"], "scene_feature": at(shape["scene_pos"]),
+                           "mask_column": at(shape["mask_pos"]), "user_sf": at(shape["user_sf_pos"]),
+                           "item_sf": at(shape["item_sf_pos"]), "feature_columns": sparse, "dense_columns": dense},
+           "model_config": dict(copy.deepcopy(shape["model_config"]), model_name=name),
+           "optim_config": copy.deepcopy(shape["optim_config"]),
+           "training_config": {"train_batch_size": 4096, "test_batch_size": 4096, "epochs": 1}, "save_config": {},
+           "b200_config": {"precision": precision, "cuda_graph": False}}
+    emb = cfg["model_config"].get("emb", 8)
+    fields = [(n, "sparse", V) for n in sparse] + [(n, "dense", 0) for n in dense]
+    cols = [SparseFeat(n, V, emb) for n in sparse] + [DenseFeat(n, 1) for n in dense]
+    torch.manual_seed(3)
+    model = get_model_class(name)(cols, init_std=0.05, device="cpu", config=cfg)
+    return model, cfg, fields
+
+
+def _oracle(model, cfg, fields, name):
+    """The oracle on the model's seeded state, incl. the tensors the reference keeps unregistered."""
+    from oracle.mmlrec_oracle import OracleTrainer
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    names = [n for n, _ in model.named_parameters()]
+    params = {k: v for k, v in sd.items() if k in names}
+    if name == "star":
+        for prefix, mods in (("linears", model.linears), ("final_layers", model.final_layers)):
+            for j, m in enumerate(mods):
+                for i in range(m.num_domains - 1):
+                    params[f"{prefix}.{j}.specific_weights.{i}"] = getattr(m, f"frozen_weight_{i}").detach().clone()
+                    params[f"{prefix}.{j}.specific_biases.{i}"] = getattr(m, f"frozen_bias_{i}").detach().clone()
+    if name in ("snr_trans", "mssm"):
+        pre, gates = ("trans", model.trans) if name == "snr_trans" else ("mssm", model.mssm)
+        for gname, g in gates.items():
+            if gname.startswith("gate"):
+                for i in range(g.output_dim):
+                    for j in range(g.input_dim):
+                        params[f"{pre}.{gname}.trans_matrix.{i}.{j}"] = g.trans_matrix[i, j].clone()
+                        if name == "mssm":
+                            params[f"{pre}.{gname}.u.{i}.{j}"] = g.u[i, j].clone()
+    tr = OracleTrainer(cfg, oracle_columns(cfg, fields), params, {k: v for k, v in sd.items() if k not in names}, names)
+    return tr, sd
+
+
+def _batch(shape, model):
+    B = _rows(shape)
+    rng = np.random.default_rng(1)
+    X = np.concatenate([rng.integers(0, V, (B, shape["n_sparse"])).astype(np.float32),
+                        rng.random((B, shape["n_dense"])).astype(np.float32)], 1)
+    y = (rng.random((B, model.num_tasks)) > 0.5).astype(np.float32)
+    return X, y
+
+
+@pytest.mark.parametrize("shape", SHAPES, ids=[s["config"] for s in SHAPES])
+def test_every_model_on_every_shipped_config_shape(shape):
+    from mmlrec_b200.engine.core import SnrGateStage
+    from mmlrec_b200.model import REFERENCE_NAMES
+    ran = 0
+    for name in REFERENCE_NAMES:
+        if name == "pcg":
+            continue   # an MMoE (main.py:53-54): covered by 'mmoe'
+        try:
+            model, cfg, fields = _build(shape, name, "fp32")
+        except ValueError:
+            continue   # the reference's constructor rejects the pair too (two-task models, models that need a scene feature)
+        tr, sd = _oracle(model, cfg, fields, name)
+        X, y = _batch(shape, model)
+        want_pred, want_loss, want = tr.loss_and_grads(torch.from_numpy(X), torch.from_numpy(y))
+        for precision in ("fp32", "bf16"):
+            if precision == "bf16":
+                model, cfg, fields = _build(shape, name, "bf16")
+            try:
+                plan = EmulatedPlan(model, _rows(shape), precision)
+                model.load_state_dict(sd, strict=True)
+                plan.build()
+            except NotImplementedError as e:
+                # the one known limit: MLP's final layer is shared by all heads, which the one-launch head kernel sums only
+                # up to 128 columns (KuaiRec MTL config: dnn_hidden_units [512, 256])
+                assert name == "mlp" and "shared by several heads" in str(e), (name, precision, str(e))
+                break
+            pred, loss = plan.forward_backward(X, y)
+            tol = 1e-5 if precision == "fp32" else 2e-2
+            assert rel_err(pred, want_pred.detach()) < tol, (name, precision)
+            assert abs(float(loss[-1]) - float(want_loss)) <= tol * abs(float(want_loss)), (name, precision)
+            ran += 1
+            if precision == "bf16":
+                continue   # (bf16 gradients at 32 random rows are cancellation noise: the benchmarked shapes pin them)
+            # hard-concrete gates that are all closed at this seed leave the towers a CONSTANT input: BatchNorm of a constant
+            # is rounding noise in any implementation (the oracle's too) -- nothing to compare behind it
+            closed = any(isinstance(st, SnrGateStage) and float(st.derived.weight.abs().max()) == 0.0 for st in plan.stages)
+            if closed and cfg["model_config"].get("dnn_use_bn", False):
+                continue
+            got_all, want_all = [], []
+            for pname, prm in model.named_parameters():
+                if getattr(prm, "_mm_kind", "") != "dense" or want.get(pname) is None:
+                    continue
+                if cfg["model_config"].get("dnn_use_bn", False) and ".linears." in pname and pname.endswith(".bias"):
+                    continue   # exactly-zero true gradient in front of BatchNorm
+                got_all.append(plan.grad(prm).flatten())
+                want_all.append(want[pname].flatten())
+            assert rel_err(torch.cat(got_all), torch.cat(want_all)) < 1e-5, (name, "dense gradient vector")
+    assert ran >= 20, "most models must build on every shipped config shape"
