@@ -1281,6 +1281,13 @@ static int heads_launch(const MmlrecHead* heads, int32_t T, int32_t B, const flo
                  esmm, scratch, stride_cta, counters, grad_mode, mask, ldm);
       MMLREC_RETURN_LAUNCH(1);
     }
+    // wide heads (129..256 columns) whose biases are cumulative or shared -- MLP / ESCM on the KuaiRec shape, [512, 256] --
+    // exist only in the one-launch kernel; everything else that wide keeps the two-kernel path below
+    if ((esmm & 6) && T <= 4 && hmax <= 256) {
+      launch_pdl(heads_fast_kernel<4, 8, 2>, dim3(cdiv(B, 16)), dim3(256), 0, stream, heads, T, B, y, ldy, pred, ld_pred, loss,
+                 esmm, scratch, stride_cta, counters, grad_mode, mask, ldm);
+      MMLREC_RETURN_LAUNCH(1);
+    }
   }
   MMLREC_CHECK_ARG(!((esmm & 6) && training && y != nullptr), "cumulative / shared biases are handled by the one-launch kernel only");
   launch_pdl(heads_kernel, dim3(n_cta), dim3(256), smem, stream, heads, T, B, y, ldy, pred, ld_pred, loss, esmm, training, scratch,

@@ -1481,8 +1481,10 @@ class HeadStage(Stage):
             h.h.want(f32=True)
         # heads sharing one final layer (MLP): only the one-launch head kernel sums their weight gradients
         shared = len({id(h.final.weight) for h in heads}) < len(heads)
-        if shared and not (self.T <= 8 and max(h.h.width for h in heads) <= 128):
-            raise NotImplementedError("a final layer shared by several heads needs T <= 8 tasks of width <= 128")
+        wmax = max(h.h.width for h in heads)
+        if shared and not ((self.T <= 8 and wmax <= 128) or (self.T <= 4 and wmax <= 256 and cumulative_bias)):
+            raise NotImplementedError("a final layer shared by several heads needs T <= 8 tasks of width <= 128 "
+                                      "(or T <= 4 of width <= 256 with cumulative biases: MLP)")
 
     def finalize(self):
         b, st = self.b, self.b.store
@@ -1511,7 +1513,8 @@ class HeadStage(Stage):
                 # an activation read by several heads of this stage: the head kernel sums their contributions
                 again = any(o.h.same_as(h.h) for o in self.heads[:self.heads.index(h)])
                 assert again or not h.h.grad_written
-                assert not again or (self.T <= 8 and h.h.width <= 128), "heads sharing an input need the one-launch kernel"
+                assert not again or (self.T <= 8 and h.h.width <= 128) or \
+                    (self.T <= 4 and h.h.width <= 256 and (self.flags & 6)), "heads sharing an input need the one-launch kernel"
                 if h.h.grad_is_f32:
                     r.d_h, r.ld_d_h = h.h.gptr, h.h.gld
                 else:

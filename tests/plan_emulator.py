@@ -179,6 +179,14 @@ class FakeLib:
         raw = bytes(view(table, np.uint8, T * C.sizeof(L.Head)))
         heads = [L.Head.from_buffer_copy(raw, i * C.sizeof(L.Head)) for i in range(T)]
         esmm, cum, shared = bool(flags & 1), bool(flags & 2), bool(flags & 4)
+        if training or external:
+            # the dispatch of heads_launch (csrc/fused_ops.cu): cumulative / shared biases and heads that share an input or
+            # a final layer exist only in the one-launch kernel, which is instantiated for these shapes
+            hmax = max(h.H for h in heads)
+            one_launch = (T <= 4 and hmax <= 64) or (T <= 8 and hmax <= 128) or (bool(flags & 6) and T <= 4 and hmax <= 256)
+            sharing = len({_ptr(h.h) for h in heads}) < T or len({_ptr(h.dw) for h in heads}) < T
+            if ((flags & 6) or sharing) and not one_launch:
+                return -1
         P = view2(pred, np.float32, B, T, ldp)
         lossv = view(loss, np.float32, T + 1)
         scal = lambda p: float(view(p, np.float32, 1)[0]) if p else 0.0   # noqa: E731
