@@ -226,3 +226,20 @@ def test_benchmarked_plans_at_full_width_match_the_oracle(workload, kw, B):
         got_all.append(g.flatten())
         want_all.append(want[name].flatten())
     assert rel_err(torch.cat(got_all), torch.cat(want_all)) < 2e-2
+
+
+def test_gpu_tested_programs_are_unchanged():
+    """profiles/plan_fingerprints_r02.json was written from the tree of the last full `pytest -m gpu` run on B200.  A planner
+    change that alters a program the GPU suite or the bench runs (buffer columns, gradient precisions, parameter order, stage
+    list) shows up here: re-run the GPU suite, then regenerate the file with tools/plan_fingerprint.py."""
+    import json
+    import os
+    import subprocess
+    import sys
+    from helpers import ROOT
+    want = json.load(open(os.path.join(ROOT, "profiles", "plan_fingerprints_r02.json")))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "plan_fingerprint.py")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = json.loads(r.stdout)
+    changed = sorted(k for k in want if got.get(k) != want[k])
+    assert not changed, f"planned programs changed since the last GPU run: {changed[:8]}"
