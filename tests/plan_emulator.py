@@ -324,6 +324,11 @@ class FakeLib:
         return self._gate_level_forward(level, B)
 
     def mmlrec_gate_level_forward_tiled(self, level, B, n_experts, H, total_wg, total_ne, total_hg, stream):
+        # the launcher's limits (csrc/gate_level.cu)
+        if not (0 < n_experts <= L.LEVEL_MAX_EXPERTS and H % 4 == 0 and total_wg % 4 == 0 and total_hg % 4 == 0
+                and 0 < total_ne <= L.LEVEL_MAX_GATES * L.LEVEL_MAX_EXPERTS
+                and self._real.mmlrec_gate_level_forward_tiled_smem(n_experts, H, total_wg, total_ne, total_hg) <= 110 * 1024):
+            return -1
         return self._gate_level_forward(level, B)
 
     def _gate_level_backward(self, level, B, tiled):
@@ -370,10 +375,18 @@ class FakeLib:
         return 0
 
     def mmlrec_gate_level_backward(self, level, B, total_wg, total_ne, total_hg, scratch, counter, stream):
+        # the launcher's limits: staged gate-head weights and 8 rows of (dlogits + gate inputs) in shared memory
+        if not (0 < total_wg <= L.LEVEL_MAX_WG and 8 * (total_ne + total_hg) * 4 <= 160 * 1024):
+            return -1
         return self._gate_level_backward(level, B, False)
 
     def mmlrec_gate_level_backward_tiled(self, level, B, n_gates, n_experts, H, total_wg, total_ne, total_hg, scratch,
                                          stream):
+        if not (0 < n_gates <= L.LEVEL_MAX_GATES and 0 < n_experts <= L.LEVEL_MAX_EXPERTS and H % 4 == 0
+                and total_wg % 4 == 0 and total_hg % 4 == 0
+                and self._real.mmlrec_gate_level_backward_tiled_smem(n_gates, n_experts, H, total_wg, total_ne,
+                                                                     total_hg) <= 110 * 1024):
+            return -1
         return self._gate_level_backward(level, B, True)
 
     # BatchNorm1d + activation (training statistics over the batch, momentum 0.1, eps 1e-5, unbiased running variance)
