@@ -746,6 +746,13 @@ def _check_tc_desc(d):
     assert not d.C_bf16 or (d.ldc_bf16 % 8 == 0 and _ptr(d.C_bf16) % 16 == 0), "C_bf16 alignment"
     assert not d.mask or (d.ldmask % 8 == 0 and _ptr(d.mask) % 16 == 0), "mask alignment"
     assert not d.colsum_b or d.c_transposed, "colsum_b comes with c_transposed"
+    if d.c_transposed:
+        assert d.C_f32 and not (d.C_bf16 or d.bias or d.mask or d.mask_bits or d.relu_bits_out or d.colsum or d.act
+                                or d.accumulate) and (not d.colsum_b or d.N <= 128), \
+            "a transposed store takes the plain fp32 product only"
+    assert not d.relu_bits_out or d.bits_out_chunks > 0, "bits_out_chunks"
+    assert not d.mask_bits or d.mask_bits_chunks > 0, "mask_bits_chunks"
+    assert d.C_f32 or d.C_bf16, "a problem without an output"
 
 
 def _copy_desc(d):
