@@ -126,4 +126,11 @@ def test_every_model_on_every_shipped_config_shape(shape):
                 got_all.append(plan.grad(prm).flatten())
                 want_all.append(want[pname].flatten())
             assert rel_err(torch.cat(got_all), torch.cat(want_all)) < 1e-5, (name, "dense gradient vector")
+            # the forward-only program (predict / evaluate: BatchNorm on its running statistics, which the training pass above
+            # has just moved in both implementations; heads without a loss)
+            for st in plan.stages:
+                st.forward(0, False)
+            with torch.no_grad():
+                want_eval = tr.forward(torch.from_numpy(X), training=False)
+            assert rel_err(plan.heads.pred, want_eval) < 1e-5, (name, "eval-mode forward")
     assert ran >= 20, "most models must build on every shipped config shape"
