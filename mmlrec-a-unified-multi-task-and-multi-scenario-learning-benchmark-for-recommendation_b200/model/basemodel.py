@@ -156,8 +156,13 @@ class BaseModel(nn.Module):
         if self.use_domain_mask:
             if self.task_name not in ("msl", "mtmsl"):
                 raise ValueError('b200_config["domain_mask"] needs task_name "msl" or "mtmsl"')
-            if self.model_config.get("model_name", "").lower() == "star":
-                raise NotImplementedError("STAR with a domain mask goes through DomainBatchNorm (not built)")
+            mname = self.model_config.get("model_name", "").lower()
+            if mname == "star" and self.model_config.get("dnn_use_bn", False):
+                # star.py:50-51: only with dnn_use_bn does the mask route the first layer through DomainBatchNorm
+                raise NotImplementedError("STAR with a domain mask AND BatchNorm goes through DomainBatchNorm (not built)")
+            if mname in ("esmm", "escm"):
+                # esmm.py:46-62 / escm.py:74-96 take the argument and never use it: there is no masked ESMM to reproduce
+                raise NotImplementedError(f"{mname}: the reference's forward ignores the domain mask")
         self.optimizer_name: Optional[str] = None
         self.lazy_adam, self.adam_hist, self._steps_since_flush = False, None, 0
         self._user_optimizer = None

@@ -187,11 +187,16 @@ def test_apg_plan_at_full_width_matches_the_oracle(precision, B):
     assert rel_err(torch.cat(got_all), torch.cat(want_all)) < tol
 
 
-@pytest.mark.parametrize("workload,kw,B", [("ae_ple_t4", dict(max_vocab=2000), 4096), ("synth26_mmoe", dict(vocab=5000), 2048)])
+import os  # noqa: E402
+
+
+@pytest.mark.parametrize("workload,kw,B", [("ae_ple_t4", dict(max_vocab=2000), 4096 if os.environ.get("MMLREC_ALL_CONFIGS") else 2048),
+                                           ("synth26_mmoe", dict(vocab=5000), 2048)])
 def test_benchmarked_plans_at_full_width_match_the_oracle(workload, kw, B):
     """The benchmarked programs themselves (BASELINE configs 2 and 5 at their unshrunk widths, bf16 mode, a split-K batch):
-    PLE-AE T=4 with experts [256, 128], gates [64], towers [64] -- a 3904-wide level-0 problem, 14-expert shared gate, four
-    gradient slices -- and the 26-field MMoE [512, 256]; vocabularies shrunk (they do not change the program)."""
+    PLE-AE T=4 with experts [256, 128], gates [64], towers [64] -- a 3904-wide level-0 problem, 14-expert shared gate, two
+    gradient slices at B = 2048 (four at the benchmarked 4096 with MMLREC_ALL_CONFIGS=1) -- and the 26-field MMoE [512, 256];
+    vocabularies shrunk (they do not change the program)."""
     from mmlrec_b200 import synthetic
     from oracle.mmlrec_oracle import OracleTrainer
     from helpers import oracle_columns

@@ -15,7 +15,12 @@ import torch
 from helpers import GOLDEN, oracle_columns, rel_err
 from plan_emulator import EmulatedPlan
 
-SHAPES = json.load(open(os.path.join(GOLDEN, "shipped_configs.json")))
+ALL_SHAPES = json.load(open(os.path.join(GOLDEN, "shipped_configs.json")))
+# The default run keeps the CPU suite short (this file is the slowest part of it): the odd-width AliExpress input (msl, 15
+# models) and MovieLens MTMSL (2 domains x 2 labels); MMLREC_ALL_CONFIGS=1 runs all 12 -- they all pass, log under
+# profiles/cpu_sweep_all_configs_r02.txt.
+_DEFAULT = ("configs_msl/config_AE.json", "configs_mtmsl/config_movielens.json")
+SHAPES = [s for s in ALL_SHAPES if os.environ.get("MMLREC_ALL_CONFIGS") or s["config"] in _DEFAULT]
 V = 50
 
 
@@ -25,7 +30,7 @@ def _rows(shape):
     return 64 if shape["model_config"].get("dnn_use_bn", False) else 16
 
 
-def _build(shape, name, precision):
+def _build(shape, name, precision, domain_mask=False):
     from mmlrec_b200.model import get_model_class
     from mmlrec_b200.model.utils import DenseFeat, SparseFeat
     sparse = [f"s{j}" for j in range(shape["n_sparse"])]
@@ -38,7 +43,7 @@ def _build(shape, name, precision):
            "model_config": dict(copy.deepcopy(shape["model_config"]), model_name=name),
            "optim_config": copy.deepcopy(shape["optim_config"]),
            "training_config": {"train_batch_size": 4096, "test_batch_size": 4096, "epochs": 1}, "save_config": {},
-           "b200_config": {"precision": precision, "cuda_graph": False}}
+           "b200_config": {"precision": precision, "cuda_graph": False, "domain_mask": domain_mask}}
     emb = cfg["model_config"].get("emb", 8)
     fields = [(n, "sparse", V) for n in sparse] + [(n, "dense", 0) for n in dense]
     cols = [SparseFeat(n, V, emb) for n in sparse] + [DenseFeat(n, 1) for n in dense]
@@ -134,3 +139,75 @@ def test_every_model_on_every_shipped_config_shape(shape):
                 want_eval = tr.forward(torch.from_numpy(X), training=False)
             assert rel_err(plan.heads.pred, want_eval) < 1e-5, (name, "eval-mode forward")
     assert ran >= 20, "most models must build on every shipped config shape"
+
+
+def test_wide_heads_with_cumulative_or_shared_biases():
+    """MLP and ESCM on the KuaiRec MTL shape ([512, 256]: a 256-wide last layer): their heads (cumulative / shared biases)
+    exist only in the one-launch head kernel, instantiated up to 256 columns for <= 4 tasks; the emulation refuses what the
+    launcher would refuse."""
+    shape = next(s for s in ALL_SHAPES if s["config"] == "configs_mtl/config_kuairec.json")
+    for name in ("mlp", "escm"):
+        model, cfg, fields = _build(shape, name, "fp32")
+        tr, sd = _oracle(model, cfg, fields, name)
+        X, y = _batch(shape, model)
+        want_pred, want_loss, want = tr.loss_and_grads(torch.from_numpy(X), torch.from_numpy(y))
+        plan = EmulatedPlan(model, _rows(shape), "fp32")
+        model.load_state_dict(sd, strict=True)
+        plan.build()
+        assert max(h.h.width for h in plan.heads.heads) == 256 and plan.heads.flags & 6
+        pred, loss = plan.forward_backward(X, y)
+        assert rel_err(pred, want_pred.detach()) < 1e-5, name
+        got = torch.cat([plan.grad(p).flatten() for n, p in model.named_parameters()
+                         if getattr(p, "_mm_kind", "") == "dense" and want.get(n) is not None])
+        ref = torch.cat([want[n].flatten() for n, p in model.named_parameters()
+                         if getattr(p, "_mm_kind", "") == "dense" and want.get(n) is not None])
+        assert rel_err(got, ref) < 1e-5, name
+
+
+# default: mtmsl (2 domains x 2 labels); MMLREC_ALL_CONFIGS=1: all seven multi-scenario configs
+MASKED = [s for s in ALL_SHAPES if s["model_config"].get("task_name") in ("msl", "mtmsl")
+          and (os.environ.get("MMLREC_ALL_CONFIGS") or s["config"] == "configs_mtmsl/config_movielens.json")]
+
+
+@pytest.mark.parametrize("shape", MASKED, ids=[s["config"] for s in MASKED])
+def test_scenario_mask_mode_on_every_multi_scenario_config(shape):
+    """``b200_config["domain_mask"]`` -- the scenario semantics the reference's classes and loop are written for (predictions x
+    the sample's mask entry, mmoe.py:101-106; BCE weighted by it, basemodel.py:273-282) -- for every model on msl / mtmsl
+    configs, fp32 program against the oracle.  ESMM / ESCM (their forward ignores the mask) and STAR with BatchNorm
+    (DomainBatchNorm) say so at construction."""
+    from mmlrec_b200.model import REFERENCE_NAMES
+    from mmlrec_b200.model.utils import get_mask
+    ran = 0
+    for name in REFERENCE_NAMES:
+        if name == "pcg":
+            continue
+        try:
+            model, cfg, fields = _build(shape, name, "fp32", domain_mask=True)
+        except ValueError:
+            continue
+        except NotImplementedError as e:
+            assert name in ("esmm", "escm") or (name == "star" and shape["model_config"].get("dnn_use_bn", False)), (name, str(e))
+            continue
+        tr, sd = _oracle(model, cfg, fields, name)
+        X, y = _batch(shape, model)
+        D = shape["num_domains"]
+        X[:, shape["mask_pos"]] = np.random.default_rng(2).choice(shape["mask_values"], len(X))
+        mask = get_mask(list(X[:, shape["mask_pos"]]), shape["mask_values"], D).float()
+        want_pred, want_loss, want = tr.loss_and_grads(torch.from_numpy(X), torch.from_numpy(y), mask)
+        plan = EmulatedPlan(model, _rows(shape), "fp32")
+        model.load_state_dict(sd, strict=True)
+        plan.build()
+        pred, loss = plan.forward_backward(X, y, mask.numpy())
+        assert rel_err(pred, want_pred.detach()) < 1e-5, name
+        assert abs(float(loss[-1]) - float(want_loss)) <= 1e-5 * abs(float(want_loss)), name
+        if cfg["model_config"].get("dnn_use_bn", False):
+            ran += 1
+            continue   # (gradients behind BatchNorm at 64 rows: pinned by the unmasked sweep and the goldens)
+        got_all, want_all = [], []
+        for pname, prm in model.named_parameters():
+            if getattr(prm, "_mm_kind", "") == "dense" and want.get(pname) is not None:
+                got_all.append(plan.grad(prm).flatten())
+                want_all.append(want[pname].flatten())
+        assert rel_err(torch.cat(got_all), torch.cat(want_all)) < 1e-5, name
+        ran += 1
+    assert ran >= 9
